@@ -1,0 +1,224 @@
+// ampmodem.cuh -- ampmodem_create(0.8, LIQUID_AMPMODEM_DSB, 0) demodulator (Liquid.chs:452-469, liquid
+// src/modem/src/ampmodem.c, 2019 redesign).  Two candidate DSB/carrier-present demodulators exist in liquid's
+// history (confidence LOW); both are implemented, CSDR_OPT_AMPMODEM_PLL selects:
+//   peak detector : |x| -> 51-tap real dc-blocking FIR -> / mod_index              (fully time-parallel)
+//   carrier PLL   : 51-tap low-pass isolates the carrier, an NCO/PLL tracks it, the 25-sample-delayed signal is
+//                   mixed down, Re()/mod_index, then the same dc-blocking FIR      (PLL loop: one thread per lane)
+#pragma once
+#include "platform.cuh"
+#ifndef CSDR_EMU
+#include "design.hpp"
+#include <vector>
+#endif
+
+namespace csdr {
+
+constexpr int kAmM = 25;                 // filter semi-length (ampmodem.c: q->m = 25)
+constexpr int kAmTaps = 2 * kAmM + 1;    // 51
+constexpr int kAmHist = kAmTaps - 1;     // 50 samples of history per lane
+
+struct AmParams {
+    int nlanes, n;
+    const float2 *x; long long x_stride;          // input chunk
+    float2 *xh; long long xh_stride;              // [hist 50 | n] copy of the input
+    float2 *x0;                                   // [lanes][n] low-passed (PLL)
+    float *mh; long long mh_stride;               // [hist 50 | n] pre-dc-block real signal
+    float *y; long long y_stride;                 // output
+    const float *h_lp, *h_dc;                     // 51 taps each; h[k] multiplies sample (i - k)
+    const float *sintab;                          // 1024-entry NCO table (pll)
+    unsigned *pll;                                // [lanes][2] theta, d_theta
+    float inv_mod, pll_alpha, pll_beta, out_scale;
+    int use_pll;
+};
+
+// xh[50+i] = x[i]; peak variant also writes mh[50+i] = |x[i]|
+__global__ void k_am_stage_in(const AmParams p)
+{
+    const int lane = blockIdx.y;
+    const float2 *x = p.x + (long long)lane * p.x_stride;
+    float2 *xh = p.xh + (long long)lane * p.xh_stride + kAmHist;
+    float *mh = p.mh + (long long)lane * p.mh_stride + kAmHist;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += gridDim.x * blockDim.x) {
+        float2 v = x[i];
+        if (p.use_pll) xh[i] = v;
+        else mh[i] = hypotf(v.x, v.y);
+    }
+}
+
+// x0[i] = sum_k h_lp[k] * xh[50 + i - k]
+__global__ void k_am_lowpass(const AmParams p)
+{
+    __shared__ float2 tile[256 + kAmHist];
+    __shared__ float h[kAmTaps];
+    const int lane = blockIdx.y;
+    const float2 *xh = p.xh + (long long)lane * p.xh_stride;
+    if (threadIdx.x < kAmTaps) h[threadIdx.x] = p.h_lp[threadIdx.x];
+    for (int base = blockIdx.x * 256; base < p.n; base += gridDim.x * 256) {
+        __syncthreads();
+        for (int j = threadIdx.x; j < 256 + kAmHist; j += blockDim.x)
+            tile[j] = (base + j < p.n + kAmHist) ? xh[base + j] : cf(0.f, 0.f);
+        __syncthreads();
+        const int i = base + threadIdx.x;
+        if (i < p.n) {
+            float ar = 0.f, ai = 0.f;
+            // oldest sample first (liquid dotprod order)
+            for (int k = kAmTaps - 1; k >= 0; k--) {
+                float2 v = tile[threadIdx.x + kAmHist - k];
+                ar += h[k] * v.x; ai += h[k] * v.y;
+            }
+            p.x0[(long long)lane * p.n + i] = cf(ar, ai);
+        }
+    }
+}
+
+__device__ __forceinline__ unsigned am_constrain(float theta)
+{
+    float pp = (float)((double)theta * 0.159154943091895);
+    float frac = pp - (float)((long long)pp);
+    if (frac < 0.0f) frac = (float)((double)frac + 1.0);
+    float scaled = frac * 4294967296.0f;
+    return scaled >= 4294967296.0f ? 0u : (unsigned)scaled;
+}
+
+// carrier PLL, sequential per lane (ampmodem_demod_dsb_pll_carrier)
+__global__ void k_am_pll(const AmParams p)
+{
+    const int lane = blockIdx.x * blockDim.x + threadIdx.x;
+    if (lane >= p.nlanes) return;
+    const float2 *xh = p.xh + (long long)lane * p.xh_stride;
+    const float2 *x0 = p.x0 + (long long)lane * p.n;
+    float *mh = p.mh + (long long)lane * p.mh_stride + kAmHist;
+    unsigned theta = p.pll[2 * lane], dtheta = p.pll[2 * lane + 1];
+    for (int i = 0; i < p.n; i++) {
+        const unsigned idx = ((theta + (1u << 21)) >> 22) & 0x3ffu;
+        const float s = p.sintab[idx], c = p.sintab[(idx + 256) & 0x3ffu];
+        const float2 a = x0[i], b = xh[kAmHist + i - kAmM];
+        const float v0i = __fsub_rn(__fmul_rn(a.y, c), __fmul_rn(a.x, s));
+        const float v1r = __fadd_rn(__fmul_rn(b.x, c), __fmul_rn(b.y, s));
+        dtheta += am_constrain(__fmul_rn(v0i, p.pll_alpha));
+        theta += am_constrain(__fmul_rn(v0i, p.pll_beta));
+        theta += dtheta;
+        mh[i] = v1r * p.inv_mod;
+    }
+    p.pll[2 * lane] = theta; p.pll[2 * lane + 1] = dtheta;
+}
+
+// y[i] = out_scale * sum_k h_dc[k] * mh[50 + i - k]
+__global__ void k_am_dcfir(const AmParams p)
+{
+    __shared__ float tile[256 + kAmHist];
+    __shared__ float h[kAmTaps];
+    const int lane = blockIdx.y;
+    const float *mh = p.mh + (long long)lane * p.mh_stride;
+    float *y = p.y + (long long)lane * p.y_stride;
+    if (threadIdx.x < kAmTaps) h[threadIdx.x] = p.h_dc[threadIdx.x];
+    for (int base = blockIdx.x * 256; base < p.n; base += gridDim.x * 256) {
+        __syncthreads();
+        for (int j = threadIdx.x; j < 256 + kAmHist; j += blockDim.x)
+            tile[j] = (base + j < p.n + kAmHist) ? mh[base + j] : 0.f;
+        __syncthreads();
+        const int i = base + threadIdx.x;
+        if (i < p.n) {
+            float acc = 0.f;
+            for (int k = kAmTaps - 1; k >= 0; k--) acc += h[k] * tile[threadIdx.x + kAmHist - k];
+            y[i] = acc * p.out_scale;
+        }
+    }
+}
+
+// keep the last 50 samples of xh / mh as the next call's history (n >= 50: plain shift; n < 50: via temp)
+__global__ void k_am_tail(const AmParams p, float2 *xtmp, float *mtmp, int phase)
+{
+    const int lane = blockIdx.x;
+    float2 *xh = p.xh + (long long)lane * p.xh_stride;
+    float *mh = p.mh + (long long)lane * p.mh_stride;
+    const int j = threadIdx.x;
+    if (j >= kAmHist) return;
+    if (phase == 0) { xtmp[lane * kAmHist + j] = xh[p.n + j]; mtmp[lane * kAmHist + j] = mh[p.n + j]; }
+    else            { xh[j] = xtmp[lane * kAmHist + j]; mh[j] = mtmp[lane * kAmHist + j]; }
+}
+
+#ifndef CSDR_EMU
+// host-side owner of the AM demodulator state (device resident)
+struct AmDemod {
+    int nlanes = 0; float mod_index = 0.8f; bool use_pll = true;
+    void *d_hlp = nullptr, *d_hdc = nullptr, *d_sintab = nullptr, *d_pll = nullptr;
+    void *d_xh = nullptr, *d_mh = nullptr, *d_x0 = nullptr, *d_xtmp = nullptr, *d_mtmp = nullptr;
+    size_t cap_n = 0;
+    unsigned long long launches = 0;
+    unsigned long long take_launches() { unsigned long long l = launches; launches = 0; return l; }
+
+    static void ck(cudaError_t e, const char *what) { if (e != cudaSuccess) throw std::runtime_error(std::string(what) + ": " + cudaGetErrorString(e)); }
+    ~AmDemod() { for (void *p : {d_hlp, d_hdc, d_sintab, d_pll, d_xh, d_mh, d_x0, d_xtmp, d_mtmp}) if (p) cudaFree(p); }
+
+    void init(cudaStream_t st, int lanes, float mod, bool pll)
+    {
+        nlanes = lanes; mod_index = mod; use_pll = pll;
+        // firfilt_rrrf_create_dc_blocker(25, 20 dB): h = delta[m] - w/sum(w), Kaiser w
+        std::vector<float> hdc(kAmTaps), hlp;
+        double beta = design::kaiser_beta(20.0f), sum = 0.0;
+        std::vector<double> w(kAmTaps);
+        for (int i = 0; i < kAmTaps; i++) { w[i] = design::kaiser(i, kAmTaps, beta); sum += w[i]; }
+        for (int i = 0; i < kAmTaps; i++) hdc[i] = (float)(-w[i] / sum);
+        hdc[kAmM] += 1.0f;
+        // firfilt_crcf_create_kaiser(51, 0.01, 40 dB, 0)
+        hlp = design::firdes_kaiser(kAmTaps, 0.01f, 40.0f, 0.0f);
+        std::vector<float> tab(1024);
+        for (int i = 0; i < 1024; i++) tab[i] = sinf((float)(2.0f * design::kPi * (float)i / 1024.0f));
+        ck(cudaMalloc(&d_hlp, kAmTaps * 4), "cudaMalloc"); ck(cudaMalloc(&d_hdc, kAmTaps * 4), "cudaMalloc");
+        ck(cudaMalloc(&d_sintab, 1024 * 4), "cudaMalloc"); ck(cudaMalloc(&d_pll, (size_t)lanes * 8), "cudaMalloc");
+        ck(cudaMalloc(&d_xtmp, (size_t)lanes * kAmHist * 8), "cudaMalloc"); ck(cudaMalloc(&d_mtmp, (size_t)lanes * kAmHist * 4), "cudaMalloc");
+        ck(cudaMemcpyAsync(d_hlp, hlp.data(), kAmTaps * 4, cudaMemcpyHostToDevice, st), "copy");
+        ck(cudaMemcpyAsync(d_hdc, hdc.data(), kAmTaps * 4, cudaMemcpyHostToDevice, st), "copy");
+        ck(cudaMemcpyAsync(d_sintab, tab.data(), 1024 * 4, cudaMemcpyHostToDevice, st), "copy");
+        ck(cudaMemsetAsync(d_pll, 0, (size_t)lanes * 8, st), "memset");
+        ck(cudaStreamSynchronize(st), "sync");
+        ensure(st, 1024);
+    }
+    void ensure(cudaStream_t st, size_t n)
+    {
+        if (n <= cap_n) return;
+        size_t want = n + n / 4;
+        void *nx = nullptr, *nm = nullptr, *n0 = nullptr;
+        ck(cudaMalloc(&nx, (size_t)nlanes * (want + kAmHist) * 8), "cudaMalloc");
+        ck(cudaMalloc(&nm, (size_t)nlanes * (want + kAmHist) * 4), "cudaMalloc");
+        ck(cudaMalloc(&n0, (size_t)nlanes * want * 8), "cudaMalloc");
+        ck(cudaMemsetAsync(nx, 0, (size_t)nlanes * (want + kAmHist) * 8, st), "memset");
+        ck(cudaMemsetAsync(nm, 0, (size_t)nlanes * (want + kAmHist) * 4, st), "memset");
+        if (d_xh) {
+            // carry the histories over (they sit at the head of each lane's buffer)
+            ck(cudaMemcpy2DAsync(nx, (want + kAmHist) * 8, d_xh, (cap_n + kAmHist) * 8, kAmHist * 8, nlanes, cudaMemcpyDeviceToDevice, st), "copy");
+            ck(cudaMemcpy2DAsync(nm, (want + kAmHist) * 4, d_mh, (cap_n + kAmHist) * 4, kAmHist * 4, nlanes, cudaMemcpyDeviceToDevice, st), "copy");
+            ck(cudaStreamSynchronize(st), "sync");
+            cudaFree(d_xh); cudaFree(d_mh); cudaFree(d_x0);
+        }
+        d_xh = nx; d_mh = nm; d_x0 = n0; cap_n = want;
+    }
+    void run(cudaStream_t st, const float2 *x, long long x_stride, float *y, long long y_stride, int n)
+    {
+        if (n <= 0) return;
+        ensure(st, (size_t)n);
+        AmParams p{};
+        p.nlanes = nlanes; p.n = n; p.x = x; p.x_stride = x_stride;
+        p.xh = (float2 *)d_xh; p.xh_stride = (long long)(cap_n + kAmHist);
+        p.x0 = (float2 *)d_x0; p.mh = (float *)d_mh; p.mh_stride = (long long)(cap_n + kAmHist);
+        p.y = y; p.y_stride = y_stride; p.h_lp = (const float *)d_hlp; p.h_dc = (const float *)d_hdc;
+        p.sintab = (const float *)d_sintab; p.pll = (unsigned *)d_pll;
+        p.inv_mod = 1.0f / mod_index; p.pll_alpha = 0.001f; p.pll_beta = sqrtf(0.001f);
+        p.use_pll = use_pll ? 1 : 0;
+        p.out_scale = use_pll ? 1.0f : 1.0f / mod_index;
+        int gx = std::max(1, std::min((n + 255) / 256, 2048));
+        k_am_stage_in<<<dim3(gx, nlanes), 256, 0, st>>>(p); launches++;
+        if (use_pll) {
+            k_am_lowpass<<<dim3(gx, nlanes), 256, 0, st>>>(p); launches++;
+            k_am_pll<<<(nlanes + 31) / 32, 32, 0, st>>>(p); launches++;
+        }
+        k_am_dcfir<<<dim3(gx, nlanes), 256, 0, st>>>(p); launches++;
+        k_am_tail<<<nlanes, 64, 0, st>>>(p, (float2 *)d_xtmp, (float *)d_mtmp, 0); launches++;
+        k_am_tail<<<nlanes, 64, 0, st>>>(p, (float2 *)d_xtmp, (float *)d_mtmp, 1); launches++;
+        ck(cudaGetLastError(), "ampmodem launch");
+    }
+};
+#endif
+
+}  // namespace csdr

@@ -1,0 +1,372 @@
+// backend.cuh -- the sequential-state blocks that run at the decimated / per-channel rate:
+//     iirfilt_crcf dc blocker   (Liquid.chs:575-589, liquid iirfilt.c "normal" form: v0 = x - a1 v1, y = v0 - v1)
+//     agc_crcf + squelch gate   (Liquid.chs:693-717, liquid agc.c; Haskell zeroes y unless status == SIGNALHI)
+//     freqdem                   (Liquid.chs:324-334, liquid freqdem.c)
+// for `nlanes` independent sample sequences (streams or channelizer channels) of n samples each.
+//
+// Parallelisation over TIME (the reference is one sequential loop per stream):
+//   * dc blocker: a linear recurrence.  k_dc_partial reduces every G-sample group to its zero-state response,
+//     k_dc_scan composes the groups (one CTA per lane, fp64) and yields the exact filter state at every group
+//     boundary; consumers restart the float32 recurrence from those states.
+//   * AGC: a contractive non-linear loop (perturbations decay like (1-alpha)^(k/2)).  Every L-sample segment is
+//     run speculatively by its own thread after a W-sample warm-up that starts from an equilibrium guess;
+//     k_backend_verify compares each segment's start state with its predecessor's end state (gain and level
+//     to 1e-6 relative, squelch mode/timer and discriminator history exactly/1e-6) and k_backend_fixup re-runs,
+//     in stream order, exactly those segments whose speculation missed.  The result equals the sequential
+//     loop to within the stated tolerance in all cases; only the speed depends on the signal.
+#pragma once
+#include "platform.cuh"
+
+namespace csdr {
+
+enum { SQ_UNKNOWN = 0, SQ_ENABLED, SQ_RISE, SQ_SIGNALHI, SQ_FALL, SQ_SIGNALLO, SQ_TIMEOUT, SQ_DISABLED };
+
+struct LaneState {                 // carried across calls, one per lane
+    float dc_re, dc_im;            // dc blocker v1
+    float g, y2p;                  // agc gain, filtered output energy
+    int mode; unsigned timer;      // squelch FSM
+    float fm_re, fm_im;            // freqdem r_prime
+};
+struct SegState { float g, y2p; int mode; unsigned timer; float fm_re, fm_im; };
+
+struct BackendParams {
+    const float2 *in; long long in_lane_stride;
+    void *out; long long out_lane_stride;      // float (demod != 0) or float2 elements
+    int n, nlanes;
+    int L, W, G, nseg, ngrp;
+    int has_dc, has_agc, demod;                // demod: 0 none (cf32 out), 1 fm (float out)
+    float dc_a1;                               // a[1] = -1 + alpha_dc
+    float alpha; double one_minus_alpha; float neg_half_alpha;
+    float g_thr;                               // rssi > threshold  <=>  g < g_thr  (bisected on the host)
+    unsigned timeout; float fm_ref;
+    int squelch_enabled;
+    int gate;                                  // 1: zero the output unless squelch status == SIGNALHI (Liquid.chs:700-704)
+    LaneState *lane;
+    SegState *seg_start, *seg_end;             // [nlanes][nseg]
+    const double2 *dcV;                        // [nlanes][ngrp+1] dc state at group boundaries
+    unsigned *flags;                           // [nlanes][nseg]
+    unsigned *counts;                          // [nlanes] speculation misses
+    unsigned long long *fixups;                // total segments re-run (diagnostic)
+};
+
+// ------------------------------------------------------------------------------------------ dc blocker
+struct DcParams {
+    const float2 *in; long long in_lane_stride;
+    float2 *out; long long out_lane_stride;
+    int n, nlanes, G, ngrp;
+    double c;                                  // 1 - alpha  (= -a1)
+    float a1;
+    double2 *P;                                // [nlanes][ngrp] zero-state group responses
+    double2 *V;                                // [nlanes][ngrp+1] state at group boundaries
+    LaneState *lane;
+};
+
+__global__ void k_dc_partial(const DcParams p)
+{
+    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long long)p.nlanes * p.ngrp) return;
+    int lane = (int)(t / p.ngrp), j = (int)(t - (long long)lane * p.ngrp);
+    const float2 *x = p.in + (long long)lane * p.in_lane_stride;
+    int i0 = j * p.G, i1 = min(i0 + p.G, p.n);
+    double ar = 0.0, ai = 0.0;
+    for (int i = i0; i < i1; i++) {
+        float2 v = x[i];
+        ar = ar * p.c + (double)v.x;
+        ai = ai * p.c + (double)v.y;
+    }
+    // a short last group is completed with zero input so that every group advances the state by c^G
+    for (int i = i1; i < i0 + p.G; i++) { ar *= p.c; ai *= p.c; }
+    p.P[t] = make_double2(ar, ai);
+}
+
+// one CTA per lane: V[j+1] = c^G V[j] + P[j], V[0] = carried state.  Chunked Hillis-Steele scan in fp64.
+__global__ void k_dc_scan(const DcParams p)
+{
+    const int lane = blockIdx.x, T = blockDim.x, t = threadIdx.x;
+    __shared__ double sr[1024], si[1024];
+    const double2 *P = p.P + (long long)lane * p.ngrp;
+    double2 *V = p.V + (long long)lane * (p.ngrp + 1);
+    const int q = (p.ngrp + T - 1) / T;                  // groups per thread
+    double A = 1.0;                                      // c^G
+    for (int i = 0; i < p.G; i++) A *= p.c;
+    const int j0 = min(t * q, p.ngrp), j1 = min(j0 + q, p.ngrp);
+    double ar = 0.0, ai = 0.0;
+    for (int j = j0; j < j1; j++) { ar = ar * A + P[j].x; ai = ai * A + P[j].y; }
+    double Aq = 1.0;                                     // A^q (a thread that owns fewer groups is padded with zeros)
+    for (int i = 0; i < q; i++) Aq *= A;
+    for (int j = j1; j < j0 + q; j++) { ar *= A; ai *= A; }
+    sr[t] = ar; si[t] = ai;
+    __syncthreads();
+    double f = Aq;
+    for (int d = 1; d < T; d <<= 1) {
+        double vr = 0.0, vi = 0.0;
+        if (t >= d) { vr = sr[t - d] * f; vi = si[t - d] * f; }
+        __syncthreads();
+        if (t >= d) { sr[t] += vr; si[t] += vi; }
+        __syncthreads();
+        f *= f;
+    }
+    // exclusive prefix for this thread + decayed carried state
+    double v0r = (double)p.lane[lane].dc_re, v0i = (double)p.lane[lane].dc_im;
+    double pw = 1.0;                                     // Aq^t
+    { double b = Aq; int e = t; while (e) { if (e & 1) pw *= b; b *= b; e >>= 1; } }
+    double wr = v0r * pw + (t ? sr[t - 1] : 0.0), wi = v0i * pw + (t ? si[t - 1] : 0.0);
+    if (t == 0) V[0] = make_double2(v0r, v0i);
+    for (int j = j0; j < j1; j++) {
+        wr = wr * A + P[j].x; wi = wi * A + P[j].y;
+        V[j + 1] = make_double2(wr, wi);
+    }
+}
+
+// stand-alone dc blocker output (iirfilt_crcf_execute_block): one thread per group restarts the float32
+// recurrence from the exact boundary state.
+__global__ void k_dc_apply(const DcParams p)
+{
+    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long long)p.nlanes * p.ngrp) return;
+    int lane = (int)(t / p.ngrp), j = (int)(t - (long long)lane * p.ngrp);
+    const float2 *x = p.in + (long long)lane * p.in_lane_stride;
+    float2 *y = p.out + (long long)lane * p.out_lane_stride;
+    double2 v = p.V[(long long)lane * (p.ngrp + 1) + j];
+    float v1r = (float)v.x, v1i = (float)v.y;
+    int i0 = j * p.G, i1 = min(i0 + p.G, p.n);
+    for (int i = i0; i < i1; i++) {
+        float2 s = x[i];
+        float v0r = __fsub_rn(s.x, __fmul_rn(p.a1, v1r));
+        float v0i = __fsub_rn(s.y, __fmul_rn(p.a1, v1i));
+        y[i] = cf(__fsub_rn(v0r, v1r), __fsub_rn(v0i, v1i));
+        v1r = v0r; v1i = v0i;
+    }
+}
+
+// store the dc state after the last sample of the chunk into the lane state
+__global__ void k_dc_finish(const DcParams p)
+{
+    int lane = blockIdx.x * blockDim.x + threadIdx.x;
+    if (lane >= p.nlanes) return;
+    // state after n samples: restart from the last full-group boundary
+    int j = p.n / p.G;
+    double2 v = p.V[(long long)lane * (p.ngrp + 1) + j];
+    float v1r = (float)v.x, v1i = (float)v.y;
+    const float2 *x = p.in + (long long)lane * p.in_lane_stride;
+    for (int i = j * p.G; i < p.n; i++) {
+        float2 s = x[i];
+        v1r = __fsub_rn(s.x, __fmul_rn(p.a1, v1r));
+        v1i = __fsub_rn(s.y, __fmul_rn(p.a1, v1i));
+    }
+    p.lane[lane].dc_re = v1r; p.lane[lane].dc_im = v1i;
+}
+
+// ------------------------------------------------------------------------------------------ agc + fm
+struct AgcRun { float g, y2p; int mode; unsigned timer; float fr, fi; };
+
+// one sample of: [dc] -> agc(+squelch gate) -> [freqdem]; returns gated agc output in (yr, yi), fm in *m
+__device__ __forceinline__ void be_step(const BackendParams &p, AgcRun &s, float xr, float xi, float &yr, float &yi,
+                                        float &m)
+{
+    if (p.has_agc) {
+        // AGC(_execute), liquid agc.c
+        yr = __fmul_rn(xr, s.g); yi = __fmul_rn(xi, s.g);
+        float y2 = __fadd_rn(__fmul_rn(yr, yr), __fmul_rn(yi, yi));
+        s.y2p = (float)(p.one_minus_alpha * (double)s.y2p + (double)__fmul_rn(p.alpha, y2));
+        if (s.y2p > 1e-6f) s.g *= expf(p.neg_half_alpha * logf(s.y2p));
+        if (s.g > 1e6f) s.g = 1e6f;
+        if (p.squelch_enabled) {
+            // AGC(_squelch_update_mode)
+            const bool ex = s.g < p.g_thr;
+            switch (s.mode) {
+            case SQ_ENABLED:  s.mode = ex ? SQ_RISE : SQ_ENABLED; break;
+            case SQ_RISE:     s.mode = ex ? SQ_SIGNALHI : SQ_FALL; break;
+            case SQ_SIGNALHI: s.mode = ex ? SQ_SIGNALHI : SQ_FALL; break;
+            case SQ_FALL:     s.mode = ex ? SQ_SIGNALHI : SQ_SIGNALLO; s.timer = p.timeout; break;
+            case SQ_SIGNALLO:
+                s.timer--;
+                if (s.timer == 0) s.mode = SQ_TIMEOUT;
+                else if (ex)      s.mode = SQ_SIGNALHI;
+                break;
+            case SQ_TIMEOUT:  s.mode = SQ_ENABLED; break;
+            default: break;
+            }
+            // Haskell agcExecuteBlock: keep the sample only while SIGNALHI
+            if (p.gate && s.mode != SQ_SIGNALHI) { yr = 0.f; yi = 0.f; }
+        }
+    } else { yr = xr; yi = xi; }
+    if (p.demod == 1) {
+        // freqdem_demodulate: arg(conj(r') r) / (2 pi kf)
+        float re = __fadd_rn(__fmul_rn(s.fr, yr), __fmul_rn(s.fi, yi));
+        float im = __fsub_rn(__fmul_rn(s.fr, yi), __fmul_rn(s.fi, yr));
+        m = atan2f(im, re) * p.fm_ref;
+        s.fr = yr; s.fi = yi;
+    }
+}
+
+__device__ __forceinline__ bool be_close(float a, float b) { return fabsf(a - b) <= 1e-6f * fmaxf(fabsf(a), fabsf(b)); }
+__device__ __forceinline__ bool be_match(const SegState &a, const SegState &b, int has_agc, int demod)
+{
+    bool ok = true;
+    if (has_agc) ok = ok && be_close(a.g, b.g) && be_close(a.y2p, b.y2p) && a.mode == b.mode &&
+                      (a.mode != SQ_SIGNALLO || a.timer == b.timer);
+    if (demod == 1) ok = ok && be_close(a.fm_re, b.fm_re) && be_close(a.fm_im, b.fm_im);
+    return ok;
+}
+
+// run samples [i0, i1) of one lane from state s / dc state (v1r, v1i); emit outputs for i >= emit_from
+__device__ __forceinline__ void be_run(const BackendParams &p, int lane, AgcRun &s, float &v1r, float &v1i, int i0,
+                                       int i1, int emit_from)
+{
+    const float2 *x = p.in + (long long)lane * p.in_lane_stride;
+    float *of = (float *)p.out + (long long)lane * p.out_lane_stride;
+    float2 *oc = (float2 *)p.out + (long long)lane * p.out_lane_stride;
+    for (int i = i0; i < i1; i++) {
+        float2 v = x[i];
+        float xr = v.x, xi = v.y;
+        if (p.has_dc) {
+            float v0r = __fsub_rn(xr, __fmul_rn(p.dc_a1, v1r));
+            float v0i = __fsub_rn(xi, __fmul_rn(p.dc_a1, v1i));
+            xr = __fsub_rn(v0r, v1r); xi = __fsub_rn(v0i, v1i);
+            v1r = v0r; v1i = v0i;
+        }
+        float yr, yi, m = 0.f;
+        be_step(p, s, xr, xi, yr, yi, m);
+        if (i >= emit_from) {
+            if (p.demod == 1) of[i] = m; else oc[i] = cf(yr, yi);
+        }
+    }
+}
+
+__device__ __forceinline__ void be_dc_state(const BackendParams &p, int lane, int i, float &v1r, float &v1i)
+{
+    // i is a multiple of G
+    if (p.has_dc) {
+        double2 v = p.dcV[(long long)lane * (p.ngrp + 1) + i / p.G];
+        v1r = (float)v.x; v1i = (float)v.y;
+    } else { v1r = 0.f; v1i = 0.f; }
+}
+
+__global__ void __launch_bounds__(128) k_backend_spec(const BackendParams p)
+{
+    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long long)p.nlanes * p.nseg) return;
+    const int lane = (int)(t / p.nseg), seg = (int)(t - (long long)lane * p.nseg);
+    const int b0 = seg * p.L, b1 = min(b0 + p.L, p.n);
+    AgcRun s; float v1r, v1i;
+    int w0 = b0 - p.W;
+    const LaneState ls = p.lane[lane];
+    if (w0 <= 0) {
+        // the warm-up reaches the chunk start: run from the true carried state (exact)
+        w0 = 0;
+        s.g = ls.g; s.y2p = ls.y2p; s.mode = ls.mode; s.timer = ls.timer; s.fr = ls.fm_re; s.fi = ls.fm_im;
+    } else {
+        // equilibrium guess: unit output energy for the first samples of the warm-up window
+        const float2 *x = p.in + (long long)lane * p.in_lane_stride;
+        float e = 0.f;
+        for (int i = 0; i < 16; i++) { float2 v = x[w0 + i]; e += v.x * v.x + v.y * v.y; }
+        e *= (1.0f / 16.0f);
+        s.g = (e > 1e-30f) ? rsqrtf(e) : 1e6f;
+        if (s.g > 1e6f) s.g = 1e6f;
+        s.y2p = 1.0f; s.mode = p.squelch_enabled ? SQ_ENABLED : SQ_DISABLED; s.timer = 0; s.fr = 0.f; s.fi = 0.f;
+    }
+    be_dc_state(p, lane, w0, v1r, v1i);
+    be_run(p, lane, s, v1r, v1i, w0, b0, b1);          // warm-up, nothing emitted
+    SegState st; st.g = s.g; st.y2p = s.y2p; st.mode = s.mode; st.timer = s.timer; st.fm_re = s.fr; st.fm_im = s.fi;
+    p.seg_start[t] = st;
+    be_run(p, lane, s, v1r, v1i, b0, b1, b0);
+    st.g = s.g; st.y2p = s.y2p; st.mode = s.mode; st.timer = s.timer; st.fm_re = s.fr; st.fm_im = s.fi;
+    p.seg_end[t] = st;
+}
+
+__global__ void k_backend_verify(const BackendParams p)
+{
+    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long long)p.nlanes * p.nseg) return;
+    const int lane = (int)(t / p.nseg), seg = (int)(t - (long long)lane * p.nseg);
+    unsigned bad = 0;
+    if (seg > 0 && !be_match(p.seg_start[t], p.seg_end[t - 1], p.has_agc, p.demod)) bad = 1;
+    p.flags[t] = bad;
+    if (bad) atomicAdd(&p.counts[lane], 1u);
+}
+
+// one CTA per lane.  Common case (no misses): copy the last segment's end state into the lane state.
+__global__ void k_backend_fixup(const BackendParams p)
+{
+    const int lane = blockIdx.x;
+    __shared__ unsigned s_next;
+    __shared__ int s_cur;
+    SegState *E = p.seg_end + (long long)lane * p.nseg;
+    const SegState *S0 = p.seg_start + (long long)lane * p.nseg;
+    unsigned *flags = p.flags + (long long)lane * p.nseg;
+    if (p.counts[lane] != 0) {
+        if (threadIdx.x == 0) s_cur = 1;
+        __syncthreads();
+        while (true) {
+            // parallel search for the next flagged segment >= s_cur
+            if (threadIdx.x == 0) s_next = 0xffffffffu;
+            __syncthreads();
+            const int cur = s_cur;
+            unsigned best = 0xffffffffu;
+            for (int j = cur + threadIdx.x; j < p.nseg; j += blockDim.x)
+                if (flags[j]) { best = (unsigned)j; break; }
+            if (best != 0xffffffffu) atomicMin(&s_next, best);
+            __syncthreads();
+            const unsigned nxt = s_next;
+            if (nxt == 0xffffffffu) break;
+            if (threadIdx.x == 0) {
+                // re-run segments in stream order from the true predecessor state until speculation re-joins
+                int seg = (int)nxt;
+                unsigned long long redone = 0;
+                while (seg < p.nseg) {
+                    const SegState pe = E[seg - 1];
+                    if (be_match(S0[seg], pe, p.has_agc, p.demod)) { flags[seg] = 0; break; }
+                    AgcRun s; s.g = pe.g; s.y2p = pe.y2p; s.mode = pe.mode; s.timer = pe.timer; s.fr = pe.fm_re; s.fi = pe.fm_im;
+                    float v1r, v1i;
+                    const int b0 = seg * p.L, b1 = min(b0 + p.L, p.n);
+                    be_dc_state(p, lane, b0, v1r, v1i);
+                    be_run(p, lane, s, v1r, v1i, b0, b1, b0);
+                    SegState ne; ne.g = s.g; ne.y2p = s.y2p; ne.mode = s.mode; ne.timer = s.timer; ne.fm_re = s.fr; ne.fm_im = s.fi;
+                    E[seg] = ne; flags[seg] = 0; redone++;
+                    seg++;      // the successor is re-checked against the new end state on the next iteration
+                }
+                s_cur = seg;
+                atomicAdd(p.fixups, redone);
+            }
+            __syncthreads();
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const SegState e = E[p.nseg - 1];
+        LaneState ls = p.lane[lane];
+        ls.g = e.g; ls.y2p = e.y2p; ls.mode = e.mode; ls.timer = e.timer; ls.fm_re = e.fm_re; ls.fm_im = e.fm_im;
+        p.lane[lane] = ls;
+        p.counts[lane] = 0;
+    }
+}
+
+// stand-alone freqdem (freqdem_demodulate_block): fully parallel, r' = previous input sample
+__global__ void k_freqdem(const float2 *__restrict__ r, float *__restrict__ m, long long n, float2 prev, float ref)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long stride = (long long)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        float2 a = (i == 0) ? prev : r[i - 1];
+        float2 b = r[i];
+        float re = __fadd_rn(__fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y));
+        float im = __fsub_rn(__fmul_rn(a.x, b.y), __fmul_rn(a.y, b.x));
+        m[i] = atan2f(im, re) * ref;
+    }
+}
+
+// mix: out[t] = sum over lanes (channel order, left fold -- Trans.hs:119-122)
+__global__ void k_lane_sum(const float *__restrict__ in, long long lane_stride, int nlanes, float *__restrict__ out,
+                           long long n /* floats */)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long stride = (long long)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        float acc = in[i];
+        for (int c = 1; c < nlanes; c++) acc = __fadd_rn(acc, in[(long long)c * lane_stride + i]);
+        out[i] = acc;
+    }
+}
+
+}  // namespace csdr

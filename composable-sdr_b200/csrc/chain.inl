@@ -1,0 +1,309 @@
+// chain.inl -- the fused receive chain (csdr_chain_*), i.e. sdrProcess of apps/SoapySDR.hs:181-283:
+//   offset (mixDown/mixUp)  ->  resampler (msresamp r 60)  ->  dcBlocker  ->  compact  ->
+//   C == 1 : demod                     where demod = (fmDemodulator kf | amDemodulator | id) . agc
+//   C  > 1 : firpfbchChannelizer C -> mux (replicate C demod) [-> mix]
+// `compact` only re-chunks (Trans.hs:58-85): here whole frames of C samples are consumed as they arrive and the
+// < C left-over samples wait in the handle.  Included at the end of csdr_b200.cu.
+
+struct csdr_chain_s {
+    Ctx ctx;
+    csdr_chain_cfg cfg;
+    unsigned C = 1, nstreams = 1, nout = 1;
+    size_t esz = 8;
+    bool has_resamp = false, has_mix = false, has_agc = false;
+    int mix_mode = 0; uint32_t mix_theta = 0, mix_dtheta = 0; int quantize = 1;
+    Frontend fe;
+    Backend be;          // C == 1: dc + agc + fm per stream;  C > 1: agc + fm per channel
+    Backend dcb;         // C > 1: the single wide-band dc blocker
+    Channelizer ch; uint32_t rot_theta = 0, rot_dtheta = 0;
+    AmDemod am;
+    DevBuf xin, r, left, chan, dem, amout, outstage;
+    size_t nleft = 0;
+    std::vector<void *> out_ptrs;
+    unsigned long long fixups_seen = 0, fixups_last = 0;
+    // host-input pipeline
+    cudaStream_t copy_stream = nullptr; cudaEvent_t ev_copy[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+    DevBuf xpipe[2];
+
+    csdr_chain_s(const csdr_chain_cfg &c) : ctx(c.device), cfg(c) {}
+    ~csdr_chain_s()
+    {
+        cudaSetDevice(ctx.device);
+        if (ctx.stream) cudaStreamSynchronize(ctx.stream);
+        if (copy_stream) { cudaStreamSynchronize(copy_stream); cudaStreamDestroy(copy_stream); }
+        for (auto e : ev_copy) if (e) cudaEventDestroy(e);
+        for (auto e : ev_done) if (e) cudaEventDestroy(e);
+    }
+};
+
+namespace {
+
+void chain_init(csdr_chain_s *q)
+{
+    const csdr_chain_cfg &c = q->cfg;
+    if (!(c.samplerate > 0)) throw CudaError{"chain: samplerate must be positive"};
+    q->C = c.channels > 1 ? c.channels : 1;
+    q->nstreams = c.nstreams > 1 ? c.nstreams : 1;
+    if (q->C > 1 && q->nstreams > 1) throw CudaError{"chain: channelizer with nstreams > 1 is not implemented"};
+    if (c.demod < 0 || c.demod > 2) throw CudaError{"chain: unknown demodulator"};
+    if (c.demod == CSDR_DEMOD_NBFM && !(c.kf > 0.0f)) throw CudaError{"chain: DeNBFM needs kf > 0"};
+    q->nout = (q->C > 1 && !c.mix) ? q->C : 1;
+    q->esz = c.demod ? sizeof(float) : sizeof(float2);
+    q->has_agc = c.agc_thresh_db != 0.0f;
+    q->quantize = g_options[CSDR_OPT_VCO_DIRECT] ? 0 : 1;
+    // f = 2*pi*offset/samplerate :: Float, f > 0 -> mixDown f, f < 0 -> mixUp (-f)   (SoapySDR.hs:200-205)
+    float f = (float)(2.0f * (float)design::kPi * (float)c.offset_hz / (float)c.samplerate);
+    if (f != 0.0f) {
+        q->has_mix = true;
+        q->mix_mode = f > 0.0f ? 1 : 2;
+        q->mix_dtheta = design::nco_constrain(f > 0.0f ? f : -f);
+    }
+    if (c.bandwidth_hz != 0.0) {
+        q->has_resamp = true;
+        q->fe.init(q->ctx, (float)(c.bandwidth_hz / c.samplerate), 60.0f, (int)q->nstreams);
+        q->fe.mix_mode = q->mix_mode; q->fe.theta0 = 0; q->fe.dtheta = q->mix_dtheta; q->fe.quantize = q->quantize;
+    }
+    const int am_lanes = (int)(q->C > 1 ? q->C : q->nstreams);
+    if (q->C == 1) {
+        q->be.has_dc = true; q->be.dc_alpha = 0.0005f;
+        q->be.has_agc = q->has_agc; q->be.agc_thr = c.agc_thresh_db;
+        q->be.demod = (c.demod == CSDR_DEMOD_NBFM) ? 1 : 0; q->be.kf = c.kf > 0 ? c.kf : 0.3f;
+        q->be.init(q->ctx, (int)q->nstreams);
+    } else {
+        q->dcb.has_dc = true; q->dcb.dc_alpha = 0.0005f;
+        q->dcb.init(q->ctx, 1);
+        q->ch.init(q->ctx, q->C, 7, 80.0f);
+        q->rot_dtheta = design::nco_constrain(design::firpfbch_rotation(q->C));
+        q->be.has_dc = false;
+        q->be.has_agc = q->has_agc; q->be.agc_thr = c.agc_thresh_db;
+        q->be.demod = (c.demod == CSDR_DEMOD_NBFM) ? 1 : 0; q->be.kf = c.kf > 0 ? c.kf : 0.3f;
+        q->be.init(q->ctx, (int)q->C);
+        q->left.ensure(sizeof(float2) * q->C);
+    }
+    if (c.demod == CSDR_DEMOD_AM) q->am.init(q->ctx.stream, am_lanes, 0.8f, g_options[CSDR_OPT_AMPMODEM_PLL] != 0);
+    q->out_ptrs.resize((size_t)q->nstreams * q->nout);
+    CK(cudaStreamCreateWithFlags(&q->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; i++) {
+        CK(cudaEventCreateWithFlags(&q->ev_copy[i], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&q->ev_done[i], cudaEventDisableTiming));
+    }
+}
+
+size_t chain_max_out(const csdr_chain_s *q, size_t nx)
+{
+    size_t n = q->has_resamp ? (size_t)q->fe.max_out((long long)nx) : nx;
+    if (q->C > 1) n = (n + q->nleft) / q->C + 1;
+    return n;
+}
+
+// Run the chain on device-resident input xd ([nstreams][nx] at x_stride).  Results go to q->out_ptrs[] (device
+// pointers, one per stream/output, capacity out_cap samples).  Returns samples per output.
+size_t chain_run_device(csdr_chain_s *q, const float2 *xd, size_t nx, size_t x_stride, size_t out_cap)
+{
+    const Ctx &c = q->ctx;
+    const unsigned S = q->nstreams;
+    // ---- offset mix + resampler
+    const float2 *r = xd; long long r_stride = (long long)x_stride; long long nr = (long long)nx;
+    if (q->has_resamp) {
+        r_stride = q->fe.max_out((long long)nx);
+        q->r.ensure(sizeof(float2) * (size_t)r_stride * S);
+        nr = q->fe.run(c, xd, (long long)nx, (long long)x_stride, q->r.as<float2>(), r_stride);
+        r = q->r.as<float2>();
+    } else if (q->has_mix && nx) {
+        r_stride = (long long)nx;
+        q->r.ensure(sizeof(float2) * nx * S);
+        for (unsigned s = 0; s < S; s++)
+            launch(k_nco_mix, dim3(grid_for((long long)nx, 256, c.sms)), dim3(256), 0, c.stream, xd + (size_t)s * x_stride,
+                   q->r.as<float2>() + (size_t)s * nx, (long long)nx, q->mix_theta, q->mix_dtheta, q->quantize,
+                   q->mix_mode == 2 ? 1 : 0);
+        q->mix_theta += (uint32_t)nx * q->mix_dtheta;
+        r = q->r.as<float2>();
+    }
+    if (nr > 0x7fffffffLL) throw CudaError{"chain: chunk too large"};
+
+    if (q->C == 1) {
+        if ((size_t)nr > out_cap) throw CudaError{"chain: output capacity too small"};
+        if (nr == 0) return 0;
+        // out_ptrs are per-stream device buffers; the back end wants one base + stride
+        const bool contiguous = (S == 1);
+        if (q->cfg.demod == CSDR_DEMOD_AM) {
+            // agc (cf32) -> ampmodem
+            q->dem.ensure(sizeof(float2) * (size_t)nr * S);
+            q->be.run(c, r, r_stride, q->dem.p, nr, (int)nr);
+            float *dst = contiguous ? (float *)q->out_ptrs[0] : (q->amout.ensure(sizeof(float) * (size_t)nr * S), q->amout.as<float>());
+            q->am.run(c.stream, q->dem.as<float2>(), nr, dst, nr, (int)nr);
+            g_launches.fetch_add(q->am.take_launches());
+            if (!contiguous)
+                for (unsigned s = 0; s < S; s++)
+                    CK(cudaMemcpyAsync(q->out_ptrs[s], dst + (size_t)s * nr, sizeof(float) * nr, cudaMemcpyDeviceToDevice, c.stream));
+        } else {
+            void *dst = q->out_ptrs[0];
+            if (!contiguous) { q->dem.ensure(q->esz * (size_t)nr * S); dst = q->dem.p; }
+            q->be.run(c, r, r_stride, dst, nr, (int)nr);
+            if (!contiguous)
+                for (unsigned s = 0; s < S; s++)
+                    CK(cudaMemcpyAsync(q->out_ptrs[s], (char *)dst + (size_t)s * nr * q->esz, q->esz * nr, cudaMemcpyDeviceToDevice, c.stream));
+        }
+        return (size_t)nr;
+    }
+
+    // ---- channelizer path: wide-band dc blocker (in place on r if it is our scratch, else into scratch)
+    const unsigned C = q->C;
+    float2 *w = nullptr;
+    if (nr) {
+        if (r == q->r.as<float2>()) w = q->r.as<float2>();
+        else { q->r.ensure(sizeof(float2) * (size_t)nr); w = q->r.as<float2>(); }
+        q->dcb.run_dc_only(c, r, 0, w, 0, (int)nr);
+    }
+    const size_t tot = q->nleft + (size_t)nr, nf = tot / C, used = nf * C;
+    if (nf > out_cap) throw CudaError{"chain: output capacity too small"};
+    if (nf) {
+        // pre-rotate [left-over | new] into the channelizer input (Liquid.chs:847)
+        float2 *slot = q->ch.input_slot(c, used);
+        if (q->nleft) {
+            launch(k_nco_mix, dim3(1), dim3(256), 0, c.stream, (const float2 *)q->left.as<float2>(), slot, (long long)q->nleft,
+                   q->rot_theta, q->rot_dtheta, q->quantize, 0);
+            q->rot_theta += (uint32_t)q->nleft * q->rot_dtheta;
+        }
+        const size_t take = used - q->nleft;
+        launch(k_nco_mix, dim3(grid_for((long long)take, 256, c.sms)), dim3(256), 0, c.stream, (const float2 *)w, slot + q->nleft,
+               (long long)take, q->rot_theta, q->rot_dtheta, q->quantize, 0);
+        q->rot_theta += (uint32_t)take * q->rot_dtheta;
+        q->chan.ensure(sizeof(float2) * used);
+        q->ch.run(c, (int)nf, q->chan.as<float2>(), (long long)nf);
+        // remaining < C samples wait for the next call
+        const size_t rem = tot - used;
+        if (rem) CK(cudaMemcpyAsync(q->left.p, w + take, sizeof(float2) * rem, cudaMemcpyDeviceToDevice, c.stream));
+        q->nleft = rem;
+        // per-channel agc -> demod
+        void *dem = nullptr;
+        if (q->cfg.demod == CSDR_DEMOD_AM) {
+            q->dem.ensure(sizeof(float2) * used);
+            q->be.run(c, q->chan.as<float2>(), (long long)nf, q->dem.p, (long long)nf, (int)nf);
+            q->amout.ensure(sizeof(float) * used);
+            q->am.run(c.stream, q->dem.as<float2>(), (long long)nf, q->amout.as<float>(), (long long)nf, (int)nf);
+            g_launches.fetch_add(q->am.take_launches());
+            dem = q->amout.p;
+        } else {
+            q->dem.ensure(q->esz * used);
+            q->be.run(c, q->chan.as<float2>(), (long long)nf, q->dem.p, (long long)nf, (int)nf);
+            dem = q->dem.p;
+        }
+        if (q->cfg.mix) {
+            // mix = foldl1 (zipWith (+)) over channels 1..C (Trans.hs:119-122); cf32 is summed as 2 floats
+            const long long nfl = (long long)nf * (long long)(q->esz / sizeof(float));
+            launch(k_lane_sum, dim3(grid_for(nfl, 256, c.sms)), dim3(256), 0, c.stream, (const float *)dem, nfl, (int)C,
+                   (float *)q->out_ptrs[0], nfl);
+        } else {
+            for (unsigned ch = 0; ch < C; ch++)
+                CK(cudaMemcpyAsync(q->out_ptrs[ch], (char *)dem + (size_t)ch * nf * q->esz, q->esz * nf, cudaMemcpyDeviceToDevice, c.stream));
+        }
+    } else if (nr) {
+        // not even one frame yet: append to the left-over buffer
+        CK(cudaMemcpyAsync(q->left.as<float2>() + q->nleft, w, sizeof(float2) * (size_t)nr, cudaMemcpyDeviceToDevice, c.stream));
+        q->nleft = tot;
+    }
+    return nf;
+}
+
+}  // namespace
+
+extern "C" {
+
+csdr_chain csdr_chain_create(const csdr_chain_cfg *cfg)
+{
+    API_BEGIN
+    if (!cfg) throw CudaError{"chain: null configuration"};
+    std::unique_ptr<csdr_chain_s> q(new csdr_chain_s(*cfg));
+    chain_init(q.get());
+    q->ctx.sync();
+    return q.release();
+    API_END(nullptr)
+}
+int csdr_chain_destroy(csdr_chain q) { delete q; return 0; }
+unsigned csdr_chain_num_outputs(csdr_chain q) { return q->nout; }
+size_t csdr_chain_out_elem_size(csdr_chain q) { return q->esz; }
+size_t csdr_chain_max_output(csdr_chain q, size_t nx) { return chain_max_out(q, nx); }
+void *csdr_chain_cuda_stream(csdr_chain q) { return (void *)q->ctx.stream; }
+void csdr_chain_print(csdr_chain q)
+{
+    const csdr_chain_cfg &c = q->cfg;
+    printf("csdr_b200 chain: sr %.1f offset %.1f bw %.1f demod %d kf %.3f agc %.1f dB channels %u mix %d streams %u\n",
+           c.samplerate, c.offset_hz, c.bandwidth_hz, c.demod, c.kf, c.agc_thresh_db, q->C, c.mix, q->nstreams);
+    if (q->has_mix) printf("  offset nco [phase: 0x%.8x rad, freq: 0x%.8x rad/sample] %s\n", q->mix_theta, q->mix_dtheta, q->mix_mode == 1 ? "down" : "up");
+    if (q->has_resamp) {
+        const auto &ms = q->fe.ms;
+        printf("  msresamp rate %.10f: %u half-band stages (m =", ms.rate, ms.S);
+        for (unsigned s = 0; s < ms.S; s++) printf(" %u", ms.st[s].m);
+        printf("), arbitrary %.10f step 0x%08x, tile %d c-samples, smem %zu B\n", ms.rate_arb, ms.step, q->fe.geo.base.Tc, q->fe.geo.smem_bytes);
+    }
+    if (q->C > 1) printf("  firpfbch %u channels, rotation freq word 0x%.8x\n", q->C, q->rot_dtheta);
+}
+
+int csdr_chain_process(csdr_chain q, const csdr_cf32 *x, size_t nx, size_t x_stride, void *const *outs, size_t out_cap,
+                       size_t *n_out)
+{
+    if (n_out) *n_out = 0;
+    API_BEGIN
+    q->ctx.use();
+    const Ctx &c = q->ctx;
+    const unsigned S = q->nstreams;
+    const size_t nptr = (size_t)S * q->nout;
+    if (S == 1) x_stride = nx;
+    // classify outputs; host outputs are produced into device staging and copied back at the end
+    bool any_host_out = false;
+    for (size_t i = 0; i < nptr; i++) if (!is_device_ptr(outs[i])) any_host_out = true;
+    const size_t cap_each = std::min(out_cap, chain_max_out(q, nx));
+    if (any_host_out) {
+        q->outstage.ensure(cap_each * q->esz * nptr);
+        for (size_t i = 0; i < nptr; i++) q->out_ptrs[i] = (char *)q->outstage.p + i * cap_each * q->esz;
+    } else {
+        for (size_t i = 0; i < nptr; i++) q->out_ptrs[i] = outs[i];
+    }
+    size_t n = 0;
+    if (nx == 0 || is_device_ptr(x)) {
+        n = chain_run_device(q, (const float2 *)x, nx, x_stride, any_host_out ? cap_each : out_cap);
+    } else {
+        // host input: one asynchronous copy per stream into contiguous device staging
+        q->xin.ensure(sizeof(float2) * nx * S);
+        CK(cudaMemcpy2DAsync(q->xin.p, nx * sizeof(float2), x, x_stride * sizeof(float2), nx * sizeof(float2), S,
+                             cudaMemcpyHostToDevice, c.stream));
+        n = chain_run_device(q, q->xin.as<float2>(), nx, nx, any_host_out ? cap_each : out_cap);
+    }
+    if (any_host_out) {
+        for (size_t i = 0; i < nptr; i++)
+            if (n) CK(cudaMemcpyAsync(outs[i], q->out_ptrs[i], n * q->esz, is_device_ptr(outs[i]) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, c.stream));
+        c.sync();
+    }
+    if (n_out) *n_out = n;
+    return 0;
+    API_END(-1)
+}
+
+int csdr_chain_seek(csdr_chain q, uint64_t n_prior)
+{
+    API_BEGIN
+    if (q->C > 1) throw CudaError{"chain: seek with a channelizer is not implemented"};
+    if (q->has_resamp) q->fe.cursor = fe_seek(q->fe.geo, n_prior);
+    else q->mix_theta = (uint32_t)n_prior * q->mix_dtheta;
+    return 0;
+    API_END(-1)
+}
+size_t csdr_chain_warmup_len(csdr_chain q)
+{
+    // front-end FIR history + dc blocker settling (0.9995^k < 1e-9 after ~41.5k post-resample samples) + AGC
+    double r = q->has_resamp ? (double)q->fe.ms.rate : 1.0;
+    size_t w = (size_t)(q->has_resamp ? q->fe.geo.hcap : 0) + (size_t)std::ceil(45000.0 / r);
+    return w;
+}
+uint64_t csdr_chain_agc_fixups(csdr_chain q)
+{
+    API_BEGIN
+    unsigned long long v = q->be.read_fixups(q->ctx);
+    unsigned long long d = v - q->fixups_seen;
+    q->fixups_seen = v;
+    return d;
+    API_END(0)
+}
+
+}  // extern "C"

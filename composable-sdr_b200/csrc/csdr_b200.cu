@@ -1,0 +1,689 @@
+// csdr_b200.cu -- host side of libcsdr_b200.so: handles, device-resident stream state, kernel launches and the
+// C ABI declared in include/csdr_b200.h.  CUDA runtime only (no torch, no other library on the data path).
+#include "../../include/csdr_b200.h"
+
+#include "platform.cuh"
+#include "design.hpp"
+#include "frontend.cuh"
+#include "frontend_plan.hpp"
+#include "backend.cuh"
+#include "pfb.cuh"
+#include <stdexcept>
+#include <string>
+#include "ampmodem.cuh"
+
+#include <atomic>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+using namespace csdr;
+
+// ------------------------------------------------------------------------------------------ library state
+namespace {
+
+thread_local std::string t_err;
+std::atomic<unsigned long long> g_launches{0};
+int g_options[8] = {0, 1, 0, 512, 384, 0, 0, 0};
+
+void set_err(const std::string &s) { t_err = s; }
+void clear_err() { t_err.clear(); }
+
+struct CudaError { std::string msg; };
+#define CK(call)                                                                                      \
+    do {                                                                                              \
+        cudaError_t e_ = (call);                                                                      \
+        if (e_ != cudaSuccess)                                                                        \
+            throw CudaError{std::string(#call) + ": " + cudaGetErrorString(e_)};                      \
+    } while (0)
+
+template <class... Args, class... Act>
+void launch(void (*k)(Args...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Act &&...a)
+{
+    k<<<grid, block, smem, st>>>(std::forward<Act>(a)...);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    CK(cudaGetLastError());
+}
+
+struct DevBuf {
+    void *p = nullptr; size_t cap = 0;
+    ~DevBuf() { if (p) cudaFree(p); }
+    DevBuf() = default;
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+    void ensure(size_t bytes)
+    {
+        if (bytes <= cap) return;
+        if (p) { CK(cudaFree(p)); p = nullptr; cap = 0; }
+        size_t want = bytes + bytes / 8 + 256;
+        CK(cudaMalloc(&p, want));
+        cap = want;
+    }
+    void ensure_zero(size_t bytes, cudaStream_t st)
+    {
+        if (bytes <= cap) return;
+        ensure(bytes);
+        CK(cudaMemsetAsync(p, 0, cap, st));
+    }
+    template <class T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+bool is_device_ptr(const void *p)
+{
+    if (!p) return false;
+    cudaPointerAttributes a;
+    cudaError_t e = cudaPointerGetAttributes(&a, p);
+    if (e != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+// Every handle owns a stream on one device.
+struct Ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int sms = 148;
+    Ctx(int dev)
+    {
+        int n = 0;
+        cudaError_t e = cudaGetDeviceCount(&n);
+        if (e != cudaSuccess || n == 0) throw CudaError{"no CUDA device available (libcsdr_b200 has no CPU fallback)"};
+        if (dev < 0) CK(cudaGetDevice(&dev));
+        device = dev;
+        CK(cudaSetDevice(device));
+        CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+        CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    }
+    ~Ctx() { if (stream) { cudaSetDevice(device); cudaStreamSynchronize(stream); cudaStreamDestroy(stream); } }
+    void use() const { CK(cudaSetDevice(device)); }
+    void sync() const { CK(cudaStreamSynchronize(stream)); }
+};
+
+// Input/output staging for the liquid-compatible block calls: host pointers are copied through device scratch.
+struct Staging {
+    DevBuf in, out;
+    const void *to_dev(const Ctx &c, const void *p, size_t bytes)
+    {
+        if (bytes == 0 || is_device_ptr(p)) return p;
+        in.ensure(bytes);
+        CK(cudaMemcpyAsync(in.p, p, bytes, cudaMemcpyHostToDevice, c.stream));
+        return in.p;
+    }
+    void *out_dev(void *p, size_t bytes)
+    {
+        if (bytes == 0 || is_device_ptr(p)) return p;
+        out.ensure(bytes);
+        return out.p;
+    }
+    void finish(const Ctx &c, void *user, void *dev, size_t bytes)
+    {
+        if (bytes && user != dev) CK(cudaMemcpyAsync(user, dev, bytes, cudaMemcpyDeviceToHost, c.stream));
+        c.sync();
+    }
+};
+
+int grid_for(long long n, int block, int sms, int per_sm = 8)
+{
+    long long g = (n + block - 1) / block;
+    long long cap = (long long)sms * per_sm;
+    return (int)std::max<long long>(1, std::min(g, cap));
+}
+
+// ---------------------------------------------------------------------------------- front end (mix + msresamp)
+struct Frontend {
+    design::MsresampPlan ms;
+    FrontendGeometry geo;
+    int nstreams = 1;
+    DevBuf hist[2]; int cur = 0;
+    DevBuf bank;
+    FrontendCursor cursor;
+    int mix_mode = 0; uint32_t theta0 = 0, dtheta = 0; int quantize = 1;
+
+    void init(const Ctx &c, float rate, float As, int streams)
+    {
+        ms = design::plan_msresamp(rate, As, g_options[CSDR_OPT_RESAMP_FC_OLD] != 0);
+        int Tc = 464;
+        if (ms.S != 3) {
+            // aim for ~4096 input samples per tile, c-count multiple of 8
+            int t = 4096 >> ms.S; t = std::max(32, std::min(2048, t));
+            Tc = (t + 7) / 8 * 8;
+        }
+        geo = plan_frontend(ms, Tc);
+        if (!geo.error.empty()) throw CudaError{geo.error};
+        nstreams = streams;
+        size_t hb = (size_t)geo.hcap * sizeof(float2) * nstreams;
+        for (auto &h : hist) { h.ensure(hb); CK(cudaMemsetAsync(h.p, 0, h.cap, c.stream)); }
+        bank.ensure(ms.bank.size() * sizeof(float));
+        CK(cudaMemcpyAsync(bank.p, ms.bank.data(), ms.bank.size() * sizeof(float), cudaMemcpyHostToDevice, c.stream));
+        CK(cudaFuncSetAttribute(k_frontend, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)geo.smem_bytes));
+        c.sync();
+    }
+    long long max_out(long long nx) const
+    {
+        // pushes <= nx/2^S + 1, each push emits at most ceil(2^24/step) outputs
+        double pushes = (double)(nx >> ms.S) + 1.0;
+        return (long long)std::ceil(pushes * 16777216.0 / (double)ms.step) + 4;
+    }
+    // x: device, nstreams x nx at x_stride; y: device, y_stride.  Returns outputs per stream.
+    long long run(const Ctx &c, const float2 *x, long long nx, long long x_stride, float2 *y, long long y_stride)
+    {
+        FrontendParams p = geo.base;
+        long long ny = fe_prepare_call(geo, cursor, nx, p);
+        p.x = x; p.hist = hist[cur].as<float2>(); p.y = y; p.hcap = geo.hcap;
+        p.x_stride = x_stride; p.y_stride = y_stride;
+        p.mix_mode = mix_mode; p.theta0 = theta0; p.dtheta = dtheta; p.quantize = quantize;
+        p.bank = bank.as<float>();
+        if (p.ntiles > 0) {
+            int gx = std::min(p.ntiles, std::max(1, c.sms * 3 / std::max(1, std::min(nstreams, c.sms * 3))));
+            launch(k_frontend, dim3(gx, nstreams), dim3(256), geo.smem_bytes, c.stream, p);
+        }
+        if (nx > 0) {
+            launch(k_hist_update, dim3((geo.hcap + 255) / 256, nstreams), dim3(256), 0, c.stream,
+                   (const float2 *)hist[cur].as<float2>(), hist[cur ^ 1].as<float2>(), x, x_stride, nx, geo.hcap);
+            cur ^= 1;
+        }
+        return ny;
+    }
+};
+
+// ---------------------------------------------------------------------------------- back end (dc, agc, fm)
+struct Backend {
+    int nlanes = 1;
+    bool has_dc = false, has_agc = false; int demod = 0;
+    float dc_alpha = 0.0005f;
+    float agc_bw = 0.1f, agc_thr = 0.f; unsigned agc_timeout = 1000; bool squelch = true, gate = true;
+    float kf = 0.3f;
+    int L = 512, W = 384, G = 128;
+    DevBuf lane, P, V, ss, se, flags, counts, fixups;
+    unsigned long long last_fixups = 0;
+
+    void init(const Ctx &c, int lanes, float g0 = 1000.0f, int mode0 = SQ_ENABLED)
+    {
+        nlanes = lanes;
+        L = std::max(64, g_options[CSDR_OPT_AGC_SEGMENT]); W = std::max(16, g_options[CSDR_OPT_AGC_WARMUP]);
+        G = 128;
+        while (L % G || W % G) G /= 2;
+        if (!has_agc) { W = (demod == 1) ? G : 0; if (W == 0) W = 0; }
+        std::vector<LaneState> ls(nlanes);
+        for (auto &l : ls) { l.dc_re = l.dc_im = 0; l.g = g0; l.y2p = 1.0f; l.mode = mode0; l.timer = 0; l.fm_re = l.fm_im = 0; }
+        lane.ensure(sizeof(LaneState) * nlanes);
+        CK(cudaMemcpyAsync(lane.p, ls.data(), sizeof(LaneState) * nlanes, cudaMemcpyHostToDevice, c.stream));
+        counts.ensure(sizeof(unsigned) * nlanes); CK(cudaMemsetAsync(counts.p, 0, counts.cap, c.stream));
+        fixups.ensure(sizeof(unsigned long long)); CK(cudaMemsetAsync(fixups.p, 0, fixups.cap, c.stream));
+        c.sync();
+    }
+    DcParams dc_params(const float2 *in, long long in_stride, float2 *out, long long out_stride, int n, int ngrp)
+    {
+        DcParams d{};
+        d.in = in; d.in_lane_stride = in_stride; d.out = out; d.out_lane_stride = out_stride;
+        d.n = n; d.nlanes = nlanes; d.G = G; d.ngrp = ngrp;
+        d.a1 = -1.0f + dc_alpha; d.c = -(double)d.a1;
+        d.P = P.as<double2>(); d.V = V.as<double2>(); d.lane = lane.as<LaneState>();
+        return d;
+    }
+    void dc_prepare(const Ctx &c, const DcParams &d)
+    {
+        long long items = (long long)nlanes * d.ngrp;
+        launch(k_dc_partial, dim3((unsigned)((items + 127) / 128)), dim3(128), 0, c.stream, d);
+        launch(k_dc_scan, dim3(nlanes), dim3(1024), 0, c.stream, d);
+        launch(k_dc_finish, dim3((nlanes + 63) / 64), dim3(64), 0, c.stream, d);
+    }
+    // dc blocker only, out may alias in
+    void run_dc_only(const Ctx &c, const float2 *in, long long in_stride, float2 *out, long long out_stride, int n)
+    {
+        if (n <= 0) return;
+        int ngrp = (n + G - 1) / G;
+        P.ensure(sizeof(double2) * (size_t)nlanes * ngrp);
+        V.ensure(sizeof(double2) * (size_t)nlanes * (ngrp + 1));
+        DcParams d = dc_params(in, in_stride, out, out_stride, n, ngrp);
+        dc_prepare(c, d);
+        long long items = (long long)nlanes * ngrp;
+        launch(k_dc_apply, dim3((unsigned)((items + 127) / 128)), dim3(128), 0, c.stream, d);
+    }
+    // [dc] -> [agc+gate] -> [fm]; out: float (demod) or float2
+    void run(const Ctx &c, const float2 *in, long long in_stride, void *out, long long out_stride, int n)
+    {
+        if (n <= 0) return;
+        int ngrp = (n + G - 1) / G, nseg = (n + L - 1) / L;
+        size_t segs = (size_t)nlanes * nseg;
+        ss.ensure(sizeof(SegState) * segs); se.ensure(sizeof(SegState) * segs); flags.ensure(sizeof(unsigned) * segs);
+        if (has_dc) {
+            P.ensure(sizeof(double2) * (size_t)nlanes * ngrp);
+            V.ensure(sizeof(double2) * (size_t)nlanes * (ngrp + 1));
+            DcParams d = dc_params(in, in_stride, nullptr, 0, n, ngrp);
+            dc_prepare(c, d);
+        }
+        BackendParams b{};
+        b.in = in; b.in_lane_stride = in_stride; b.out = out; b.out_lane_stride = out_stride;
+        b.n = n; b.nlanes = nlanes; b.L = L; b.W = W; b.G = G; b.nseg = nseg; b.ngrp = ngrp;
+        b.has_dc = has_dc; b.has_agc = has_agc; b.demod = demod;
+        b.dc_a1 = -1.0f + dc_alpha;
+        b.alpha = agc_bw; b.one_minus_alpha = 1.0 - (double)agc_bw; b.neg_half_alpha = -0.5f * agc_bw;
+        b.g_thr = design::agc_gain_threshold(agc_thr); b.timeout = agc_timeout;
+        b.fm_ref = (float)(1.0f / (2 * design::kPi * kf));
+        b.squelch_enabled = squelch ? 1 : 0; b.gate = gate ? 1 : 0;
+        b.lane = lane.as<LaneState>(); b.seg_start = ss.as<SegState>(); b.seg_end = se.as<SegState>();
+        b.dcV = V.as<double2>(); b.flags = flags.as<unsigned>(); b.counts = counts.as<unsigned>();
+        b.fixups = fixups.as<unsigned long long>();
+        unsigned gb = (unsigned)((segs + 127) / 128);
+        launch(k_backend_spec, dim3(gb), dim3(128), 0, c.stream, b);
+        launch(k_backend_verify, dim3(gb), dim3(128), 0, c.stream, b);
+        launch(k_backend_fixup, dim3(nlanes), dim3(128), 0, c.stream, b);
+    }
+    unsigned long long read_fixups(const Ctx &c)
+    {
+        unsigned long long v = 0;
+        CK(cudaMemcpyAsync(&v, fixups.p, sizeof(v), cudaMemcpyDeviceToHost, c.stream));
+        c.sync();
+        return v;
+    }
+    LaneState read_lane(const Ctx &c, int i)
+    {
+        LaneState l;
+        CK(cudaMemcpyAsync(&l, lane.as<LaneState>() + i, sizeof(l), cudaMemcpyDeviceToHost, c.stream));
+        c.sync();
+        return l;
+    }
+    void write_lane(const Ctx &c, int i, const LaneState &l)
+    {
+        CK(cudaMemcpyAsync(lane.as<LaneState>() + i, &l, sizeof(l), cudaMemcpyHostToDevice, c.stream));
+        c.sync();
+    }
+};
+
+// ---------------------------------------------------------------------------------- channelizer
+struct Channelizer {
+    unsigned M = 0, m = 0, P = 0; float As = 0;
+    std::vector<float> h;
+    DevBuf hd, tw, xr[2]; int cur = 0;       // xr: [(P-1)*M history | new samples], ping-pong for the history
+    int log2M = -1, F = 1;
+    size_t smem = 0;
+
+    void init(const Ctx &c, unsigned M_, unsigned m_, float As_)
+    {
+        M = M_; m = m_; As = As_; P = 2 * m;
+        h = design::design_firpfbch(M, m, As);
+        hd.ensure(h.size() * sizeof(float));
+        CK(cudaMemcpyAsync(hd.p, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice, c.stream));
+        std::vector<float2> t(M);
+        for (unsigned i = 0; i < M; i++) {
+            t[i].x = (float)std::cos(-2.0 * design::kPi * (double)i / (double)M);
+            t[i].y = (float)std::sin(-2.0 * design::kPi * (double)i / (double)M);
+        }
+        tw.ensure(M * sizeof(float2));
+        CK(cudaMemcpyAsync(tw.p, t.data(), M * sizeof(float2), cudaMemcpyHostToDevice, c.stream));
+        log2M = -1;
+        if (M > 1 && (M & (M - 1)) == 0) { log2M = 0; while ((1u << log2M) < M) log2M++; }
+        int elems = 8192;                              // F*M complex samples per CTA (64 KB)
+        F = std::max(1, elems / (int)M);
+        if (F > 256) F = 256;
+        smem = (size_t)F * M * sizeof(float2) * (log2M >= 0 ? 1 : 2);
+        if (smem > 200 * 1024) throw CudaError{"firpfbch: channel count too large for one CTA tile"};
+        CK(cudaFuncSetAttribute(k_pfb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        size_t hb = (size_t)(P - 1) * M * sizeof(float2);
+        for (auto &b : xr) { b.ensure(hb); CK(cudaMemsetAsync(b.p, 0, b.cap, c.stream)); }
+        c.sync();
+    }
+    size_t hist_samples() const { return (size_t)(P - 1) * M; }
+    // where the caller must place n = nf*M pre-rotated samples before calling run()
+    float2 *input_slot(const Ctx &c, size_t n)
+    {
+        size_t need = (hist_samples() + n) * sizeof(float2);
+        if (need > xr[cur].cap) {
+            // grow while keeping the carried history
+            DevBuf nb; nb.ensure(need);
+            CK(cudaMemcpyAsync(nb.p, xr[cur].p, hist_samples() * sizeof(float2), cudaMemcpyDeviceToDevice, c.stream));
+            c.sync();
+            std::swap(xr[cur].p, nb.p); std::swap(xr[cur].cap, nb.cap);
+        }
+        return xr[cur].as<float2>() + hist_samples();
+    }
+    void run(const Ctx &c, int nf, float2 *y, long long y_stride)
+    {
+        if (nf <= 0) return;
+        PfbParams p{};
+        p.xr = xr[cur].as<float2>(); p.y = y; p.y_stride = y_stride;
+        p.M = (int)M; p.P = (int)P; p.nf = nf; p.F = F; p.log2M = log2M;
+        p.h = hd.as<float>(); p.tw = tw.as<float2>();
+        launch(k_pfb, dim3((nf + F - 1) / F), dim3(256), smem, c.stream, p);
+        int H = (int)hist_samples();
+        xr[cur ^ 1].ensure((size_t)H * sizeof(float2));
+        launch(k_copy_tail, dim3((H + 255) / 256), dim3(256), 0, c.stream, (const float2 *)xr[cur].as<float2>(),
+               xr[cur ^ 1].as<float2>(), (long long)nf * M, H);
+        cur ^= 1;
+    }
+};
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------ handles
+struct csdr_nco_s {
+    Ctx ctx; Staging st; int type; uint32_t theta = 0, dtheta = 0;
+    csdr_nco_s(int t) : ctx(-1), type(t) {}
+    int quantize() const { return (type == 1 && g_options[CSDR_OPT_VCO_DIRECT]) ? 0 : 1; }
+};
+struct csdr_msresamp_s { Ctx ctx; Staging st; Frontend fe; csdr_msresamp_s() : ctx(-1) {} };
+struct csdr_iirfilt_s { Ctx ctx; Staging st; Backend be; float alpha; csdr_iirfilt_s() : ctx(-1) {} };
+struct csdr_firpfbch_s { Ctx ctx; Staging st; Channelizer ch; DevBuf tmp; csdr_firpfbch_s() : ctx(-1) {} };
+struct csdr_agc_s {
+    Ctx ctx; Staging st; Backend be; bool started = false;
+    float bw = 1e-2f, g = 1.0f, thr = 0.0f; unsigned timeout = 100; int mode = SQ_DISABLED;
+    csdr_agc_s() : ctx(-1) {}
+};
+struct csdr_freqdem_s { Ctx ctx; Staging st; float kf, ref; float2 prev; csdr_freqdem_s() : ctx(-1) { prev.x = prev.y = 0; } };
+struct csdr_ampmodem_s { Ctx ctx; Staging st; AmDemod am; csdr_ampmodem_s() : ctx(-1) {} };
+
+#define API_BEGIN clear_err(); try {
+#define API_END(ret_fail)                                                    \
+    } catch (const CudaError &e) { set_err(e.msg); return ret_fail; }        \
+      catch (const std::exception &e) { set_err(e.what()); return ret_fail; }
+#define API_END_VOID                                                         \
+    } catch (const CudaError &e) { set_err(e.msg); }                         \
+      catch (const std::exception &e) { set_err(e.what()); }
+
+extern "C" {
+
+const char *csdr_version(void) { return "csdr_b200 0.1 (sm_100a)"; }
+const char *csdr_last_error(void) { return t_err.c_str(); }
+int csdr_device_count(void) { int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; } return n; }
+int csdr_set_device(int device)
+{
+    API_BEGIN CK(cudaSetDevice(device)); return 0; API_END(-1)
+}
+void *csdr_host_alloc(size_t bytes)
+{
+    API_BEGIN void *p = nullptr; CK(cudaHostAlloc(&p, bytes, cudaHostAllocDefault)); return p; API_END(nullptr)
+}
+void csdr_host_free(void *p) { if (p) cudaFreeHost(p); }
+uint64_t csdr_kernel_launches(void) { return g_launches.load(); }
+int csdr_synchronize(void) { API_BEGIN CK(cudaDeviceSynchronize()); return 0; API_END(-1) }
+int csdr_set_option(int opt, int value) { if (opt < 0 || opt >= 8) return -1; g_options[opt] = value; return 0; }
+int csdr_get_option(int opt) { return (opt < 0 || opt >= 8) ? -1 : g_options[opt]; }
+
+// ---------------------------------------------------------------- nco_crcf
+csdr_nco csdr_nco_crcf_create(int type)
+{
+    API_BEGIN return new csdr_nco_s(type); API_END(nullptr)
+}
+void csdr_nco_crcf_destroy(csdr_nco q) { delete q; }
+void csdr_nco_crcf_print(csdr_nco q)
+{
+    if (q) printf("nco [phase: 0x%.8x rad, freq: 0x%.8x rad/sample]\n", q->theta, q->dtheta);
+}
+void csdr_nco_crcf_set_frequency(csdr_nco q, float dtheta) { q->dtheta = design::nco_constrain(dtheta); }
+void csdr_nco_crcf_set_phase(csdr_nco q, float theta) { q->theta = design::nco_constrain(theta); }
+uint32_t csdr_nco_crcf_get_phase_word(csdr_nco q) { return q->theta; }
+uint32_t csdr_nco_crcf_get_freq_word(csdr_nco q) { return q->dtheta; }
+static void nco_mix(csdr_nco q, const csdr_cf32 *x, csdr_cf32 *y, unsigned n, int up)
+{
+    API_BEGIN
+    if (!n) return;
+    q->ctx.use();
+    size_t bytes = (size_t)n * sizeof(float2);
+    const float2 *xd = (const float2 *)q->st.to_dev(q->ctx, x, bytes);
+    float2 *yd = (float2 *)q->st.out_dev(y, bytes);
+    launch(k_nco_mix, dim3(grid_for(n, 256, q->ctx.sms)), dim3(256), 0, q->ctx.stream, xd, yd, (long long)n, q->theta,
+           q->dtheta, q->quantize(), up);
+    q->theta += (uint32_t)n * q->dtheta;
+    q->st.finish(q->ctx, y, yd, bytes);
+    API_END_VOID
+}
+void csdr_nco_crcf_mix_block_down(csdr_nco q, const csdr_cf32 *x, csdr_cf32 *y, unsigned n) { nco_mix(q, x, y, n, 0); }
+void csdr_nco_crcf_mix_block_up(csdr_nco q, const csdr_cf32 *x, csdr_cf32 *y, unsigned n) { nco_mix(q, x, y, n, 1); }
+
+// ---------------------------------------------------------------- msresamp_crcf
+csdr_msresamp csdr_msresamp_crcf_create(float r, float As)
+{
+    API_BEGIN
+    if (!(r > 0.0f)) throw CudaError{"msresamp_crcf_create: rate must be positive"};
+    std::unique_ptr<csdr_msresamp_s> q(new csdr_msresamp_s());
+    q->fe.init(q->ctx, r, As, 1);
+    return q.release();
+    API_END(nullptr)
+}
+void csdr_msresamp_crcf_destroy(csdr_msresamp q) { delete q; }
+float csdr_msresamp_crcf_get_rate(csdr_msresamp q) { return q->fe.ms.rate; }
+void csdr_msresamp_crcf_print(csdr_msresamp q)
+{
+    const auto &ms = q->fe.ms;
+    printf("multi-stage resampler (csdr_b200)\n  composite rate      : %12.10f\n", ms.rate);
+    printf("  type                : %s\n", ms.interp ? "interp" : "decim");
+    printf("  num halfband stages : %u (rate 2^-%u)\n", ms.S, ms.S);
+    for (unsigned s = 0; s < ms.S; s++) printf("    stage[%u] m = %u (%u taps)\n", s, ms.st[s].m, 4 * ms.st[s].m + 1);
+    printf("  arbitrary resampler : rate %12.10f, npfb %u, m %u, step 0x%08x\n", ms.rate_arb, ms.npfb, ms.m_arb, ms.step);
+}
+void csdr_msresamp_crcf_execute(csdr_msresamp q, const csdr_cf32 *x, unsigned nx, csdr_cf32 *y, unsigned *ny)
+{
+    if (ny) *ny = 0;
+    API_BEGIN
+    q->ctx.use();
+    const float2 *xd = (const float2 *)q->st.to_dev(q->ctx, x, (size_t)nx * sizeof(float2));
+    size_t cap = (size_t)q->fe.max_out(nx) * sizeof(float2);
+    float2 *yd = (float2 *)q->st.out_dev(y, cap);
+    long long n = q->fe.run(q->ctx, xd, nx, 0, yd, 0);
+    q->st.finish(q->ctx, y, yd, (size_t)n * sizeof(float2));
+    if (ny) *ny = (unsigned)n;
+    API_END_VOID
+}
+unsigned csdr_msresamp_num_stages(csdr_msresamp q) { return q->fe.ms.S; }
+unsigned csdr_msresamp_stage_m(csdr_msresamp q, unsigned s) { return s < q->fe.ms.S ? q->fe.ms.st[s].m : 0; }
+int csdr_msresamp_stage_taps(csdr_msresamp q, unsigned s, float *h1)
+{
+    if (s >= q->fe.ms.S) return -1;
+    memcpy(h1, q->fe.ms.st[s].h1.data(), q->fe.ms.st[s].h1.size() * sizeof(float));
+    return 0;
+}
+uint32_t csdr_msresamp_resamp_step(csdr_msresamp q) { return q->fe.ms.step; }
+int csdr_msresamp_resamp_bank(csdr_msresamp q, float *bank, unsigned *npfb)
+{
+    if (npfb) *npfb = q->fe.ms.npfb;
+    if (bank) memcpy(bank, q->fe.ms.bank.data(), q->fe.ms.bank.size() * sizeof(float));
+    return 0;
+}
+
+// ---------------------------------------------------------------- iirfilt_crcf dc blocker
+csdr_iirfilt csdr_iirfilt_crcf_create_dc_blocker(float alpha)
+{
+    API_BEGIN
+    std::unique_ptr<csdr_iirfilt_s> q(new csdr_iirfilt_s());
+    q->alpha = alpha;
+    q->be.has_dc = true; q->be.dc_alpha = alpha;
+    q->be.init(q->ctx, 1);
+    return q.release();
+    API_END(nullptr)
+}
+void csdr_iirfilt_crcf_destroy(csdr_iirfilt q) { delete q; }
+void csdr_iirfilt_crcf_print(csdr_iirfilt q)
+{
+    printf("iir filter [normal]:\n  b :   %12.8f %12.8f\n  a :   %12.8f %12.8f\n", 1.0f, -1.0f, 1.0f, -1.0f + q->alpha);
+}
+void csdr_iirfilt_crcf_execute_block(csdr_iirfilt q, const csdr_cf32 *x, unsigned n, csdr_cf32 *y)
+{
+    API_BEGIN
+    if (!n) return;
+    q->ctx.use();
+    size_t bytes = (size_t)n * sizeof(float2);
+    const float2 *xd = (const float2 *)q->st.to_dev(q->ctx, x, bytes);
+    float2 *yd = (float2 *)q->st.out_dev(y, bytes);
+    q->be.run_dc_only(q->ctx, xd, 0, yd, 0, (int)n);
+    q->st.finish(q->ctx, y, yd, bytes);
+    API_END_VOID
+}
+
+// ---------------------------------------------------------------- firpfbch_crcf
+csdr_firpfbch csdr_firpfbch_crcf_create_kaiser(int type, unsigned M, unsigned m, float As)
+{
+    API_BEGIN
+    if (type != 0) throw CudaError{"firpfbch_crcf_create_kaiser: only LIQUID_ANALYZER (0) is implemented"};
+    if (M < 2 || m < 1) throw CudaError{"firpfbch_crcf_create_kaiser: need M >= 2 and m >= 1"};
+    std::unique_ptr<csdr_firpfbch_s> q(new csdr_firpfbch_s());
+    q->ch.init(q->ctx, M, m, As);
+    return q.release();
+    API_END(nullptr)
+}
+void csdr_firpfbch_crcf_destroy(csdr_firpfbch q) { delete q; }
+void csdr_firpfbch_crcf_print(csdr_firpfbch q)
+{
+    printf("firpfbch (analyzer) [%u channels]:\n", q->ch.M);
+    for (size_t i = 0; i < q->ch.h.size(); i++) printf("  h[%3zu] = %12.8f + %12.8f*j\n", i, q->ch.h[i], 0.0f);
+}
+int csdr_firpfbch_taps(csdr_firpfbch q, float *h) { memcpy(h, q->ch.h.data(), q->ch.h.size() * sizeof(float)); return 0; }
+int csdr_firpfbch_execute_block(csdr_firpfbch q, csdr_nco nco, const csdr_cf32 *x, unsigned n, csdr_cf32 *y)
+{
+    API_BEGIN
+    if (!n) return 0;
+    q->ctx.use();
+    const unsigned M = q->ch.M;
+    const unsigned nf = n / M;
+    size_t bytes_in = (size_t)n * sizeof(float2), bytes_out = (size_t)nf * M * sizeof(float2);
+    const float2 *xd = (const float2 *)q->st.to_dev(q->ctx, x, bytes_in);
+    float2 *yd = (float2 *)q->st.out_dev(y, bytes_out);
+    // pre-rotate the whole chunk (Liquid.chs:847), tail included, into the channelizer's input slot
+    float2 *slot = q->ch.input_slot(q->ctx, (size_t)nf * M + M);
+    if (nco) {
+        launch(k_nco_mix, dim3(grid_for(n, 256, q->ctx.sms)), dim3(256), 0, q->ctx.stream, xd, slot, (long long)n,
+               nco->theta, nco->dtheta, nco->quantize(), 0);
+        nco->theta += (uint32_t)n * nco->dtheta;
+    } else {
+        CK(cudaMemcpyAsync(slot, xd, bytes_in, cudaMemcpyDeviceToDevice, q->ctx.stream));
+    }
+    q->ch.run(q->ctx, (int)nf, yd, nf);
+    q->st.finish(q->ctx, y, yd, bytes_out);
+    return 0;
+    API_END(-1)
+}
+void csdr_firpfbch_crcf_analyzer_execute(csdr_firpfbch q, const csdr_cf32 *x, csdr_cf32 *y)
+{
+    csdr_firpfbch_execute_block(q, nullptr, x, q->ch.M, y);
+}
+
+// ---------------------------------------------------------------- agc_crcf
+csdr_agc csdr_agc_crcf_create(void)
+{
+    API_BEGIN return new csdr_agc_s(); API_END(nullptr)
+}
+void csdr_agc_crcf_destroy(csdr_agc q) { delete q; }
+static void agc_push_config(csdr_agc q)
+{
+    // (re)build the device state from the host-side configuration; called lazily before the first execute
+    if (q->started) return;
+    q->be.has_dc = false; q->be.has_agc = true; q->be.demod = 0;
+    q->be.agc_bw = q->bw; q->be.agc_thr = q->thr; q->be.agc_timeout = q->timeout; q->be.squelch = q->mode != SQ_DISABLED;
+    q->be.init(q->ctx, 1, q->g, q->mode);
+    q->started = true;
+}
+static LaneState agc_lane(csdr_agc q) { agc_push_config(q); return q->be.read_lane(q->ctx, 0); }
+void csdr_agc_crcf_print(csdr_agc q)
+{
+    API_BEGIN
+    LaneState l = agc_lane(q);
+    printf("agc [rssi: %12.4f dB, output gain: %.3f dB, bw: %12.4e, locked: no, squelch: %s]:\n",
+           -20 * log10((double)l.g), 0.0, q->bw, q->mode == SQ_DISABLED ? "disabled" : "enabled");
+    API_END_VOID
+}
+void csdr_agc_crcf_set_bandwidth(csdr_agc q, float bt) { q->bw = bt; if (q->started) q->be.agc_bw = bt; }
+void csdr_agc_crcf_set_signal_level(csdr_agc q, float x2)
+{
+    API_BEGIN
+    q->g = 1.0f / x2;
+    if (q->started) { LaneState l = q->be.read_lane(q->ctx, 0); l.g = q->g; l.y2p = 1.0f; q->be.write_lane(q->ctx, 0, l); }
+    API_END_VOID
+}
+void csdr_agc_crcf_squelch_enable(csdr_agc q)
+{
+    API_BEGIN
+    q->mode = SQ_ENABLED;
+    if (q->started) { q->be.squelch = true; LaneState l = q->be.read_lane(q->ctx, 0); l.mode = SQ_ENABLED; q->be.write_lane(q->ctx, 0, l); }
+    API_END_VOID
+}
+void csdr_agc_crcf_squelch_set_threshold(csdr_agc q, float t) { q->thr = t; if (q->started) q->be.agc_thr = t; }
+void csdr_agc_crcf_squelch_set_timeout(csdr_agc q, unsigned t) { q->timeout = t; if (q->started) q->be.agc_timeout = t; }
+float csdr_agc_crcf_get_rssi(csdr_agc q)
+{
+    API_BEGIN LaneState l = agc_lane(q); return (float)(-20 * log10((double)l.g)); API_END(0.0f)
+}
+int csdr_agc_crcf_squelch_get_status(csdr_agc q)
+{
+    API_BEGIN LaneState l = agc_lane(q); return l.mode; API_END(0)
+}
+static int agc_exec(csdr_agc q, const csdr_cf32 *x, unsigned n, csdr_cf32 *y, bool gate)
+{
+    API_BEGIN
+    if (!n) return 0;
+    q->ctx.use();
+    agc_push_config(q);
+    // liquid's agc_crcf_execute_block does not gate; the gate is the Haskell wrapper's (Liquid.chs:700-704)
+    size_t bytes = (size_t)n * sizeof(float2);
+    const float2 *xd = (const float2 *)q->st.to_dev(q->ctx, x, bytes);
+    float2 *yd = (float2 *)q->st.out_dev(y, bytes);
+    q->be.squelch = (q->mode != SQ_DISABLED);
+    q->be.gate = gate;
+    q->be.run(q->ctx, xd, 0, yd, 0, (int)n);
+    q->st.finish(q->ctx, y, yd, bytes);
+    return 0;
+    API_END(-1)
+}
+void csdr_agc_crcf_execute_block(csdr_agc q, const csdr_cf32 *x, unsigned n, csdr_cf32 *y) { agc_exec(q, x, n, y, false); }
+int csdr_agc_squelch_execute_block(csdr_agc q, const csdr_cf32 *x, unsigned n, csdr_cf32 *y) { return agc_exec(q, x, n, y, true); }
+
+// ---------------------------------------------------------------- freqdem
+csdr_freqdem csdr_freqdem_create(float kf)
+{
+    API_BEGIN
+    if (!(kf > 0.0f)) throw CudaError{"freqdem_create: modulation factor must be positive"};
+    std::unique_ptr<csdr_freqdem_s> q(new csdr_freqdem_s());
+    q->kf = kf; q->ref = (float)(1.0f / (2 * design::kPi * kf));
+    return q.release();
+    API_END(nullptr)
+}
+void csdr_freqdem_destroy(csdr_freqdem q) { delete q; }
+void csdr_freqdem_print(csdr_freqdem q) { printf("freqdem:\n    mod. factor :   %8.4f\n", q->kf); }
+void csdr_freqdem_demodulate_block(csdr_freqdem q, const csdr_cf32 *r, unsigned n, float *m)
+{
+    API_BEGIN
+    if (!n) return;
+    q->ctx.use();
+    const float2 *rd = (const float2 *)q->st.to_dev(q->ctx, r, (size_t)n * sizeof(float2));
+    float *md = (float *)q->st.out_dev(m, (size_t)n * sizeof(float));
+    launch(k_freqdem, dim3(grid_for(n, 256, q->ctx.sms)), dim3(256), 0, q->ctx.stream, rd, md, (long long)n, q->prev, q->ref);
+    CK(cudaMemcpyAsync(&q->prev, rd + (n - 1), sizeof(float2), cudaMemcpyDeviceToHost, q->ctx.stream));
+    q->st.finish(q->ctx, m, md, (size_t)n * sizeof(float));
+    API_END_VOID
+}
+
+// ---------------------------------------------------------------- ampmodem
+csdr_ampmodem csdr_ampmodem_create(float mod_index, int type, int suppressed)
+{
+    API_BEGIN
+    if (type != 0 || suppressed != 0) throw CudaError{"ampmodem_create: only DSB with carrier (type 0, suppressed 0) is implemented"};
+    std::unique_ptr<csdr_ampmodem_s> q(new csdr_ampmodem_s());
+    q->am.init(q->ctx.stream, 1, mod_index, g_options[CSDR_OPT_AMPMODEM_PLL] != 0);
+    CK(cudaStreamSynchronize(q->ctx.stream));
+    return q.release();
+    API_END(nullptr)
+}
+void csdr_ampmodem_destroy(csdr_ampmodem q) { delete q; }
+void csdr_ampmodem_print(csdr_ampmodem q)
+{
+    printf("ampmodem:\n    type            :   double side-band\n    supp. carrier   :   no\n    mod. index      :   %-8.4f\n", q->am.mod_index);
+}
+void csdr_ampmodem_demodulate_block(csdr_ampmodem q, const csdr_cf32 *r, unsigned n, float *m)
+{
+    API_BEGIN
+    if (!n) return;
+    q->ctx.use();
+    const float2 *rd = (const float2 *)q->st.to_dev(q->ctx, r, (size_t)n * sizeof(float2));
+    float *md = (float *)q->st.out_dev(m, (size_t)n * sizeof(float));
+    q->am.run(q->ctx.stream, rd, 0, md, 0, (int)n);
+    g_launches.fetch_add(q->am.take_launches());
+    q->st.finish(q->ctx, m, md, (size_t)n * sizeof(float));
+    API_END_VOID
+}
+
+}  // extern "C"
+
+#include "chain.inl"

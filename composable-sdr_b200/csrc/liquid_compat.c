@@ -1,0 +1,63 @@
+/*
+ * liquid_compat.c -- libcsdr_liquid_compat.so: the liquid-dsp symbol names that src/ComposableSDR/Liquid.chs
+ * imports for the receive chain, forwarded to libcsdr_b200.so.  Linking the reference with
+ * `extra-libraries: SoapySDR, csdr_liquid_compat, csdr_b200, liquid` (composable-sdr.cabal:38) resolves these
+ * imports to the GPU blocks with no source change; every other liquid symbol still comes from libliquid.
+ * (Kept in a separate library so that libcsdr_b200.so can be loaded next to a real libliquid for A/B checks.)
+ */
+#include "../../include/csdr_b200.h"
+
+typedef csdr_cf32 cf;
+
+/* Liquid.chs:746-780 */
+void *nco_crcf_create(int type) { return csdr_nco_crcf_create(type); }
+void nco_crcf_destroy(void *q) { csdr_nco_crcf_destroy((csdr_nco)q); }
+void nco_crcf_print(void *q) { csdr_nco_crcf_print((csdr_nco)q); }
+void nco_crcf_set_frequency(void *q, float f) { csdr_nco_crcf_set_frequency((csdr_nco)q, f); }
+void nco_crcf_set_phase(void *q, float p) { csdr_nco_crcf_set_phase((csdr_nco)q, p); }
+void nco_crcf_mix_block_down(void *q, cf *x, cf *y, unsigned n) { csdr_nco_crcf_mix_block_down((csdr_nco)q, x, y, n); }
+void nco_crcf_mix_block_up(void *q, cf *x, cf *y, unsigned n) { csdr_nco_crcf_mix_block_up((csdr_nco)q, x, y, n); }
+
+/* Liquid.chs:58-73 */
+void *msresamp_crcf_create(float r, float As) { return csdr_msresamp_crcf_create(r, As); }
+void msresamp_crcf_destroy(void *q) { csdr_msresamp_crcf_destroy((csdr_msresamp)q); }
+void msresamp_crcf_print(void *q) { csdr_msresamp_crcf_print((csdr_msresamp)q); }
+float msresamp_crcf_get_rate(void *q) { return csdr_msresamp_crcf_get_rate((csdr_msresamp)q); }
+void msresamp_crcf_execute(void *q, cf *x, unsigned nx, cf *y, unsigned *ny) { csdr_msresamp_crcf_execute((csdr_msresamp)q, x, nx, y, ny); }
+
+/* Liquid.chs:550-567 */
+void *iirfilt_crcf_create_dc_blocker(float alpha) { return csdr_iirfilt_crcf_create_dc_blocker(alpha); }
+void iirfilt_crcf_destroy(void *q) { csdr_iirfilt_crcf_destroy((csdr_iirfilt)q); }
+void iirfilt_crcf_print(void *q) { csdr_iirfilt_crcf_print((csdr_iirfilt)q); }
+void iirfilt_crcf_execute_block(void *q, cf *x, unsigned n, cf *y) { csdr_iirfilt_crcf_execute_block((csdr_iirfilt)q, x, n, y); }
+
+/* Liquid.chs:732-742 */
+void *firpfbch_crcf_create_kaiser(int type, unsigned M, unsigned m, float As) { return csdr_firpfbch_crcf_create_kaiser(type, M, m, As); }
+void firpfbch_crcf_destroy(void *q) { csdr_firpfbch_crcf_destroy((csdr_firpfbch)q); }
+void firpfbch_crcf_print(void *q) { csdr_firpfbch_crcf_print((csdr_firpfbch)q); }
+void firpfbch_crcf_analyzer_execute(void *q, cf *x, cf *y) { csdr_firpfbch_crcf_analyzer_execute((csdr_firpfbch)q, x, y); }
+
+/* Liquid.chs:660-691 */
+void *agc_crcf_create(void) { return csdr_agc_crcf_create(); }
+void agc_crcf_destroy(void *q) { csdr_agc_crcf_destroy((csdr_agc)q); }
+void agc_crcf_print(void *q) { csdr_agc_crcf_print((csdr_agc)q); }
+void agc_crcf_set_bandwidth(void *q, float bt) { csdr_agc_crcf_set_bandwidth((csdr_agc)q, bt); }
+void agc_crcf_set_signal_level(void *q, float x2) { csdr_agc_crcf_set_signal_level((csdr_agc)q, x2); }
+void agc_crcf_squelch_enable(void *q) { csdr_agc_crcf_squelch_enable((csdr_agc)q); }
+void agc_crcf_squelch_set_threshold(void *q, float t) { csdr_agc_crcf_squelch_set_threshold((csdr_agc)q, t); }
+void agc_crcf_squelch_set_timeout(void *q, unsigned t) { csdr_agc_crcf_squelch_set_timeout((csdr_agc)q, t); }
+void agc_crcf_execute_block(void *q, cf *x, unsigned n, cf *y) { csdr_agc_crcf_execute_block((csdr_agc)q, x, n, y); }
+float agc_crcf_get_rssi(void *q) { return csdr_agc_crcf_get_rssi((csdr_agc)q); }
+int agc_crcf_squelch_get_status(void *q) { return csdr_agc_crcf_squelch_get_status((csdr_agc)q); }
+
+/* Liquid.chs:305-315 */
+void *freqdem_create(float kf) { return csdr_freqdem_create(kf); }
+void freqdem_destroy(void *q) { csdr_freqdem_destroy((csdr_freqdem)q); }
+void freqdem_print(void *q) { csdr_freqdem_print((csdr_freqdem)q); }
+void freqdem_demodulate_block(void *q, cf *r, unsigned n, float *m) { csdr_freqdem_demodulate_block((csdr_freqdem)q, r, n, m); }
+
+/* Liquid.chs:441-450 */
+void *ampmodem_create(float mod_index, int type, int suppressed) { return csdr_ampmodem_create(mod_index, type, suppressed); }
+void ampmodem_destroy(void *q) { csdr_ampmodem_destroy((csdr_ampmodem)q); }
+void ampmodem_print(void *q) { csdr_ampmodem_print((csdr_ampmodem)q); }
+void ampmodem_demodulate_block(void *q, cf *r, unsigned n, float *m) { csdr_ampmodem_demodulate_block((csdr_ampmodem)q, r, n, m); }

@@ -1,0 +1,84 @@
+"""Synthetic CF32 inputs for the BASELINE configs.  numpy Philox, seed 0x5D2B200; zero-mean by
+construction.  Used by tests, smoke() and bench.py (the bench's device-resident input is generated the same way
+on the GPU with torch, see bench.py)."""
+import numpy as np
+
+SEED = 0x5D2B200
+
+
+def _rng(stream_id):
+    return np.random.Generator(np.random.Philox(key=SEED + int(stream_id)))
+
+
+def noise(n, sigma, stream_id=0):
+    g = _rng(stream_id)
+    return (sigma * (g.standard_normal(n, dtype=np.float32) + 1j * g.standard_normal(n, dtype=np.float32))).astype(np.complex64)
+
+
+def fm_carrier(n, sr, f0, amp=0.5, dev=50e3, f_audio=1e3, keyed=None, k0=0):
+    """FM-modulated tone at f0 Hz; keyed=(on_s, period_s) switches the carrier on/off (exercises the squelch)."""
+    k = np.arange(k0, k0 + n, dtype=np.float64)
+    phase = 2 * np.pi * f0 * k / sr - (dev / f_audio) * np.cos(2 * np.pi * f_audio * k / sr)
+    x = amp * np.exp(1j * phase)
+    if keyed is not None:
+        on, period = keyed
+        x = x * ((k / sr) % period < on)
+    return x.astype(np.complex64)
+
+
+def am_carrier(n, sr, f0, amp=0.5, index=0.8, f_audio=1e3, k0=0):
+    k = np.arange(k0, k0 + n, dtype=np.float64)
+    env = 1.0 + index * np.sin(2 * np.pi * f_audio * k / sr)
+    return (amp / (1 + index) * env * np.exp(2j * np.pi * f0 * k / sr)).astype(np.complex64)
+
+
+def tone(n, sr, f0, amp, k0=0):
+    k = np.arange(k0, k0 + n, dtype=np.float64)
+    return (amp * np.exp(2j * np.pi * f0 * k / sr)).astype(np.complex64)
+
+
+def config1(n, k0=0):
+    """C1/C2 input: SR 2.56 MS/s, FM carrier at +100 kHz, interferer at -400 kHz, noise."""
+    return _cfg12(n, 2.56e6, None, k0)
+
+
+def _cfg12(n, sr, keyed, k0):
+    g = np.random.Generator(np.random.Philox(key=[SEED + 12, int(k0)]))
+    nz = 0.05 * (g.standard_normal(n, dtype=np.float32) + 1j * g.standard_normal(n, dtype=np.float32))
+    x = nz + fm_carrier(n, sr, 1e5, 0.5, 50e3, 1e3, keyed, k0) + tone(n, sr, -4e5, 0.3, k0)
+    return x.astype(np.complex64)
+
+
+def config2(n, k0=0, keyed=(0.05, 0.2)):
+    """C2: as C1 with the carrier keyed 50 ms on / 200 ms period."""
+    return _cfg12(n, 2.56e6, keyed, k0)
+
+
+def config3(n, channels=16, sr=2.56e6):
+    """C3: NBFM carriers at the channel centres f_k = (k - (C-1)/2)/C * SR, every other one keyed."""
+    x = noise(n, 0.01, 3).astype(np.complex64)
+    for k in range(channels):
+        f0 = (k - (channels - 1) / 2.0) / channels * sr
+        keyed = (0.002, 0.008) if (k % 2) else None
+        x = x + fm_carrier(n, sr, f0, 0.05 + 0.01 * k, 0.02 * sr / channels, sr / channels / 40.0, keyed)
+    return x.astype(np.complex64)
+
+
+def config4(n, channels=1024, active=64, sr=1e9):
+    """C4: `active` of `channels` channels carry NBFM with random amplitudes 0.01-0.5."""
+    g = _rng(4)
+    x = noise(n, 0.003, 40)
+    idx = g.choice(channels, size=active, replace=False)
+    amps = g.uniform(0.01, 0.5, size=active)
+    for k, a in zip(idx, amps):
+        f0 = (k - (channels - 1) / 2.0) / channels * sr
+        x = x + fm_carrier(n, sr, f0, a, 0.1 * sr / channels, sr / channels / 50.0)
+    return x.astype(np.complex64)
+
+
+def config5(n, nstreams, sr=10e6):
+    """C5: per stream one AM carrier (index 0.8, 1 kHz tone) at +1 MHz plus noise."""
+    out = np.empty((nstreams, n), np.complex64)
+    for s in range(nstreams):
+        out[s] = noise(n, 0.02, 500 + s) + am_carrier(n, sr, 1e6, 0.4 + 0.002 * s, 0.8, 1e3 + 10 * s)
+    return out

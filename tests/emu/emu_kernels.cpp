@@ -1,0 +1,121 @@
+// emu_kernels.cpp -- TEST-ONLY: runs the real kernel sources (composable-sdr_b200/csrc/*.cuh) under the CPU
+// thread emulator (cuda_emu.h) so tile geometry / state carry can be checked against the oracle without a GPU.
+// Built by tests/emu/build.py with g++ -DCSDR_EMU; never part of libcsdr_b200.so.
+#include "cuda_emu.h"
+#include "frontend.cuh"
+#include "frontend_plan.hpp"
+#include "backend.cuh"
+#include <vector>
+#include <cstdio>
+
+using namespace csdr;
+
+extern "C" {
+
+// mix (mode 0/1/2, freq in radians/sample) + msresamp(rate, As), fed in the given chunk sizes.
+// Returns total outputs written to y (capacity cap), or -1.
+long long emu_frontend(float rate, float As, int mix_mode, float freq, int quantize, int Tc, int nthreads,
+                       const float2 *x, long long n, const long long *chunks, int nchunks, float2 *y, long long cap,
+                       unsigned long long seek)
+{
+    design::MsresampPlan ms = design::plan_msresamp(rate, As);
+    FrontendGeometry g = plan_frontend(ms, Tc);
+    if (!g.error.empty()) { fprintf(stderr, "%s\n", g.error.c_str()); return -1; }
+    std::vector<float2> hist[2];
+    hist[0].assign(g.hcap, make_float2(0, 0)); hist[1] = hist[0];
+    int cur_h = 0;
+    FrontendCursor cur = seek ? fe_seek(g, seek) : FrontendCursor();
+    long long pos = 0, total = 0;
+    for (int c = 0; c < nchunks; c++) {
+        long long nx = chunks[c];
+        if (pos + nx > n) return -1;
+        FrontendParams p = g.base;
+        long long ny = fe_prepare_call(g, cur, nx, p);
+        if (total + ny > cap) return -1;
+        p.x = x + pos; p.hist = hist[cur_h].data(); p.y = y + total; p.hcap = g.hcap;
+        p.x_stride = 0; p.y_stride = 0;
+        p.mix_mode = mix_mode; p.theta0 = 0; p.dtheta = design::nco_constrain(freq); p.quantize = quantize;
+        p.bank = ms.bank.data();
+        if (p.ntiles > 0)
+            csdr_emu::launch(dim3(std::min(p.ntiles, 3)), dim3(nthreads), g.smem_bytes, k_frontend, p);
+        csdr_emu::launch(dim3((g.hcap + 127) / 128), dim3(128), 0, k_hist_update, (const float2 *)hist[cur_h].data(),
+                         hist[cur_h ^ 1].data(), x + pos, 0LL, nx, g.hcap);
+        cur_h ^= 1;
+        pos += nx; total += ny;
+    }
+    return total;
+}
+
+// dc blocker -> agc(+gate) -> fm for nlanes lanes of n samples, fed in chunks; out is float (demod=1) or cf32.
+long long emu_backend(int nlanes, long long lane_stride, int has_dc, float dc_alpha, int has_agc, float thr_db,
+                      int demod, float kf, int L, int W, int G, const float2 *x, long long n, const long long *chunks,
+                      int nchunks, void *out, unsigned long long *fixups_out)
+{
+    std::vector<LaneState> lane(nlanes);
+    for (auto &l : lane) { l.dc_re = l.dc_im = 0; l.g = 1000.0f; l.y2p = 1.0f; l.mode = SQ_ENABLED; l.timer = 0; l.fm_re = l.fm_im = 0; }
+    unsigned long long fixups = 0;
+    long long pos = 0;
+    for (int c = 0; c < nchunks; c++) {
+        int nx = (int)chunks[c];
+        if (nx == 0) continue;
+        int ngrp = (nx + G - 1) / G, nseg = (nx + L - 1) / L;
+        std::vector<double2> P((size_t)nlanes * ngrp), V((size_t)nlanes * (ngrp + 1));
+        std::vector<SegState> ss((size_t)nlanes * nseg), se((size_t)nlanes * nseg);
+        std::vector<unsigned> flags((size_t)nlanes * nseg), counts(nlanes, 0);
+        DcParams d{};
+        d.in = x + pos; d.in_lane_stride = lane_stride; d.n = nx; d.nlanes = nlanes; d.G = G; d.ngrp = ngrp;
+        d.a1 = -1.0f + dc_alpha; d.c = -(double)d.a1; d.P = P.data(); d.V = V.data(); d.lane = lane.data();
+        if (has_dc) {
+            csdr_emu::launch(dim3((nlanes * ngrp + 63) / 64), dim3(64), 0, k_dc_partial, d);
+            csdr_emu::launch(dim3(nlanes), dim3(64), 0, k_dc_scan, d);
+            csdr_emu::launch(dim3((nlanes + 31) / 32), dim3(32), 0, k_dc_finish, d);
+        }
+        BackendParams b{};
+        b.in = x + pos; b.in_lane_stride = lane_stride;
+        b.out = demod ? (void *)((float *)out + pos) : (void *)((float2 *)out + pos); b.out_lane_stride = lane_stride;
+        b.n = nx; b.nlanes = nlanes; b.L = L; b.W = W; b.G = G; b.nseg = nseg; b.ngrp = ngrp;
+        b.has_dc = has_dc; b.has_agc = has_agc; b.demod = demod; b.dc_a1 = d.a1;
+        b.alpha = 0.1f; b.one_minus_alpha = 1.0 - (double)b.alpha; b.neg_half_alpha = -0.5f * b.alpha;
+        b.g_thr = design::agc_gain_threshold(thr_db); b.timeout = 1000; b.fm_ref = (float)(1.0f / (2 * design::kPi * kf));
+        b.squelch_enabled = 1; b.gate = 1;
+        b.lane = lane.data(); b.seg_start = ss.data(); b.seg_end = se.data(); b.dcV = V.data();
+        b.flags = flags.data(); b.counts = counts.data(); b.fixups = &fixups;
+        csdr_emu::launch(dim3((nlanes * nseg + 31) / 32), dim3(32), 0, k_backend_spec, b);
+        csdr_emu::launch(dim3((nlanes * nseg + 31) / 32), dim3(32), 0, k_backend_verify, b);
+        csdr_emu::launch(dim3(nlanes), dim3(32), 0, k_backend_fixup, b);
+        pos += nx;
+    }
+    if (fixups_out) *fixups_out = fixups;
+    return pos;
+}
+
+}  // extern "C"
+
+// ---- product-side filter design (design.hpp), exported so the CPU suite can compare it with the oracle ----
+extern "C" {
+int emu_design_msresamp(float rate, float As, unsigned *S, unsigned *m /*[12]*/, float *h1 /*[12][32]*/, float *rate_arb,
+                        unsigned *step, unsigned *npfb, float *bank /* npfb*14 */)
+{
+    design::MsresampPlan p = design::plan_msresamp(rate, As);
+    *S = p.S; *rate_arb = p.rate_arb; *step = p.step; *npfb = p.npfb;
+    for (unsigned s = 0; s < p.S && s < 12; s++) {
+        m[s] = p.st[s].m;
+        for (size_t u = 0; u < p.st[s].h1.size() && u < 32; u++) h1[s * 32 + u] = p.st[s].h1[u];
+    }
+    if (bank) memcpy(bank, p.bank.data(), p.bank.size() * sizeof(float));
+    return 0;
+}
+int emu_design_firpfbch(unsigned M, unsigned m, float As, float *h) { auto v = design::design_firpfbch(M, m, As); memcpy(h, v.data(), v.size() * 4); return (int)v.size(); }
+unsigned emu_design_nco_constrain(float f) { return design::nco_constrain(f); }
+float emu_design_rotation(unsigned C) { return design::firpfbch_rotation(C); }
+float emu_design_agc_threshold(float thr) { return design::agc_gain_threshold(thr); }
+int emu_frontend_geometry(float rate, float As, int Tc, int *n /*[13]*/, int *d /*[13]*/, int *hcap, int *smem)
+{
+    design::MsresampPlan ms = design::plan_msresamp(rate, As);
+    FrontendGeometry g = plan_frontend(ms, Tc);
+    if (!g.error.empty()) return -1;
+    for (int i = 0; i <= g.base.S; i++) { n[i] = g.base.n[i]; d[i] = g.base.d[i]; }
+    *hcap = g.hcap; *smem = (int)g.smem_bytes;
+    return g.base.S;
+}
+}

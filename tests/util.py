@@ -1,0 +1,56 @@
+"""Shared helpers for the parity tests.
+
+Tolerance (stated once, used everywhere): the north star asks for "max relative error <= 1e-4 or output SNR vs
+reference >= 80 dB".  All arithmetic is float32; `assert_parity` checks BOTH
+    max |y - ref| <= rel * max |ref|          (peak-relative error, rel = 1e-4 unless a test says otherwise)
+    SNR = 10 log10( sum |ref|^2 / sum |y - ref|^2 ) >= 80 dB
+"""
+import numpy as np
+
+REL_TOL = 1e-4
+SNR_DB = 80.0
+
+
+def snr_db(y, ref):
+    y = np.asarray(y)
+    ref = np.asarray(ref)
+    num = float(np.sum(np.abs(ref.astype(np.complex128)) ** 2))
+    den = float(np.sum(np.abs(y.astype(np.complex128) - ref.astype(np.complex128)) ** 2))
+    if den == 0.0:
+        return np.inf
+    if num == 0.0:
+        return -np.inf
+    return 10.0 * np.log10(num / den)
+
+
+def assert_parity(y, ref, rel=REL_TOL, snr=SNR_DB, what=""):
+    y = np.asarray(y)
+    ref = np.asarray(ref)
+    assert y.shape == ref.shape, f"{what}: shape {y.shape} != {ref.shape}"
+    if ref.size == 0:
+        return
+    peak = float(np.max(np.abs(ref)))
+    err = float(np.max(np.abs(y - ref)))
+    s = snr_db(y, ref)
+    assert err <= rel * max(peak, 1e-30), f"{what}: max err {err:.3e} > {rel:g} * peak {peak:.3e} (snr {s:.1f} dB)"
+    assert s >= snr, f"{what}: SNR {s:.1f} dB < {snr} dB"
+
+
+def chunked(x, sizes):
+    pos = 0
+    i = 0
+    while pos < len(x):
+        n = sizes[i % len(sizes)]
+        yield x[pos:pos + n]
+        pos += n
+        i += 1
+
+
+def make_signal(n, seed=0, amp=0.5):
+    """zero-mean complex test input: noise + two tones"""
+    g = np.random.default_rng(seed)
+    k = np.arange(n)
+    x = 0.05 * (g.standard_normal(n) + 1j * g.standard_normal(n))
+    x = x + amp * np.exp(2j * np.pi * 0.0391 * k + 1j * 3.0 * np.sin(2 * np.pi * k / 2560.0))
+    x = x + 0.3 * np.exp(-2j * np.pi * 0.156 * k)
+    return x.astype(np.complex64)
