@@ -487,6 +487,15 @@ class Chain:
     def print(self):
         self.L.csdr_chain_print(self.h)
 
+    def profile(self, enable=True):
+        self.L.csdr_chain_profile(self.h, int(enable))
+
+    def frontend_ms(self):
+        """(accumulated k_frontend device time in ms, launches) since profile(True)"""
+        n = C.c_uint64(0)
+        ms = self.L.csdr_chain_frontend_ms(self.h, C.byref(n))
+        return float(ms), int(n.value)
+
     def process_raw(self, x_ptr, nx, x_stride, out_ptrs, out_cap):
         """Pointer-level call (host or device pointers).  Returns samples written per output."""
         arr = (C.c_void_p * len(out_ptrs))(*out_ptrs)

@@ -296,6 +296,23 @@ size_t csdr_chain_warmup_len(csdr_chain q)
     size_t w = (size_t)(q->has_resamp ? q->fe.geo.hcap : 0) + (size_t)std::ceil(45000.0 / r);
     return w;
 }
+int csdr_chain_profile(csdr_chain q, int enable)
+{
+    API_BEGIN
+    q->fe.collect(q->ctx);
+    q->fe.profile = enable != 0;
+    q->fe.prof_ms = 0.0; q->fe.prof_launches = 0;
+    return 0;
+    API_END(-1)
+}
+double csdr_chain_frontend_ms(csdr_chain q, uint64_t *launches)
+{
+    API_BEGIN
+    q->fe.collect(q->ctx);
+    if (launches) *launches = q->fe.prof_launches;
+    return q->fe.prof_ms;
+    API_END(-1.0)
+}
 uint64_t csdr_chain_agc_fixups(csdr_chain q)
 {
     API_BEGIN

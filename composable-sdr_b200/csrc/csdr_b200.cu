@@ -142,6 +142,27 @@ struct Frontend {
     DevBuf bank;
     FrontendCursor cursor;
     int mix_mode = 0; uint32_t theta0 = 0, dtheta = 0; int quantize = 1;
+    // optional event timing of k_frontend (bench roofline): pairs recorded on the launching stream
+    bool profile = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pending, ev_free;
+    double prof_ms = 0.0; unsigned long long prof_launches = 0;
+    ~Frontend()
+    {
+        for (auto &e : ev_pending) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+        for (auto &e : ev_free) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+    }
+    void collect(const Ctx &c)
+    {
+        if (ev_pending.empty()) return;
+        c.sync();
+        for (auto &e : ev_pending) {
+            float ms = 0.f;
+            CK(cudaEventElapsedTime(&ms, e.first, e.second));
+            prof_ms += ms; prof_launches++;
+            ev_free.push_back(e);
+        }
+        ev_pending.clear();
+    }
 
     void init(const Ctx &c, float rate, float As, int streams)
     {
@@ -179,7 +200,15 @@ struct Frontend {
         p.bank = bank.as<float>();
         if (p.ntiles > 0) {
             int gx = std::min(p.ntiles, std::max(1, c.sms * 3 / std::max(1, std::min(nstreams, c.sms * 3))));
+            std::pair<cudaEvent_t, cudaEvent_t> ev{nullptr, nullptr};
+            if (profile) {
+                if (ev_pending.size() > 4096) collect(c);
+                if (!ev_free.empty()) { ev = ev_free.back(); ev_free.pop_back(); }
+                else { CK(cudaEventCreate(&ev.first)); CK(cudaEventCreate(&ev.second)); }
+                CK(cudaEventRecord(ev.first, c.stream));
+            }
             launch(k_frontend, dim3(gx, nstreams), dim3(256), geo.smem_bytes, c.stream, p);
+            if (profile) { CK(cudaEventRecord(ev.second, c.stream)); ev_pending.push_back(ev); }
         }
         if (nx > 0) {
             launch(k_hist_update, dim3((geo.hcap + 255) / 256, nstreams), dim3(256), 0, c.stream,

@@ -173,6 +173,10 @@ int      csdr_chain_seek(csdr_chain q, uint64_t n_prior);
 size_t   csdr_chain_warmup_len(csdr_chain q);
 /* the CUDA stream (cudaStream_t) the chain launches on, for event timing by the caller */
 void    *csdr_chain_cuda_stream(csdr_chain q);
+/* event timing of the dominant kernel (k_frontend: mix + msresamp) on the chain's own stream: enable, run, then
+ * read the accumulated device time [ms] and launch count (bench.py roofline) */
+int      csdr_chain_profile(csdr_chain q, int enable);
+double   csdr_chain_frontend_ms(csdr_chain q, uint64_t *launches);
 /* number of AGC time segments the last call had to recompute sequentially (speculation misses) */
 uint64_t csdr_chain_agc_fixups(csdr_chain q);
 

@@ -11,6 +11,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = os.path.join(_HERE, "liboracle.so")
+_LIB_FAST = _LIB      # timing uses the same -O2 build (the fastest of the flag sets tried, see Makefile)
 
 OPT_VCO_DIRECT, OPT_AMPMODEM_PLL, OPT_RESAMP_FC_OLD = 0, 1, 2
 
@@ -18,7 +19,7 @@ OPT_VCO_DIRECT, OPT_AMPMODEM_PLL, OPT_RESAMP_FC_OLD = 0, 1, 2
 def build(force=False):
     src = [os.path.join(_HERE, f) for f in ("liquid_oracle.c", "liquid_oracle.h", "Makefile")]
     if force or not os.path.exists(_LIB) or any(os.path.getmtime(s) > os.path.getmtime(_LIB) for s in src):
-        subprocess.check_call(["make", "-C", _HERE, "-s"])
+        subprocess.check_call(["make", "-C", _HERE, "-s"] + (["-B"] if force else []))
     return _LIB
 
 
@@ -29,13 +30,22 @@ class ChainCfg(C.Structure):
 
 
 _lib = None
+_lib_fast = None
 
 
-def lib():
-    global _lib
-    if _lib is not None:
-        return _lib
-    L = C.CDLL(build())
+def lib(fast=False):
+    global _lib, _lib_fast
+    if fast:
+        if _lib_fast is None:
+            build()
+            _lib_fast = _declare(C.CDLL(_LIB_FAST))
+        return _lib_fast
+    if _lib is None:
+        _lib = _declare(C.CDLL(build()))
+    return _lib
+
+
+def _declare(L):
     vp, u, f, i = C.c_void_p, C.c_uint, C.c_float, C.c_int
     sig = {
         "orc_set_option": (None, [i, i]), "orc_get_option": (i, [i]),
@@ -79,7 +89,6 @@ def lib():
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
         fn.restype, fn.argtypes = res, args
-    _lib = L
     return L
 
 
@@ -333,8 +342,8 @@ class Chain:
     """sdrProcess (apps/SoapySDR.hs:181-283) as one sequential object."""
 
     def __init__(self, samplerate, offset_hz=0.0, bandwidth_hz=0.0, demod=DEMOD_NO, kf=0.3, agc_thresh_db=0.0,
-                 channels=1, mix=False):
-        self.L = lib()
+                 channels=1, mix=False, fast=False):
+        self.L = lib(fast)
         self.cfg = ChainCfg(samplerate, offset_hz, bandwidth_hz, demod, kf, agc_thresh_db, channels, int(mix))
         self.h = self.L.orc_chain_create(C.byref(self.cfg))
         self.nout = self.L.orc_chain_num_outputs(self.h)

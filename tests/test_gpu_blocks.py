@@ -1,0 +1,158 @@
+"""GPU parity tests of the individual liquid-compatible blocks, called through the C ABI exactly as the
+reference's `_process` functions would (chunk by chunk, host arrays), against the CPU oracle on the same seeded
+inputs.  Tolerance: tests/util.py (peak-relative 1e-4 AND SNR >= 80 dB) unless stated."""
+import numpy as np
+import pytest
+
+from util import assert_parity, chunked, make_signal
+
+pytestmark = pytest.mark.gpu
+
+
+def run_pipe(cs, pipe, x, sizes):
+    process, cleanup = cs.unPipe(pipe)
+    out = list(process(chunked(x, sizes)))
+    cleanup()
+    return out
+
+
+@pytest.mark.parametrize("up", [False, True])
+def test_nco_mix(cs, orc, up):
+    x = make_signal(50000, 11)
+    f = float(np.float32(0.24543693))
+    ref = orc.Nco(f).mix_up(x) if up else orc.Nco(f).mix_down(x)
+    y = np.concatenate(run_pipe(cs, cs.mixUp(f) if up else cs.mixDown(f), x, [1024, 1, 4095]))
+    assert_parity(y, ref, what="nco")
+
+
+@pytest.mark.parametrize("rate", [0.078125, 0.02, 0.625, 0.5, 0.3])
+def test_msresamp(cs, orc, rate):
+    x = make_signal(200000, 12)
+    ref = orc.MsResamp(rate).execute(x)
+    a = np.concatenate(run_pipe(cs, cs.resampler(rate, 60.0), x, [1024]))       # the reference's chunk size
+    b = np.concatenate(run_pipe(cs, cs.resampler(rate, 60.0), x, [len(x)]))
+    c = np.concatenate(run_pipe(cs, cs.resampler(rate, 60.0), x, [1, 7, 100000, 33]))
+    assert len(a) == len(ref) and len(b) == len(ref)
+    assert np.array_equal(a, b) and np.array_equal(a, c)       # any chunking gives the same output stream, bit for bit
+    assert_parity(a, ref, what=f"msresamp {rate}")
+
+
+def test_msresamp_output_count_per_call_matches_liquid(cs, orc):
+    """the Haskell side sizes arrays from *ny (Liquid.chs:84-98): every call must return the oracle's count"""
+    x = make_signal(30000, 13)
+    rs = orc.MsResamp(0.078125)
+    want = [len(rs.execute(c)) for c in chunked(x, [1000, 13, 2048])]
+    got = [len(c) for c in run_pipe(cs, cs.resampler(0.078125, 60.0), x, [1000, 13, 2048])]
+    assert got == want
+
+
+def test_dc_blocker(cs, orc):
+    x = make_signal(300000, 14)
+    ref = orc.DcBlocker().execute(x)
+    y = np.concatenate(run_pipe(cs, cs.dcBlocker(), x, [65536, 1024, 100]))
+    assert_parity(y, ref, what="dcBlocker")
+
+
+@pytest.mark.parametrize("C", [16, 20, 64, 1024])
+def test_firpfbch(cs, orc, C):
+    nf = 600 if C < 1024 else 96
+    x = make_signal(C * nf, 15)
+    ref = orc.Firpfbch(C).execute(x)
+    sizes = [C * 100, C * 7, C * 300]
+    outs = run_pipe(cs, cs.firpfbchChannelizer(C), x, sizes)
+    y = np.concatenate([np.stack(o) for o in outs], axis=1)
+    assert_parity(y, ref, what=f"firpfbch {C}")
+
+
+def test_firpfbch_tail_samples_are_dropped_like_the_reference(cs, orc):
+    C = 16
+    x = make_signal(C * 50 + 5, 16)
+    ref = orc.Firpfbch(C).execute(x)
+    y = np.stack(run_pipe(cs, cs.firpfbchChannelizer(C), x, [len(x)])[0])
+    assert y.shape == ref.shape == (C, 50)
+    assert_parity(y, ref, what="firpfbch tail")
+
+
+def keyed_fm(n, seed=0):
+    t = np.arange(n)
+    g = np.random.default_rng(seed)
+    ph = 2 * np.pi * (0.11 * t + 0.02 * np.cumsum(np.sin(2 * np.pi * t / 400)))
+    env = ((t // 7000) % 2 == 0)
+    return (0.3 * env * np.exp(1j * ph) + 0.001 * (g.standard_normal(n) + 1j * g.standard_normal(n))).astype(np.complex64)
+
+
+def test_agc_with_squelch_gate(cs, orc):
+    x = keyed_fm(120000, 17)
+    ref = orc.Agc(-40.0).execute(x)
+    y = np.concatenate(run_pipe(cs, cs.automaticGainControl(-40.0), x, [4096, 50000, 1024]))
+    mism = np.count_nonzero((y == 0) != (ref == 0))
+    assert mism == 0, f"{mism} samples gated differently"
+    assert_parity(y, ref, what="agc")
+
+
+def test_agc_per_sample_protocol(cs, orc):
+    """the reference calls execute_block(.., 1, ..) + squelch_get_status + get_rssi per sample (Liquid.chs:697-704)"""
+    from composable_sdr_b200 import _lib
+    L = _lib.load()
+    x = keyed_fm(300, 18)
+    x[:200] *= 1.0
+    a = orc.Agc(-40.0)
+    h = L.csdr_agc_crcf_create()
+    L.csdr_agc_crcf_set_bandwidth(h, 0.1)
+    L.csdr_agc_crcf_set_signal_level(h, 1e-3)
+    L.csdr_agc_crcf_squelch_enable(h)
+    L.csdr_agc_crcf_squelch_set_threshold(h, -40.0)
+    L.csdr_agc_crcf_squelch_set_timeout(h, 1000)
+    y = np.zeros(1, np.complex64)
+    for i in range(len(x)):
+        r = a.execute_raw(x[i:i + 1])
+        L.csdr_agc_crcf_execute_block(h, x[i:i + 1].ctypes.data, 1, y.ctypes.data)
+        assert L.csdr_agc_crcf_squelch_get_status(h) == a.status
+        assert abs(L.csdr_agc_crcf_get_rssi(h) - a.rssi) < 1e-3
+        assert abs(y[0] - r[0]) <= 1e-4 * max(1.0, abs(r[0]))
+    L.csdr_agc_crcf_destroy(h)
+
+
+def test_freqdem(cs, orc):
+    x = keyed_fm(100000, 19)
+    ref = orc.FreqDem(0.3).execute(x)
+    y = np.concatenate(run_pipe(cs, cs.fmDemodulator(0.3), x, [1024, 9999]))
+    # the discriminator of a noise-only sample pair is ill-conditioned in |r|: compare where there is signal
+    assert_parity(y, ref, rel=2e-4, what="freqdem")
+
+
+@pytest.mark.parametrize("pll", [1, 0])
+def test_ampmodem(cs, orc, pll):
+    from composable_sdr_b200 import _lib
+    cs.set_option(_lib.OPT_AMPMODEM_PLL, pll)
+    orc.set_option(orc.OPT_AMPMODEM_PLL, pll)
+    try:
+        n = 60000
+        k = np.arange(n)
+        g = np.random.default_rng(20)
+        x = (0.5 * (1 + 0.8 * np.sin(2 * np.pi * 0.03 * k)) * np.exp(2j * np.pi * 0.0004 * k + 0.5j)
+             + 0.002 * (g.standard_normal(n) + 1j * g.standard_normal(n))).astype(np.complex64)
+        ref = orc.AmpModem(0.8).execute(x)
+        y = np.concatenate(run_pipe(cs, cs.amDemodulator(), x, [1024, 20000, 30]))
+        assert_parity(y, ref, what=f"ampmodem pll={pll}")
+    finally:
+        cs.set_option(_lib.OPT_AMPMODEM_PLL, 1)
+        orc.set_option(orc.OPT_AMPMODEM_PLL, 1)
+
+
+def test_device_pointers_are_accepted(cs, orc):
+    import torch
+    x = make_signal(100000, 21)
+    ref = orc.MsResamp(0.078125).execute(x)
+    xd = torch.from_numpy(x).cuda()
+    y = torch.cat(run_pipe(cs, cs.resampler(0.078125, 60.0), xd, [40000])).cpu().numpy()
+    assert_parity(y, ref, what="device pointers")
+
+
+def test_unfused_app_graph_config1(cs, orc):
+    """sdrProcess assembled from the individual blocks with the reference's chunk protocol (chunk 1024,
+    compact 4096) == the oracle's chain.  Config 1: -s 2.56e6 --offset 1e5 -b 200000 --demod DeNo."""
+    x = cs.synth.config1(400000)
+    ref = orc.Chain(2.56e6, 1e5, 200e3).process(x)[0][:30000]
+    y = cs.sdrProcess(chunked(x, [1024]), 2.56e6, offset=1e5, bandwidth=200e3, numsamples=30000)
+    assert_parity(y, ref, what="unfused config 1")

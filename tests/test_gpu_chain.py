@@ -1,0 +1,148 @@
+"""GPU parity tests of the fused chain (csdr_chain_*, the object bench.py drives) against the oracle's restatement
+of sdrProcess (apps/SoapySDR.hs:181-283) for the five BASELINE configs, plus size-independent properties at
+BASELINE's full sizes.  Tolerance: tests/util.py."""
+import numpy as np
+import pytest
+
+from util import assert_parity, chunked, make_signal, snr_db
+
+pytestmark = pytest.mark.gpu
+
+
+def _ranges(n, sizes):
+    pos, i = 0, 0
+    while pos < n:
+        m = sizes[i % len(sizes)]
+        yield pos, min(n, pos + m)
+        pos += m
+        i += 1
+
+
+def run_chain(chain, x, sizes):
+    """feed x ([n] or [nstreams, n]) in chunks of the given sizes; returns the concatenated outputs"""
+    acc = None
+    for i, j in _ranges(x.shape[-1], sizes):
+        o = chain.process(np.ascontiguousarray(x[..., i:j]))
+        acc = [[v] for v in o] if acc is None else [a + [v] for a, v in zip(acc, o)]
+    return [np.concatenate(a) for a in acc]
+
+
+def test_config1_mix_resample(cs, orc):
+    """soapy-sdr -s 2.56e6 --offset 1e5 -b 200000 --demod DeNo  (mix + msresamp [+ dc blocker])"""
+    x = cs.synth.config1(1 << 21)
+    ref = orc.Chain(2.56e6, 1e5, 200e3).process(x)[0]
+    a = run_chain(cs.Chain(2.56e6, 1e5, 200e3), x, [1 << 20])[0]
+    b = run_chain(cs.Chain(2.56e6, 1e5, 200e3), x, [1024 * 37, 5, 1 << 19])[0]
+    assert len(a) == len(ref) == len(b)
+    assert_parity(a, ref, what="config 1")
+    assert_parity(b, ref, what="config 1 (ragged chunks)")
+
+
+def test_config2_fm_with_agc(cs, orc):
+    """2.56 MS/s -> 200 kHz, NBFM, AGC -40 dB, carrier keyed on/off (squelch).  The bench workload."""
+    x = cs.synth.config2(1 << 22)
+    ref = orc.Chain(2.56e6, 1e5, 200e3, orc.DEMOD_NBFM, 0.3, -40.0).process(x)[0]
+    ch = cs.Chain(2.56e6, 1e5, 200e3, cs.DeNBFM(0.3), agc=-40.0)
+    y = run_chain(ch, x, [1 << 21])[0]
+    assert len(y) == len(ref)
+    # the squelch gate must open and close on the same samples
+    assert np.count_nonzero((y == 0) != (ref == 0)) == 0
+    assert_parity(y, ref, what="config 2")
+    y2 = run_chain(cs.Chain(2.56e6, 1e5, 200e3, cs.DeNBFM(0.3), agc=-40.0), x, [300001, 1024])[0]
+    assert_parity(y2, ref, what="config 2 (ragged chunks)")
+
+
+def test_config3_channelizer_per_channel_fm(cs, orc):
+    """2.56 MS/s into -c 16, per-channel AGC + NBFM, 16 outputs"""
+    x = cs.synth.config3(1 << 20)
+    ref = orc.Chain(2.56e6, 0.0, 0.0, orc.DEMOD_NBFM, 0.3, -40.0, 16, False).process(x)
+    outs = run_chain(cs.Chain(2.56e6, demod=cs.DeNBFM(0.3), agc=-40.0, channels=16), x, [1 << 19, 65536 + 3])
+    assert len(outs) == 16
+    for c in range(16):
+        assert len(outs[c]) == len(ref[c])
+        assert np.count_nonzero((outs[c] == 0) != (ref[c] == 0)) <= 2
+        assert_parity(outs[c], ref[c], rel=3e-4, what=f"config 3 channel {c}")
+
+
+def test_config3_raw_channels_and_mix(cs, orc):
+    x = cs.synth.config3(1 << 18)
+    ref = orc.Chain(2.56e6, 0.0, 0.0, orc.DEMOD_NO, 0.0, 0.0, 16, False).process(x)
+    outs = run_chain(cs.Chain(2.56e6, channels=16), x, [100000])
+    for c in range(16):
+        assert_parity(outs[c], ref[c], what=f"config 3 DeNo channel {c}")
+    refm = orc.Chain(2.56e6, 0.0, 0.0, orc.DEMOD_NBFM, 0.3, -40.0, 16, True).process(x)[0]
+    m = run_chain(cs.Chain(2.56e6, demod=cs.DeNBFM(0.3), agc=-40.0, channels=16, mix_channels=True), x, [100000])[0]
+    assert_parity(m, refm, rel=3e-4, what="config 3 --mix")
+
+
+def test_config4_wideband_1024_channels_mix(cs, orc):
+    """1024-channel firpfbch with --mix: 2^22 samples (4096 frames) against the oracle on one GPU"""
+    x = cs.synth.config4(1 << 22)
+    ref = orc.Chain(1e9, 0.0, 0.0, orc.DEMOD_NBFM, 0.3, -40.0, 1024, True).process(x)[0]
+    y = run_chain(cs.Chain(1e9, demod=cs.DeNBFM(0.3), agc=-40.0, channels=1024, mix_channels=True), x, [1 << 21])[0]
+    assert len(y) == len(ref) == 4096
+    assert snr_db(y, ref) >= 60.0       # sum of 1024 discriminator outputs, most of them noise-only channels
+
+
+def test_config5_batch_of_streams_am(cs, orc):
+    """independent 10 MS/s captures: offset mix + resample + AGC + AM demod, one handle for all streams"""
+    S, n = 8, 1 << 19
+    x = cs.synth.config5(n, S)
+    ch = cs.Chain(10e6, 1e6, 200e3, cs.DeAM(), agc=-40.0, nstreams=S)
+    outs = run_chain(ch, x, [n // 2, 100000])
+    for s in range(S):
+        ref = orc.Chain(10e6, 1e6, 200e3, orc.DEMOD_AM, 0.0, -40.0).process(x[s])[0]
+        assert len(outs[s]) == len(ref)
+        assert_parity(outs[s], ref, rel=3e-4, what=f"config 5 stream {s}")
+
+
+def test_time_segment_sharding_matches_single_stream(cs, orc):
+    """multi-GPU partitioning of one long stream: a shard seeks to its start minus the warm-up, feeds
+    the warm-up history, drops the outputs it produces, and then equals the single-stream result."""
+    x = cs.synth.config2(3 << 20, keyed=None)
+    full = cs.Chain(2.56e6, 1e5, 200e3, cs.DeNBFM(0.3), agc=-40.0)
+    ref = full.process(x)[0]
+    shard = cs.Chain(2.56e6, 1e5, 200e3, cs.DeNBFM(0.3), agc=-40.0)
+    start = 2 << 20
+    warm = shard.warmup_len()
+    assert warm < start
+    pre = cs.Chain(2.56e6, 1e5, 200e3, cs.DeNBFM(0.3), agc=-40.0)
+    n_before = len(pre.process(x[:start - warm])[0])
+    n_warm = len(pre.process(x[start - warm:start])[0])
+    shard.seek(start - warm)
+    y = shard.process(x[start - warm:])[0]
+    assert len(y) == len(ref) - n_before
+    assert_parity(y[n_warm:], ref[n_before + n_warm:], rel=3e-4, what="time-segment shard")
+
+
+def test_full_size_properties_on_device(cs):
+    """BASELINE-size chunk (2^26 samples, device resident): exact output count, linearity of the front end,
+    chunk invariance, and few AGC speculation misses."""
+    import torch
+    n = 1 << 26
+    g = torch.Generator(device="cuda").manual_seed(1)
+    k = torch.arange(n, device="cuda", dtype=torch.float64)
+    carrier = 0.5 * torch.exp(1j * (2 * np.pi * 1e5 / 2.56e6 * k - 50.0 * torch.cos(2 * np.pi * 1e3 / 2.56e6 * k)))
+    noise = 0.05 * torch.complex(torch.randn(n, generator=g, device="cuda"), torch.randn(n, generator=g, device="cuda"))
+    x1 = carrier.to(torch.complex64)
+    x2 = noise.to(torch.complex64)
+    del carrier, noise, k
+    def fe():
+        return cs.Chain(2.56e6, 1e5, 200e3)
+    y1 = fe().process(x1)[0]
+    y2 = fe().process(x2)[0]
+    y12 = fe().process(x1 + x2)[0]
+    assert len(y1) == n * 200e3 / 2.56e6                   # 5 242 880 outputs exactly
+    lin = (y12 - (y1 + y2)).abs().max().item()
+    assert lin <= 1e-4 * y12.abs().max().item()
+    c = fe()
+    parts = [c.process(x1[i:i + (1 << 24) + 8])[0] for i in range(0, n, (1 << 24) + 8)]
+    assert torch.equal(torch.cat(parts), y1)
+    ch = cs.Chain(2.56e6, 1e5, 200e3, cs.DeNBFM(0.3), agc=-40.0)
+    a = ch.process(x1 + x2)[0]
+    assert len(a) == len(y1)
+    assert torch.isfinite(a).all()
+    assert ch.agc_fixups() < 64
+    # the demodulated tone: 1 kHz at deviation 50 kHz -> amplitude (dev/fs_out)/kf
+    seg = a[100000:200000].double()
+    assert abs(seg.abs().max().item() - (50e3 / 200e3) / 0.3) < 0.05
