@@ -8,12 +8,11 @@
 //   * dc blocker: a linear recurrence.  k_dc_partial reduces every G-sample group to its zero-state response,
 //     k_dc_scan composes the groups (one CTA per lane, fp64) and yields the exact filter state at every group
 //     boundary; consumers restart the float32 recurrence from those states.
-//   * AGC: a contractive non-linear loop (perturbations decay like (1-alpha)^(k/2)).  Every L-sample segment is
-//     run speculatively by its own thread after a W-sample warm-up that starts from an equilibrium guess;
-//     k_backend_verify compares each segment's start state with its predecessor's end state (gain and level
-//     to 1e-6 relative, squelch mode/timer and discriminator history exactly/1e-6) and k_backend_fixup re-runs,
-//     in stream order, exactly those segments whose speculation missed.  The result equals the sequential
-//     loop to within the stated tolerance in all cases; only the speed depends on the signal.
+//   * AGC + squelch: the gain loop is contractive, so L-sample segments are run speculatively after a W-sample
+//     warm-up and verified against their predecessors; the squelch state machine never feeds back into the gain
+//     and is resolved EXACTLY afterwards on one threshold bit per sample; the gate is applied last as a mask.
+//     Details at "agc + fm" below.  The result equals the sequential loop to within the stated tolerance in all
+//     cases (gate positions exactly); only the speed depends on the signal.
 #pragma once
 #include "platform.cuh"
 
@@ -29,6 +28,7 @@ struct LaneState {                 // carried across calls, one per lane
 };
 struct SegState { float g, y2p; int mode; unsigned timer; float fm_re, fm_im; };
 
+struct FsmState;
 struct BackendParams {
     const float2 *in; long long in_lane_stride;
     void *out; long long out_lane_stride;      // float (demod != 0) or float2 elements
@@ -42,11 +42,16 @@ struct BackendParams {
     int squelch_enabled;
     int gate;                                  // 1: zero the output unless squelch status == SIGNALHI (Liquid.chs:700-704)
     LaneState *lane;
-    SegState *seg_start, *seg_end;             // [nlanes][nseg]
+    SegState *seg_start, *seg_end;             // [nlanes][nseg] gain-loop state at segment boundaries
     const double2 *dcV;                        // [nlanes][ngrp+1] dc state at group boundaries
-    unsigned *flags;                           // [nlanes][nseg]
-    unsigned *counts;                          // [nlanes] speculation misses
-    unsigned long long *fixups;                // total segments re-run (diagnostic)
+    int nwords, FW;                            // 32-sample words per lane; FSM replay length in segments
+    unsigned *exbits, *gatebits;               // [nlanes][nwords] threshold-exceeded / gate-open bit per sample
+    unsigned *sgnr, *sgni;                     // [nlanes][nwords] sign bits of the ungated agc output (discriminator
+                                               // values next to a closed gate are signed-zero artefacts: +-pi or 0)
+    unsigned *prev_sign;                       // [nlanes] sign bits (re | im << 1) of the sample before this chunk
+    FsmState *fsm_start, *fsm_end;      // [nlanes][nseg]
+    unsigned *prev_gate;                       // [nlanes] gate of the sample before this chunk
+    unsigned long long *fixups;                // [2] segments re-run: gain loop, squelch FSM (diagnostic)
 };
 
 // ------------------------------------------------------------------------------------------ dc blocker
@@ -158,12 +163,43 @@ __global__ void k_dc_finish(const DcParams p)
 }
 
 // ------------------------------------------------------------------------------------------ agc + fm
-struct AgcRun { float g, y2p; int mode; unsigned timer; float fr, fi; };
+// The squelch FSM does not feed back into the gain loop, so the work is split:
+//   pass G (k_backend_spec / k_backend_fixup): the gain trajectory.  Each L-sample segment is run by its own thread
+//       after a W-sample warm-up (the loop is contractive: perturbations decay like (1-alpha)^(k/2)); it writes the
+//       UNGATED outputs (agc samples, or discriminator values of ungated neighbours) and one "rssi > threshold" bit
+//       per sample.  Segment start states are verified against the predecessor's end state (1e-6 relative) and the
+//       rare misses (e.g. a gain frozen by digital silence) are re-run in stream order.
+//   pass F (k_backend_fsm / k_backend_fsm_fix): the squelch state machine, EXACT, on the bit stream.  Each segment
+//       re-derives its entry state by replaying the bits of the preceding FW segments (any entry state is forgotten
+//       after timeout+4 samples except for measure-zero coincidences), emits one gate bit per sample, and entry states
+//       are again verified against the predecessor's exit state and repaired in order where they differ.
+//   pass A (k_backend_gate): zero the outputs where the gate is closed: y[i] if !gate[i]; the discriminator output
+//       m[i] = arg(conj(r[i-1]) r[i]) if !(gate[i-1] && gate[i])  (arg(0) = 0, as in liquid).
+struct AgcRun { float g, y2p; float fr, fi; };
 
-// one sample of: [dc] -> agc(+squelch gate) -> [freqdem]; returns gated agc output in (yr, yi), fm in *m
-__device__ __forceinline__ void be_step(const BackendParams &p, AgcRun &s, float xr, float xi, float &yr, float &yi,
+__device__ __forceinline__ void fsm_step(int &mode, unsigned &timer, bool ex, unsigned timeout)
+{
+    // AGC(_squelch_update_mode), liquid agc.c
+    switch (mode) {
+    case SQ_ENABLED:  mode = ex ? SQ_RISE : SQ_ENABLED; break;
+    case SQ_RISE:     mode = ex ? SQ_SIGNALHI : SQ_FALL; break;
+    case SQ_SIGNALHI: mode = ex ? SQ_SIGNALHI : SQ_FALL; break;
+    case SQ_FALL:     mode = ex ? SQ_SIGNALHI : SQ_SIGNALLO; timer = timeout; break;
+    case SQ_SIGNALLO:
+        timer--;
+        if (timer == 0) mode = SQ_TIMEOUT;
+        else if (ex)    mode = SQ_SIGNALHI;
+        break;
+    case SQ_TIMEOUT:  mode = SQ_ENABLED; break;
+    default: break;
+    }
+}
+
+// one sample of the gain loop: ungated agc output (yr, yi), threshold bit, ungated discriminator value
+__device__ __forceinline__ bool be_step(const BackendParams &p, AgcRun &s, float xr, float xi, float &yr, float &yi,
                                         float &m)
 {
+    bool ex = true;
     if (p.has_agc) {
         // AGC(_execute), liquid agc.c
         yr = __fmul_rn(xr, s.g); yi = __fmul_rn(xi, s.g);
@@ -171,25 +207,7 @@ __device__ __forceinline__ void be_step(const BackendParams &p, AgcRun &s, float
         s.y2p = (float)(p.one_minus_alpha * (double)s.y2p + (double)__fmul_rn(p.alpha, y2));
         if (s.y2p > 1e-6f) s.g *= expf(p.neg_half_alpha * logf(s.y2p));
         if (s.g > 1e6f) s.g = 1e6f;
-        if (p.squelch_enabled) {
-            // AGC(_squelch_update_mode)
-            const bool ex = s.g < p.g_thr;
-            switch (s.mode) {
-            case SQ_ENABLED:  s.mode = ex ? SQ_RISE : SQ_ENABLED; break;
-            case SQ_RISE:     s.mode = ex ? SQ_SIGNALHI : SQ_FALL; break;
-            case SQ_SIGNALHI: s.mode = ex ? SQ_SIGNALHI : SQ_FALL; break;
-            case SQ_FALL:     s.mode = ex ? SQ_SIGNALHI : SQ_SIGNALLO; s.timer = p.timeout; break;
-            case SQ_SIGNALLO:
-                s.timer--;
-                if (s.timer == 0) s.mode = SQ_TIMEOUT;
-                else if (ex)      s.mode = SQ_SIGNALHI;
-                break;
-            case SQ_TIMEOUT:  s.mode = SQ_ENABLED; break;
-            default: break;
-            }
-            // Haskell agcExecuteBlock: keep the sample only while SIGNALHI
-            if (p.gate && s.mode != SQ_SIGNALHI) { yr = 0.f; yi = 0.f; }
-        }
+        ex = s.g < p.g_thr;                       // rssi = -20 log10(g) > threshold
     } else { yr = xr; yi = xi; }
     if (p.demod == 1) {
         // freqdem_demodulate: arg(conj(r') r) / (2 pi kf)
@@ -198,25 +216,32 @@ __device__ __forceinline__ void be_step(const BackendParams &p, AgcRun &s, float
         m = atan2f(im, re) * p.fm_ref;
         s.fr = yr; s.fi = yi;
     }
+    return ex;
 }
 
-__device__ __forceinline__ bool be_close(float a, float b) { return fabsf(a - b) <= 1e-6f * fmaxf(fabsf(a), fabsf(b)); }
+__device__ __forceinline__ bool be_close(float a, float b, float atol = 0.f)
+{
+    return fabsf(a - b) <= 1e-6f * fmaxf(fabsf(a), fabsf(b)) + atol;
+}
 __device__ __forceinline__ bool be_match(const SegState &a, const SegState &b, int has_agc, int demod)
 {
     bool ok = true;
-    if (has_agc) ok = ok && be_close(a.g, b.g) && be_close(a.y2p, b.y2p) && a.mode == b.mode &&
-                      (a.mode != SQ_SIGNALLO || a.timer == b.timer);
-    if (demod == 1) ok = ok && be_close(a.fm_re, b.fm_re) && be_close(a.fm_im, b.fm_im);
+    if (has_agc) ok = ok && be_close(a.g, b.g) && be_close(a.y2p, b.y2p);
+    if (demod == 1) ok = ok && be_close(a.fm_re, b.fm_re, 1e-5f) && be_close(a.fm_im, b.fm_im, 1e-5f);
     return ok;
 }
 
-// run samples [i0, i1) of one lane from state s / dc state (v1r, v1i); emit outputs for i >= emit_from
+// run samples [i0, i1) of one lane from state s / dc state (v1r, v1i); emit outputs and threshold bits for
+// i >= emit_from (emit_from and i1 - or the chunk end - delimit whole 32-bit words owned by the caller)
 __device__ __forceinline__ void be_run(const BackendParams &p, int lane, AgcRun &s, float &v1r, float &v1i, int i0,
                                        int i1, int emit_from)
 {
     const float2 *x = p.in + (long long)lane * p.in_lane_stride;
     float *of = (float *)p.out + (long long)lane * p.out_lane_stride;
     float2 *oc = (float2 *)p.out + (long long)lane * p.out_lane_stride;
+    unsigned *bits = p.exbits + (long long)lane * p.nwords;
+    unsigned *sr = p.sgnr + (long long)lane * p.nwords, *si = p.sgni + (long long)lane * p.nwords;
+    unsigned word = 0, wr = 0, wi = 0;
     for (int i = i0; i < i1; i++) {
         float2 v = x[i];
         float xr = v.x, xi = v.y;
@@ -227,9 +252,17 @@ __device__ __forceinline__ void be_run(const BackendParams &p, int lane, AgcRun 
             v1r = v0r; v1i = v0i;
         }
         float yr, yi, m = 0.f;
-        be_step(p, s, xr, xi, yr, yi, m);
+        const bool ex = be_step(p, s, xr, xi, yr, yi, m);
         if (i >= emit_from) {
             if (p.demod == 1) of[i] = m; else oc[i] = cf(yr, yi);
+            word |= (ex ? 1u : 0u) << (i & 31);
+            wr |= ((unsigned)__float_as_int(yr) >> 31) << (i & 31);
+            wi |= ((unsigned)__float_as_int(yi) >> 31) << (i & 31);
+            if ((i & 31) == 31 || i == i1 - 1) {
+                bits[i >> 5] = word; word = 0;
+                if (p.demod == 1) { sr[i >> 5] = wr; si[i >> 5] = wi; }
+                wr = 0; wi = 0;
+            }
         }
     }
 }
@@ -241,6 +274,12 @@ __device__ __forceinline__ void be_dc_state(const BackendParams &p, int lane, in
         double2 v = p.dcV[(long long)lane * (p.ngrp + 1) + i / p.G];
         v1r = (float)v.x; v1i = (float)v.y;
     } else { v1r = 0.f; v1i = 0.f; }
+}
+
+__device__ __forceinline__ SegState be_pack(const AgcRun &s)
+{
+    SegState st; st.g = s.g; st.y2p = s.y2p; st.mode = 0; st.timer = 0; st.fm_re = s.fr; st.fm_im = s.fi;
+    return st;
 }
 
 __global__ void __launch_bounds__(128) k_backend_spec(const BackendParams p)
@@ -255,7 +294,7 @@ __global__ void __launch_bounds__(128) k_backend_spec(const BackendParams p)
     if (w0 <= 0) {
         // the warm-up reaches the chunk start: run from the true carried state (exact)
         w0 = 0;
-        s.g = ls.g; s.y2p = ls.y2p; s.mode = ls.mode; s.timer = ls.timer; s.fr = ls.fm_re; s.fi = ls.fm_im;
+        s.g = ls.g; s.y2p = ls.y2p; s.fr = ls.fm_re; s.fi = ls.fm_im;
     } else {
         // equilibrium guess: unit output energy for the first samples of the warm-up window
         const float2 *x = p.in + (long long)lane * p.in_lane_stride;
@@ -264,29 +303,16 @@ __global__ void __launch_bounds__(128) k_backend_spec(const BackendParams p)
         e *= (1.0f / 16.0f);
         s.g = (e > 1e-30f) ? rsqrtf(e) : 1e6f;
         if (s.g > 1e6f) s.g = 1e6f;
-        s.y2p = 1.0f; s.mode = p.squelch_enabled ? SQ_ENABLED : SQ_DISABLED; s.timer = 0; s.fr = 0.f; s.fi = 0.f;
+        s.y2p = 1.0f; s.fr = 0.f; s.fi = 0.f;
     }
     be_dc_state(p, lane, w0, v1r, v1i);
     be_run(p, lane, s, v1r, v1i, w0, b0, b1);          // warm-up, nothing emitted
-    SegState st; st.g = s.g; st.y2p = s.y2p; st.mode = s.mode; st.timer = s.timer; st.fm_re = s.fr; st.fm_im = s.fi;
-    p.seg_start[t] = st;
+    p.seg_start[t] = be_pack(s);
     be_run(p, lane, s, v1r, v1i, b0, b1, b0);
-    st.g = s.g; st.y2p = s.y2p; st.mode = s.mode; st.timer = s.timer; st.fm_re = s.fr; st.fm_im = s.fi;
-    p.seg_end[t] = st;
+    p.seg_end[t] = be_pack(s);
 }
 
-__global__ void k_backend_verify(const BackendParams p)
-{
-    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= (long long)p.nlanes * p.nseg) return;
-    const int lane = (int)(t / p.nseg), seg = (int)(t - (long long)lane * p.nseg);
-    unsigned bad = 0;
-    if (seg > 0 && !be_match(p.seg_start[t], p.seg_end[t - 1], p.has_agc, p.demod)) bad = 1;
-    p.flags[t] = bad;
-    if (bad) atomicAdd(&p.counts[lane], 1u);
-}
-
-// one CTA per lane.  Common case (no misses): copy the last segment's end state into the lane state.
+// one CTA per lane: verify the gain speculation, re-run the misses in stream order, store the lane's gain state
 __global__ void k_backend_fixup(const BackendParams p)
 {
     const int lane = blockIdx.x;
@@ -294,51 +320,184 @@ __global__ void k_backend_fixup(const BackendParams p)
     __shared__ int s_cur;
     SegState *E = p.seg_end + (long long)lane * p.nseg;
     const SegState *S0 = p.seg_start + (long long)lane * p.nseg;
-    unsigned *flags = p.flags + (long long)lane * p.nseg;
-    if (p.counts[lane] != 0) {
-        if (threadIdx.x == 0) s_cur = 1;
+    if (threadIdx.x == 0) s_cur = 1;
+    __syncthreads();
+    while (true) {
+        // parallel search for the first segment >= s_cur whose start state does not continue its predecessor
+        if (threadIdx.x == 0) s_next = 0xffffffffu;
         __syncthreads();
-        while (true) {
-            // parallel search for the next flagged segment >= s_cur
-            if (threadIdx.x == 0) s_next = 0xffffffffu;
-            __syncthreads();
-            const int cur = s_cur;
-            unsigned best = 0xffffffffu;
-            for (int j = cur + threadIdx.x; j < p.nseg; j += blockDim.x)
-                if (flags[j]) { best = (unsigned)j; break; }
-            if (best != 0xffffffffu) atomicMin(&s_next, best);
-            __syncthreads();
-            const unsigned nxt = s_next;
-            if (nxt == 0xffffffffu) break;
-            if (threadIdx.x == 0) {
-                // re-run segments in stream order from the true predecessor state until speculation re-joins
-                int seg = (int)nxt;
-                unsigned long long redone = 0;
-                while (seg < p.nseg) {
-                    const SegState pe = E[seg - 1];
-                    if (be_match(S0[seg], pe, p.has_agc, p.demod)) { flags[seg] = 0; break; }
-                    AgcRun s; s.g = pe.g; s.y2p = pe.y2p; s.mode = pe.mode; s.timer = pe.timer; s.fr = pe.fm_re; s.fi = pe.fm_im;
-                    float v1r, v1i;
-                    const int b0 = seg * p.L, b1 = min(b0 + p.L, p.n);
-                    be_dc_state(p, lane, b0, v1r, v1i);
-                    be_run(p, lane, s, v1r, v1i, b0, b1, b0);
-                    SegState ne; ne.g = s.g; ne.y2p = s.y2p; ne.mode = s.mode; ne.timer = s.timer; ne.fm_re = s.fr; ne.fm_im = s.fi;
-                    E[seg] = ne; flags[seg] = 0; redone++;
-                    seg++;      // the successor is re-checked against the new end state on the next iteration
-                }
-                s_cur = seg;
-                atomicAdd(p.fixups, redone);
+        const int cur = s_cur;
+        for (int j = cur + threadIdx.x; j < p.nseg; j += blockDim.x)
+            if (!be_match(S0[j], E[j - 1], p.has_agc, p.demod)) { atomicMin(&s_next, (unsigned)j); break; }
+        __syncthreads();
+        const unsigned nxt = s_next;
+        if (nxt == 0xffffffffu) break;
+        if (threadIdx.x == 0) {
+            int seg = (int)nxt;
+            unsigned long long redone = 0;
+            while (seg < p.nseg) {
+                const SegState pe = E[seg - 1];
+                if (be_match(S0[seg], pe, p.has_agc, p.demod)) break;
+                AgcRun s; s.g = pe.g; s.y2p = pe.y2p; s.fr = pe.fm_re; s.fi = pe.fm_im;
+                float v1r, v1i;
+                const int b0 = seg * p.L, b1 = min(b0 + p.L, p.n);
+                be_dc_state(p, lane, b0, v1r, v1i);
+                be_run(p, lane, s, v1r, v1i, b0, b1, b0);
+                E[seg] = be_pack(s);
+                redone++;
+                seg++;      // the successor is re-checked against the new end state on the next iteration
             }
-            __syncthreads();
+            s_cur = seg;
+            atomicAdd(p.fixups, redone);
         }
+        __syncthreads();
     }
     __syncthreads();
     if (threadIdx.x == 0) {
         const SegState e = E[p.nseg - 1];
         LaneState ls = p.lane[lane];
-        ls.g = e.g; ls.y2p = e.y2p; ls.mode = e.mode; ls.timer = e.timer; ls.fm_re = e.fm_re; ls.fm_im = e.fm_im;
+        p.prev_sign[lane] = ((unsigned)__float_as_int(ls.fm_re) >> 31) | (((unsigned)__float_as_int(ls.fm_im) >> 31) << 1);
+        ls.g = e.g; ls.y2p = e.y2p; ls.fm_re = e.fm_re; ls.fm_im = e.fm_im;
         p.lane[lane] = ls;
-        p.counts[lane] = 0;
+    }
+}
+
+// ---- squelch FSM on the threshold bits
+struct FsmState { int mode; unsigned timer; };
+__device__ __forceinline__ bool fsm_same(const FsmState &a, const FsmState &b)
+{
+    return a.mode == b.mode && (a.mode != SQ_SIGNALLO || a.timer == b.timer);
+}
+
+// run the FSM over bits [i0, i1) of a lane; when gate != nullptr write one gate bit (mode == SIGNALHI) per sample
+__device__ __forceinline__ void fsm_run(const BackendParams &p, const unsigned *bits, unsigned *gate, FsmState &s,
+                                        int i0, int i1)
+{
+    int i = i0;
+    while (i < i1) {
+        const int w = i >> 5, lo = i & 31, cnt = min(32 - lo, i1 - i);
+        const unsigned full = (cnt == 32) ? 0xffffffffu : ((1u << cnt) - 1u);
+        const unsigned word = (bits[w] >> lo) & full;
+        unsigned gw = 0;
+        if (word == full && s.mode == SQ_SIGNALHI) gw = full;                              // stays open
+        else if (word == 0 && s.mode == SQ_ENABLED) gw = 0;                                // stays closed
+        else if (word == 0 && s.mode == SQ_SIGNALLO && s.timer > (unsigned)cnt) s.timer -= (unsigned)cnt;
+        else {
+            for (int b = 0; b < cnt; b++) {
+                fsm_step(s.mode, s.timer, (word >> b) & 1u, p.timeout);
+                gw |= (s.mode == SQ_SIGNALHI ? 1u : 0u) << b;
+            }
+        }
+        if (gate) {
+            // words are owned by one segment except for a ragged chunk end; lo != 0 only happens at i0 of a replay
+            if (lo == 0) gate[w] = gw; else gate[w] = (gate[w] & ((1u << lo) - 1u)) | (gw << lo);
+        }
+        i += cnt;
+    }
+}
+
+__global__ void __launch_bounds__(128) k_backend_fsm(const BackendParams p)
+{
+    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long long)p.nlanes * p.nseg) return;
+    const int lane = (int)(t / p.nseg), seg = (int)(t - (long long)lane * p.nseg);
+    const unsigned *bits = p.exbits + (long long)lane * p.nwords;
+    unsigned *gate = p.gatebits + (long long)lane * p.nwords;
+    const int b0 = seg * p.L, b1 = min(b0 + p.L, p.n);
+    FsmState s;
+    int w0 = b0 - p.FW * p.L;
+    if (w0 <= 0) { w0 = 0; s.mode = p.lane[lane].mode; s.timer = p.lane[lane].timer; }   // exact
+    else { s.mode = SQ_ENABLED; s.timer = 0; }
+    fsm_run(p, bits, nullptr, s, w0, b0);
+    p.fsm_start[t] = s;
+    fsm_run(p, bits, gate, s, b0, b1);
+    p.fsm_end[t] = s;
+}
+
+__global__ void k_backend_fsm_fix(const BackendParams p)
+{
+    const int lane = blockIdx.x;
+    __shared__ unsigned s_next;
+    __shared__ int s_cur;
+    FsmState *E = p.fsm_end + (long long)lane * p.nseg;
+    const FsmState *S0 = p.fsm_start + (long long)lane * p.nseg;
+    const unsigned *bits = p.exbits + (long long)lane * p.nwords;
+    unsigned *gate = p.gatebits + (long long)lane * p.nwords;
+    if (threadIdx.x == 0) s_cur = 1;
+    __syncthreads();
+    while (true) {
+        if (threadIdx.x == 0) s_next = 0xffffffffu;
+        __syncthreads();
+        const int cur = s_cur;
+        for (int j = cur + threadIdx.x; j < p.nseg; j += blockDim.x)
+            if (!fsm_same(S0[j], E[j - 1])) { atomicMin(&s_next, (unsigned)j); break; }
+        __syncthreads();
+        const unsigned nxt = s_next;
+        if (nxt == 0xffffffffu) break;
+        if (threadIdx.x == 0) {
+            int seg = (int)nxt;
+            unsigned long long redone = 0;
+            while (seg < p.nseg) {
+                FsmState s = E[seg - 1];
+                if (fsm_same(S0[seg], s)) break;
+                const int b0 = seg * p.L, b1 = min(b0 + p.L, p.n);
+                fsm_run(p, bits, gate, s, b0, b1);
+                E[seg] = s;
+                redone++;
+                seg++;
+            }
+            s_cur = seg;
+            atomicAdd(p.fixups + 1, redone);
+        }
+        __syncthreads();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        // gate of the last sample of the previous chunk, needed by the discriminator's first sample
+        p.prev_gate[lane] = (p.lane[lane].mode == SQ_SIGNALHI) ? 1u : 0u;
+        const FsmState e = E[p.nseg - 1];
+        p.lane[lane].mode = e.mode; p.lane[lane].timer = e.timer;
+    }
+}
+
+// apply the gate.  One thread per 32 samples.  cf32 output: closed samples become 0+0j (Liquid.chs:704).
+// Discriminator output: m[i] = arg(conj(r'[i-1]) r'[i]) with r' the GATED samples; when either neighbour is closed the
+// product is a signed zero whose argument is 0 or +-pi exactly as in the sequential code, so those values are
+// recomputed here from the sign bits of the ungated samples.
+__global__ void k_backend_gate(const BackendParams p)
+{
+    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long long)p.nlanes * p.nwords) return;
+    const int lane = (int)(t / p.nwords), w = (int)(t - (long long)lane * p.nwords);
+    const unsigned *gate = p.gatebits + (long long)lane * p.nwords;
+    const int i0 = w * 32, cnt = min(32, p.n - i0);
+    const unsigned full = (cnt == 32) ? 0xffffffffu : ((1u << cnt) - 1u);
+    const unsigned g = gate[w] & full;
+    if (p.demod != 1) {
+        if (g == full) return;
+        float2 *oc = (float2 *)p.out + (long long)lane * p.out_lane_stride + i0;
+        for (int b = 0; b < cnt; b++)
+            if (!((g >> b) & 1u)) oc[b] = cf(0.f, 0.f);
+        return;
+    }
+    const unsigned gprev = (g << 1) | (w ? (gate[w - 1] >> 31) : p.prev_gate[lane]);
+    if ((g & gprev & full) == full) return;              // every sample and its predecessor are open
+    const unsigned *sr = p.sgnr + (long long)lane * p.nwords, *si = p.sgni + (long long)lane * p.nwords;
+    const unsigned r = sr[w], im = si[w];
+    const unsigned rprev = (r << 1) | (w ? (sr[w - 1] >> 31) : (p.prev_sign[lane] & 1u));
+    const unsigned iprev = (im << 1) | (w ? (si[w - 1] >> 31) : ((p.prev_sign[lane] >> 1) & 1u));
+    float *of = (float *)p.out + (long long)lane * p.out_lane_stride + i0;
+    for (int b = 0; b < cnt; b++) {
+        const bool open = (g >> b) & 1u, popen = (gprev >> b) & 1u;
+        if (open && popen) continue;
+        // unit-magnitude stand-ins carry the signs; a closed sample is +0+0j
+        const float yr = open ? (((r >> b) & 1u) ? -1.f : 1.f) : 0.f;
+        const float yi = open ? (((im >> b) & 1u) ? -1.f : 1.f) : 0.f;
+        const float fr = popen ? (((rprev >> b) & 1u) ? -1.f : 1.f) : 0.f;
+        const float fi = popen ? (((iprev >> b) & 1u) ? -1.f : 1.f) : 0.f;
+        const float re = __fadd_rn(__fmul_rn(fr, yr), __fmul_rn(fi, yi));
+        const float ii = __fsub_rn(__fmul_rn(fr, yi), __fmul_rn(fi, yr));
+        of[b] = atan2f(ii, re) * p.fm_ref;
     }
 }
 

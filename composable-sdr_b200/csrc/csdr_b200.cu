@@ -5,6 +5,7 @@
 #include "platform.cuh"
 #include "design.hpp"
 #include "frontend.cuh"
+#include "frontend_std.cuh"
 #include "frontend_plan.hpp"
 #include "backend.cuh"
 #include "pfb.cuh"
@@ -142,6 +143,7 @@ struct Frontend {
     DevBuf bank;
     FrontendCursor cursor;
     int mix_mode = 0; uint32_t theta0 = 0, dtheta = 0; int quantize = 1;
+    void (*kernel)(FrontendParams) = k_frontend;
     // optional event timing of k_frontend (bench roofline): pairs recorded on the launching stream
     bool profile = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pending, ev_free;
@@ -173,14 +175,26 @@ struct Frontend {
             int t = 4096 >> ms.S; t = std::max(32, std::min(2048, t));
             Tc = (t + 7) / 8 * 8;
         }
-        geo = plan_frontend(ms, Tc);
+        geo = plan_frontend(ms, Tc, g_options[CSDR_OPT_GENERIC_FRONTEND] == 0);
         if (!geo.error.empty()) throw CudaError{geo.error};
+        kernel = k_frontend;
+        if (geo.std_kernel) {
+            switch (ms.S) {
+            case 1: kernel = k_frontend_std<1>; break;
+            case 2: kernel = k_frontend_std<2>; break;
+            case 3: kernel = k_frontend_std<3>; break;
+            case 4: kernel = k_frontend_std<4>; break;
+            case 5: kernel = k_frontend_std<5>; break;
+            case 6: kernel = k_frontend_std<6>; break;
+            default: throw CudaError{"frontend: no specialised kernel for this stage count"};
+            }
+        }
         nstreams = streams;
         size_t hb = (size_t)geo.hcap * sizeof(float2) * nstreams;
         for (auto &h : hist) { h.ensure(hb); CK(cudaMemsetAsync(h.p, 0, h.cap, c.stream)); }
         bank.ensure(ms.bank.size() * sizeof(float));
         CK(cudaMemcpyAsync(bank.p, ms.bank.data(), ms.bank.size() * sizeof(float), cudaMemcpyHostToDevice, c.stream));
-        CK(cudaFuncSetAttribute(k_frontend, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)geo.smem_bytes));
+        CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)geo.smem_bytes));
         c.sync();
     }
     long long max_out(long long nx) const
@@ -207,7 +221,7 @@ struct Frontend {
                 else { CK(cudaEventCreate(&ev.first)); CK(cudaEventCreate(&ev.second)); }
                 CK(cudaEventRecord(ev.first, c.stream));
             }
-            launch(k_frontend, dim3(gx, nstreams), dim3(256), geo.smem_bytes, c.stream, p);
+            launch(kernel, dim3(gx, nstreams), dim3(256), geo.smem_bytes, c.stream, p);
             if (profile) { CK(cudaEventRecord(ev.second, c.stream)); ev_pending.push_back(ev); }
         }
         if (nx > 0) {
@@ -227,8 +241,8 @@ struct Backend {
     float agc_bw = 0.1f, agc_thr = 0.f; unsigned agc_timeout = 1000; bool squelch = true, gate = true;
     float kf = 0.3f;
     int L = 512, W = 384, G = 128;
-    DevBuf lane, P, V, ss, se, flags, counts, fixups;
-    unsigned long long last_fixups = 0;
+    DevBuf lane, P, V, ss, se, fs, fe, exbits, gatebits, sgnr, sgni, prev_gate, prev_sign, fixups;
+    int FW = 3;
 
     void init(const Ctx &c, int lanes, float g0 = 1000.0f, int mode0 = SQ_ENABLED)
     {
@@ -241,8 +255,9 @@ struct Backend {
         for (auto &l : ls) { l.dc_re = l.dc_im = 0; l.g = g0; l.y2p = 1.0f; l.mode = mode0; l.timer = 0; l.fm_re = l.fm_im = 0; }
         lane.ensure(sizeof(LaneState) * nlanes);
         CK(cudaMemcpyAsync(lane.p, ls.data(), sizeof(LaneState) * nlanes, cudaMemcpyHostToDevice, c.stream));
-        counts.ensure(sizeof(unsigned) * nlanes); CK(cudaMemsetAsync(counts.p, 0, counts.cap, c.stream));
-        fixups.ensure(sizeof(unsigned long long)); CK(cudaMemsetAsync(fixups.p, 0, fixups.cap, c.stream));
+        prev_gate.ensure(sizeof(unsigned) * nlanes); CK(cudaMemsetAsync(prev_gate.p, 0, prev_gate.cap, c.stream));
+        prev_sign.ensure(sizeof(unsigned) * nlanes); CK(cudaMemsetAsync(prev_sign.p, 0, prev_sign.cap, c.stream));
+        fixups.ensure(2 * sizeof(unsigned long long)); CK(cudaMemsetAsync(fixups.p, 0, fixups.cap, c.stream));
         c.sync();
     }
     DcParams dc_params(const float2 *in, long long in_stride, float2 *out, long long out_stride, int n, int ngrp)
@@ -277,9 +292,12 @@ struct Backend {
     void run(const Ctx &c, const float2 *in, long long in_stride, void *out, long long out_stride, int n)
     {
         if (n <= 0) return;
-        int ngrp = (n + G - 1) / G, nseg = (n + L - 1) / L;
+        int ngrp = (n + G - 1) / G, nseg = (n + L - 1) / L, nwords = (n + 31) / 32;
         size_t segs = (size_t)nlanes * nseg;
-        ss.ensure(sizeof(SegState) * segs); se.ensure(sizeof(SegState) * segs); flags.ensure(sizeof(unsigned) * segs);
+        ss.ensure(sizeof(SegState) * segs); se.ensure(sizeof(SegState) * segs);
+        fs.ensure(sizeof(FsmState) * segs); fe.ensure(sizeof(FsmState) * segs);
+        exbits.ensure(sizeof(unsigned) * (size_t)nlanes * nwords); gatebits.ensure(sizeof(unsigned) * (size_t)nlanes * nwords);
+        sgnr.ensure(sizeof(unsigned) * (size_t)nlanes * nwords); sgni.ensure(sizeof(unsigned) * (size_t)nlanes * nwords);
         if (has_dc) {
             P.ensure(sizeof(double2) * (size_t)nlanes * ngrp);
             V.ensure(sizeof(double2) * (size_t)nlanes * (ngrp + 1));
@@ -296,19 +314,33 @@ struct Backend {
         b.fm_ref = (float)(1.0f / (2 * design::kPi * kf));
         b.squelch_enabled = squelch ? 1 : 0; b.gate = gate ? 1 : 0;
         b.lane = lane.as<LaneState>(); b.seg_start = ss.as<SegState>(); b.seg_end = se.as<SegState>();
-        b.dcV = V.as<double2>(); b.flags = flags.as<unsigned>(); b.counts = counts.as<unsigned>();
+        b.dcV = V.as<double2>();
+        b.nwords = nwords;
+        // the FSM forgets its entry state after timeout + 4 samples: replay that many bits (in whole segments)
+        b.FW = (int)std::min<unsigned>(64u, (agc_timeout + 8 + (unsigned)L - 1) / (unsigned)L);
+        b.exbits = exbits.as<unsigned>(); b.gatebits = gatebits.as<unsigned>();
+        b.fsm_start = fs.as<FsmState>(); b.fsm_end = fe.as<FsmState>();
+        b.prev_gate = prev_gate.as<unsigned>(); b.prev_sign = prev_sign.as<unsigned>();
+        b.sgnr = sgnr.as<unsigned>(); b.sgni = sgni.as<unsigned>();
         b.fixups = fixups.as<unsigned long long>();
         unsigned gb = (unsigned)((segs + 127) / 128);
         launch(k_backend_spec, dim3(gb), dim3(128), 0, c.stream, b);
-        launch(k_backend_verify, dim3(gb), dim3(128), 0, c.stream, b);
-        launch(k_backend_fixup, dim3(nlanes), dim3(128), 0, c.stream, b);
+        launch(k_backend_fixup, dim3(nlanes), dim3(256), 0, c.stream, b);
+        if (has_agc) {
+            launch(k_backend_fsm, dim3(gb), dim3(128), 0, c.stream, b);
+            launch(k_backend_fsm_fix, dim3(nlanes), dim3(256), 0, c.stream, b);
+            if (gate) {
+                long long words = (long long)nlanes * nwords;
+                launch(k_backend_gate, dim3((unsigned)((words + 127) / 128)), dim3(128), 0, c.stream, b);
+            }
+        }
     }
     unsigned long long read_fixups(const Ctx &c)
     {
-        unsigned long long v = 0;
-        CK(cudaMemcpyAsync(&v, fixups.p, sizeof(v), cudaMemcpyDeviceToHost, c.stream));
+        unsigned long long v[2] = {0, 0};
+        CK(cudaMemcpyAsync(v, fixups.p, sizeof(v), cudaMemcpyDeviceToHost, c.stream));
         c.sync();
-        return v;
+        return v[0] + v[1];
     }
     LaneState read_lane(const Ctx &c, int i)
     {

@@ -25,6 +25,7 @@
 // per output instead of 2m+1).
 #pragma once
 #include "platform.cuh"
+#include "frontend_geom.hpp"
 
 namespace csdr {
 
@@ -64,8 +65,6 @@ struct FrontendParams {
     int smem_bytes;
 };
 
-__device__ __forceinline__ int fe_pad(int k) { return k + (k >> 3); }   // level-0 (c) buffer: 1 pad per 8
-
 // address of sample i in a level buffer with layout factor D (power of two) and sub-array stride
 template <int D>
 __device__ __forceinline__ int fe_addr(int i, int stride)
@@ -75,8 +74,9 @@ __device__ __forceinline__ int fe_addr(int i, int stride)
 }
 __device__ __forceinline__ int fe_addr_rt(int i, int D, int stride)
 {
-    int p = i >> 1;
-    return ((i & 1) * D + (p & (D - 1))) * stride + (p / D);
+    const int p = i >> 1;
+    const int lg = (D == 8) ? 3 : (D == 4) ? 2 : (D == 2) ? 1 : 0;      // D is 1, 2, 4 or 8
+    return ((i & 1) * D + (p & (D - 1))) * stride + (p >> lg);
 }
 
 // phasor of the NCO at phase word `th`:  (cos, sin)
@@ -92,7 +92,7 @@ __device__ __forceinline__ float2 fe_phasor(unsigned th, int quantize)
 
 // One half-band decimation stage over a tile: n_out outputs, R per thread slot.
 //   out[q] = E[q+M] + sum_{u<2M} g[u] * O[q+u]       (E/O = even/odd samples of the input level)
-// LAST: write zeta*out to the padded linear c buffer, else into the next level's (D2, stride2) layout.
+// LAST: write zeta*out to the linear c buffer, else into the next level's (D2, stride2) layout.
 template <int M, int R, bool LAST>
 __device__ __forceinline__ void fe_stage(const float2 *__restrict__ in, int stride, float2 *__restrict__ out,
                                          int D2, int stride2, int n_out, const float *__restrict__ g_taps,
@@ -126,7 +126,7 @@ __device__ __forceinline__ void fe_stage(const float2 *__restrict__ in, int stri
 #pragma unroll
         for (int r = 0; r < R; r++) {
             int q = t * R + r;
-            if (LAST) out[fe_pad(q)] = cf(ar[r] * zeta, ai[r] * zeta);
+            if (LAST) out[q] = cf(ar[r] * zeta, ai[r] * zeta);
             else      out[fe_addr_rt(q, D2, stride2)] = cf(ar[r], ai[r]);
         }
     }
@@ -145,7 +145,7 @@ __device__ void fe_stage_generic(const float2 *__restrict__ in, int D, int strid
             ar = fmaf(g[u], v.x, ar);
             ai = fmaf(g[u], v.y, ai);
         }
-        if (LAST) out[fe_pad(q)] = cf(ar * zeta, ai * zeta);
+        if (LAST) out[q] = cf(ar * zeta, ai * zeta);
         else      out[fe_addr_rt(q, D2, stride2)] = cf(ar, ai);
     }
 }
@@ -220,7 +220,7 @@ __global__ void __launch_bounds__(256, 3) k_frontend(const CSDR_GRID_CONSTANT Fr
                     v = cf(v.x * w.x - v.y * s, v.y * w.x + v.x * s);
                 }
                 if (S) dst[fe_addr_rt(i, D, stride)] = v;
-                else   dst[fe_pad(i)] = v;
+                else   dst[i] = v;
             }
         }
         __syncthreads();
@@ -247,7 +247,7 @@ __global__ void __launch_bounds__(256, 3) k_frontend(const CSDR_GRID_CONSTANT Fr
                 float ar = 0.f, ai = 0.f;
 #pragma unroll
                 for (int j = 0; j < kHsub; j++) {
-                    float2 v = cbuf[fe_pad(k - j)];
+                    float2 v = cbuf[k - j];
                     ar = fmaf(h[j], v.x, ar);
                     ai = fmaf(h[j], v.y, ai);
                 }

@@ -1,0 +1,73 @@
+// frontend_geom.hpp -- tile geometry of the fused front end, as ONE constexpr function used both at compile time
+// (k_frontend_std<S>: every shared-memory address is an immediate) and at run time (generic kernel, host planning).
+//
+// Levels: level 0 = output of the half-band cascade ("c" samples, input of the arbitrary resampler);
+// level L >= 1 = input of half-band stage L-1; level S = the (mixed) raw input samples.
+// Tile t produces c indices [kA, kA+Tc); level L holds n[L] samples starting at absolute index
+// lo_L = (kA - kHcPad) * 2^L + d[L].  Half-band stage s (liquid index; s = 0 is the lowest rate) computes
+//   out[q] = in[2(q+m)+sh] + sum_{u<2m} h1[u] * in[2(q+u)+1+sh]            sh = shift of its input level
+// which is y[k] = sum_i h[i] x[2k+1-i] of resamp2.c re-indexed to the tile.
+#pragma once
+#include "platform.cuh"
+
+namespace csdr {
+
+struct FeGeom {
+    int S = 0, Tc = 0, shift = 0;
+    int m[kMaxStages] = {}, R[kMaxStages] = {};
+    int d[kMaxStages + 1] = {}, n[kMaxStages + 1] = {}, stride[kMaxStages + 1] = {}, off[kMaxStages + 1] = {};
+    int total_f2 = 0;     // float2 elements of all level buffers
+    int hcap = 0;         // raw-sample history the first tile of a chunk may reach back over
+};
+
+__host__ __device__ constexpr int ce_max(int a, int b) { return a > b ? a : b; }
+__host__ __device__ constexpr int ce_roundup(int v, int m) { return (v + m - 1) / m * m; }
+
+// shift = 1: the top level starts one sample early so that pairs (2p, 2p+1) are 16-byte aligned float4 loads when
+// the chunk is; top_mod = required (sub-array stride mod 16) of the top level for conflict-free loader stores
+// (4 for the float4 loader, 2 for the scalar loader).
+__host__ __device__ constexpr FeGeom fe_make_geom(int S, int Tc, const int *m, int shift, int top_mod)
+{
+    FeGeom g{};
+    g.S = S; g.Tc = Tc; g.shift = S > 0 ? shift : 0;
+    for (int s = 0; s < S; s++) { g.m[s] = m[s]; g.R[s] = (s == 0 && S > 1) ? 4 : 8; }
+    g.n[0] = Tc + kHcPad; g.d[0] = 0;
+    for (int L = 0; L < S; L++) {
+        const int sh = (L + 1 == S) ? g.shift : 0;
+        const int need = 2 * g.n[L] + 4 * g.m[L] - 2 + sh;
+        int mult = 2 * g.R[L];
+        if (L + 1 < S) mult = ce_max(mult, g.R[L + 1]);
+        g.n[L + 1] = ce_roundup(need, mult);
+        g.d[L + 1] = 2 * g.d[L] + 1 - 4 * g.m[L] - sh;
+    }
+    int sizeA = 0, sizeB = 0;
+    for (int L = 1; L <= S; L++) {
+        const int D = g.R[L - 1];
+        int st = g.n[L] / (2 * D) + 1;
+        if (L == S) { while ((st & 15) != top_mod) st++; }
+        g.stride[L] = st;
+        const int sz = 2 * D * st;
+        if (((S - L) & 1) == 0) sizeA = ce_max(sizeA, sz); else sizeB = ce_max(sizeB, sz);
+    }
+    const int size0 = ce_roundup(g.n[0] + 2, 2);
+    g.off[0] = 0;
+    for (int L = 1; L <= S; L++) g.off[L] = size0 + ((((S - L) & 1) == 0) ? 0 : sizeA);
+    g.total_f2 = size0 + sizeA + sizeB;
+    g.hcap = ce_roundup(((1 << S) - 1) + (kHcPad << S) - g.d[S] + 1, 64);
+    return g;
+}
+
+// the half-band plan msresamp_crcf_create(r, 60 dB) always produces (As + 5 = 65 dB per stage): m = 10, 5, 3, 3, ...
+struct FeStdM { int v[kMaxStages] = {10, 5, 3, 3, 3, 3, 3, 3, 3, 3, 3, 3}; };
+__host__ __device__ constexpr int fe_std_tc(int S)
+{
+    return S == 1 ? 1792 : S == 2 ? 896 : S == 3 ? 400 : S == 4 ? 208 : S == 5 ? 96 : 48;
+}
+__host__ __device__ constexpr FeGeom fe_make_geom_std(int S)
+{
+    FeStdM mm{};
+    return fe_make_geom(S, fe_std_tc(S), mm.v, 1, 4);
+}
+constexpr int kFeStdMaxS = 6;      // k_frontend_std is instantiated for S = 1..6
+
+}  // namespace csdr

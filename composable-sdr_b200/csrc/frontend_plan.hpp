@@ -2,6 +2,7 @@
 // csdr_b200.cu and the CPU-only emulation test.
 #pragma once
 #include "frontend.cuh"
+#include "frontend_geom.hpp"
 #include "design.hpp"
 #include <string>
 
@@ -9,6 +10,8 @@ namespace csdr {
 
 struct FrontendGeometry {
     FrontendParams base;     // geometry + taps filled in; per-call fields zero
+    FeGeom geom;
+    bool std_kernel = false; // k_frontend_std<S> applies (compile-time geometry)
     int hcap = 0;            // raw-sample history the kernel may reach back over
     size_t smem_bytes = 0;
     std::string error;
@@ -16,54 +19,39 @@ struct FrontendGeometry {
 
 inline int fe_roundup(int v, int m) { return (v + m - 1) / m * m; }
 
-// Tc: c-samples (half-band cascade outputs) per tile; multiple of 8
-inline FrontendGeometry plan_frontend(const design::MsresampPlan &ms, int Tc)
+// Tc: c-samples (half-band cascade outputs) per tile for the generic kernel; multiple of 8.  allow_std: use the
+// compile-time geometry (and its own tile size) when the half-band plan is the standard one.
+inline FrontendGeometry plan_frontend(const design::MsresampPlan &ms, int Tc, bool allow_std = true)
 {
     FrontendGeometry g{};
     FrontendParams &p = g.base;
     if (ms.interp) { g.error = "msresamp: interpolation (rate > 1) is not implemented on the GPU path"; return g; }
     if (ms.S > (unsigned)kMaxStages) { g.error = "msresamp: too many half-band stages"; return g; }
     if (2 * ms.m_arb != (unsigned)kHsub) { g.error = "msresamp: unexpected arbitrary-stage length"; return g; }
-    p.S = (int)ms.S;
+    const int S = (int)ms.S;
+    int m[kMaxStages] = {};
+    FeStdM stdm{};
+    bool is_std = allow_std && S >= 1 && S <= kFeStdMaxS;
+    for (int s = 0; s < S; s++) {
+        m[s] = (int)ms.st[s].m;
+        if (m[s] > kMaxHbM) { g.error = "msresamp: half-band stage too long"; return g; }
+        if (m[s] != stdm.v[s]) is_std = false;
+    }
+    g.std_kernel = is_std;
+    g.geom = is_std ? fe_make_geom_std(S) : fe_make_geom(S, Tc, m, 0, 2);
+    const FeGeom &G = g.geom;
+    p.S = S; p.Tc = G.Tc;
     p.zeta = 1.0f / (float)(1u << ms.S);
     p.step = ms.step; p.bits = (int)ms.bits;
-    for (int s = 0; s < p.S; s++) {
-        p.m[s] = (int)ms.st[s].m;
-        if (p.m[s] > kMaxHbM) { g.error = "msresamp: half-band stage too long"; return g; }
+    for (int s = 0; s < S; s++) {
+        p.m[s] = G.m[s]; p.R[s] = G.R[s];
         for (int u = 0; u < 2 * p.m[s]; u++) p.taps[s][u] = ms.st[s].h1[u];
-        p.R[s] = (s == 0 && p.S > 1) ? 4 : 8;
     }
-    p.Tc = Tc;
-    p.n[0] = Tc + kHcPad; p.d[0] = 0;
-    for (int L = 0; L < p.S; L++) {
-        int need = 2 * p.n[L] + 4 * p.m[L] - 2;
-        int mult = 2 * p.R[L];
-        if (L + 1 < p.S) mult = std::max(mult, p.R[L + 1]);
-        p.n[L + 1] = fe_roundup(need, mult);
-        p.d[L + 1] = 2 * p.d[L] + 1 - 4 * p.m[L];
-    }
-    // shared-memory carve-up: level 0 (c buffer, padded), then two ping-pong regions for levels >= 1
-    int size0 = p.n[0] + (p.n[0] >> 3) + 8;
-    int sizeA = 0, sizeB = 0;
-    for (int L = 1; L <= p.S; L++) {
-        int D = p.R[L - 1];
-        int st = p.n[L] / (2 * D) + 1;
-        if (L == p.S) { while ((st & 15) != 2) st++; }     // loader writes conflict-free (see frontend.cuh)
-        p.stride[L] = st;
-        int sz = 2 * D * st;
-        if (((p.S - L) & 1) == 0) sizeA = std::max(sizeA, sz); else sizeB = std::max(sizeB, sz);
-    }
-    p.stride[0] = 0;
-    p.off[0] = 0;
-    size0 = fe_roundup(size0, 2);
-    for (int L = 1; L <= p.S; L++) p.off[L] = size0 + ((((p.S - L) & 1) == 0) ? 0 : sizeA);
-    if (p.S == 0) { /* loader writes level 0 directly */ }
-    int total_f2 = size0 + sizeA + sizeB;
-    p.off_bank = 2 * total_f2;
-    g.smem_bytes = (size_t)total_f2 * 8 + (size_t)(1u << ms.bits) * (kHsub + 1) * 4;
+    for (int L = 0; L <= S; L++) { p.n[L] = G.n[L]; p.d[L] = G.d[L]; p.stride[L] = G.stride[L]; p.off[L] = G.off[L]; }
+    p.off_bank = 2 * G.total_f2;
+    g.smem_bytes = (size_t)G.total_f2 * 8 + (size_t)(1u << ms.bits) * (kHsub + 1) * 4;
     p.smem_bytes = (int)g.smem_bytes;
-    // history: n0 - lo_S(first tile) <= (2^S - 1) + (kHcPad << S) - d[S]
-    g.hcap = fe_roundup(((1 << p.S) - 1) + (kHcPad << p.S) - p.d[p.S] + 1, 64);
+    g.hcap = G.hcap;
     return g;
 }
 

@@ -1,0 +1,206 @@
+// frontend_std.cuh -- k_frontend_std<S>: the fused front end (see frontend.cuh) specialised at compile time for
+// the half-band plan msresamp_crcf_create(r, 60 dB) always produces (m = 10, 5, 3, 3, ...; the reference hard-codes
+// As = 60, apps/SoapySDR.hs:194).  The whole tile geometry is constexpr (frontend_geom.hpp), so every shared-memory
+// access is base register + immediate, loop trip counts are constants and the half-band taps are read straight
+// from the kernel-parameter constant bank by the FFMAs.  Other plans use the generic k_frontend.
+//
+// Per input sample the kernel issues ~13 instructions in the loader (one LDG.128 per two samples, phase IMAD,
+// I2F, FMUL, two MUFU, four FP for the complex rotation, STS.64), ~17 FFMA + ~3 LDS.64 in the half-band cascade and
+// ~5 in the arbitrary resampler.
+#pragma once
+#include "frontend.cuh"
+
+namespace csdr {
+
+template <int S> struct FeStd { static constexpr FeGeom G = fe_make_geom_std(S); };
+
+__device__ __forceinline__ float4 fe_ldg_stream(const float4 *p)
+{
+#ifdef CSDR_EMU
+    return *p;
+#else
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+#endif
+}
+
+// v * conj(phasor) (down) or v * phasor (up)
+template <int MIX>
+__device__ __forceinline__ float2 fe_mix(float2 v, unsigned th, int quantize)
+{
+    if (MIX == 0) return v;
+    const float2 w = fe_phasor(th, quantize);
+    const float s = (MIX == 1) ? -w.y : w.y;
+    return cf(v.x * w.x - v.y * s, v.y * w.x + v.x * s);
+}
+
+// ---- top level: global -> (mix) -> shared, in the consumer's de-interleaved layout -------------------------
+template <int S, int MIX>
+__device__ __forceinline__ void fe_load_top(const FrontendParams &p, const float2 *__restrict__ xs,
+                                            const float2 *__restrict__ hs, float2 *__restrict__ dst, long long lo)
+{
+    constexpr FeGeom G = FeStd<S>::G;
+    constexpr int NS = G.n[S], STR = G.stride[S], D = G.R[S - 1];
+    static_assert(D == 8 && NS % 2 == 0, "loader assumes an 8-way layout of the top level");
+    const int tid = threadIdx.x;
+    const long long rel0 = lo - p.n0;
+    const unsigned th0 = p.theta0 + (unsigned)lo * p.dtheta;
+    const bool inside = rel0 >= 0 && rel0 + NS <= p.nx;
+    if (inside && ((reinterpret_cast<uintptr_t>(xs + rel0) & 15) == 0)) {
+        // fast path: one 16-byte load = the (even, odd) pair p; pair -> sub-array p & 7, index p >> 3
+        const float4 *src = reinterpret_cast<const float4 *>(xs + rel0);
+        float2 *dE = dst + (tid & 7) * STR + (tid >> 3);
+        float2 *dO = dE + D * STR;
+        constexpr int NP = NS / 2, IT = (NP + 255) / 256;
+#pragma unroll 4
+        for (int k = 0; k < IT; k++) {
+            const int pi = tid + 256 * k;
+            if (pi < NP) {
+                const float4 v = fe_ldg_stream(src + pi);
+                const unsigned th = th0 + (unsigned)(2 * pi) * p.dtheta;
+                dE[32 * k] = fe_mix<MIX>(cf(v.x, v.y), th, p.quantize);
+                dO[32 * k] = fe_mix<MIX>(cf(v.z, v.w), th + p.dtheta, p.quantize);
+            }
+        }
+    } else if (inside) {
+        // chunk not 16-byte aligned at this tile: 8-byte loads, sample i -> plane i & 1, pair i >> 1
+        const float2 *src = xs + rel0;
+        float2 *d0 = dst + ((tid & 1) * D + ((tid >> 1) & 7)) * STR + (tid >> 4);
+        constexpr int IT = (NS + 255) / 256;
+#pragma unroll 4
+        for (int k = 0; k < IT; k++) {
+            const int i = tid + 256 * k;
+            if (i < NS) d0[16 * k] = fe_mix<MIX>(src[i], th0 + (unsigned)i * p.dtheta, p.quantize);
+        }
+    } else {
+        // edge tile: samples before the chunk come from the carried history, samples after it are zero
+        for (int i = tid; i < NS; i += 256) {
+            const long long rel = rel0 + i;
+            float2 v = cf(0.f, 0.f);
+            if (rel >= 0) { if (rel < p.nx) v = xs[rel]; }
+            else if (rel >= -(long long)p.hcap) v = hs[p.hcap + rel];
+            dst[fe_addr<D>(i, STR)] = fe_mix<MIX>(v, th0 + (unsigned)i * p.dtheta, p.quantize);
+        }
+    }
+}
+
+// ---- one half-band stage with compile-time geometry --------------------------------------------------------
+//   out[q] = C[q+M] + sum_{u<2M} g[u] * T[q+u+SH]     T/C = tap/centre planes (odd/even samples; swapped when the
+//   input level is shifted by one sample), R consecutive outputs per thread slot
+template <int M, int R, int STR, int SH, int NOUT, bool LAST, int D2, int STR2>
+__device__ __forceinline__ void fe_stage_c(const float2 *__restrict__ in, float2 *__restrict__ out,
+                                           const float *__restrict__ g, float zeta)
+{
+    const float2 *T = in + (SH ? 0 : R * STR);
+    const float2 *C = in + (SH ? R * STR : 0);
+    constexpr int NSLOTS = NOUT / R;
+    for (int t = threadIdx.x; t < NSLOTS; t += 256) {
+        float ar[R], ai[R];
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            const float2 e = C[((M + r) % R) * STR + t + (M + r) / R];
+            ar[r] = e.x; ai[r] = e.y;
+        }
+#pragma unroll
+        for (int c = 0; c < R + 2 * M - 1; c++) {
+            const float2 v = T[((c + SH) % R) * STR + t + (c + SH) / R];
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                const int u = c - r;
+                if (u >= 0 && u < 2 * M) {
+                    ar[r] = fmaf(g[u], v.x, ar[r]);
+                    ai[r] = fmaf(g[u], v.y, ai[r]);
+                }
+            }
+        }
+        if constexpr (LAST) {
+            float2 *o = out + t * R;
+#pragma unroll
+            for (int r = 0; r < R; r++) o[r] = cf(ar[r] * zeta, ai[r] * zeta);
+        } else {
+            // q = R t + r -> plane r & 1, pair p = (R/2) t + (r >> 1) -> sub-array p & (D2-1), index p / D2
+            static_assert(R == 8 && (D2 == 8 || D2 == 4), "store pattern written for R = 8 producers");
+            float2 *o = (D2 == 8) ? out + ((t & 1) << 2) * STR2 + (t >> 1) : out + t;
+#pragma unroll
+            for (int r = 0; r < R; r++) o[((r & 1) * D2 + (r >> 1)) * STR2] = cf(ar[r], ai[r]);
+        }
+    }
+}
+
+template <int S, int s>
+__device__ __forceinline__ void fe_run_stages(const FrontendParams &p, float2 *smem)
+{
+    constexpr FeGeom G = FeStd<S>::G;
+    constexpr bool LAST = (s == 0);
+    constexpr int D2 = LAST ? 1 : G.R[LAST ? 0 : s - 1];
+    constexpr int SH = (s == S - 1) ? G.shift : 0;
+    fe_stage_c<G.m[s], G.R[s], G.stride[s + 1], SH, G.n[s], LAST, D2, G.stride[s]>(
+        smem + G.off[s + 1], smem + G.off[s], p.taps[s], p.zeta);
+    __syncthreads();
+    if constexpr (s > 0) fe_run_stages<S, s - 1>(p, smem);
+}
+
+template <int S>
+__global__ void __launch_bounds__(256, 3) k_frontend_std(const CSDR_GRID_CONSTANT FrontendParams p)
+{
+    constexpr FeGeom G = FeStd<S>::G;
+    CSDR_DYN_SMEM(smem_raw);
+    float2 *smem = reinterpret_cast<float2 *>(smem_raw);
+    float *bank_s = reinterpret_cast<float *>(smem_raw) + 2 * G.total_f2;
+    __shared__ int s_orange[2];
+
+    const int npfb = 1 << p.bits;
+    for (int i = threadIdx.x; i < npfb * kHsub; i += 256) {
+        const int row = i / kHsub, col = i - row * kHsub;
+        bank_s[row * (kHsub + 1) + col] = p.bank[i];
+    }
+    const float2 *xs = p.x + (long long)blockIdx.y * p.x_stride;
+    const float2 *hs = p.hist + (long long)blockIdx.y * p.hcap;
+    float2 *ys = p.y + (long long)blockIdx.y * p.y_stride;
+    const unsigned mask = (unsigned)npfb - 1u;
+    const int sh = 24 - p.bits;
+
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+        const long long kArel = (long long)tile * G.Tc;                 // pushes relative to K0
+        const long long kBrel = min(kArel + (long long)G.Tc, p.K1 - p.K0);
+        const long long c_lo = p.K0 + kArel - kHcPad;
+        if (threadIdx.x == 0) {
+            // outputs emitted by pushes [kA, kB): o' with kArel*2^24 <= ph0 + o'*step < kBrel*2^24
+            const unsigned long long st = p.step;
+            const unsigned long long a = (unsigned long long)kArel << 24, b = (unsigned long long)kBrel << 24;
+            s_orange[0] = (a > p.ph0) ? (int)((a - p.ph0 + st - 1) / st) : 0;
+            s_orange[1] = (b > p.ph0) ? (int)((b - p.ph0 + st - 1) / st) : 0;
+        }
+        const long long lo = c_lo * (1LL << S) + G.d[S];
+        if (p.mix_mode == 1)      fe_load_top<S, 1>(p, xs, hs, smem + G.off[S], lo);
+        else if (p.mix_mode == 2) fe_load_top<S, 2>(p, xs, hs, smem + G.off[S], lo);
+        else                      fe_load_top<S, 0>(p, xs, hs, smem + G.off[S], lo);
+        __syncthreads();
+
+        fe_run_stages<S, S - 1>(p, smem);
+
+        // arbitrary resampler: output o' -> push k = (ph0 + o'*step) >> 24, branch = next `bits` bits of the phase
+        {
+            const float2 *cbuf = smem + G.off[0] + kHcPad - (int)kArel;   // cbuf[k] for k relative to K0
+            const int oA = s_orange[0], oB = s_orange[1];
+            for (int o = oA + threadIdx.x; o < oB; o += 256) {
+                const unsigned long long ph = p.ph0 + (unsigned long long)(unsigned)o * p.step;
+                const float2 *c = cbuf + (int)(ph >> 24);
+                const float *h = bank_s + ((unsigned)(ph >> sh) & mask) * (kHsub + 1);
+                float ar = 0.f, ai = 0.f;
+#pragma unroll
+                for (int j = 0; j < kHsub; j++) {
+                    const float2 v = c[-j];
+                    ar = fmaf(h[j], v.x, ar);
+                    ai = fmaf(h[j], v.y, ai);
+                }
+                ys[o] = cf(ar, ai);
+            }
+        }
+        __syncthreads();   // smem is reused by the next tile
+    }
+}
+
+}  // namespace csdr

@@ -3,6 +3,7 @@
 // Built by tests/emu/build.py with g++ -DCSDR_EMU; never part of libcsdr_b200.so.
 #include "cuda_emu.h"
 #include "frontend.cuh"
+#include "frontend_std.cuh"
 #include "frontend_plan.hpp"
 #include "backend.cuh"
 #include <vector>
@@ -16,10 +17,27 @@ extern "C" {
 // Returns total outputs written to y (capacity cap), or -1.
 long long emu_frontend(float rate, float As, int mix_mode, float freq, int quantize, int Tc, int nthreads,
                        const float2 *x, long long n, const long long *chunks, int nchunks, float2 *y, long long cap,
-                       unsigned long long seek)
+                       unsigned long long seek, int allow_std, long long misalign)
 {
     design::MsresampPlan ms = design::plan_msresamp(rate, As);
-    FrontendGeometry g = plan_frontend(ms, Tc);
+    FrontendGeometry g = plan_frontend(ms, Tc, allow_std != 0);
+    void (*kernel)(FrontendParams) = k_frontend;
+    if (g.std_kernel) {
+        nthreads = 256;
+        switch (ms.S) {
+        case 1: kernel = k_frontend_std<1>; break;
+        case 2: kernel = k_frontend_std<2>; break;
+        case 3: kernel = k_frontend_std<3>; break;
+        case 4: kernel = k_frontend_std<4>; break;
+        case 5: kernel = k_frontend_std<5>; break;
+        default: kernel = k_frontend_std<6>; break;
+        }
+    }
+    // the caller's buffer is copied to a 16-byte aligned (or deliberately misaligned) one: exercises both loaders
+    std::vector<float2> xbuf((size_t)n + 4);
+    float2 *xa = (float2 *)(((uintptr_t)xbuf.data() + 15) & ~(uintptr_t)15) + misalign;
+    memcpy(xa, x, (size_t)n * sizeof(float2));
+    x = xa;
     if (!g.error.empty()) { fprintf(stderr, "%s\n", g.error.c_str()); return -1; }
     std::vector<float2> hist[2];
     hist[0].assign(g.hcap, make_float2(0, 0)); hist[1] = hist[0];
@@ -37,7 +55,7 @@ long long emu_frontend(float rate, float As, int mix_mode, float freq, int quant
         p.mix_mode = mix_mode; p.theta0 = 0; p.dtheta = design::nco_constrain(freq); p.quantize = quantize;
         p.bank = ms.bank.data();
         if (p.ntiles > 0)
-            csdr_emu::launch(dim3(std::min(p.ntiles, 3)), dim3(nthreads), g.smem_bytes, k_frontend, p);
+            csdr_emu::launch(dim3(std::min(p.ntiles, 3)), dim3(nthreads), g.smem_bytes, kernel, p);
         csdr_emu::launch(dim3((g.hcap + 127) / 128), dim3(128), 0, k_hist_update, (const float2 *)hist[cur_h].data(),
                          hist[cur_h ^ 1].data(), x + pos, 0LL, nx, g.hcap);
         cur_h ^= 1;
@@ -53,7 +71,7 @@ long long emu_backend(int nlanes, long long lane_stride, int has_dc, float dc_al
 {
     std::vector<LaneState> lane(nlanes);
     for (auto &l : lane) { l.dc_re = l.dc_im = 0; l.g = 1000.0f; l.y2p = 1.0f; l.mode = SQ_ENABLED; l.timer = 0; l.fm_re = l.fm_im = 0; }
-    unsigned long long fixups = 0;
+    unsigned long long fixups2[2] = {0, 0};
     long long pos = 0;
     for (int c = 0; c < nchunks; c++) {
         int nx = (int)chunks[c];
@@ -61,7 +79,10 @@ long long emu_backend(int nlanes, long long lane_stride, int has_dc, float dc_al
         int ngrp = (nx + G - 1) / G, nseg = (nx + L - 1) / L;
         std::vector<double2> P((size_t)nlanes * ngrp), V((size_t)nlanes * (ngrp + 1));
         std::vector<SegState> ss((size_t)nlanes * nseg), se((size_t)nlanes * nseg);
-        std::vector<unsigned> flags((size_t)nlanes * nseg), counts(nlanes, 0);
+        std::vector<FsmState> fs((size_t)nlanes * nseg), fe((size_t)nlanes * nseg);
+        int nwords = (nx + 31) / 32;
+        std::vector<unsigned> exb((size_t)nlanes * nwords), gb((size_t)nlanes * nwords), pg(nlanes, 0), ps(nlanes, 0);
+        std::vector<unsigned> sgr((size_t)nlanes * nwords), sgi((size_t)nlanes * nwords);
         DcParams d{};
         d.in = x + pos; d.in_lane_stride = lane_stride; d.n = nx; d.nlanes = nlanes; d.G = G; d.ngrp = ngrp;
         d.a1 = -1.0f + dc_alpha; d.c = -(double)d.a1; d.P = P.data(); d.V = V.data(); d.lane = lane.data();
@@ -79,13 +100,19 @@ long long emu_backend(int nlanes, long long lane_stride, int has_dc, float dc_al
         b.g_thr = design::agc_gain_threshold(thr_db); b.timeout = 1000; b.fm_ref = (float)(1.0f / (2 * design::kPi * kf));
         b.squelch_enabled = 1; b.gate = 1;
         b.lane = lane.data(); b.seg_start = ss.data(); b.seg_end = se.data(); b.dcV = V.data();
-        b.flags = flags.data(); b.counts = counts.data(); b.fixups = &fixups;
+        b.nwords = nwords; b.FW = (1000 + 8 + L - 1) / L;
+        b.exbits = exb.data(); b.gatebits = gb.data(); b.fsm_start = fs.data(); b.fsm_end = fe.data();
+        b.prev_gate = pg.data(); b.prev_sign = ps.data(); b.sgnr = sgr.data(); b.sgni = sgi.data(); b.fixups = fixups2;
         csdr_emu::launch(dim3((nlanes * nseg + 31) / 32), dim3(32), 0, k_backend_spec, b);
-        csdr_emu::launch(dim3((nlanes * nseg + 31) / 32), dim3(32), 0, k_backend_verify, b);
         csdr_emu::launch(dim3(nlanes), dim3(32), 0, k_backend_fixup, b);
+        if (has_agc) {
+            csdr_emu::launch(dim3((nlanes * nseg + 31) / 32), dim3(32), 0, k_backend_fsm, b);
+            csdr_emu::launch(dim3(nlanes), dim3(32), 0, k_backend_fsm_fix, b);
+            csdr_emu::launch(dim3((nlanes * nwords + 31) / 32), dim3(32), 0, k_backend_gate, b);
+        }
         pos += nx;
     }
-    if (fixups_out) *fixups_out = fixups;
+    if (fixups_out) { fixups_out[0] = fixups2[0]; fixups_out[1] = fixups2[1]; }
     return pos;
 }
 

@@ -14,7 +14,7 @@ def load():
         L = C.CDLL(_build.build())
         L.emu_frontend.restype = C.c_longlong
         L.emu_frontend.argtypes = [C.c_float, C.c_float, C.c_int, C.c_float, C.c_int, C.c_int, C.c_int, C.c_void_p,
-                                   C.c_longlong, C.c_void_p, C.c_int, C.c_void_p, C.c_longlong, C.c_ulonglong]
+                                   C.c_longlong, C.c_void_p, C.c_int, C.c_void_p, C.c_longlong, C.c_ulonglong, C.c_int, C.c_longlong]
         L.emu_backend.restype = C.c_longlong
         L.emu_backend.argtypes = [C.c_int, C.c_longlong, C.c_int, C.c_float, C.c_int, C.c_float, C.c_int, C.c_float,
                                   C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_longlong, C.c_void_p, C.c_int, C.c_void_p,
@@ -37,14 +37,15 @@ class Emu:
     def __init__(self, L):
         self.L = L
 
-    def frontend(self, x, rate, As=60.0, mix_mode=1, freq=0.0, quantize=1, Tc=64, nthreads=64, chunks=None, seek=0):
+    def frontend(self, x, rate, As=60.0, mix_mode=1, freq=0.0, quantize=1, Tc=64, nthreads=64, chunks=None, seek=0,
+                 std=True, misalign=0):
         x = np.ascontiguousarray(x, np.complex64)
         chunks = [x.size] if chunks is None else list(chunks)
         ch = np.array(chunks, np.int64)
         cap = int(2 * np.ceil(rate * x.size)) + 64
         y = np.zeros(cap, np.complex64)
         n = self.L.emu_frontend(rate, As, mix_mode, freq, quantize, Tc, nthreads, x.ctypes.data, x.size, ch.ctypes.data,
-                                len(chunks), y.ctypes.data, cap, seek)
+                                len(chunks), y.ctypes.data, cap, seek, int(std), misalign)
         assert n >= 0, "emu_frontend failed"
         return y[:n]
 
@@ -54,10 +55,10 @@ class Emu:
         chunks = [n] if chunks is None else list(chunks)
         ch = np.array(chunks, np.int64)
         out = np.zeros((nlanes, n), np.float32 if demod else np.complex64)
-        fx = C.c_ulonglong(0)
+        fx = (C.c_ulonglong * 2)(0, 0)
         self.L.emu_backend(nlanes, n, has_dc, 0.0005, has_agc, thr, demod, kf, L, W, G, x.ctypes.data, n, ch.ctypes.data,
-                           len(chunks), out.ctypes.data, C.byref(fx))
-        return out, fx.value
+                           len(chunks), out.ctypes.data, fx)
+        return out, (fx[0], fx[1])
 
     def design_msresamp(self, rate, As=60.0):
         S, step, npfb = C.c_uint(0), C.c_uint(0), C.c_uint(0)

@@ -39,9 +39,9 @@ def test_agc_threshold_is_exact_boundary(orc, emu):
 
 
 def test_frontend_geometry(emu):
-    S, n, d, hcap, smem = emu.geometry(0.078125, 60.0, 464)
+    S, n, d, hcap, smem = emu.geometry(0.078125, 60.0, 464)       # standard plan -> compile-time geometry
     assert S == 3
-    assert d == [0, -39, -97, -205]                       # lo_L = (c_lo << L) + d[L]
-    assert n[0] == 480 and all(v % 8 == 0 for v in n)
-    assert hcap >= 7 + (16 << 3) + 205
+    assert d == [0, -39, -97, -206]                       # lo_L = (c_lo << L) + d[L]; top level shifted by one
+    assert n[0] == 416 and all(v % 8 == 0 for v in n)
+    assert hcap >= 7 + (16 << 3) + 206
     assert smem <= 75 * 1024                              # 3 CTAs / SM

@@ -7,25 +7,32 @@ import pytest
 from util import assert_parity, make_signal
 
 
-@pytest.mark.parametrize("rate,As,Tc,nthreads,mix", [
-    (0.078125, 60.0, 464, 256, 1), (0.078125, 60.0, 64, 64, 2), (0.02, 60.0, 128, 128, 1),
-    (0.625, 60.0, 256, 128, 0), (0.078125, 40.0, 64, 64, 1), (0.078125, 80.0, 64, 64, 0)])
-def test_frontend_matches_oracle(orc, emu, rate, As, Tc, nthreads, mix):
-    x = make_signal(24000, 7)
+@pytest.mark.parametrize("rate,As,Tc,nthreads,mix,std", [
+    (0.078125, 60.0, 464, 256, 1, False), (0.078125, 60.0, 64, 64, 2, False), (0.02, 60.0, 128, 128, 1, False),
+    (0.625, 60.0, 256, 128, 0, False), (0.078125, 40.0, 64, 64, 1, True), (0.078125, 80.0, 64, 64, 0, True),
+    # compile-time-geometry kernel k_frontend_std<S>, S = 1..6
+    (0.3, 60.0, 0, 256, 1, True), (0.2, 60.0, 0, 256, 2, True), (0.078125, 60.0, 0, 256, 1, True),
+    (0.04, 60.0, 0, 256, 0, True), (0.02, 60.0, 0, 256, 1, True), (0.011, 60.0, 0, 256, 1, True)])
+def test_frontend_matches_oracle(orc, emu, rate, As, Tc, nthreads, mix, std):
+    x = make_signal(40000, 7)
     f = float(np.float32(0.24543693))
     xm = {0: lambda v: v, 1: orc.Nco(f).mix_down, 2: orc.Nco(f).mix_up}[mix](x)
     ref = orc.MsResamp(rate, As).execute(xm)
-    y = emu.frontend(x, rate, As=As, mix_mode=mix, freq=f, Tc=Tc, nthreads=nthreads)
+    y = emu.frontend(x, rate, As=As, mix_mode=mix, freq=f, Tc=Tc, nthreads=nthreads, std=std)
     assert_parity(y, ref, what="frontend")
+    if std:
+        # 8-byte aligned chunk: the scalar loader path must give the same bits as the float4 path
+        assert np.array_equal(emu.frontend(x, rate, As=As, mix_mode=mix, freq=f, Tc=Tc, nthreads=nthreads, misalign=1), y)
 
 
 def test_frontend_chunk_invariance_is_bit_exact(emu):
     x = make_signal(20000, 8)
-    a = emu.frontend(x, 0.078125, freq=0.3)
     sizes = [1, 7, 1000, 3, 4096, 5000]
     sizes.append(len(x) - sum(sizes))
-    b = emu.frontend(x, 0.078125, freq=0.3, chunks=sizes)
-    assert np.array_equal(a, b)
+    for std in (False, True):
+        a = emu.frontend(x, 0.078125, freq=0.3, std=std)
+        b = emu.frontend(x, 0.078125, freq=0.3, chunks=sizes, std=std)
+        assert np.array_equal(a, b)
 
 
 def test_frontend_seek_with_warmup(orc, emu):
