@@ -5,9 +5,9 @@
 // for `nlanes` independent sample sequences (streams or channelizer channels) of n samples each.
 //
 // Parallelisation over TIME (the reference is one sequential loop per stream):
-//   * dc blocker: a linear recurrence.  k_dc_partial reduces every G-sample group to its zero-state response,
-//     k_dc_scan composes the groups (one CTA per lane, fp64) and yields the exact filter state at every group
-//     boundary; consumers restart the float32 recurrence from those states.
+//   * dc blocker: a linear recurrence.  k_dc_local reduces every G-sample group to its zero-state response and
+//     scans the groups of a CTA, k_dc_carry chains the CTAs (fp64): the exact filter state at every group boundary
+//     is then one multiply-add away, and consumers restart the float32 recurrence from those states.
 //   * AGC + squelch: the gain loop is contractive, so L-sample segments are run speculatively after a W-sample
 //     warm-up and verified against their predecessors; the squelch state machine never feeds back into the gain
 //     and is resolved EXACTLY afterwards on one threshold bit per sample; the gate is applied last as a mask.
@@ -36,14 +36,14 @@ struct BackendParams {
     int L, W, G, nseg, ngrp;
     int has_dc, has_agc, demod;                // demod: 0 none (cf32 out), 1 fm (float out)
     float dc_a1;                               // a[1] = -1 + alpha_dc
-    float alpha; double one_minus_alpha; float neg_half_alpha;
+    float alpha; float one_minus_alpha_f; float neg_half_alpha;
     float g_thr;                               // rssi > threshold  <=>  g < g_thr  (bisected on the host)
     unsigned timeout; float fm_ref;
     int squelch_enabled;
     int gate;                                  // 1: zero the output unless squelch status == SIGNALHI (Liquid.chs:700-704)
     LaneState *lane;
     SegState *seg_start, *seg_end;             // [nlanes][nseg] gain-loop state at segment boundaries
-    const double2 *dcV;                        // [nlanes][ngrp+1] dc state at group boundaries
+    const double2 *dcVloc, *dcCarry; const double *dcPowA; int nblk;   // dc state at group boundaries (see dc blocker)
     int nwords, FW;                            // 32-sample words per lane; FSM replay length in segments
     unsigned *exbits, *gatebits;               // [nlanes][nwords] threshold-exceeded / gate-open bit per sample
     unsigned *sgnr, *sgni;                     // [nlanes][nwords] sign bits of the ungated agc output (discriminator
@@ -51,59 +51,62 @@ struct BackendParams {
     unsigned *prev_sign;                       // [nlanes] sign bits (re | im << 1) of the sample before this chunk
     FsmState *fsm_start, *fsm_end;      // [nlanes][nseg]
     unsigned *prev_gate;                       // [nlanes] gate of the sample before this chunk
+    unsigned *first_bad;                       // [nlanes][2] first segment whose start state does not continue its
+                                               // predecessor (gain loop, squelch FSM); 0xffffffff = none
     unsigned long long *fixups;                // [2] segments re-run: gain loop, squelch FSM (diagnostic)
 };
 
 // ------------------------------------------------------------------------------------------ dc blocker
+// v[n] = x[n] + c v[n-1] (c = 1 - alpha), y[n] = v[n] - v[n-1].  The state at every G-sample group boundary is
+//   V(j) = Vloc[j-1] + carry[b] * A^k ,   A = c^G, b = (j-1) / kDcGB, k = (j-1) % kDcGB + 1
+// Vloc = in-block inclusive scan of the groups' zero-state responses (k_dc_local, one group per thread, kDcGB
+// groups per CTA), carry[b] = state at the start of block b (k_dc_carry, sequential over the few blocks), all fp64.
+constexpr int kDcGB = 256;
+
 struct DcParams {
     const float2 *in; long long in_lane_stride;
     float2 *out; long long out_lane_stride;
-    int n, nlanes, G, ngrp;
+    int n, nlanes, G, ngrp, nblk;
     double c;                                  // 1 - alpha  (= -a1)
     float a1;
-    double2 *P;                                // [nlanes][ngrp] zero-state group responses
-    double2 *V;                                // [nlanes][ngrp+1] state at group boundaries
+    double2 *Vloc;                             // [nlanes][ngrp]  block-local state at the END of group j
+    double2 *carry;                            // [nlanes][nblk]  state at the start of block b
+    const double *powA;                        // [kDcGB + 1]     A^k
     LaneState *lane;
 };
 
-__global__ void k_dc_partial(const DcParams p)
+__device__ __forceinline__ double2 dc_state_at(const double2 *Vloc, const double2 *carry, const double *powA,
+                                               int ngrp, int nblk, int lane, int j)
 {
-    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= (long long)p.nlanes * p.ngrp) return;
-    int lane = (int)(t / p.ngrp), j = (int)(t - (long long)lane * p.ngrp);
-    const float2 *x = p.in + (long long)lane * p.in_lane_stride;
-    int i0 = j * p.G, i1 = min(i0 + p.G, p.n);
-    double ar = 0.0, ai = 0.0;
-    for (int i = i0; i < i1; i++) {
-        float2 v = x[i];
-        ar = ar * p.c + (double)v.x;
-        ai = ai * p.c + (double)v.y;
-    }
-    // a short last group is completed with zero input so that every group advances the state by c^G
-    for (int i = i1; i < i0 + p.G; i++) { ar *= p.c; ai *= p.c; }
-    p.P[t] = make_double2(ar, ai);
+    // filter state before group j (= after j groups)
+    const double2 *cl = carry + (long long)lane * nblk;
+    if (j == 0) return cl[0];
+    const int b = (j - 1) / kDcGB, k = (j - 1) - b * kDcGB + 1;
+    const double2 v = Vloc[(long long)lane * ngrp + (j - 1)], cb = cl[b];
+    const double a = powA[k];
+    return make_double2(v.x + cb.x * a, v.y + cb.y * a);
 }
 
-// one CTA per lane: V[j+1] = c^G V[j] + P[j], V[0] = carried state.  Chunked Hillis-Steele scan in fp64.
-__global__ void k_dc_scan(const DcParams p)
+__global__ void __launch_bounds__(kDcGB) k_dc_local(const DcParams p)
 {
-    const int lane = blockIdx.x, T = blockDim.x, t = threadIdx.x;
-    __shared__ double sr[1024], si[1024];
-    const double2 *P = p.P + (long long)lane * p.ngrp;
-    double2 *V = p.V + (long long)lane * (p.ngrp + 1);
-    const int q = (p.ngrp + T - 1) / T;                  // groups per thread
-    double A = 1.0;                                      // c^G
-    for (int i = 0; i < p.G; i++) A *= p.c;
-    const int j0 = min(t * q, p.ngrp), j1 = min(j0 + q, p.ngrp);
+    __shared__ double sr[kDcGB], si[kDcGB];
+    const int lane = blockIdx.y, t = threadIdx.x, j = blockIdx.x * kDcGB + t;
+    const float2 *x = p.in + (long long)lane * p.in_lane_stride;
     double ar = 0.0, ai = 0.0;
-    for (int j = j0; j < j1; j++) { ar = ar * A + P[j].x; ai = ai * A + P[j].y; }
-    double Aq = 1.0;                                     // A^q (a thread that owns fewer groups is padded with zeros)
-    for (int i = 0; i < q; i++) Aq *= A;
-    for (int j = j1; j < j0 + q; j++) { ar *= A; ai *= A; }
+    if (j < p.ngrp) {
+        const int i0 = j * p.G, i1 = min(i0 + p.G, p.n);
+        for (int i = i0; i < i1; i++) {
+            const float2 v = x[i];
+            ar = ar * p.c + (double)v.x;
+            ai = ai * p.c + (double)v.y;
+        }
+        // a short last group is completed with zero input so that every group advances the state by c^G
+        for (int i = i1; i < i0 + p.G; i++) { ar *= p.c; ai *= p.c; }
+    }
     sr[t] = ar; si[t] = ai;
     __syncthreads();
-    double f = Aq;
-    for (int d = 1; d < T; d <<= 1) {
+    double f = p.powA[1];
+    for (int d = 1; d < kDcGB; d <<= 1) {
         double vr = 0.0, vi = 0.0;
         if (t >= d) { vr = sr[t - d] * f; vi = si[t - d] * f; }
         __syncthreads();
@@ -111,20 +114,40 @@ __global__ void k_dc_scan(const DcParams p)
         __syncthreads();
         f *= f;
     }
-    // exclusive prefix for this thread + decayed carried state
-    double v0r = (double)p.lane[lane].dc_re, v0i = (double)p.lane[lane].dc_im;
-    double pw = 1.0;                                     // Aq^t
-    { double b = Aq; int e = t; while (e) { if (e & 1) pw *= b; b *= b; e >>= 1; } }
-    double wr = v0r * pw + (t ? sr[t - 1] : 0.0), wi = v0i * pw + (t ? si[t - 1] : 0.0);
-    if (t == 0) V[0] = make_double2(v0r, v0i);
-    for (int j = j0; j < j1; j++) {
-        wr = wr * A + P[j].x; wi = wi * A + P[j].y;
-        V[j + 1] = make_double2(wr, wi);
+    if (j < p.ngrp) p.Vloc[(long long)lane * p.ngrp + j] = make_double2(sr[t], si[t]);
+}
+
+// one thread per lane: carries of the (few) blocks, then the state after the last sample goes into the lane state
+__global__ void k_dc_carry(const DcParams p)
+{
+    const int lane = blockIdx.x * blockDim.x + threadIdx.x;
+    if (lane >= p.nlanes) return;
+    double2 *cl = p.carry + (long long)lane * p.nblk;
+    double cr = (double)p.lane[lane].dc_re, ci = (double)p.lane[lane].dc_im;
+    const double AB = p.powA[kDcGB];
+    for (int b = 0; b < p.nblk; b++) {
+        cl[b] = make_double2(cr, ci);
+        const int jl = min((b + 1) * kDcGB, p.ngrp) - 1;       // last group of block b
+        if (jl == (b + 1) * kDcGB - 1) {
+            const double2 v = p.Vloc[(long long)lane * p.ngrp + jl];
+            cr = cr * AB + v.x; ci = ci * AB + v.y;
+        }
     }
+    // state after n samples: restart from the last full-group boundary
+    const int jf = p.n / p.G;
+    const double2 v = dc_state_at(p.Vloc, p.carry, p.powA, p.ngrp, p.nblk, lane, jf);
+    float v1r = (float)v.x, v1i = (float)v.y;
+    const float2 *x = p.in + (long long)lane * p.in_lane_stride;
+    for (int i = jf * p.G; i < p.n; i++) {
+        const float2 s = x[i];
+        v1r = __fsub_rn(s.x, __fmul_rn(p.a1, v1r));
+        v1i = __fsub_rn(s.y, __fmul_rn(p.a1, v1i));
+    }
+    p.lane[lane].dc_re = v1r; p.lane[lane].dc_im = v1i;
 }
 
 // stand-alone dc blocker output (iirfilt_crcf_execute_block): one thread per group restarts the float32
-// recurrence from the exact boundary state.
+// recurrence from the exact boundary state.  May run in place (k_dc_carry has already read what it needs).
 __global__ void k_dc_apply(const DcParams p)
 {
     long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -132,7 +155,7 @@ __global__ void k_dc_apply(const DcParams p)
     int lane = (int)(t / p.ngrp), j = (int)(t - (long long)lane * p.ngrp);
     const float2 *x = p.in + (long long)lane * p.in_lane_stride;
     float2 *y = p.out + (long long)lane * p.out_lane_stride;
-    double2 v = p.V[(long long)lane * (p.ngrp + 1) + j];
+    const double2 v = dc_state_at(p.Vloc, p.carry, p.powA, p.ngrp, p.nblk, lane, j);
     float v1r = (float)v.x, v1i = (float)v.y;
     int i0 = j * p.G, i1 = min(i0 + p.G, p.n);
     for (int i = i0; i < i1; i++) {
@@ -142,24 +165,6 @@ __global__ void k_dc_apply(const DcParams p)
         y[i] = cf(__fsub_rn(v0r, v1r), __fsub_rn(v0i, v1i));
         v1r = v0r; v1i = v0i;
     }
-}
-
-// store the dc state after the last sample of the chunk into the lane state
-__global__ void k_dc_finish(const DcParams p)
-{
-    int lane = blockIdx.x * blockDim.x + threadIdx.x;
-    if (lane >= p.nlanes) return;
-    // state after n samples: restart from the last full-group boundary
-    int j = p.n / p.G;
-    double2 v = p.V[(long long)lane * (p.ngrp + 1) + j];
-    float v1r = (float)v.x, v1i = (float)v.y;
-    const float2 *x = p.in + (long long)lane * p.in_lane_stride;
-    for (int i = j * p.G; i < p.n; i++) {
-        float2 s = x[i];
-        v1r = __fsub_rn(s.x, __fmul_rn(p.a1, v1r));
-        v1i = __fsub_rn(s.y, __fmul_rn(p.a1, v1i));
-    }
-    p.lane[lane].dc_re = v1r; p.lane[lane].dc_im = v1i;
 }
 
 // ------------------------------------------------------------------------------------------ agc + fm
@@ -204,7 +209,10 @@ __device__ __forceinline__ bool be_step(const BackendParams &p, AgcRun &s, float
         // AGC(_execute), liquid agc.c
         yr = __fmul_rn(xr, s.g); yi = __fmul_rn(xi, s.g);
         float y2 = __fadd_rn(__fmul_rn(yr, yr), __fmul_rn(yi, yi));
-        s.y2p = (float)(p.one_minus_alpha * (double)s.y2p + (double)__fmul_rn(p.alpha, y2));
+        // liquid evaluates (1.0 - alpha) * y2' + alpha * y2 in double and rounds to float; the float32 FMA below differs
+        // from it by at most one ulp of y2' (6e-8 relative), i.e. 3e-9 per step in the gain: far below the 1e-6 at
+        // which two float32 runs of this loop settle anyway
+        s.y2p = fmaf(p.one_minus_alpha_f, s.y2p, __fmul_rn(p.alpha, y2));
         if (s.y2p > 1e-6f) s.g *= expf(p.neg_half_alpha * logf(s.y2p));
         if (s.g > 1e6f) s.g = 1e6f;
         ex = s.g < p.g_thr;                       // rssi = -20 log10(g) > threshold
@@ -221,7 +229,7 @@ __device__ __forceinline__ bool be_step(const BackendParams &p, AgcRun &s, float
 
 __device__ __forceinline__ bool be_close(float a, float b, float atol = 0.f)
 {
-    return fabsf(a - b) <= 1e-6f * fmaxf(fabsf(a), fabsf(b)) + atol;
+    return fabsf(a - b) <= 1e-5f * fmaxf(fabsf(a), fabsf(b)) + atol;   // fp32 rounding keeps two runs ~1e-6 apart
 }
 __device__ __forceinline__ bool be_match(const SegState &a, const SegState &b, int has_agc, int demod)
 {
@@ -231,37 +239,54 @@ __device__ __forceinline__ bool be_match(const SegState &a, const SegState &b, i
     return ok;
 }
 
-// run samples [i0, i1) of one lane from state s / dc state (v1r, v1i); emit outputs and threshold bits for
-// i >= emit_from (emit_from and i1 - or the chunk end - delimit whole 32-bit words owned by the caller)
+// run samples [i0, i1) of one lane from state s / dc state (v1r, v1i).  EMIT: write outputs, threshold bits and
+// sign bits (the caller owns whole 32-sample words: i0 % 32 == 0 and i1 is a multiple of 32 or the chunk end).
+// Samples are fetched eight at a time, one block ahead of the recurrence, so that the sequential chain never waits
+// for memory.
+template <bool EMIT>
 __device__ __forceinline__ void be_run(const BackendParams &p, int lane, AgcRun &s, float &v1r, float &v1i, int i0,
-                                       int i1, int emit_from)
+                                       int i1)
 {
-    const float2 *x = p.in + (long long)lane * p.in_lane_stride;
-    float *of = (float *)p.out + (long long)lane * p.out_lane_stride;
-    float2 *oc = (float2 *)p.out + (long long)lane * p.out_lane_stride;
+    const float2 *__restrict__ x = p.in + (long long)lane * p.in_lane_stride;
+    float *__restrict__ of = (float *)p.out + (long long)lane * p.out_lane_stride;
+    float2 *__restrict__ oc = (float2 *)p.out + (long long)lane * p.out_lane_stride;
     unsigned *bits = p.exbits + (long long)lane * p.nwords;
     unsigned *sr = p.sgnr + (long long)lane * p.nwords, *si = p.sgni + (long long)lane * p.nwords;
     unsigned word = 0, wr = 0, wi = 0;
-    for (int i = i0; i < i1; i++) {
-        float2 v = x[i];
-        float xr = v.x, xi = v.y;
-        if (p.has_dc) {
-            float v0r = __fsub_rn(xr, __fmul_rn(p.dc_a1, v1r));
-            float v0i = __fsub_rn(xi, __fmul_rn(p.dc_a1, v1i));
-            xr = __fsub_rn(v0r, v1r); xi = __fsub_rn(v0i, v1i);
-            v1r = v0r; v1i = v0i;
-        }
-        float yr, yi, m = 0.f;
-        const bool ex = be_step(p, s, xr, xi, yr, yi, m);
-        if (i >= emit_from) {
-            if (p.demod == 1) of[i] = m; else oc[i] = cf(yr, yi);
-            word |= (ex ? 1u : 0u) << (i & 31);
-            wr |= ((unsigned)__float_as_int(yr) >> 31) << (i & 31);
-            wi |= ((unsigned)__float_as_int(yi) >> 31) << (i & 31);
-            if ((i & 31) == 31 || i == i1 - 1) {
-                bits[i >> 5] = word; word = 0;
-                if (p.demod == 1) { sr[i >> 5] = wr; si[i >> 5] = wi; }
-                wr = 0; wi = 0;
+    constexpr int B = 8;
+    float2 cur[B], nxt[B];
+    auto fetch = [&](float2 (&dst)[B], int i) {
+#pragma unroll
+        for (int k = 0; k < B; k++) dst[k] = (i + k < i1) ? __ldg(x + i + k) : cf(0.f, 0.f);
+    };
+    if (i0 < i1) fetch(nxt, i0);
+    for (int i = i0; i < i1; i += B) {
+#pragma unroll
+        for (int k = 0; k < B; k++) cur[k] = nxt[k];
+        if (i + B < i1) fetch(nxt, i + B);
+#pragma unroll
+        for (int k = 0; k < B; k++) {
+            if (i + k >= i1) break;
+            float xr = cur[k].x, xi = cur[k].y;
+            if (p.has_dc) {
+                float v0r = __fsub_rn(xr, __fmul_rn(p.dc_a1, v1r));
+                float v0i = __fsub_rn(xi, __fmul_rn(p.dc_a1, v1i));
+                xr = __fsub_rn(v0r, v1r); xi = __fsub_rn(v0i, v1i);
+                v1r = v0r; v1i = v0i;
+            }
+            float yr, yi, m = 0.f;
+            const bool ex = be_step(p, s, xr, xi, yr, yi, m);
+            if (EMIT) {
+                const int ii = i + k;
+                if (p.demod == 1) of[ii] = m; else oc[ii] = cf(yr, yi);
+                word |= (ex ? 1u : 0u) << (ii & 31);
+                wr |= ((unsigned)__float_as_int(yr) >> 31) << (ii & 31);
+                wi |= ((unsigned)__float_as_int(yi) >> 31) << (ii & 31);
+                if ((ii & 31) == 31 || ii == i1 - 1) {
+                    bits[ii >> 5] = word; word = 0;
+                    if (p.demod == 1) { sr[ii >> 5] = wr; si[ii >> 5] = wi; }
+                    wr = 0; wi = 0;
+                }
             }
         }
     }
@@ -271,7 +296,7 @@ __device__ __forceinline__ void be_dc_state(const BackendParams &p, int lane, in
 {
     // i is a multiple of G
     if (p.has_dc) {
-        double2 v = p.dcV[(long long)lane * (p.ngrp + 1) + i / p.G];
+        const double2 v = dc_state_at(p.dcVloc, p.dcCarry, p.dcPowA, p.ngrp, p.nblk, lane, i / p.G);
         v1r = (float)v.x; v1i = (float)v.y;
     } else { v1r = 0.f; v1i = 0.f; }
 }
@@ -306,13 +331,23 @@ __global__ void __launch_bounds__(128) k_backend_spec(const BackendParams p)
         s.y2p = 1.0f; s.fr = 0.f; s.fi = 0.f;
     }
     be_dc_state(p, lane, w0, v1r, v1i);
-    be_run(p, lane, s, v1r, v1i, w0, b0, b1);          // warm-up, nothing emitted
+    be_run<false>(p, lane, s, v1r, v1i, w0, b0);       // warm-up, nothing emitted
     p.seg_start[t] = be_pack(s);
-    be_run(p, lane, s, v1r, v1i, b0, b1, b0);
+    be_run<true>(p, lane, s, v1r, v1i, b0, b1);
     p.seg_end[t] = be_pack(s);
 }
 
-// one CTA per lane: verify the gain speculation, re-run the misses in stream order, store the lane's gain state
+// grid-wide verification of the gain speculation: first segment per lane that does not continue its predecessor
+__global__ void k_backend_verify(const BackendParams p)
+{
+    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long long)p.nlanes * p.nseg) return;
+    const int lane = (int)(t / p.nseg), seg = (int)(t - (long long)lane * p.nseg);
+    if (seg > 0 && !be_match(p.seg_start[t], p.seg_end[t - 1], p.has_agc, p.demod))
+        atomicMin(&p.first_bad[2 * lane], (unsigned)seg);
+}
+
+// one CTA per lane: re-run the misses in stream order (rare), store the lane's gain state
 __global__ void k_backend_fixup(const BackendParams p)
 {
     const int lane = blockIdx.x;
@@ -320,16 +355,20 @@ __global__ void k_backend_fixup(const BackendParams p)
     __shared__ int s_cur;
     SegState *E = p.seg_end + (long long)lane * p.nseg;
     const SegState *S0 = p.seg_start + (long long)lane * p.nseg;
+    bool first = true;
     if (threadIdx.x == 0) s_cur = 1;
     __syncthreads();
     while (true) {
-        // parallel search for the first segment >= s_cur whose start state does not continue its predecessor
-        if (threadIdx.x == 0) s_next = 0xffffffffu;
+        if (threadIdx.x == 0) s_next = first ? p.first_bad[2 * lane] : 0xffffffffu;
         __syncthreads();
-        const int cur = s_cur;
-        for (int j = cur + threadIdx.x; j < p.nseg; j += blockDim.x)
-            if (!be_match(S0[j], E[j - 1], p.has_agc, p.demod)) { atomicMin(&s_next, (unsigned)j); break; }
-        __syncthreads();
+        if (!first) {
+            // after a repair: parallel search for the next segment >= s_cur that does not continue its predecessor
+            const int cur = s_cur;
+            for (int j = cur + threadIdx.x; j < p.nseg; j += blockDim.x)
+                if (!be_match(S0[j], E[j - 1], p.has_agc, p.demod)) { atomicMin(&s_next, (unsigned)j); break; }
+            __syncthreads();
+        }
+        first = false;
         const unsigned nxt = s_next;
         if (nxt == 0xffffffffu) break;
         if (threadIdx.x == 0) {
@@ -342,7 +381,7 @@ __global__ void k_backend_fixup(const BackendParams p)
                 float v1r, v1i;
                 const int b0 = seg * p.L, b1 = min(b0 + p.L, p.n);
                 be_dc_state(p, lane, b0, v1r, v1i);
-                be_run(p, lane, s, v1r, v1i, b0, b1, b0);
+                be_run<true>(p, lane, s, v1r, v1i, b0, b1);
                 E[seg] = be_pack(s);
                 redone++;
                 seg++;      // the successor is re-checked against the new end state on the next iteration
@@ -359,6 +398,7 @@ __global__ void k_backend_fixup(const BackendParams p)
         p.prev_sign[lane] = ((unsigned)__float_as_int(ls.fm_re) >> 31) | (((unsigned)__float_as_int(ls.fm_im) >> 31) << 1);
         ls.g = e.g; ls.y2p = e.y2p; ls.fm_re = e.fm_re; ls.fm_im = e.fm_im;
         p.lane[lane] = ls;
+        p.first_bad[2 * lane] = 0xffffffffu;
     }
 }
 
@@ -414,6 +454,14 @@ __global__ void __launch_bounds__(128) k_backend_fsm(const BackendParams p)
     p.fsm_end[t] = s;
 }
 
+__global__ void k_backend_fsm_verify(const BackendParams p)
+{
+    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long long)p.nlanes * p.nseg) return;
+    const int lane = (int)(t / p.nseg), seg = (int)(t - (long long)lane * p.nseg);
+    if (seg > 0 && !fsm_same(p.fsm_start[t], p.fsm_end[t - 1])) atomicMin(&p.first_bad[2 * lane + 1], (unsigned)seg);
+}
+
 __global__ void k_backend_fsm_fix(const BackendParams p)
 {
     const int lane = blockIdx.x;
@@ -423,15 +471,19 @@ __global__ void k_backend_fsm_fix(const BackendParams p)
     const FsmState *S0 = p.fsm_start + (long long)lane * p.nseg;
     const unsigned *bits = p.exbits + (long long)lane * p.nwords;
     unsigned *gate = p.gatebits + (long long)lane * p.nwords;
+    bool first = true;
     if (threadIdx.x == 0) s_cur = 1;
     __syncthreads();
     while (true) {
-        if (threadIdx.x == 0) s_next = 0xffffffffu;
+        if (threadIdx.x == 0) s_next = first ? p.first_bad[2 * lane + 1] : 0xffffffffu;
         __syncthreads();
-        const int cur = s_cur;
-        for (int j = cur + threadIdx.x; j < p.nseg; j += blockDim.x)
-            if (!fsm_same(S0[j], E[j - 1])) { atomicMin(&s_next, (unsigned)j); break; }
-        __syncthreads();
+        if (!first) {
+            const int cur = s_cur;
+            for (int j = cur + threadIdx.x; j < p.nseg; j += blockDim.x)
+                if (!fsm_same(S0[j], E[j - 1])) { atomicMin(&s_next, (unsigned)j); break; }
+            __syncthreads();
+        }
+        first = false;
         const unsigned nxt = s_next;
         if (nxt == 0xffffffffu) break;
         if (threadIdx.x == 0) {
@@ -457,6 +509,7 @@ __global__ void k_backend_fsm_fix(const BackendParams p)
         p.prev_gate[lane] = (p.lane[lane].mode == SQ_SIGNALHI) ? 1u : 0u;
         const FsmState e = E[p.nseg - 1];
         p.lane[lane].mode = e.mode; p.lane[lane].timer = e.timer;
+        p.first_bad[2 * lane + 1] = 0xffffffffu;
     }
 }
 
@@ -525,6 +578,39 @@ __global__ void k_lane_sum(const float *__restrict__ in, long long lane_stride, 
         float acc = in[i];
         for (int c = 1; c < nlanes; c++) acc = __fadd_rn(acc, in[(long long)c * lane_stride + i]);
         out[i] = acc;
+    }
+}
+
+// ------------------------------------------------------------------------------------------ launch sequences
+// `launch(kernel, grid, block, smem_bytes, args...)` is supplied by the caller (CUDA stream launcher in
+// csdr_b200.cu, thread emulator in the CPU-only tests) so that both run the same sequence with the same grids.
+template <class Launch>
+inline void be_launch_dc(Launch &launch, const DcParams &d, bool apply)
+{
+    launch(k_dc_local, dim3(d.nblk, d.nlanes), dim3(kDcGB), 0, d);
+    launch(k_dc_carry, dim3((d.nlanes + 63) / 64), dim3(64), 0, d);
+    if (apply) {
+        const long long items = (long long)d.nlanes * d.ngrp;
+        launch(k_dc_apply, dim3((unsigned)((items + 127) / 128)), dim3(128), 0, d);
+    }
+}
+
+template <class Launch>
+inline void be_launch(Launch &launch, const BackendParams &b)
+{
+    const long long segs = (long long)b.nlanes * b.nseg;
+    const unsigned gb = (unsigned)((segs + 127) / 128);
+    launch(k_backend_spec, dim3(gb), dim3(128), 0, b);
+    launch(k_backend_verify, dim3(gb), dim3(128), 0, b);
+    launch(k_backend_fixup, dim3(b.nlanes), dim3(128), 0, b);
+    if (b.has_agc) {
+        launch(k_backend_fsm, dim3(gb), dim3(128), 0, b);
+        launch(k_backend_fsm_verify, dim3(gb), dim3(128), 0, b);
+        launch(k_backend_fsm_fix, dim3(b.nlanes), dim3(128), 0, b);
+        if (b.gate) {
+            const long long words = (long long)b.nlanes * b.nwords;
+            launch(k_backend_gate, dim3((unsigned)((words + 127) / 128)), dim3(128), 0, b);
+        }
     }
 }
 

@@ -144,6 +144,7 @@ struct Frontend {
     FrontendCursor cursor;
     int mix_mode = 0; uint32_t theta0 = 0, dtheta = 0; int quantize = 1;
     void (*kernel)(FrontendParams) = k_frontend;
+    int ctas_per_sm = 2;
     // optional event timing of k_frontend (bench roofline): pairs recorded on the launching stream
     bool profile = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pending, ev_free;
@@ -195,6 +196,8 @@ struct Frontend {
         bank.ensure(ms.bank.size() * sizeof(float));
         CK(cudaMemcpyAsync(bank.p, ms.bank.data(), ms.bank.size() * sizeof(float), cudaMemcpyHostToDevice, c.stream));
         CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)geo.smem_bytes));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kernel, 256, geo.smem_bytes));
+        if (ctas_per_sm < 1) throw CudaError{"frontend: tile does not fit in shared memory"};
         c.sync();
     }
     long long max_out(long long nx) const
@@ -213,7 +216,8 @@ struct Frontend {
         p.mix_mode = mix_mode; p.theta0 = theta0; p.dtheta = dtheta; p.quantize = quantize;
         p.bank = bank.as<float>();
         if (p.ntiles > 0) {
-            int gx = std::min(p.ntiles, std::max(1, c.sms * 3 / std::max(1, std::min(nstreams, c.sms * 3))));
+            const int slots = c.sms * ctas_per_sm;      // persistent CTAs: one wave, tiles strided over the grid
+            int gx = std::min(p.ntiles, std::max(1, slots / std::max(1, std::min(nstreams, slots))));
             std::pair<cudaEvent_t, cudaEvent_t> ev{nullptr, nullptr};
             if (profile) {
                 if (ev_pending.size() > 4096) collect(c);
@@ -241,7 +245,7 @@ struct Backend {
     float agc_bw = 0.1f, agc_thr = 0.f; unsigned agc_timeout = 1000; bool squelch = true, gate = true;
     float kf = 0.3f;
     int L = 512, W = 384, G = 128;
-    DevBuf lane, P, V, ss, se, fs, fe, exbits, gatebits, sgnr, sgni, prev_gate, prev_sign, fixups;
+    DevBuf lane, Vloc, carry, powA, ss, se, fs, fe, exbits, gatebits, sgnr, sgni, prev_gate, prev_sign, first_bad, fixups;
     int FW = 3;
 
     void init(const Ctx &c, int lanes, float g0 = 1000.0f, int mode0 = SQ_ENABLED)
@@ -257,64 +261,76 @@ struct Backend {
         CK(cudaMemcpyAsync(lane.p, ls.data(), sizeof(LaneState) * nlanes, cudaMemcpyHostToDevice, c.stream));
         prev_gate.ensure(sizeof(unsigned) * nlanes); CK(cudaMemsetAsync(prev_gate.p, 0, prev_gate.cap, c.stream));
         prev_sign.ensure(sizeof(unsigned) * nlanes); CK(cudaMemsetAsync(prev_sign.p, 0, prev_sign.cap, c.stream));
+        first_bad.ensure(sizeof(unsigned) * 2 * nlanes); CK(cudaMemsetAsync(first_bad.p, 0xff, first_bad.cap, c.stream));
+        // A^k, A = c^G, for the dc blocker's group-boundary states
+        {
+            const double cc = -(double)(-1.0f + dc_alpha);
+            double A = 1.0;
+            for (int i = 0; i < G; i++) A *= cc;
+            std::vector<double> pw(kDcGB + 1);
+            pw[0] = 1.0;
+            for (int k = 1; k <= kDcGB; k++) pw[k] = pw[k - 1] * A;
+            powA.ensure(sizeof(double) * pw.size());
+            CK(cudaMemcpyAsync(powA.p, pw.data(), sizeof(double) * pw.size(), cudaMemcpyHostToDevice, c.stream));
+            c.sync();
+        }
         fixups.ensure(2 * sizeof(unsigned long long)); CK(cudaMemsetAsync(fixups.p, 0, fixups.cap, c.stream));
         c.sync();
     }
-    DcParams dc_params(const float2 *in, long long in_stride, float2 *out, long long out_stride, int n, int ngrp)
+    struct Launcher {
+        cudaStream_t st;
+        template <class... Args, class... Act>
+        void operator()(void (*k)(Args...), dim3 grid, dim3 block, size_t smem, Act &&...a) const
+        {
+            launch(k, grid, block, smem, st, std::forward<Act>(a)...);
+        }
+    };
+    DcParams dc_params(const float2 *in, long long in_stride, float2 *out, long long out_stride, int n)
     {
         DcParams d{};
         d.in = in; d.in_lane_stride = in_stride; d.out = out; d.out_lane_stride = out_stride;
-        d.n = n; d.nlanes = nlanes; d.G = G; d.ngrp = ngrp;
+        d.n = n; d.nlanes = nlanes; d.G = G; d.ngrp = (n + G - 1) / G; d.nblk = (d.ngrp + kDcGB - 1) / kDcGB;
         d.a1 = -1.0f + dc_alpha; d.c = -(double)d.a1;
-        d.P = P.as<double2>(); d.V = V.as<double2>(); d.lane = lane.as<LaneState>();
+        Vloc.ensure(sizeof(double2) * (size_t)nlanes * d.ngrp);
+        carry.ensure(sizeof(double2) * (size_t)nlanes * d.nblk);
+        d.Vloc = Vloc.as<double2>(); d.carry = carry.as<double2>(); d.powA = powA.as<double>();
+        d.lane = lane.as<LaneState>();
         return d;
-    }
-    void dc_prepare(const Ctx &c, const DcParams &d)
-    {
-        long long items = (long long)nlanes * d.ngrp;
-        launch(k_dc_partial, dim3((unsigned)((items + 127) / 128)), dim3(128), 0, c.stream, d);
-        launch(k_dc_scan, dim3(nlanes), dim3(1024), 0, c.stream, d);
-        launch(k_dc_finish, dim3((nlanes + 63) / 64), dim3(64), 0, c.stream, d);
     }
     // dc blocker only, out may alias in
     void run_dc_only(const Ctx &c, const float2 *in, long long in_stride, float2 *out, long long out_stride, int n)
     {
         if (n <= 0) return;
-        int ngrp = (n + G - 1) / G;
-        P.ensure(sizeof(double2) * (size_t)nlanes * ngrp);
-        V.ensure(sizeof(double2) * (size_t)nlanes * (ngrp + 1));
-        DcParams d = dc_params(in, in_stride, out, out_stride, n, ngrp);
-        dc_prepare(c, d);
-        long long items = (long long)nlanes * ngrp;
-        launch(k_dc_apply, dim3((unsigned)((items + 127) / 128)), dim3(128), 0, c.stream, d);
+        DcParams d = dc_params(in, in_stride, out, out_stride, n);
+        Launcher l{c.stream};
+        be_launch_dc(l, d, true);
     }
     // [dc] -> [agc+gate] -> [fm]; out: float (demod) or float2
     void run(const Ctx &c, const float2 *in, long long in_stride, void *out, long long out_stride, int n)
     {
         if (n <= 0) return;
+        Launcher l{c.stream};
         int ngrp = (n + G - 1) / G, nseg = (n + L - 1) / L, nwords = (n + 31) / 32;
         size_t segs = (size_t)nlanes * nseg;
         ss.ensure(sizeof(SegState) * segs); se.ensure(sizeof(SegState) * segs);
         fs.ensure(sizeof(FsmState) * segs); fe.ensure(sizeof(FsmState) * segs);
         exbits.ensure(sizeof(unsigned) * (size_t)nlanes * nwords); gatebits.ensure(sizeof(unsigned) * (size_t)nlanes * nwords);
         sgnr.ensure(sizeof(unsigned) * (size_t)nlanes * nwords); sgni.ensure(sizeof(unsigned) * (size_t)nlanes * nwords);
-        if (has_dc) {
-            P.ensure(sizeof(double2) * (size_t)nlanes * ngrp);
-            V.ensure(sizeof(double2) * (size_t)nlanes * (ngrp + 1));
-            DcParams d = dc_params(in, in_stride, nullptr, 0, n, ngrp);
-            dc_prepare(c, d);
-        }
         BackendParams b{};
+        if (has_dc) {
+            DcParams d = dc_params(in, in_stride, nullptr, 0, n);
+            be_launch_dc(l, d, false);
+            b.dcVloc = d.Vloc; b.dcCarry = d.carry; b.dcPowA = d.powA; b.nblk = d.nblk;
+        }
         b.in = in; b.in_lane_stride = in_stride; b.out = out; b.out_lane_stride = out_stride;
         b.n = n; b.nlanes = nlanes; b.L = L; b.W = W; b.G = G; b.nseg = nseg; b.ngrp = ngrp;
         b.has_dc = has_dc; b.has_agc = has_agc; b.demod = demod;
         b.dc_a1 = -1.0f + dc_alpha;
-        b.alpha = agc_bw; b.one_minus_alpha = 1.0 - (double)agc_bw; b.neg_half_alpha = -0.5f * agc_bw;
+        b.alpha = agc_bw; b.one_minus_alpha_f = (float)(1.0 - (double)agc_bw); b.neg_half_alpha = -0.5f * agc_bw;
         b.g_thr = design::agc_gain_threshold(agc_thr); b.timeout = agc_timeout;
         b.fm_ref = (float)(1.0f / (2 * design::kPi * kf));
         b.squelch_enabled = squelch ? 1 : 0; b.gate = gate ? 1 : 0;
         b.lane = lane.as<LaneState>(); b.seg_start = ss.as<SegState>(); b.seg_end = se.as<SegState>();
-        b.dcV = V.as<double2>();
         b.nwords = nwords;
         // the FSM forgets its entry state after timeout + 4 samples: replay that many bits (in whole segments)
         b.FW = (int)std::min<unsigned>(64u, (agc_timeout + 8 + (unsigned)L - 1) / (unsigned)L);
@@ -322,18 +338,9 @@ struct Backend {
         b.fsm_start = fs.as<FsmState>(); b.fsm_end = fe.as<FsmState>();
         b.prev_gate = prev_gate.as<unsigned>(); b.prev_sign = prev_sign.as<unsigned>();
         b.sgnr = sgnr.as<unsigned>(); b.sgni = sgni.as<unsigned>();
+        b.first_bad = first_bad.as<unsigned>();
         b.fixups = fixups.as<unsigned long long>();
-        unsigned gb = (unsigned)((segs + 127) / 128);
-        launch(k_backend_spec, dim3(gb), dim3(128), 0, c.stream, b);
-        launch(k_backend_fixup, dim3(nlanes), dim3(256), 0, c.stream, b);
-        if (has_agc) {
-            launch(k_backend_fsm, dim3(gb), dim3(128), 0, c.stream, b);
-            launch(k_backend_fsm_fix, dim3(nlanes), dim3(256), 0, c.stream, b);
-            if (gate) {
-                long long words = (long long)nlanes * nwords;
-                launch(k_backend_gate, dim3((unsigned)((words + 127) / 128)), dim3(128), 0, c.stream, b);
-            }
-        }
+        be_launch(l, b);
     }
     unsigned long long read_fixups(const Ctx &c)
     {

@@ -17,16 +17,18 @@ struct FeGeom {
     int m[kMaxStages] = {}, R[kMaxStages] = {};
     int d[kMaxStages + 1] = {}, n[kMaxStages + 1] = {}, stride[kMaxStages + 1] = {}, off[kMaxStages + 1] = {};
     int total_f2 = 0;     // float2 elements of all level buffers
+    int off_raw = 0;      // float2 offset of the raw staging buffer (n[S] samples) the bulk copy lands in, 0 = none
     int hcap = 0;         // raw-sample history the first tile of a chunk may reach back over
 };
 
 __host__ __device__ constexpr int ce_max(int a, int b) { return a > b ? a : b; }
 __host__ __device__ constexpr int ce_roundup(int v, int m) { return (v + m - 1) / m * m; }
 
-// shift = 1: the top level starts one sample early so that pairs (2p, 2p+1) are 16-byte aligned float4 loads when
-// the chunk is; top_mod = required (sub-array stride mod 16) of the top level for conflict-free loader stores
-// (4 for the float4 loader, 2 for the scalar loader).
-__host__ __device__ constexpr FeGeom fe_make_geom(int S, int Tc, const int *m, int shift, int top_mod)
+// shift = 1: the top level starts one sample early so that pairs (2p, 2p+1) are 16-byte aligned when the chunk is.
+// Sub-array strides are == 2 (mod 16): 64-bit shared accesses are served per half-warp, and with this stride both the
+// loader (pair p -> sub-array p & 7, index p >> 3) and the R = 8 producers (t -> sub-array 4 (t & 1) + c, index t >> 1)
+// touch 16 distinct 8-byte banks per half-warp.  raw = 1 reserves the staging buffer of the bulk-copy pipeline.
+__host__ __device__ constexpr FeGeom fe_make_geom(int S, int Tc, const int *m, int shift, int raw)
 {
     FeGeom g{};
     g.S = S; g.Tc = Tc; g.shift = S > 0 ? shift : 0;
@@ -44,7 +46,7 @@ __host__ __device__ constexpr FeGeom fe_make_geom(int S, int Tc, const int *m, i
     for (int L = 1; L <= S; L++) {
         const int D = g.R[L - 1];
         int st = g.n[L] / (2 * D) + 1;
-        if (L == S) { while ((st & 15) != top_mod) st++; }
+        while ((st & 15) != 2) st++;
         g.stride[L] = st;
         const int sz = 2 * D * st;
         if (((S - L) & 1) == 0) sizeA = ce_max(sizeA, sz); else sizeB = ce_max(sizeB, sz);
@@ -53,6 +55,7 @@ __host__ __device__ constexpr FeGeom fe_make_geom(int S, int Tc, const int *m, i
     g.off[0] = 0;
     for (int L = 1; L <= S; L++) g.off[L] = size0 + ((((S - L) & 1) == 0) ? 0 : sizeA);
     g.total_f2 = size0 + sizeA + sizeB;
+    if (raw && S > 0) { g.off_raw = g.total_f2; g.total_f2 += g.n[S]; }
     g.hcap = ce_roundup(((1 << S) - 1) + (kHcPad << S) - g.d[S] + 1, 64);
     return g;
 }
@@ -66,7 +69,7 @@ __host__ __device__ constexpr int fe_std_tc(int S)
 __host__ __device__ constexpr FeGeom fe_make_geom_std(int S)
 {
     FeStdM mm{};
-    return fe_make_geom(S, fe_std_tc(S), mm.v, 1, 4);
+    return fe_make_geom(S, fe_std_tc(S), mm.v, 1, 1);
 }
 constexpr int kFeStdMaxS = 6;      // k_frontend_std is instantiated for S = 1..6
 

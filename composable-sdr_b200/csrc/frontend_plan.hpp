@@ -38,7 +38,7 @@ inline FrontendGeometry plan_frontend(const design::MsresampPlan &ms, int Tc, bo
         if (m[s] != stdm.v[s]) is_std = false;
     }
     g.std_kernel = is_std;
-    g.geom = is_std ? fe_make_geom_std(S) : fe_make_geom(S, Tc, m, 0, 2);
+    g.geom = is_std ? fe_make_geom_std(S) : fe_make_geom(S, Tc, m, 0, 0);
     const FeGeom &G = g.geom;
     p.S = S; p.Tc = G.Tc;
     p.zeta = 1.0f / (float)(1u << ms.S);

@@ -4,9 +4,8 @@
 // access is base register + immediate, loop trip counts are constants and the half-band taps are read straight
 // from the kernel-parameter constant bank by the FFMAs.  Other plans use the generic k_frontend.
 //
-// Per input sample the kernel issues ~13 instructions in the loader (one LDG.128 per two samples, phase IMAD,
-// I2F, FMUL, two MUFU, four FP for the complex rotation, STS.64), ~17 FFMA + ~3 LDS.64 in the half-band cascade and
-// ~5 in the arbitrary resampler.
+// Raw input tiles are staged in shared memory by TMA bulk copies (cp.async.bulk + mbarrier) one tile ahead, so the
+// HBM latency is hidden behind the filtering of the previous tile; the mixer then reads pairs with LDS.128.
 #pragma once
 #include "frontend.cuh"
 
@@ -36,10 +35,21 @@ __device__ __forceinline__ float2 fe_mix(float2 v, unsigned th, int quantize)
     return cf(v.x * w.x - v.y * s, v.y * w.x + v.x * s);
 }
 
-// ---- top level: global -> (mix) -> shared, in the consumer's de-interleaved layout -------------------------
+// ---- top level: (mix) -> shared, in the consumer's de-interleaved layout ------------------------------------
+// A tile that lies inside the chunk at a 16-byte aligned address is "bulk": its raw samples were staged in shared
+// memory by a TMA bulk copy issued while the previous tile was being filtered.
+template <int S>
+__device__ __forceinline__ bool fe_tile_is_bulk(const FrontendParams &p, const float2 *xs, long long lo)
+{
+    constexpr int NS = FeStd<S>::G.n[S];
+    const long long rel0 = lo - p.n0;
+    return rel0 >= 0 && rel0 + NS <= p.nx && ((reinterpret_cast<uintptr_t>(xs + rel0) & 15) == 0);
+}
+
 template <int S, int MIX>
 __device__ __forceinline__ void fe_load_top(const FrontendParams &p, const float2 *__restrict__ xs,
-                                            const float2 *__restrict__ hs, float2 *__restrict__ dst, long long lo)
+                                            const float2 *__restrict__ hs, float2 *__restrict__ dst, long long lo,
+                                            const float2 *__restrict__ raw, bool bulk)
 {
     constexpr FeGeom G = FeStd<S>::G;
     constexpr int NS = G.n[S], STR = G.stride[S], D = G.R[S - 1];
@@ -48,24 +58,24 @@ __device__ __forceinline__ void fe_load_top(const FrontendParams &p, const float
     const long long rel0 = lo - p.n0;
     const unsigned th0 = p.theta0 + (unsigned)lo * p.dtheta;
     const bool inside = rel0 >= 0 && rel0 + NS <= p.nx;
-    if (inside && ((reinterpret_cast<uintptr_t>(xs + rel0) & 15) == 0)) {
-        // fast path: one 16-byte load = the (even, odd) pair p; pair -> sub-array p & 7, index p >> 3
-        const float4 *src = reinterpret_cast<const float4 *>(xs + rel0);
+    if (bulk) {
+        // one 16-byte shared load = the (even, odd) pair p; pair -> sub-array p & 7, index p >> 3
+        const float4 *src = reinterpret_cast<const float4 *>(raw);
         float2 *dE = dst + (tid & 7) * STR + (tid >> 3);
         float2 *dO = dE + D * STR;
         constexpr int NP = NS / 2, IT = (NP + 255) / 256;
-#pragma unroll 4
+#pragma unroll
         for (int k = 0; k < IT; k++) {
             const int pi = tid + 256 * k;
             if (pi < NP) {
-                const float4 v = fe_ldg_stream(src + pi);
+                const float4 v = src[pi];
                 const unsigned th = th0 + (unsigned)(2 * pi) * p.dtheta;
                 dE[32 * k] = fe_mix<MIX>(cf(v.x, v.y), th, p.quantize);
                 dO[32 * k] = fe_mix<MIX>(cf(v.z, v.w), th + p.dtheta, p.quantize);
             }
         }
     } else if (inside) {
-        // chunk not 16-byte aligned at this tile: 8-byte loads, sample i -> plane i & 1, pair i >> 1
+        // chunk not 16-byte aligned at this tile: 8-byte global loads, sample i -> plane i & 1, pair i >> 1
         const float2 *src = xs + rel0;
         float2 *d0 = dst + ((tid & 1) * D + ((tid >> 1) & 7)) * STR + (tid >> 4);
         constexpr int IT = (NS + 255) / 256;
@@ -143,13 +153,16 @@ __device__ __forceinline__ void fe_run_stages(const FrontendParams &p, float2 *s
 }
 
 template <int S>
-__global__ void __launch_bounds__(256, 3) k_frontend_std(const CSDR_GRID_CONSTANT FrontendParams p)
+__global__ void __launch_bounds__(256, 2) k_frontend_std(const CSDR_GRID_CONSTANT FrontendParams p)
 {
     constexpr FeGeom G = FeStd<S>::G;
+    constexpr int NS = G.n[S];
     CSDR_DYN_SMEM(smem_raw);
     float2 *smem = reinterpret_cast<float2 *>(smem_raw);
     float *bank_s = reinterpret_cast<float *>(smem_raw) + 2 * G.total_f2;
+    float2 *raw = smem + G.off_raw;
     __shared__ int s_orange[2];
+    __shared__ __align__(8) unsigned long long s_bar;
 
     const int npfb = 1 << p.bits;
     for (int i = threadIdx.x; i < npfb * kHsub; i += 256) {
@@ -161,11 +174,21 @@ __global__ void __launch_bounds__(256, 3) k_frontend_std(const CSDR_GRID_CONSTAN
     float2 *ys = p.y + (long long)blockIdx.y * p.y_stride;
     const unsigned mask = (unsigned)npfb - 1u;
     const int sh = 24 - p.bits;
+    auto tile_lo = [&](int tile) { return (p.K0 + (long long)tile * G.Tc - kHcPad) * (1LL << S) + G.d[S]; };
+
+    // bulk-copy pipeline: the raw samples of the next tile are fetched by the TMA while this tile is filtered
+    unsigned parity = 0;
+    if (threadIdx.x == 0) {
+        bulk_init(&s_bar);
+        const int t0 = blockIdx.x;
+        if (t0 < p.ntiles && fe_tile_is_bulk<S>(p, xs, tile_lo(t0)))
+            bulk_copy_g2s(raw, xs + (tile_lo(t0) - p.n0), NS * (unsigned)sizeof(float2), &s_bar);
+    }
+    __syncthreads();
 
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
         const long long kArel = (long long)tile * G.Tc;                 // pushes relative to K0
         const long long kBrel = min(kArel + (long long)G.Tc, p.K1 - p.K0);
-        const long long c_lo = p.K0 + kArel - kHcPad;
         if (threadIdx.x == 0) {
             // outputs emitted by pushes [kA, kB): o' with kArel*2^24 <= ph0 + o'*step < kBrel*2^24
             const unsigned long long st = p.step;
@@ -173,11 +196,19 @@ __global__ void __launch_bounds__(256, 3) k_frontend_std(const CSDR_GRID_CONSTAN
             s_orange[0] = (a > p.ph0) ? (int)((a - p.ph0 + st - 1) / st) : 0;
             s_orange[1] = (b > p.ph0) ? (int)((b - p.ph0 + st - 1) / st) : 0;
         }
-        const long long lo = c_lo * (1LL << S) + G.d[S];
-        if (p.mix_mode == 1)      fe_load_top<S, 1>(p, xs, hs, smem + G.off[S], lo);
-        else if (p.mix_mode == 2) fe_load_top<S, 2>(p, xs, hs, smem + G.off[S], lo);
-        else                      fe_load_top<S, 0>(p, xs, hs, smem + G.off[S], lo);
+        const long long lo = tile_lo(tile);
+        const bool bulk = fe_tile_is_bulk<S>(p, xs, lo);
+        if (bulk) { bulk_wait(&s_bar, parity); parity ^= 1u; }
+        if (p.mix_mode == 1)      fe_load_top<S, 1>(p, xs, hs, smem + G.off[S], lo, raw, bulk);
+        else if (p.mix_mode == 2) fe_load_top<S, 2>(p, xs, hs, smem + G.off[S], lo, raw, bulk);
+        else                      fe_load_top<S, 0>(p, xs, hs, smem + G.off[S], lo, raw, bulk);
         __syncthreads();
+        // the staging buffer is free again: start fetching the next tile of this CTA
+        if (threadIdx.x == 0) {
+            const int nt = tile + (int)gridDim.x;
+            if (nt < p.ntiles && fe_tile_is_bulk<S>(p, xs, tile_lo(nt)))
+                bulk_copy_g2s(raw, xs + (tile_lo(nt) - p.n0), NS * (unsigned)sizeof(float2), &s_bar);
+        }
 
         fe_run_stages<S, S - 1>(p, smem);
 

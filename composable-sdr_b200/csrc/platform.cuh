@@ -18,6 +18,37 @@
 
 namespace csdr {
 
+// ---- TMA bulk copy (cp.async.bulk, global -> shared, completion on an mbarrier) ------------------------------
+// Used to stage the next tile of raw input while the current tile is being filtered.  Under the test-only CPU
+// emulation the copy is a synchronous memcpy by the issuing thread and the barrier wait is a no-op (the kernels'
+// own __syncthreads order the accesses).
+#ifdef CSDR_EMU
+__device__ inline void bulk_init(unsigned long long *) {}
+__device__ inline void bulk_copy_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *) { memcpy(dst, src, bytes); }
+__device__ inline void bulk_wait(unsigned long long *, unsigned) {}
+#else
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void bulk_init(unsigned long long *bar)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+// one elected thread: arm the barrier with the byte count, then launch the copy (16-byte aligned, size % 16 == 0)
+__device__ __forceinline__ void bulk_copy_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar)
+{
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // earlier generic-proxy accesses to dst are done
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_wait(unsigned long long *bar, unsigned parity)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tWAIT_%=:\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+                 "@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+#endif
+
 constexpr int kMaxStages = 12;   // half-band stages (2^12 decimation) supported by the fused front end
 constexpr int kMaxHbM    = 16;   // max half-band semi-length m (2m taps)
 constexpr int kHsub      = 14;   // taps per polyphase branch of the arbitrary resampler (2*7, msresamp.c)

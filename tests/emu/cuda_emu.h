@@ -22,6 +22,7 @@
 #define __restrict__
 #define __launch_bounds__(...)
 #define __shared__ static
+#define __align__(n) __attribute__((aligned(n)))
 
 struct float2 { float x, y; };
 struct float4 { float x, y, z, w; };

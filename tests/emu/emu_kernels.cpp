@@ -67,7 +67,7 @@ long long emu_frontend(float rate, float As, int mix_mode, float freq, int quant
 // dc blocker -> agc(+gate) -> fm for nlanes lanes of n samples, fed in chunks; out is float (demod=1) or cf32.
 long long emu_backend(int nlanes, long long lane_stride, int has_dc, float dc_alpha, int has_agc, float thr_db,
                       int demod, float kf, int L, int W, int G, const float2 *x, long long n, const long long *chunks,
-                      int nchunks, void *out, unsigned long long *fixups_out)
+                      int nchunks, void *out, unsigned long long *fixups_out, float *dbg /* optional [nseg][8] of the last chunk */)
 {
     std::vector<LaneState> lane(nlanes);
     for (auto &l : lane) { l.dc_re = l.dc_im = 0; l.g = 1000.0f; l.y2p = 1.0f; l.mode = SQ_ENABLED; l.timer = 0; l.fm_re = l.fm_im = 0; }
@@ -76,40 +76,37 @@ long long emu_backend(int nlanes, long long lane_stride, int has_dc, float dc_al
     for (int c = 0; c < nchunks; c++) {
         int nx = (int)chunks[c];
         if (nx == 0) continue;
-        int ngrp = (nx + G - 1) / G, nseg = (nx + L - 1) / L;
-        std::vector<double2> P((size_t)nlanes * ngrp), V((size_t)nlanes * (ngrp + 1));
+        int ngrp = (nx + G - 1) / G, nseg = (nx + L - 1) / L, nblk = (ngrp + kDcGB - 1) / kDcGB;
+        std::vector<double2> Vloc((size_t)nlanes * ngrp), carry((size_t)nlanes * nblk);
+        std::vector<double> powA(kDcGB + 1);
         std::vector<SegState> ss((size_t)nlanes * nseg), se((size_t)nlanes * nseg);
         std::vector<FsmState> fs((size_t)nlanes * nseg), fe((size_t)nlanes * nseg);
         int nwords = (nx + 31) / 32;
         std::vector<unsigned> exb((size_t)nlanes * nwords), gb((size_t)nlanes * nwords), pg(nlanes, 0), ps(nlanes, 0);
-        std::vector<unsigned> sgr((size_t)nlanes * nwords), sgi((size_t)nlanes * nwords);
+        std::vector<unsigned> sgr((size_t)nlanes * nwords), sgi((size_t)nlanes * nwords), fb(2 * nlanes, 0xffffffffu);
         DcParams d{};
-        d.in = x + pos; d.in_lane_stride = lane_stride; d.n = nx; d.nlanes = nlanes; d.G = G; d.ngrp = ngrp;
-        d.a1 = -1.0f + dc_alpha; d.c = -(double)d.a1; d.P = P.data(); d.V = V.data(); d.lane = lane.data();
-        if (has_dc) {
-            csdr_emu::launch(dim3((nlanes * ngrp + 63) / 64), dim3(64), 0, k_dc_partial, d);
-            csdr_emu::launch(dim3(nlanes), dim3(64), 0, k_dc_scan, d);
-            csdr_emu::launch(dim3((nlanes + 31) / 32), dim3(32), 0, k_dc_finish, d);
-        }
+        d.in = x + pos; d.in_lane_stride = lane_stride; d.n = nx; d.nlanes = nlanes; d.G = G; d.ngrp = ngrp; d.nblk = nblk;
+        d.a1 = -1.0f + dc_alpha; d.c = -(double)d.a1; d.Vloc = Vloc.data(); d.carry = carry.data(); d.lane = lane.data();
+        { double A = 1.0; for (int i = 0; i < G; i++) A *= d.c; powA[0] = 1.0; for (int k = 1; k <= kDcGB; k++) powA[k] = powA[k - 1] * A; }
+        d.powA = powA.data();
+        auto launch = [](auto k, dim3 g, dim3 b, size_t smem, auto... a) { csdr_emu::launch(g, b, smem, k, a...); };
+        if (has_dc) be_launch_dc(launch, d, false);
         BackendParams b{};
         b.in = x + pos; b.in_lane_stride = lane_stride;
         b.out = demod ? (void *)((float *)out + pos) : (void *)((float2 *)out + pos); b.out_lane_stride = lane_stride;
         b.n = nx; b.nlanes = nlanes; b.L = L; b.W = W; b.G = G; b.nseg = nseg; b.ngrp = ngrp;
         b.has_dc = has_dc; b.has_agc = has_agc; b.demod = demod; b.dc_a1 = d.a1;
-        b.alpha = 0.1f; b.one_minus_alpha = 1.0 - (double)b.alpha; b.neg_half_alpha = -0.5f * b.alpha;
+        b.alpha = 0.1f; b.one_minus_alpha_f = (float)(1.0 - (double)b.alpha); b.neg_half_alpha = -0.5f * b.alpha;
         b.g_thr = design::agc_gain_threshold(thr_db); b.timeout = 1000; b.fm_ref = (float)(1.0f / (2 * design::kPi * kf));
         b.squelch_enabled = 1; b.gate = 1;
-        b.lane = lane.data(); b.seg_start = ss.data(); b.seg_end = se.data(); b.dcV = V.data();
+        b.lane = lane.data(); b.seg_start = ss.data(); b.seg_end = se.data();
+        b.dcVloc = Vloc.data(); b.dcCarry = carry.data(); b.dcPowA = powA.data(); b.nblk = nblk;
         b.nwords = nwords; b.FW = (1000 + 8 + L - 1) / L;
         b.exbits = exb.data(); b.gatebits = gb.data(); b.fsm_start = fs.data(); b.fsm_end = fe.data();
-        b.prev_gate = pg.data(); b.prev_sign = ps.data(); b.sgnr = sgr.data(); b.sgni = sgi.data(); b.fixups = fixups2;
-        csdr_emu::launch(dim3((nlanes * nseg + 31) / 32), dim3(32), 0, k_backend_spec, b);
-        csdr_emu::launch(dim3(nlanes), dim3(32), 0, k_backend_fixup, b);
-        if (has_agc) {
-            csdr_emu::launch(dim3((nlanes * nseg + 31) / 32), dim3(32), 0, k_backend_fsm, b);
-            csdr_emu::launch(dim3(nlanes), dim3(32), 0, k_backend_fsm_fix, b);
-            csdr_emu::launch(dim3((nlanes * nwords + 31) / 32), dim3(32), 0, k_backend_gate, b);
-        }
+        b.prev_gate = pg.data(); b.prev_sign = ps.data(); b.sgnr = sgr.data(); b.sgni = sgi.data();
+        b.first_bad = fb.data(); b.fixups = fixups2;
+        be_launch(launch, b);
+        if (dbg) for (int i = 0; i < nseg; i++) { float *d8 = dbg + 8 * i; d8[0] = ss[i].g; d8[1] = ss[i].y2p; d8[2] = ss[i].fm_re; d8[3] = ss[i].fm_im; d8[4] = se[i].g; d8[5] = se[i].y2p; d8[6] = se[i].fm_re; d8[7] = se[i].fm_im; }
         pos += nx;
     }
     if (fixups_out) { fixups_out[0] = fixups2[0]; fixups_out[1] = fixups2[1]; }

@@ -18,7 +18,7 @@ def load():
         L.emu_backend.restype = C.c_longlong
         L.emu_backend.argtypes = [C.c_int, C.c_longlong, C.c_int, C.c_float, C.c_int, C.c_float, C.c_int, C.c_float,
                                   C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_longlong, C.c_void_p, C.c_int, C.c_void_p,
-                                  C.POINTER(C.c_ulonglong)]
+                                  C.POINTER(C.c_ulonglong), C.c_void_p]
         L.emu_design_nco_constrain.restype = C.c_uint
         L.emu_design_nco_constrain.argtypes = [C.c_float]
         L.emu_design_rotation.restype = C.c_float
@@ -49,7 +49,8 @@ class Emu:
         assert n >= 0, "emu_frontend failed"
         return y[:n]
 
-    def backend(self, x, nlanes=1, has_dc=1, has_agc=1, thr=-40.0, demod=1, kf=0.3, L=512, W=384, G=128, chunks=None):
+    def backend(self, x, nlanes=1, has_dc=1, has_agc=1, thr=-40.0, demod=1, kf=0.3, L=512, W=384, G=128, chunks=None,
+                debug=None):
         x = np.ascontiguousarray(x, np.complex64).reshape(nlanes, -1)
         n = x.shape[1]
         chunks = [n] if chunks is None else list(chunks)
@@ -57,7 +58,7 @@ class Emu:
         out = np.zeros((nlanes, n), np.float32 if demod else np.complex64)
         fx = (C.c_ulonglong * 2)(0, 0)
         self.L.emu_backend(nlanes, n, has_dc, 0.0005, has_agc, thr, demod, kf, L, W, G, x.ctypes.data, n, ch.ctypes.data,
-                           len(chunks), out.ctypes.data, fx)
+                           len(chunks), out.ctypes.data, fx, debug.ctypes.data if debug is not None else None)
         return out, (fx[0], fx[1])
 
     def design_msresamp(self, rate, As=60.0):

@@ -4,7 +4,7 @@ BASELINE's full sizes.  Tolerance: tests/util.py."""
 import numpy as np
 import pytest
 
-from util import assert_parity, chunked, make_signal, snr_db
+from util import REL_TOL_AFTER_DCBLOCK, assert_parity, chunked, make_signal, snr_db
 
 pytestmark = pytest.mark.gpu
 
@@ -47,9 +47,9 @@ def test_config2_fm_with_agc(cs, orc):
     assert len(y) == len(ref)
     # the squelch gate must open and close on the same samples
     assert np.count_nonzero((y == 0) != (ref == 0)) == 0
-    assert_parity(y, ref, what="config 2")
+    assert_parity(y, ref, rel=REL_TOL_AFTER_DCBLOCK, what="config 2")
     y2 = run_chain(cs.Chain(2.56e6, 1e5, 200e3, cs.DeNBFM(0.3), agc=-40.0), x, [300001, 1024])[0]
-    assert_parity(y2, ref, what="config 2 (ragged chunks)")
+    assert_parity(y2, ref, rel=REL_TOL_AFTER_DCBLOCK, what="config 2 (ragged chunks)")
 
 
 def test_config3_channelizer_per_channel_fm(cs, orc):
@@ -93,7 +93,8 @@ def test_config5_batch_of_streams_am(cs, orc):
     for s in range(S):
         ref = orc.Chain(10e6, 1e6, 200e3, orc.DEMOD_AM, 0.0, -40.0).process(x[s])[0]
         assert len(outs[s]) == len(ref)
-        assert_parity(outs[s], ref, rel=3e-4, what=f"config 5 stream {s}")
+        skip = 2000                      # the first AGC attack (gain 1000 on a -8 dB carrier) dominates the peak
+        assert_parity(outs[s][skip:], ref[skip:], rel=REL_TOL_AFTER_DCBLOCK, what=f"config 5 stream {s}")
 
 
 def test_time_segment_sharding_matches_single_stream(cs, orc):
@@ -112,7 +113,7 @@ def test_time_segment_sharding_matches_single_stream(cs, orc):
     shard.seek(start - warm)
     y = shard.process(x[start - warm:])[0]
     assert len(y) == len(ref) - n_before
-    assert_parity(y[n_warm:], ref[n_before + n_warm:], rel=3e-4, what="time-segment shard")
+    assert_parity(y[n_warm:], ref[n_before + n_warm:], rel=REL_TOL_AFTER_DCBLOCK, what="time-segment shard")
 
 
 def test_full_size_properties_on_device(cs):
@@ -136,8 +137,17 @@ def test_full_size_properties_on_device(cs):
     lin = (y12 - (y1 + y2)).abs().max().item()
     assert lin <= 1e-4 * y12.abs().max().item()
     c = fe()
-    parts = [c.process(x1[i:i + (1 << 24) + 8])[0] for i in range(0, n, (1 << 24) + 8)]
-    assert torch.equal(torch.cat(parts), y1)
+    parts = torch.cat([c.process(x1[i:i + (1 << 24) + 8])[0] for i in range(0, n, (1 << 24) + 8)])
+    assert parts.shape == y1.shape                          # (the dc blocker's fp64 carries depend on the chunking)
+    assert (parts - y1).abs().max().item() <= 1e-4 * y1.abs().max().item()
+    r1 = cs.resampler(0.078125, 60.0)                      # the front end alone is bit-exact under re-chunking
+    h = r1._start()
+    a = r1._process(h, x2)
+    r1._done(h)
+    h = r1._start()
+    b = torch.cat([r1._process(h, x2[i:i + (1 << 24) + 8]) for i in range(0, n, (1 << 24) + 8)])
+    r1._done(h)
+    assert torch.equal(a, b)
     ch = cs.Chain(2.56e6, 1e5, 200e3, cs.DeNBFM(0.3), agc=-40.0)
     a = ch.process(x1 + x2)[0]
     assert len(a) == len(y1)

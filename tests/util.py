@@ -9,6 +9,12 @@ import numpy as np
 
 REL_TOL = 1e-4
 SNR_DB = 80.0
+# Discriminator / AM outputs taken AFTER the chain's dc blocker: the wanted carrier sits at (or next to) DC after the
+# offset mix, so the blocker's state |v| ~ |x| / alpha is ~10^3 times the signal and float32 rounding of the
+# recurrence (~6e-8 |v|) is ~1e-4 of the signal; where the squelch is open on noise only (~30 dB lower) the
+# discriminator turns that into ~5e-3 rad.  Any two float32 evaluation orders of liquid's recurrence differ by this
+# much.  Such outputs are held to SNR >= 80 dB and a peak-relative error of 5e-3.
+REL_TOL_AFTER_DCBLOCK = 5e-3
 
 
 def snr_db(y, ref):
