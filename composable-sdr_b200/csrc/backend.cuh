@@ -117,33 +117,47 @@ __global__ void __launch_bounds__(kDcGB) k_dc_local(const DcParams p)
     if (j < p.ngrp) p.Vloc[(long long)lane * p.ngrp + j] = make_double2(sr[t], si[t]);
 }
 
-// one thread per lane: carries of the (few) blocks, then the state after the last sample goes into the lane state
-__global__ void k_dc_carry(const DcParams p)
+// one CTA per lane: carries of the (few) blocks, then the state after the last sample goes into the lane state
+__global__ void __launch_bounds__(256) k_dc_carry(const DcParams p)
 {
-    const int lane = blockIdx.x * blockDim.x + threadIdx.x;
-    if (lane >= p.nlanes) return;
+    const int lane = blockIdx.x, t = threadIdx.x;
+    __shared__ double ar[1024], ai[1024];
     double2 *cl = p.carry + (long long)lane * p.nblk;
-    double cr = (double)p.lane[lane].dc_re, ci = (double)p.lane[lane].dc_im;
-    const double AB = p.powA[kDcGB];
-    for (int b = 0; b < p.nblk; b++) {
-        cl[b] = make_double2(cr, ci);
-        const int jl = min((b + 1) * kDcGB, p.ngrp) - 1;       // last group of block b
-        if (jl == (b + 1) * kDcGB - 1) {
-            const double2 v = p.Vloc[(long long)lane * p.ngrp + jl];
-            cr = cr * AB + v.x; ci = ci * AB + v.y;
+    // block aggregates (state contribution of a full block), fetched in parallel
+    for (int b = t; b < p.nblk && b < 1024; b += blockDim.x) {
+        const int jl = (b + 1) * kDcGB - 1;
+        double2 v = make_double2(0.0, 0.0);
+        if (jl < p.ngrp) v = p.Vloc[(long long)lane * p.ngrp + jl];
+        ar[b] = v.x; ai[b] = v.y;
+    }
+    __syncthreads();
+    if (t == 0) {
+        double cr = (double)p.lane[lane].dc_re, ci = (double)p.lane[lane].dc_im;
+        const double AB = p.powA[kDcGB];
+        for (int b = 0; b < p.nblk; b++) {
+            cl[b] = make_double2(cr, ci);
+            double vr, vi;
+            if (b < 1024) { vr = ar[b]; vi = ai[b]; }
+            else {
+                const int jl = (b + 1) * kDcGB - 1;
+                double2 v = make_double2(0.0, 0.0);
+                if (jl < p.ngrp) v = p.Vloc[(long long)lane * p.ngrp + jl];
+                vr = v.x; vi = v.y;
+            }
+            cr = cr * AB + vr; ci = ci * AB + vi;
         }
+        // state after n samples: restart from the last full-group boundary
+        const int jf = p.n / p.G;
+        const double2 v = dc_state_at(p.Vloc, p.carry, p.powA, p.ngrp, p.nblk, lane, jf);
+        float v1r = (float)v.x, v1i = (float)v.y;
+        const float2 *x = p.in + (long long)lane * p.in_lane_stride;
+        for (int i = jf * p.G; i < p.n; i++) {
+            const float2 s = x[i];
+            v1r = __fsub_rn(s.x, __fmul_rn(p.a1, v1r));
+            v1i = __fsub_rn(s.y, __fmul_rn(p.a1, v1i));
+        }
+        p.lane[lane].dc_re = v1r; p.lane[lane].dc_im = v1i;
     }
-    // state after n samples: restart from the last full-group boundary
-    const int jf = p.n / p.G;
-    const double2 v = dc_state_at(p.Vloc, p.carry, p.powA, p.ngrp, p.nblk, lane, jf);
-    float v1r = (float)v.x, v1i = (float)v.y;
-    const float2 *x = p.in + (long long)lane * p.in_lane_stride;
-    for (int i = jf * p.G; i < p.n; i++) {
-        const float2 s = x[i];
-        v1r = __fsub_rn(s.x, __fmul_rn(p.a1, v1r));
-        v1i = __fsub_rn(s.y, __fmul_rn(p.a1, v1i));
-    }
-    p.lane[lane].dc_re = v1r; p.lane[lane].dc_im = v1i;
 }
 
 // stand-alone dc blocker output (iirfilt_crcf_execute_block): one thread per group restarts the float32
@@ -233,10 +247,10 @@ __device__ __forceinline__ bool be_close(float a, float b, float atol = 0.f)
 }
 __device__ __forceinline__ bool be_match(const SegState &a, const SegState &b, int has_agc, int demod)
 {
-    bool ok = true;
-    if (has_agc) ok = ok && be_close(a.g, b.g) && be_close(a.y2p, b.y2p);
-    if (demod == 1) ok = ok && be_close(a.fm_re, b.fm_re, 1e-5f) && be_close(a.fm_im, b.fm_im, 1e-5f);
-    return ok;
+    // the discriminator history is the previous ungated sample x * g: it continues whenever the gain does (and is
+    // exactly the previous input sample when there is no AGC)
+    (void)demod;
+    return !has_agc || (be_close(a.g, b.g) && be_close(a.y2p, b.y2p));
 }
 
 // run samples [i0, i1) of one lane from state s / dc state (v1r, v1i).  EMIT: write outputs, threshold bits and
@@ -588,7 +602,7 @@ template <class Launch>
 inline void be_launch_dc(Launch &launch, const DcParams &d, bool apply)
 {
     launch(k_dc_local, dim3(d.nblk, d.nlanes), dim3(kDcGB), 0, d);
-    launch(k_dc_carry, dim3((d.nlanes + 63) / 64), dim3(64), 0, d);
+    launch(k_dc_carry, dim3(d.nlanes), dim3(256), 0, d);
     if (apply) {
         const long long items = (long long)d.nlanes * d.ngrp;
         launch(k_dc_apply, dim3((unsigned)((items + 127) / 128)), dim3(128), 0, d);

@@ -244,7 +244,7 @@ struct Backend {
     float dc_alpha = 0.0005f;
     float agc_bw = 0.1f, agc_thr = 0.f; unsigned agc_timeout = 1000; bool squelch = true, gate = true;
     float kf = 0.3f;
-    int L = 512, W = 384, G = 128;
+    int L = 512, W = 384, G = 128; bool fixed_L = false;
     DevBuf lane, Vloc, carry, powA, ss, se, fs, fe, exbits, gatebits, sgnr, sgni, prev_gate, prev_sign, first_bad, fixups;
     int FW = 3;
 
@@ -252,6 +252,7 @@ struct Backend {
     {
         nlanes = lanes;
         L = std::max(64, g_options[CSDR_OPT_AGC_SEGMENT]); W = std::max(16, g_options[CSDR_OPT_AGC_WARMUP]);
+        fixed_L = g_options[CSDR_OPT_AGC_SEGMENT] != 512;      // an explicit setting is taken literally
         G = 128;
         while (L % G || W % G) G /= 2;
         if (!has_agc) { W = (demod == 1) ? G : 0; if (W == 0) W = 0; }
@@ -310,6 +311,12 @@ struct Backend {
     {
         if (n <= 0) return;
         Launcher l{c.stream};
+        // segment length: the per-segment recurrences are latency bound, so aim for >= ~64k concurrent chains
+        // (shorter segments = more chains but relatively more warm-up work); L stays a multiple of G
+        int L = this->L;
+        if (has_agc && !fixed_L) {
+            while (L > G && (long long)nlanes * ((n + L - 1) / L) < 65536) L /= 2;
+        }
         int ngrp = (n + G - 1) / G, nseg = (n + L - 1) / L, nwords = (n + 31) / 32;
         size_t segs = (size_t)nlanes * nseg;
         ss.ensure(sizeof(SegState) * segs); se.ensure(sizeof(SegState) * segs);

@@ -29,9 +29,10 @@ __device__ __forceinline__ float4 fe_ldg_stream(const float4 *p)
 template <int MIX>
 __device__ __forceinline__ float2 fe_mix(float2 v, unsigned th, int quantize)
 {
-    if (MIX == 0) return v;
-    const float2 w = fe_phasor(th, quantize);
-    const float s = (MIX == 1) ? -w.y : w.y;
+    if ((MIX & 3) == 0) return v;
+    const float2 w = fe_phasor(th, (MIX & 4) ? 0 : ((MIX & 8) ? 1 : quantize));     // bits 2/3: flag known at compile time
+    constexpr int MODE = MIX & 3;
+    const float s = (MODE == 1) ? -w.y : w.y;
     return cf(v.x * w.x - v.y * s, v.y * w.x + v.x * s);
 }
 
@@ -107,34 +108,28 @@ __device__ __forceinline__ void fe_stage_c(const float2 *__restrict__ in, float2
     const float2 *C = in + (SH ? R * STR : 0);
     constexpr int NSLOTS = NOUT / R;
     for (int t = threadIdx.x; t < NSLOTS; t += 256) {
-        float ar[R], ai[R];
+        float2 acc[R];
 #pragma unroll
-        for (int r = 0; r < R; r++) {
-            const float2 e = C[((M + r) % R) * STR + t + (M + r) / R];
-            ar[r] = e.x; ai[r] = e.y;
-        }
+        for (int r = 0; r < R; r++) acc[r] = C[((M + r) % R) * STR + t + (M + r) / R];
 #pragma unroll
         for (int c = 0; c < R + 2 * M - 1; c++) {
             const float2 v = T[((c + SH) % R) * STR + t + (c + SH) / R];
 #pragma unroll
             for (int r = 0; r < R; r++) {
                 const int u = c - r;
-                if (u >= 0 && u < 2 * M) {
-                    ar[r] = fmaf(g[u], v.x, ar[r]);
-                    ai[r] = fmaf(g[u], v.y, ai[r]);
-                }
+                if (u >= 0 && u < 2 * M) ffma2(acc[r], g[u], v);
             }
         }
         if constexpr (LAST) {
             float2 *o = out + t * R;
 #pragma unroll
-            for (int r = 0; r < R; r++) o[r] = cf(ar[r] * zeta, ai[r] * zeta);
+            for (int r = 0; r < R; r++) o[r] = cf(acc[r].x * zeta, acc[r].y * zeta);
         } else {
             // q = R t + r -> plane r & 1, pair p = (R/2) t + (r >> 1) -> sub-array p & (D2-1), index p / D2
             static_assert(R == 8 && (D2 == 8 || D2 == 4), "store pattern written for R = 8 producers");
             float2 *o = (D2 == 8) ? out + ((t & 1) << 2) * STR2 + (t >> 1) : out + t;
 #pragma unroll
-            for (int r = 0; r < R; r++) o[((r & 1) * D2 + (r >> 1)) * STR2] = cf(ar[r], ai[r]);
+            for (int r = 0; r < R; r++) o[((r & 1) * D2 + (r >> 1)) * STR2] = acc[r];
         }
     }
 }
@@ -152,6 +147,33 @@ __device__ __forceinline__ void fe_run_stages(const FrontendParams &p, float2 *s
     if constexpr (s > 0) fe_run_stages<S, s - 1>(p, smem);
 }
 
+// ceil(num / st) for num < 2^57, st < 2^26 without a 64-bit division: fp64 estimate + exact integer correction
+__device__ __forceinline__ long long fe_ceil_div(unsigned long long num, unsigned st, double inv_st)
+{
+    long long q = (long long)((double)num * inv_st);
+    long long r = (long long)num - q * (long long)st;
+    while (r < 0) { q--; r += st; }
+    while (r >= (long long)st) { q++; r -= st; }
+    return q + (r != 0);
+}
+
+struct FeTileInfo { long long lo; int bulk, oA, oB, pad; };
+
+// everything one tile needs that is not per-thread work: computed by ONE thread, one tile ahead
+template <int S>
+__device__ __forceinline__ void fe_tile_info(const FrontendParams &p, const float2 *xs, int tile, double inv_st, FeTileInfo &ti)
+{
+    constexpr FeGeom G = FeStd<S>::G;
+    const long long kArel = (long long)tile * G.Tc;                 // pushes relative to K0
+    const long long kBrel = min(kArel + (long long)G.Tc, p.K1 - p.K0);
+    ti.lo = (p.K0 + kArel - kHcPad) * (1LL << S) + G.d[S];
+    ti.bulk = fe_tile_is_bulk<S>(p, xs, ti.lo) ? 1 : 0;
+    // outputs emitted by pushes [kA, kB): o' with kArel*2^24 <= ph0 + o'*step < kBrel*2^24
+    const unsigned long long a = (unsigned long long)kArel << 24, b = (unsigned long long)kBrel << 24;
+    ti.oA = (a > p.ph0) ? (int)fe_ceil_div(a - p.ph0, p.step, inv_st) : 0;
+    ti.oB = (b > p.ph0) ? (int)fe_ceil_div(b - p.ph0, p.step, inv_st) : 0;
+}
+
 template <int S>
 __global__ void __launch_bounds__(256, 2) k_frontend_std(const CSDR_GRID_CONSTANT FrontendParams p)
 {
@@ -161,7 +183,7 @@ __global__ void __launch_bounds__(256, 2) k_frontend_std(const CSDR_GRID_CONSTAN
     float2 *smem = reinterpret_cast<float2 *>(smem_raw);
     float *bank_s = reinterpret_cast<float *>(smem_raw) + 2 * G.total_f2;
     float2 *raw = smem + G.off_raw;
-    __shared__ int s_orange[2];
+    __shared__ FeTileInfo s_info[2];
     __shared__ __align__(8) unsigned long long s_bar;
 
     const int npfb = 1 << p.bits;
@@ -174,48 +196,47 @@ __global__ void __launch_bounds__(256, 2) k_frontend_std(const CSDR_GRID_CONSTAN
     float2 *ys = p.y + (long long)blockIdx.y * p.y_stride;
     const unsigned mask = (unsigned)npfb - 1u;
     const int sh = 24 - p.bits;
-    auto tile_lo = [&](int tile) { return (p.K0 + (long long)tile * G.Tc - kHcPad) * (1LL << S) + G.d[S]; };
+    const double inv_st = 1.0 / (double)p.step;
 
     // bulk-copy pipeline: the raw samples of the next tile are fetched by the TMA while this tile is filtered
     unsigned parity = 0;
     if (threadIdx.x == 0) {
         bulk_init(&s_bar);
-        const int t0 = blockIdx.x;
-        if (t0 < p.ntiles && fe_tile_is_bulk<S>(p, xs, tile_lo(t0)))
-            bulk_copy_g2s(raw, xs + (tile_lo(t0) - p.n0), NS * (unsigned)sizeof(float2), &s_bar);
+        if ((int)blockIdx.x < p.ntiles) {
+            fe_tile_info<S>(p, xs, (int)blockIdx.x, inv_st, s_info[0]);
+            if (s_info[0].bulk) bulk_copy_g2s(raw, xs + (s_info[0].lo - p.n0), NS * (unsigned)sizeof(float2), &s_bar);
+        }
     }
     __syncthreads();
 
-    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
-        const long long kArel = (long long)tile * G.Tc;                 // pushes relative to K0
-        const long long kBrel = min(kArel + (long long)G.Tc, p.K1 - p.K0);
-        if (threadIdx.x == 0) {
-            // outputs emitted by pushes [kA, kB): o' with kArel*2^24 <= ph0 + o'*step < kBrel*2^24
-            const unsigned long long st = p.step;
-            const unsigned long long a = (unsigned long long)kArel << 24, b = (unsigned long long)kBrel << 24;
-            s_orange[0] = (a > p.ph0) ? (int)((a - p.ph0 + st - 1) / st) : 0;
-            s_orange[1] = (b > p.ph0) ? (int)((b - p.ph0 + st - 1) / st) : 0;
-        }
-        const long long lo = tile_lo(tile);
-        const bool bulk = fe_tile_is_bulk<S>(p, xs, lo);
+    int cur = 0;
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, cur ^= 1) {
+        const long long lo = s_info[cur].lo;
+        const bool bulk = s_info[cur].bulk != 0;
         if (bulk) { bulk_wait(&s_bar, parity); parity ^= 1u; }
-        if (p.mix_mode == 1)      fe_load_top<S, 1>(p, xs, hs, smem + G.off[S], lo, raw, bulk);
-        else if (p.mix_mode == 2) fe_load_top<S, 2>(p, xs, hs, smem + G.off[S], lo, raw, bulk);
-        else                      fe_load_top<S, 0>(p, xs, hs, smem + G.off[S], lo, raw, bulk);
+        float2 *top = smem + G.off[S];
+        if (p.mix_mode == 0)      fe_load_top<S, 0>(p, xs, hs, top, lo, raw, bulk);
+        else if (p.quantize) { if (p.mix_mode == 1) fe_load_top<S, 1 | 8>(p, xs, hs, top, lo, raw, bulk);
+                               else                 fe_load_top<S, 2 | 8>(p, xs, hs, top, lo, raw, bulk); }
+        else                 { if (p.mix_mode == 1) fe_load_top<S, 1 | 4>(p, xs, hs, top, lo, raw, bulk);
+                               else                 fe_load_top<S, 2 | 4>(p, xs, hs, top, lo, raw, bulk); }
         __syncthreads();
-        // the staging buffer is free again: start fetching the next tile of this CTA
+        // the staging buffer is free again: prepare the next tile of this CTA and start fetching it
         if (threadIdx.x == 0) {
             const int nt = tile + (int)gridDim.x;
-            if (nt < p.ntiles && fe_tile_is_bulk<S>(p, xs, tile_lo(nt)))
-                bulk_copy_g2s(raw, xs + (tile_lo(nt) - p.n0), NS * (unsigned)sizeof(float2), &s_bar);
+            if (nt < p.ntiles) {
+                fe_tile_info<S>(p, xs, nt, inv_st, s_info[cur ^ 1]);
+                if (s_info[cur ^ 1].bulk)
+                    bulk_copy_g2s(raw, xs + (s_info[cur ^ 1].lo - p.n0), NS * (unsigned)sizeof(float2), &s_bar);
+            }
         }
 
         fe_run_stages<S, S - 1>(p, smem);
 
         // arbitrary resampler: output o' -> push k = (ph0 + o'*step) >> 24, branch = next `bits` bits of the phase
         {
-            const float2 *cbuf = smem + G.off[0] + kHcPad - (int)kArel;   // cbuf[k] for k relative to K0
-            const int oA = s_orange[0], oB = s_orange[1];
+            const float2 *cbuf = smem + G.off[0] + kHcPad - tile * G.Tc;   // cbuf[k] for k relative to K0
+            const int oA = s_info[cur].oA, oB = s_info[cur].oB;
             for (int o = oA + threadIdx.x; o < oB; o += 256) {
                 const unsigned long long ph = p.ph0 + (unsigned long long)(unsigned)o * p.step;
                 const float2 *c = cbuf + (int)(ph >> 24);

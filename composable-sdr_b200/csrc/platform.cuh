@@ -56,4 +56,19 @@ constexpr int kHcPad     = 16;   // c-rate history carried into every tile (>= k
 
 __host__ __device__ inline float2 cf(float re, float im) { float2 z; z.x = re; z.y = im; return z; }
 
+// acc += g * v on both halves of a complex sample with ONE instruction: Blackwell's packed FP32 FMA (PTX
+// fma.rn.f32x2, SASS FFMA2; a uniform real tap is broadcast as a scalar operand).  Two IEEE fused multiply-adds,
+// bit-identical to two fmaf().
+__device__ __forceinline__ void ffma2(float2 &acc, float g, float2 v)
+{
+#ifdef CSDR_EMU
+    acc.x = fmaf(g, v.x, acc.x); acc.y = fmaf(g, v.y, acc.y);
+#else
+    unsigned long long a = *reinterpret_cast<unsigned long long *>(&acc);
+    const unsigned long long b = *reinterpret_cast<const unsigned long long *>(&v);
+    asm("{\n\t.reg .b64 gg;\n\tmov.b64 gg, {%2, %2};\n\tfma.rn.f32x2 %0, gg, %1, %0;\n\t}" : "+l"(a) : "l"(b), "f"(g));
+    acc = *reinterpret_cast<float2 *>(&a);
+#endif
+}
+
 }  // namespace csdr

@@ -65,12 +65,14 @@ def config3(n, channels=16, sr=2.56e6):
 
 
 def config4(n, channels=1024, active=64, sr=1e9):
-    """C4: `active` of `channels` channels carry NBFM with random amplitudes 0.03-0.5 (0.01, SURVEY's lower bound, sits
-    exactly on the -40 dB squelch threshold, where the gate decision is ill-conditioned in float32)."""
+    """C4: `active` of `channels` channels carry NBFM with random amplitudes (64 of 1024 active)."""
     g = _rng(4)
-    x = noise(n, 0.003, 40)
+    # channel outputs of the un-normalised M-point analyzer carry a tone of amplitude A as A*M and white noise of
+    # std s as ~s*sqrt(M): noise-only channels must stay below the -40 dB squelch threshold (they are gated), active
+    # ones well above it
+    x = noise(n, 3e-5, 40)
     idx = g.choice(channels, size=active, replace=False)
-    amps = g.uniform(0.03, 0.5, size=active)
+    amps = g.uniform(0.003, 0.05, size=active)
     for k, a in zip(idx, amps):
         f0 = (k - (channels - 1) / 2.0) / channels * sr
         x = x + fm_carrier(n, sr, f0, a, 0.1 * sr / channels, sr / channels / 50.0)
