@@ -53,7 +53,8 @@ struct BackendParams {
     unsigned *prev_gate;                       // [nlanes] gate of the sample before this chunk
     unsigned *first_bad;                       // [nlanes][2] first segment whose start state does not continue its
                                                // predecessor (gain loop, squelch FSM); 0xffffffff = none
-    unsigned long long *fixups;                // [2] segments re-run: gain loop, squelch FSM (diagnostic)
+    unsigned *bad_list; unsigned *bad_count; unsigned bad_cap;   // segments to refine after the first verification
+    unsigned long long *fixups;                // [3] segments re-run in order: gain loop, squelch FSM; refined in parallel
 };
 
 // ------------------------------------------------------------------------------------------ dc blocker
@@ -327,6 +328,7 @@ __global__ void __launch_bounds__(128) k_backend_spec(const BackendParams p)
     if (t >= (long long)p.nlanes * p.nseg) return;
     const int lane = (int)(t / p.nseg), seg = (int)(t - (long long)lane * p.nseg);
     const int b0 = seg * p.L, b1 = min(b0 + p.L, p.n);
+    if (t == 0) *p.bad_count = 0;
     AgcRun s; float v1r, v1i;
     int w0 = b0 - p.W;
     const LaneState ls = p.lane[lane];
@@ -351,14 +353,42 @@ __global__ void __launch_bounds__(128) k_backend_spec(const BackendParams p)
     p.seg_end[t] = be_pack(s);
 }
 
-// grid-wide verification of the gain speculation: first segment per lane that does not continue its predecessor
-__global__ void k_backend_verify(const BackendParams p)
+// grid-wide verification of the gain speculation.  pass 0: collect the segments whose start state does not continue
+// their predecessor's end state; pass 1 (after k_backend_refine): first such segment per lane, for the in-order repair.
+__global__ void k_backend_verify(const BackendParams p, int pass)
 {
     long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (long long)p.nlanes * p.nseg) return;
     const int lane = (int)(t / p.nseg), seg = (int)(t - (long long)lane * p.nseg);
-    if (seg > 0 && !be_match(p.seg_start[t], p.seg_end[t - 1], p.has_agc, p.demod))
+    if (seg == 0 || be_match(p.seg_start[t], p.seg_end[t - 1], p.has_agc, p.demod)) return;
+    if (pass == 0) {
+        const unsigned idx = atomicAdd(p.bad_count, 1u);
+        if (idx < p.bad_cap) p.bad_list[idx] = (unsigned)t;
+    } else {
         atomicMin(&p.first_bad[2 * lane], (unsigned)seg);
+    }
+}
+
+// second chance, in parallel: a start state that is slightly off (the warm-up met an un-damped stretch of the
+// loop) is replaced by the predecessor's END state, which is accurate because the predecessor's own L samples
+// damped its error; the segment is re-run from there.  (A predecessor that is being refined at the same time may
+// be read before or after its update: both values are valid to well below the tolerance.)
+__global__ void __launch_bounds__(128) k_backend_refine(const BackendParams p)
+{
+    const unsigned count = min(*p.bad_count, p.bad_cap);
+    for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < count; idx += gridDim.x * blockDim.x) {
+        const long long t = p.bad_list[idx];
+        const int lane = (int)(t / p.nseg), seg = (int)(t - (long long)lane * p.nseg);
+        const SegState pe = p.seg_end[t - 1];
+        AgcRun s; s.g = pe.g; s.y2p = pe.y2p; s.fr = pe.fm_re; s.fi = pe.fm_im;
+        float v1r, v1i;
+        const int b0 = seg * p.L, b1 = min(b0 + p.L, p.n);
+        be_dc_state(p, lane, b0, v1r, v1i);
+        p.seg_start[t] = pe;
+        be_run<true>(p, lane, s, v1r, v1i, b0, b1);
+        p.seg_end[t] = be_pack(s);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(p.fixups + 2, (unsigned long long)count);
 }
 
 // one CTA per lane: re-run the misses in stream order (rare), store the lane's gain state
@@ -615,7 +645,11 @@ inline void be_launch(Launch &launch, const BackendParams &b)
     const long long segs = (long long)b.nlanes * b.nseg;
     const unsigned gb = (unsigned)((segs + 127) / 128);
     launch(k_backend_spec, dim3(gb), dim3(128), 0, b);
-    launch(k_backend_verify, dim3(gb), dim3(128), 0, b);
+    if (b.has_agc) {
+        launch(k_backend_verify, dim3(gb), dim3(128), 0, b, 0);
+        launch(k_backend_refine, dim3(64), dim3(128), 0, b);
+        launch(k_backend_verify, dim3(gb), dim3(128), 0, b, 1);
+    }
     launch(k_backend_fixup, dim3(b.nlanes), dim3(128), 0, b);
     if (b.has_agc) {
         launch(k_backend_fsm, dim3(gb), dim3(128), 0, b);

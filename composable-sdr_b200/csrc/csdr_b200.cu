@@ -245,8 +245,8 @@ struct Backend {
     float agc_bw = 0.1f, agc_thr = 0.f; unsigned agc_timeout = 1000; bool squelch = true, gate = true;
     float kf = 0.3f;
     int L = 512, W = 384, G = 128; bool fixed_L = false;
-    DevBuf lane, Vloc, carry, powA, ss, se, fs, fe, exbits, gatebits, sgnr, sgni, prev_gate, prev_sign, first_bad, fixups;
-    int FW = 3;
+    DevBuf lane, Vloc, carry, powA, ss, se, fs, fe, exbits, gatebits, sgnr, sgni, prev_gate, prev_sign, first_bad, bad_list, bad_count, fixups;
+    int FW = 3; unsigned long long last_refined = 0;
 
     void init(const Ctx &c, int lanes, float g0 = 1000.0f, int mode0 = SQ_ENABLED)
     {
@@ -275,7 +275,8 @@ struct Backend {
             CK(cudaMemcpyAsync(powA.p, pw.data(), sizeof(double) * pw.size(), cudaMemcpyHostToDevice, c.stream));
             c.sync();
         }
-        fixups.ensure(2 * sizeof(unsigned long long)); CK(cudaMemsetAsync(fixups.p, 0, fixups.cap, c.stream));
+        fixups.ensure(3 * sizeof(unsigned long long)); CK(cudaMemsetAsync(fixups.p, 0, fixups.cap, c.stream));
+        bad_list.ensure(sizeof(unsigned) * 65536); bad_count.ensure(sizeof(unsigned)); CK(cudaMemsetAsync(bad_count.p, 0, bad_count.cap, c.stream));
         c.sync();
     }
     struct Launcher {
@@ -346,14 +347,17 @@ struct Backend {
         b.prev_gate = prev_gate.as<unsigned>(); b.prev_sign = prev_sign.as<unsigned>();
         b.sgnr = sgnr.as<unsigned>(); b.sgni = sgni.as<unsigned>();
         b.first_bad = first_bad.as<unsigned>();
+        b.bad_list = bad_list.as<unsigned>(); b.bad_count = bad_count.as<unsigned>(); b.bad_cap = 65536;
         b.fixups = fixups.as<unsigned long long>();
         be_launch(l, b);
     }
     unsigned long long read_fixups(const Ctx &c)
     {
-        unsigned long long v[2] = {0, 0};
+        // sequential (in-order) repairs only: these are the ones that cost time; parallel refinements are v[2]
+        unsigned long long v[3] = {0, 0, 0};
         CK(cudaMemcpyAsync(v, fixups.p, sizeof(v), cudaMemcpyDeviceToHost, c.stream));
         c.sync();
+        last_refined = v[2];
         return v[0] + v[1];
     }
     LaneState read_lane(const Ctx &c, int i)

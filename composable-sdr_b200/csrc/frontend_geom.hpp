@@ -69,7 +69,7 @@ __host__ __device__ constexpr int fe_std_tc(int S)
 __host__ __device__ constexpr FeGeom fe_make_geom_std(int S)
 {
     FeStdM mm{};
-    return fe_make_geom(S, fe_std_tc(S), mm.v, 1, 1);
+    return fe_make_geom(S, fe_std_tc(S), mm.v, 1, 0);
 }
 constexpr int kFeStdMaxS = 6;      // k_frontend_std is instantiated for S = 1..6
 

@@ -4,8 +4,8 @@
 // access is base register + immediate, loop trip counts are constants and the half-band taps are read straight
 // from the kernel-parameter constant bank by the FFMAs.  Other plans use the generic k_frontend.
 //
-// Raw input tiles are staged in shared memory by TMA bulk copies (cp.async.bulk + mbarrier) one tile ahead, so the
-// HBM latency is hidden behind the filtering of the previous tile; the mixer then reads pairs with LDS.128.
+// Raw input tiles are fetched one tile ahead with 16-byte streaming loads held in registers, so the HBM latency is
+// hidden behind the filtering of the previous tile.
 #pragma once
 #include "frontend.cuh"
 
@@ -37,8 +37,8 @@ __device__ __forceinline__ float2 fe_mix(float2 v, unsigned th, int quantize)
 }
 
 // ---- top level: (mix) -> shared, in the consumer's de-interleaved layout ------------------------------------
-// A tile that lies inside the chunk at a 16-byte aligned address is "bulk": its raw samples were staged in shared
-// memory by a TMA bulk copy issued while the previous tile was being filtered.
+// A tile that lies inside the chunk at a 16-byte aligned address is "bulk": its raw samples are prefetched into
+// registers (fe_prefetch) while the previous tile is being filtered.
 template <int S>
 __device__ __forceinline__ bool fe_tile_is_bulk(const FrontendParams &p, const float2 *xs, long long lo)
 {
@@ -47,10 +47,28 @@ __device__ __forceinline__ bool fe_tile_is_bulk(const FrontendParams &p, const f
     return rel0 >= 0 && rel0 + NS <= p.nx && ((reinterpret_cast<uintptr_t>(xs + rel0) & 15) == 0);
 }
 
+template <int S> struct FePrefetch {
+    static constexpr int NP = FeStd<S>::G.n[S] / 2, IT = (NP + 255) / 256;
+    float4 v[IT];
+};
+
+// issue the 16-byte loads of a bulk tile; they complete while the previous tile is being filtered
+template <int S>
+__device__ __forceinline__ void fe_prefetch(FePrefetch<S> &pre, const FrontendParams &p, const float2 *__restrict__ xs,
+                                            long long lo)
+{
+    const float4 *src = reinterpret_cast<const float4 *>(xs + (lo - p.n0));
+#pragma unroll
+    for (int k = 0; k < FePrefetch<S>::IT; k++) {
+        const int pi = threadIdx.x + 256 * k;
+        if (pi < FePrefetch<S>::NP) pre.v[k] = fe_ldg_stream(src + pi);
+    }
+}
+
 template <int S, int MIX>
 __device__ __forceinline__ void fe_load_top(const FrontendParams &p, const float2 *__restrict__ xs,
                                             const float2 *__restrict__ hs, float2 *__restrict__ dst, long long lo,
-                                            const float2 *__restrict__ raw, bool bulk)
+                                            const FePrefetch<S> &pre, bool bulk)
 {
     constexpr FeGeom G = FeStd<S>::G;
     constexpr int NS = G.n[S], STR = G.stride[S], D = G.R[S - 1];
@@ -60,16 +78,14 @@ __device__ __forceinline__ void fe_load_top(const FrontendParams &p, const float
     const unsigned th0 = p.theta0 + (unsigned)lo * p.dtheta;
     const bool inside = rel0 >= 0 && rel0 + NS <= p.nx;
     if (bulk) {
-        // one 16-byte shared load = the (even, odd) pair p; pair -> sub-array p & 7, index p >> 3
-        const float4 *src = reinterpret_cast<const float4 *>(raw);
+        // one 16-byte load = the (even, odd) pair p; pair -> sub-array p & 7, index p >> 3
         float2 *dE = dst + (tid & 7) * STR + (tid >> 3);
         float2 *dO = dE + D * STR;
-        constexpr int NP = NS / 2, IT = (NP + 255) / 256;
 #pragma unroll
-        for (int k = 0; k < IT; k++) {
+        for (int k = 0; k < FePrefetch<S>::IT; k++) {
             const int pi = tid + 256 * k;
-            if (pi < NP) {
-                const float4 v = src[pi];
+            if (pi < FePrefetch<S>::NP) {
+                const float4 v = pre.v[k];
                 const unsigned th = th0 + (unsigned)(2 * pi) * p.dtheta;
                 dE[32 * k] = fe_mix<MIX>(cf(v.x, v.y), th, p.quantize);
                 dO[32 * k] = fe_mix<MIX>(cf(v.z, v.w), th + p.dtheta, p.quantize);
@@ -178,13 +194,10 @@ template <int S>
 __global__ void __launch_bounds__(256, 2) k_frontend_std(const CSDR_GRID_CONSTANT FrontendParams p)
 {
     constexpr FeGeom G = FeStd<S>::G;
-    constexpr int NS = G.n[S];
     CSDR_DYN_SMEM(smem_raw);
     float2 *smem = reinterpret_cast<float2 *>(smem_raw);
     float *bank_s = reinterpret_cast<float *>(smem_raw) + 2 * G.total_f2;
-    float2 *raw = smem + G.off_raw;
-    __shared__ FeTileInfo s_info[2];
-    __shared__ __align__(8) unsigned long long s_bar;
+    __shared__ FeTileInfo s_info[3];
 
     const int npfb = 1 << p.bits;
     for (int i = threadIdx.x; i < npfb * kHsub; i += 256) {
@@ -197,39 +210,36 @@ __global__ void __launch_bounds__(256, 2) k_frontend_std(const CSDR_GRID_CONSTAN
     const unsigned mask = (unsigned)npfb - 1u;
     const int sh = 24 - p.bits;
     const double inv_st = 1.0 / (double)p.step;
+    const int gstep = (int)gridDim.x;
 
-    // bulk-copy pipeline: the raw samples of the next tile are fetched by the TMA while this tile is filtered
-    unsigned parity = 0;
+    // Software pipeline over the tiles of this (persistent) CTA: the raw samples of tile i+1 are loaded into
+    // registers while tile i is filtered, so the sequential load -> mix -> filter chain never waits for HBM.
+    // (A TMA bulk-copy staging buffer does the same but costs two extra passes over shared memory, the resource this
+    // kernel is bound by; measured 217 us vs the register pipeline, see DESIGN.md.)  Tile bookkeeping (absolute
+    // position, alignment, output range) is done by one thread, two tiles ahead.
     if (threadIdx.x == 0) {
-        bulk_init(&s_bar);
-        if ((int)blockIdx.x < p.ntiles) {
-            fe_tile_info<S>(p, xs, (int)blockIdx.x, inv_st, s_info[0]);
-            if (s_info[0].bulk) bulk_copy_g2s(raw, xs + (s_info[0].lo - p.n0), NS * (unsigned)sizeof(float2), &s_bar);
-        }
+        const int t0 = (int)blockIdx.x;
+        if (t0 < p.ntiles) fe_tile_info<S>(p, xs, t0, inv_st, s_info[0]);
+        if (t0 + gstep < p.ntiles) fe_tile_info<S>(p, xs, t0 + gstep, inv_st, s_info[1]);
     }
     __syncthreads();
+    FePrefetch<S> pre;
+    if ((int)blockIdx.x < p.ntiles && s_info[0].bulk) fe_prefetch<S>(pre, p, xs, s_info[0].lo);
 
     int cur = 0;
-    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, cur ^= 1) {
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gstep) {
+        const int nxt = cur == 2 ? 0 : cur + 1, nxt2 = nxt == 2 ? 0 : nxt + 1;
         const long long lo = s_info[cur].lo;
         const bool bulk = s_info[cur].bulk != 0;
-        if (bulk) { bulk_wait(&s_bar, parity); parity ^= 1u; }
         float2 *top = smem + G.off[S];
-        if (p.mix_mode == 0)      fe_load_top<S, 0>(p, xs, hs, top, lo, raw, bulk);
-        else if (p.quantize) { if (p.mix_mode == 1) fe_load_top<S, 1 | 8>(p, xs, hs, top, lo, raw, bulk);
-                               else                 fe_load_top<S, 2 | 8>(p, xs, hs, top, lo, raw, bulk); }
-        else                 { if (p.mix_mode == 1) fe_load_top<S, 1 | 4>(p, xs, hs, top, lo, raw, bulk);
-                               else                 fe_load_top<S, 2 | 4>(p, xs, hs, top, lo, raw, bulk); }
+        if (p.mix_mode == 0)      fe_load_top<S, 0>(p, xs, hs, top, lo, pre, bulk);
+        else if (p.quantize) { if (p.mix_mode == 1) fe_load_top<S, 1 | 8>(p, xs, hs, top, lo, pre, bulk);
+                               else                 fe_load_top<S, 2 | 8>(p, xs, hs, top, lo, pre, bulk); }
+        else                 { if (p.mix_mode == 1) fe_load_top<S, 1 | 4>(p, xs, hs, top, lo, pre, bulk);
+                               else                 fe_load_top<S, 2 | 4>(p, xs, hs, top, lo, pre, bulk); }
+        if (threadIdx.x == 0 && tile + 2 * gstep < p.ntiles) fe_tile_info<S>(p, xs, tile + 2 * gstep, inv_st, s_info[nxt2]);
         __syncthreads();
-        // the staging buffer is free again: prepare the next tile of this CTA and start fetching it
-        if (threadIdx.x == 0) {
-            const int nt = tile + (int)gridDim.x;
-            if (nt < p.ntiles) {
-                fe_tile_info<S>(p, xs, nt, inv_st, s_info[cur ^ 1]);
-                if (s_info[cur ^ 1].bulk)
-                    bulk_copy_g2s(raw, xs + (s_info[cur ^ 1].lo - p.n0), NS * (unsigned)sizeof(float2), &s_bar);
-            }
-        }
+        if (tile + gstep < p.ntiles && s_info[nxt].bulk) fe_prefetch<S>(pre, p, xs, s_info[nxt].lo);
 
         fe_run_stages<S, S - 1>(p, smem);
 
@@ -252,6 +262,7 @@ __global__ void __launch_bounds__(256, 2) k_frontend_std(const CSDR_GRID_CONSTAN
             }
         }
         __syncthreads();   // smem is reused by the next tile
+        cur = nxt;
     }
 }
 

@@ -71,7 +71,7 @@ long long emu_backend(int nlanes, long long lane_stride, int has_dc, float dc_al
 {
     std::vector<LaneState> lane(nlanes);
     for (auto &l : lane) { l.dc_re = l.dc_im = 0; l.g = 1000.0f; l.y2p = 1.0f; l.mode = SQ_ENABLED; l.timer = 0; l.fm_re = l.fm_im = 0; }
-    unsigned long long fixups2[2] = {0, 0};
+    unsigned long long fixups2[3] = {0, 0, 0};
     long long pos = 0;
     for (int c = 0; c < nchunks; c++) {
         int nx = (int)chunks[c];
@@ -83,7 +83,8 @@ long long emu_backend(int nlanes, long long lane_stride, int has_dc, float dc_al
         std::vector<FsmState> fs((size_t)nlanes * nseg), fe((size_t)nlanes * nseg);
         int nwords = (nx + 31) / 32;
         std::vector<unsigned> exb((size_t)nlanes * nwords), gb((size_t)nlanes * nwords), pg(nlanes, 0), ps(nlanes, 0);
-        std::vector<unsigned> sgr((size_t)nlanes * nwords), sgi((size_t)nlanes * nwords), fb(2 * nlanes, 0xffffffffu);
+        std::vector<unsigned> sgr((size_t)nlanes * nwords), sgi((size_t)nlanes * nwords), fb(2 * nlanes, 0xffffffffu), blist(4096);
+        unsigned bcount = 0;
         DcParams d{};
         d.in = x + pos; d.in_lane_stride = lane_stride; d.n = nx; d.nlanes = nlanes; d.G = G; d.ngrp = ngrp; d.nblk = nblk;
         d.a1 = -1.0f + dc_alpha; d.c = -(double)d.a1; d.Vloc = Vloc.data(); d.carry = carry.data(); d.lane = lane.data();
@@ -104,12 +105,12 @@ long long emu_backend(int nlanes, long long lane_stride, int has_dc, float dc_al
         b.nwords = nwords; b.FW = (1000 + 8 + L - 1) / L;
         b.exbits = exb.data(); b.gatebits = gb.data(); b.fsm_start = fs.data(); b.fsm_end = fe.data();
         b.prev_gate = pg.data(); b.prev_sign = ps.data(); b.sgnr = sgr.data(); b.sgni = sgi.data();
-        b.first_bad = fb.data(); b.fixups = fixups2;
+        b.first_bad = fb.data(); b.fixups = fixups2; b.bad_list = blist.data(); b.bad_count = &bcount; b.bad_cap = 4096;
         be_launch(launch, b);
         if (dbg) for (int i = 0; i < nseg; i++) { float *d8 = dbg + 8 * i; d8[0] = ss[i].g; d8[1] = ss[i].y2p; d8[2] = ss[i].fm_re; d8[3] = ss[i].fm_im; d8[4] = se[i].g; d8[5] = se[i].y2p; d8[6] = se[i].fm_re; d8[7] = se[i].fm_im; }
         pos += nx;
     }
-    if (fixups_out) { fixups_out[0] = fixups2[0]; fixups_out[1] = fixups2[1]; }
+    if (fixups_out) { fixups_out[0] = fixups2[0]; fixups_out[1] = fixups2[1]; fixups_out[2] = fixups2[2]; }
     return pos;
 }
 

@@ -56,10 +56,10 @@ class Emu:
         chunks = [n] if chunks is None else list(chunks)
         ch = np.array(chunks, np.int64)
         out = np.zeros((nlanes, n), np.float32 if demod else np.complex64)
-        fx = (C.c_ulonglong * 2)(0, 0)
+        fx = (C.c_ulonglong * 3)(0, 0, 0)
         self.L.emu_backend(nlanes, n, has_dc, 0.0005, has_agc, thr, demod, kf, L, W, G, x.ctypes.data, n, ch.ctypes.data,
                            len(chunks), out.ctypes.data, fx, debug.ctypes.data if debug is not None else None)
-        return out, (fx[0], fx[1])
+        return out, (fx[0], fx[1], fx[2])
 
     def design_msresamp(self, rate, As=60.0):
         S, step, npfb = C.c_uint(0), C.c_uint(0), C.c_uint(0)
