@@ -40,6 +40,7 @@ struct BackendParams {
     float g_thr;                               // rssi > threshold  <=>  g < g_thr  (bisected on the host)
     unsigned timeout; float fm_ref;
     int squelch_enabled;
+    int exact_math;                            // 1: library expf/logf/atan2f in the per-sample loop (slower)
     int gate;                                  // 1: zero the output unless squelch status == SIGNALHI (Liquid.chs:700-704)
     LaneState *lane;
     SegState *seg_start, *seg_end;             // [nlanes][nseg] gain-loop state at segment boundaries
@@ -215,6 +216,30 @@ __device__ __forceinline__ void fsm_step(int &mode, unsigned &timer, bool ex, un
     }
 }
 
+// arg(x + jy) with a degree-8 minimax polynomial for atan on [0, 1] (max error 1.1e-7 rad, float32-limited; the
+// library atan2f is ~3x the instructions).  Exact zeros keep the library's signed-zero semantics.
+__device__ __forceinline__ float be_atan2(float y, float x)
+{
+    const float ax = fabsf(x), ay = fabsf(y);
+    const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
+    if (mx == 0.f || !(mx < 1e37f)) return atan2f(y, x);
+    const float a = __fdividef(mn, mx);
+    const float s = a * a;
+    float r = 0.0028340641874819994f;
+    r = fmaf(r, s, -0.016005029901862144f);
+    r = fmaf(r, s, 0.042587608098983765f);
+    r = fmaf(r, s, -0.07495445758104324f);
+    r = fmaf(r, s, 0.10636754333972931f);
+    r = fmaf(r, s, -0.14202570915222168f);
+    r = fmaf(r, s, 0.19992484152317047f);
+    r = fmaf(r, s, -0.3333306610584259f);
+    r = fmaf(r, s, 1.0f);
+    r *= a;
+    if (ay > ax) r = 1.57079637f - r;
+    if (x < 0.f) r = 3.14159274f - r;
+    return copysignf(r, y);
+}
+
 // one sample of the gain loop: ungated agc output (yr, yi), threshold bit, ungated discriminator value
 __device__ __forceinline__ bool be_step(const BackendParams &p, AgcRun &s, float xr, float xi, float &yr, float &yi,
                                         float &m)
@@ -228,7 +253,10 @@ __device__ __forceinline__ bool be_step(const BackendParams &p, AgcRun &s, float
         // from it by at most one ulp of y2' (6e-8 relative), i.e. 3e-9 per step in the gain: far below the 1e-6 at
         // which two float32 runs of this loop settle anyway
         s.y2p = fmaf(p.one_minus_alpha_f, s.y2p, __fmul_rn(p.alpha, y2));
-        if (s.y2p > 1e-6f) s.g *= expf(p.neg_half_alpha * logf(s.y2p));
+        // g *= y2'^(-alpha/2).  Default: SFU exp2/log2 (each step is good to ~3e-7 relative and the loop is
+        // contractive, so the gain stays within ~1e-6 of the libm evaluation); exact_math selects expf/logf.
+        if (s.y2p > 1e-6f)
+            s.g *= p.exact_math ? expf(p.neg_half_alpha * logf(s.y2p)) : __expf(p.neg_half_alpha * __logf(s.y2p));
         if (s.g > 1e6f) s.g = 1e6f;
         ex = s.g < p.g_thr;                       // rssi = -20 log10(g) > threshold
     } else { yr = xr; yi = xi; }
@@ -236,7 +264,7 @@ __device__ __forceinline__ bool be_step(const BackendParams &p, AgcRun &s, float
         // freqdem_demodulate: arg(conj(r') r) / (2 pi kf)
         float re = __fadd_rn(__fmul_rn(s.fr, yr), __fmul_rn(s.fi, yi));
         float im = __fsub_rn(__fmul_rn(s.fr, yi), __fmul_rn(s.fi, yr));
-        m = atan2f(im, re) * p.fm_ref;
+        m = (p.exact_math ? atan2f(im, re) : be_atan2(im, re)) * p.fm_ref;
         s.fr = yr; s.fi = yi;
     }
     return ex;

@@ -338,6 +338,7 @@ struct Backend {
         b.g_thr = design::agc_gain_threshold(agc_thr); b.timeout = agc_timeout;
         b.fm_ref = (float)(1.0f / (2 * design::kPi * kf));
         b.squelch_enabled = squelch ? 1 : 0; b.gate = gate ? 1 : 0;
+        b.exact_math = g_options[CSDR_OPT_AGC_EXACT_MATH] ? 1 : 0;
         b.lane = lane.as<LaneState>(); b.seg_start = ss.as<SegState>(); b.seg_end = se.as<SegState>();
         b.nwords = nwords;
         // the FSM forgets its entry state after timeout + 4 samples: replay that many bits (in whole segments)

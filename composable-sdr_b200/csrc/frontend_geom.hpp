@@ -32,7 +32,9 @@ __host__ __device__ constexpr FeGeom fe_make_geom(int S, int Tc, const int *m, i
 {
     FeGeom g{};
     g.S = S; g.Tc = Tc; g.shift = S > 0 ? shift : 0;
-    for (int s = 0; s < S; s++) { g.m[s] = m[s]; g.R[s] = (s == 0 && S > 1) ? 4 : 8; }
+    // outputs per thread slot: 8 at the input-rate stages, fewer at the last (lowest-rate) stages so that every stage
+    // keeps ~200+ threads of the CTA busy
+    for (int s = 0; s < S; s++) { g.m[s] = m[s]; g.R[s] = (s >= 2 || s == S - 1) ? 8 : (s == 1 ? 4 : (S >= 3 ? 2 : 4)); }
     g.n[0] = Tc + kHcPad; g.d[0] = 0;
     for (int L = 0; L < S; L++) {
         const int sh = (L + 1 == S) ? g.shift : 0;

@@ -141,11 +141,21 @@ __device__ __forceinline__ void fe_stage_c(const float2 *__restrict__ in, float2
 #pragma unroll
             for (int r = 0; r < R; r++) o[r] = cf(acc[r].x * zeta, acc[r].y * zeta);
         } else {
-            // q = R t + r -> plane r & 1, pair p = (R/2) t + (r >> 1) -> sub-array p & (D2-1), index p / D2
-            static_assert(R == 8 && (D2 == 8 || D2 == 4), "store pattern written for R = 8 producers");
-            float2 *o = (D2 == 8) ? out + ((t & 1) << 2) * STR2 + (t >> 1) : out + t;
+            // q = R t + r -> plane r & 1, pair p = H t + (r >> 1) (H = R/2) -> sub-array p & (D2-1), index p / D2
+            constexpr int H = R / 2;
+            static_assert(H >= 1 && (D2 & (D2 - 1)) == 0, "layout factors are powers of two");
+            if constexpr (H >= D2) {
+                // sub-array = (r >> 1) & (D2-1) for every t, index = (H / D2) t + (r >> 1) / D2
+                float2 *o = out + t * (H / D2);
 #pragma unroll
-            for (int r = 0; r < R; r++) o[((r & 1) * D2 + (r >> 1)) * STR2] = acc[r];
+                for (int r = 0; r < R; r++) o[((r & 1) * D2 + ((r >> 1) & (D2 - 1))) * STR2 + (r >> 1) / D2] = acc[r];
+            } else {
+                // K = D2 / H slots share one index: sub-array = H (t & (K-1)) + (r >> 1), index = t / K
+                constexpr int K = D2 / H;
+                float2 *o = out + (H * (t & (K - 1))) * STR2 + t / K;
+#pragma unroll
+                for (int r = 0; r < R; r++) o[((r & 1) * D2 + (r >> 1)) * STR2] = acc[r];
+            }
         }
     }
 }

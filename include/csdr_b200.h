@@ -47,7 +47,8 @@ enum {
     CSDR_OPT_RESAMP_FC_OLD= 2, /* 0: arbitrary stage (m=7, fc=min(.515 r,.49), npfb=256); 1: (7, 0.4, 64) */
     CSDR_OPT_AGC_SEGMENT  = 3, /* AGC time-segment length (samples), default 512 */
     CSDR_OPT_AGC_WARMUP   = 4, /* AGC warm-up length (samples), default 384 */
-    CSDR_OPT_GENERIC_FRONTEND = 5 /* 1: always use the run-time-geometry front-end kernel (tests) */
+    CSDR_OPT_GENERIC_FRONTEND = 5, /* 1: always use the run-time-geometry front-end kernel (tests) */
+    CSDR_OPT_AGC_EXACT_MATH = 6   /* 1: library expf/logf/atan2f in the AGC/discriminator loop instead of the SFU forms */
 };
 int         csdr_set_option(int opt, int value);
 int         csdr_get_option(int opt);

@@ -86,11 +86,13 @@ static inline float emu_cosf(float x) { return cosf(x); }
 static inline void emu_sincosf(float x, float *s, float *c) { *s = sinf(x); *c = cosf(x); }
 static inline float emu_log2f(float x) { return log2f(x); }
 static inline float emu_expf(float x) { return expf(x); }
+static inline float emu_logf(float x) { return logf(x); }
 #define __sinf emu_sinf
 #define __cosf emu_cosf
 #define __sincosf emu_sincosf
 #define __log2f emu_log2f
 #define __expf emu_expf
+#define __logf emu_logf
 static inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
 static inline float __frcp_rn(float x) { return 1.0f / x; }
 static inline float __fdividef(float a, float b) { return a / b; }
