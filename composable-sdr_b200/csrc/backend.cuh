@@ -240,12 +240,16 @@ __device__ __forceinline__ float be_atan2(float y, float x)
     return copysignf(r, y);
 }
 
+// compile-time configuration of the per-sample loop (runtime flags inside it would fence the instruction scheduler)
+enum { BE_DC = 1, BE_AGC = 2, BE_FM = 4, BE_EXACT = 8, BE_NCFG = 16 };
+
 // one sample of the gain loop: ungated agc output (yr, yi), threshold bit, ungated discriminator value
+template <int CFG>
 __device__ __forceinline__ bool be_step(const BackendParams &p, AgcRun &s, float xr, float xi, float &yr, float &yi,
                                         float &m)
 {
     bool ex = true;
-    if (p.has_agc) {
+    if (CFG & BE_AGC) {
         // AGC(_execute), liquid agc.c
         yr = __fmul_rn(xr, s.g); yi = __fmul_rn(xi, s.g);
         float y2 = __fadd_rn(__fmul_rn(yr, yr), __fmul_rn(yi, yi));
@@ -253,18 +257,18 @@ __device__ __forceinline__ bool be_step(const BackendParams &p, AgcRun &s, float
         // from it by at most one ulp of y2' (6e-8 relative), i.e. 3e-9 per step in the gain: far below the 1e-6 at
         // which two float32 runs of this loop settle anyway
         s.y2p = fmaf(p.one_minus_alpha_f, s.y2p, __fmul_rn(p.alpha, y2));
-        // g *= y2'^(-alpha/2).  Default: SFU exp2/log2 (each step is good to ~3e-7 relative and the loop is
-        // contractive, so the gain stays within ~1e-6 of the libm evaluation); exact_math selects expf/logf.
-        if (s.y2p > 1e-6f)
-            s.g *= p.exact_math ? expf(p.neg_half_alpha * logf(s.y2p)) : __expf(p.neg_half_alpha * __logf(s.y2p));
-        if (s.g > 1e6f) s.g = 1e6f;
+        // g *= y2'^(-alpha/2) unless y2' <= 1e-6.  Default: SFU exp2/log2 (each step is good to ~3e-7 relative and
+        // the loop is contractive, so the gain stays within ~1e-6 of the libm evaluation); BE_EXACT: expf/logf.
+        const float f = (CFG & BE_EXACT) ? expf(p.neg_half_alpha * logf(s.y2p)) : __expf(p.neg_half_alpha * __logf(s.y2p));
+        s.g *= (s.y2p > 1e-6f) ? f : 1.0f;
+        s.g = fminf(s.g, 1e6f);
         ex = s.g < p.g_thr;                       // rssi = -20 log10(g) > threshold
     } else { yr = xr; yi = xi; }
-    if (p.demod == 1) {
+    if (CFG & BE_FM) {
         // freqdem_demodulate: arg(conj(r') r) / (2 pi kf)
         float re = __fadd_rn(__fmul_rn(s.fr, yr), __fmul_rn(s.fi, yi));
         float im = __fsub_rn(__fmul_rn(s.fr, yi), __fmul_rn(s.fi, yr));
-        m = (p.exact_math ? atan2f(im, re) : be_atan2(im, re)) * p.fm_ref;
+        m = ((CFG & BE_EXACT) ? atan2f(im, re) : be_atan2(im, re)) * p.fm_ref;
         s.fr = yr; s.fi = yi;
     }
     return ex;
@@ -286,7 +290,7 @@ __device__ __forceinline__ bool be_match(const SegState &a, const SegState &b, i
 // sign bits (the caller owns whole 32-sample words: i0 % 32 == 0 and i1 is a multiple of 32 or the chunk end).
 // Samples are fetched eight at a time, one block ahead of the recurrence, so that the sequential chain never waits
 // for memory.
-template <bool EMIT>
+template <bool EMIT, int CFG>
 __device__ __forceinline__ void be_run(const BackendParams &p, int lane, AgcRun &s, float &v1r, float &v1i, int i0,
                                        int i1)
 {
@@ -311,23 +315,23 @@ __device__ __forceinline__ void be_run(const BackendParams &p, int lane, AgcRun 
         for (int k = 0; k < B; k++) {
             if (i + k >= i1) break;
             float xr = cur[k].x, xi = cur[k].y;
-            if (p.has_dc) {
+            if (CFG & BE_DC) {
                 float v0r = __fsub_rn(xr, __fmul_rn(p.dc_a1, v1r));
                 float v0i = __fsub_rn(xi, __fmul_rn(p.dc_a1, v1i));
                 xr = __fsub_rn(v0r, v1r); xi = __fsub_rn(v0i, v1i);
                 v1r = v0r; v1i = v0i;
             }
             float yr, yi, m = 0.f;
-            const bool ex = be_step(p, s, xr, xi, yr, yi, m);
+            const bool ex = be_step<CFG>(p, s, xr, xi, yr, yi, m);
             if (EMIT) {
                 const int ii = i + k;
-                if (p.demod == 1) of[ii] = m; else oc[ii] = cf(yr, yi);
+                if (CFG & BE_FM) of[ii] = m; else oc[ii] = cf(yr, yi);
                 word |= (ex ? 1u : 0u) << (ii & 31);
                 wr |= ((unsigned)__float_as_int(yr) >> 31) << (ii & 31);
                 wi |= ((unsigned)__float_as_int(yi) >> 31) << (ii & 31);
                 if ((ii & 31) == 31 || ii == i1 - 1) {
                     bits[ii >> 5] = word; word = 0;
-                    if (p.demod == 1) { sr[ii >> 5] = wr; si[ii >> 5] = wi; }
+                    if (CFG & BE_FM) { sr[ii >> 5] = wr; si[ii >> 5] = wi; }
                     wr = 0; wi = 0;
                 }
             }
@@ -350,6 +354,7 @@ __device__ __forceinline__ SegState be_pack(const AgcRun &s)
     return st;
 }
 
+template <int CFG>
 __global__ void __launch_bounds__(128) k_backend_spec(const BackendParams p)
 {
     long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -375,9 +380,9 @@ __global__ void __launch_bounds__(128) k_backend_spec(const BackendParams p)
         s.y2p = 1.0f; s.fr = 0.f; s.fi = 0.f;
     }
     be_dc_state(p, lane, w0, v1r, v1i);
-    be_run<false>(p, lane, s, v1r, v1i, w0, b0);       // warm-up, nothing emitted
+    be_run<false, CFG>(p, lane, s, v1r, v1i, w0, b0);  // warm-up, nothing emitted
     p.seg_start[t] = be_pack(s);
-    be_run<true>(p, lane, s, v1r, v1i, b0, b1);
+    be_run<true, CFG>(p, lane, s, v1r, v1i, b0, b1);
     p.seg_end[t] = be_pack(s);
 }
 
@@ -401,6 +406,7 @@ __global__ void k_backend_verify(const BackendParams p, int pass)
 // loop) is replaced by the predecessor's END state, which is accurate because the predecessor's own L samples
 // damped its error; the segment is re-run from there.  (A predecessor that is being refined at the same time may
 // be read before or after its update: both values are valid to well below the tolerance.)
+template <int CFG>
 __global__ void __launch_bounds__(128) k_backend_refine(const BackendParams p)
 {
     const unsigned count = min(*p.bad_count, p.bad_cap);
@@ -413,13 +419,14 @@ __global__ void __launch_bounds__(128) k_backend_refine(const BackendParams p)
         const int b0 = seg * p.L, b1 = min(b0 + p.L, p.n);
         be_dc_state(p, lane, b0, v1r, v1i);
         p.seg_start[t] = pe;
-        be_run<true>(p, lane, s, v1r, v1i, b0, b1);
+        be_run<true, CFG>(p, lane, s, v1r, v1i, b0, b1);
         p.seg_end[t] = be_pack(s);
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(p.fixups + 2, (unsigned long long)count);
 }
 
 // one CTA per lane: re-run the misses in stream order (rare), store the lane's gain state
+template <int CFG>
 __global__ void k_backend_fixup(const BackendParams p)
 {
     const int lane = blockIdx.x;
@@ -453,7 +460,7 @@ __global__ void k_backend_fixup(const BackendParams p)
                 float v1r, v1i;
                 const int b0 = seg * p.L, b1 = min(b0 + p.L, p.n);
                 be_dc_state(p, lane, b0, v1r, v1i);
-                be_run<true>(p, lane, s, v1r, v1i, b0, b1);
+                be_run<true, CFG>(p, lane, s, v1r, v1i, b0, b1);
                 E[seg] = be_pack(s);
                 redone++;
                 seg++;      // the successor is re-checked against the new end state on the next iteration
@@ -667,18 +674,33 @@ inline void be_launch_dc(Launch &launch, const DcParams &d, bool apply)
     }
 }
 
+template <int CFG, class Launch>
+inline void be_launch_gain(Launch &launch, const BackendParams &b, unsigned gb)
+{
+    launch(k_backend_spec<CFG>, dim3(gb), dim3(128), 0, b);
+    if (CFG & BE_AGC) {
+        launch(k_backend_verify, dim3(gb), dim3(128), 0, b, 0);
+        launch(k_backend_refine<CFG>, dim3(64), dim3(128), 0, b);
+        launch(k_backend_verify, dim3(gb), dim3(128), 0, b, 1);
+    }
+    launch(k_backend_fixup<CFG>, dim3(b.nlanes), dim3(128), 0, b);
+}
+template <int N, class Launch>
+inline void be_dispatch_gain(int cfg, Launch &launch, const BackendParams &b, unsigned gb)
+{
+    if constexpr (N >= 0) {
+        if (cfg == N) be_launch_gain<N>(launch, b, gb);
+        else be_dispatch_gain<N - 1>(cfg, launch, b, gb);
+    }
+}
+
 template <class Launch>
 inline void be_launch(Launch &launch, const BackendParams &b)
 {
     const long long segs = (long long)b.nlanes * b.nseg;
     const unsigned gb = (unsigned)((segs + 127) / 128);
-    launch(k_backend_spec, dim3(gb), dim3(128), 0, b);
-    if (b.has_agc) {
-        launch(k_backend_verify, dim3(gb), dim3(128), 0, b, 0);
-        launch(k_backend_refine, dim3(64), dim3(128), 0, b);
-        launch(k_backend_verify, dim3(gb), dim3(128), 0, b, 1);
-    }
-    launch(k_backend_fixup, dim3(b.nlanes), dim3(128), 0, b);
+    const int cfg = (b.has_dc ? BE_DC : 0) | (b.has_agc ? BE_AGC : 0) | (b.demod == 1 ? BE_FM : 0) | (b.exact_math ? BE_EXACT : 0);
+    be_dispatch_gain<BE_NCFG - 1>(cfg, launch, b, gb);
     if (b.has_agc) {
         launch(k_backend_fsm, dim3(gb), dim3(128), 0, b);
         launch(k_backend_fsm_verify, dim3(gb), dim3(128), 0, b);

@@ -253,22 +253,37 @@ __global__ void __launch_bounds__(256, 2) k_frontend_std(const CSDR_GRID_CONSTAN
 
         fe_run_stages<S, S - 1>(p, smem);
 
-        // arbitrary resampler: output o' -> push k = (ph0 + o'*step) >> 24, branch = next `bits` bits of the phase
+        // arbitrary resampler (rate_arb < 1: every push emits at most one output).  One thread per PAIR of pushes:
+        // the 16 c-samples both windows need are fetched with eight conflict-free 16-byte loads and stay in registers;
+        // output o' has phase ph0 + o'*step, belongs to push (phase >> 24) and uses branch = next `bits` phase bits.
         {
-            const float2 *cbuf = smem + G.off[0] + kHcPad - tile * G.Tc;   // cbuf[k] for k relative to K0
-            const int oA = s_info[cur].oA, oB = s_info[cur].oB;
-            for (int o = oA + threadIdx.x; o < oB; o += 256) {
-                const unsigned long long ph = p.ph0 + (unsigned long long)(unsigned)o * p.step;
-                const float2 *c = cbuf + (int)(ph >> 24);
-                const float *h = bank_s + ((unsigned)(ph >> sh) & mask) * (kHsub + 1);
-                float ar = 0.f, ai = 0.f;
+            const float2 *cb = smem + G.off[0];            // local index i <-> push (tile*Tc - kHcPad + i) relative to K0
+            const long long kArel = (long long)tile * G.Tc;
+            const int npush = (int)min((long long)G.Tc, p.K1 - p.K0 - kArel);
+            for (int t = threadIdx.x; t < G.Tc / 2; t += 256) {
+                if (2 * t >= npush) break;
+                float2 w[16];                               // local indices 2t+2 .. 2t+17; push e ends at w[14 + e]
+                const float4 *src = reinterpret_cast<const float4 *>(cb + 2 * t + 2);
 #pragma unroll
-                for (int j = 0; j < kHsub; j++) {
-                    const float2 v = c[-j];
-                    ar = fmaf(h[j], v.x, ar);
-                    ai = fmaf(h[j], v.y, ai);
+                for (int i = 0; i < 8; i++) { const float4 q = src[i]; w[2 * i] = cf(q.x, q.y); w[2 * i + 1] = cf(q.z, q.w); }
+                const unsigned long long kk = (unsigned long long)(kArel + 2 * t);
+                const unsigned long long a = kk << 24;
+                long long o = (a > p.ph0) ? fe_ceil_div(a - p.ph0, p.step, inv_st) : 0;   // first output at or after push kk
+#pragma unroll
+                for (int e = 0; e < 2; e++) {
+                    const unsigned long long ph = p.ph0 + (unsigned long long)o * p.step;
+                    if (2 * t + e < npush && (ph >> 24) == kk + e) {
+                        const float *h = bank_s + ((unsigned)(ph >> sh) & mask) * (kHsub + 1);
+                        float ar = 0.f, ai = 0.f;
+#pragma unroll
+                        for (int j = 0; j < kHsub; j++) {
+                            ar = fmaf(h[j], w[14 + e - j].x, ar);
+                            ai = fmaf(h[j], w[14 + e - j].y, ai);
+                        }
+                        ys[o] = cf(ar, ai);
+                        o++;
+                    }
                 }
-                ys[o] = cf(ar, ai);
             }
         }
         __syncthreads();   // smem is reused by the next tile
