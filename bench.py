@@ -287,7 +287,10 @@ def run_ours(args):
                          "peak_kind": peak_kind, "bytes_per_sample": B_ALG, "launches": fe_launches,
                          "avg_launch_ms": fe_ms / max(fe_launches, 1),
                          "share_of_step": fe_ms / ms if ms > 0 else None,
-                         "traffic": (tr or {}).get("dram_bytes_per_launch")},
+                         # DRAM bytes of one launch from the committed ncu --set full capture, scaled from the
+                         # captured chunk size to this run's chunk (traffic is linear in the samples streamed)
+                         "traffic": (tr["dram_bytes_per_launch"] * n / tr["chunk_samples"]) if tr else None,
+                         "traffic_source": (tr or {}).get("source")},
             "outputs_per_step": int(ny), "agc_fixups": int(fixups),
         }
         if world == 1 and not args.no_cpu:

@@ -302,10 +302,21 @@ __device__ __forceinline__ void be_run(const BackendParams &p, int lane, AgcRun 
     unsigned word = 0, wr = 0, wi = 0;
     constexpr int B = 8;
     float2 cur[B], nxt[B];
+    // 16-byte loads (two samples each) when the lane's samples are 16-byte aligned: every lane reads its own cache
+    // line, so the number of load instructions is what the LSU pays for
+    const bool vec = ((reinterpret_cast<uintptr_t>(x) & 15) == 0) && ((i0 & 1) == 0);
     auto fetch = [&](float2 (&dst)[B], int i) {
+        if (vec && i + B <= i1) {
+            const float4 *x4 = reinterpret_cast<const float4 *>(x + i);
 #pragma unroll
-        for (int k = 0; k < B; k++) dst[k] = (i + k < i1) ? __ldg(x + i + k) : cf(0.f, 0.f);
+            for (int k = 0; k < B / 2; k++) { const float4 q = __ldg(x4 + k); dst[2 * k] = cf(q.x, q.y); dst[2 * k + 1] = cf(q.z, q.w); }
+        } else {
+#pragma unroll
+            for (int k = 0; k < B; k++) dst[k] = (i + k < i1) ? __ldg(x + i + k) : cf(0.f, 0.f);
+        }
     };
+    const bool vec_out = EMIT && (CFG & BE_FM) && ((reinterpret_cast<uintptr_t>(of) & 15) == 0) && ((i0 & 3) == 0);
+    float mbuf[B];
     if (i0 < i1) fetch(nxt, i0);
     for (int i = i0; i < i1; i += B) {
 #pragma unroll
@@ -325,7 +336,7 @@ __device__ __forceinline__ void be_run(const BackendParams &p, int lane, AgcRun 
             const bool ex = be_step<CFG>(p, s, xr, xi, yr, yi, m);
             if (EMIT) {
                 const int ii = i + k;
-                if (CFG & BE_FM) of[ii] = m; else oc[ii] = cf(yr, yi);
+                if (CFG & BE_FM) { if (vec_out) mbuf[k] = m; else of[ii] = m; } else oc[ii] = cf(yr, yi);
                 word |= (ex ? 1u : 0u) << (ii & 31);
                 wr |= ((unsigned)__float_as_int(yr) >> 31) << (ii & 31);
                 wi |= ((unsigned)__float_as_int(yi) >> 31) << (ii & 31);
@@ -334,6 +345,16 @@ __device__ __forceinline__ void be_run(const BackendParams &p, int lane, AgcRun 
                     if (CFG & BE_FM) { sr[ii >> 5] = wr; si[ii >> 5] = wi; }
                     wr = 0; wi = 0;
                 }
+            }
+        }
+        if (EMIT && vec_out) {
+            if (i + B <= i1) {
+                float4 *o4 = reinterpret_cast<float4 *>(of + i);
+                o4[0] = make_float4(mbuf[0], mbuf[1], mbuf[2], mbuf[3]);
+                o4[1] = make_float4(mbuf[4], mbuf[5], mbuf[6], mbuf[7]);
+            } else {
+#pragma unroll
+                for (int k = 0; k < B; k++) if (i + k < i1) of[i + k] = mbuf[k];
             }
         }
     }
