@@ -21,9 +21,20 @@ struct csdr_chain_s {
     size_t nleft = 0;
     std::vector<void *> out_ptrs;
     unsigned long long fixups_seen = 0, fixups_last = 0;
-    // host-input pipeline
+    // second stream: the back end of part i runs while the front end filters part i+1 (and host copies overlap)
     cudaStream_t copy_stream = nullptr; cudaEvent_t ev_copy[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+    cudaStream_t be_stream = nullptr;
+    std::vector<cudaEvent_t> ev_pool;
     DevBuf xpipe[2];
+    cudaEvent_t event(size_t i)
+    {
+        while (ev_pool.size() <= i) {
+            cudaEvent_t e = nullptr;
+            CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            ev_pool.push_back(e);
+        }
+        return ev_pool[i];
+    }
 
     csdr_chain_s(const csdr_chain_cfg &c) : ctx(c.device), cfg(c) {}
     ~csdr_chain_s()
@@ -31,6 +42,8 @@ struct csdr_chain_s {
         cudaSetDevice(ctx.device);
         if (ctx.stream) cudaStreamSynchronize(ctx.stream);
         if (copy_stream) { cudaStreamSynchronize(copy_stream); cudaStreamDestroy(copy_stream); }
+        if (be_stream) { cudaStreamSynchronize(be_stream); cudaStreamDestroy(be_stream); }
+        for (auto e : ev_pool) if (e) cudaEventDestroy(e);
         for (auto e : ev_copy) if (e) cudaEventDestroy(e);
         for (auto e : ev_done) if (e) cudaEventDestroy(e);
     }
@@ -83,6 +96,7 @@ void chain_init(csdr_chain_s *q)
     if (c.demod == CSDR_DEMOD_AM) q->am.init(q->ctx.stream, am_lanes, 0.8f, g_options[CSDR_OPT_AMPMODEM_PLL] != 0);
     q->out_ptrs.resize((size_t)q->nstreams * q->nout);
     CK(cudaStreamCreateWithFlags(&q->copy_stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&q->be_stream, cudaStreamNonBlocking));
     for (int i = 0; i < 2; i++) {
         CK(cudaEventCreateWithFlags(&q->ev_copy[i], cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&q->ev_done[i], cudaEventDisableTiming));
@@ -102,6 +116,30 @@ size_t chain_run_device(csdr_chain_s *q, const float2 *xd, size_t nx, size_t x_s
 {
     const Ctx &c = q->ctx;
     const unsigned S = q->nstreams;
+    // ---- single stream, resampler, no AM: software pipeline over parts of the chunk.  The front end of part i+1
+    // (all SMs, shared-memory bound) overlaps the back end of part i (latency-bound recurrences, few warps).
+    if (q->C == 1 && S == 1 && q->has_resamp && q->cfg.demod != CSDR_DEMOD_AM && nx >= ((size_t)1 << 23) &&
+        g_options[CSDR_OPT_NO_OVERLAP] == 0) {
+        size_t nparts = std::min<size_t>(8, std::max<size_t>(2, nx >> 24));
+        size_t part = ((nx + nparts - 1) / nparts + 255) & ~(size_t)255;
+        nparts = (nx + part - 1) / part;
+        const size_t rcap = ((size_t)q->fe.max_out((long long)part) + 3) & ~(size_t)3;
+        q->r.ensure(sizeof(float2) * rcap * nparts);
+        size_t produced = 0;
+        for (size_t i = 0; i < nparts; i++) {
+            const size_t off = i * part, n_i = std::min(part, nx - off);
+            float2 *ri = q->r.as<float2>() + i * rcap;
+            const long long nr_i = q->fe.run(c, xd + off, (long long)n_i, 0, ri, 0);
+            if (produced + (size_t)nr_i > out_cap) throw CudaError{"chain: output capacity too small"};
+            CK(cudaEventRecord(q->event(i), c.stream));
+            CK(cudaStreamWaitEvent(q->be_stream, q->event(i), 0));
+            q->be.run_on(q->be_stream, ri, 0, (char *)q->out_ptrs[0] + produced * q->esz, 0, (int)nr_i);
+            produced += (size_t)nr_i;
+        }
+        CK(cudaEventRecord(q->event(nparts), q->be_stream));
+        CK(cudaStreamWaitEvent(c.stream, q->event(nparts), 0));
+        return produced;
+    }
     // ---- offset mix + resampler
     const float2 *r = xd; long long r_stride = (long long)x_stride; long long nr = (long long)nx;
     if (q->has_resamp) {

@@ -310,8 +310,12 @@ struct Backend {
     // [dc] -> [agc+gate] -> [fm]; out: float (demod) or float2
     void run(const Ctx &c, const float2 *in, long long in_stride, void *out, long long out_stride, int n)
     {
+        run_on(c.stream, in, in_stride, out, out_stride, n);
+    }
+    void run_on(cudaStream_t st, const float2 *in, long long in_stride, void *out, long long out_stride, int n)
+    {
         if (n <= 0) return;
-        Launcher l{c.stream};
+        Launcher l{st};
         // segment length: the per-segment recurrences are latency bound, so aim for >= ~64k concurrent chains
         // (shorter segments = more chains but relatively more warm-up work); L stays a multiple of G
         int L = this->L;

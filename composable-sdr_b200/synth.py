@@ -72,7 +72,9 @@ def config4(n, channels=1024, active=64, sr=1e9):
     # ones well above it
     x = noise(n, 3e-5, 40)
     idx = g.choice(channels, size=active, replace=False)
-    amps = g.uniform(0.003, 0.02, size=active)      # adjacent-channel leakage (-80 dB) stays well below the squelch
+    # (the 1024-level NCO of the pre-rotation leaves spurs ~45 dB below a carrier in other channels: carriers
+    # are kept below 0 dB at the analyzer output so that their spurs stay clear of the -40 dB squelch threshold)
+    amps = g.uniform(1e-4, 7e-4, size=active)
     for k, a in zip(idx, amps):
         f0 = (k - (channels - 1) / 2.0) / channels * sr
         x = x + fm_carrier(n, sr, f0, a, 0.1 * sr / channels, sr / channels / 50.0)

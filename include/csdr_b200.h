@@ -48,7 +48,8 @@ enum {
     CSDR_OPT_AGC_SEGMENT  = 3, /* AGC time-segment length (samples), default 512 */
     CSDR_OPT_AGC_WARMUP   = 4, /* AGC warm-up length (samples), default 384 */
     CSDR_OPT_GENERIC_FRONTEND = 5, /* 1: always use the run-time-geometry front-end kernel (tests) */
-    CSDR_OPT_AGC_EXACT_MATH = 6   /* 1: library expf/logf/atan2f in the AGC/discriminator loop instead of the SFU forms */
+    CSDR_OPT_AGC_EXACT_MATH = 6,  /* 1: library expf/logf/atan2f in the AGC/discriminator loop instead of the SFU forms */
+    CSDR_OPT_NO_OVERLAP = 7       /* 1: do not overlap front end and back end of consecutive parts of a chunk */
 };
 int         csdr_set_option(int opt, int value);
 int         csdr_get_option(int opt);
