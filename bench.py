@@ -270,7 +270,9 @@ def run_ours(args):
 
     if rank == 0:
         peak, peak_kind = measured_peak()
-        ach = B_ALG * n / (fe_ms / max(fe_launches, 1) * 1e-3) / 1e9 if fe_ms > 0 else None
+        # the chain may split a chunk into parts (one k_frontend launch each): bytes per launch = bytes per step / parts
+        parts = max(1, fe_launches // max(args.steps, 1))
+        ach = B_ALG * (n / parts) / (fe_ms / max(fe_launches, 1) * 1e-3) / 1e9 if fe_ms > 0 else None
         tr = ncu_traffic()
         line = {
             "metric": METRIC, "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps,
@@ -289,7 +291,8 @@ def run_ours(args):
                          "share_of_step": fe_ms / ms if ms > 0 else None,
                          # DRAM bytes of one launch from the committed ncu --set full capture, scaled from the
                          # captured chunk size to this run's chunk (traffic is linear in the samples streamed)
-                         "traffic": (tr["dram_bytes_per_launch"] * n / tr["chunk_samples"]) if tr else None,
+                         "traffic": (tr["dram_bytes_per_launch"] * (n / parts) / tr["chunk_samples"]) if tr else None,
+                         "samples_per_launch": n // parts,
                          "traffic_source": (tr or {}).get("source")},
             "outputs_per_step": int(ny), "agc_fixups": int(fixups),
         }

@@ -120,7 +120,8 @@ size_t chain_run_device(csdr_chain_s *q, const float2 *xd, size_t nx, size_t x_s
     // (all SMs, shared-memory bound) overlaps the back end of part i (latency-bound recurrences, few warps).
     if (q->C == 1 && S == 1 && q->has_resamp && q->cfg.demod != CSDR_DEMOD_AM && nx >= ((size_t)1 << 23) &&
         g_options[CSDR_OPT_NO_OVERLAP] == 0) {
-        size_t nparts = std::min<size_t>(8, std::max<size_t>(2, nx >> 24));
+        // few, large parts: the back end of a part is latency bound (~0.15 ms almost regardless of its size)
+        size_t nparts = nx >= ((size_t)1 << 28) ? 4 : 2;
         size_t part = ((nx + nparts - 1) / nparts + 255) & ~(size_t)255;
         nparts = (nx + part - 1) / part;
         const size_t rcap = ((size_t)q->fe.max_out((long long)part) + 3) & ~(size_t)3;

@@ -60,3 +60,18 @@ def make_signal(n, seed=0, amp=0.5):
     x = x + amp * np.exp(2j * np.pi * 0.0391 * k + 1j * 3.0 * np.sin(2 * np.pi * k / 2560.0))
     x = x + 0.3 * np.exp(-2j * np.pi * 0.156 * k)
     return x.astype(np.complex64)
+
+
+def away_from_gate_edges(ref, guard=1):
+    """mask of samples whose squelch gate and whose neighbours' gates are all open or all closed.  At an edge the
+    discriminator sees one zeroed sample and returns arg(+-0 +- j0) = 0 or +-pi: the sign comes from the sign of a
+    possibly tiny ungated component, which float32 rounding can flip; those samples are compared separately."""
+    closed = (np.asarray(ref) == 0)
+    edge = np.zeros(closed.shape, bool)
+    d = closed[1:] != closed[:-1]
+    for k in range(-guard, guard + 1):
+        idx = np.nonzero(d)[0] + 1 + k
+        idx = idx[(idx >= 0) & (idx < closed.size)]
+        edge[idx] = True
+    # isolated +-pi artefacts also appear one sample after the gate opens
+    return ~edge
