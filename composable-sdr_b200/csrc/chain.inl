@@ -116,10 +116,12 @@ size_t chain_run_device(csdr_chain_s *q, const float2 *xd, size_t nx, size_t x_s
 {
     const Ctx &c = q->ctx;
     const unsigned S = q->nstreams;
-    // ---- single stream, resampler, no AM: software pipeline over parts of the chunk.  The front end of part i+1
-    // (all SMs, shared-memory bound) overlaps the back end of part i (latency-bound recurrences, few warps).
+    // ---- optional (CSDR_OPT_OVERLAP): software pipeline over parts of the chunk, back end of part i on a second
+    // stream while the front end filters part i+1.  Measured on B200 it does not pay (0.87 ms vs 0.79 ms per 2^27
+    // samples): the persistent front-end grid leaves room for one back-end CTA per SM, and the back end needs the
+    // whole machine to hide the latency of its recurrences.  Off by default.
     if (q->C == 1 && S == 1 && q->has_resamp && q->cfg.demod != CSDR_DEMOD_AM && nx >= ((size_t)1 << 23) &&
-        g_options[CSDR_OPT_NO_OVERLAP] == 0) {
+        g_options[CSDR_OPT_OVERLAP] != 0) {
         // few, large parts: the back end of a part is latency bound (~0.15 ms almost regardless of its size)
         size_t nparts = nx >= ((size_t)1 << 28) ? 4 : 2;
         size_t part = ((nx + nparts - 1) / nparts + 255) & ~(size_t)255;

@@ -49,7 +49,7 @@ enum {
     CSDR_OPT_AGC_WARMUP   = 4, /* AGC warm-up length (samples), default 384 */
     CSDR_OPT_GENERIC_FRONTEND = 5, /* 1: always use the run-time-geometry front-end kernel (tests) */
     CSDR_OPT_AGC_EXACT_MATH = 6,  /* 1: library expf/logf/atan2f in the AGC/discriminator loop instead of the SFU forms */
-    CSDR_OPT_NO_OVERLAP = 7       /* 1: do not overlap front end and back end of consecutive parts of a chunk */
+    CSDR_OPT_OVERLAP = 7          /* 1: overlap the back end of part i with the front end of part i+1 (2 streams) */
 };
 int         csdr_set_option(int opt, int value);
 int         csdr_get_option(int opt);

@@ -29,12 +29,18 @@ def snr_db(y, ref):
     return 10.0 * np.log10(num / den)
 
 
-def assert_parity(y, ref, rel=REL_TOL, snr=SNR_DB, what=""):
+def assert_parity(y, ref, rel=REL_TOL, snr=SNR_DB, what="", period=None):
+    """period: for discriminator outputs, 1/kf (= 2 pi in units of the output).  arg() has a branch cut at +-pi: on a
+    noise-only sample pair that lands next to it, rounding decides between -pi+e and +pi-e, so errors are compared
+    modulo the period."""
     y = np.asarray(y)
     ref = np.asarray(ref)
     assert y.shape == ref.shape, f"{what}: shape {y.shape} != {ref.shape}"
     if ref.size == 0:
         return
+    if period is not None:
+        d = y.astype(np.float64) - ref.astype(np.float64)
+        y = (ref.astype(np.float64) + (d - period * np.round(d / period)))
     peak = float(np.max(np.abs(ref)))
     err = float(np.max(np.abs(y - ref)))
     s = snr_db(y, ref)
