@@ -484,6 +484,12 @@ class Chain:
     def agc_fixups(self):
         return int(self.L.csdr_chain_agc_fixups(self.h))
 
+    def agc_counters(self):
+        """cumulative (gain segments repaired in order, squelch-FSM segments repaired in order, gain segments refined)"""
+        v = (C.c_uint64 * 3)()
+        self.L.csdr_chain_agc_counters(self.h, v)
+        return int(v[0]), int(v[1]), int(v[2])
+
     def print(self):
         self.L.csdr_chain_print(self.h)
 

@@ -446,6 +446,9 @@ __global__ void __launch_bounds__(128) k_backend_refine(const BackendParams p)
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(p.fixups + 2, (unsigned long long)count);
 }
 
+// the list is consumed: empty it for the next verification round
+__global__ void k_backend_list_reset(const BackendParams p) { *p.bad_count = 0; }
+
 // one CTA per lane: re-run the misses in stream order (rare), store the lane's gain state
 template <int CFG>
 __global__ void k_backend_fixup(const BackendParams p)
@@ -700,6 +703,12 @@ inline void be_launch_gain(Launch &launch, const BackendParams &b, unsigned gb)
 {
     launch(k_backend_spec<CFG>, dim3(gb), dim3(128), 0, b);
     if (CFG & BE_AGC) {
+        // two rounds of verify + parallel refine (a run of consecutive misses needs one round per level of
+        // inaccuracy handed down the run; an empty list costs a few microseconds), then the in-order repair
+        launch(k_backend_verify, dim3(gb), dim3(128), 0, b, 0);
+        launch.debug_after_verify(b);
+        launch(k_backend_refine<CFG>, dim3(64), dim3(128), 0, b);
+        launch(k_backend_list_reset, dim3(1), dim3(1), 0, b);
         launch(k_backend_verify, dim3(gb), dim3(128), 0, b, 0);
         launch(k_backend_refine<CFG>, dim3(64), dim3(128), 0, b);
         launch(k_backend_verify, dim3(gb), dim3(128), 0, b, 1);

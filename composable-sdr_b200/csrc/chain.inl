@@ -363,5 +363,15 @@ uint64_t csdr_chain_agc_fixups(csdr_chain q)
     return d;
     API_END(0)
 }
+int csdr_chain_agc_counters(csdr_chain q, uint64_t out[3])
+{
+    API_BEGIN
+    unsigned long long v[3] = {0, 0, 0};
+    CK(cudaMemcpyAsync(v, q->be.fixups.p, sizeof(v), cudaMemcpyDeviceToHost, q->ctx.stream));
+    q->ctx.sync();
+    out[0] = v[0]; out[1] = v[1]; out[2] = v[2];
+    return 0;
+    API_END(-1)
+}
 
 }  // extern "C"

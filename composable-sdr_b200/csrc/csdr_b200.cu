@@ -30,7 +30,7 @@ namespace {
 
 thread_local std::string t_err;
 std::atomic<unsigned long long> g_launches{0};
-int g_options[8] = {0, 1, 0, 512, 384, 0, 0, 0};
+int g_options[16] = {0, 1, 0, 512, 384, 0, 0, 0, 0};
 
 void set_err(const std::string &s) { t_err = s; }
 void clear_err() { t_err.clear(); }
@@ -247,6 +247,11 @@ struct Backend {
     int L = 512, W = 384, G = 128; bool fixed_L = false;
     DevBuf lane, Vloc, carry, powA, ss, se, fs, fe, exbits, gatebits, sgnr, sgni, prev_gate, prev_sign, first_bad, bad_list, bad_count, fixups;
     int FW = 3; unsigned long long last_refined = 0;
+    // self-tuning warm-up: the counters of every call are copied to pinned memory asynchronously; the next call looks
+    // at them (no synchronisation) and lengthens / shortens the warm-up
+    unsigned long long *h_counters = nullptr; cudaEvent_t ev_counters = nullptr; bool counters_pending = false;
+    unsigned long long seen[3] = {0, 0, 0}; int W_cur = 0, calm_calls = 0; long long last_nseg = 1;
+    ~Backend() { if (h_counters) cudaFreeHost(h_counters); if (ev_counters) cudaEventDestroy(ev_counters); }
 
     void init(const Ctx &c, int lanes, float g0 = 1000.0f, int mode0 = SQ_ENABLED)
     {
@@ -281,6 +286,25 @@ struct Backend {
     }
     struct Launcher {
         cudaStream_t st;
+        // CSDR_OPT_DEBUG: print the first speculation misses (start state vs predecessor's end state)
+        void debug_after_verify(const BackendParams &b) const
+        {
+            if (!g_options[CSDR_OPT_DEBUG]) return;
+            CK(cudaStreamSynchronize(st));
+            unsigned cnt = 0;
+            CK(cudaMemcpy(&cnt, b.bad_count, sizeof(cnt), cudaMemcpyDeviceToHost));
+            unsigned show = std::min(cnt, 12u);
+            std::vector<unsigned> lst(show);
+            if (show) CK(cudaMemcpy(lst.data(), b.bad_list, show * sizeof(unsigned), cudaMemcpyDeviceToHost));
+            fprintf(stderr, "[csdr debug] n=%d L=%d W=%d nseg=%d: %u segments do not continue their predecessor\n", b.n, b.L, b.W, b.nseg, cnt);
+            for (unsigned i = 0; i < show; i++) {
+                SegState a, e;
+                CK(cudaMemcpy(&a, b.seg_start + lst[i], sizeof(a), cudaMemcpyDeviceToHost));
+                CK(cudaMemcpy(&e, b.seg_end + lst[i] - 1, sizeof(e), cudaMemcpyDeviceToHost));
+                fprintf(stderr, "  seg %u: start g=%.9g y2p=%.9g | pred end g=%.9g y2p=%.9g | rel %.3g %.3g\n", lst[i], a.g, a.y2p, e.g,
+                        e.y2p, fabs(a.g - e.g) / fmax(a.g, e.g), fabs(a.y2p - e.y2p) / fmax(a.y2p, e.y2p));
+            }
+        }
         template <class... Args, class... Act>
         void operator()(void (*k)(Args...), dim3 grid, dim3 block, size_t smem, Act &&...a) const
         {
@@ -322,6 +346,22 @@ struct Backend {
         if (has_agc && !fixed_L) {
             while (L > G && (long long)nlanes * ((n + L - 1) / L) < 65536) L /= 2;
         }
+        int W = this->W;
+        if (has_agc && !fixed_L) {
+            if (!h_counters) {
+                CK(cudaHostAlloc((void **)&h_counters, 3 * sizeof(unsigned long long), cudaHostAllocDefault));
+                CK(cudaEventCreateWithFlags(&ev_counters, cudaEventDisableTiming));
+                W_cur = this->W;
+            }
+            if (counters_pending && cudaEventQuery(ev_counters) == cudaSuccess) {
+                counters_pending = false;
+                const unsigned long long seq = h_counters[0] - seen[0], refined = h_counters[2] - seen[2];
+                seen[0] = h_counters[0]; seen[1] = h_counters[1]; seen[2] = h_counters[2];
+                if (seq > 0 || refined * 200 > (unsigned long long)last_nseg) { W_cur = std::min(W_cur * 2, 6144); calm_calls = 0; }
+                else if (refined == 0 && ++calm_calls >= 8 && W_cur > this->W) { W_cur /= 2; calm_calls = 0; }
+            }
+            W = W_cur;
+        }
         int ngrp = (n + G - 1) / G, nseg = (n + L - 1) / L, nwords = (n + 31) / 32;
         size_t segs = (size_t)nlanes * nseg;
         ss.ensure(sizeof(SegState) * segs); se.ensure(sizeof(SegState) * segs);
@@ -355,6 +395,12 @@ struct Backend {
         b.bad_list = bad_list.as<unsigned>(); b.bad_count = bad_count.as<unsigned>(); b.bad_cap = 65536;
         b.fixups = fixups.as<unsigned long long>();
         be_launch(l, b);
+        if (has_agc && !fixed_L && !counters_pending) {
+            CK(cudaMemcpyAsync(h_counters, fixups.p, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+            CK(cudaEventRecord(ev_counters, st));
+            counters_pending = true;
+            last_nseg = (long long)nlanes * nseg;
+        }
     }
     unsigned long long read_fixups(const Ctx &c)
     {
@@ -485,8 +531,8 @@ void *csdr_host_alloc(size_t bytes)
 void csdr_host_free(void *p) { if (p) cudaFreeHost(p); }
 uint64_t csdr_kernel_launches(void) { return g_launches.load(); }
 int csdr_synchronize(void) { API_BEGIN CK(cudaDeviceSynchronize()); return 0; API_END(-1) }
-int csdr_set_option(int opt, int value) { if (opt < 0 || opt >= 8) return -1; g_options[opt] = value; return 0; }
-int csdr_get_option(int opt) { return (opt < 0 || opt >= 8) ? -1 : g_options[opt]; }
+int csdr_set_option(int opt, int value) { if (opt < 0 || opt >= 16) return -1; g_options[opt] = value; return 0; }
+int csdr_get_option(int opt) { return (opt < 0 || opt >= 16) ? -1 : g_options[opt]; }
 
 // ---------------------------------------------------------------- nco_crcf
 csdr_nco csdr_nco_crcf_create(int type)

@@ -49,7 +49,8 @@ enum {
     CSDR_OPT_AGC_WARMUP   = 4, /* AGC warm-up length (samples), default 384 */
     CSDR_OPT_GENERIC_FRONTEND = 5, /* 1: always use the run-time-geometry front-end kernel (tests) */
     CSDR_OPT_AGC_EXACT_MATH = 6,  /* 1: library expf/logf/atan2f in the AGC/discriminator loop instead of the SFU forms */
-    CSDR_OPT_OVERLAP = 7          /* 1: overlap the back end of part i with the front end of part i+1 (2 streams) */
+    CSDR_OPT_OVERLAP = 7,         /* 1: overlap the back end of part i with the front end of part i+1 (2 streams) */
+    CSDR_OPT_DEBUG = 8            /* 1: print AGC speculation diagnostics to stderr (synchronises) */
 };
 int         csdr_set_option(int opt, int value);
 int         csdr_get_option(int opt);
@@ -182,6 +183,9 @@ int      csdr_chain_profile(csdr_chain q, int enable);
 double   csdr_chain_frontend_ms(csdr_chain q, uint64_t *launches);
 /* number of AGC time segments the last call had to recompute sequentially (speculation misses) */
 uint64_t csdr_chain_agc_fixups(csdr_chain q);
+/* cumulative counters: [0] gain-loop segments repaired in order, [1] squelch-FSM segments repaired in order,
+ * [2] gain-loop segments refined in parallel */
+int      csdr_chain_agc_counters(csdr_chain q, uint64_t out[3]);
 
 #ifdef __cplusplus
 }

@@ -34,7 +34,8 @@ def run(name, chain, x, steps=5, warmup=2, b_alg=None):
     ms = e0.elapsed_time(e1) / steps
     tot = x.numel()
     line = {"config": name, "input_samples_per_step": tot, "ms_per_step": ms, "Msamples_per_s": tot / ms / 1e3,
-            "outputs_per_step": n, "launches_per_step": (cs.kernel_launches() - l0) / steps}
+            "outputs_per_step": n, "launches_per_step": (cs.kernel_launches() - l0) / steps,
+            "agc_counters(seq gain, seq fsm, refined)": chain.agc_counters()}
     if b_alg:
         line["hbm_frac_of_6540GBs"] = b_alg * tot / (ms * 1e-3) / 1e9 / 6540.2
     print(json.dumps(line), flush=True)

@@ -11,6 +11,11 @@
 
 using namespace csdr;
 
+struct EmuLaunch {
+    template <class K, class... A> void operator()(K k, dim3 g, dim3 b, size_t smem, A... a) const { csdr_emu::launch(g, b, smem, k, a...); }
+    void debug_after_verify(const BackendParams &) const {}
+};
+
 extern "C" {
 
 // mix (mode 0/1/2, freq in radians/sample) + msresamp(rate, As), fed in the given chunk sizes.
@@ -90,7 +95,7 @@ long long emu_backend(int nlanes, long long lane_stride, int has_dc, float dc_al
         d.a1 = -1.0f + dc_alpha; d.c = -(double)d.a1; d.Vloc = Vloc.data(); d.carry = carry.data(); d.lane = lane.data();
         { double A = 1.0; for (int i = 0; i < G; i++) A *= d.c; powA[0] = 1.0; for (int k = 1; k <= kDcGB; k++) powA[k] = powA[k - 1] * A; }
         d.powA = powA.data();
-        auto launch = [](auto k, dim3 g, dim3 b, size_t smem, auto... a) { csdr_emu::launch(g, b, smem, k, a...); };
+        EmuLaunch launch;
         if (has_dc) be_launch_dc(launch, d, false);
         BackendParams b{};
         b.in = x + pos; b.in_lane_stride = lane_stride;
