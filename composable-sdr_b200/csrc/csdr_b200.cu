@@ -30,7 +30,7 @@ namespace {
 
 thread_local std::string t_err;
 std::atomic<unsigned long long> g_launches{0};
-int g_options[16] = {0, 1, 0, 512, 384, 0, 0, 0, 0};
+int g_options[16] = {0, 1, 0, 512, 384, 0, 0, 0, 0, 0};
 
 void set_err(const std::string &s) { t_err = s; }
 void clear_err() { t_err.clear(); }
@@ -176,18 +176,26 @@ struct Frontend {
             int t = 4096 >> ms.S; t = std::max(32, std::min(2048, t));
             Tc = (t + 7) / 8 * 8;
         }
-        geo = plan_frontend(ms, Tc, g_options[CSDR_OPT_GENERIC_FRONTEND] == 0);
+        geo = plan_frontend(ms, Tc, g_options[CSDR_OPT_GENERIC_FRONTEND] == 0, g_options[CSDR_OPT_FRONTEND_VARIANT]);
         if (!geo.error.empty()) throw CudaError{geo.error};
         kernel = k_frontend;
-        if (geo.std_kernel) {
+        if (geo.std_kernel && geo.variant == 0) {
             switch (ms.S) {
-            case 1: kernel = k_frontend_std<1>; break;
-            case 2: kernel = k_frontend_std<2>; break;
-            case 3: kernel = k_frontend_std<3>; break;
-            case 4: kernel = k_frontend_std<4>; break;
-            case 5: kernel = k_frontend_std<5>; break;
-            case 6: kernel = k_frontend_std<6>; break;
+            case 1: kernel = k_frontend_std<1, 0>; break;
+            case 2: kernel = k_frontend_std<2, 0>; break;
+            case 3: kernel = k_frontend_std<3, 0>; break;
+            case 4: kernel = k_frontend_std<4, 0>; break;
+            case 5: kernel = k_frontend_std<5, 0>; break;
+            case 6: kernel = k_frontend_std<6, 0>; break;
             default: throw CudaError{"frontend: no specialised kernel for this stage count"};
+            }
+        } else if (geo.std_kernel) {
+            switch (ms.S) {
+            case 1: kernel = k_frontend_std<1, 1>; break;
+            case 2: kernel = k_frontend_std<2, 1>; break;
+            case 3: kernel = k_frontend_std<3, 1>; break;
+            case 4: kernel = k_frontend_std<4, 1>; break;
+            default: throw CudaError{"frontend: no TMA-staged kernel for this stage count"};
             }
         }
         nstreams = streams;

@@ -69,11 +69,18 @@ __host__ __device__ constexpr int fe_std_tc(int S)
 {
     return S == 1 ? 1792 : S == 2 ? 896 : S == 3 ? 400 : S == 4 ? 208 : S == 5 ? 96 : 48;
 }
-__host__ __device__ constexpr FeGeom fe_make_geom_std(int S)
+// variant 1: TMA bulk-copy staging buffer instead of the register prefetch, polyphase bank read through L1, and tiles
+// small enough for three CTAs per SM (<= ~75 KB each)
+__host__ __device__ constexpr int fe_std_tc_tma(int S)
+{
+    return S == 1 ? 1536 : S == 2 ? 768 : S == 3 ? 384 : 192;
+}
+__host__ __device__ constexpr FeGeom fe_make_geom_std(int S, int variant = 0)
 {
     FeStdM mm{};
-    return fe_make_geom(S, fe_std_tc(S), mm.v, 1, 0);
+    return variant ? fe_make_geom(S, fe_std_tc_tma(S), mm.v, 1, 1) : fe_make_geom(S, fe_std_tc(S), mm.v, 1, 0);
 }
-constexpr int kFeStdMaxS = 6;      // k_frontend_std is instantiated for S = 1..6
+constexpr int kFeStdMaxS = 6;      // k_frontend_std<S, 0> is instantiated for S = 1..6
+constexpr int kFeTmaMaxS = 4;      // k_frontend_std<S, 1> for S = 1..4
 
 }  // namespace csdr

@@ -11,7 +11,8 @@ namespace csdr {
 struct FrontendGeometry {
     FrontendParams base;     // geometry + taps filled in; per-call fields zero
     FeGeom geom;
-    bool std_kernel = false; // k_frontend_std<S> applies (compile-time geometry)
+    bool std_kernel = false; // k_frontend_std<S, V> applies (compile-time geometry)
+    int variant = 0;         // 0: register prefetch, 2 CTAs/SM; 1: TMA staging buffer, bank through L1, 3 CTAs/SM
     int hcap = 0;            // raw-sample history the kernel may reach back over
     size_t smem_bytes = 0;
     std::string error;
@@ -21,7 +22,7 @@ inline int fe_roundup(int v, int m) { return (v + m - 1) / m * m; }
 
 // Tc: c-samples (half-band cascade outputs) per tile for the generic kernel; multiple of 8.  allow_std: use the
 // compile-time geometry (and its own tile size) when the half-band plan is the standard one.
-inline FrontendGeometry plan_frontend(const design::MsresampPlan &ms, int Tc, bool allow_std = true)
+inline FrontendGeometry plan_frontend(const design::MsresampPlan &ms, int Tc, bool allow_std = true, int variant = 0)
 {
     FrontendGeometry g{};
     FrontendParams &p = g.base;
@@ -38,7 +39,8 @@ inline FrontendGeometry plan_frontend(const design::MsresampPlan &ms, int Tc, bo
         if (m[s] != stdm.v[s]) is_std = false;
     }
     g.std_kernel = is_std;
-    g.geom = is_std ? fe_make_geom_std(S) : fe_make_geom(S, Tc, m, 0, 0);
+    g.variant = (is_std && variant == 1 && S <= kFeTmaMaxS) ? 1 : 0;
+    g.geom = is_std ? fe_make_geom_std(S, g.variant) : fe_make_geom(S, Tc, m, 0, 0);
     const FeGeom &G = g.geom;
     p.S = S; p.Tc = G.Tc;
     p.zeta = 1.0f / (float)(1u << ms.S);
@@ -49,7 +51,7 @@ inline FrontendGeometry plan_frontend(const design::MsresampPlan &ms, int Tc, bo
     }
     for (int L = 0; L <= S; L++) { p.n[L] = G.n[L]; p.d[L] = G.d[L]; p.stride[L] = G.stride[L]; p.off[L] = G.off[L]; }
     p.off_bank = 2 * G.total_f2;
-    g.smem_bytes = (size_t)G.total_f2 * 8 + (size_t)(1u << ms.bits) * (kHsub + 1) * 4;
+    g.smem_bytes = (size_t)G.total_f2 * 8 + (g.variant ? 0 : (size_t)(1u << ms.bits) * (kHsub + 1) * 4);
     p.smem_bytes = (int)g.smem_bytes;
     g.hcap = G.hcap;
     return g;

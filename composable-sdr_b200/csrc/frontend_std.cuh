@@ -11,7 +11,7 @@
 
 namespace csdr {
 
-template <int S> struct FeStd { static constexpr FeGeom G = fe_make_geom_std(S); };
+template <int S, int V = 0> struct FeStd { static constexpr FeGeom G = fe_make_geom_std(S, V); };
 
 __device__ __forceinline__ float4 fe_ldg_stream(const float4 *p)
 {
@@ -39,38 +39,38 @@ __device__ __forceinline__ float2 fe_mix(float2 v, unsigned th, int quantize)
 // ---- top level: (mix) -> shared, in the consumer's de-interleaved layout ------------------------------------
 // A tile that lies inside the chunk at a 16-byte aligned address is "bulk": its raw samples are prefetched into
 // registers (fe_prefetch) while the previous tile is being filtered.
-template <int S>
+template <int S, int V>
 __device__ __forceinline__ bool fe_tile_is_bulk(const FrontendParams &p, const float2 *xs, long long lo)
 {
-    constexpr int NS = FeStd<S>::G.n[S];
+    constexpr int NS = FeStd<S, V>::G.n[S];
     const long long rel0 = lo - p.n0;
     return rel0 >= 0 && rel0 + NS <= p.nx && ((reinterpret_cast<uintptr_t>(xs + rel0) & 15) == 0);
 }
 
-template <int S> struct FePrefetch {
-    static constexpr int NP = FeStd<S>::G.n[S] / 2, IT = (NP + 255) / 256;
-    float4 v[IT];
+template <int S, int V> struct FePrefetch {
+    static constexpr int NP = FeStd<S, V>::G.n[S] / 2, IT = (NP + 255) / 256;
+    float4 v[V ? 1 : IT];          // variant 1 stages through shared memory instead
 };
 
 // issue the 16-byte loads of a bulk tile; they complete while the previous tile is being filtered
 template <int S>
-__device__ __forceinline__ void fe_prefetch(FePrefetch<S> &pre, const FrontendParams &p, const float2 *__restrict__ xs,
+__device__ __forceinline__ void fe_prefetch(FePrefetch<S, 0> &pre, const FrontendParams &p, const float2 *__restrict__ xs,
                                             long long lo)
 {
     const float4 *src = reinterpret_cast<const float4 *>(xs + (lo - p.n0));
 #pragma unroll
-    for (int k = 0; k < FePrefetch<S>::IT; k++) {
+    for (int k = 0; k < FePrefetch<S, 0>::IT; k++) {
         const int pi = threadIdx.x + 256 * k;
-        if (pi < FePrefetch<S>::NP) pre.v[k] = fe_ldg_stream(src + pi);
+        if (pi < FePrefetch<S, 0>::NP) pre.v[k] = fe_ldg_stream(src + pi);
     }
 }
 
-template <int S, int MIX>
+template <int S, int V, int MIX>
 __device__ __forceinline__ void fe_load_top(const FrontendParams &p, const float2 *__restrict__ xs,
                                             const float2 *__restrict__ hs, float2 *__restrict__ dst, long long lo,
-                                            const FePrefetch<S> &pre, bool bulk)
+                                            const FePrefetch<S, V> &pre, const float2 *__restrict__ raw, bool bulk)
 {
-    constexpr FeGeom G = FeStd<S>::G;
+    constexpr FeGeom G = FeStd<S, V>::G;
     constexpr int NS = G.n[S], STR = G.stride[S], D = G.R[S - 1];
     static_assert(D == 8 && NS % 2 == 0, "loader assumes an 8-way layout of the top level");
     const int tid = threadIdx.x;
@@ -82,10 +82,10 @@ __device__ __forceinline__ void fe_load_top(const FrontendParams &p, const float
         float2 *dE = dst + (tid & 7) * STR + (tid >> 3);
         float2 *dO = dE + D * STR;
 #pragma unroll
-        for (int k = 0; k < FePrefetch<S>::IT; k++) {
+        for (int k = 0; k < FePrefetch<S, V>::IT; k++) {
             const int pi = tid + 256 * k;
-            if (pi < FePrefetch<S>::NP) {
-                const float4 v = pre.v[k];
+            if (pi < FePrefetch<S, V>::NP) {
+                const float4 v = V ? reinterpret_cast<const float4 *>(raw)[pi] : pre.v[V ? 0 : k];
                 const unsigned th = th0 + (unsigned)(2 * pi) * p.dtheta;
                 dE[32 * k] = fe_mix<MIX>(cf(v.x, v.y), th, p.quantize);
                 dO[32 * k] = fe_mix<MIX>(cf(v.z, v.w), th + p.dtheta, p.quantize);
@@ -160,17 +160,17 @@ __device__ __forceinline__ void fe_stage_c(const float2 *__restrict__ in, float2
     }
 }
 
-template <int S, int s>
+template <int S, int V, int s>
 __device__ __forceinline__ void fe_run_stages(const FrontendParams &p, float2 *smem)
 {
-    constexpr FeGeom G = FeStd<S>::G;
+    constexpr FeGeom G = FeStd<S, V>::G;
     constexpr bool LAST = (s == 0);
     constexpr int D2 = LAST ? 1 : G.R[LAST ? 0 : s - 1];
     constexpr int SH = (s == S - 1) ? G.shift : 0;
     fe_stage_c<G.m[s], G.R[s], G.stride[s + 1], SH, G.n[s], LAST, D2, G.stride[s]>(
         smem + G.off[s + 1], smem + G.off[s], p.taps[s], p.zeta);
     __syncthreads();
-    if constexpr (s > 0) fe_run_stages<S, s - 1>(p, smem);
+    if constexpr (s > 0) fe_run_stages<S, V, s - 1>(p, smem);
 }
 
 // ceil(num / st) for num < 2^57, st < 2^26 without a 64-bit division: fp64 estimate + exact integer correction
@@ -186,33 +186,38 @@ __device__ __forceinline__ long long fe_ceil_div(unsigned long long num, unsigne
 struct FeTileInfo { long long lo; int bulk, oA, oB, pad; };
 
 // everything one tile needs that is not per-thread work: computed by ONE thread, one tile ahead
-template <int S>
+template <int S, int V>
 __device__ __forceinline__ void fe_tile_info(const FrontendParams &p, const float2 *xs, int tile, double inv_st, FeTileInfo &ti)
 {
-    constexpr FeGeom G = FeStd<S>::G;
+    constexpr FeGeom G = FeStd<S, V>::G;
     const long long kArel = (long long)tile * G.Tc;                 // pushes relative to K0
     const long long kBrel = min(kArel + (long long)G.Tc, p.K1 - p.K0);
     ti.lo = (p.K0 + kArel - kHcPad) * (1LL << S) + G.d[S];
-    ti.bulk = fe_tile_is_bulk<S>(p, xs, ti.lo) ? 1 : 0;
+    ti.bulk = fe_tile_is_bulk<S, V>(p, xs, ti.lo) ? 1 : 0;
     // outputs emitted by pushes [kA, kB): o' with kArel*2^24 <= ph0 + o'*step < kBrel*2^24
     const unsigned long long a = (unsigned long long)kArel << 24, b = (unsigned long long)kBrel << 24;
     ti.oA = (a > p.ph0) ? (int)fe_ceil_div(a - p.ph0, p.step, inv_st) : 0;
     ti.oB = (b > p.ph0) ? (int)fe_ceil_div(b - p.ph0, p.step, inv_st) : 0;
 }
 
-template <int S>
-__global__ void __launch_bounds__(256, 2) k_frontend_std(const CSDR_GRID_CONSTANT FrontendParams p)
+template <int S, int V>
+__global__ void __launch_bounds__(256, V ? 3 : 2) k_frontend_std(const CSDR_GRID_CONSTANT FrontendParams p)
 {
-    constexpr FeGeom G = FeStd<S>::G;
+    constexpr FeGeom G = FeStd<S, V>::G;
+    constexpr int NS = G.n[S];
     CSDR_DYN_SMEM(smem_raw);
     float2 *smem = reinterpret_cast<float2 *>(smem_raw);
-    float *bank_s = reinterpret_cast<float *>(smem_raw) + 2 * G.total_f2;
+    float *bank_s = reinterpret_cast<float *>(smem_raw) + 2 * G.total_f2;    // variant 0 only
+    const float2 *raw = smem + G.off_raw;                                     // variant 1 only
     __shared__ FeTileInfo s_info[3];
+    __shared__ __align__(8) unsigned long long s_bar;
 
     const int npfb = 1 << p.bits;
-    for (int i = threadIdx.x; i < npfb * kHsub; i += 256) {
-        const int row = i / kHsub, col = i - row * kHsub;
-        bank_s[row * (kHsub + 1) + col] = p.bank[i];
+    if (!V) {
+        for (int i = threadIdx.x; i < npfb * kHsub; i += 256) {
+            const int row = i / kHsub, col = i - row * kHsub;
+            bank_s[row * (kHsub + 1) + col] = p.bank[i];
+        }
     }
     const float2 *xs = p.x + (long long)blockIdx.y * p.x_stride;
     const float2 *hs = p.hist + (long long)blockIdx.y * p.hcap;
@@ -227,14 +232,20 @@ __global__ void __launch_bounds__(256, 2) k_frontend_std(const CSDR_GRID_CONSTAN
     // (A TMA bulk-copy staging buffer does the same but costs two extra passes over shared memory, the resource this
     // kernel is bound by; measured 217 us vs the register pipeline, see DESIGN.md.)  Tile bookkeeping (absolute
     // position, alignment, output range) is done by one thread, two tiles ahead.
+    // Variant 1 stages the raw tile in shared memory with a TMA bulk copy (cp.async.bulk + mbarrier) issued as soon as
+    // the previous tile has been mixed: no prefetch registers, three CTAs per SM.
+    unsigned parity = 0;
     if (threadIdx.x == 0) {
         const int t0 = (int)blockIdx.x;
-        if (t0 < p.ntiles) fe_tile_info<S>(p, xs, t0, inv_st, s_info[0]);
-        if (t0 + gstep < p.ntiles) fe_tile_info<S>(p, xs, t0 + gstep, inv_st, s_info[1]);
+        if (V) bulk_init(&s_bar);
+        if (t0 < p.ntiles) fe_tile_info<S, V>(p, xs, t0, inv_st, s_info[0]);
+        if (t0 + gstep < p.ntiles) fe_tile_info<S, V>(p, xs, t0 + gstep, inv_st, s_info[1]);
+        if (V && t0 < p.ntiles && s_info[0].bulk)
+            bulk_copy_g2s(smem + G.off_raw, xs + (s_info[0].lo - p.n0), NS * (unsigned)sizeof(float2), &s_bar);
     }
     __syncthreads();
-    FePrefetch<S> pre;
-    if ((int)blockIdx.x < p.ntiles && s_info[0].bulk) fe_prefetch<S>(pre, p, xs, s_info[0].lo);
+    FePrefetch<S, V> pre;
+    if constexpr (!V) { if ((int)blockIdx.x < p.ntiles && s_info[0].bulk) fe_prefetch<S>(pre, p, xs, s_info[0].lo); }
 
     int cur = 0;
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gstep) {
@@ -242,16 +253,23 @@ __global__ void __launch_bounds__(256, 2) k_frontend_std(const CSDR_GRID_CONSTAN
         const long long lo = s_info[cur].lo;
         const bool bulk = s_info[cur].bulk != 0;
         float2 *top = smem + G.off[S];
-        if (p.mix_mode == 0)      fe_load_top<S, 0>(p, xs, hs, top, lo, pre, bulk);
-        else if (p.quantize) { if (p.mix_mode == 1) fe_load_top<S, 1 | 8>(p, xs, hs, top, lo, pre, bulk);
-                               else                 fe_load_top<S, 2 | 8>(p, xs, hs, top, lo, pre, bulk); }
-        else                 { if (p.mix_mode == 1) fe_load_top<S, 1 | 4>(p, xs, hs, top, lo, pre, bulk);
-                               else                 fe_load_top<S, 2 | 4>(p, xs, hs, top, lo, pre, bulk); }
-        if (threadIdx.x == 0 && tile + 2 * gstep < p.ntiles) fe_tile_info<S>(p, xs, tile + 2 * gstep, inv_st, s_info[nxt2]);
+        if (V && bulk) { bulk_wait(&s_bar, parity); parity ^= 1u; }
+        if (p.mix_mode == 0)      fe_load_top<S, V, 0>(p, xs, hs, top, lo, pre, raw, bulk);
+        else if (p.quantize) { if (p.mix_mode == 1) fe_load_top<S, V, 1 | 8>(p, xs, hs, top, lo, pre, raw, bulk);
+                               else                 fe_load_top<S, V, 2 | 8>(p, xs, hs, top, lo, pre, raw, bulk); }
+        else                 { if (p.mix_mode == 1) fe_load_top<S, V, 1 | 4>(p, xs, hs, top, lo, pre, raw, bulk);
+                               else                 fe_load_top<S, V, 2 | 4>(p, xs, hs, top, lo, pre, raw, bulk); }
+        if (threadIdx.x == 0 && tile + 2 * gstep < p.ntiles) fe_tile_info<S, V>(p, xs, tile + 2 * gstep, inv_st, s_info[nxt2]);
         __syncthreads();
-        if (tile + gstep < p.ntiles && s_info[nxt].bulk) fe_prefetch<S>(pre, p, xs, s_info[nxt].lo);
+        if constexpr (V) {
+            // the staging buffer has been consumed: start fetching the next tile of this CTA
+            if (threadIdx.x == 0 && tile + gstep < p.ntiles && s_info[nxt].bulk)
+                bulk_copy_g2s(smem + G.off_raw, xs + (s_info[nxt].lo - p.n0), NS * (unsigned)sizeof(float2), &s_bar);
+        } else {
+            if (tile + gstep < p.ntiles && s_info[nxt].bulk) fe_prefetch<S>(pre, p, xs, s_info[nxt].lo);
+        }
 
-        fe_run_stages<S, S - 1>(p, smem);
+        fe_run_stages<S, V, S - 1>(p, smem);
 
         // arbitrary resampler (rate_arb < 1: every push emits at most one output).  One thread per PAIR of pushes:
         // the 16 c-samples both windows need are fetched with eight conflict-free 16-byte loads and stay in registers;
@@ -273,12 +291,14 @@ __global__ void __launch_bounds__(256, 2) k_frontend_std(const CSDR_GRID_CONSTAN
                 for (int e = 0; e < 2; e++) {
                     const unsigned long long ph = p.ph0 + (unsigned long long)o * p.step;
                     if (2 * t + e < npush && (ph >> 24) == kk + e) {
-                        const float *h = bank_s + ((unsigned)(ph >> sh) & mask) * (kHsub + 1);
+                        const float *h = V ? p.bank + ((unsigned)(ph >> sh) & mask) * kHsub
+                                           : bank_s + ((unsigned)(ph >> sh) & mask) * (kHsub + 1);
                         float ar = 0.f, ai = 0.f;
 #pragma unroll
                         for (int j = 0; j < kHsub; j++) {
-                            ar = fmaf(h[j], w[14 + e - j].x, ar);
-                            ai = fmaf(h[j], w[14 + e - j].y, ai);
+                            const float hj = V ? __ldg(h + j) : h[j];
+                            ar = fmaf(hj, w[14 + e - j].x, ar);
+                            ai = fmaf(hj, w[14 + e - j].y, ai);
                         }
                         ys[o] = cf(ar, ai);
                         o++;

@@ -25,17 +25,26 @@ long long emu_frontend(float rate, float As, int mix_mode, float freq, int quant
                        unsigned long long seek, int allow_std, long long misalign)
 {
     design::MsresampPlan ms = design::plan_msresamp(rate, As);
-    FrontendGeometry g = plan_frontend(ms, Tc, allow_std != 0);
+    FrontendGeometry g = plan_frontend(ms, Tc, allow_std != 0, allow_std == 2 ? 1 : 0);
     void (*kernel)(FrontendParams) = k_frontend;
     if (g.std_kernel) {
         nthreads = 256;
-        switch (ms.S) {
-        case 1: kernel = k_frontend_std<1>; break;
-        case 2: kernel = k_frontend_std<2>; break;
-        case 3: kernel = k_frontend_std<3>; break;
-        case 4: kernel = k_frontend_std<4>; break;
-        case 5: kernel = k_frontend_std<5>; break;
-        default: kernel = k_frontend_std<6>; break;
+        if (g.variant == 0) {
+            switch (ms.S) {
+            case 1: kernel = k_frontend_std<1, 0>; break;
+            case 2: kernel = k_frontend_std<2, 0>; break;
+            case 3: kernel = k_frontend_std<3, 0>; break;
+            case 4: kernel = k_frontend_std<4, 0>; break;
+            case 5: kernel = k_frontend_std<5, 0>; break;
+            default: kernel = k_frontend_std<6, 0>; break;
+            }
+        } else {
+            switch (ms.S) {
+            case 1: kernel = k_frontend_std<1, 1>; break;
+            case 2: kernel = k_frontend_std<2, 1>; break;
+            case 3: kernel = k_frontend_std<3, 1>; break;
+            default: kernel = k_frontend_std<4, 1>; break;
+            }
         }
     }
     // the caller's buffer is copied to a 16-byte aligned (or deliberately misaligned) one: exercises both loaders

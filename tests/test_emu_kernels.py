@@ -12,7 +12,9 @@ from util import assert_parity, make_signal
     (0.625, 60.0, 256, 128, 0, False), (0.078125, 40.0, 64, 64, 1, True), (0.078125, 80.0, 64, 64, 0, True),
     # compile-time-geometry kernel k_frontend_std<S>, S = 1..6
     (0.3, 60.0, 0, 256, 1, True), (0.2, 60.0, 0, 256, 2, True), (0.078125, 60.0, 0, 256, 1, True),
-    (0.04, 60.0, 0, 256, 0, True), (0.02, 60.0, 0, 256, 1, True), (0.011, 60.0, 0, 256, 1, True)])
+    (0.04, 60.0, 0, 256, 0, True), (0.02, 60.0, 0, 256, 1, True), (0.011, 60.0, 0, 256, 1, True),
+    # TMA-staged variant k_frontend_std<S, 1>, S = 1..4
+    (0.3, 60.0, 0, 256, 1, 2), (0.2, 60.0, 0, 256, 0, 2), (0.078125, 60.0, 0, 256, 1, 2), (0.04, 60.0, 0, 256, 2, 2)])
 def test_frontend_matches_oracle(orc, emu, rate, As, Tc, nthreads, mix, std):
     x = make_signal(40000, 7)
     f = float(np.float32(0.24543693))
