@@ -20,4 +20,4 @@ for variant in (0, 1):
     print(f"variant {variant}: k_frontend {ms / k * 1e3:.1f} us per 2^27 samples -> {n / (ms / k) / 1e6:.1f} GS/s, "
           f"{8.3125 * n / (ms / k * 1e-3) / 1e9 / 6540.2:.3f} of measured HBM roofline", flush=True)
     ch.close()
-cs.set_option(9, 0)
+cs.set_option(9, 1)
