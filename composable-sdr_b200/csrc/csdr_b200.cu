@@ -30,7 +30,7 @@ namespace {
 
 thread_local std::string t_err;
 std::atomic<unsigned long long> g_launches{0};
-int g_options[16] = {0, 1, 0, 512, 384, 0, 0, 0, 0, 1};
+int g_options[16] = {0, 1, 0, 512, 384, 0, 0, 0, 0, 2};
 
 void set_err(const std::string &s) { t_err = s; }
 void clear_err() { t_err.clear(); }
@@ -140,7 +140,7 @@ struct Frontend {
     FrontendGeometry geo;
     int nstreams = 1;
     DevBuf hist[2]; int cur = 0;
-    DevBuf bank;
+    DevBuf bank, bank16;
     FrontendCursor cursor;
     int mix_mode = 0; uint32_t theta0 = 0, dtheta = 0; int quantize = 1;
     void (*kernel)(FrontendParams) = k_frontend;
@@ -189,6 +189,15 @@ struct Frontend {
             case 6: kernel = k_frontend_std<6, 0>; break;
             default: throw CudaError{"frontend: no specialised kernel for this stage count"};
             }
+        } else if (geo.std_kernel && geo.variant == 2) {
+            switch (ms.S) {
+            case 2: kernel = k_frontend_v2<2>; break;
+            case 3: kernel = k_frontend_v2<3>; break;
+            case 4: kernel = k_frontend_v2<4>; break;
+            case 5: kernel = k_frontend_v2<5>; break;
+            case 6: kernel = k_frontend_v2<6>; break;
+            default: throw CudaError{"frontend: no fused-mix kernel for this stage count"};
+            }
         } else if (geo.std_kernel) {
             switch (ms.S) {
             case 1: kernel = k_frontend_std<1, 1>; break;
@@ -203,6 +212,14 @@ struct Frontend {
         for (auto &h : hist) { h.ensure(hb); CK(cudaMemsetAsync(h.p, 0, h.cap, c.stream)); }
         bank.ensure(ms.bank.size() * sizeof(float));
         CK(cudaMemcpyAsync(bank.p, ms.bank.data(), ms.bank.size() * sizeof(float), cudaMemcpyHostToDevice, c.stream));
+        {
+            const size_t rows = ms.bank.size() / kHsub;
+            std::vector<float> b16(rows * 16, 0.f);
+            for (size_t r = 0; r < rows; r++) for (int j = 0; j < kHsub; j++) b16[r * 16 + j] = ms.bank[r * kHsub + j];
+            bank16.ensure(b16.size() * sizeof(float));
+            CK(cudaMemcpyAsync(bank16.p, b16.data(), b16.size() * sizeof(float), cudaMemcpyHostToDevice, c.stream));
+            c.sync();      // b16 goes out of scope
+        }
         CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)geo.smem_bytes));
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kernel, 256, geo.smem_bytes));
         if (ctas_per_sm < 1) throw CudaError{"frontend: tile does not fit in shared memory"};
@@ -222,7 +239,7 @@ struct Frontend {
         p.x = x; p.hist = hist[cur].as<float2>(); p.y = y; p.hcap = geo.hcap;
         p.x_stride = x_stride; p.y_stride = y_stride;
         p.mix_mode = mix_mode; p.theta0 = theta0; p.dtheta = dtheta; p.quantize = quantize;
-        p.bank = bank.as<float>();
+        p.bank = bank.as<float>(); p.bank16 = bank16.as<float>();
         if (p.ntiles > 0) {
             const int slots = c.sms * ctas_per_sm;      // persistent CTAs: one wave, tiles strided over the grid
             int gx = std::min(p.ntiles, std::max(1, slots / std::max(1, std::min(nstreams, slots))));

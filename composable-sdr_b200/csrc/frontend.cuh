@@ -59,6 +59,7 @@ struct FrontendParams {
     // arbitrary resampler
     unsigned step; int bits;    // npfb = 1<<bits
     const float *bank;          // [npfb][kHsub], bank[i][j] multiplies c[k-j]
+    const float *bank16;        // the same rows padded to 16 floats (16-byte loads through L1)
     unsigned long long ph0;     // resampler phase (liquid's q->phase) before push K0: output o' of this call has
                                 // phase ph0 + o'*step relative to push K0
     int off_bank;               // float offset (in floats) of the bank copy in dynamic smem
@@ -79,15 +80,29 @@ __device__ __forceinline__ int fe_addr_rt(int i, int D, int stride)
     return ((i & 1) * D + (p & (D - 1))) * stride + (p >> lg);
 }
 
+// Phasor with the quantisation mode known at compile time.  The phase index is turned into a float by bit insertion
+// (2^23 + k has k in its mantissa), not by an int->float conversion: conversions share the XU pipe with the sin/cos
+// evaluations, which is the pipe this per-sample work is bound by.  Q = 1: NCO sine table, 1024 levels, th already
+// carries the +2^21 rounding offset; Q = 0: the top 23 phase bits.
+template <int Q>
+__device__ __forceinline__ float2 fe_phasor_q(unsigned th)
+{
+    constexpr float a = Q ? 6.1359231515425649e-3f : 7.4901405658478575e-7f;    // 2 pi / 1024, 2 pi / 2^23
+#ifdef CSDR_EMU
+    const unsigned kbits = 0x4B000000u | (Q ? (th >> 22) : (th >> 9));
+#else
+    const unsigned kbits = Q ? __funnelshift_r(th, 0x4B000000u >> 10, 22) : __funnelshift_r(th, 0x4B000000u >> 23, 9);
+#endif
+    const float ang = fmaf(__uint_as_float(kbits), a, -8388608.0f * a);          // k * a, rounded once (2^23 a is exact)
+    float s, c;
+    __sincosf(ang, &s, &c);
+    return cf(c, s);
+}
+
 // phasor of the NCO at phase word `th`:  (cos, sin)
 __device__ __forceinline__ float2 fe_phasor(unsigned th, int quantize)
 {
-    if (quantize) th = (th + (1u << 21)) & 0xffc00000u;      // NCO(_index): round to 1024 levels
-    // signed phase in (-pi, pi]: the SFU approximations are most accurate there (abs err ~2^-21.4)
-    float a = (float)(int)th * 1.4629180792671596e-9f;       // 2*pi / 2^32
-    float s, c;
-    __sincosf(a, &s, &c);
-    return cf(c, s);
+    return quantize ? fe_phasor_q<1>(th + (1u << 21)) : fe_phasor_q<0>(th);   // NCO(_index): round to 1024 levels
 }
 
 // One half-band decimation stage over a tile: n_out outputs, R per thread slot.

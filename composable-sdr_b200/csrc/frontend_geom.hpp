@@ -45,20 +45,25 @@ __host__ __device__ constexpr FeGeom fe_make_geom(int S, int Tc, const int *m, i
         g.n[L + 1] = ce_roundup(need, mult);
         g.d[L + 1] = 2 * g.d[L] + 1 - 4 * g.m[L] - sh;
     }
-    int sizeA = 0, sizeB = 0;
+    // raw = 2: the top level has a buffer of its own (the next tile is copied into it while the lower stages of the
+    // current tile run); the lower levels ping-pong between two regions as before
+    const int priv = (raw == 2 && S > 0) ? 1 : 0;
+    int sizeA = 0, sizeB = 0, sizeT = 0;
     for (int L = 1; L <= S; L++) {
         const int D = g.R[L - 1];
         int st = g.n[L] / (2 * D) + 1;
         while ((st & 15) != 2) st++;
         g.stride[L] = st;
         const int sz = 2 * D * st;
-        if (((S - L) & 1) == 0) sizeA = ce_max(sizeA, sz); else sizeB = ce_max(sizeB, sz);
+        if (priv && L == S) sizeT = sz;
+        else if (((S - L) & 1) == 0) sizeA = ce_max(sizeA, sz); else sizeB = ce_max(sizeB, sz);
     }
     const int size0 = ce_roundup(g.n[0] + 2, 2);
     g.off[0] = 0;
-    for (int L = 1; L <= S; L++) g.off[L] = size0 + ((((S - L) & 1) == 0) ? 0 : sizeA);
-    g.total_f2 = size0 + sizeA + sizeB;
-    if (raw && S > 0) { g.off_raw = g.total_f2; g.total_f2 += g.n[S]; }
+    for (int L = 1; L <= S; L++) g.off[L] = size0 + sizeT + ((((S - L) & 1) == 0) ? 0 : sizeA);
+    if (priv) g.off[S] = size0;
+    g.total_f2 = size0 + sizeT + sizeA + sizeB;
+    if (raw == 1 && S > 0) { g.off_raw = g.total_f2; g.total_f2 += g.n[S]; }
     g.hcap = ce_roundup(((1 << S) - 1) + (kHcPad << S) - g.d[S] + 1, 64);
     return g;
 }
@@ -75,12 +80,20 @@ __host__ __device__ constexpr int fe_std_tc_tma(int S)
 {
     return S == 1 ? 1536 : S == 2 ? 768 : S == 3 ? 384 : 192;
 }
+// variant 2: the raw tile is copied asynchronously straight into the top level's layout and mixed by the first
+// half-band stage as it reads; <= ~55 KB per CTA, four CTAs per SM
+__host__ __device__ constexpr int fe_std_tc_v2(int S)
+{
+    return S == 2 ? 768 : S == 3 ? 384 : S == 4 ? 176 : S == 5 ? 64 : 32;
+}
 __host__ __device__ constexpr FeGeom fe_make_geom_std(int S, int variant = 0)
 {
     FeStdM mm{};
-    return variant ? fe_make_geom(S, fe_std_tc_tma(S), mm.v, 1, 1) : fe_make_geom(S, fe_std_tc(S), mm.v, 1, 0);
+    return variant == 2 ? fe_make_geom(S, fe_std_tc_v2(S), mm.v, 1, 2)
+         : variant == 1 ? fe_make_geom(S, fe_std_tc_tma(S), mm.v, 1, 1) : fe_make_geom(S, fe_std_tc(S), mm.v, 1, 0);
 }
 constexpr int kFeStdMaxS = 6;      // k_frontend_std<S, 0> is instantiated for S = 1..6
 constexpr int kFeTmaMaxS = 4;      // k_frontend_std<S, 1> for S = 1..4
+constexpr int kFeV2MinS = 2;       // k_frontend_v2<S> for S = 2..6 (with one stage the fused mix would redo 2.2x the work)
 
 }  // namespace csdr

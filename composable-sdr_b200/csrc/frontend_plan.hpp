@@ -12,7 +12,8 @@ struct FrontendGeometry {
     FrontendParams base;     // geometry + taps filled in; per-call fields zero
     FeGeom geom;
     bool std_kernel = false; // k_frontend_std<S, V> applies (compile-time geometry)
-    int variant = 0;         // 0: register prefetch, 2 CTAs/SM; 1: TMA staging buffer, bank through L1, 3 CTAs/SM
+    int variant = 0;         // 0: register prefetch, 2 CTAs/SM; 1: TMA staging buffer, bank through L1, 3 CTAs/SM;
+                             // 2: asynchronous copy into the top level + mix fused into the first stage, 4 CTAs/SM
     int hcap = 0;            // raw-sample history the kernel may reach back over
     size_t smem_bytes = 0;
     std::string error;
@@ -39,7 +40,10 @@ inline FrontendGeometry plan_frontend(const design::MsresampPlan &ms, int Tc, bo
         if (m[s] != stdm.v[s]) is_std = false;
     }
     g.std_kernel = is_std;
-    g.variant = (is_std && variant == 1 && S <= kFeTmaMaxS) ? 1 : 0;
+    // variant 2 falls back to 1 where it does not apply (a single half-band stage), variant 1 to 0 (S > 4)
+    g.variant = 0;
+    if (is_std && variant == 2 && S >= kFeV2MinS) g.variant = 2;
+    else if (is_std && variant >= 1 && S <= kFeTmaMaxS) g.variant = 1;
     g.geom = is_std ? fe_make_geom_std(S, g.variant) : fe_make_geom(S, Tc, m, 0, 0);
     const FeGeom &G = g.geom;
     p.S = S; p.Tc = G.Tc;

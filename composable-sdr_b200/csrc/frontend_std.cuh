@@ -36,6 +36,18 @@ __device__ __forceinline__ float2 fe_mix(float2 v, unsigned th, int quantize)
     return cf(v.x * w.x - v.y * s, v.y * w.x + v.x * s);
 }
 
+// MIX: bits 0-1 = mode (0 none, 1 down: v * conj(w), 2 up: v * w), bit 3 = quantised NCO
+template <int MIX>
+__device__ __forceinline__ float2 fe_mix_q(float2 v, unsigned th)
+{
+    if constexpr ((MIX & 3) == 0) return v;
+    else {
+        const float2 w = fe_phasor_q<(MIX >> 3) & 1>(th);
+        const float s = ((MIX & 3) == 1) ? -w.y : w.y;
+        return cf(v.x * w.x - v.y * s, v.y * w.x + v.x * s);
+    }
+}
+
 // ---- top level: (mix) -> shared, in the consumer's de-interleaved layout ------------------------------------
 // A tile that lies inside the chunk at a 16-byte aligned address is "bulk": its raw samples are prefetched into
 // registers (fe_prefetch) while the previous tile is being filtered.
@@ -44,7 +56,7 @@ __device__ __forceinline__ bool fe_tile_is_bulk(const FrontendParams &p, const f
 {
     constexpr int NS = FeStd<S, V>::G.n[S];
     const long long rel0 = lo - p.n0;
-    return rel0 >= 0 && rel0 + NS <= p.nx && ((reinterpret_cast<uintptr_t>(xs + rel0) & 15) == 0);
+    return rel0 >= 0 && rel0 + NS <= p.nx && (V == 2 || (reinterpret_cast<uintptr_t>(xs + rel0) & 15) == 0);
 }
 
 template <int S, int V> struct FePrefetch {
@@ -116,20 +128,26 @@ __device__ __forceinline__ void fe_load_top(const FrontendParams &p, const float
 // ---- one half-band stage with compile-time geometry --------------------------------------------------------
 //   out[q] = C[q+M] + sum_{u<2M} g[u] * T[q+u+SH]     T/C = tap/centre planes (odd/even samples; swapped when the
 //   input level is shifted by one sample), R consecutive outputs per thread slot
-template <int M, int R, int STR, int SH, int NOUT, bool LAST, int D2, int STR2>
+//   MIX != 0 (variant 2, top stage only): the level holds RAW samples; every sample read is multiplied by the NCO
+//   phasor of its position first (thb = phase word of local sample 0, dth = phase step per sample).
+template <int M, int R, int STR, int SH, int NOUT, bool LAST, int D2, int STR2, int MIX = 0>
 __device__ __forceinline__ void fe_stage_c(const float2 *__restrict__ in, float2 *__restrict__ out,
-                                           const float *__restrict__ g, float zeta)
+                                           const float *__restrict__ g, float zeta, unsigned thb = 0, unsigned dth = 0)
 {
     const float2 *T = in + (SH ? 0 : R * STR);
     const float2 *C = in + (SH ? R * STR : 0);
     constexpr int NSLOTS = NOUT / R;
     for (int t = threadIdx.x; t < NSLOTS; t += 256) {
+        // tap plane element e <-> local sample 2 (R t + e) + (SH ? 0 : 1), centre plane the other parity
+        const unsigned ths = thb + (unsigned)(2 * R * t) * dth;
         float2 acc[R];
 #pragma unroll
-        for (int r = 0; r < R; r++) acc[r] = C[((M + r) % R) * STR + t + (M + r) / R];
+        for (int r = 0; r < R; r++)
+            acc[r] = fe_mix_q<MIX>(C[((M + r) % R) * STR + t + (M + r) / R], ths + (unsigned)(2 * (M + r) + (SH ? 1 : 0)) * dth);
 #pragma unroll
         for (int c = 0; c < R + 2 * M - 1; c++) {
-            const float2 v = T[((c + SH) % R) * STR + t + (c + SH) / R];
+            const float2 v = fe_mix_q<MIX>(T[((c + SH) % R) * STR + t + (c + SH) / R],
+                                           ths + (unsigned)(2 * (c + SH) + (SH ? 0 : 1)) * dth);
 #pragma unroll
             for (int r = 0; r < R; r++) {
                 const int u = c - r;
@@ -183,7 +201,12 @@ __device__ __forceinline__ long long fe_ceil_div(unsigned long long num, unsigne
     return q + (r != 0);
 }
 
-struct FeTileInfo { long long lo; int bulk, oA, oB, pad; };
+struct FeTileInfo {
+    long long lo; int bulk, oA, oB;
+    unsigned phA;     // timing phase of output oA relative to the tile's first push, in [0, step)
+    float fA;         // phA / 2^24
+    int pad;
+};
 
 // everything one tile needs that is not per-thread work: computed by ONE thread, one tile ahead
 template <int S, int V>
@@ -198,6 +221,63 @@ __device__ __forceinline__ void fe_tile_info(const FrontendParams &p, const floa
     const unsigned long long a = (unsigned long long)kArel << 24, b = (unsigned long long)kBrel << 24;
     ti.oA = (a > p.ph0) ? (int)fe_ceil_div(a - p.ph0, p.step, inv_st) : 0;
     ti.oB = (b > p.ph0) ? (int)fe_ceil_div(b - p.ph0, p.step, inv_st) : 0;
+    ti.phA = (unsigned)(p.ph0 + (unsigned long long)ti.oA * p.step - a);
+    ti.fA = (float)ti.phA * (1.0f / 16777216.0f);
+}
+
+// ---- arbitrary resampler over one tile (rate_arb < 1: every push emits at most one output) --------------------
+// One thread per PAIR of pushes: the 16 c-samples both windows need are fetched with eight conflict-free 16-byte
+// loads and stay in registers.  Output oA + j has timing phase phA + j*step relative to the tile, belongs to local
+// push (phase >> 24) and uses branch = the next `bits` phase bits.  The first j of a thread is estimated in fp32 and
+// corrected exactly in integers (no division).  BANK16: taps come from the 16-float rows of p.bank16 through L1
+// (four 16-byte loads per output), else from the padded copy of the bank in shared memory.
+template <int TC, bool BANK16>
+__device__ __forceinline__ void fe_resample_tile(const FrontendParams &p, const float2 *__restrict__ cb, float2 *__restrict__ ys,
+                                                 const FeTileInfo &ti, int npush, const float *__restrict__ bank_s, float rate_f)
+{
+    const unsigned mask = (1u << p.bits) - 1u;
+    const int sh = 24 - p.bits;
+    const unsigned phA = ti.phA;
+    const float fA = ti.fA;
+    float2 *yo = ys + ti.oA;
+    for (int t = threadIdx.x; t < TC / 2; t += 256) {
+        if (2 * t >= npush) break;
+        float2 w[16];                               // local indices 2t+2 .. 2t+17; push e ends at w[14 + e]
+        const float4 *src = reinterpret_cast<const float4 *>(cb + 2 * t + 2);
+#pragma unroll
+        for (int i = 0; i < 8; i++) { const float4 q = src[i]; w[2 * i] = cf(q.x, q.y); w[2 * i + 1] = cf(q.z, q.w); }
+        // first output at or after local push 2t
+        const unsigned long long target = (unsigned long long)(2 * t) << 24;
+        const float jf = ((float)(2 * t) - fA) * rate_f;
+        int j = jf > 0.f ? (int)jf : 0;
+        unsigned long long P = phA + (unsigned long long)(unsigned)j * p.step;
+        while (P < target) { j++; P += p.step; }
+        while (j > 0 && P - p.step >= target) { j--; P -= p.step; }
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+            if (2 * t + e < npush && (int)(P >> 24) == 2 * t + e) {
+                const unsigned br = ((unsigned)P >> sh) & mask;
+                float h[16];
+                if constexpr (BANK16) {
+                    const float4 *h4 = reinterpret_cast<const float4 *>(p.bank16) + br * 4;
+#pragma unroll
+                    for (int i = 0; i < 4; i++) { const float4 q = __ldg(h4 + i); h[4 * i] = q.x; h[4 * i + 1] = q.y; h[4 * i + 2] = q.z; h[4 * i + 3] = q.w; }
+                } else {
+                    const float *hr = bank_s + br * (kHsub + 1);
+#pragma unroll
+                    for (int i = 0; i < kHsub; i++) h[i] = hr[i];
+                }
+                float ar = 0.f, ai = 0.f;
+#pragma unroll
+                for (int jj = 0; jj < kHsub; jj++) {
+                    ar = fmaf(h[jj], w[14 + e - jj].x, ar);
+                    ai = fmaf(h[jj], w[14 + e - jj].y, ai);
+                }
+                yo[j] = cf(ar, ai);
+                j++; P += p.step;
+            }
+        }
+    }
 }
 
 template <int S, int V>
@@ -222,9 +302,8 @@ __global__ void __launch_bounds__(256, V ? 3 : 2) k_frontend_std(const CSDR_GRID
     const float2 *xs = p.x + (long long)blockIdx.y * p.x_stride;
     const float2 *hs = p.hist + (long long)blockIdx.y * p.hcap;
     float2 *ys = p.y + (long long)blockIdx.y * p.y_stride;
-    const unsigned mask = (unsigned)npfb - 1u;
-    const int sh = 24 - p.bits;
     const double inv_st = 1.0 / (double)p.step;
+    const float rate_f = 16777216.0f / (float)p.step;
     const int gstep = (int)gridDim.x;
 
     // Software pipeline over the tiles of this (persistent) CTA: the raw samples of tile i+1 are loaded into
@@ -271,42 +350,120 @@ __global__ void __launch_bounds__(256, V ? 3 : 2) k_frontend_std(const CSDR_GRID
 
         fe_run_stages<S, V, S - 1>(p, smem);
 
-        // arbitrary resampler (rate_arb < 1: every push emits at most one output).  One thread per PAIR of pushes:
-        // the 16 c-samples both windows need are fetched with eight conflict-free 16-byte loads and stay in registers;
-        // output o' has phase ph0 + o'*step, belongs to push (phase >> 24) and uses branch = next `bits` phase bits.
         {
-            const float2 *cb = smem + G.off[0];            // local index i <-> push (tile*Tc - kHcPad + i) relative to K0
-            const long long kArel = (long long)tile * G.Tc;
-            const int npush = (int)min((long long)G.Tc, p.K1 - p.K0 - kArel);
-            for (int t = threadIdx.x; t < G.Tc / 2; t += 256) {
-                if (2 * t >= npush) break;
-                float2 w[16];                               // local indices 2t+2 .. 2t+17; push e ends at w[14 + e]
-                const float4 *src = reinterpret_cast<const float4 *>(cb + 2 * t + 2);
-#pragma unroll
-                for (int i = 0; i < 8; i++) { const float4 q = src[i]; w[2 * i] = cf(q.x, q.y); w[2 * i + 1] = cf(q.z, q.w); }
-                const unsigned long long kk = (unsigned long long)(kArel + 2 * t);
-                const unsigned long long a = kk << 24;
-                long long o = (a > p.ph0) ? fe_ceil_div(a - p.ph0, p.step, inv_st) : 0;   // first output at or after push kk
-#pragma unroll
-                for (int e = 0; e < 2; e++) {
-                    const unsigned long long ph = p.ph0 + (unsigned long long)o * p.step;
-                    if (2 * t + e < npush && (ph >> 24) == kk + e) {
-                        const float *h = V ? p.bank + ((unsigned)(ph >> sh) & mask) * kHsub
-                                           : bank_s + ((unsigned)(ph >> sh) & mask) * (kHsub + 1);
-                        float ar = 0.f, ai = 0.f;
-#pragma unroll
-                        for (int j = 0; j < kHsub; j++) {
-                            const float hj = V ? __ldg(h + j) : h[j];
-                            ar = fmaf(hj, w[14 + e - j].x, ar);
-                            ai = fmaf(hj, w[14 + e - j].y, ai);
-                        }
-                        ys[o] = cf(ar, ai);
-                        o++;
-                    }
-                }
-            }
+            const int npush = (int)min((long long)G.Tc, p.K1 - p.K0 - (long long)tile * G.Tc);
+            fe_resample_tile<G.Tc, V != 0>(p, smem + G.off[0], ys, s_info[cur], npush, bank_s, rate_f);
         }
         __syncthreads();   // smem is reused by the next tile
+        cur = nxt;
+    }
+}
+
+// =============================================================================================================
+// Variant 2: no separate mixing pass.  The raw tile is copied asynchronously (cp.async, 8 bytes per thread and
+// instruction) from global memory straight into the top level's de-interleaved layout while the lower stages of the
+// previous tile run; the first half-band stage multiplies every sample it reads by the NCO phasor of its position.
+// One pass over shared memory and one barrier fewer per tile than variant 1, ~53 KB per CTA -> four CTAs per SM; the
+// price is that samples shared by neighbouring thread slots are mixed twice (21 phasors per 16 raw samples for m = 3).
+
+// lane l of warp w copies, per round k, sample 2 (16 (w + 8k) + (l & 15)) + (l >> 4): a warp reads 256 contiguous
+// bytes and each half-warp writes one plane of 16 consecutive pairs = 16 distinct 8-byte banks
+template <int S>
+__device__ __forceinline__ void fe_fill_top(const FrontendParams &p, const float2 *__restrict__ xs,
+                                            const float2 *__restrict__ hs, float2 *__restrict__ dst, long long lo, bool bulk)
+{
+    constexpr FeGeom G = FeStd<S, 2>::G;
+    constexpr int NS = G.n[S], STR = G.stride[S], D = G.R[S - 1], NP = NS / 2, IT = (NP + 127) / 128;
+    static_assert(D == 8 && NS % 2 == 0, "loader assumes an 8-way layout of the top level");
+    const int tid = threadIdx.x, w = tid >> 5, l = tid & 31;
+    const long long rel0 = lo - p.n0;
+    float2 *d0 = dst + ((l >> 4) * D + (l & 7)) * STR + 2 * w + ((l >> 3) & 1);
+    const int i0 = 32 * w + 2 * (l & 15) + (l >> 4), pr0 = 16 * w + (l & 15);
+    if (bulk) {
+        const float2 *src = xs + rel0 + i0;
+#pragma unroll
+        for (int k = 0; k < IT; k++)
+            if (pr0 + 128 * k < NP) async_copy8(d0 + 16 * k, src + 256 * k);
+    } else {
+        // edge tile: samples before the chunk come from the carried history, samples after it are zero
+        for (int k = 0; k < IT; k++) {
+            if (pr0 + 128 * k >= NP) break;
+            const long long rel = rel0 + i0 + 256 * k;
+            float2 v = cf(0.f, 0.f);
+            if (rel >= 0) { if (rel < p.nx) v = xs[rel]; }
+            else if (rel >= -(long long)p.hcap) v = hs[p.hcap + rel];
+            d0[16 * k] = v;
+        }
+    }
+}
+
+template <int S, int s, int MIX>
+__device__ __forceinline__ void fe_run_stage_v2(const FrontendParams &p, float2 *smem, unsigned thb)
+{
+    constexpr FeGeom G = FeStd<S, 2>::G;
+    constexpr bool LAST = (s == 0);
+    constexpr int D2 = LAST ? 1 : G.R[LAST ? 0 : s - 1];
+    constexpr int SH = (s == S - 1) ? G.shift : 0;
+    fe_stage_c<G.m[s], G.R[s], G.stride[s + 1], SH, G.n[s], LAST, D2, G.stride[s], MIX>(
+        smem + G.off[s + 1], smem + G.off[s], p.taps[s], p.zeta, thb, p.dtheta);
+}
+template <int S, int s>
+__device__ __forceinline__ void fe_run_lower_v2(const FrontendParams &p, float2 *smem)
+{
+    fe_run_stage_v2<S, s, 0>(p, smem, 0u);
+    __syncthreads();
+    if constexpr (s > 0) fe_run_lower_v2<S, s - 1>(p, smem);
+}
+
+template <int S>
+__global__ void __launch_bounds__(256, 4) k_frontend_v2(const CSDR_GRID_CONSTANT FrontendParams p)
+{
+    constexpr FeGeom G = FeStd<S, 2>::G;
+    static_assert(S >= 2, "variant 2 needs a half-band stage below the mixing one");
+    CSDR_DYN_SMEM(smem_raw);
+    float2 *smem = reinterpret_cast<float2 *>(smem_raw);
+    __shared__ FeTileInfo s_info[3];
+
+    const float2 *xs = p.x + (long long)blockIdx.y * p.x_stride;
+    const float2 *hs = p.hist + (long long)blockIdx.y * p.hcap;
+    float2 *ys = p.y + (long long)blockIdx.y * p.y_stride;
+    const double inv_st = 1.0 / (double)p.step;
+    const float rate_f = 16777216.0f / (float)p.step;
+    const int gstep = (int)gridDim.x;
+    float2 *top = smem + G.off[S];
+
+    if (threadIdx.x == 0) {
+        const int t0 = (int)blockIdx.x;
+        if (t0 < p.ntiles) fe_tile_info<S, 2>(p, xs, t0, inv_st, s_info[0]);
+        if (t0 + gstep < p.ntiles) fe_tile_info<S, 2>(p, xs, t0 + gstep, inv_st, s_info[1]);
+    }
+    __syncthreads();
+    if ((int)blockIdx.x < p.ntiles) fe_fill_top<S>(p, xs, hs, top, s_info[0].lo, s_info[0].bulk != 0);
+    async_copy_wait();
+    __syncthreads();
+
+    int cur = 0;
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gstep) {
+        const int nxt = cur == 2 ? 0 : cur + 1, nxt2 = nxt == 2 ? 0 : nxt + 1;
+        // phase word of the tile's local sample 0 (+ the table-rounding offset of the quantised NCO)
+        const unsigned thb = p.theta0 + (unsigned)s_info[cur].lo * p.dtheta + (p.quantize ? (1u << 21) : 0u);
+        if (p.mix_mode == 0)      fe_run_stage_v2<S, S - 1, 0>(p, smem, thb);
+        else if (p.quantize) { if (p.mix_mode == 1) fe_run_stage_v2<S, S - 1, 1 | 8>(p, smem, thb);
+                               else                 fe_run_stage_v2<S, S - 1, 2 | 8>(p, smem, thb); }
+        else                 { if (p.mix_mode == 1) fe_run_stage_v2<S, S - 1, 1>(p, smem, thb);
+                               else                 fe_run_stage_v2<S, S - 1, 2>(p, smem, thb); }
+        __syncthreads();
+        // the top level has been consumed: start copying the next tile of this CTA into it
+        if (tile + gstep < p.ntiles) fe_fill_top<S>(p, xs, hs, top, s_info[nxt].lo, s_info[nxt].bulk != 0);
+        if (threadIdx.x == 0 && tile + 2 * gstep < p.ntiles) fe_tile_info<S, 2>(p, xs, tile + 2 * gstep, inv_st, s_info[nxt2]);
+
+        fe_run_lower_v2<S, S - 2>(p, smem);
+        {
+            const int npush = (int)min((long long)G.Tc, p.K1 - p.K0 - (long long)tile * G.Tc);
+            fe_resample_tile<G.Tc, true>(p, smem + G.off[0], ys, s_info[cur], npush, nullptr, rate_f);
+        }
+        async_copy_wait();
+        __syncthreads();   // next tile's raw samples are in place; the lower levels may be overwritten
         cur = nxt;
     }
 }

@@ -26,6 +26,8 @@ namespace csdr {
 __device__ inline void bulk_init(unsigned long long *) {}
 __device__ inline void bulk_copy_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *) { memcpy(dst, src, bytes); }
 __device__ inline void bulk_wait(unsigned long long *, unsigned) {}
+__device__ inline void async_copy8(void *dst, const void *src) { memcpy(dst, src, 8); }
+__device__ inline void async_copy_wait() {}
 #else
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void bulk_init(unsigned long long *bar)
@@ -46,6 +48,17 @@ __device__ __forceinline__ void bulk_wait(unsigned long long *bar, unsigned pari
     asm volatile("{\n\t.reg .pred p;\n\tWAIT_%=:\n\t"
                  "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
                  "@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// ---- per-thread asynchronous 8-byte copy global -> shared (cp.async, SASS LDGSTS): no register staging, any
+// destination address, so a tile can be scattered straight into the consumer's de-interleaved layout
+__device__ __forceinline__ void async_copy8(void *dst, const void *src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+// every copy this thread issued has landed (a __syncthreads then publishes them to the CTA)
+__device__ __forceinline__ void async_copy_wait()
+{
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
 }
 #endif
 

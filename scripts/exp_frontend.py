@@ -6,7 +6,7 @@ import composable_sdr_b200 as cs
 from bench_configs import sig
 n = 1 << 27
 x = sig(n, 1)
-for variant in (0, 1):
+for variant in (0, 1, 2):
     cs.set_option(9, variant)
     ch = cs.Chain(2.56e6, 1e5, 200e3)
     cap = ch.max_output(n)
@@ -20,4 +20,4 @@ for variant in (0, 1):
     print(f"variant {variant}: k_frontend {ms / k * 1e3:.1f} us per 2^27 samples -> {n / (ms / k) / 1e6:.1f} GS/s, "
           f"{8.3125 * n / (ms / k * 1e-3) / 1e9 / 6540.2:.3f} of measured HBM roofline", flush=True)
     ch.close()
-cs.set_option(9, 1)
+cs.set_option(9, 2)

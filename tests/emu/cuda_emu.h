@@ -103,6 +103,7 @@ static inline float __fmaf_rn(float a, float b, float c) { return fmaf(a, b, c);
 static inline float __int2float_rn(int x) { return (float)x; }
 static inline float __uint2float_rn(unsigned x) { return (float)x; }
 static inline int __float_as_int(float f) { int i; memcpy(&i, &f, 4); return i; }
+static inline float __uint_as_float(unsigned i) { float f; memcpy(&f, &i, 4); return f; }
 static inline float __int_as_float(int i) { float f; memcpy(&f, &i, 4); return f; }
 static inline unsigned __brev(unsigned v) { unsigned r = 0; for (int i = 0; i < 32; i++) if (v & (1u << i)) r |= 1u << (31 - i); return r; }
 template <class T> static inline T __ldg(const T *p) { return *p; }

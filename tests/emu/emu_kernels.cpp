@@ -25,7 +25,7 @@ long long emu_frontend(float rate, float As, int mix_mode, float freq, int quant
                        unsigned long long seek, int allow_std, long long misalign)
 {
     design::MsresampPlan ms = design::plan_msresamp(rate, As);
-    FrontendGeometry g = plan_frontend(ms, Tc, allow_std != 0, allow_std == 2 ? 1 : 0);
+    FrontendGeometry g = plan_frontend(ms, Tc, allow_std != 0, allow_std >= 2 ? allow_std - 1 : 0);
     void (*kernel)(FrontendParams) = k_frontend;
     if (g.std_kernel) {
         nthreads = 256;
@@ -37,6 +37,14 @@ long long emu_frontend(float rate, float As, int mix_mode, float freq, int quant
             case 4: kernel = k_frontend_std<4, 0>; break;
             case 5: kernel = k_frontend_std<5, 0>; break;
             default: kernel = k_frontend_std<6, 0>; break;
+            }
+        } else if (g.variant == 2) {
+            switch (ms.S) {
+            case 2: kernel = k_frontend_v2<2>; break;
+            case 3: kernel = k_frontend_v2<3>; break;
+            case 4: kernel = k_frontend_v2<4>; break;
+            case 5: kernel = k_frontend_v2<5>; break;
+            default: kernel = k_frontend_v2<6>; break;
             }
         } else {
             switch (ms.S) {
@@ -68,6 +76,9 @@ long long emu_frontend(float rate, float As, int mix_mode, float freq, int quant
         p.x_stride = 0; p.y_stride = 0;
         p.mix_mode = mix_mode; p.theta0 = 0; p.dtheta = design::nco_constrain(freq); p.quantize = quantize;
         p.bank = ms.bank.data();
+        std::vector<float> b16(ms.bank.size() / kHsub * 16, 0.f);
+        for (size_t r = 0; r < ms.bank.size() / kHsub; r++) for (int j = 0; j < kHsub; j++) b16[r * 16 + j] = ms.bank[r * kHsub + j];
+        p.bank16 = b16.data();
         if (p.ntiles > 0)
             csdr_emu::launch(dim3(std::min(p.ntiles, 3)), dim3(nthreads), g.smem_bytes, kernel, p);
         csdr_emu::launch(dim3((g.hcap + 127) / 128), dim3(128), 0, k_hist_update, (const float2 *)hist[cur_h].data(),

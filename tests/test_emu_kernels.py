@@ -14,7 +14,10 @@ from util import assert_parity, make_signal
     (0.3, 60.0, 0, 256, 1, True), (0.2, 60.0, 0, 256, 2, True), (0.078125, 60.0, 0, 256, 1, True),
     (0.04, 60.0, 0, 256, 0, True), (0.02, 60.0, 0, 256, 1, True), (0.011, 60.0, 0, 256, 1, True),
     # TMA-staged variant k_frontend_std<S, 1>, S = 1..4
-    (0.3, 60.0, 0, 256, 1, 2), (0.2, 60.0, 0, 256, 0, 2), (0.078125, 60.0, 0, 256, 1, 2), (0.04, 60.0, 0, 256, 2, 2)])
+    (0.3, 60.0, 0, 256, 1, 2), (0.2, 60.0, 0, 256, 0, 2), (0.078125, 60.0, 0, 256, 1, 2), (0.04, 60.0, 0, 256, 2, 2),
+    # fused-mix variant k_frontend_v2<S>, S = 2..6
+    (0.2, 60.0, 0, 256, 1, 3), (0.078125, 60.0, 0, 256, 1, 3), (0.078125, 60.0, 0, 256, 0, 3), (0.04, 60.0, 0, 256, 2, 3),
+    (0.02, 60.0, 0, 256, 1, 3), (0.011, 60.0, 0, 256, 2, 3)])
 def test_frontend_matches_oracle(orc, emu, rate, As, Tc, nthreads, mix, std):
     x = make_signal(40000, 7)
     f = float(np.float32(0.24543693))
