@@ -144,7 +144,7 @@ struct Frontend {
     FrontendCursor cursor;
     int mix_mode = 0; uint32_t theta0 = 0, dtheta = 0; int quantize = 1;
     void (*kernel)(FrontendParams) = k_frontend;
-    int ctas_per_sm = 2;
+    int ctas_per_sm = 2, fe_threads = 256;
     // optional event timing of k_frontend (bench roofline): pairs recorded on the launching stream
     bool profile = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pending, ev_free;
@@ -189,6 +189,16 @@ struct Frontend {
             case 6: kernel = k_frontend_std<6, 0>; break;
             default: throw CudaError{"frontend: no specialised kernel for this stage count"};
             }
+        } else if (geo.std_kernel && geo.variant == 3) {
+            switch (ms.S) {
+            case 1: kernel = k_frontend_v3<1>; break;
+            case 2: kernel = k_frontend_v3<2>; break;
+            case 3: kernel = k_frontend_v3<3>; break;
+            case 4: kernel = k_frontend_v3<4>; break;
+            case 5: kernel = k_frontend_v3<5>; break;
+            case 6: kernel = k_frontend_v3<6>; break;
+            default: throw CudaError{"frontend: no direct-read kernel for this stage count"};
+            }
         } else if (geo.std_kernel && geo.variant == 2) {
             switch (ms.S) {
             case 2: kernel = k_frontend_v2<2>; break;
@@ -221,7 +231,8 @@ struct Frontend {
             c.sync();      // b16 goes out of scope
         }
         CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)geo.smem_bytes));
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kernel, 256, geo.smem_bytes));
+        fe_threads = geo.std_kernel ? kFeNT : 256;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kernel, fe_threads, geo.smem_bytes));
         if (ctas_per_sm < 1) throw CudaError{"frontend: tile does not fit in shared memory"};
         c.sync();
     }
@@ -250,7 +261,7 @@ struct Frontend {
                 else { CK(cudaEventCreate(&ev.first)); CK(cudaEventCreate(&ev.second)); }
                 CK(cudaEventRecord(ev.first, c.stream));
             }
-            launch(kernel, dim3(gx, nstreams), dim3(256), geo.smem_bytes, c.stream, p);
+            launch(kernel, dim3(gx, nstreams), dim3(fe_threads), geo.smem_bytes, c.stream, p);
             if (profile) { CK(cudaEventRecord(ev.second, c.stream)); ev_pending.push_back(ev); }
         }
         if (nx > 0) {

@@ -66,18 +66,19 @@ struct FrontendParams {
     int smem_bytes;
 };
 
-// address of sample i in a level buffer with layout factor D (power of two) and sub-array stride
+// address of sample i in a level buffer with layout factor D (power of two) and sub-array stride: plane i & 1
+// (planes are D * stride + kFePlanePad apart), pair p = i >> 1 -> sub-array p & (D-1), index p / D
 template <int D>
 __device__ __forceinline__ int fe_addr(int i, int stride)
 {
     int p = i >> 1;
-    return ((i & 1) * D + (p & (D - 1))) * stride + (p / D);
+    return (i & 1) * (D * stride + kFePlanePad) + (p & (D - 1)) * stride + (p / D);
 }
 __device__ __forceinline__ int fe_addr_rt(int i, int D, int stride)
 {
     const int p = i >> 1;
     const int lg = (D == 8) ? 3 : (D == 4) ? 2 : (D == 2) ? 1 : 0;      // D is 1, 2, 4 or 8
-    return ((i & 1) * D + (p & (D - 1))) * stride + (p >> lg);
+    return (i & 1) * (D * stride + kFePlanePad) + (p & (D - 1)) * stride + (p >> lg);
 }
 
 // Phasor with the quantisation mode known at compile time.  The phase index is turned into a float by bit insertion
@@ -117,7 +118,7 @@ __device__ __forceinline__ void fe_stage(const float2 *__restrict__ in, int stri
 #pragma unroll
     for (int u = 0; u < 2 * M; u++) g[u] = g_taps[u];
     const float2 *E = in;
-    const float2 *O = in + R * stride;
+    const float2 *O = in + R * stride + kFePlanePad;
     const int nslots = n_out / R;
     for (int t = threadIdx.x; t < nslots; t += blockDim.x) {
         float ar[R], ai[R];

@@ -12,6 +12,11 @@
 
 namespace csdr {
 
+#ifndef CSDR_FE_NT
+#define CSDR_FE_NT 256
+#endif
+constexpr int kFeNT = CSDR_FE_NT;   // threads per CTA of the compile-time-geometry kernels
+
 struct FeGeom {
     int S = 0, Tc = 0, shift = 0;
     int m[kMaxStages] = {}, R[kMaxStages] = {};
@@ -36,25 +41,36 @@ __host__ __device__ constexpr FeGeom fe_make_geom(int S, int Tc, const int *m, i
     // more threads busy but re-read shared memory more often, and shared-memory bandwidth is what binds this kernel
     // (measured: slots 8/4/2 -> 236 us, 8/8/4 -> 227 us per 2^26 samples).
     for (int s = 0; s < S; s++) { g.m[s] = m[s]; g.R[s] = (s == 0 && S > 1) ? 4 : 8; }
+    // raw = 3: the top level is the raw tile itself, linear, as the bulk copy delivers it; the first half-band stage
+    // reads (even, odd) pairs from it with 16-byte loads, kFeTopR outputs per thread slot (odd: conflict-free)
+    const int direct = (raw == 3 && S > 0) ? 1 : 0;
+    if (direct) g.R[S - 1] = kFeTopR;
     g.n[0] = Tc + kHcPad; g.d[0] = 0;
     for (int L = 0; L < S; L++) {
         const int sh = (L + 1 == S) ? g.shift : 0;
         const int need = 2 * g.n[L] + 4 * g.m[L] - 2 + sh;
         int mult = 2 * g.R[L];
-        if (L + 1 < S) mult = ce_max(mult, g.R[L + 1]);
+        if (L + 1 < S && !(direct && L + 2 == S)) mult = ce_max(mult, g.R[L + 1]);
+        if (direct && L + 1 == S) mult = 2;
         g.n[L + 1] = ce_roundup(need, mult);
         g.d[L + 1] = 2 * g.d[L] + 1 - 4 * g.m[L] - sh;
     }
     // raw = 2: the top level has a buffer of its own (the next tile is copied into it while the lower stages of the
     // current tile run); the lower levels ping-pong between two regions as before
-    const int priv = (raw == 2 && S > 0) ? 1 : 0;
+    const int priv = ((raw == 2 || raw == 3) && S > 0) ? 1 : 0;
     int sizeA = 0, sizeB = 0, sizeT = 0;
     for (int L = 1; L <= S; L++) {
+        if (direct && L == S) {
+            // the last slot may run past n[S-1] outputs; its reads stay inside the buffer
+            const int slots = (g.n[S - 1] + kFeTopR - 1) / kFeTopR;
+            sizeT = ce_roundup(ce_max(g.n[S], 2 * (kFeTopR * slots + 2 * g.m[S - 1] + 1)), 2) + 2;
+            continue;
+        }
         const int D = g.R[L - 1];
         int st = g.n[L] / (2 * D) + 1;
         while ((st & 15) != 2) st++;
         g.stride[L] = st;
-        const int sz = 2 * D * st;
+        const int sz = ce_roundup(2 * D * st + kFePlanePad, 2);
         if (priv && L == S) sizeT = sz;
         else if (((S - L) & 1) == 0) sizeA = ce_max(sizeA, sz); else sizeB = ce_max(sizeB, sz);
     }
@@ -86,10 +102,16 @@ __host__ __device__ constexpr int fe_std_tc_v2(int S)
 {
     return S == 2 ? 768 : S == 3 ? 384 : S == 4 ? 176 : S == 5 ? 64 : 32;
 }
+// variant 3: bulk copy (TMA) into a linear staging buffer that IS the top level; the first stage reads pairs from it
+// and mixes in registers; the polyphase bank lives in shared memory; three CTAs per SM
+__host__ __device__ constexpr int fe_std_tc_v3(int S)
+{
+    return S == 1 ? 1536 : S == 2 ? 768 : S == 3 ? 384 : S == 4 ? 192 : S == 5 ? 64 : 32;
+}
 __host__ __device__ constexpr FeGeom fe_make_geom_std(int S, int variant = 0)
 {
     FeStdM mm{};
-    return variant == 2 ? fe_make_geom(S, fe_std_tc_v2(S), mm.v, 1, 2)
+    return variant == 3 ? fe_make_geom(S, fe_std_tc_v3(S), mm.v, 1, 3) : variant == 2 ? fe_make_geom(S, fe_std_tc_v2(S), mm.v, 1, 2)
          : variant == 1 ? fe_make_geom(S, fe_std_tc_tma(S), mm.v, 1, 1) : fe_make_geom(S, fe_std_tc(S), mm.v, 1, 0);
 }
 constexpr int kFeStdMaxS = 6;      // k_frontend_std<S, 0> is instantiated for S = 1..6

@@ -25,6 +25,20 @@ __device__ __forceinline__ float4 fe_ldg_stream(const float4 *p)
 #endif
 }
 
+// 16-byte read-only load that asks L1 to keep the line (the polyphase bank is re-read by every tile while the raw
+// samples stream through the same cache)
+__device__ __forceinline__ float4 fe_ldg_keep(const float4 *p)
+{
+#ifdef CSDR_EMU
+    return *p;
+#else
+    float4 v;
+    asm volatile("ld.global.nc.L1::evict_last.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+#endif
+}
+
 // v * conj(phasor) (down) or v * phasor (up)
 template <int MIX>
 __device__ __forceinline__ float2 fe_mix(float2 v, unsigned th, int quantize)
@@ -60,7 +74,7 @@ __device__ __forceinline__ bool fe_tile_is_bulk(const FrontendParams &p, const f
 }
 
 template <int S, int V> struct FePrefetch {
-    static constexpr int NP = FeStd<S, V>::G.n[S] / 2, IT = (NP + 255) / 256;
+    static constexpr int NP = FeStd<S, V>::G.n[S] / 2, IT = (NP + kFeNT - 1) / kFeNT;
     float4 v[V ? 1 : IT];          // variant 1 stages through shared memory instead
 };
 
@@ -72,7 +86,7 @@ __device__ __forceinline__ void fe_prefetch(FePrefetch<S, 0> &pre, const Fronten
     const float4 *src = reinterpret_cast<const float4 *>(xs + (lo - p.n0));
 #pragma unroll
     for (int k = 0; k < FePrefetch<S, 0>::IT; k++) {
-        const int pi = threadIdx.x + 256 * k;
+        const int pi = threadIdx.x + kFeNT * k;
         if (pi < FePrefetch<S, 0>::NP) pre.v[k] = fe_ldg_stream(src + pi);
     }
 }
@@ -92,30 +106,30 @@ __device__ __forceinline__ void fe_load_top(const FrontendParams &p, const float
     if (bulk) {
         // one 16-byte load = the (even, odd) pair p; pair -> sub-array p & 7, index p >> 3
         float2 *dE = dst + (tid & 7) * STR + (tid >> 3);
-        float2 *dO = dE + D * STR;
+        float2 *dO = dE + D * STR + kFePlanePad;
 #pragma unroll
         for (int k = 0; k < FePrefetch<S, V>::IT; k++) {
-            const int pi = tid + 256 * k;
+            const int pi = tid + kFeNT * k;
             if (pi < FePrefetch<S, V>::NP) {
                 const float4 v = V ? reinterpret_cast<const float4 *>(raw)[pi] : pre.v[V ? 0 : k];
                 const unsigned th = th0 + (unsigned)(2 * pi) * p.dtheta;
-                dE[32 * k] = fe_mix<MIX>(cf(v.x, v.y), th, p.quantize);
-                dO[32 * k] = fe_mix<MIX>(cf(v.z, v.w), th + p.dtheta, p.quantize);
+                dE[(kFeNT / 8) * k] = fe_mix<MIX>(cf(v.x, v.y), th, p.quantize);
+                dO[(kFeNT / 8) * k] = fe_mix<MIX>(cf(v.z, v.w), th + p.dtheta, p.quantize);
             }
         }
     } else if (inside) {
         // chunk not 16-byte aligned at this tile: 8-byte global loads, sample i -> plane i & 1, pair i >> 1
         const float2 *src = xs + rel0;
-        float2 *d0 = dst + ((tid & 1) * D + ((tid >> 1) & 7)) * STR + (tid >> 4);
-        constexpr int IT = (NS + 255) / 256;
+        float2 *d0 = dst + (tid & 1) * (D * STR + kFePlanePad) + ((tid >> 1) & 7) * STR + (tid >> 4);
+        constexpr int IT = (NS + kFeNT - 1) / kFeNT;
 #pragma unroll 4
         for (int k = 0; k < IT; k++) {
-            const int i = tid + 256 * k;
-            if (i < NS) d0[16 * k] = fe_mix<MIX>(src[i], th0 + (unsigned)i * p.dtheta, p.quantize);
+            const int i = tid + kFeNT * k;
+            if (i < NS) d0[(kFeNT / 16) * k] = fe_mix<MIX>(src[i], th0 + (unsigned)i * p.dtheta, p.quantize);
         }
     } else {
         // edge tile: samples before the chunk come from the carried history, samples after it are zero
-        for (int i = tid; i < NS; i += 256) {
+        for (int i = tid; i < NS; i += kFeNT) {
             const long long rel = rel0 + i;
             float2 v = cf(0.f, 0.f);
             if (rel >= 0) { if (rel < p.nx) v = xs[rel]; }
@@ -134,10 +148,10 @@ template <int M, int R, int STR, int SH, int NOUT, bool LAST, int D2, int STR2, 
 __device__ __forceinline__ void fe_stage_c(const float2 *__restrict__ in, float2 *__restrict__ out,
                                            const float *__restrict__ g, float zeta, unsigned thb = 0, unsigned dth = 0)
 {
-    const float2 *T = in + (SH ? 0 : R * STR);
-    const float2 *C = in + (SH ? R * STR : 0);
+    const float2 *T = in + (SH ? 0 : R * STR + kFePlanePad);
+    const float2 *C = in + (SH ? R * STR + kFePlanePad : 0);
     constexpr int NSLOTS = NOUT / R;
-    for (int t = threadIdx.x; t < NSLOTS; t += 256) {
+    for (int t = threadIdx.x; t < NSLOTS; t += kFeNT) {
         // tap plane element e <-> local sample 2 (R t + e) + (SH ? 0 : 1), centre plane the other parity
         const unsigned ths = thb + (unsigned)(2 * R * t) * dth;
         float2 acc[R];
@@ -166,13 +180,13 @@ __device__ __forceinline__ void fe_stage_c(const float2 *__restrict__ in, float2
                 // sub-array = (r >> 1) & (D2-1) for every t, index = (H / D2) t + (r >> 1) / D2
                 float2 *o = out + t * (H / D2);
 #pragma unroll
-                for (int r = 0; r < R; r++) o[((r & 1) * D2 + ((r >> 1) & (D2 - 1))) * STR2 + (r >> 1) / D2] = acc[r];
+                for (int r = 0; r < R; r++) o[(r & 1) * (D2 * STR2 + kFePlanePad) + ((r >> 1) & (D2 - 1)) * STR2 + (r >> 1) / D2] = acc[r];
             } else {
                 // K = D2 / H slots share one index: sub-array = H (t & (K-1)) + (r >> 1), index = t / K
                 constexpr int K = D2 / H;
                 float2 *o = out + (H * (t & (K - 1))) * STR2 + t / K;
 #pragma unroll
-                for (int r = 0; r < R; r++) o[((r & 1) * D2 + (r >> 1)) * STR2] = acc[r];
+                for (int r = 0; r < R; r++) o[(r & 1) * (D2 * STR2 + kFePlanePad) + (r >> 1) * STR2] = acc[r];
             }
         }
     }
@@ -240,7 +254,7 @@ __device__ __forceinline__ void fe_resample_tile(const FrontendParams &p, const 
     const unsigned phA = ti.phA;
     const float fA = ti.fA;
     float2 *yo = ys + ti.oA;
-    for (int t = threadIdx.x; t < TC / 2; t += 256) {
+    for (int t = threadIdx.x; t < TC / 2; t += kFeNT) {
         if (2 * t >= npush) break;
         float2 w[16];                               // local indices 2t+2 .. 2t+17; push e ends at w[14 + e]
         const float4 *src = reinterpret_cast<const float4 *>(cb + 2 * t + 2);
@@ -261,7 +275,7 @@ __device__ __forceinline__ void fe_resample_tile(const FrontendParams &p, const 
                 if constexpr (BANK16) {
                     const float4 *h4 = reinterpret_cast<const float4 *>(p.bank16) + br * 4;
 #pragma unroll
-                    for (int i = 0; i < 4; i++) { const float4 q = __ldg(h4 + i); h[4 * i] = q.x; h[4 * i + 1] = q.y; h[4 * i + 2] = q.z; h[4 * i + 3] = q.w; }
+                    for (int i = 0; i < 4; i++) { const float4 q = fe_ldg_keep(h4 + i); h[4 * i] = q.x; h[4 * i + 1] = q.y; h[4 * i + 2] = q.z; h[4 * i + 3] = q.w; }
                 } else {
                     const float *hr = bank_s + br * (kHsub + 1);
 #pragma unroll
@@ -281,7 +295,7 @@ __device__ __forceinline__ void fe_resample_tile(const FrontendParams &p, const 
 }
 
 template <int S, int V>
-__global__ void __launch_bounds__(256, V ? 3 : 2) k_frontend_std(const CSDR_GRID_CONSTANT FrontendParams p)
+__global__ void __launch_bounds__(kFeNT, V ? 3 : 2) k_frontend_std(const CSDR_GRID_CONSTANT FrontendParams p)
 {
     constexpr FeGeom G = FeStd<S, V>::G;
     constexpr int NS = G.n[S];
@@ -294,7 +308,7 @@ __global__ void __launch_bounds__(256, V ? 3 : 2) k_frontend_std(const CSDR_GRID
 
     const int npfb = 1 << p.bits;
     if (!V) {
-        for (int i = threadIdx.x; i < npfb * kHsub; i += 256) {
+        for (int i = threadIdx.x; i < npfb * kHsub; i += kFeNT) {
             const int row = i / kHsub, col = i - row * kHsub;
             bank_s[row * (kHsub + 1) + col] = p.bank[i];
         }
@@ -366,33 +380,33 @@ __global__ void __launch_bounds__(256, V ? 3 : 2) k_frontend_std(const CSDR_GRID
 // One pass over shared memory and one barrier fewer per tile than variant 1, ~53 KB per CTA -> four CTAs per SM; the
 // price is that samples shared by neighbouring thread slots are mixed twice (21 phasors per 16 raw samples for m = 3).
 
-// lane l of warp w copies, per round k, sample 2 (16 (w + 8k) + (l & 15)) + (l >> 4): a warp reads 256 contiguous
-// bytes and each half-warp writes one plane of 16 consecutive pairs = 16 distinct 8-byte banks
+// thread tid copies, per round k, sample tid + NT k -> plane tid & 1, pair (tid >> 1) + (NT/2) k: a warp reads 256
+// contiguous bytes, and the 16 samples of every 128-byte line land in 16 distinct 8-byte banks (the one-element pad
+// between the planes shifts the odd plane by one bank)
 template <int S>
 __device__ __forceinline__ void fe_fill_top(const FrontendParams &p, const float2 *__restrict__ xs,
                                             const float2 *__restrict__ hs, float2 *__restrict__ dst, long long lo, bool bulk)
 {
     constexpr FeGeom G = FeStd<S, 2>::G;
-    constexpr int NS = G.n[S], STR = G.stride[S], D = G.R[S - 1], NP = NS / 2, IT = (NP + 127) / 128;
+    constexpr int NS = G.n[S], STR = G.stride[S], D = G.R[S - 1], IT = (NS + kFeNT - 1) / kFeNT;
     static_assert(D == 8 && NS % 2 == 0, "loader assumes an 8-way layout of the top level");
-    const int tid = threadIdx.x, w = tid >> 5, l = tid & 31;
+    const int tid = threadIdx.x;
     const long long rel0 = lo - p.n0;
-    float2 *d0 = dst + ((l >> 4) * D + (l & 7)) * STR + 2 * w + ((l >> 3) & 1);
-    const int i0 = 32 * w + 2 * (l & 15) + (l >> 4), pr0 = 16 * w + (l & 15);
+    float2 *d0 = dst + (tid & 1) * (D * STR + kFePlanePad) + ((tid >> 1) & 7) * STR + (tid >> 4);
     if (bulk) {
-        const float2 *src = xs + rel0 + i0;
+        const float2 *src = xs + rel0 + tid;
 #pragma unroll
         for (int k = 0; k < IT; k++)
-            if (pr0 + 128 * k < NP) async_copy8(d0 + 16 * k, src + 256 * k);
+            if (tid + kFeNT * k < NS) async_copy8(d0 + (kFeNT / 16) * k, src + kFeNT * k);
     } else {
         // edge tile: samples before the chunk come from the carried history, samples after it are zero
         for (int k = 0; k < IT; k++) {
-            if (pr0 + 128 * k >= NP) break;
-            const long long rel = rel0 + i0 + 256 * k;
+            if (tid + kFeNT * k >= NS) break;
+            const long long rel = rel0 + tid + kFeNT * k;
             float2 v = cf(0.f, 0.f);
             if (rel >= 0) { if (rel < p.nx) v = xs[rel]; }
             else if (rel >= -(long long)p.hcap) v = hs[p.hcap + rel];
-            d0[16 * k] = v;
+            d0[(kFeNT / 16) * k] = v;
         }
     }
 }
@@ -416,7 +430,7 @@ __device__ __forceinline__ void fe_run_lower_v2(const FrontendParams &p, float2 
 }
 
 template <int S>
-__global__ void __launch_bounds__(256, 4) k_frontend_v2(const CSDR_GRID_CONSTANT FrontendParams p)
+__global__ void __launch_bounds__(kFeNT, 4) k_frontend_v2(const CSDR_GRID_CONSTANT FrontendParams p)
 {
     constexpr FeGeom G = FeStd<S, 2>::G;
     static_assert(S >= 2, "variant 2 needs a half-band stage below the mixing one");
@@ -447,6 +461,11 @@ __global__ void __launch_bounds__(256, 4) k_frontend_v2(const CSDR_GRID_CONSTANT
         const int nxt = cur == 2 ? 0 : cur + 1, nxt2 = nxt == 2 ? 0 : nxt + 1;
         // phase word of the tile's local sample 0 (+ the table-rounding offset of the quantised NCO)
         const unsigned thb = p.theta0 + (unsigned)s_info[cur].lo * p.dtheta + (p.quantize ? (1u << 21) : 0u);
+#ifdef CSDR_FE_SKIP
+        if (CSDR_FE_SKIP & 2) {}
+        else if (CSDR_FE_SKIP & 1) fe_run_stage_v2<S, S - 1, 0>(p, smem, thb);
+        else
+#endif
         if (p.mix_mode == 0)      fe_run_stage_v2<S, S - 1, 0>(p, smem, thb);
         else if (p.quantize) { if (p.mix_mode == 1) fe_run_stage_v2<S, S - 1, 1 | 8>(p, smem, thb);
                                else                 fe_run_stage_v2<S, S - 1, 2 | 8>(p, smem, thb); }
@@ -454,16 +473,176 @@ __global__ void __launch_bounds__(256, 4) k_frontend_v2(const CSDR_GRID_CONSTANT
                                else                 fe_run_stage_v2<S, S - 1, 2>(p, smem, thb); }
         __syncthreads();
         // the top level has been consumed: start copying the next tile of this CTA into it
+#ifdef CSDR_FE_SKIP
+        if (!(CSDR_FE_SKIP & 16))
+#endif
         if (tile + gstep < p.ntiles) fe_fill_top<S>(p, xs, hs, top, s_info[nxt].lo, s_info[nxt].bulk != 0);
         if (threadIdx.x == 0 && tile + 2 * gstep < p.ntiles) fe_tile_info<S, 2>(p, xs, tile + 2 * gstep, inv_st, s_info[nxt2]);
 
+#ifdef CSDR_FE_SKIP
+        if (!(CSDR_FE_SKIP & 4))
+#endif
         fe_run_lower_v2<S, S - 2>(p, smem);
+#ifdef CSDR_FE_SKIP
+        if (!(CSDR_FE_SKIP & 8))
+#endif
         {
             const int npush = (int)min((long long)G.Tc, p.K1 - p.K0 - (long long)tile * G.Tc);
             fe_resample_tile<G.Tc, true>(p, smem + G.off[0], ys, s_info[cur], npush, nullptr, rate_f);
         }
         async_copy_wait();
         __syncthreads();   // next tile's raw samples are in place; the lower levels may be overwritten
+        cur = nxt;
+    }
+}
+
+// =============================================================================================================
+// Variant 3: the raw tile is bulk-copied (TMA) into a linear staging buffer and the first half-band stage reads it
+// there: one 16-byte load fetches the (even, odd) pair -- the even sample is a tap input, the odd one a centre input
+// (the top level starts one sample early, shift = 1) -- and both are multiplied by the NCO phasor in registers.
+// kFeTopR = 7 outputs per thread slot: consecutive slots start 7 pairs apart, so the eight lanes of a quarter-warp
+// hit eight different 16-byte banks.  No mixing pass, no de-interleaving pass, no LSU work for the copy; the lower
+// stages and the resampler are the ones of variant 0 (bank in shared memory).
+template <int M, int NOUT, bool LAST, int D2, int STR2, int MIX>
+__device__ __forceinline__ void fe_stage_top(const float2 *__restrict__ raw, float2 *__restrict__ out,
+                                             const float *__restrict__ g, float zeta, unsigned thb, unsigned dth)
+{
+    constexpr int R = kFeTopR, NSLOTS = (NOUT + R - 1) / R, NC = R + 2 * M - 1;
+    for (int t = threadIdx.x; t < NSLOTS; t += kFeNT) {
+        // output q = R t + r:  centre = odd sample of pair q + M, tap u = even sample of pair q + u + 1
+        const float4 *src = reinterpret_cast<const float4 *>(raw) + (R * t + 1);
+        const unsigned ths = thb + (unsigned)(2 * (R * t + 1)) * dth;
+        float2 acc[R];
+#pragma unroll
+        for (int r = 0; r < R; r++) acc[r] = cf(0.f, 0.f);
+#pragma unroll
+        for (int c = 0; c < NC; c++) {
+            const float4 pr = src[c];
+            const float2 v = fe_mix_q<MIX>(cf(pr.x, pr.y), ths + (unsigned)(2 * c) * dth);
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                const int u = c - r;
+                if (u >= 0 && u < 2 * M) ffma2(acc[r], g[u], v);
+            }
+            if (c >= M - 1 && c < M - 1 + R) {
+                const float2 e = fe_mix_q<MIX>(cf(pr.z, pr.w), ths + (unsigned)(2 * c + 1) * dth);
+                acc[c - (M - 1)].x += e.x; acc[c - (M - 1)].y += e.y;
+            }
+        }
+        const int q0 = R * t;
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            const int q = q0 + r;
+            if (q < NOUT) {
+                if constexpr (LAST) out[q] = cf(acc[r].x * zeta, acc[r].y * zeta);
+                else out[(q & 1) * (D2 * STR2 + kFePlanePad) + ((q >> 1) & (D2 - 1)) * STR2 + (q >> 1) / D2] = acc[r];
+            }
+        }
+    }
+}
+
+template <int S, int MIX>
+__device__ __forceinline__ void fe_run_top_v3(const FrontendParams &p, float2 *smem, unsigned thb)
+{
+    constexpr FeGeom G = FeStd<S, 3>::G;
+    constexpr bool LAST = (S == 1);
+    constexpr int D2 = LAST ? 1 : G.R[LAST ? 0 : S - 2];
+    static_assert(G.shift == 1, "pairs are (tap, centre) only when the top level starts one sample early");
+    fe_stage_top<G.m[S - 1], G.n[S - 1], LAST, D2, G.stride[S - 1], MIX>(smem + G.off[S], smem + G.off[S - 1],
+                                                                          p.taps[S - 1], p.zeta, thb, p.dtheta);
+}
+template <int S, int s>
+__device__ __forceinline__ void fe_run_lower_v3(const FrontendParams &p, float2 *smem)
+{
+    constexpr FeGeom G = FeStd<S, 3>::G;
+    constexpr bool LAST = (s == 0);
+    constexpr int D2 = LAST ? 1 : G.R[LAST ? 0 : s - 1];
+    fe_stage_c<G.m[s], G.R[s], G.stride[s + 1], 0, G.n[s], LAST, D2, G.stride[s]>(
+        smem + G.off[s + 1], smem + G.off[s], p.taps[s], p.zeta);
+    __syncthreads();
+    if constexpr (s > 0) fe_run_lower_v3<S, s - 1>(p, smem);
+}
+
+// staging[i] = raw sample lo + i for a tile the bulk copy cannot fetch (it reaches into the carried history, past
+// the end of the chunk, or the chunk is not 16-byte aligned there)
+template <int S>
+__device__ __forceinline__ void fe_fill_staging(const FrontendParams &p, const float2 *__restrict__ xs,
+                                                const float2 *__restrict__ hs, float2 *__restrict__ raw, long long lo)
+{
+    constexpr int NS = FeStd<S, 3>::G.n[S];
+    const long long rel0 = lo - p.n0;
+    for (int i = threadIdx.x; i < NS; i += kFeNT) {
+        const long long rel = rel0 + i;
+        float2 v = cf(0.f, 0.f);
+        if (rel >= 0) { if (rel < p.nx) v = xs[rel]; }
+        else if (rel >= -(long long)p.hcap) v = hs[p.hcap + rel];
+        raw[i] = v;
+    }
+}
+
+template <int S>
+__global__ void __launch_bounds__(kFeNT, 3) k_frontend_v3(const CSDR_GRID_CONSTANT FrontendParams p)
+{
+    constexpr FeGeom G = FeStd<S, 3>::G;
+    constexpr int NS = G.n[S];
+    CSDR_DYN_SMEM(smem_raw);
+    float2 *smem = reinterpret_cast<float2 *>(smem_raw);
+    float *bank_s = reinterpret_cast<float *>(smem_raw) + 2 * G.total_f2;
+    float2 *raw = smem + G.off[S];
+    __shared__ FeTileInfo s_info[3];
+    __shared__ __align__(8) unsigned long long s_bar;
+
+    const int npfb = 1 << p.bits;
+    for (int i = threadIdx.x; i < npfb * kHsub; i += kFeNT) {
+        const int row = i / kHsub, col = i - row * kHsub;
+        bank_s[row * (kHsub + 1) + col] = p.bank[i];
+    }
+    const float2 *xs = p.x + (long long)blockIdx.y * p.x_stride;
+    const float2 *hs = p.hist + (long long)blockIdx.y * p.hcap;
+    float2 *ys = p.y + (long long)blockIdx.y * p.y_stride;
+    const double inv_st = 1.0 / (double)p.step;
+    const float rate_f = 16777216.0f / (float)p.step;
+    const int gstep = (int)gridDim.x;
+
+    unsigned parity = 0;
+    if (threadIdx.x == 0) {
+        const int t0 = (int)blockIdx.x;
+        bulk_init(&s_bar);
+        if (t0 < p.ntiles) fe_tile_info<S, 3>(p, xs, t0, inv_st, s_info[0]);
+        if (t0 + gstep < p.ntiles) fe_tile_info<S, 3>(p, xs, t0 + gstep, inv_st, s_info[1]);
+    }
+    __syncthreads();
+    if ((int)blockIdx.x < p.ntiles) {
+        if (s_info[0].bulk) { if (threadIdx.x == 0) bulk_copy_g2s(raw, xs + (s_info[0].lo - p.n0), NS * (unsigned)sizeof(float2), &s_bar); }
+        else fe_fill_staging<S>(p, xs, hs, raw, s_info[0].lo);
+    }
+    __syncthreads();
+
+    int cur = 0;
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gstep) {
+        const int nxt = cur == 2 ? 0 : cur + 1, nxt2 = nxt == 2 ? 0 : nxt + 1;
+        if (s_info[cur].bulk) { bulk_wait(&s_bar, parity); parity ^= 1u; }
+        // phase word of the tile's local sample 0 (+ the table-rounding offset of the quantised NCO)
+        const unsigned thb = p.theta0 + (unsigned)s_info[cur].lo * p.dtheta + (p.quantize ? (1u << 21) : 0u);
+        if (p.mix_mode == 0)      fe_run_top_v3<S, 0>(p, smem, thb);
+        else if (p.quantize) { if (p.mix_mode == 1) fe_run_top_v3<S, 1 | 8>(p, smem, thb);
+                               else                 fe_run_top_v3<S, 2 | 8>(p, smem, thb); }
+        else                 { if (p.mix_mode == 1) fe_run_top_v3<S, 1>(p, smem, thb);
+                               else                 fe_run_top_v3<S, 2>(p, smem, thb); }
+        __syncthreads();
+        // the staging buffer has been consumed: start fetching the next tile of this CTA
+        if (tile + gstep < p.ntiles) {
+            if (s_info[nxt].bulk) { if (threadIdx.x == 0) bulk_copy_g2s(raw, xs + (s_info[nxt].lo - p.n0), NS * (unsigned)sizeof(float2), &s_bar); }
+            else fe_fill_staging<S>(p, xs, hs, raw, s_info[nxt].lo);
+        }
+        if (threadIdx.x == 0 && tile + 2 * gstep < p.ntiles) fe_tile_info<S, 3>(p, xs, tile + 2 * gstep, inv_st, s_info[nxt2]);
+
+        if constexpr (S >= 2) fe_run_lower_v3<S, S - 2>(p, smem);
+        {
+            const int npush = (int)min((long long)G.Tc, p.K1 - p.K0 - (long long)tile * G.Tc);
+            fe_resample_tile<G.Tc, false>(p, smem + G.off[0], ys, s_info[cur], npush, bank_s, rate_f);
+        }
+        __syncthreads();   // lower levels may be overwritten; a synchronously filled staging buffer is complete
         cur = nxt;
     }
 }

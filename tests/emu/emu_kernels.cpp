@@ -28,7 +28,7 @@ long long emu_frontend(float rate, float As, int mix_mode, float freq, int quant
     FrontendGeometry g = plan_frontend(ms, Tc, allow_std != 0, allow_std >= 2 ? allow_std - 1 : 0);
     void (*kernel)(FrontendParams) = k_frontend;
     if (g.std_kernel) {
-        nthreads = 256;
+        nthreads = kFeNT;
         if (g.variant == 0) {
             switch (ms.S) {
             case 1: kernel = k_frontend_std<1, 0>; break;
@@ -37,6 +37,15 @@ long long emu_frontend(float rate, float As, int mix_mode, float freq, int quant
             case 4: kernel = k_frontend_std<4, 0>; break;
             case 5: kernel = k_frontend_std<5, 0>; break;
             default: kernel = k_frontend_std<6, 0>; break;
+            }
+        } else if (g.variant == 3) {
+            switch (ms.S) {
+            case 1: kernel = k_frontend_v3<1>; break;
+            case 2: kernel = k_frontend_v3<2>; break;
+            case 3: kernel = k_frontend_v3<3>; break;
+            case 4: kernel = k_frontend_v3<4>; break;
+            case 5: kernel = k_frontend_v3<5>; break;
+            default: kernel = k_frontend_v3<6>; break;
             }
         } else if (g.variant == 2) {
             switch (ms.S) {

@@ -17,7 +17,10 @@ from util import assert_parity, make_signal
     (0.3, 60.0, 0, 256, 1, 2), (0.2, 60.0, 0, 256, 0, 2), (0.078125, 60.0, 0, 256, 1, 2), (0.04, 60.0, 0, 256, 2, 2),
     # fused-mix variant k_frontend_v2<S>, S = 2..6
     (0.2, 60.0, 0, 256, 1, 3), (0.078125, 60.0, 0, 256, 1, 3), (0.078125, 60.0, 0, 256, 0, 3), (0.04, 60.0, 0, 256, 2, 3),
-    (0.02, 60.0, 0, 256, 1, 3), (0.011, 60.0, 0, 256, 2, 3)])
+    (0.02, 60.0, 0, 256, 1, 3), (0.011, 60.0, 0, 256, 2, 3),
+    # direct-read variant k_frontend_v3<S>, S = 1..6
+    (0.3, 60.0, 0, 256, 1, 4), (0.2, 60.0, 0, 256, 2, 4), (0.078125, 60.0, 0, 256, 1, 4), (0.078125, 60.0, 0, 256, 0, 4),
+    (0.04, 60.0, 0, 256, 2, 4), (0.02, 60.0, 0, 256, 1, 4), (0.011, 60.0, 0, 256, 1, 4)])
 def test_frontend_matches_oracle(orc, emu, rate, As, Tc, nthreads, mix, std):
     x = make_signal(40000, 7)
     f = float(np.float32(0.24543693))
@@ -27,7 +30,7 @@ def test_frontend_matches_oracle(orc, emu, rate, As, Tc, nthreads, mix, std):
     assert_parity(y, ref, what="frontend")
     if std:
         # 8-byte aligned chunk: the scalar loader path must give the same bits as the float4 path
-        assert np.array_equal(emu.frontend(x, rate, As=As, mix_mode=mix, freq=f, Tc=Tc, nthreads=nthreads, misalign=1), y)
+        assert np.array_equal(emu.frontend(x, rate, As=As, mix_mode=mix, freq=f, Tc=Tc, nthreads=nthreads, std=std, misalign=1), y)
 
 
 def test_frontend_chunk_invariance_is_bit_exact(emu):

@@ -40,8 +40,8 @@ def test_msresamp_generic_kernel(cs, orc):
         cs.set_option(5, 0)
 
 
-@pytest.mark.parametrize("variant", [0, 1])
-@pytest.mark.parametrize("rate", [0.3, 0.15, 0.078125, 0.04])
+@pytest.mark.parametrize("variant", [0, 1, 3])
+@pytest.mark.parametrize("rate", [0.3, 0.15, 0.078125, 0.04, 0.02, 0.011])
 def test_msresamp_other_input_pipelines(cs, orc, rate, variant):
     """CSDR_OPT_FRONTEND_VARIANT: 0 = raw tiles prefetched into registers (two CTAs per SM), 1 = staged in shared
     memory by cp.async.bulk (three CTAs per SM); the default, 2, copies them asynchronously into the top level's
