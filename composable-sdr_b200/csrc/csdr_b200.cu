@@ -30,7 +30,7 @@ namespace {
 
 thread_local std::string t_err;
 std::atomic<unsigned long long> g_launches{0};
-int g_options[16] = {0, 1, 0, 512, 384, 0, 0, 0, 0, 2};
+int g_options[16] = {0, 1, 0, 512, 384, 0, 0, 0, 0, 3};
 
 void set_err(const std::string &s) { t_err = s; }
 void clear_err() { t_err.clear(); }

@@ -580,6 +580,11 @@ __device__ __forceinline__ void fe_fill_staging(const FrontendParams &p, const f
     }
 }
 
+#if defined(CSDR_FE_SKIP) && (CSDR_FE_SKIP & 16)
+#define FE_NOFILL 1        // timing experiments only: leave the staging buffer as it is
+#else
+#define FE_NOFILL 0
+#endif
 template <int S>
 __global__ void __launch_bounds__(kFeNT, 3) k_frontend_v3(const CSDR_GRID_CONSTANT FrontendParams p)
 {
@@ -613,7 +618,7 @@ __global__ void __launch_bounds__(kFeNT, 3) k_frontend_v3(const CSDR_GRID_CONSTA
     }
     __syncthreads();
     if ((int)blockIdx.x < p.ntiles) {
-        if (s_info[0].bulk) { if (threadIdx.x == 0) bulk_copy_g2s(raw, xs + (s_info[0].lo - p.n0), NS * (unsigned)sizeof(float2), &s_bar); }
+        if (FE_NOFILL) {} else if (s_info[0].bulk) { if (threadIdx.x == 0) bulk_copy_g2s(raw, xs + (s_info[0].lo - p.n0), NS * (unsigned)sizeof(float2), &s_bar); }
         else fe_fill_staging<S>(p, xs, hs, raw, s_info[0].lo);
     }
     __syncthreads();
@@ -621,9 +626,14 @@ __global__ void __launch_bounds__(kFeNT, 3) k_frontend_v3(const CSDR_GRID_CONSTA
     int cur = 0;
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gstep) {
         const int nxt = cur == 2 ? 0 : cur + 1, nxt2 = nxt == 2 ? 0 : nxt + 1;
-        if (s_info[cur].bulk) { bulk_wait(&s_bar, parity); parity ^= 1u; }
+        if (s_info[cur].bulk && !FE_NOFILL) { bulk_wait(&s_bar, parity); parity ^= 1u; }
         // phase word of the tile's local sample 0 (+ the table-rounding offset of the quantised NCO)
         const unsigned thb = p.theta0 + (unsigned)s_info[cur].lo * p.dtheta + (p.quantize ? (1u << 21) : 0u);
+#ifdef CSDR_FE_SKIP
+        if (CSDR_FE_SKIP & 2) {}
+        else if (CSDR_FE_SKIP & 1) fe_run_top_v3<S, 0>(p, smem, thb);
+        else
+#endif
         if (p.mix_mode == 0)      fe_run_top_v3<S, 0>(p, smem, thb);
         else if (p.quantize) { if (p.mix_mode == 1) fe_run_top_v3<S, 1 | 8>(p, smem, thb);
                                else                 fe_run_top_v3<S, 2 | 8>(p, smem, thb); }
@@ -632,12 +642,19 @@ __global__ void __launch_bounds__(kFeNT, 3) k_frontend_v3(const CSDR_GRID_CONSTA
         __syncthreads();
         // the staging buffer has been consumed: start fetching the next tile of this CTA
         if (tile + gstep < p.ntiles) {
-            if (s_info[nxt].bulk) { if (threadIdx.x == 0) bulk_copy_g2s(raw, xs + (s_info[nxt].lo - p.n0), NS * (unsigned)sizeof(float2), &s_bar); }
+            if (FE_NOFILL) {} else if (s_info[nxt].bulk) { if (threadIdx.x == 0) bulk_copy_g2s(raw, xs + (s_info[nxt].lo - p.n0), NS * (unsigned)sizeof(float2), &s_bar); }
             else fe_fill_staging<S>(p, xs, hs, raw, s_info[nxt].lo);
         }
-        if (threadIdx.x == 0 && tile + 2 * gstep < p.ntiles) fe_tile_info<S, 3>(p, xs, tile + 2 * gstep, inv_st, s_info[nxt2]);
+        // bookkeeping for the tile after next: by a thread of the last warp, which has no slot in the lower stages
+        if (threadIdx.x == kFeNT - 32 && tile + 2 * gstep < p.ntiles) fe_tile_info<S, 3>(p, xs, tile + 2 * gstep, inv_st, s_info[nxt2]);
 
+#ifdef CSDR_FE_SKIP
+        if (!(CSDR_FE_SKIP & 4))
+#endif
         if constexpr (S >= 2) fe_run_lower_v3<S, S - 2>(p, smem);
+#ifdef CSDR_FE_SKIP
+        if (!(CSDR_FE_SKIP & 8))
+#endif
         {
             const int npush = (int)min((long long)G.Tc, p.K1 - p.K0 - (long long)tile * G.Tc);
             fe_resample_tile<G.Tc, false>(p, smem + G.off[0], ys, s_info[cur], npush, bank_s, rate_f);

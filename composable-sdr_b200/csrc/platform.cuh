@@ -66,7 +66,10 @@ constexpr int kMaxStages = 12;   // half-band stages (2^12 decimation) supported
 constexpr int kMaxHbM    = 16;   // max half-band semi-length m (2m taps)
 constexpr int kHsub      = 14;   // taps per polyphase branch of the arbitrary resampler (2*7, msresamp.c)
 constexpr int kFePlanePad = 1;   // elements between the even and the odd plane of a level buffer (see fe_fill_top)
-constexpr int kFeTopR  = 7;      // outputs per thread slot of a first stage that reads the linear raw tile (variant 3)
+#ifndef CSDR_FE_TOPR
+#define CSDR_FE_TOPR 7
+#endif
+constexpr int kFeTopR  = CSDR_FE_TOPR;      // outputs per thread slot of a first stage that reads the linear raw tile (variant 3)
 constexpr int kHcPad     = 16;   // c-rate history carried into every tile (>= kHsub-1, multiple of 8)
 
 __host__ __device__ inline float2 cf(float re, float im) { float2 z; z.x = re; z.y = im; return z; }

@@ -51,8 +51,9 @@ enum {
     CSDR_OPT_AGC_EXACT_MATH = 6,  /* 1: library expf/logf/atan2f in the AGC/discriminator loop instead of the SFU forms */
     CSDR_OPT_OVERLAP = 7,         /* 1: overlap the back end of part i with the front end of part i+1 (2 streams) */
     CSDR_OPT_DEBUG = 8,           /* 1: print AGC speculation diagnostics to stderr (synchronises) */
-    CSDR_OPT_FRONTEND_VARIANT = 9 /* front-end input pipeline: 0 register prefetch (2 CTAs/SM), 1 TMA bulk-copy staging (3 CTAs/SM),
-                                          2 (default) asynchronous copy + mix fused into the first half-band stage (4 CTAs/SM) */
+    CSDR_OPT_FRONTEND_VARIANT = 9 /* front-end input pipeline: 0 register prefetch (2 CTAs/SM), 1 TMA bulk-copy staging +
+                                      mixing pass (3 CTAs/SM), 2 asynchronous copy + mix fused into the first half-band
+                                      stage (4 CTAs/SM), 3 (default) first stage reads the TMA-staged tile directly */
 };
 int         csdr_set_option(int opt, int value);
 int         csdr_get_option(int opt);

@@ -9,6 +9,7 @@ n = 1 << 27
 x = sig(n, 1)
 variant = int(sys.argv[1])
 cs.set_option(9, variant)
+if len(sys.argv) > 3: cs.set_option(10, int(sys.argv[3]))
 ch = cs.Chain(2.56e6, 1e5, 200e3)
 cap = ch.max_output(n)
 out = torch.empty(cap, dtype=torch.complex64, device="cuda")
