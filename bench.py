@@ -48,17 +48,61 @@ def ncu_traffic():
 
 
 class ClockSampler:
-    """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    """SM clock and throttle reasons sampled DURING the timed region (B200_PROFILING.md's clocks line).  NVML from a
+    thread (a sample every ~0.5 ms: the timed region of the default run is only ~15 ms); nvidia-smi -lms if the
+    NVML binding is missing."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    REASONS = ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"), (0x4, "sw_power_cap"))
 
-    def __init__(self, gpu_index):
+    def __init__(self, gpu_index, uuid=None):
         self.idx = gpu_index
         self.proc = None
         self.lines = []
+        self.sm, self.reasons, self.smmax = [], set(), None
+        self.h = None
+        self.run = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            h = None
+            if uuid:
+                try:
+                    h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + str(uuid)) if not str(uuid).startswith("GPU-") else str(uuid))
+                except Exception:
+                    h = None
+            self.h = h or pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+            self.smmax = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.h = None
+
+    def _sample(self):
+        nv = self.nv
+        self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+        try:
+            mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+        except Exception:
+            mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+        for bit, name in self.REASONS:
+            if mask & bit:
+                self.reasons.add(name)
+
+    def _loop(self):
+        while self.run:
+            try:
+                self._sample()
+            except Exception:
+                break
+            time.sleep(0.0005)
 
     def start(self):
+        if self.h is not None:
+            self.run = True
+            self.t = threading.Thread(target=self._loop, daemon=True)
+            self.t.start()
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
                                           "--format=csv,noheader,nounits", "-lms", "100"],
@@ -73,6 +117,15 @@ class ClockSampler:
             self.lines.append(line.strip())
 
     def stop(self):
+        if self.h is not None:
+            try:
+                self._sample()          # the GPU is still draining the last launches: counts as under load
+            except Exception:
+                pass
+            self.run = False
+            self.t.join(timeout=1)
+            return {"sm_mhz": statistics.median(self.sm) if self.sm else None, "sm_max_mhz": self.smmax,
+                    "reasons": sorted(self.reasons), "samples": len(self.sm), "source": "nvml"}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -95,7 +148,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smmax) if smmax else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi"}
 
 
 def device_input(torch, n, rank):
@@ -224,7 +277,11 @@ def run_ours(args):
     barrier()
     chain.profile(True)
     launches0 = cs.kernel_launches()
-    clocks = ClockSampler(local)
+    try:
+        uuid = str(torch.cuda.get_device_properties(torch.cuda.current_device()).uuid)
+    except Exception:
+        uuid = None
+    clocks = ClockSampler(local, uuid)
     clocks.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)

@@ -83,27 +83,30 @@ __device__ __forceinline__ int fe_addr_rt(int i, int D, int stride)
 
 // Phasor with the quantisation mode known at compile time.  The phase index is turned into a float by bit insertion
 // (2^23 + k has k in its mantissa), not by an int->float conversion: conversions share the XU pipe with the sin/cos
-// evaluations, which is the pipe this per-sample work is bound by.  Q = 1: NCO sine table, 1024 levels, th already
-// carries the +2^21 rounding offset; Q = 0: the top 23 phase bits.
+// evaluations.  `th` is the phase word PLUS HALF A TURN (callers fold the 2^31 into their base phase), so that
+// k - K/2 is the signed index and the angle lies in [-pi, pi), where the SFU approximations are most accurate
+// (abs err ~2^-21.4).  Q = 1: NCO sine table, K = 1024 levels, th also carries the +2^21 rounding offset;
+// Q = 0: K = 2^23, the top 23 phase bits.
+constexpr unsigned kFePhaseBias = 0x80000000u;
 template <int Q>
 __device__ __forceinline__ float2 fe_phasor_q(unsigned th)
 {
-    constexpr float a = Q ? 6.1359231515425649e-3f : 7.4901405658478575e-7f;    // 2 pi / 1024, 2 pi / 2^23
 #ifdef CSDR_EMU
     const unsigned kbits = 0x4B000000u | (Q ? (th >> 22) : (th >> 9));
 #else
     const unsigned kbits = Q ? __funnelshift_r(th, 0x4B000000u >> 10, 22) : __funnelshift_r(th, 0x4B000000u >> 23, 9);
 #endif
-    const float ang = fmaf(__uint_as_float(kbits), a, -8388608.0f * a);          // k * a, rounded once (2^23 a is exact)
+    // revolutions in [-0.5, 0.5): (2^23 + k) / K - (2^23 / K + 0.5), every step exact in fp32
+    const float rev = Q ? fmaf(__uint_as_float(kbits), 9.765625e-4f, -8192.5f) : (__uint_as_float(kbits) - 8388608.0f) * 1.1920928955078125e-7f - 0.5f;
     float s, c;
-    __sincosf(ang, &s, &c);
+    __sincosf(rev * 6.283185307179586f, &s, &c);
     return cf(c, s);
 }
 
 // phasor of the NCO at phase word `th`:  (cos, sin)
 __device__ __forceinline__ float2 fe_phasor(unsigned th, int quantize)
 {
-    return quantize ? fe_phasor_q<1>(th + (1u << 21)) : fe_phasor_q<0>(th);   // NCO(_index): round to 1024 levels
+    return quantize ? fe_phasor_q<1>(th + (1u << 21) + kFePhaseBias) : fe_phasor_q<0>(th + kFePhaseBias);   // NCO(_index): round to 1024 levels
 }
 
 // One half-band decimation stage over a tile: n_out outputs, R per thread slot.

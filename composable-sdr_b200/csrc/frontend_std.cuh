@@ -460,7 +460,7 @@ __global__ void __launch_bounds__(kFeNT, 4) k_frontend_v2(const CSDR_GRID_CONSTA
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gstep) {
         const int nxt = cur == 2 ? 0 : cur + 1, nxt2 = nxt == 2 ? 0 : nxt + 1;
         // phase word of the tile's local sample 0 (+ the table-rounding offset of the quantised NCO)
-        const unsigned thb = p.theta0 + (unsigned)s_info[cur].lo * p.dtheta + (p.quantize ? (1u << 21) : 0u);
+        const unsigned thb = p.theta0 + (unsigned)s_info[cur].lo * p.dtheta + (p.quantize ? (1u << 21) : 0u) + kFePhaseBias;
 #ifdef CSDR_FE_SKIP
         if (CSDR_FE_SKIP & 2) {}
         else if (CSDR_FE_SKIP & 1) fe_run_stage_v2<S, S - 1, 0>(p, smem, thb);
@@ -628,7 +628,7 @@ __global__ void __launch_bounds__(kFeNT, 3) k_frontend_v3(const CSDR_GRID_CONSTA
         const int nxt = cur == 2 ? 0 : cur + 1, nxt2 = nxt == 2 ? 0 : nxt + 1;
         if (s_info[cur].bulk && !FE_NOFILL) { bulk_wait(&s_bar, parity); parity ^= 1u; }
         // phase word of the tile's local sample 0 (+ the table-rounding offset of the quantised NCO)
-        const unsigned thb = p.theta0 + (unsigned)s_info[cur].lo * p.dtheta + (p.quantize ? (1u << 21) : 0u);
+        const unsigned thb = p.theta0 + (unsigned)s_info[cur].lo * p.dtheta + (p.quantize ? (1u << 21) : 0u) + kFePhaseBias;
 #ifdef CSDR_FE_SKIP
         if (CSDR_FE_SKIP & 2) {}
         else if (CSDR_FE_SKIP & 1) fe_run_top_v3<S, 0>(p, smem, thb);
