@@ -4,15 +4,23 @@
 //     freqdem                   (Liquid.chs:324-334, liquid freqdem.c)
 // for `nlanes` independent sample sequences (streams or channelizer channels) of n samples each.
 //
-// Parallelisation over TIME (the reference is one sequential loop per stream):
-//   * dc blocker: a linear recurrence.  k_dc_local reduces every G-sample group to its zero-state response and
-//     scans the groups of a CTA, k_dc_carry chains the CTAs (fp64): the exact filter state at every group boundary
-//     is then one multiply-add away, and consumers restart the float32 recurrence from those states.
-//   * AGC + squelch: the gain loop is contractive, so L-sample segments are run speculatively after a W-sample
-//     warm-up and verified against their predecessors; the squelch state machine never feeds back into the gain
-//     and is resolved EXACTLY afterwards on one threshold bit per sample; the gate is applied last as a mask.
-//     Details at "agc + fm" below.  The result equals the sequential loop to within the stated tolerance in all
-//     cases (gate positions exactly); only the speed depends on the signal.
+// Parallelisation over TIME (the reference is one sequential loop per stream).  Only the AGC gain is a genuinely
+// sequential, non-linear recurrence; everything else is arranged around it as coalesced, fully parallel passes:
+//   1. dc blocker (linear recurrence): k_dc_local reduces every G-sample group to its zero-state response (one warp
+//      per group, fp64) and scans the groups of a CTA, k_dc_carry scans the CTAs: the exact filter state at every
+//      group boundary is then one multiply-add away.
+//   2. k_be_prep (one warp per group): dc-blocked samples y_dc[n] and their power p[n] = |y_dc[n]|^2.
+//   3. k_agc_chain: the gain loop sees its input only through p[n]  (|x g|^2 = g^2 p), so the chain is
+//      g^2 p -> one-pole filter -> g *= y2'^(-alpha/2): ~11 instructions per sample.  The loop is contractive, so
+//      L-sample segments are run speculatively after a W-sample warm-up, each by its own thread, writing the gain
+//      after every sample; start states are verified against the predecessors' end states, misses are refined in
+//      parallel and, as a last resort, repaired in stream order (k_agc_verify / k_agc_refine / k_agc_fixup).
+//   4. k_be_emit (one sample per thread, one 32-sample word per warp): ungated output y = y_dc g, discriminator
+//      value, "rssi > threshold" bit and sign bits by warp ballot.
+//   5. the squelch state machine never feeds back into the gain and is resolved EXACTLY on one threshold bit per
+//      sample (k_backend_fsm*); the gate is applied last as a mask (k_backend_gate).
+// The result equals the sequential loop to within the stated tolerance in all cases (gate positions exactly, given
+// the threshold bits); only the speed depends on the signal.
 #pragma once
 #include "platform.cuh"
 
@@ -24,9 +32,9 @@ struct LaneState {                 // carried across calls, one per lane
     float dc_re, dc_im;            // dc blocker v1
     float g, y2p;                  // agc gain, filtered output energy
     int mode; unsigned timer;      // squelch FSM
-    float fm_re, fm_im;            // freqdem r_prime
+    float fm_re, fm_im;            // freqdem r_prime: the last UNGATED agc output sample
 };
-struct SegState { float g, y2p; int mode; unsigned timer; float fm_re, fm_im; };
+struct SegState { float g, y2p; };
 
 struct FsmState;
 struct BackendParams {
@@ -35,22 +43,23 @@ struct BackendParams {
     int n, nlanes;
     int L, W, G, nseg, ngrp;
     int has_dc, has_agc, demod;                // demod: 0 none (cf32 out), 1 fm (float out)
-    float dc_a1;                               // a[1] = -1 + alpha_dc
     float alpha; float one_minus_alpha_f; float neg_half_alpha;
     float g_thr;                               // rssi > threshold  <=>  g < g_thr  (bisected on the host)
     unsigned timeout; float fm_ref;
     int squelch_enabled;
-    int exact_math;                            // 1: library expf/logf/atan2f in the per-sample loop (slower)
+    int exact_math;                            // 1: library expf/logf/atan2f instead of the SFU forms (slower)
     int gate;                                  // 1: zero the output unless squelch status == SIGNALHI (Liquid.chs:700-704)
     LaneState *lane;
+    const float2 *ydc; long long ydc_stride;   // dc-blocked samples (= in when there is no dc blocker)
+    const float *pw; float *gpost; long long pw_stride;   // [nlanes][pw_stride] power, gain AFTER each sample
+    float *g_first; float2 *y_first;           // [nlanes] gain / ungated output before the chunk's first sample
     SegState *seg_start, *seg_end;             // [nlanes][nseg] gain-loop state at segment boundaries
-    const double2 *dcVloc, *dcCarry; const double *dcPowA; int nblk;   // dc state at group boundaries (see dc blocker)
     int nwords, FW;                            // 32-sample words per lane; FSM replay length in segments
     unsigned *exbits, *gatebits;               // [nlanes][nwords] threshold-exceeded / gate-open bit per sample
     unsigned *sgnr, *sgni;                     // [nlanes][nwords] sign bits of the ungated agc output (discriminator
                                                // values next to a closed gate are signed-zero artefacts: +-pi or 0)
     unsigned *prev_sign;                       // [nlanes] sign bits (re | im << 1) of the sample before this chunk
-    FsmState *fsm_start, *fsm_end;      // [nlanes][nseg]
+    FsmState *fsm_start, *fsm_end;             // [nlanes][nseg]
     unsigned *prev_gate;                       // [nlanes] gate of the sample before this chunk
     unsigned *first_bad;                       // [nlanes][2] first segment whose start state does not continue its
                                                // predecessor (gain loop, squelch FSM); 0xffffffff = none
@@ -61,15 +70,18 @@ struct BackendParams {
 // ------------------------------------------------------------------------------------------ dc blocker
 // v[n] = x[n] + c v[n-1] (c = 1 - alpha), y[n] = v[n] - v[n-1].  The state at every G-sample group boundary is
 //   V(j) = Vloc[j-1] + carry[b] * A^k ,   A = c^G, b = (j-1) / kDcGB, k = (j-1) % kDcGB + 1
-// Vloc = in-block inclusive scan of the groups' zero-state responses (k_dc_local, one group per thread, kDcGB
-// groups per CTA), carry[b] = state at the start of block b (k_dc_carry, sequential over the few blocks), all fp64.
-constexpr int kDcGB = 256;
+// Vloc = in-block inclusive scan of the groups' zero-state responses (k_dc_local: kDcGB groups per CTA, one warp per
+// group, each lane G/32 consecutive samples), carry[b] = state at the start of block b (k_dc_carry), all fp64.
+constexpr int kDcGB = 64;
+constexpr int kDcWarps = 8;
 
 struct DcParams {
     const float2 *in; long long in_lane_stride;
-    float2 *out; long long out_lane_stride;
-    int n, nlanes, G, ngrp, nblk;
+    float2 *out; long long out_lane_stride;    // dc-blocked samples (nullptr: not wanted)
+    float *pw; long long pw_stride;            // |y|^2 (nullptr: not wanted)
+    int n, nlanes, G, ngrp, nblk, has_dc;
     double c;                                  // 1 - alpha  (= -a1)
+    double cS[5];                              // c^(S d), S = G/32 samples per lane, d = 1, 2, 4, 8, 16
     float a1;
     double2 *Vloc;                             // [nlanes][ngrp]  block-local state at the END of group j
     double2 *carry;                            // [nlanes][nblk]  state at the start of block b
@@ -89,65 +101,110 @@ __device__ __forceinline__ double2 dc_state_at(const double2 *Vloc, const double
     return make_double2(v.x + cb.x * a, v.y + cb.y * a);
 }
 
-__global__ void __launch_bounds__(kDcGB) k_dc_local(const DcParams p)
+// the S = G/32 consecutive samples of this lane in group j (zero past the end of the chunk); 16-byte loads when the
+// lane's samples are 16-byte aligned
+template <int S>
+__device__ __forceinline__ void dc_load(const float2 *__restrict__ x, int n, int i0, float2 (&v)[S])
 {
-    __shared__ double sr[kDcGB], si[kDcGB];
-    const int lane = blockIdx.y, t = threadIdx.x, j = blockIdx.x * kDcGB + t;
-    const float2 *x = p.in + (long long)lane * p.in_lane_stride;
-    double ar = 0.0, ai = 0.0;
-    if (j < p.ngrp) {
-        const int i0 = j * p.G, i1 = min(i0 + p.G, p.n);
-        for (int i = i0; i < i1; i++) {
-            const float2 v = x[i];
-            ar = ar * p.c + (double)v.x;
-            ai = ai * p.c + (double)v.y;
-        }
-        // a short last group is completed with zero input so that every group advances the state by c^G
-        for (int i = i1; i < i0 + p.G; i++) { ar *= p.c; ai *= p.c; }
+    if (S >= 2 && i0 + S <= n && (reinterpret_cast<uintptr_t>(x + i0) & 15) == 0) {
+        const float4 *x4 = reinterpret_cast<const float4 *>(x + i0);
+#pragma unroll
+        for (int k = 0; k < S / 2; k++) { const float4 q = __ldg(x4 + k); v[2 * k] = cf(q.x, q.y); v[2 * k + 1] = cf(q.z, q.w); }
+    } else {
+#pragma unroll
+        for (int k = 0; k < S; k++) v[k] = (i0 + k < n) ? __ldg(x + i0 + k) : cf(0.f, 0.f);
     }
-    sr[t] = ar; si[t] = ai;
-    __syncthreads();
-    double f = p.powA[1];
-    for (int d = 1; d < kDcGB; d <<= 1) {
-        double vr = 0.0, vi = 0.0;
-        if (t >= d) { vr = sr[t - d] * f; vi = si[t - d] * f; }
-        __syncthreads();
-        if (t >= d) { sr[t] += vr; si[t] += vi; }
-        __syncthreads();
-        f *= f;
-    }
-    if (j < p.ngrp) p.Vloc[(long long)lane * p.ngrp + j] = make_double2(sr[t], si[t]);
 }
 
-// one CTA per lane: carries of the (few) blocks, then the state after the last sample goes into the lane state
-__global__ void __launch_bounds__(256) k_dc_carry(const DcParams p)
+// inclusive warp scan of the affine maps  s -> m s + a  (composition left to right): afterwards lane l holds the map
+// of lanes 0..l, i.e. (m^(l+1), zero-state response at the end of lane l's samples)
+__device__ __forceinline__ void dc_warp_scan(double &ar, double &ai, double &m, const double (&cS)[5])
 {
-    const int lane = blockIdx.x, t = threadIdx.x;
-    __shared__ double ar[1024], ai[1024];
-    double2 *cl = p.carry + (long long)lane * p.nblk;
-    // block aggregates (state contribution of a full block), fetched in parallel
-    for (int b = t; b < p.nblk && b < 1024; b += blockDim.x) {
-        const int jl = (b + 1) * kDcGB - 1;
-        double2 v = make_double2(0.0, 0.0);
-        if (jl < p.ngrp) v = p.Vloc[(long long)lane * p.ngrp + jl];
-        ar[b] = v.x; ai[b] = v.y;
+    const int l = threadIdx.x & 31;
+#pragma unroll
+    for (int s = 0; s < 5; s++) {
+        const int d = 1 << s;
+        const double pr = __shfl_up_sync(0xffffffffu, ar, d), pi = __shfl_up_sync(0xffffffffu, ai, d);
+        if (l >= d) { ar += pr * m; ai += pi * m; }        // own map applied after the predecessor block's
+        // every lane's multiplier is cS[0]^(number of lanes it covers): doubles until it reaches lane 0
+        const double pm = __shfl_up_sync(0xffffffffu, m, d);
+        if (l >= d) m *= pm;
+    }
+    (void)cS;
+}
+
+template <int S>
+__global__ void __launch_bounds__(32 * kDcWarps) k_dc_local(const DcParams p)
+{
+    constexpr int GW = kDcGB / kDcWarps;               // groups per warp
+    __shared__ double sr[kDcGB], si[kDcGB];
+    const int lane = blockIdx.y, t = threadIdx.x, w = t >> 5, l = t & 31;
+    const float2 *x = p.in + (long long)lane * p.in_lane_stride;
+    const double A = p.powA[1];
+    double Rr = 0.0, Ri = 0.0;                          // zero-state response of this warp's run of groups
+    for (int k = 0; k < GW; k++) {
+        const int j = blockIdx.x * kDcGB + w * GW + k;
+        float2 v[S];
+        dc_load<S>(x, (j < p.ngrp) ? p.n : 0, j * p.G + l * S, v);
+        double ar = 0.0, ai = 0.0;
+#pragma unroll
+        for (int q = 0; q < S; q++) { ar = ar * p.c + (double)v[q].x; ai = ai * p.c + (double)v[q].y; }
+        double m = p.cS[0];
+        dc_warp_scan(ar, ai, m, p.cS);
+        const double Tr = __shfl_sync(0xffffffffu, ar, 31), Ti = __shfl_sync(0xffffffffu, ai, 31);
+        Rr = Rr * A + Tr; Ri = Ri * A + Ti;
+        if (l == 0) { sr[w * GW + k] = Rr; si[w * GW + k] = Ri; }
     }
     __syncthreads();
-    if (t == 0) {
-        double cr = (double)p.lane[lane].dc_re, ci = (double)p.lane[lane].dc_im;
-        const double AB = p.powA[kDcGB];
-        for (int b = 0; b < p.nblk; b++) {
-            cl[b] = make_double2(cr, ci);
-            double vr, vi;
-            if (b < 1024) { vr = ar[b]; vi = ai[b]; }
-            else {
-                const int jl = (b + 1) * kDcGB - 1;
-                double2 v = make_double2(0.0, 0.0);
-                if (jl < p.ngrp) v = p.Vloc[(long long)lane * p.ngrp + jl];
-                vr = v.x; vi = v.y;
-            }
-            cr = cr * AB + vr; ci = ci * AB + vi;
+    if (t < kDcGB) {
+        const int j = blockIdx.x * kDcGB + t, tw = t / GW, tk = t - tw * GW;
+        // state at the start of warp tw's run inside this block
+        double pr = 0.0, pi = 0.0;
+        for (int q = 0; q < tw; q++) {
+            const double a = p.powA[GW * (tw - 1 - q)];
+            pr += sr[q * GW + GW - 1] * a; pi += si[q * GW + GW - 1] * a;
         }
+        const double a = p.powA[tk + 1];
+        if (j < p.ngrp) p.Vloc[(long long)lane * p.ngrp + j] = make_double2(sr[t] + pr * a, si[t] + pi * a);
+    }
+}
+
+// one CTA per lane: carries of the blocks (affine scan, 1024 blocks per round), then the state after the last
+// sample goes into the lane state
+__global__ void __launch_bounds__(1024) k_dc_carry(const DcParams p)
+{
+    const int lane = blockIdx.x, t = threadIdx.x;
+    __shared__ double sm[1024], sr[1024], si[1024];
+    __shared__ double cr, ci;
+    double2 *cl = p.carry + (long long)lane * p.nblk;
+    if (t == 0) { cr = (double)p.lane[lane].dc_re; ci = (double)p.lane[lane].dc_im; }
+    __syncthreads();
+    const double AB = p.powA[kDcGB];
+    for (int base = 0; base < p.nblk; base += 1024) {
+        const int b = base + t;
+        // map of block b: s -> AB s + (zero-state response of the whole block)
+        double m = AB, ar = 0.0, ai = 0.0;
+        const int jl = (b + 1) * kDcGB - 1;
+        if (b < p.nblk && jl < p.ngrp) { const double2 v = p.Vloc[(long long)lane * p.ngrp + jl]; ar = v.x; ai = v.y; }
+        sm[t] = m; sr[t] = ar; si[t] = ai;
+        __syncthreads();
+        for (int d = 1; d < 1024; d <<= 1) {
+            double pm = 1.0, pr = 0.0, pi = 0.0;
+            if (t >= d) { pm = sm[t - d]; pr = sr[t - d]; pi = si[t - d]; }
+            __syncthreads();
+            if (t >= d) { ar += pr * m; ai += pi * m; m *= pm; sm[t] = m; sr[t] = ar; si[t] = ai; }
+            __syncthreads();
+        }
+        // carry[b] = state at the START of block b: the inclusive map of blocks base..b-1 applied to the round's carry
+        if (b < p.nblk) {
+            if (t == 0) cl[b] = make_double2(cr, ci);
+            else cl[b] = make_double2(sr[t - 1] + cr * sm[t - 1], si[t - 1] + ci * sm[t - 1]);
+        }
+        __syncthreads();
+        if (t == 1023) { const double nr = ar + cr * m, ni = ai + ci * m; cr = nr; ci = ni; }
+        __syncthreads();
+    }
+    if (t == 0) {
         // state after n samples: restart from the last full-group boundary
         const int jf = p.n / p.G;
         const double2 v = dc_state_at(p.Vloc, p.carry, p.powA, p.ngrp, p.nblk, lane, jf);
@@ -162,42 +219,63 @@ __global__ void __launch_bounds__(256) k_dc_carry(const DcParams p)
     }
 }
 
-// stand-alone dc blocker output (iirfilt_crcf_execute_block): one thread per group restarts the float32
-// recurrence from the exact boundary state.  May run in place (k_dc_carry has already read what it needs).
-__global__ void k_dc_apply(const DcParams p)
+// dc-blocked samples and/or their power, one warp per group: the filter state before each lane's samples comes from
+// the exact group-boundary state and a warp scan, then every lane runs the float32 recurrence of iirfilt over its
+// own G/32 samples.  out may alias in (every lane reads its samples before it writes them).
+template <int S>
+__global__ void __launch_bounds__(256) k_be_prep(const DcParams p)
 {
-    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= (long long)p.nlanes * p.ngrp) return;
-    int lane = (int)(t / p.ngrp), j = (int)(t - (long long)lane * p.ngrp);
+    const long long gw = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int l = threadIdx.x & 31;
+    if (gw >= (long long)p.nlanes * p.ngrp) return;                      // whole warps leave together
+    const int lane = (int)(gw / p.ngrp), j = (int)(gw - (long long)lane * p.ngrp);
     const float2 *x = p.in + (long long)lane * p.in_lane_stride;
-    float2 *y = p.out + (long long)lane * p.out_lane_stride;
-    const double2 v = dc_state_at(p.Vloc, p.carry, p.powA, p.ngrp, p.nblk, lane, j);
-    float v1r = (float)v.x, v1i = (float)v.y;
-    int i0 = j * p.G, i1 = min(i0 + p.G, p.n);
-    for (int i = i0; i < i1; i++) {
-        float2 s = x[i];
-        float v0r = __fsub_rn(s.x, __fmul_rn(p.a1, v1r));
-        float v0i = __fsub_rn(s.y, __fmul_rn(p.a1, v1i));
-        y[i] = cf(__fsub_rn(v0r, v1r), __fsub_rn(v0i, v1i));
-        v1r = v0r; v1i = v0i;
+    const int i0 = j * p.G + l * S;
+    float2 v[S];
+    dc_load<S>(x, p.n, i0, v);
+    if (p.has_dc) {
+        double ar = 0.0, ai = 0.0;
+#pragma unroll
+        for (int q = 0; q < S; q++) { ar = ar * p.c + (double)v[q].x; ai = ai * p.c + (double)v[q].y; }
+        double m = p.cS[0];
+        dc_warp_scan(ar, ai, m, p.cS);
+        // state before this lane's samples = map of lanes 0..l-1 applied to the group's entry state
+        const double2 V = dc_state_at(p.Vloc, p.carry, p.powA, p.ngrp, p.nblk, lane, j);
+        double er = __shfl_up_sync(0xffffffffu, ar, 1), ei = __shfl_up_sync(0xffffffffu, ai, 1), em = __shfl_up_sync(0xffffffffu, m, 1);
+        if (l == 0) { er = 0.0; ei = 0.0; em = 1.0; }
+        float v1r = (float)(er + V.x * em), v1i = (float)(ei + V.y * em);
+#pragma unroll
+        for (int q = 0; q < S; q++) {
+            const float v0r = __fsub_rn(v[q].x, __fmul_rn(p.a1, v1r));
+            const float v0i = __fsub_rn(v[q].y, __fmul_rn(p.a1, v1i));
+            v[q] = cf(__fsub_rn(v0r, v1r), __fsub_rn(v0i, v1i));
+            v1r = v0r; v1i = v0i;
+        }
+    }
+    if (p.out) {
+        float2 *y = p.out + (long long)lane * p.out_lane_stride + i0;
+        if (S == 4 && i0 + S <= p.n && (reinterpret_cast<uintptr_t>(y) & 15) == 0) {
+            reinterpret_cast<float4 *>(y)[0] = make_float4(v[0].x, v[0].y, v[1 % S].x, v[1 % S].y);
+            reinterpret_cast<float4 *>(y)[1] = make_float4(v[2 % S].x, v[2 % S].y, v[3 % S].x, v[3 % S].y);
+        } else {
+#pragma unroll
+            for (int q = 0; q < S; q++) if (i0 + q < p.n) y[q] = v[q];
+        }
+    }
+    if (p.pw) {
+        float *w = p.pw + (long long)lane * p.pw_stride + i0;
+        float e[S];
+#pragma unroll
+        for (int q = 0; q < S; q++) e[q] = __fadd_rn(__fmul_rn(v[q].x, v[q].x), __fmul_rn(v[q].y, v[q].y));
+        if (S == 4 && i0 + S <= p.n) *reinterpret_cast<float4 *>(w) = make_float4(e[0], e[1 % S], e[2 % S], e[3 % S]);   // pw_stride % 4 == 0
+        else {
+#pragma unroll
+            for (int q = 0; q < S; q++) if (i0 + q < p.n) w[q] = e[q];
+        }
     }
 }
 
-// ------------------------------------------------------------------------------------------ agc + fm
-// The squelch FSM does not feed back into the gain loop, so the work is split:
-//   pass G (k_backend_spec / k_backend_fixup): the gain trajectory.  Each L-sample segment is run by its own thread
-//       after a W-sample warm-up (the loop is contractive: perturbations decay like (1-alpha)^(k/2)); it writes the
-//       UNGATED outputs (agc samples, or discriminator values of ungated neighbours) and one "rssi > threshold" bit
-//       per sample.  Segment start states are verified against the predecessor's end state (1e-6 relative) and the
-//       rare misses (e.g. a gain frozen by digital silence) are re-run in stream order.
-//   pass F (k_backend_fsm / k_backend_fsm_fix): the squelch state machine, EXACT, on the bit stream.  Each segment
-//       re-derives its entry state by replaying the bits of the preceding FW segments (any entry state is forgotten
-//       after timeout+4 samples except for measure-zero coincidences), emits one gate bit per sample, and entry states
-//       are again verified against the predecessor's exit state and repaired in order where they differ.
-//   pass A (k_backend_gate): zero the outputs where the gate is closed: y[i] if !gate[i]; the discriminator output
-//       m[i] = arg(conj(r[i-1]) r[i]) if !(gate[i-1] && gate[i])  (arg(0) = 0, as in liquid).
-struct AgcRun { float g, y2p; float fr, fi; };
-
+// ------------------------------------------------------------------------------------------ agc gain loop
 __device__ __forceinline__ void fsm_step(int &mode, unsigned &timer, bool ex, unsigned timeout)
 {
     // AGC(_squelch_update_mode), liquid agc.c
@@ -240,181 +318,125 @@ __device__ __forceinline__ float be_atan2(float y, float x)
     return copysignf(r, y);
 }
 
-// compile-time configuration of the per-sample loop (runtime flags inside it would fence the instruction scheduler)
-enum { BE_DC = 1, BE_AGC = 2, BE_FM = 4, BE_EXACT = 8, BE_NCFG = 16 };
 
-// one sample of the gain loop: ungated agc output (yr, yi), threshold bit, ungated discriminator value
-template <int CFG>
-__device__ __forceinline__ bool be_step(const BackendParams &p, AgcRun &s, float xr, float xi, float &yr, float &yi,
-                                        float &m)
+// one step of AGC(_execute), liquid agc.c, seen from the gain:  y = x g, y2 = |y|^2 = g^2 |x|^2,
+// y2' = (1-alpha) y2' + alpha y2 (liquid evaluates this in double and rounds to float; the float32 FMA differs from it
+// by at most one ulp of y2'), g *= y2'^(-alpha/2) unless y2' <= 1e-6, g <= 1e6.  Default: SFU exp2/log2 (each step
+// good to ~3e-7 relative; the loop is contractive, so the gain stays within ~1e-6 of the libm evaluation).
+__device__ __forceinline__ float be_lg2(float x)
 {
-    bool ex = true;
-    if (CFG & BE_AGC) {
-        // AGC(_execute), liquid agc.c
-        yr = __fmul_rn(xr, s.g); yi = __fmul_rn(xi, s.g);
-        float y2 = __fadd_rn(__fmul_rn(yr, yr), __fmul_rn(yi, yi));
-        // liquid evaluates (1.0 - alpha) * y2' + alpha * y2 in double and rounds to float; the float32 FMA below differs
-        // from it by at most one ulp of y2' (6e-8 relative), i.e. 3e-9 per step in the gain: far below the 1e-6 at
-        // which two float32 runs of this loop settle anyway
-        s.y2p = fmaf(p.one_minus_alpha_f, s.y2p, __fmul_rn(p.alpha, y2));
-        // g *= y2'^(-alpha/2) unless y2' <= 1e-6.  Default: SFU exp2/log2 (each step is good to ~3e-7 relative and
-        // the loop is contractive, so the gain stays within ~1e-6 of the libm evaluation); BE_EXACT: expf/logf.
-        const float f = (CFG & BE_EXACT) ? expf(p.neg_half_alpha * logf(s.y2p)) : __expf(p.neg_half_alpha * __logf(s.y2p));
-        s.g *= (s.y2p > 1e-6f) ? f : 1.0f;
-        s.g = fminf(s.g, 1e6f);
-        ex = s.g < p.g_thr;                       // rssi = -20 log10(g) > threshold
-    } else { yr = xr; yi = xi; }
-    if (CFG & BE_FM) {
-        // freqdem_demodulate: arg(conj(r') r) / (2 pi kf)
-        float re = __fadd_rn(__fmul_rn(s.fr, yr), __fmul_rn(s.fi, yi));
-        float im = __fsub_rn(__fmul_rn(s.fr, yi), __fmul_rn(s.fi, yr));
-        m = ((CFG & BE_EXACT) ? atan2f(im, re) : be_atan2(im, re)) * p.fm_ref;
-        s.fr = yr; s.fi = yi;
+#ifdef CSDR_EMU
+    return log2f(x);
+#else
+    float r; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r;
+#endif
+}
+__device__ __forceinline__ float be_ex2(float x)
+{
+#ifdef CSDR_EMU
+    return exp2f(x);
+#else
+    float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r;
+#endif
+}
+template <bool EXACT>
+__device__ __forceinline__ void agc_step(const BackendParams &p, float &g, float &y2p, float pw)
+{
+    const float y2 = __fmul_rn(__fmul_rn(g, g), pw);
+    y2p = fmaf(p.one_minus_alpha_f, y2p, __fmul_rn(p.alpha, y2));
+    const float f = EXACT ? expf(p.neg_half_alpha * logf(y2p)) : be_ex2(p.neg_half_alpha * be_lg2(y2p));
+    g *= (y2p > 1e-6f) ? f : 1.0f;
+    g = fminf(g, 1e6f);
+}
+
+// run samples [i0, i1) of one lane's power sequence; EMIT: store the gain after every sample.  i0 is a multiple
+// of 4; powers are fetched eight at a time, one block ahead of the recurrence.
+template <bool EMIT, bool EXACT>
+__device__ __forceinline__ void agc_run(const BackendParams &p, int lane, float &g, float &y2p, int i0, int i1)
+{
+    const float *__restrict__ pw = p.pw + (long long)lane * p.pw_stride;
+    float *__restrict__ go = p.gpost + (long long)lane * p.pw_stride;
+    int i = i0;
+    if (i + 8 <= i1) {
+        const float4 *p4 = reinterpret_cast<const float4 *>(pw + i);
+        float4 na = __ldg(p4), nb = __ldg(p4 + 1);
+        for (; i + 8 <= i1; i += 8) {
+            const float c[8] = {na.x, na.y, na.z, na.w, nb.x, nb.y, nb.z, nb.w};
+            if (i + 16 <= i1) { const float4 *q4 = reinterpret_cast<const float4 *>(pw + i + 8); na = __ldg(q4); nb = __ldg(q4 + 1); }
+            float o[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) { agc_step<EXACT>(p, g, y2p, c[k]); o[k] = g; }
+            if (EMIT) {
+                float4 *o4 = reinterpret_cast<float4 *>(go + i);
+                o4[0] = make_float4(o[0], o[1], o[2], o[3]);
+                o4[1] = make_float4(o[4], o[5], o[6], o[7]);
+            }
+        }
     }
-    return ex;
+    for (; i < i1; i++) { agc_step<EXACT>(p, g, y2p, pw[i]); if (EMIT) go[i] = g; }
 }
 
 __device__ __forceinline__ bool be_close(float a, float b, float atol = 0.f)
 {
     return fabsf(a - b) <= 1e-5f * fmaxf(fabsf(a), fabsf(b)) + atol;   // fp32 rounding keeps two runs ~1e-6 apart
 }
-__device__ __forceinline__ bool be_match(const SegState &a, const SegState &b, int has_agc, int demod)
+__device__ __forceinline__ bool be_match(const SegState &a, const SegState &b)
 {
-    // the discriminator history is the previous ungated sample x * g: it continues whenever the gain does (and is
-    // exactly the previous input sample when there is no AGC)
-    (void)demod;
-    return !has_agc || (be_close(a.g, b.g) && be_close(a.y2p, b.y2p));
+    return be_close(a.g, b.g) && be_close(a.y2p, b.y2p);
 }
 
-// run samples [i0, i1) of one lane from state s / dc state (v1r, v1i).  EMIT: write outputs, threshold bits and
-// sign bits (the caller owns whole 32-sample words: i0 % 32 == 0 and i1 is a multiple of 32 or the chunk end).
-// Samples are fetched eight at a time, one block ahead of the recurrence, so that the sequential chain never waits
-// for memory.
-template <bool EMIT, int CFG>
-__device__ __forceinline__ void be_run(const BackendParams &p, int lane, AgcRun &s, float &v1r, float &v1i, int i0,
-                                       int i1)
-{
-    const float2 *__restrict__ x = p.in + (long long)lane * p.in_lane_stride;
-    float *__restrict__ of = (float *)p.out + (long long)lane * p.out_lane_stride;
-    float2 *__restrict__ oc = (float2 *)p.out + (long long)lane * p.out_lane_stride;
-    unsigned *bits = p.exbits + (long long)lane * p.nwords;
-    unsigned *sr = p.sgnr + (long long)lane * p.nwords, *si = p.sgni + (long long)lane * p.nwords;
-    unsigned word = 0, wr = 0, wi = 0;
-    constexpr int B = 8;
-    float2 cur[B], nxt[B];
-    // 16-byte loads (two samples each) when the lane's samples are 16-byte aligned: every lane reads its own cache
-    // line, so the number of load instructions is what the LSU pays for
-    const bool vec = ((reinterpret_cast<uintptr_t>(x) & 15) == 0) && ((i0 & 1) == 0);
-    auto fetch = [&](float2 (&dst)[B], int i) {
-        if (vec && i + B <= i1) {
-            const float4 *x4 = reinterpret_cast<const float4 *>(x + i);
-#pragma unroll
-            for (int k = 0; k < B / 2; k++) { const float4 q = __ldg(x4 + k); dst[2 * k] = cf(q.x, q.y); dst[2 * k + 1] = cf(q.z, q.w); }
-        } else {
-#pragma unroll
-            for (int k = 0; k < B; k++) dst[k] = (i + k < i1) ? __ldg(x + i + k) : cf(0.f, 0.f);
-        }
-    };
-    const bool vec_out = EMIT && (CFG & BE_FM) && ((reinterpret_cast<uintptr_t>(of) & 15) == 0) && ((i0 & 3) == 0);
-    float mbuf[B];
-    if (i0 < i1) fetch(nxt, i0);
-    for (int i = i0; i < i1; i += B) {
-#pragma unroll
-        for (int k = 0; k < B; k++) cur[k] = nxt[k];
-        if (i + B < i1) fetch(nxt, i + B);
-#pragma unroll
-        for (int k = 0; k < B; k++) {
-            if (i + k >= i1) break;
-            float xr = cur[k].x, xi = cur[k].y;
-            if (CFG & BE_DC) {
-                float v0r = __fsub_rn(xr, __fmul_rn(p.dc_a1, v1r));
-                float v0i = __fsub_rn(xi, __fmul_rn(p.dc_a1, v1i));
-                xr = __fsub_rn(v0r, v1r); xi = __fsub_rn(v0i, v1i);
-                v1r = v0r; v1i = v0i;
-            }
-            float yr, yi, m = 0.f;
-            const bool ex = be_step<CFG>(p, s, xr, xi, yr, yi, m);
-            if (EMIT) {
-                const int ii = i + k;
-                if (CFG & BE_FM) { if (vec_out) mbuf[k] = m; else of[ii] = m; } else oc[ii] = cf(yr, yi);
-                word |= (ex ? 1u : 0u) << (ii & 31);
-                wr |= ((unsigned)__float_as_int(yr) >> 31) << (ii & 31);
-                wi |= ((unsigned)__float_as_int(yi) >> 31) << (ii & 31);
-                if ((ii & 31) == 31 || ii == i1 - 1) {
-                    bits[ii >> 5] = word; word = 0;
-                    if (CFG & BE_FM) { sr[ii >> 5] = wr; si[ii >> 5] = wi; }
-                    wr = 0; wi = 0;
-                }
-            }
-        }
-        if (EMIT && vec_out) {
-            if (i + B <= i1) {
-                float4 *o4 = reinterpret_cast<float4 *>(of + i);
-                o4[0] = make_float4(mbuf[0], mbuf[1], mbuf[2], mbuf[3]);
-                o4[1] = make_float4(mbuf[4], mbuf[5], mbuf[6], mbuf[7]);
-            } else {
-#pragma unroll
-                for (int k = 0; k < B; k++) if (i + k < i1) of[i + k] = mbuf[k];
-            }
-        }
-    }
-}
-
-__device__ __forceinline__ void be_dc_state(const BackendParams &p, int lane, int i, float &v1r, float &v1i)
-{
-    // i is a multiple of G
-    if (p.has_dc) {
-        const double2 v = dc_state_at(p.dcVloc, p.dcCarry, p.dcPowA, p.ngrp, p.nblk, lane, i / p.G);
-        v1r = (float)v.x; v1i = (float)v.y;
-    } else { v1r = 0.f; v1i = 0.f; }
-}
-
-__device__ __forceinline__ SegState be_pack(const AgcRun &s)
-{
-    SegState st; st.g = s.g; st.y2p = s.y2p; st.mode = 0; st.timer = 0; st.fm_re = s.fr; st.fm_im = s.fi;
-    return st;
-}
-
-template <int CFG>
-__global__ void __launch_bounds__(128) k_backend_spec(const BackendParams p)
+template <bool EXACT>
+__global__ void __launch_bounds__(128) k_agc_chain(const BackendParams p)
 {
     long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (long long)p.nlanes * p.nseg) return;
     const int lane = (int)(t / p.nseg), seg = (int)(t - (long long)lane * p.nseg);
     const int b0 = seg * p.L, b1 = min(b0 + p.L, p.n);
     if (t == 0) *p.bad_count = 0;
-    AgcRun s; float v1r, v1i;
+    float g, y2p;
     int w0 = b0 - p.W;
-    const LaneState ls = p.lane[lane];
     if (w0 <= 0) {
         // the warm-up reaches the chunk start: run from the true carried state (exact)
         w0 = 0;
-        s.g = ls.g; s.y2p = ls.y2p; s.fr = ls.fm_re; s.fi = ls.fm_im;
+        const LaneState ls = p.lane[lane];
+        g = ls.g; y2p = ls.y2p;
     } else {
         // equilibrium guess: unit output energy for the first samples of the warm-up window
-        const float2 *x = p.in + (long long)lane * p.in_lane_stride;
+        const float4 *q = reinterpret_cast<const float4 *>(p.pw + (long long)lane * p.pw_stride + w0);
         float e = 0.f;
-        for (int i = 0; i < 16; i++) { float2 v = x[w0 + i]; e += v.x * v.x + v.y * v.y; }
+        for (int i = 0; i < 4; i++) { const float4 v = __ldg(q + i); e += (v.x + v.y) + (v.z + v.w); }
         e *= (1.0f / 16.0f);
-        s.g = (e > 1e-30f) ? rsqrtf(e) : 1e6f;
-        if (s.g > 1e6f) s.g = 1e6f;
-        s.y2p = 1.0f; s.fr = 0.f; s.fi = 0.f;
+        g = (e > 1e-30f) ? rsqrtf(e) : 1e6f;
+        if (g > 1e6f) g = 1e6f;
+        y2p = 1.0f;
     }
-    be_dc_state(p, lane, w0, v1r, v1i);
-    be_run<false, CFG>(p, lane, s, v1r, v1i, w0, b0);  // warm-up, nothing emitted
-    p.seg_start[t] = be_pack(s);
-    be_run<true, CFG>(p, lane, s, v1r, v1i, b0, b1);
-    p.seg_end[t] = be_pack(s);
+    agc_run<false, EXACT>(p, lane, g, y2p, w0, b0);  // warm-up, nothing stored
+    SegState s0; s0.g = g; s0.y2p = y2p;
+    p.seg_start[t] = s0;
+    agc_run<true, EXACT>(p, lane, g, y2p, b0, b1);
+    SegState s1; s1.g = g; s1.y2p = y2p;
+    p.seg_end[t] = s1;
+}
+
+// what the chunk's first sample needs from the previous chunk (the lane state is overwritten before k_be_emit runs)
+__global__ void k_be_first(const BackendParams p)
+{
+    const int lane = blockIdx.x * blockDim.x + threadIdx.x;
+    if (lane >= p.nlanes) return;
+    const LaneState ls = p.lane[lane];
+    p.g_first[lane] = ls.g;
+    p.y_first[lane] = cf(ls.fm_re, ls.fm_im);
+    p.prev_sign[lane] = ((unsigned)__float_as_int(ls.fm_re) >> 31) | (((unsigned)__float_as_int(ls.fm_im) >> 31) << 1);
 }
 
 // grid-wide verification of the gain speculation.  pass 0: collect the segments whose start state does not continue
-// their predecessor's end state; pass 1 (after k_backend_refine): first such segment per lane, for the in-order repair.
-__global__ void k_backend_verify(const BackendParams p, int pass)
+// their predecessor's end state; pass 1 (after k_agc_refine): first such segment per lane, for the in-order repair.
+__global__ void k_agc_verify(const BackendParams p, int pass)
 {
     long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (long long)p.nlanes * p.nseg) return;
     const int lane = (int)(t / p.nseg), seg = (int)(t - (long long)lane * p.nseg);
-    if (seg == 0 || be_match(p.seg_start[t], p.seg_end[t - 1], p.has_agc, p.demod)) return;
+    if (seg == 0 || be_match(p.seg_start[t], p.seg_end[t - 1])) return;
     if (pass == 0) {
         const unsigned idx = atomicAdd(p.bad_count, 1u);
         if (idx < p.bad_cap) p.bad_list[idx] = (unsigned)t;
@@ -427,21 +449,20 @@ __global__ void k_backend_verify(const BackendParams p, int pass)
 // loop) is replaced by the predecessor's END state, which is accurate because the predecessor's own L samples
 // damped its error; the segment is re-run from there.  (A predecessor that is being refined at the same time may
 // be read before or after its update: both values are valid to well below the tolerance.)
-template <int CFG>
-__global__ void __launch_bounds__(128) k_backend_refine(const BackendParams p)
+template <bool EXACT>
+__global__ void __launch_bounds__(128) k_agc_refine(const BackendParams p)
 {
     const unsigned count = min(*p.bad_count, p.bad_cap);
     for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < count; idx += gridDim.x * blockDim.x) {
         const long long t = p.bad_list[idx];
         const int lane = (int)(t / p.nseg), seg = (int)(t - (long long)lane * p.nseg);
         const SegState pe = p.seg_end[t - 1];
-        AgcRun s; s.g = pe.g; s.y2p = pe.y2p; s.fr = pe.fm_re; s.fi = pe.fm_im;
-        float v1r, v1i;
+        float g = pe.g, y2p = pe.y2p;
         const int b0 = seg * p.L, b1 = min(b0 + p.L, p.n);
-        be_dc_state(p, lane, b0, v1r, v1i);
         p.seg_start[t] = pe;
-        be_run<true, CFG>(p, lane, s, v1r, v1i, b0, b1);
-        p.seg_end[t] = be_pack(s);
+        agc_run<true, EXACT>(p, lane, g, y2p, b0, b1);
+        SegState s1; s1.g = g; s1.y2p = y2p;
+        p.seg_end[t] = s1;
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(p.fixups + 2, (unsigned long long)count);
 }
@@ -450,8 +471,8 @@ __global__ void __launch_bounds__(128) k_backend_refine(const BackendParams p)
 __global__ void k_backend_list_reset(const BackendParams p) { *p.bad_count = 0; }
 
 // one CTA per lane: re-run the misses in stream order (rare), store the lane's gain state
-template <int CFG>
-__global__ void k_backend_fixup(const BackendParams p)
+template <bool EXACT>
+__global__ void k_agc_fixup(const BackendParams p)
 {
     const int lane = blockIdx.x;
     __shared__ unsigned s_next;
@@ -468,7 +489,7 @@ __global__ void k_backend_fixup(const BackendParams p)
             // after a repair: parallel search for the next segment >= s_cur that does not continue its predecessor
             const int cur = s_cur;
             for (int j = cur + threadIdx.x; j < p.nseg; j += blockDim.x)
-                if (!be_match(S0[j], E[j - 1], p.has_agc, p.demod)) { atomicMin(&s_next, (unsigned)j); break; }
+                if (!be_match(S0[j], E[j - 1])) { atomicMin(&s_next, (unsigned)j); break; }
             __syncthreads();
         }
         first = false;
@@ -479,13 +500,12 @@ __global__ void k_backend_fixup(const BackendParams p)
             unsigned long long redone = 0;
             while (seg < p.nseg) {
                 const SegState pe = E[seg - 1];
-                if (be_match(S0[seg], pe, p.has_agc, p.demod)) break;
-                AgcRun s; s.g = pe.g; s.y2p = pe.y2p; s.fr = pe.fm_re; s.fi = pe.fm_im;
-                float v1r, v1i;
+                if (be_match(S0[seg], pe)) break;
+                float g = pe.g, y2p = pe.y2p;
                 const int b0 = seg * p.L, b1 = min(b0 + p.L, p.n);
-                be_dc_state(p, lane, b0, v1r, v1i);
-                be_run<true, CFG>(p, lane, s, v1r, v1i, b0, b1);
-                E[seg] = be_pack(s);
+                agc_run<true, EXACT>(p, lane, g, y2p, b0, b1);
+                SegState s1; s1.g = g; s1.y2p = y2p;
+                E[seg] = s1;
                 redone++;
                 seg++;      // the successor is re-checked against the new end state on the next iteration
             }
@@ -497,11 +517,62 @@ __global__ void k_backend_fixup(const BackendParams p)
     __syncthreads();
     if (threadIdx.x == 0) {
         const SegState e = E[p.nseg - 1];
-        LaneState ls = p.lane[lane];
-        p.prev_sign[lane] = ((unsigned)__float_as_int(ls.fm_re) >> 31) | (((unsigned)__float_as_int(ls.fm_im) >> 31) << 1);
-        ls.g = e.g; ls.y2p = e.y2p; ls.fm_re = e.fm_re; ls.fm_im = e.fm_im;
-        p.lane[lane] = ls;
+        p.lane[lane].g = e.g; p.lane[lane].y2p = e.y2p;
         p.first_bad[2 * lane] = 0xffffffffu;
+    }
+}
+
+// ------------------------------------------------------------------------------------------ emission
+// One sample per thread, one 32-sample word per warp and iteration.  y[n] = y_dc[n] * (gain before sample n);
+// threshold bit = (gain after sample n) < g_thr; discriminator m[n] = arg(conj(y[n-1]) y[n]) / (2 pi kf)
+// (freqdem_demodulate).  Without an AGC the gain is 1 and there are no bits.
+template <bool AGC, bool FM, bool EXACT>
+__global__ void __launch_bounds__(256) k_be_emit(const BackendParams p)
+{
+    const long long nw = (long long)p.nlanes * p.nwords;
+    const int l = threadIdx.x & 31;
+    for (long long t = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; t < nw; t += ((long long)gridDim.x * blockDim.x) >> 5) {
+        const int lane = (int)(t / p.nwords), w = (int)(t - (long long)lane * p.nwords);
+        const int i = w * 32 + l;
+        const bool in = i < p.n;
+        const float2 *x = p.ydc + (long long)lane * p.ydc_stride;
+        const float *gp = p.gpost + (long long)lane * p.pw_stride;
+        float2 y = cf(0.f, 0.f), yp = cf(0.f, 0.f);
+        float ga = 1.f;
+        if (in) {
+            y = x[i];
+            if (AGC) {
+                ga = gp[i];
+                const float g0 = (i == 0) ? p.g_first[lane] : gp[i - 1];
+                y = cf(__fmul_rn(y.x, g0), __fmul_rn(y.y, g0));
+            }
+            if (FM) {
+                if (i == 0) yp = p.y_first[lane];
+                else {
+                    yp = x[i - 1];
+                    if (AGC) { const float g1 = (i == 1) ? p.g_first[lane] : gp[i - 2]; yp = cf(__fmul_rn(yp.x, g1), __fmul_rn(yp.y, g1)); }
+                }
+            }
+        }
+        if (AGC) {
+            const unsigned ex = __ballot_sync(0xffffffffu, in && ga < p.g_thr);       // rssi = -20 log10(g) > threshold
+            if (l == 0) p.exbits[(long long)lane * p.nwords + w] = ex;
+            if (FM) {
+                const unsigned sr = __ballot_sync(0xffffffffu, in && (__float_as_int(y.x) < 0));
+                const unsigned si = __ballot_sync(0xffffffffu, in && (__float_as_int(y.y) < 0));
+                if (l == 0) { p.sgnr[(long long)lane * p.nwords + w] = sr; p.sgni[(long long)lane * p.nwords + w] = si; }
+            }
+        }
+        if (in) {
+            if (FM) {
+                const float re = __fadd_rn(__fmul_rn(yp.x, y.x), __fmul_rn(yp.y, y.y));
+                const float im = __fsub_rn(__fmul_rn(yp.x, y.y), __fmul_rn(yp.y, y.x));
+                ((float *)p.out)[(long long)lane * p.out_lane_stride + i] = (EXACT ? atan2f(im, re) : be_atan2(im, re)) * p.fm_ref;
+            } else {
+                ((float2 *)p.out)[(long long)lane * p.out_lane_stride + i] = y;
+            }
+            if (i == p.n - 1) { p.lane[lane].fm_re = y.x; p.lane[lane].fm_im = y.y; }
+        }
     }
 }
 
@@ -688,50 +759,61 @@ __global__ void k_lane_sum(const float *__restrict__ in, long long lane_stride, 
 // `launch(kernel, grid, block, smem_bytes, args...)` is supplied by the caller (CUDA stream launcher in
 // csdr_b200.cu, thread emulator in the CPU-only tests) so that both run the same sequence with the same grids.
 template <class Launch>
+inline void be_launch_prep(Launch &launch, const DcParams &d)
+{
+    const long long warps = (long long)d.nlanes * d.ngrp;
+    const dim3 grid((unsigned)((warps + 7) / 8)), block(256);
+    if (d.G == 128)     launch(k_be_prep<4>, grid, block, 0, d);
+    else if (d.G == 64) launch(k_be_prep<2>, grid, block, 0, d);
+    else                launch(k_be_prep<1>, grid, block, 0, d);
+}
+// group-boundary states (and the lane's final state); apply: also the dc-blocked samples / powers d asks for
+template <class Launch>
 inline void be_launch_dc(Launch &launch, const DcParams &d, bool apply)
 {
-    launch(k_dc_local, dim3(d.nblk, d.nlanes), dim3(kDcGB), 0, d);
-    launch(k_dc_carry, dim3(d.nlanes), dim3(256), 0, d);
-    if (apply) {
-        const long long items = (long long)d.nlanes * d.ngrp;
-        launch(k_dc_apply, dim3((unsigned)((items + 127) / 128)), dim3(128), 0, d);
-    }
+    const dim3 grid(d.nblk, d.nlanes), block(32 * kDcWarps);
+    if (d.G == 128)     launch(k_dc_local<4>, grid, block, 0, d);
+    else if (d.G == 64) launch(k_dc_local<2>, grid, block, 0, d);
+    else                launch(k_dc_local<1>, grid, block, 0, d);
+    launch(k_dc_carry, dim3(d.nlanes), dim3(1024), 0, d);
+    if (apply) be_launch_prep(launch, d);
 }
 
-template <int CFG, class Launch>
+template <bool EXACT, class Launch>
 inline void be_launch_gain(Launch &launch, const BackendParams &b, unsigned gb)
 {
-    launch(k_backend_spec<CFG>, dim3(gb), dim3(128), 0, b);
-    if (CFG & BE_AGC) {
-        // two rounds of verify + parallel refine (a run of consecutive misses needs one round per level of
-        // inaccuracy handed down the run; an empty list costs a few microseconds), then the in-order repair
-        launch(k_backend_verify, dim3(gb), dim3(128), 0, b, 0);
-        launch.debug_after_verify(b);
-        launch(k_backend_refine<CFG>, dim3(64), dim3(128), 0, b);
-        launch(k_backend_list_reset, dim3(1), dim3(1), 0, b);
-        launch(k_backend_verify, dim3(gb), dim3(128), 0, b, 0);
-        launch(k_backend_refine<CFG>, dim3(64), dim3(128), 0, b);
-        launch(k_backend_verify, dim3(gb), dim3(128), 0, b, 1);
-    }
-    launch(k_backend_fixup<CFG>, dim3(b.nlanes), dim3(128), 0, b);
-}
-template <int N, class Launch>
-inline void be_dispatch_gain(int cfg, Launch &launch, const BackendParams &b, unsigned gb)
-{
-    if constexpr (N >= 0) {
-        if (cfg == N) be_launch_gain<N>(launch, b, gb);
-        else be_dispatch_gain<N - 1>(cfg, launch, b, gb);
-    }
+    launch(k_agc_chain<EXACT>, dim3(gb), dim3(128), 0, b);
+    // two rounds of verify + parallel refine (a run of consecutive misses needs one round per level of
+    // inaccuracy handed down the run; an empty list costs a few microseconds), then the in-order repair
+    launch(k_agc_verify, dim3(gb), dim3(128), 0, b, 0);
+    launch.debug_after_verify(b);
+    launch(k_agc_refine<EXACT>, dim3(64), dim3(128), 0, b);
+    launch(k_backend_list_reset, dim3(1), dim3(1), 0, b);
+    launch(k_agc_verify, dim3(gb), dim3(128), 0, b, 0);
+    launch(k_agc_refine<EXACT>, dim3(64), dim3(128), 0, b);
+    launch(k_agc_verify, dim3(gb), dim3(128), 0, b, 1);
+    launch(k_agc_fixup<EXACT>, dim3(b.nlanes), dim3(128), 0, b);
 }
 
+template <bool AGC, bool FM, class Launch>
+inline void be_launch_emit(Launch &launch, const BackendParams &b)
+{
+    const long long words = (long long)b.nlanes * b.nwords;
+    const dim3 grid((unsigned)((words + 7) / 8)), block(256);
+    if (b.exact_math) launch(k_be_emit<AGC, FM, true>, grid, block, 0, b);
+    else              launch(k_be_emit<AGC, FM, false>, grid, block, 0, b);
+}
+
+// everything after the dc/power pass: gain loop, emission, squelch FSM, gate
 template <class Launch>
 inline void be_launch(Launch &launch, const BackendParams &b)
 {
     const long long segs = (long long)b.nlanes * b.nseg;
     const unsigned gb = (unsigned)((segs + 127) / 128);
-    const int cfg = (b.has_dc ? BE_DC : 0) | (b.has_agc ? BE_AGC : 0) | (b.demod == 1 ? BE_FM : 0) | (b.exact_math ? BE_EXACT : 0);
-    be_dispatch_gain<BE_NCFG - 1>(cfg, launch, b, gb);
+    launch(k_be_first, dim3((b.nlanes + 127) / 128), dim3(128), 0, b);
     if (b.has_agc) {
+        if (b.exact_math) be_launch_gain<true>(launch, b, gb); else be_launch_gain<false>(launch, b, gb);
+        if (b.demod == 1) be_launch_emit<true, true>(launch, b); else be_launch_emit<true, false>(launch, b);
         launch(k_backend_fsm, dim3(gb), dim3(128), 0, b);
         launch(k_backend_fsm_verify, dim3(gb), dim3(128), 0, b);
         launch(k_backend_fsm_fix, dim3(b.nlanes), dim3(128), 0, b);
@@ -739,6 +821,8 @@ inline void be_launch(Launch &launch, const BackendParams &b)
             const long long words = (long long)b.nlanes * b.nwords;
             launch(k_backend_gate, dim3((unsigned)((words + 127) / 128)), dim3(128), 0, b);
         }
+    } else {
+        if (b.demod == 1) be_launch_emit<false, true>(launch, b); else be_launch_emit<false, false>(launch, b);
     }
 }
 

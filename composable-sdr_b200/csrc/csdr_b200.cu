@@ -282,6 +282,7 @@ struct Backend {
     float kf = 0.3f;
     int L = 512, W = 384, G = 128; bool fixed_L = false;
     DevBuf lane, Vloc, carry, powA, ss, se, fs, fe, exbits, gatebits, sgnr, sgni, prev_gate, prev_sign, first_bad, bad_list, bad_count, fixups;
+    DevBuf ydc, pwbuf, gpost, g_first, y_first;
     int FW = 3; unsigned long long last_refined = 0;
     // self-tuning warm-up: the counters of every call are copied to pinned memory asynchronously; the next call looks
     // at them (no synchronisation) and lengthens / shortens the warm-up
@@ -292,11 +293,11 @@ struct Backend {
     void init(const Ctx &c, int lanes, float g0 = 1000.0f, int mode0 = SQ_ENABLED)
     {
         nlanes = lanes;
-        L = std::max(64, g_options[CSDR_OPT_AGC_SEGMENT]); W = std::max(16, g_options[CSDR_OPT_AGC_WARMUP]);
+        // segment and warm-up lengths in whole 32-sample words (one warp handles a dc group, one ballot a word)
+        L = (std::max(64, g_options[CSDR_OPT_AGC_SEGMENT]) + 31) / 32 * 32; W = (std::max(32, g_options[CSDR_OPT_AGC_WARMUP]) + 31) / 32 * 32;
         fixed_L = g_options[CSDR_OPT_AGC_SEGMENT] != 512;      // an explicit setting is taken literally
         G = 128;
         while (L % G || W % G) G /= 2;
-        if (!has_agc) { W = (demod == 1) ? G : 0; if (W == 0) W = 0; }
         std::vector<LaneState> ls(nlanes);
         for (auto &l : ls) { l.dc_re = l.dc_im = 0; l.g = g0; l.y2p = 1.0f; l.mode = mode0; l.timer = 0; l.fm_re = l.fm_im = 0; }
         lane.ensure(sizeof(LaneState) * nlanes);
@@ -352,7 +353,8 @@ struct Backend {
         DcParams d{};
         d.in = in; d.in_lane_stride = in_stride; d.out = out; d.out_lane_stride = out_stride;
         d.n = n; d.nlanes = nlanes; d.G = G; d.ngrp = (n + G - 1) / G; d.nblk = (d.ngrp + kDcGB - 1) / kDcGB;
-        d.a1 = -1.0f + dc_alpha; d.c = -(double)d.a1;
+        d.a1 = -1.0f + dc_alpha; d.c = -(double)d.a1; d.has_dc = 1;
+        { double cs = 1.0; for (int i = 0; i < G / 32; i++) cs *= d.c; for (int k = 0; k < 5; k++) { d.cS[k] = cs; cs *= cs; } }
         Vloc.ensure(sizeof(double2) * (size_t)nlanes * d.ngrp);
         carry.ensure(sizeof(double2) * (size_t)nlanes * d.nblk);
         d.Vloc = Vloc.as<double2>(); d.carry = carry.as<double2>(); d.powA = powA.as<double>();
@@ -377,10 +379,10 @@ struct Backend {
         if (n <= 0) return;
         Launcher l{st};
         // segment length: the per-segment recurrences are latency bound, so aim for >= ~64k concurrent chains
-        // (shorter segments = more chains but relatively more warm-up work); L stays a multiple of G
+        // (shorter segments = more chains but relatively more warm-up work); whole 32-sample words
         int L = this->L;
         if (has_agc && !fixed_L) {
-            while (L > G && (long long)nlanes * ((n + L - 1) / L) < 65536) L /= 2;
+            while (L > 64 && L % 64 == 0 && (long long)nlanes * ((n + L - 1) / L) < 65536) L /= 2;
         }
         int W = this->W;
         if (has_agc && !fixed_L) {
@@ -404,22 +406,43 @@ struct Backend {
         fs.ensure(sizeof(FsmState) * segs); fe.ensure(sizeof(FsmState) * segs);
         exbits.ensure(sizeof(unsigned) * (size_t)nlanes * nwords); gatebits.ensure(sizeof(unsigned) * (size_t)nlanes * nwords);
         sgnr.ensure(sizeof(unsigned) * (size_t)nlanes * nwords); sgni.ensure(sizeof(unsigned) * (size_t)nlanes * nwords);
+        g_first.ensure(sizeof(float) * nlanes); y_first.ensure(sizeof(float2) * nlanes);
+        const long long pws = ((long long)n + 3) / 4 * 4;          // lane stride of the per-sample work arrays
         BackendParams b{};
-        if (has_dc) {
+        b.ydc = in; b.ydc_stride = in_stride;
+        {
+            // dc blocker (states, then samples) and the power sequence the gain loop runs on
             DcParams d = dc_params(in, in_stride, nullptr, 0, n);
-            be_launch_dc(l, d, false);
-            b.dcVloc = d.Vloc; b.dcCarry = d.carry; b.dcPowA = d.powA; b.nblk = d.nblk;
+            d.has_dc = has_dc ? 1 : 0;
+            if (has_dc) {
+                ydc.ensure(sizeof(float2) * (size_t)nlanes * pws);
+                d.out = ydc.as<float2>(); d.out_lane_stride = pws;
+                b.ydc = ydc.as<float2>(); b.ydc_stride = pws;
+            } else if ((const void *)in == (const void *)out && demod == 0) {
+                // in-place cf32 call: k_be_emit reads the sample before the one it writes
+                ydc.ensure(sizeof(float2) * (size_t)nlanes * pws);
+                CK(cudaMemcpy2DAsync(ydc.p, sizeof(float2) * pws, in, sizeof(float2) * (size_t)(nlanes > 1 ? in_stride : n), sizeof(float2) * (size_t)n,
+                                     nlanes, cudaMemcpyDeviceToDevice, st));
+                b.ydc = ydc.as<float2>(); b.ydc_stride = pws;
+            }
+            if (has_agc) {
+                pwbuf.ensure(sizeof(float) * (size_t)nlanes * pws); gpost.ensure(sizeof(float) * (size_t)nlanes * pws);
+                d.pw = pwbuf.as<float>(); d.pw_stride = pws;
+            }
+            if (has_dc) be_launch_dc(l, d, true);
+            else if (has_agc) be_launch_prep(l, d);
         }
         b.in = in; b.in_lane_stride = in_stride; b.out = out; b.out_lane_stride = out_stride;
         b.n = n; b.nlanes = nlanes; b.L = L; b.W = W; b.G = G; b.nseg = nseg; b.ngrp = ngrp;
         b.has_dc = has_dc; b.has_agc = has_agc; b.demod = demod;
-        b.dc_a1 = -1.0f + dc_alpha;
         b.alpha = agc_bw; b.one_minus_alpha_f = (float)(1.0 - (double)agc_bw); b.neg_half_alpha = -0.5f * agc_bw;
         b.g_thr = design::agc_gain_threshold(agc_thr); b.timeout = agc_timeout;
         b.fm_ref = (float)(1.0f / (2 * design::kPi * kf));
         b.squelch_enabled = squelch ? 1 : 0; b.gate = gate ? 1 : 0;
         b.exact_math = g_options[CSDR_OPT_AGC_EXACT_MATH] ? 1 : 0;
         b.lane = lane.as<LaneState>(); b.seg_start = ss.as<SegState>(); b.seg_end = se.as<SegState>();
+        b.pw = pwbuf.as<float>(); b.gpost = gpost.as<float>(); b.pw_stride = pws;
+        b.g_first = g_first.as<float>(); b.y_first = y_first.as<float2>();
         b.nwords = nwords;
         // the FSM forgets its entry state after timeout + 4 samples: replay that many bits (in whole segments)
         b.FW = (int)std::min<unsigned>(64u, (agc_timeout + 8 + (unsigned)L - 1) / (unsigned)L);

@@ -37,6 +37,11 @@ namespace csdr_emu {
 inline thread_local uint3 t_threadIdx, t_blockIdx;
 inline uint3 g_blockDim, g_gridDim;
 inline pthread_barrier_t g_barrier;
+// warp-level exchange (shuffles, ballots): every lane of a warp must take part, as on the GPU with a full mask
+constexpr int kMaxWarps = 64;
+inline pthread_barrier_t g_warp_barrier[kMaxWarps];
+inline unsigned long long g_warp_slot[kMaxWarps][32];
+inline thread_local unsigned t_warp = 0, t_lane = 0, t_warp_lanes = 32;
 inline unsigned char *g_dyn_smem = nullptr;
 inline unsigned char *dyn_smem() { return g_dyn_smem; }
 inline unsigned long long g_launches = 0;
@@ -54,17 +59,22 @@ void launch(dim3 grid, dim3 block, size_t smem_bytes, K kernel, Args... args)
     for (unsigned by = 0; by < grid.y; by++)
     for (unsigned bx = 0; bx < grid.x; bx++) {
         pthread_barrier_init(&g_barrier, nullptr, nthreads);
+        const unsigned nwarps = (nthreads + 31) / 32;
+        if (nwarps > (unsigned)kMaxWarps) abort();
+        for (unsigned w = 0; w < nwarps; w++) pthread_barrier_init(&g_warp_barrier[w], nullptr, std::min(32u, nthreads - 32 * w));
         std::vector<std::thread> th;
         th.reserve(nthreads);
         for (unsigned t = 0; t < nthreads; t++) {
             th.emplace_back([=]() {
                 t_blockIdx = {bx, by, bz};
                 t_threadIdx = {t % block.x, (t / block.x) % block.y, t / (block.x * block.y)};
+                t_warp = t / 32; t_lane = t % 32; t_warp_lanes = std::min(32u, nthreads - 32 * (t / 32));
                 kernel(args...);
             });
         }
         for (auto &x : th) x.join();
         pthread_barrier_destroy(&g_barrier);
+        for (unsigned w = 0; w < nwarps; w++) pthread_barrier_destroy(&g_warp_barrier[w]);
     }
     g_dyn_smem = nullptr;
 }
@@ -77,6 +87,36 @@ void launch(dim3 grid, dim3 block, size_t smem_bytes, K kernel, Args... args)
 
 static inline void __syncthreads() { pthread_barrier_wait(&::csdr_emu::g_barrier); }
 static inline void __syncwarp() {}
+namespace csdr_emu {
+template <class T> inline T warp_exchange(T v, int src_lane)
+{
+    static_assert(sizeof(T) <= 8, "emulated shuffles move at most 8 bytes");
+    unsigned long long raw = 0;
+    memcpy(&raw, &v, sizeof(T));
+    g_warp_slot[t_warp][t_lane] = raw;
+    pthread_barrier_wait(&g_warp_barrier[t_warp]);
+    T out = v;
+    if (src_lane >= 0 && src_lane < (int)t_warp_lanes) memcpy(&out, &g_warp_slot[t_warp][src_lane], sizeof(T));
+    pthread_barrier_wait(&g_warp_barrier[t_warp]);
+    return out;
+}
+}  // namespace csdr_emu
+template <class T> static inline T __shfl_sync(unsigned, T v, int src) { return ::csdr_emu::warp_exchange(v, src & 31); }
+template <class T> static inline T __shfl_up_sync(unsigned, T v, unsigned d)
+{
+    const int src = (int)::csdr_emu::t_lane - (int)d;
+    return ::csdr_emu::warp_exchange(v, src < 0 ? (int)::csdr_emu::t_lane : src);      // lanes below d keep their own value
+}
+static inline unsigned __ballot_sync(unsigned, int pred)
+{
+    using namespace ::csdr_emu;
+    g_warp_slot[t_warp][t_lane] = pred ? 1ull : 0ull;
+    pthread_barrier_wait(&g_warp_barrier[t_warp]);
+    unsigned r = 0;
+    for (unsigned l = 0; l < t_warp_lanes; l++) r |= (unsigned)g_warp_slot[t_warp][l] << l;
+    pthread_barrier_wait(&g_warp_barrier[t_warp]);
+    return r;
+}
 static inline void __threadfence() { __sync_synchronize(); }
 
 // math intrinsics (host libm stands in for the SFU approximations; tests use tolerances)

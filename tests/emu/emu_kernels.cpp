@@ -101,7 +101,7 @@ long long emu_frontend(float rate, float As, int mix_mode, float freq, int quant
 // dc blocker -> agc(+gate) -> fm for nlanes lanes of n samples, fed in chunks; out is float (demod=1) or cf32.
 long long emu_backend(int nlanes, long long lane_stride, int has_dc, float dc_alpha, int has_agc, float thr_db,
                       int demod, float kf, int L, int W, int G, const float2 *x, long long n, const long long *chunks,
-                      int nchunks, void *out, unsigned long long *fixups_out, float *dbg /* optional [nseg][8] of the last chunk */)
+                      int nchunks, void *out, unsigned long long *fixups_out, float *dbg /* optional [nseg][4] of the last chunk */)
 {
     std::vector<LaneState> lane(nlanes);
     for (auto &l : lane) { l.dc_re = l.dc_im = 0; l.g = 1000.0f; l.y2p = 1.0f; l.mode = SQ_ENABLED; l.timer = 0; l.fm_re = l.fm_im = 0; }
@@ -111,37 +111,45 @@ long long emu_backend(int nlanes, long long lane_stride, int has_dc, float dc_al
         int nx = (int)chunks[c];
         if (nx == 0) continue;
         int ngrp = (nx + G - 1) / G, nseg = (nx + L - 1) / L, nblk = (ngrp + kDcGB - 1) / kDcGB;
+        const long long pws = (nx + 3) / 4 * 4;
         std::vector<double2> Vloc((size_t)nlanes * ngrp), carry((size_t)nlanes * nblk);
         std::vector<double> powA(kDcGB + 1);
         std::vector<SegState> ss((size_t)nlanes * nseg), se((size_t)nlanes * nseg);
         std::vector<FsmState> fs((size_t)nlanes * nseg), fe((size_t)nlanes * nseg);
+        std::vector<float2> ydc((size_t)nlanes * pws), yfirst(nlanes);
+        std::vector<float> pw((size_t)nlanes * pws), gpost((size_t)nlanes * pws), gfirst(nlanes);
         int nwords = (nx + 31) / 32;
         std::vector<unsigned> exb((size_t)nlanes * nwords), gb((size_t)nlanes * nwords), pg(nlanes, 0), ps(nlanes, 0);
         std::vector<unsigned> sgr((size_t)nlanes * nwords), sgi((size_t)nlanes * nwords), fb(2 * nlanes, 0xffffffffu), blist(4096);
         unsigned bcount = 0;
         DcParams d{};
         d.in = x + pos; d.in_lane_stride = lane_stride; d.n = nx; d.nlanes = nlanes; d.G = G; d.ngrp = ngrp; d.nblk = nblk;
+        d.has_dc = has_dc; d.out = has_dc ? ydc.data() : nullptr; d.out_lane_stride = pws;
+        d.pw = has_agc ? pw.data() : nullptr; d.pw_stride = pws;
         d.a1 = -1.0f + dc_alpha; d.c = -(double)d.a1; d.Vloc = Vloc.data(); d.carry = carry.data(); d.lane = lane.data();
         { double A = 1.0; for (int i = 0; i < G; i++) A *= d.c; powA[0] = 1.0; for (int k = 1; k <= kDcGB; k++) powA[k] = powA[k - 1] * A; }
+        { double cs = 1.0; for (int i = 0; i < G / 32; i++) cs *= d.c; for (int k = 0; k < 5; k++) { d.cS[k] = cs; cs *= cs; } }
         d.powA = powA.data();
         EmuLaunch launch;
-        if (has_dc) be_launch_dc(launch, d, false);
+        if (has_dc) be_launch_dc(launch, d, true);
+        else if (has_agc) be_launch_prep(launch, d);
         BackendParams b{};
         b.in = x + pos; b.in_lane_stride = lane_stride;
         b.out = demod ? (void *)((float *)out + pos) : (void *)((float2 *)out + pos); b.out_lane_stride = lane_stride;
         b.n = nx; b.nlanes = nlanes; b.L = L; b.W = W; b.G = G; b.nseg = nseg; b.ngrp = ngrp;
-        b.has_dc = has_dc; b.has_agc = has_agc; b.demod = demod; b.dc_a1 = d.a1;
+        b.has_dc = has_dc; b.has_agc = has_agc; b.demod = demod;
         b.alpha = 0.1f; b.one_minus_alpha_f = (float)(1.0 - (double)b.alpha); b.neg_half_alpha = -0.5f * b.alpha;
         b.g_thr = design::agc_gain_threshold(thr_db); b.timeout = 1000; b.fm_ref = (float)(1.0f / (2 * design::kPi * kf));
         b.squelch_enabled = 1; b.gate = 1;
         b.lane = lane.data(); b.seg_start = ss.data(); b.seg_end = se.data();
-        b.dcVloc = Vloc.data(); b.dcCarry = carry.data(); b.dcPowA = powA.data(); b.nblk = nblk;
+        b.ydc = has_dc ? ydc.data() : x + pos; b.ydc_stride = has_dc ? pws : lane_stride;
+        b.pw = pw.data(); b.gpost = gpost.data(); b.pw_stride = pws; b.g_first = gfirst.data(); b.y_first = yfirst.data();
         b.nwords = nwords; b.FW = (1000 + 8 + L - 1) / L;
         b.exbits = exb.data(); b.gatebits = gb.data(); b.fsm_start = fs.data(); b.fsm_end = fe.data();
         b.prev_gate = pg.data(); b.prev_sign = ps.data(); b.sgnr = sgr.data(); b.sgni = sgi.data();
         b.first_bad = fb.data(); b.fixups = fixups2; b.bad_list = blist.data(); b.bad_count = &bcount; b.bad_cap = 4096;
         be_launch(launch, b);
-        if (dbg) for (int i = 0; i < nseg; i++) { float *d8 = dbg + 8 * i; d8[0] = ss[i].g; d8[1] = ss[i].y2p; d8[2] = ss[i].fm_re; d8[3] = ss[i].fm_im; d8[4] = se[i].g; d8[5] = se[i].y2p; d8[6] = se[i].fm_re; d8[7] = se[i].fm_im; }
+        if (dbg) for (int i = 0; i < nseg; i++) { float *d4 = dbg + 4 * i; d4[0] = ss[i].g; d4[1] = ss[i].y2p; d4[2] = se[i].g; d4[3] = se[i].y2p; }
         pos += nx;
     }
     if (fixups_out) { fixups_out[0] = fixups2[0]; fixups_out[1] = fixups2[1]; fixups_out[2] = fixups2[2]; }
