@@ -23,6 +23,7 @@
 // the threshold bits); only the speed depends on the signal.
 #pragma once
 #include "platform.cuh"
+#include <algorithm>
 
 namespace csdr {
 
@@ -225,10 +226,8 @@ __global__ void __launch_bounds__(1024) k_dc_carry(const DcParams p)
 template <int S>
 __global__ void __launch_bounds__(256) k_be_prep(const DcParams p)
 {
-    const long long gw = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int l = threadIdx.x & 31;
-    if (gw >= (long long)p.nlanes * p.ngrp) return;                      // whole warps leave together
-    const int lane = (int)(gw / p.ngrp), j = (int)(gw - (long long)lane * p.ngrp);
+    const int lane = blockIdx.y, l = threadIdx.x & 31, j = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (j >= p.ngrp) return;                                             // whole warps leave together
     const float2 *x = p.in + (long long)lane * p.in_lane_stride;
     const int i0 = j * p.G + l * S;
     float2 v[S];
@@ -385,14 +384,34 @@ __device__ __forceinline__ bool be_match(const SegState &a, const SegState &b)
     return be_close(a.g, b.g) && be_close(a.y2p, b.y2p);
 }
 
+// what the chunk's first sample needs from the previous chunk (the lane state is overwritten before k_be_emit runs)
+__device__ __forceinline__ void be_save_first(const BackendParams &p, int lane)
+{
+    const LaneState ls = p.lane[lane];
+    p.g_first[lane] = ls.g;
+    p.y_first[lane] = cf(ls.fm_re, ls.fm_im);
+    p.prev_sign[lane] = ((unsigned)__float_as_int(ls.fm_re) >> 31) | (((unsigned)__float_as_int(ls.fm_im) >> 31) << 1);
+}
+
+// start state of a speculative segment whose warm-up window starts at w0 > 0: unit output energy for the mean power
+// e of the window's first 16 samples
+__device__ __forceinline__ void agc_guess(float e, float &g, float &y2p)
+{
+    g = (e > 1e-30f) ? rsqrtf(e) : 1e6f;
+    if (g > 1e6f) g = 1e6f;
+    y2p = 1.0f;
+}
+
+// One thread per segment, segments of any length, powers and gains in global memory (every lane walks its own cache
+// lines): used when the staged kernel below does not apply, and by the repair kernels.
 template <bool EXACT>
 __global__ void __launch_bounds__(128) k_agc_chain(const BackendParams p)
 {
-    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= (long long)p.nlanes * p.nseg) return;
-    const int lane = (int)(t / p.nseg), seg = (int)(t - (long long)lane * p.nseg);
+    const int lane = blockIdx.y, seg = blockIdx.x * blockDim.x + threadIdx.x;
+    if (seg == 0) { if (lane == 0) { p.bad_count[0] = 0; p.bad_count[1] = 0; } be_save_first(p, lane); }
+    if (seg >= p.nseg) return;
+    const long long t = (long long)lane * p.nseg + seg;
     const int b0 = seg * p.L, b1 = min(b0 + p.L, p.n);
-    if (t == 0) *p.bad_count = 0;
     float g, y2p;
     int w0 = b0 - p.W;
     if (w0 <= 0) {
@@ -401,14 +420,10 @@ __global__ void __launch_bounds__(128) k_agc_chain(const BackendParams p)
         const LaneState ls = p.lane[lane];
         g = ls.g; y2p = ls.y2p;
     } else {
-        // equilibrium guess: unit output energy for the first samples of the warm-up window
         const float4 *q = reinterpret_cast<const float4 *>(p.pw + (long long)lane * p.pw_stride + w0);
         float e = 0.f;
         for (int i = 0; i < 4; i++) { const float4 v = __ldg(q + i); e += (v.x + v.y) + (v.z + v.w); }
-        e *= (1.0f / 16.0f);
-        g = (e > 1e-30f) ? rsqrtf(e) : 1e6f;
-        if (g > 1e6f) g = 1e6f;
-        y2p = 1.0f;
+        agc_guess(e * (1.0f / 16.0f), g, y2p);
     }
     agc_run<false, EXACT>(p, lane, g, y2p, w0, b0);  // warm-up, nothing stored
     SegState s0; s0.g = g; s0.y2p = y2p;
@@ -418,27 +433,82 @@ __global__ void __launch_bounds__(128) k_agc_chain(const BackendParams p)
     p.seg_end[t] = s1;
 }
 
-// what the chunk's first sample needs from the previous chunk (the lane state is overwritten before k_be_emit runs)
+// The same, staged through shared memory (L a power of two, W a multiple of L): the CTA's blockDim.x consecutive
+// segments and the warm-up window before them are one contiguous stretch of the power sequence, copied in with
+// coalesced loads; time u (relative to the stretch) lives at index u + u / L, so threads that are L samples apart
+// hit different banks.  All warm-ups first (they read other threads' segments), then every thread overwrites its
+// own segment with the gains, which go back to global memory coalesced.
+template <bool EXACT>
+__global__ void __launch_bounds__(128) k_agc_chain_staged(const BackendParams p, int lgL)
+{
+    CSDR_DYN_SMEM(smem_raw);
+    float *sm = reinterpret_cast<float *>(smem_raw);
+    const int lane = blockIdx.y, T = blockDim.x, tid = threadIdx.x, seg = blockIdx.x * T + tid;
+    if (blockIdx.x == 0 && tid == 0) { if (lane == 0) { p.bad_count[0] = 0; p.bad_count[1] = 0; } be_save_first(p, lane); }
+    const int B0 = blockIdx.x * T * p.L, B1 = min(B0 + T * p.L, p.n);
+    const int tO = B0 - p.W;                                  // time of stretch index 0 (may be negative)
+    const float *__restrict__ pw = p.pw + (long long)lane * p.pw_stride;
+    for (int u = max(0, -tO) + tid; u < B1 - tO; u += T) sm[u + (u >> lgL)] = pw[tO + u];
+    __syncthreads();
+    const int b0 = seg * p.L, b1 = min(b0 + p.L, p.n);
+    const bool live = seg < p.nseg;
+    float g = 1.f, y2p = 1.f;
+    if (live) {
+        int u = b0 - p.W - tO;
+        if (b0 - p.W <= 0) {
+            u = -tO;                                          // time 0: the true carried state (exact)
+            const LaneState ls = p.lane[lane];
+            g = ls.g; y2p = ls.y2p;
+        } else {
+            const float *q = sm + u + (u >> lgL);
+            float e = 0.f;
+            for (int i = 0; i < 16; i++) e += q[i];
+            agc_guess(e * (1.0f / 16.0f), g, y2p);
+        }
+        const int uw = b0 - tO;
+        while (u < uw) {                                      // warm-up, one L-block (or what is left of it) at a time
+            const int ue = min(((u >> lgL) + 1) << lgL, uw);
+            const float *q = sm + u + (u >> lgL);
+            const int cnt = ue - u;
+#pragma unroll 8
+            for (int k = 0; k < cnt; k++) agc_step<EXACT>(p, g, y2p, q[k]);
+            u = ue;
+        }
+        SegState s0; s0.g = g; s0.y2p = y2p;
+        p.seg_start[(long long)lane * p.nseg + seg] = s0;
+    }
+    __syncthreads();
+    if (live) {
+        const int u = b0 - tO, cnt = b1 - b0;                 // one L-block
+        float *q = sm + u + (u >> lgL);
+#pragma unroll 8
+        for (int k = 0; k < cnt; k++) { agc_step<EXACT>(p, g, y2p, q[k]); q[k] = g; }
+        SegState s1; s1.g = g; s1.y2p = y2p;
+        p.seg_end[(long long)lane * p.nseg + seg] = s1;
+    }
+    __syncthreads();
+    float *__restrict__ go = p.gpost + (long long)lane * p.pw_stride;
+    for (int u = p.W + tid; u < B1 - tO; u += T) go[tO + u] = sm[u + (u >> lgL)];
+}
+
+// no AGC: the chain kernel is not run, the first-sample state is saved by a launch of its own
 __global__ void k_be_first(const BackendParams p)
 {
     const int lane = blockIdx.x * blockDim.x + threadIdx.x;
-    if (lane >= p.nlanes) return;
-    const LaneState ls = p.lane[lane];
-    p.g_first[lane] = ls.g;
-    p.y_first[lane] = cf(ls.fm_re, ls.fm_im);
-    p.prev_sign[lane] = ((unsigned)__float_as_int(ls.fm_re) >> 31) | (((unsigned)__float_as_int(ls.fm_im) >> 31) << 1);
+    if (lane < p.nlanes) be_save_first(p, lane);
 }
 
-// grid-wide verification of the gain speculation.  pass 0: collect the segments whose start state does not continue
-// their predecessor's end state; pass 1 (after k_agc_refine): first such segment per lane, for the in-order repair.
-__global__ void k_agc_verify(const BackendParams p, int pass)
+// grid-wide verification of the gain speculation.  round 0 / 1: collect the segments whose start state does not
+// continue their predecessor's end state (list for k_agc_refine; each round has its own counter, zeroed by the chain
+// kernel); round 2: first such segment per lane, for the in-order repair.
+__global__ void k_agc_verify(const BackendParams p, int round)
 {
-    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= (long long)p.nlanes * p.nseg) return;
-    const int lane = (int)(t / p.nseg), seg = (int)(t - (long long)lane * p.nseg);
-    if (seg == 0 || be_match(p.seg_start[t], p.seg_end[t - 1])) return;
-    if (pass == 0) {
-        const unsigned idx = atomicAdd(p.bad_count, 1u);
+    const int lane = blockIdx.y, seg = blockIdx.x * blockDim.x + threadIdx.x;
+    if (seg == 0 || seg >= p.nseg) return;
+    const long long t = (long long)lane * p.nseg + seg;
+    if (be_match(p.seg_start[t], p.seg_end[t - 1])) return;
+    if (round < 2) {
+        const unsigned idx = atomicAdd(p.bad_count + round, 1u);
         if (idx < p.bad_cap) p.bad_list[idx] = (unsigned)t;
     } else {
         atomicMin(&p.first_bad[2 * lane], (unsigned)seg);
@@ -450,9 +520,9 @@ __global__ void k_agc_verify(const BackendParams p, int pass)
 // damped its error; the segment is re-run from there.  (A predecessor that is being refined at the same time may
 // be read before or after its update: both values are valid to well below the tolerance.)
 template <bool EXACT>
-__global__ void __launch_bounds__(128) k_agc_refine(const BackendParams p)
+__global__ void __launch_bounds__(128) k_agc_refine(const BackendParams p, int round)
 {
-    const unsigned count = min(*p.bad_count, p.bad_cap);
+    const unsigned count = min(p.bad_count[round], p.bad_cap);
     for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < count; idx += gridDim.x * blockDim.x) {
         const long long t = p.bad_list[idx];
         const int lane = (int)(t / p.nseg), seg = (int)(t - (long long)lane * p.nseg);
@@ -466,9 +536,6 @@ __global__ void __launch_bounds__(128) k_agc_refine(const BackendParams p)
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(p.fixups + 2, (unsigned long long)count);
 }
-
-// the list is consumed: empty it for the next verification round
-__global__ void k_backend_list_reset(const BackendParams p) { *p.bad_count = 0; }
 
 // one CTA per lane: re-run the misses in stream order (rare), store the lane's gain state
 template <bool EXACT>
@@ -529,14 +596,14 @@ __global__ void k_agc_fixup(const BackendParams p)
 template <bool AGC, bool FM, bool EXACT>
 __global__ void __launch_bounds__(256) k_be_emit(const BackendParams p)
 {
-    const long long nw = (long long)p.nlanes * p.nwords;
-    const int l = threadIdx.x & 31;
-    for (long long t = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; t < nw; t += ((long long)gridDim.x * blockDim.x) >> 5) {
-        const int lane = (int)(t / p.nwords), w = (int)(t - (long long)lane * p.nwords);
+    const int lane = blockIdx.y, l = threadIdx.x & 31;
+    const float2 *__restrict__ x = p.ydc + (long long)lane * p.ydc_stride;
+    const float *__restrict__ gp = p.gpost + (long long)lane * p.pw_stride;
+    unsigned *exb = p.exbits + (long long)lane * p.nwords, *sgr = p.sgnr + (long long)lane * p.nwords, *sgi = p.sgni + (long long)lane * p.nwords;
+    const int wstep = (int)((gridDim.x * blockDim.x) >> 5);
+    for (int w = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5); w < p.nwords; w += wstep) {
         const int i = w * 32 + l;
         const bool in = i < p.n;
-        const float2 *x = p.ydc + (long long)lane * p.ydc_stride;
-        const float *gp = p.gpost + (long long)lane * p.pw_stride;
         float2 y = cf(0.f, 0.f), yp = cf(0.f, 0.f);
         float ga = 1.f;
         if (in) {
@@ -556,11 +623,11 @@ __global__ void __launch_bounds__(256) k_be_emit(const BackendParams p)
         }
         if (AGC) {
             const unsigned ex = __ballot_sync(0xffffffffu, in && ga < p.g_thr);       // rssi = -20 log10(g) > threshold
-            if (l == 0) p.exbits[(long long)lane * p.nwords + w] = ex;
+            if (l == 0) exb[w] = ex;
             if (FM) {
                 const unsigned sr = __ballot_sync(0xffffffffu, in && (__float_as_int(y.x) < 0));
                 const unsigned si = __ballot_sync(0xffffffffu, in && (__float_as_int(y.y) < 0));
-                if (l == 0) { p.sgnr[(long long)lane * p.nwords + w] = sr; p.sgni[(long long)lane * p.nwords + w] = si; }
+                if (l == 0) { sgr[w] = sr; sgi[w] = si; }
             }
         }
         if (in) {
@@ -761,8 +828,7 @@ __global__ void k_lane_sum(const float *__restrict__ in, long long lane_stride, 
 template <class Launch>
 inline void be_launch_prep(Launch &launch, const DcParams &d)
 {
-    const long long warps = (long long)d.nlanes * d.ngrp;
-    const dim3 grid((unsigned)((warps + 7) / 8)), block(256);
+    const dim3 grid((unsigned)((d.ngrp + 7) / 8), d.nlanes), block(256);
     if (d.G == 128)     launch(k_be_prep<4>, grid, block, 0, d);
     else if (d.G == 64) launch(k_be_prep<2>, grid, block, 0, d);
     else                launch(k_be_prep<1>, grid, block, 0, d);
@@ -779,27 +845,46 @@ inline void be_launch_dc(Launch &launch, const DcParams &d, bool apply)
     if (apply) be_launch_prep(launch, d);
 }
 
-template <bool EXACT, class Launch>
-inline void be_launch_gain(Launch &launch, const BackendParams &b, unsigned gb)
+// threads per CTA of the staged chain kernel for segment length L (0: not applicable) and its shared memory
+inline int be_chain_threads(int L, int W)
 {
-    launch(k_agc_chain<EXACT>, dim3(gb), dim3(128), 0, b);
+    if (L < 32 || (L & (L - 1)) || L > 1024 || W % L) return 0;
+    return L <= 128 ? 128 : L == 256 ? 64 : 32;
+}
+inline size_t be_chain_smem(int L, int W, int T)
+{
+    const size_t len = (size_t)W + (size_t)T * L;
+    return (len + len / L + 8) * sizeof(float);
+}
+
+template <bool EXACT, class Launch>
+inline void be_launch_gain(Launch &launch, const BackendParams &b)
+{
+    int T = be_chain_threads(b.L, b.W);
+    if (T && be_chain_smem(b.L, b.W, T) > 200 * 1024) T = 0;
+    if (T) {
+        int lgL = 0;
+        while ((1 << lgL) < b.L) lgL++;
+        launch(k_agc_chain_staged<EXACT>, dim3((b.nseg + T - 1) / T, b.nlanes), dim3(T), be_chain_smem(b.L, b.W, T), b, lgL);
+    } else {
+        launch(k_agc_chain<EXACT>, dim3((b.nseg + 127) / 128, b.nlanes), dim3(128), 0, b);
+    }
     // two rounds of verify + parallel refine (a run of consecutive misses needs one round per level of
     // inaccuracy handed down the run; an empty list costs a few microseconds), then the in-order repair
-    launch(k_agc_verify, dim3(gb), dim3(128), 0, b, 0);
+    const dim3 gv((b.nseg + 127) / 128, b.nlanes);
+    launch(k_agc_verify, gv, dim3(128), 0, b, 0);
     launch.debug_after_verify(b);
-    launch(k_agc_refine<EXACT>, dim3(64), dim3(128), 0, b);
-    launch(k_backend_list_reset, dim3(1), dim3(1), 0, b);
-    launch(k_agc_verify, dim3(gb), dim3(128), 0, b, 0);
-    launch(k_agc_refine<EXACT>, dim3(64), dim3(128), 0, b);
-    launch(k_agc_verify, dim3(gb), dim3(128), 0, b, 1);
+    launch(k_agc_refine<EXACT>, dim3(64), dim3(128), 0, b, 0);
+    launch(k_agc_verify, gv, dim3(128), 0, b, 1);
+    launch(k_agc_refine<EXACT>, dim3(64), dim3(128), 0, b, 1);
+    launch(k_agc_verify, gv, dim3(128), 0, b, 2);
     launch(k_agc_fixup<EXACT>, dim3(b.nlanes), dim3(128), 0, b);
 }
 
 template <bool AGC, bool FM, class Launch>
 inline void be_launch_emit(Launch &launch, const BackendParams &b)
 {
-    const long long words = (long long)b.nlanes * b.nwords;
-    const dim3 grid((unsigned)((words + 7) / 8)), block(256);
+    const dim3 grid((unsigned)std::min(65535, (b.nwords + 7) / 8), b.nlanes), block(256);
     if (b.exact_math) launch(k_be_emit<AGC, FM, true>, grid, block, 0, b);
     else              launch(k_be_emit<AGC, FM, false>, grid, block, 0, b);
 }
@@ -810,9 +895,8 @@ inline void be_launch(Launch &launch, const BackendParams &b)
 {
     const long long segs = (long long)b.nlanes * b.nseg;
     const unsigned gb = (unsigned)((segs + 127) / 128);
-    launch(k_be_first, dim3((b.nlanes + 127) / 128), dim3(128), 0, b);
     if (b.has_agc) {
-        if (b.exact_math) be_launch_gain<true>(launch, b, gb); else be_launch_gain<false>(launch, b, gb);
+        if (b.exact_math) be_launch_gain<true>(launch, b); else be_launch_gain<false>(launch, b);
         if (b.demod == 1) be_launch_emit<true, true>(launch, b); else be_launch_emit<true, false>(launch, b);
         launch(k_backend_fsm, dim3(gb), dim3(128), 0, b);
         launch(k_backend_fsm_verify, dim3(gb), dim3(128), 0, b);
@@ -822,6 +906,7 @@ inline void be_launch(Launch &launch, const BackendParams &b)
             launch(k_backend_gate, dim3((unsigned)((words + 127) / 128)), dim3(128), 0, b);
         }
     } else {
+        launch(k_be_first, dim3((b.nlanes + 127) / 128), dim3(128), 0, b);
         if (b.demod == 1) be_launch_emit<false, true>(launch, b); else be_launch_emit<false, false>(launch, b);
     }
 }

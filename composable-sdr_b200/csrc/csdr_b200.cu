@@ -318,7 +318,9 @@ struct Backend {
             c.sync();
         }
         fixups.ensure(3 * sizeof(unsigned long long)); CK(cudaMemsetAsync(fixups.p, 0, fixups.cap, c.stream));
-        bad_list.ensure(sizeof(unsigned) * 65536); bad_count.ensure(sizeof(unsigned)); CK(cudaMemsetAsync(bad_count.p, 0, bad_count.cap, c.stream));
+        bad_list.ensure(sizeof(unsigned) * 65536); bad_count.ensure(2 * sizeof(unsigned)); CK(cudaMemsetAsync(bad_count.p, 0, bad_count.cap, c.stream));
+        CK(cudaFuncSetAttribute(k_agc_chain_staged<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        CK(cudaFuncSetAttribute(k_agc_chain_staged<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         c.sync();
     }
     struct Launcher {
@@ -400,6 +402,9 @@ struct Backend {
             }
             W = W_cur;
         }
+        // the staged gain-loop kernel wants the warm-up in whole segments
+        if (has_agc && be_chain_threads(L, (W + L - 1) / L * L) && be_chain_smem(L, (W + L - 1) / L * L, be_chain_threads(L, (W + L - 1) / L * L)) <= 200 * 1024)
+            W = (W + L - 1) / L * L;
         int ngrp = (n + G - 1) / G, nseg = (n + L - 1) / L, nwords = (n + 31) / 32;
         size_t segs = (size_t)nlanes * nseg;
         ss.ensure(sizeof(SegState) * segs); se.ensure(sizeof(SegState) * segs);

@@ -121,7 +121,7 @@ long long emu_backend(int nlanes, long long lane_stride, int has_dc, float dc_al
         int nwords = (nx + 31) / 32;
         std::vector<unsigned> exb((size_t)nlanes * nwords), gb((size_t)nlanes * nwords), pg(nlanes, 0), ps(nlanes, 0);
         std::vector<unsigned> sgr((size_t)nlanes * nwords), sgi((size_t)nlanes * nwords), fb(2 * nlanes, 0xffffffffu), blist(4096);
-        unsigned bcount = 0;
+        unsigned bcount[2] = {0, 0};
         DcParams d{};
         d.in = x + pos; d.in_lane_stride = lane_stride; d.n = nx; d.nlanes = nlanes; d.G = G; d.ngrp = ngrp; d.nblk = nblk;
         d.has_dc = has_dc; d.out = has_dc ? ydc.data() : nullptr; d.out_lane_stride = pws;
@@ -147,7 +147,7 @@ long long emu_backend(int nlanes, long long lane_stride, int has_dc, float dc_al
         b.nwords = nwords; b.FW = (1000 + 8 + L - 1) / L;
         b.exbits = exb.data(); b.gatebits = gb.data(); b.fsm_start = fs.data(); b.fsm_end = fe.data();
         b.prev_gate = pg.data(); b.prev_sign = ps.data(); b.sgnr = sgr.data(); b.sgni = sgi.data();
-        b.first_bad = fb.data(); b.fixups = fixups2; b.bad_list = blist.data(); b.bad_count = &bcount; b.bad_cap = 4096;
+        b.first_bad = fb.data(); b.fixups = fixups2; b.bad_list = blist.data(); b.bad_count = bcount; b.bad_cap = 4096;
         be_launch(launch, b);
         if (dbg) for (int i = 0; i < nseg; i++) { float *d4 = dbg + 4 * i; d4[0] = ss[i].g; d4[1] = ss[i].y2p; d4[2] = se[i].g; d4[3] = se[i].y2p; }
         pos += nx;

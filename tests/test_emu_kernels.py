@@ -58,7 +58,8 @@ def test_frontend_seek_with_warmup(orc, emu):
     assert_parity(y[100:], tail[100:], what="seek")
 
 
-@pytest.mark.parametrize("kw", [dict(), dict(demod=0), dict(has_dc=0), dict(has_agc=0, demod=0)])
+@pytest.mark.parametrize("kw", [dict(), dict(demod=0), dict(has_dc=0), dict(has_agc=0, demod=0), dict(L=128, W=384),
+                                dict(L=64, W=384, G=64, demod=0), dict(L=256, W=512, has_dc=0), dict(has_agc=0)])
 def test_backend_matches_oracle(orc, emu, kw):
     n = 30000
     t = np.arange(n)
