@@ -4,7 +4,7 @@ BASELINE's full sizes.  Tolerance: tests/util.py."""
 import numpy as np
 import pytest
 
-from util import REL_TOL_AFTER_DCBLOCK, assert_parity, chunked, make_signal, snr_db
+from util import REL_TOL_AFTER_DCBLOCK, REL_TOL_FM_NOISE, assert_parity, chunked, make_signal, snr_db
 
 pytestmark = pytest.mark.gpu
 
@@ -79,7 +79,7 @@ def test_config3_channelizer_per_channel_fm(cs, orc):
     for c in range(16):
         assert len(outs[c]) == len(ref[c])
         assert np.count_nonzero((outs[c] == 0) != (ref[c] == 0)) <= 2
-        assert_parity(outs[c], ref[c], rel=3e-4, what=f"config 3 channel {c}")
+        assert_parity(outs[c], ref[c], rel=REL_TOL_FM_NOISE, period=1 / 0.3, what=f"config 3 channel {c}")
 
 
 def test_config3_raw_channels_and_mix(cs, orc):
@@ -90,7 +90,7 @@ def test_config3_raw_channels_and_mix(cs, orc):
         assert_parity(outs[c], ref[c], what=f"config 3 DeNo channel {c}")
     refm = orc.Chain(2.56e6, 0.0, 0.0, orc.DEMOD_NBFM, 0.3, -40.0, 16, True).process(x)[0]
     m = run_chain(cs.Chain(2.56e6, demod=cs.DeNBFM(0.3), agc=-40.0, channels=16, mix_channels=True), x, [100000])[0]
-    assert_parity(m, refm, rel=3e-4, what="config 3 --mix")
+    assert_parity(m, refm, rel=REL_TOL_FM_NOISE, what="config 3 --mix")
 
 
 def test_config4_wideband_1024_channels_mix(cs, orc):

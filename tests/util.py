@@ -15,6 +15,10 @@ SNR_DB = 80.0
 # discriminator turns that into ~5e-3 rad.  Any two float32 evaluation orders of liquid's recurrence differ by this
 # much.  Such outputs are held to SNR >= 80 dB and a peak-relative error of 5e-3.
 REL_TOL_AFTER_DCBLOCK = 5e-3
+# FM discriminator on a channel that carries noise or a weak signal: arg(conj(r[n-1]) r[n]) is ill-conditioned wherever
+# |r[n-1] r[n]| is small (the float32 rounding of the channelizer, ~1e-7 of the channel's level, is divided by that
+# product), so single samples may differ by ~1e-3 of the +-pi range while the SNR stays above 80 dB
+REL_TOL_FM_NOISE = 5e-3
 
 
 def snr_db(y, ref):
