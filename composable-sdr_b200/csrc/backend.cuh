@@ -226,50 +226,55 @@ __global__ void __launch_bounds__(1024) k_dc_carry(const DcParams p)
 template <int S>
 __global__ void __launch_bounds__(256) k_be_prep(const DcParams p)
 {
-    const int lane = blockIdx.y, l = threadIdx.x & 31, j = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
-    if (j >= p.ngrp) return;                                             // whole warps leave together
-    const float2 *x = p.in + (long long)lane * p.in_lane_stride;
-    const int i0 = j * p.G + l * S;
-    float2 v[S];
-    dc_load<S>(x, p.n, i0, v);
-    if (p.has_dc) {
-        double ar = 0.0, ai = 0.0;
+    const int lane = blockIdx.y, l = threadIdx.x & 31;
+    const float2 *__restrict__ x = p.in + (long long)lane * p.in_lane_stride;
+    float2 *__restrict__ yo = p.out ? p.out + (long long)lane * p.out_lane_stride : nullptr;
+    float *__restrict__ wo = p.pw ? p.pw + (long long)lane * p.pw_stride : nullptr;
+    const int jstep = (int)((gridDim.x * blockDim.x) >> 5);
+    // several groups per warp: the pointer set-up above is paid once
+    for (int j = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5); j < p.ngrp; j += jstep) {     // warp-uniform
+        const int i0 = j * p.G + l * S;
+        float2 v[S];
+        dc_load<S>(x, p.n, i0, v);
+        if (p.has_dc) {
+            double ar = 0.0, ai = 0.0;
 #pragma unroll
-        for (int q = 0; q < S; q++) { ar = ar * p.c + (double)v[q].x; ai = ai * p.c + (double)v[q].y; }
-        double m = p.cS[0];
-        dc_warp_scan(ar, ai, m, p.cS);
-        // state before this lane's samples = map of lanes 0..l-1 applied to the group's entry state
-        const double2 V = dc_state_at(p.Vloc, p.carry, p.powA, p.ngrp, p.nblk, lane, j);
-        double er = __shfl_up_sync(0xffffffffu, ar, 1), ei = __shfl_up_sync(0xffffffffu, ai, 1), em = __shfl_up_sync(0xffffffffu, m, 1);
-        if (l == 0) { er = 0.0; ei = 0.0; em = 1.0; }
-        float v1r = (float)(er + V.x * em), v1i = (float)(ei + V.y * em);
+            for (int q = 0; q < S; q++) { ar = ar * p.c + (double)v[q].x; ai = ai * p.c + (double)v[q].y; }
+            double m = p.cS[0];
+            dc_warp_scan(ar, ai, m, p.cS);
+            // state before this lane's samples = map of lanes 0..l-1 applied to the group's entry state
+            const double2 V = dc_state_at(p.Vloc, p.carry, p.powA, p.ngrp, p.nblk, lane, j);
+            double er = __shfl_up_sync(0xffffffffu, ar, 1), ei = __shfl_up_sync(0xffffffffu, ai, 1), em = __shfl_up_sync(0xffffffffu, m, 1);
+            if (l == 0) { er = 0.0; ei = 0.0; em = 1.0; }
+            float v1r = (float)(er + V.x * em), v1i = (float)(ei + V.y * em);
 #pragma unroll
-        for (int q = 0; q < S; q++) {
-            const float v0r = __fsub_rn(v[q].x, __fmul_rn(p.a1, v1r));
-            const float v0i = __fsub_rn(v[q].y, __fmul_rn(p.a1, v1i));
-            v[q] = cf(__fsub_rn(v0r, v1r), __fsub_rn(v0i, v1i));
-            v1r = v0r; v1i = v0i;
+            for (int q = 0; q < S; q++) {
+                const float v0r = __fsub_rn(v[q].x, __fmul_rn(p.a1, v1r));
+                const float v0i = __fsub_rn(v[q].y, __fmul_rn(p.a1, v1i));
+                v[q] = cf(__fsub_rn(v0r, v1r), __fsub_rn(v0i, v1i));
+                v1r = v0r; v1i = v0i;
+            }
         }
-    }
-    if (p.out) {
-        float2 *y = p.out + (long long)lane * p.out_lane_stride + i0;
-        if (S == 4 && i0 + S <= p.n && (reinterpret_cast<uintptr_t>(y) & 15) == 0) {
-            reinterpret_cast<float4 *>(y)[0] = make_float4(v[0].x, v[0].y, v[1 % S].x, v[1 % S].y);
-            reinterpret_cast<float4 *>(y)[1] = make_float4(v[2 % S].x, v[2 % S].y, v[3 % S].x, v[3 % S].y);
-        } else {
+        if (yo) {
+            float2 *y = yo + i0;
+            if (S == 4 && i0 + S <= p.n && (reinterpret_cast<uintptr_t>(y) & 15) == 0) {
+                reinterpret_cast<float4 *>(y)[0] = make_float4(v[0].x, v[0].y, v[1 % S].x, v[1 % S].y);
+                reinterpret_cast<float4 *>(y)[1] = make_float4(v[2 % S].x, v[2 % S].y, v[3 % S].x, v[3 % S].y);
+            } else {
 #pragma unroll
-            for (int q = 0; q < S; q++) if (i0 + q < p.n) y[q] = v[q];
+                for (int q = 0; q < S; q++) if (i0 + q < p.n) y[q] = v[q];
+            }
         }
-    }
-    if (p.pw) {
-        float *w = p.pw + (long long)lane * p.pw_stride + i0;
-        float e[S];
+        if (wo) {
+            float *w = wo + i0;
+            float e[S];
 #pragma unroll
-        for (int q = 0; q < S; q++) e[q] = __fadd_rn(__fmul_rn(v[q].x, v[q].x), __fmul_rn(v[q].y, v[q].y));
-        if (S == 4 && i0 + S <= p.n) *reinterpret_cast<float4 *>(w) = make_float4(e[0], e[1 % S], e[2 % S], e[3 % S]);   // pw_stride % 4 == 0
-        else {
+            for (int q = 0; q < S; q++) e[q] = __fadd_rn(__fmul_rn(v[q].x, v[q].x), __fmul_rn(v[q].y, v[q].y));
+            if (S == 4 && i0 + S <= p.n) *reinterpret_cast<float4 *>(w) = make_float4(e[0], e[1 % S], e[2 % S], e[3 % S]);   // pw_stride % 4 == 0
+            else {
 #pragma unroll
-            for (int q = 0; q < S; q++) if (i0 + q < p.n) w[q] = e[q];
+                for (int q = 0; q < S; q++) if (i0 + q < p.n) w[q] = e[q];
+            }
         }
     }
 }
@@ -339,13 +344,26 @@ __device__ __forceinline__ float be_ex2(float x)
 #endif
 }
 template <bool EXACT>
-__device__ __forceinline__ void agc_step(const BackendParams &p, float &g, float &y2p, float pw)
+__device__ __forceinline__ void agc_step(const BackendParams &p, float &g, float &g2, float &y2p, float pw)
 {
-    const float y2 = __fmul_rn(__fmul_rn(g, g), pw);
-    y2p = fmaf(p.one_minus_alpha_f, y2p, __fmul_rn(p.alpha, y2));
-    const float f = EXACT ? expf(p.neg_half_alpha * logf(y2p)) : be_ex2(p.neg_half_alpha * be_lg2(y2p));
-    g *= (y2p > 1e-6f) ? f : 1.0f;
-    g = fminf(g, 1e6f);
+    if (EXACT) {
+        const float y2 = __fmul_rn(__fmul_rn(g, g), pw);
+        y2p = fmaf(p.one_minus_alpha_f, y2p, __fmul_rn(p.alpha, y2));
+        const float f = expf(p.neg_half_alpha * logf(y2p));
+        g *= (y2p > 1e-6f) ? f : 1.0f;
+        g = fminf(g, 1e6f);
+    } else {
+        // the recurrence closes through g^2, so g^2 is carried as a state of its own and updated with the squared
+        // factor (a second, independent exp2): the dependent chain per sample is FMA -> lg2 -> mul -> ex2 -> mul -> min,
+        // and the gain itself only trails it.  (g2 / g^2 drifts by rounding, ~1e-7 sqrt(samples); it is re-derived from
+        // g at the start of every segment.)
+        y2p = fmaf(__fmul_rn(p.alpha, pw), g2, __fmul_rn(p.one_minus_alpha_f, y2p));
+        const float lg = be_lg2(y2p);
+        const bool ok = y2p > 1e-6f;
+        const float f2 = be_ex2(__fmul_rn(2.0f * p.neg_half_alpha, lg)), f = be_ex2(__fmul_rn(p.neg_half_alpha, lg));
+        g2 = fminf(ok ? __fmul_rn(g2, f2) : g2, 1e12f);
+        g = fminf(ok ? __fmul_rn(g, f) : g, 1e6f);
+    }
 }
 
 // run samples [i0, i1) of one lane's power sequence; EMIT: store the gain after every sample.  i0 is a multiple
@@ -356,6 +374,7 @@ __device__ __forceinline__ void agc_run(const BackendParams &p, int lane, float 
     const float *__restrict__ pw = p.pw + (long long)lane * p.pw_stride;
     float *__restrict__ go = p.gpost + (long long)lane * p.pw_stride;
     int i = i0;
+    float g2 = __fmul_rn(g, g);
     if (i + 8 <= i1) {
         const float4 *p4 = reinterpret_cast<const float4 *>(pw + i);
         float4 na = __ldg(p4), nb = __ldg(p4 + 1);
@@ -364,7 +383,7 @@ __device__ __forceinline__ void agc_run(const BackendParams &p, int lane, float 
             if (i + 16 <= i1) { const float4 *q4 = reinterpret_cast<const float4 *>(pw + i + 8); na = __ldg(q4); nb = __ldg(q4 + 1); }
             float o[8];
 #pragma unroll
-            for (int k = 0; k < 8; k++) { agc_step<EXACT>(p, g, y2p, c[k]); o[k] = g; }
+            for (int k = 0; k < 8; k++) { agc_step<EXACT>(p, g, g2, y2p, c[k]); o[k] = g; }
             if (EMIT) {
                 float4 *o4 = reinterpret_cast<float4 *>(go + i);
                 o4[0] = make_float4(o[0], o[1], o[2], o[3]);
@@ -372,7 +391,7 @@ __device__ __forceinline__ void agc_run(const BackendParams &p, int lane, float 
             }
         }
     }
-    for (; i < i1; i++) { agc_step<EXACT>(p, g, y2p, pw[i]); if (EMIT) go[i] = g; }
+    for (; i < i1; i++) { agc_step<EXACT>(p, g, g2, y2p, pw[i]); if (EMIT) go[i] = g; }
 }
 
 __device__ __forceinline__ bool be_close(float a, float b, float atol = 0.f)
@@ -466,12 +485,13 @@ __global__ void __launch_bounds__(128) k_agc_chain_staged(const BackendParams p,
             agc_guess(e * (1.0f / 16.0f), g, y2p);
         }
         const int uw = b0 - tO;
+        float g2 = __fmul_rn(g, g);
         while (u < uw) {                                      // warm-up, one L-block (or what is left of it) at a time
             const int ue = min(((u >> lgL) + 1) << lgL, uw);
             const float *q = sm + u + (u >> lgL);
             const int cnt = ue - u;
 #pragma unroll 8
-            for (int k = 0; k < cnt; k++) agc_step<EXACT>(p, g, y2p, q[k]);
+            for (int k = 0; k < cnt; k++) agc_step<EXACT>(p, g, g2, y2p, q[k]);
             u = ue;
         }
         SegState s0; s0.g = g; s0.y2p = y2p;
@@ -481,8 +501,9 @@ __global__ void __launch_bounds__(128) k_agc_chain_staged(const BackendParams p,
     if (live) {
         const int u = b0 - tO, cnt = b1 - b0;                 // one L-block
         float *q = sm + u + (u >> lgL);
+        float g2 = __fmul_rn(g, g);
 #pragma unroll 8
-        for (int k = 0; k < cnt; k++) { agc_step<EXACT>(p, g, y2p, q[k]); q[k] = g; }
+        for (int k = 0; k < cnt; k++) { agc_step<EXACT>(p, g, g2, y2p, q[k]); q[k] = g; }
         SegState s1; s1.g = g; s1.y2p = y2p;
         p.seg_end[(long long)lane * p.nseg + seg] = s1;
     }
@@ -600,10 +621,14 @@ __global__ void __launch_bounds__(256) k_be_emit(const BackendParams p)
     const float2 *__restrict__ x = p.ydc + (long long)lane * p.ydc_stride;
     const float *__restrict__ gp = p.gpost + (long long)lane * p.pw_stride;
     unsigned *exb = p.exbits + (long long)lane * p.nwords, *sgr = p.sgnr + (long long)lane * p.nwords, *sgi = p.sgni + (long long)lane * p.nwords;
+    float *__restrict__ of = (float *)p.out + (long long)lane * p.out_lane_stride;
+    float2 *__restrict__ oc = (float2 *)p.out + (long long)lane * p.out_lane_stride;
+    const float g_thr = p.g_thr, fm_ref = p.fm_ref;
+    const int n = p.n, nwords = p.nwords;
     const int wstep = (int)((gridDim.x * blockDim.x) >> 5);
-    for (int w = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5); w < p.nwords; w += wstep) {
+    for (int w = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5); w < nwords; w += wstep) {
         const int i = w * 32 + l;
-        const bool in = i < p.n;
+        const bool in = i < n;
         float2 y = cf(0.f, 0.f), yp = cf(0.f, 0.f);
         float ga = 1.f;
         if (in) {
@@ -622,7 +647,7 @@ __global__ void __launch_bounds__(256) k_be_emit(const BackendParams p)
             }
         }
         if (AGC) {
-            const unsigned ex = __ballot_sync(0xffffffffu, in && ga < p.g_thr);       // rssi = -20 log10(g) > threshold
+            const unsigned ex = __ballot_sync(0xffffffffu, in && ga < g_thr);       // rssi = -20 log10(g) > threshold
             if (l == 0) exb[w] = ex;
             if (FM) {
                 const unsigned sr = __ballot_sync(0xffffffffu, in && (__float_as_int(y.x) < 0));
@@ -634,11 +659,11 @@ __global__ void __launch_bounds__(256) k_be_emit(const BackendParams p)
             if (FM) {
                 const float re = __fadd_rn(__fmul_rn(yp.x, y.x), __fmul_rn(yp.y, y.y));
                 const float im = __fsub_rn(__fmul_rn(yp.x, y.y), __fmul_rn(yp.y, y.x));
-                ((float *)p.out)[(long long)lane * p.out_lane_stride + i] = (EXACT ? atan2f(im, re) : be_atan2(im, re)) * p.fm_ref;
+                of[i] = (EXACT ? atan2f(im, re) : be_atan2(im, re)) * fm_ref;
             } else {
-                ((float2 *)p.out)[(long long)lane * p.out_lane_stride + i] = y;
+                oc[i] = y;
             }
-            if (i == p.n - 1) { p.lane[lane].fm_re = y.x; p.lane[lane].fm_im = y.y; }
+            if (i == n - 1) { p.lane[lane].fm_re = y.x; p.lane[lane].fm_im = y.y; }
         }
     }
 }
@@ -828,7 +853,7 @@ __global__ void k_lane_sum(const float *__restrict__ in, long long lane_stride, 
 template <class Launch>
 inline void be_launch_prep(Launch &launch, const DcParams &d)
 {
-    const dim3 grid((unsigned)((d.ngrp + 7) / 8), d.nlanes), block(256);
+    const dim3 grid((unsigned)std::max(1, std::min(65535, (d.ngrp + 63) / 64)), d.nlanes), block(256);   // ~8 groups per warp
     if (d.G == 128)     launch(k_be_prep<4>, grid, block, 0, d);
     else if (d.G == 64) launch(k_be_prep<2>, grid, block, 0, d);
     else                launch(k_be_prep<1>, grid, block, 0, d);
@@ -884,7 +909,7 @@ inline void be_launch_gain(Launch &launch, const BackendParams &b)
 template <bool AGC, bool FM, class Launch>
 inline void be_launch_emit(Launch &launch, const BackendParams &b)
 {
-    const dim3 grid((unsigned)std::min(65535, (b.nwords + 7) / 8), b.nlanes), block(256);
+    const dim3 grid((unsigned)std::max(1, std::min(65535, (b.nwords + 127) / 128)), b.nlanes), block(256);   // ~16 words per warp
     if (b.exact_math) launch(k_be_emit<AGC, FM, true>, grid, block, 0, b);
     else              launch(k_be_emit<AGC, FM, false>, grid, block, 0, b);
 }
