@@ -54,6 +54,7 @@ SIGNATURES = {
     "csdr_chain_cuda_stream": (_vp, [_vp]), "csdr_chain_profile": (_i, [_vp, _i]),
     "csdr_chain_frontend_ms": (C.c_double, [_vp, C.POINTER(C.c_uint64)]), "csdr_chain_agc_fixups": (C.c_uint64, [_vp]),
     "csdr_chain_agc_counters": (_i, [_vp, C.POINTER(C.c_uint64)]),
+    "csdr_chain_agc_plan": (_i, [_vp, C.POINTER(C.c_int)]),
 }
 
 OPT_VCO_DIRECT, OPT_AMPMODEM_PLL, OPT_RESAMP_FC_OLD, OPT_AGC_SEGMENT, OPT_AGC_WARMUP = 0, 1, 2, 3, 4

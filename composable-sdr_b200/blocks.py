@@ -490,6 +490,12 @@ class Chain:
         self.L.csdr_chain_agc_counters(self.h, v)
         return int(v[0]), int(v[1]), int(v[2])
 
+    def agc_plan(self):
+        """(segment length, warm-up length) of the gain-loop speculation in the last call"""
+        v = (C.c_int * 2)()
+        self.L.csdr_chain_agc_plan(self.h, v)
+        return int(v[0]), int(v[1])
+
     def print(self):
         self.L.csdr_chain_print(self.h)
 

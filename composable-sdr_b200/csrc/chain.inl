@@ -373,5 +373,12 @@ int csdr_chain_agc_counters(csdr_chain q, uint64_t out[3])
     return 0;
     API_END(-1)
 }
+int csdr_chain_agc_plan(csdr_chain q, int out[2])
+{
+    API_BEGIN
+    out[0] = q->be.last_L; out[1] = q->be.last_W;
+    return 0;
+    API_END(-1)
+}
 
 }  // extern "C"

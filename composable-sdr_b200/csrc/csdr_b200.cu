@@ -30,7 +30,7 @@ namespace {
 
 thread_local std::string t_err;
 std::atomic<unsigned long long> g_launches{0};
-int g_options[16] = {0, 1, 0, 512, 384, 0, 0, 0, 0, 3};
+int g_options[16] = {0, 1, 0, 512, 384, 0, 0, 0, 0, 1};
 
 void set_err(const std::string &s) { t_err = s; }
 void clear_err() { t_err.clear(); }
@@ -140,7 +140,7 @@ struct Frontend {
     FrontendGeometry geo;
     int nstreams = 1;
     DevBuf hist[2]; int cur = 0;
-    DevBuf bank, bank16;
+    DevBuf bank;
     FrontendCursor cursor;
     int mix_mode = 0; uint32_t theta0 = 0, dtheta = 0; int quantize = 1;
     void (*kernel)(FrontendParams) = k_frontend;
@@ -181,40 +181,23 @@ struct Frontend {
         kernel = k_frontend;
         if (geo.std_kernel && geo.variant == 0) {
             switch (ms.S) {
-            case 1: kernel = k_frontend_std<1, 0>; break;
-            case 2: kernel = k_frontend_std<2, 0>; break;
-            case 3: kernel = k_frontend_std<3, 0>; break;
-            case 4: kernel = k_frontend_std<4, 0>; break;
-            case 5: kernel = k_frontend_std<5, 0>; break;
-            case 6: kernel = k_frontend_std<6, 0>; break;
+            case 1: kernel = k_frontend_std<1>; break;
+            case 2: kernel = k_frontend_std<2>; break;
+            case 3: kernel = k_frontend_std<3>; break;
+            case 4: kernel = k_frontend_std<4>; break;
+            case 5: kernel = k_frontend_std<5>; break;
+            case 6: kernel = k_frontend_std<6>; break;
             default: throw CudaError{"frontend: no specialised kernel for this stage count"};
-            }
-        } else if (geo.std_kernel && geo.variant == 3) {
-            switch (ms.S) {
-            case 1: kernel = k_frontend_v3<1>; break;
-            case 2: kernel = k_frontend_v3<2>; break;
-            case 3: kernel = k_frontend_v3<3>; break;
-            case 4: kernel = k_frontend_v3<4>; break;
-            case 5: kernel = k_frontend_v3<5>; break;
-            case 6: kernel = k_frontend_v3<6>; break;
-            default: throw CudaError{"frontend: no direct-read kernel for this stage count"};
-            }
-        } else if (geo.std_kernel && geo.variant == 2) {
-            switch (ms.S) {
-            case 2: kernel = k_frontend_v2<2>; break;
-            case 3: kernel = k_frontend_v2<3>; break;
-            case 4: kernel = k_frontend_v2<4>; break;
-            case 5: kernel = k_frontend_v2<5>; break;
-            case 6: kernel = k_frontend_v2<6>; break;
-            default: throw CudaError{"frontend: no fused-mix kernel for this stage count"};
             }
         } else if (geo.std_kernel) {
             switch (ms.S) {
-            case 1: kernel = k_frontend_std<1, 1>; break;
-            case 2: kernel = k_frontend_std<2, 1>; break;
-            case 3: kernel = k_frontend_std<3, 1>; break;
-            case 4: kernel = k_frontend_std<4, 1>; break;
-            default: throw CudaError{"frontend: no TMA-staged kernel for this stage count"};
+            case 1: kernel = k_frontend_direct<1>; break;
+            case 2: kernel = k_frontend_direct<2>; break;
+            case 3: kernel = k_frontend_direct<3>; break;
+            case 4: kernel = k_frontend_direct<4>; break;
+            case 5: kernel = k_frontend_direct<5>; break;
+            case 6: kernel = k_frontend_direct<6>; break;
+            default: throw CudaError{"frontend: no direct-read kernel for this stage count"};
             }
         }
         nstreams = streams;
@@ -222,14 +205,6 @@ struct Frontend {
         for (auto &h : hist) { h.ensure(hb); CK(cudaMemsetAsync(h.p, 0, h.cap, c.stream)); }
         bank.ensure(ms.bank.size() * sizeof(float));
         CK(cudaMemcpyAsync(bank.p, ms.bank.data(), ms.bank.size() * sizeof(float), cudaMemcpyHostToDevice, c.stream));
-        {
-            const size_t rows = ms.bank.size() / kHsub;
-            std::vector<float> b16(rows * 16, 0.f);
-            for (size_t r = 0; r < rows; r++) for (int j = 0; j < kHsub; j++) b16[r * 16 + j] = ms.bank[r * kHsub + j];
-            bank16.ensure(b16.size() * sizeof(float));
-            CK(cudaMemcpyAsync(bank16.p, b16.data(), b16.size() * sizeof(float), cudaMemcpyHostToDevice, c.stream));
-            c.sync();      // b16 goes out of scope
-        }
         CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)geo.smem_bytes));
         fe_threads = geo.std_kernel ? kFeNT : 256;
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kernel, fe_threads, geo.smem_bytes));
@@ -250,7 +225,7 @@ struct Frontend {
         p.x = x; p.hist = hist[cur].as<float2>(); p.y = y; p.hcap = geo.hcap;
         p.x_stride = x_stride; p.y_stride = y_stride;
         p.mix_mode = mix_mode; p.theta0 = theta0; p.dtheta = dtheta; p.quantize = quantize;
-        p.bank = bank.as<float>(); p.bank16 = bank16.as<float>();
+        p.bank = bank.as<float>();
         if (p.ntiles > 0) {
             const int slots = c.sms * ctas_per_sm;      // persistent CTAs: one wave, tiles strided over the grid
             int gx = std::min(p.ntiles, std::max(1, slots / std::max(1, std::min(nstreams, slots))));
@@ -283,7 +258,7 @@ struct Backend {
     int L = 512, W = 384, G = 128; bool fixed_L = false;
     DevBuf lane, Vloc, carry, powA, ss, se, fs, fe, exbits, gatebits, sgnr, sgni, prev_gate, prev_sign, first_bad, bad_list, bad_count, fixups;
     DevBuf ydc, pwbuf, gpost, g_first, y_first;
-    int FW = 3; unsigned long long last_refined = 0;
+    int FW = 3; unsigned long long last_refined = 0; int last_L = 0, last_W = 0;
     // self-tuning warm-up: the counters of every call are copied to pinned memory asynchronously; the next call looks
     // at them (no synchronisation) and lengthens / shortens the warm-up
     unsigned long long *h_counters = nullptr; cudaEvent_t ev_counters = nullptr; bool counters_pending = false;
@@ -405,6 +380,7 @@ struct Backend {
         // the staged gain-loop kernel wants the warm-up in whole segments
         if (has_agc && be_chain_threads(L, (W + L - 1) / L * L) && be_chain_smem(L, (W + L - 1) / L * L, be_chain_threads(L, (W + L - 1) / L * L)) <= 200 * 1024)
             W = (W + L - 1) / L * L;
+        last_L = L; last_W = W;
         int ngrp = (n + G - 1) / G, nseg = (n + L - 1) / L, nwords = (n + 31) / 32;
         size_t segs = (size_t)nlanes * nseg;
         ss.ensure(sizeof(SegState) * segs); se.ensure(sizeof(SegState) * segs);

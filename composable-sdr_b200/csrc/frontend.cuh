@@ -59,7 +59,6 @@ struct FrontendParams {
     // arbitrary resampler
     unsigned step; int bits;    // npfb = 1<<bits
     const float *bank;          // [npfb][kHsub], bank[i][j] multiplies c[k-j]
-    const float *bank16;        // the same rows padded to 16 floats (16-byte loads through L1)
     unsigned long long ph0;     // resampler phase (liquid's q->phase) before push K0: output o' of this call has
                                 // phase ph0 + o'*step relative to push K0
     int off_bank;               // float offset (in floats) of the bank copy in dynamic smem

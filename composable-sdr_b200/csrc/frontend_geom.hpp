@@ -22,7 +22,6 @@ struct FeGeom {
     int m[kMaxStages] = {}, R[kMaxStages] = {};
     int d[kMaxStages + 1] = {}, n[kMaxStages + 1] = {}, stride[kMaxStages + 1] = {}, off[kMaxStages + 1] = {};
     int total_f2 = 0;     // float2 elements of all level buffers
-    int off_raw = 0;      // float2 offset of the raw staging buffer (n[S] samples) the bulk copy lands in, 0 = none
     int hcap = 0;         // raw-sample history the first tile of a chunk may reach back over
 };
 
@@ -32,7 +31,7 @@ __host__ __device__ constexpr int ce_roundup(int v, int m) { return (v + m - 1) 
 // shift = 1: the top level starts one sample early so that pairs (2p, 2p+1) are 16-byte aligned when the chunk is.
 // Sub-array strides are == 2 (mod 16): 64-bit shared accesses are served per half-warp, and with this stride both the
 // loader (pair p -> sub-array p & 7, index p >> 3) and the R = 8 producers (t -> sub-array 4 (t & 1) + c, index t >> 1)
-// touch 16 distinct 8-byte banks per half-warp.  raw = 1 reserves the staging buffer of the bulk-copy pipeline.
+// touch 16 distinct 8-byte banks per half-warp.
 __host__ __device__ constexpr FeGeom fe_make_geom(int S, int Tc, const int *m, int shift, int raw)
 {
     FeGeom g{};
@@ -41,9 +40,9 @@ __host__ __device__ constexpr FeGeom fe_make_geom(int S, int Tc, const int *m, i
     // more threads busy but re-read shared memory more often, and shared-memory bandwidth is what binds this kernel
     // (measured: slots 8/4/2 -> 236 us, 8/8/4 -> 227 us per 2^26 samples).
     for (int s = 0; s < S; s++) { g.m[s] = m[s]; g.R[s] = (s == 0 && S > 1) ? 4 : 8; }
-    // raw = 3: the top level is the raw tile itself, linear, as the bulk copy delivers it; the first half-band stage
+    // raw = 1: the top level is the raw tile itself, linear, as the bulk copy delivers it; the first half-band stage
     // reads (even, odd) pairs from it with 16-byte loads, kFeTopR outputs per thread slot (odd: conflict-free)
-    const int direct = (raw == 3 && S > 0) ? 1 : 0;
+    const int direct = (raw == 1 && S > 0) ? 1 : 0;
     if (direct) g.R[S - 1] = kFeTopR;
     g.n[0] = Tc + kHcPad; g.d[0] = 0;
     for (int L = 0; L < S; L++) {
@@ -55,9 +54,9 @@ __host__ __device__ constexpr FeGeom fe_make_geom(int S, int Tc, const int *m, i
         g.n[L + 1] = ce_roundup(need, mult);
         g.d[L + 1] = 2 * g.d[L] + 1 - 4 * g.m[L] - sh;
     }
-    // raw = 2: the top level has a buffer of its own (the next tile is copied into it while the lower stages of the
-    // current tile run); the lower levels ping-pong between two regions as before
-    const int priv = ((raw == 2 || raw == 3) && S > 0) ? 1 : 0;
+    // the staging buffer is private (the next tile is copied into it while the lower stages of the current tile run);
+    // the de-interleaved levels ping-pong between two regions
+    const int priv = direct;
     int sizeA = 0, sizeB = 0, sizeT = 0;
     for (int L = 1; L <= S; L++) {
         if (direct && L == S) {
@@ -79,7 +78,6 @@ __host__ __device__ constexpr FeGeom fe_make_geom(int S, int Tc, const int *m, i
     for (int L = 1; L <= S; L++) g.off[L] = size0 + sizeT + ((((S - L) & 1) == 0) ? 0 : sizeA);
     if (priv) g.off[S] = size0;
     g.total_f2 = size0 + sizeT + sizeA + sizeB;
-    if (raw == 1 && S > 0) { g.off_raw = g.total_f2; g.total_f2 += g.n[S]; }
     g.hcap = ce_roundup(((1 << S) - 1) + (kHcPad << S) - g.d[S] + 1, 64);
     return g;
 }
@@ -90,32 +88,17 @@ __host__ __device__ constexpr int fe_std_tc(int S)
 {
     return S == 1 ? 1792 : S == 2 ? 896 : S == 3 ? 400 : S == 4 ? 208 : S == 5 ? 96 : 48;
 }
-// variant 1: TMA bulk-copy staging buffer instead of the register prefetch, polyphase bank read through L1, and tiles
-// small enough for three CTAs per SM (<= ~75 KB each)
-__host__ __device__ constexpr int fe_std_tc_tma(int S)
-{
-    return S == 1 ? 1536 : S == 2 ? 768 : S == 3 ? 384 : 192;
-}
-// variant 2: the raw tile is copied asynchronously straight into the top level's layout and mixed by the first
-// half-band stage as it reads; <= ~55 KB per CTA, four CTAs per SM
-__host__ __device__ constexpr int fe_std_tc_v2(int S)
-{
-    return S == 2 ? 768 : S == 3 ? 384 : S == 4 ? 176 : S == 5 ? 64 : 32;
-}
-// variant 3: bulk copy (TMA) into a linear staging buffer that IS the top level; the first stage reads pairs from it
-// and mixes in registers; the polyphase bank lives in shared memory; three CTAs per SM
-__host__ __device__ constexpr int fe_std_tc_v3(int S)
+// variant 1 (k_frontend_direct): bulk copy (TMA) into a linear staging buffer that IS the top level; the first stage
+// reads pairs from it and mixes in registers; three CTAs per SM
+__host__ __device__ constexpr int fe_std_tc_direct(int S)
 {
     return S == 1 ? 1536 : S == 2 ? 768 : S == 3 ? 384 : S == 4 ? 192 : S == 5 ? 64 : 32;
 }
 __host__ __device__ constexpr FeGeom fe_make_geom_std(int S, int variant = 0)
 {
     FeStdM mm{};
-    return variant == 3 ? fe_make_geom(S, fe_std_tc_v3(S), mm.v, 1, 3) : variant == 2 ? fe_make_geom(S, fe_std_tc_v2(S), mm.v, 1, 2)
-         : variant == 1 ? fe_make_geom(S, fe_std_tc_tma(S), mm.v, 1, 1) : fe_make_geom(S, fe_std_tc(S), mm.v, 1, 0);
+    return variant ? fe_make_geom(S, fe_std_tc_direct(S), mm.v, 1, 1) : fe_make_geom(S, fe_std_tc(S), mm.v, 1, 0);
 }
-constexpr int kFeStdMaxS = 6;      // k_frontend_std<S, 0> is instantiated for S = 1..6
-constexpr int kFeTmaMaxS = 4;      // k_frontend_std<S, 1> for S = 1..4
-constexpr int kFeV2MinS = 2;       // k_frontend_v2<S> for S = 2..6 (with one stage the fused mix would redo 2.2x the work)
+constexpr int kFeStdMaxS = 6;      // both kernels are instantiated for S = 1..6
 
 }  // namespace csdr

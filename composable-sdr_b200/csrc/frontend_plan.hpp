@@ -12,9 +12,7 @@ struct FrontendGeometry {
     FrontendParams base;     // geometry + taps filled in; per-call fields zero
     FeGeom geom;
     bool std_kernel = false; // k_frontend_std<S, V> applies (compile-time geometry)
-    int variant = 0;         // 0: register prefetch, 2 CTAs/SM; 1: TMA staging buffer, bank through L1, 3 CTAs/SM;
-                             // 2: asynchronous copy into the top level + mix fused into the first stage, 4 CTAs/SM;
-                             // 3: TMA staging buffer read directly by the first stage (mix in registers), 3 CTAs/SM
+    int variant = 0;         // 0: k_frontend_std (register prefetch + loader pass), 1: k_frontend_direct (TMA staging read in place)
     int hcap = 0;            // raw-sample history the kernel may reach back over
     size_t smem_bytes = 0;
     std::string error;
@@ -41,11 +39,7 @@ inline FrontendGeometry plan_frontend(const design::MsresampPlan &ms, int Tc, bo
         if (m[s] != stdm.v[s]) is_std = false;
     }
     g.std_kernel = is_std;
-    // variant 2 falls back to 1 where it does not apply (a single half-band stage), variant 1 to 0 (S > 4)
-    g.variant = 0;
-    if (is_std && variant == 3) g.variant = 3;
-    else if (is_std && variant == 2 && S >= kFeV2MinS) g.variant = 2;
-    else if (is_std && variant >= 1 && S <= kFeTmaMaxS) g.variant = 1;
+    g.variant = (is_std && variant != 0) ? 1 : 0;
     g.geom = is_std ? fe_make_geom_std(S, g.variant) : fe_make_geom(S, Tc, m, 0, 0);
     const FeGeom &G = g.geom;
     p.S = S; p.Tc = G.Tc;
@@ -57,7 +51,7 @@ inline FrontendGeometry plan_frontend(const design::MsresampPlan &ms, int Tc, bo
     }
     for (int L = 0; L <= S; L++) { p.n[L] = G.n[L]; p.d[L] = G.d[L]; p.stride[L] = G.stride[L]; p.off[L] = G.off[L]; }
     p.off_bank = 2 * G.total_f2;
-    g.smem_bytes = (size_t)G.total_f2 * 8 + ((g.variant == 1 || g.variant == 2) ? 0 : (size_t)(1u << ms.bits) * (kHsub + 1) * 4);
+    g.smem_bytes = (size_t)G.total_f2 * 8 + (size_t)(1u << ms.bits) * (kHsub + 1) * 4;
     p.smem_bytes = (int)g.smem_bytes;
     g.hcap = G.hcap;
     return g;

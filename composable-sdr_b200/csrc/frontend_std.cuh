@@ -1,11 +1,14 @@
-// frontend_std.cuh -- k_frontend_std<S>: the fused front end (see frontend.cuh) specialised at compile time for
-// the half-band plan msresamp_crcf_create(r, 60 dB) always produces (m = 10, 5, 3, 3, ...; the reference hard-codes
-// As = 60, apps/SoapySDR.hs:194).  The whole tile geometry is constexpr (frontend_geom.hpp), so every shared-memory
-// access is base register + immediate, loop trip counts are constants and the half-band taps are read straight
-// from the kernel-parameter constant bank by the FFMAs.  Other plans use the generic k_frontend.
+// frontend_std.cuh -- the fused front end (see frontend.cuh) specialised at compile time for the half-band plan
+// msresamp_crcf_create(r, 60 dB) always produces (m = 10, 5, 3, 3, ...; the reference hard-codes As = 60,
+// apps/SoapySDR.hs:194).  The whole tile geometry is constexpr (frontend_geom.hpp), so every shared-memory access is
+// base register + immediate, loop trip counts are constants and the half-band taps are read straight from the
+// kernel-parameter constant bank by the FFMAs.  Other plans use the generic k_frontend.
 //
-// Raw input tiles are fetched one tile ahead with 16-byte streaming loads held in registers, so the HBM latency is
-// hidden behind the filtering of the previous tile.
+// Two kernels share the stage, bookkeeping and resampler code:
+//   k_frontend_direct<S> (default): the raw tile is bulk-copied (TMA, cp.async.bulk + mbarrier) one tile ahead into a
+//       linear staging buffer and the first half-band stage reads it there, mixing in registers.  3 CTAs per SM.
+//   k_frontend_std<S>: raw samples are prefetched into registers one tile ahead, mixed and written de-interleaved by a
+//       separate loader pass.  2 CTAs per SM.  Kept as the cross-check of the direct kernel (CSDR_OPT_FRONTEND_VARIANT).
 #pragma once
 #include "frontend.cuh"
 
@@ -20,20 +23,6 @@ __device__ __forceinline__ float4 fe_ldg_stream(const float4 *p)
 #else
     float4 v;
     asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
-                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
-    return v;
-#endif
-}
-
-// 16-byte read-only load that asks L1 to keep the line (the polyphase bank is re-read by every tile while the raw
-// samples stream through the same cache)
-__device__ __forceinline__ float4 fe_ldg_keep(const float4 *p)
-{
-#ifdef CSDR_EMU
-    return *p;
-#else
-    float4 v;
-    asm volatile("ld.global.nc.L1::evict_last.v4.f32 {%0,%1,%2,%3}, [%4];"
                  : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
     return v;
 #endif
@@ -70,33 +59,33 @@ __device__ __forceinline__ bool fe_tile_is_bulk(const FrontendParams &p, const f
 {
     constexpr int NS = FeStd<S, V>::G.n[S];
     const long long rel0 = lo - p.n0;
-    return rel0 >= 0 && rel0 + NS <= p.nx && (V == 2 || (reinterpret_cast<uintptr_t>(xs + rel0) & 15) == 0);
+    return rel0 >= 0 && rel0 + NS <= p.nx && (reinterpret_cast<uintptr_t>(xs + rel0) & 15) == 0;
 }
 
-template <int S, int V> struct FePrefetch {
-    static constexpr int NP = FeStd<S, V>::G.n[S] / 2, IT = (NP + kFeNT - 1) / kFeNT;
-    float4 v[V ? 1 : IT];          // variant 1 stages through shared memory instead
+template <int S> struct FePrefetch {
+    static constexpr int NP = FeStd<S, 0>::G.n[S] / 2, IT = (NP + kFeNT - 1) / kFeNT;
+    float4 v[IT];
 };
 
 // issue the 16-byte loads of a bulk tile; they complete while the previous tile is being filtered
 template <int S>
-__device__ __forceinline__ void fe_prefetch(FePrefetch<S, 0> &pre, const FrontendParams &p, const float2 *__restrict__ xs,
+__device__ __forceinline__ void fe_prefetch(FePrefetch<S> &pre, const FrontendParams &p, const float2 *__restrict__ xs,
                                             long long lo)
 {
     const float4 *src = reinterpret_cast<const float4 *>(xs + (lo - p.n0));
 #pragma unroll
-    for (int k = 0; k < FePrefetch<S, 0>::IT; k++) {
+    for (int k = 0; k < FePrefetch<S>::IT; k++) {
         const int pi = threadIdx.x + kFeNT * k;
-        if (pi < FePrefetch<S, 0>::NP) pre.v[k] = fe_ldg_stream(src + pi);
+        if (pi < FePrefetch<S>::NP) pre.v[k] = fe_ldg_stream(src + pi);
     }
 }
 
-template <int S, int V, int MIX>
+template <int S, int MIX>
 __device__ __forceinline__ void fe_load_top(const FrontendParams &p, const float2 *__restrict__ xs,
                                             const float2 *__restrict__ hs, float2 *__restrict__ dst, long long lo,
-                                            const FePrefetch<S, V> &pre, const float2 *__restrict__ raw, bool bulk)
+                                            const FePrefetch<S> &pre, bool bulk)
 {
-    constexpr FeGeom G = FeStd<S, V>::G;
+    constexpr FeGeom G = FeStd<S, 0>::G;
     constexpr int NS = G.n[S], STR = G.stride[S], D = G.R[S - 1];
     static_assert(D == 8 && NS % 2 == 0, "loader assumes an 8-way layout of the top level");
     const int tid = threadIdx.x;
@@ -108,10 +97,10 @@ __device__ __forceinline__ void fe_load_top(const FrontendParams &p, const float
         float2 *dE = dst + (tid & 7) * STR + (tid >> 3);
         float2 *dO = dE + D * STR + kFePlanePad;
 #pragma unroll
-        for (int k = 0; k < FePrefetch<S, V>::IT; k++) {
+        for (int k = 0; k < FePrefetch<S>::IT; k++) {
             const int pi = tid + kFeNT * k;
-            if (pi < FePrefetch<S, V>::NP) {
-                const float4 v = V ? reinterpret_cast<const float4 *>(raw)[pi] : pre.v[V ? 0 : k];
+            if (pi < FePrefetch<S>::NP) {
+                const float4 v = pre.v[k];
                 const unsigned th = th0 + (unsigned)(2 * pi) * p.dtheta;
                 dE[(kFeNT / 8) * k] = fe_mix<MIX>(cf(v.x, v.y), th, p.quantize);
                 dO[(kFeNT / 8) * k] = fe_mix<MIX>(cf(v.z, v.w), th + p.dtheta, p.quantize);
@@ -142,26 +131,20 @@ __device__ __forceinline__ void fe_load_top(const FrontendParams &p, const float
 // ---- one half-band stage with compile-time geometry --------------------------------------------------------
 //   out[q] = C[q+M] + sum_{u<2M} g[u] * T[q+u+SH]     T/C = tap/centre planes (odd/even samples; swapped when the
 //   input level is shifted by one sample), R consecutive outputs per thread slot
-//   MIX != 0 (variant 2, top stage only): the level holds RAW samples; every sample read is multiplied by the NCO
-//   phasor of its position first (thb = phase word of local sample 0, dth = phase step per sample).
-template <int M, int R, int STR, int SH, int NOUT, bool LAST, int D2, int STR2, int MIX = 0>
+template <int M, int R, int STR, int SH, int NOUT, bool LAST, int D2, int STR2>
 __device__ __forceinline__ void fe_stage_c(const float2 *__restrict__ in, float2 *__restrict__ out,
-                                           const float *__restrict__ g, float zeta, unsigned thb = 0, unsigned dth = 0)
+                                           const float *__restrict__ g, float zeta)
 {
     const float2 *T = in + (SH ? 0 : R * STR + kFePlanePad);
     const float2 *C = in + (SH ? R * STR + kFePlanePad : 0);
     constexpr int NSLOTS = NOUT / R;
     for (int t = threadIdx.x; t < NSLOTS; t += kFeNT) {
-        // tap plane element e <-> local sample 2 (R t + e) + (SH ? 0 : 1), centre plane the other parity
-        const unsigned ths = thb + (unsigned)(2 * R * t) * dth;
         float2 acc[R];
 #pragma unroll
-        for (int r = 0; r < R; r++)
-            acc[r] = fe_mix_q<MIX>(C[((M + r) % R) * STR + t + (M + r) / R], ths + (unsigned)(2 * (M + r) + (SH ? 1 : 0)) * dth);
+        for (int r = 0; r < R; r++) acc[r] = C[((M + r) % R) * STR + t + (M + r) / R];
 #pragma unroll
         for (int c = 0; c < R + 2 * M - 1; c++) {
-            const float2 v = fe_mix_q<MIX>(T[((c + SH) % R) * STR + t + (c + SH) / R],
-                                           ths + (unsigned)(2 * (c + SH) + (SH ? 0 : 1)) * dth);
+            const float2 v = T[((c + SH) % R) * STR + t + (c + SH) / R];
 #pragma unroll
             for (int r = 0; r < R; r++) {
                 const int u = c - r;
@@ -243,9 +226,8 @@ __device__ __forceinline__ void fe_tile_info(const FrontendParams &p, const floa
 // One thread per PAIR of pushes: the 16 c-samples both windows need are fetched with eight conflict-free 16-byte
 // loads and stay in registers.  Output oA + j has timing phase phA + j*step relative to the tile, belongs to local
 // push (phase >> 24) and uses branch = the next `bits` phase bits.  The first j of a thread is estimated in fp32 and
-// corrected exactly in integers (no division).  BANK16: taps come from the 16-float rows of p.bank16 through L1
-// (four 16-byte loads per output), else from the padded copy of the bank in shared memory.
-template <int TC, bool BANK16>
+// corrected exactly in integers (no division).  Taps come from the padded copy of the bank in shared memory.
+template <int TC>
 __device__ __forceinline__ void fe_resample_tile(const FrontendParams &p, const float2 *__restrict__ cb, float2 *__restrict__ ys,
                                                  const FeTileInfo &ti, int npush, const float *__restrict__ bank_s, float rate_f)
 {
@@ -271,16 +253,10 @@ __device__ __forceinline__ void fe_resample_tile(const FrontendParams &p, const 
         for (int e = 0; e < 2; e++) {
             if (2 * t + e < npush && (int)(P >> 24) == 2 * t + e) {
                 const unsigned br = ((unsigned)P >> sh) & mask;
-                float h[16];
-                if constexpr (BANK16) {
-                    const float4 *h4 = reinterpret_cast<const float4 *>(p.bank16) + br * 4;
+                float h[kHsub];
+                const float *hr = bank_s + br * (kHsub + 1);
 #pragma unroll
-                    for (int i = 0; i < 4; i++) { const float4 q = fe_ldg_keep(h4 + i); h[4 * i] = q.x; h[4 * i + 1] = q.y; h[4 * i + 2] = q.z; h[4 * i + 3] = q.w; }
-                } else {
-                    const float *hr = bank_s + br * (kHsub + 1);
-#pragma unroll
-                    for (int i = 0; i < kHsub; i++) h[i] = hr[i];
-                }
+                for (int i = 0; i < kHsub; i++) h[i] = hr[i];
                 float ar = 0.f, ai = 0.f;
 #pragma unroll
                 for (int jj = 0; jj < kHsub; jj++) {
@@ -294,24 +270,19 @@ __device__ __forceinline__ void fe_resample_tile(const FrontendParams &p, const 
     }
 }
 
-template <int S, int V>
-__global__ void __launch_bounds__(kFeNT, V ? 3 : 2) k_frontend_std(const CSDR_GRID_CONSTANT FrontendParams p)
+template <int S>
+__global__ void __launch_bounds__(kFeNT, 2) k_frontend_std(const CSDR_GRID_CONSTANT FrontendParams p)
 {
-    constexpr FeGeom G = FeStd<S, V>::G;
-    constexpr int NS = G.n[S];
+    constexpr FeGeom G = FeStd<S, 0>::G;
     CSDR_DYN_SMEM(smem_raw);
     float2 *smem = reinterpret_cast<float2 *>(smem_raw);
-    float *bank_s = reinterpret_cast<float *>(smem_raw) + 2 * G.total_f2;    // variant 0 only
-    const float2 *raw = smem + G.off_raw;                                     // variant 1 only
+    float *bank_s = reinterpret_cast<float *>(smem_raw) + 2 * G.total_f2;
     __shared__ FeTileInfo s_info[3];
-    __shared__ __align__(8) unsigned long long s_bar;
 
     const int npfb = 1 << p.bits;
-    if (!V) {
-        for (int i = threadIdx.x; i < npfb * kHsub; i += kFeNT) {
-            const int row = i / kHsub, col = i - row * kHsub;
-            bank_s[row * (kHsub + 1) + col] = p.bank[i];
-        }
+    for (int i = threadIdx.x; i < npfb * kHsub; i += kFeNT) {
+        const int row = i / kHsub, col = i - row * kHsub;
+        bank_s[row * (kHsub + 1) + col] = p.bank[i];
     }
     const float2 *xs = p.x + (long long)blockIdx.y * p.x_stride;
     const float2 *hs = p.hist + (long long)blockIdx.y * p.hcap;
@@ -322,23 +293,15 @@ __global__ void __launch_bounds__(kFeNT, V ? 3 : 2) k_frontend_std(const CSDR_GR
 
     // Software pipeline over the tiles of this (persistent) CTA: the raw samples of tile i+1 are loaded into
     // registers while tile i is filtered, so the sequential load -> mix -> filter chain never waits for HBM.
-    // (A TMA bulk-copy staging buffer does the same but costs two extra passes over shared memory, the resource this
-    // kernel is bound by; measured 217 us vs the register pipeline, see DESIGN.md.)  Tile bookkeeping (absolute
-    // position, alignment, output range) is done by one thread, two tiles ahead.
-    // Variant 1 stages the raw tile in shared memory with a TMA bulk copy (cp.async.bulk + mbarrier) issued as soon as
-    // the previous tile has been mixed: no prefetch registers, three CTAs per SM.
-    unsigned parity = 0;
+    // Tile bookkeeping (absolute position, alignment, output range) is done by one thread, two tiles ahead.
     if (threadIdx.x == 0) {
         const int t0 = (int)blockIdx.x;
-        if (V) bulk_init(&s_bar);
-        if (t0 < p.ntiles) fe_tile_info<S, V>(p, xs, t0, inv_st, s_info[0]);
-        if (t0 + gstep < p.ntiles) fe_tile_info<S, V>(p, xs, t0 + gstep, inv_st, s_info[1]);
-        if (V && t0 < p.ntiles && s_info[0].bulk)
-            bulk_copy_g2s(smem + G.off_raw, xs + (s_info[0].lo - p.n0), NS * (unsigned)sizeof(float2), &s_bar);
+        if (t0 < p.ntiles) fe_tile_info<S, 0>(p, xs, t0, inv_st, s_info[0]);
+        if (t0 + gstep < p.ntiles) fe_tile_info<S, 0>(p, xs, t0 + gstep, inv_st, s_info[1]);
     }
     __syncthreads();
-    FePrefetch<S, V> pre;
-    if constexpr (!V) { if ((int)blockIdx.x < p.ntiles && s_info[0].bulk) fe_prefetch<S>(pre, p, xs, s_info[0].lo); }
+    FePrefetch<S> pre;
+    if ((int)blockIdx.x < p.ntiles && s_info[0].bulk) fe_prefetch<S>(pre, p, xs, s_info[0].lo);
 
     int cur = 0;
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gstep) {
@@ -346,27 +309,19 @@ __global__ void __launch_bounds__(kFeNT, V ? 3 : 2) k_frontend_std(const CSDR_GR
         const long long lo = s_info[cur].lo;
         const bool bulk = s_info[cur].bulk != 0;
         float2 *top = smem + G.off[S];
-        if (V && bulk) { bulk_wait(&s_bar, parity); parity ^= 1u; }
-        if (p.mix_mode == 0)      fe_load_top<S, V, 0>(p, xs, hs, top, lo, pre, raw, bulk);
-        else if (p.quantize) { if (p.mix_mode == 1) fe_load_top<S, V, 1 | 8>(p, xs, hs, top, lo, pre, raw, bulk);
-                               else                 fe_load_top<S, V, 2 | 8>(p, xs, hs, top, lo, pre, raw, bulk); }
-        else                 { if (p.mix_mode == 1) fe_load_top<S, V, 1 | 4>(p, xs, hs, top, lo, pre, raw, bulk);
-                               else                 fe_load_top<S, V, 2 | 4>(p, xs, hs, top, lo, pre, raw, bulk); }
-        if (threadIdx.x == 0 && tile + 2 * gstep < p.ntiles) fe_tile_info<S, V>(p, xs, tile + 2 * gstep, inv_st, s_info[nxt2]);
+        if (p.mix_mode == 0)      fe_load_top<S, 0>(p, xs, hs, top, lo, pre, bulk);
+        else if (p.quantize) { if (p.mix_mode == 1) fe_load_top<S, 1 | 8>(p, xs, hs, top, lo, pre, bulk);
+                               else                 fe_load_top<S, 2 | 8>(p, xs, hs, top, lo, pre, bulk); }
+        else                 { if (p.mix_mode == 1) fe_load_top<S, 1 | 4>(p, xs, hs, top, lo, pre, bulk);
+                               else                 fe_load_top<S, 2 | 4>(p, xs, hs, top, lo, pre, bulk); }
+        if (threadIdx.x == 0 && tile + 2 * gstep < p.ntiles) fe_tile_info<S, 0>(p, xs, tile + 2 * gstep, inv_st, s_info[nxt2]);
         __syncthreads();
-        if constexpr (V) {
-            // the staging buffer has been consumed: start fetching the next tile of this CTA
-            if (threadIdx.x == 0 && tile + gstep < p.ntiles && s_info[nxt].bulk)
-                bulk_copy_g2s(smem + G.off_raw, xs + (s_info[nxt].lo - p.n0), NS * (unsigned)sizeof(float2), &s_bar);
-        } else {
-            if (tile + gstep < p.ntiles && s_info[nxt].bulk) fe_prefetch<S>(pre, p, xs, s_info[nxt].lo);
-        }
+        if (tile + gstep < p.ntiles && s_info[nxt].bulk) fe_prefetch<S>(pre, p, xs, s_info[nxt].lo);
 
-        fe_run_stages<S, V, S - 1>(p, smem);
-
+        fe_run_stages<S, 0, S - 1>(p, smem);
         {
             const int npush = (int)min((long long)G.Tc, p.K1 - p.K0 - (long long)tile * G.Tc);
-            fe_resample_tile<G.Tc, V != 0>(p, smem + G.off[0], ys, s_info[cur], npush, bank_s, rate_f);
+            fe_resample_tile<G.Tc>(p, smem + G.off[0], ys, s_info[cur], npush, bank_s, rate_f);
         }
         __syncthreads();   // smem is reused by the next tile
         cur = nxt;
@@ -374,135 +329,12 @@ __global__ void __launch_bounds__(kFeNT, V ? 3 : 2) k_frontend_std(const CSDR_GR
 }
 
 // =============================================================================================================
-// Variant 2: no separate mixing pass.  The raw tile is copied asynchronously (cp.async, 8 bytes per thread and
-// instruction) from global memory straight into the top level's de-interleaved layout while the lower stages of the
-// previous tile run; the first half-band stage multiplies every sample it reads by the NCO phasor of its position.
-// One pass over shared memory and one barrier fewer per tile than variant 1, ~53 KB per CTA -> four CTAs per SM; the
-// price is that samples shared by neighbouring thread slots are mixed twice (21 phasors per 16 raw samples for m = 3).
-
-// thread tid copies, per round k, sample tid + NT k -> plane tid & 1, pair (tid >> 1) + (NT/2) k: a warp reads 256
-// contiguous bytes, and the 16 samples of every 128-byte line land in 16 distinct 8-byte banks (the one-element pad
-// between the planes shifts the odd plane by one bank)
-template <int S>
-__device__ __forceinline__ void fe_fill_top(const FrontendParams &p, const float2 *__restrict__ xs,
-                                            const float2 *__restrict__ hs, float2 *__restrict__ dst, long long lo, bool bulk)
-{
-    constexpr FeGeom G = FeStd<S, 2>::G;
-    constexpr int NS = G.n[S], STR = G.stride[S], D = G.R[S - 1], IT = (NS + kFeNT - 1) / kFeNT;
-    static_assert(D == 8 && NS % 2 == 0, "loader assumes an 8-way layout of the top level");
-    const int tid = threadIdx.x;
-    const long long rel0 = lo - p.n0;
-    float2 *d0 = dst + (tid & 1) * (D * STR + kFePlanePad) + ((tid >> 1) & 7) * STR + (tid >> 4);
-    if (bulk) {
-        const float2 *src = xs + rel0 + tid;
-#pragma unroll
-        for (int k = 0; k < IT; k++)
-            if (tid + kFeNT * k < NS) async_copy8(d0 + (kFeNT / 16) * k, src + kFeNT * k);
-    } else {
-        // edge tile: samples before the chunk come from the carried history, samples after it are zero
-        for (int k = 0; k < IT; k++) {
-            if (tid + kFeNT * k >= NS) break;
-            const long long rel = rel0 + tid + kFeNT * k;
-            float2 v = cf(0.f, 0.f);
-            if (rel >= 0) { if (rel < p.nx) v = xs[rel]; }
-            else if (rel >= -(long long)p.hcap) v = hs[p.hcap + rel];
-            d0[(kFeNT / 16) * k] = v;
-        }
-    }
-}
-
-template <int S, int s, int MIX>
-__device__ __forceinline__ void fe_run_stage_v2(const FrontendParams &p, float2 *smem, unsigned thb)
-{
-    constexpr FeGeom G = FeStd<S, 2>::G;
-    constexpr bool LAST = (s == 0);
-    constexpr int D2 = LAST ? 1 : G.R[LAST ? 0 : s - 1];
-    constexpr int SH = (s == S - 1) ? G.shift : 0;
-    fe_stage_c<G.m[s], G.R[s], G.stride[s + 1], SH, G.n[s], LAST, D2, G.stride[s], MIX>(
-        smem + G.off[s + 1], smem + G.off[s], p.taps[s], p.zeta, thb, p.dtheta);
-}
-template <int S, int s>
-__device__ __forceinline__ void fe_run_lower_v2(const FrontendParams &p, float2 *smem)
-{
-    fe_run_stage_v2<S, s, 0>(p, smem, 0u);
-    __syncthreads();
-    if constexpr (s > 0) fe_run_lower_v2<S, s - 1>(p, smem);
-}
-
-template <int S>
-__global__ void __launch_bounds__(kFeNT, 4) k_frontend_v2(const CSDR_GRID_CONSTANT FrontendParams p)
-{
-    constexpr FeGeom G = FeStd<S, 2>::G;
-    static_assert(S >= 2, "variant 2 needs a half-band stage below the mixing one");
-    CSDR_DYN_SMEM(smem_raw);
-    float2 *smem = reinterpret_cast<float2 *>(smem_raw);
-    __shared__ FeTileInfo s_info[3];
-
-    const float2 *xs = p.x + (long long)blockIdx.y * p.x_stride;
-    const float2 *hs = p.hist + (long long)blockIdx.y * p.hcap;
-    float2 *ys = p.y + (long long)blockIdx.y * p.y_stride;
-    const double inv_st = 1.0 / (double)p.step;
-    const float rate_f = 16777216.0f / (float)p.step;
-    const int gstep = (int)gridDim.x;
-    float2 *top = smem + G.off[S];
-
-    if (threadIdx.x == 0) {
-        const int t0 = (int)blockIdx.x;
-        if (t0 < p.ntiles) fe_tile_info<S, 2>(p, xs, t0, inv_st, s_info[0]);
-        if (t0 + gstep < p.ntiles) fe_tile_info<S, 2>(p, xs, t0 + gstep, inv_st, s_info[1]);
-    }
-    __syncthreads();
-    if ((int)blockIdx.x < p.ntiles) fe_fill_top<S>(p, xs, hs, top, s_info[0].lo, s_info[0].bulk != 0);
-    async_copy_wait();
-    __syncthreads();
-
-    int cur = 0;
-    for (int tile = blockIdx.x; tile < p.ntiles; tile += gstep) {
-        const int nxt = cur == 2 ? 0 : cur + 1, nxt2 = nxt == 2 ? 0 : nxt + 1;
-        // phase word of the tile's local sample 0 (+ the table-rounding offset of the quantised NCO)
-        const unsigned thb = p.theta0 + (unsigned)s_info[cur].lo * p.dtheta + (p.quantize ? (1u << 21) : 0u) + kFePhaseBias;
-#ifdef CSDR_FE_SKIP
-        if (CSDR_FE_SKIP & 2) {}
-        else if (CSDR_FE_SKIP & 1) fe_run_stage_v2<S, S - 1, 0>(p, smem, thb);
-        else
-#endif
-        if (p.mix_mode == 0)      fe_run_stage_v2<S, S - 1, 0>(p, smem, thb);
-        else if (p.quantize) { if (p.mix_mode == 1) fe_run_stage_v2<S, S - 1, 1 | 8>(p, smem, thb);
-                               else                 fe_run_stage_v2<S, S - 1, 2 | 8>(p, smem, thb); }
-        else                 { if (p.mix_mode == 1) fe_run_stage_v2<S, S - 1, 1>(p, smem, thb);
-                               else                 fe_run_stage_v2<S, S - 1, 2>(p, smem, thb); }
-        __syncthreads();
-        // the top level has been consumed: start copying the next tile of this CTA into it
-#ifdef CSDR_FE_SKIP
-        if (!(CSDR_FE_SKIP & 16))
-#endif
-        if (tile + gstep < p.ntiles) fe_fill_top<S>(p, xs, hs, top, s_info[nxt].lo, s_info[nxt].bulk != 0);
-        if (threadIdx.x == 0 && tile + 2 * gstep < p.ntiles) fe_tile_info<S, 2>(p, xs, tile + 2 * gstep, inv_st, s_info[nxt2]);
-
-#ifdef CSDR_FE_SKIP
-        if (!(CSDR_FE_SKIP & 4))
-#endif
-        fe_run_lower_v2<S, S - 2>(p, smem);
-#ifdef CSDR_FE_SKIP
-        if (!(CSDR_FE_SKIP & 8))
-#endif
-        {
-            const int npush = (int)min((long long)G.Tc, p.K1 - p.K0 - (long long)tile * G.Tc);
-            fe_resample_tile<G.Tc, true>(p, smem + G.off[0], ys, s_info[cur], npush, nullptr, rate_f);
-        }
-        async_copy_wait();
-        __syncthreads();   // next tile's raw samples are in place; the lower levels may be overwritten
-        cur = nxt;
-    }
-}
-
-// =============================================================================================================
-// Variant 3: the raw tile is bulk-copied (TMA) into a linear staging buffer and the first half-band stage reads it
+// k_frontend_direct: the raw tile is bulk-copied (TMA) into a linear staging buffer and the first half-band stage reads it
 // there: one 16-byte load fetches the (even, odd) pair -- the even sample is a tap input, the odd one a centre input
 // (the top level starts one sample early, shift = 1) -- and both are multiplied by the NCO phasor in registers.
 // kFeTopR = 7 outputs per thread slot: consecutive slots start 7 pairs apart, so the eight lanes of a quarter-warp
 // hit eight different 16-byte banks.  No mixing pass, no de-interleaving pass, no LSU work for the copy; the lower
-// stages and the resampler are the ones of variant 0 (bank in shared memory).
+// stages and the resampler are those of k_frontend_std.
 template <int M, int NOUT, bool LAST, int D2, int STR2, int MIX>
 __device__ __forceinline__ void fe_stage_top(const float2 *__restrict__ raw, float2 *__restrict__ out,
                                              const float *__restrict__ g, float zeta, unsigned thb, unsigned dth)
@@ -542,34 +374,22 @@ __device__ __forceinline__ void fe_stage_top(const float2 *__restrict__ raw, flo
 }
 
 template <int S, int MIX>
-__device__ __forceinline__ void fe_run_top_v3(const FrontendParams &p, float2 *smem, unsigned thb)
+__device__ __forceinline__ void fe_run_top(const FrontendParams &p, float2 *smem, unsigned thb)
 {
-    constexpr FeGeom G = FeStd<S, 3>::G;
+    constexpr FeGeom G = FeStd<S, 1>::G;
     constexpr bool LAST = (S == 1);
     constexpr int D2 = LAST ? 1 : G.R[LAST ? 0 : S - 2];
     static_assert(G.shift == 1, "pairs are (tap, centre) only when the top level starts one sample early");
     fe_stage_top<G.m[S - 1], G.n[S - 1], LAST, D2, G.stride[S - 1], MIX>(smem + G.off[S], smem + G.off[S - 1],
                                                                           p.taps[S - 1], p.zeta, thb, p.dtheta);
 }
-template <int S, int s>
-__device__ __forceinline__ void fe_run_lower_v3(const FrontendParams &p, float2 *smem)
-{
-    constexpr FeGeom G = FeStd<S, 3>::G;
-    constexpr bool LAST = (s == 0);
-    constexpr int D2 = LAST ? 1 : G.R[LAST ? 0 : s - 1];
-    fe_stage_c<G.m[s], G.R[s], G.stride[s + 1], 0, G.n[s], LAST, D2, G.stride[s]>(
-        smem + G.off[s + 1], smem + G.off[s], p.taps[s], p.zeta);
-    __syncthreads();
-    if constexpr (s > 0) fe_run_lower_v3<S, s - 1>(p, smem);
-}
-
 // staging[i] = raw sample lo + i for a tile the bulk copy cannot fetch (it reaches into the carried history, past
 // the end of the chunk, or the chunk is not 16-byte aligned there)
 template <int S>
 __device__ __forceinline__ void fe_fill_staging(const FrontendParams &p, const float2 *__restrict__ xs,
                                                 const float2 *__restrict__ hs, float2 *__restrict__ raw, long long lo)
 {
-    constexpr int NS = FeStd<S, 3>::G.n[S];
+    constexpr int NS = FeStd<S, 1>::G.n[S];
     const long long rel0 = lo - p.n0;
     for (int i = threadIdx.x; i < NS; i += kFeNT) {
         const long long rel = rel0 + i;
@@ -586,9 +406,9 @@ __device__ __forceinline__ void fe_fill_staging(const FrontendParams &p, const f
 #define FE_NOFILL 0
 #endif
 template <int S>
-__global__ void __launch_bounds__(kFeNT, 3) k_frontend_v3(const CSDR_GRID_CONSTANT FrontendParams p)
+__global__ void __launch_bounds__(kFeNT, 3) k_frontend_direct(const CSDR_GRID_CONSTANT FrontendParams p)
 {
-    constexpr FeGeom G = FeStd<S, 3>::G;
+    constexpr FeGeom G = FeStd<S, 1>::G;
     constexpr int NS = G.n[S];
     CSDR_DYN_SMEM(smem_raw);
     float2 *smem = reinterpret_cast<float2 *>(smem_raw);
@@ -613,8 +433,8 @@ __global__ void __launch_bounds__(kFeNT, 3) k_frontend_v3(const CSDR_GRID_CONSTA
     if (threadIdx.x == 0) {
         const int t0 = (int)blockIdx.x;
         bulk_init(&s_bar);
-        if (t0 < p.ntiles) fe_tile_info<S, 3>(p, xs, t0, inv_st, s_info[0]);
-        if (t0 + gstep < p.ntiles) fe_tile_info<S, 3>(p, xs, t0 + gstep, inv_st, s_info[1]);
+        if (t0 < p.ntiles) fe_tile_info<S, 1>(p, xs, t0, inv_st, s_info[0]);
+        if (t0 + gstep < p.ntiles) fe_tile_info<S, 1>(p, xs, t0 + gstep, inv_st, s_info[1]);
     }
     __syncthreads();
     if ((int)blockIdx.x < p.ntiles) {
@@ -631,14 +451,14 @@ __global__ void __launch_bounds__(kFeNT, 3) k_frontend_v3(const CSDR_GRID_CONSTA
         const unsigned thb = p.theta0 + (unsigned)s_info[cur].lo * p.dtheta + (p.quantize ? (1u << 21) : 0u) + kFePhaseBias;
 #ifdef CSDR_FE_SKIP
         if (CSDR_FE_SKIP & 2) {}
-        else if (CSDR_FE_SKIP & 1) fe_run_top_v3<S, 0>(p, smem, thb);
+        else if (CSDR_FE_SKIP & 1) fe_run_top<S, 0>(p, smem, thb);
         else
 #endif
-        if (p.mix_mode == 0)      fe_run_top_v3<S, 0>(p, smem, thb);
-        else if (p.quantize) { if (p.mix_mode == 1) fe_run_top_v3<S, 1 | 8>(p, smem, thb);
-                               else                 fe_run_top_v3<S, 2 | 8>(p, smem, thb); }
-        else                 { if (p.mix_mode == 1) fe_run_top_v3<S, 1>(p, smem, thb);
-                               else                 fe_run_top_v3<S, 2>(p, smem, thb); }
+        if (p.mix_mode == 0)      fe_run_top<S, 0>(p, smem, thb);
+        else if (p.quantize) { if (p.mix_mode == 1) fe_run_top<S, 1 | 8>(p, smem, thb);
+                               else                 fe_run_top<S, 2 | 8>(p, smem, thb); }
+        else                 { if (p.mix_mode == 1) fe_run_top<S, 1>(p, smem, thb);
+                               else                 fe_run_top<S, 2>(p, smem, thb); }
         __syncthreads();
         // the staging buffer has been consumed: start fetching the next tile of this CTA
         if (tile + gstep < p.ntiles) {
@@ -646,18 +466,18 @@ __global__ void __launch_bounds__(kFeNT, 3) k_frontend_v3(const CSDR_GRID_CONSTA
             else fe_fill_staging<S>(p, xs, hs, raw, s_info[nxt].lo);
         }
         // bookkeeping for the tile after next: by a thread of the last warp, which has no slot in the lower stages
-        if (threadIdx.x == kFeNT - 32 && tile + 2 * gstep < p.ntiles) fe_tile_info<S, 3>(p, xs, tile + 2 * gstep, inv_st, s_info[nxt2]);
+        if (threadIdx.x == kFeNT - 32 && tile + 2 * gstep < p.ntiles) fe_tile_info<S, 1>(p, xs, tile + 2 * gstep, inv_st, s_info[nxt2]);
 
 #ifdef CSDR_FE_SKIP
         if (!(CSDR_FE_SKIP & 4))
 #endif
-        if constexpr (S >= 2) fe_run_lower_v3<S, S - 2>(p, smem);
+        if constexpr (S >= 2) fe_run_stages<S, 1, S - 2>(p, smem);
 #ifdef CSDR_FE_SKIP
         if (!(CSDR_FE_SKIP & 8))
 #endif
         {
             const int npush = (int)min((long long)G.Tc, p.K1 - p.K0 - (long long)tile * G.Tc);
-            fe_resample_tile<G.Tc, false>(p, smem + G.off[0], ys, s_info[cur], npush, bank_s, rate_f);
+            fe_resample_tile<G.Tc>(p, smem + G.off[0], ys, s_info[cur], npush, bank_s, rate_f);
         }
         __syncthreads();   // lower levels may be overwritten; a synchronously filled staging buffer is complete
         cur = nxt;

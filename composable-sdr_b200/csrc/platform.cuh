@@ -26,8 +26,6 @@ namespace csdr {
 __device__ inline void bulk_init(unsigned long long *) {}
 __device__ inline void bulk_copy_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *) { memcpy(dst, src, bytes); }
 __device__ inline void bulk_wait(unsigned long long *, unsigned) {}
-__device__ inline void async_copy8(void *dst, const void *src) { memcpy(dst, src, 8); }
-__device__ inline void async_copy_wait() {}
 #else
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void bulk_init(unsigned long long *bar)
@@ -49,27 +47,17 @@ __device__ __forceinline__ void bulk_wait(unsigned long long *bar, unsigned pari
                  "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
                  "@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
-// ---- per-thread asynchronous 8-byte copy global -> shared (cp.async, SASS LDGSTS): no register staging, any
-// destination address, so a tile can be scattered straight into the consumer's de-interleaved layout
-__device__ __forceinline__ void async_copy8(void *dst, const void *src)
-{
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
-}
-// every copy this thread issued has landed (a __syncthreads then publishes them to the CTA)
-__device__ __forceinline__ void async_copy_wait()
-{
-    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
-}
 #endif
 
 constexpr int kMaxStages = 12;   // half-band stages (2^12 decimation) supported by the fused front end
 constexpr int kMaxHbM    = 16;   // max half-band semi-length m (2m taps)
 constexpr int kHsub      = 14;   // taps per polyphase branch of the arbitrary resampler (2*7, msresamp.c)
-constexpr int kFePlanePad = 1;   // elements between the even and the odd plane of a level buffer (see fe_fill_top)
+constexpr int kFePlanePad = 1;   // elements between the even and the odd plane of a level buffer: a thread pair that writes
+                                 // (even, odd) samples of the same pair index then hits two different banks
 #ifndef CSDR_FE_TOPR
 #define CSDR_FE_TOPR 7
 #endif
-constexpr int kFeTopR  = CSDR_FE_TOPR;      // outputs per thread slot of a first stage that reads the linear raw tile (variant 3)
+constexpr int kFeTopR  = CSDR_FE_TOPR;      // outputs per thread slot of a first stage that reads the linear raw tile (k_frontend_direct)
 constexpr int kHcPad     = 16;   // c-rate history carried into every tile (>= kHsub-1, multiple of 8)
 
 __host__ __device__ inline float2 cf(float re, float im) { float2 z; z.x = re; z.y = im; return z; }

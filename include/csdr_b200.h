@@ -51,9 +51,8 @@ enum {
     CSDR_OPT_AGC_EXACT_MATH = 6,  /* 1: library expf/logf/atan2f in the AGC/discriminator loop instead of the SFU forms */
     CSDR_OPT_OVERLAP = 7,         /* 1: overlap the back end of part i with the front end of part i+1 (2 streams) */
     CSDR_OPT_DEBUG = 8,           /* 1: print AGC speculation diagnostics to stderr (synchronises) */
-    CSDR_OPT_FRONTEND_VARIANT = 9 /* front-end input pipeline: 0 register prefetch (2 CTAs/SM), 1 TMA bulk-copy staging +
-                                      mixing pass (3 CTAs/SM), 2 asynchronous copy + mix fused into the first half-band
-                                      stage (4 CTAs/SM), 3 (default) first stage reads the TMA-staged tile directly */
+    CSDR_OPT_FRONTEND_VARIANT = 9 /* front-end kernel for the standard half-band plan: 1 (default) TMA-staged raw tile read in
+                                     place by the first half-band stage (3 CTAs/SM); 0 register prefetch + mixing pass (2 CTAs/SM) */
 };
 int         csdr_set_option(int opt, int value);
 int         csdr_get_option(int opt);
@@ -189,6 +188,8 @@ uint64_t csdr_chain_agc_fixups(csdr_chain q);
 /* cumulative counters: [0] gain-loop segments repaired in order, [1] squelch-FSM segments repaired in order,
  * [2] gain-loop segments refined in parallel */
 int      csdr_chain_agc_counters(csdr_chain q, uint64_t out[3]);
+/* segment length and warm-up length (samples) the gain-loop speculation used in the last call (self-tuning) */
+int      csdr_chain_agc_plan(csdr_chain q, int out[2]);
 
 #ifdef __cplusplus
 }

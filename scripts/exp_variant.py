@@ -1,4 +1,4 @@
-"""time k_frontend for one variant (usage: exp_variant.py VARIANT [label])"""
+"""time k_frontend for one variant (usage: exp_variant.py VARIANT(0|1) [label])"""
 import sys, os
 ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "scripts"))
@@ -7,7 +7,7 @@ import composable_sdr_b200 as cs
 from bench_configs import sig
 n = 1 << 27
 x = sig(n, 1)
-variant = int(sys.argv[1])
+variant = int(sys.argv[1])          # 1 = k_frontend_direct (default), 0 = k_frontend_std
 cs.set_option(9, variant)
 if len(sys.argv) > 3: cs.set_option(10, int(sys.argv[3]))
 ch = cs.Chain(2.56e6, 1e5, 200e3)

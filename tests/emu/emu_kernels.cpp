@@ -31,36 +31,21 @@ long long emu_frontend(float rate, float As, int mix_mode, float freq, int quant
         nthreads = kFeNT;
         if (g.variant == 0) {
             switch (ms.S) {
-            case 1: kernel = k_frontend_std<1, 0>; break;
-            case 2: kernel = k_frontend_std<2, 0>; break;
-            case 3: kernel = k_frontend_std<3, 0>; break;
-            case 4: kernel = k_frontend_std<4, 0>; break;
-            case 5: kernel = k_frontend_std<5, 0>; break;
-            default: kernel = k_frontend_std<6, 0>; break;
-            }
-        } else if (g.variant == 3) {
-            switch (ms.S) {
-            case 1: kernel = k_frontend_v3<1>; break;
-            case 2: kernel = k_frontend_v3<2>; break;
-            case 3: kernel = k_frontend_v3<3>; break;
-            case 4: kernel = k_frontend_v3<4>; break;
-            case 5: kernel = k_frontend_v3<5>; break;
-            default: kernel = k_frontend_v3<6>; break;
-            }
-        } else if (g.variant == 2) {
-            switch (ms.S) {
-            case 2: kernel = k_frontend_v2<2>; break;
-            case 3: kernel = k_frontend_v2<3>; break;
-            case 4: kernel = k_frontend_v2<4>; break;
-            case 5: kernel = k_frontend_v2<5>; break;
-            default: kernel = k_frontend_v2<6>; break;
+            case 1: kernel = k_frontend_std<1>; break;
+            case 2: kernel = k_frontend_std<2>; break;
+            case 3: kernel = k_frontend_std<3>; break;
+            case 4: kernel = k_frontend_std<4>; break;
+            case 5: kernel = k_frontend_std<5>; break;
+            default: kernel = k_frontend_std<6>; break;
             }
         } else {
             switch (ms.S) {
-            case 1: kernel = k_frontend_std<1, 1>; break;
-            case 2: kernel = k_frontend_std<2, 1>; break;
-            case 3: kernel = k_frontend_std<3, 1>; break;
-            default: kernel = k_frontend_std<4, 1>; break;
+            case 1: kernel = k_frontend_direct<1>; break;
+            case 2: kernel = k_frontend_direct<2>; break;
+            case 3: kernel = k_frontend_direct<3>; break;
+            case 4: kernel = k_frontend_direct<4>; break;
+            case 5: kernel = k_frontend_direct<5>; break;
+            default: kernel = k_frontend_direct<6>; break;
             }
         }
     }
@@ -85,9 +70,6 @@ long long emu_frontend(float rate, float As, int mix_mode, float freq, int quant
         p.x_stride = 0; p.y_stride = 0;
         p.mix_mode = mix_mode; p.theta0 = 0; p.dtheta = design::nco_constrain(freq); p.quantize = quantize;
         p.bank = ms.bank.data();
-        std::vector<float> b16(ms.bank.size() / kHsub * 16, 0.f);
-        for (size_t r = 0; r < ms.bank.size() / kHsub; r++) for (int j = 0; j < kHsub; j++) b16[r * 16 + j] = ms.bank[r * kHsub + j];
-        p.bank16 = b16.data();
         if (p.ntiles > 0)
             csdr_emu::launch(dim3(std::min(p.ntiles, 3)), dim3(nthreads), g.smem_bytes, kernel, p);
         csdr_emu::launch(dim3((g.hcap + 127) / 128), dim3(128), 0, k_hist_update, (const float2 *)hist[cur_h].data(),

@@ -45,7 +45,7 @@ class Emu:
         cap = int(2 * np.ceil(rate * x.size)) + 64
         y = np.zeros(cap, np.complex64)
         n = self.L.emu_frontend(rate, As, mix_mode, freq, quantize, Tc, nthreads, x.ctypes.data, x.size, ch.ctypes.data,
-                                len(chunks), y.ctypes.data, cap, seek, int(std), misalign)      # std: 0 generic, 1 register prefetch, 2 TMA staging, 3 fused mix, 4 direct read
+                                len(chunks), y.ctypes.data, cap, seek, int(std), misalign)      # std: 0 generic kernel, 1 k_frontend_std (register prefetch), 2 k_frontend_direct
         assert n >= 0, "emu_frontend failed"
         return y[:n]
 

@@ -13,14 +13,9 @@ from util import assert_parity, make_signal
     # compile-time-geometry kernel k_frontend_std<S>, S = 1..6
     (0.3, 60.0, 0, 256, 1, True), (0.2, 60.0, 0, 256, 2, True), (0.078125, 60.0, 0, 256, 1, True),
     (0.04, 60.0, 0, 256, 0, True), (0.02, 60.0, 0, 256, 1, True), (0.011, 60.0, 0, 256, 1, True),
-    # TMA-staged variant k_frontend_std<S, 1>, S = 1..4
-    (0.3, 60.0, 0, 256, 1, 2), (0.2, 60.0, 0, 256, 0, 2), (0.078125, 60.0, 0, 256, 1, 2), (0.04, 60.0, 0, 256, 2, 2),
-    # fused-mix variant k_frontend_v2<S>, S = 2..6
-    (0.2, 60.0, 0, 256, 1, 3), (0.078125, 60.0, 0, 256, 1, 3), (0.078125, 60.0, 0, 256, 0, 3), (0.04, 60.0, 0, 256, 2, 3),
-    (0.02, 60.0, 0, 256, 1, 3), (0.011, 60.0, 0, 256, 2, 3),
-    # direct-read variant k_frontend_v3<S>, S = 1..6
-    (0.3, 60.0, 0, 256, 1, 4), (0.2, 60.0, 0, 256, 2, 4), (0.078125, 60.0, 0, 256, 1, 4), (0.078125, 60.0, 0, 256, 0, 4),
-    (0.04, 60.0, 0, 256, 2, 4), (0.02, 60.0, 0, 256, 1, 4), (0.011, 60.0, 0, 256, 1, 4)])
+    # k_frontend_direct<S>, S = 1..6
+    (0.3, 60.0, 0, 256, 1, 2), (0.2, 60.0, 0, 256, 2, 2), (0.078125, 60.0, 0, 256, 1, 2), (0.078125, 60.0, 0, 256, 0, 2),
+    (0.04, 60.0, 0, 256, 2, 2), (0.02, 60.0, 0, 256, 1, 2), (0.011, 60.0, 0, 256, 1, 2)])
 def test_frontend_matches_oracle(orc, emu, rate, As, Tc, nthreads, mix, std):
     x = make_signal(40000, 7)
     f = float(np.float32(0.24543693))
@@ -37,7 +32,7 @@ def test_frontend_chunk_invariance_is_bit_exact(emu):
     x = make_signal(20000, 8)
     sizes = [1, 7, 1000, 3, 4096, 5000]
     sizes.append(len(x) - sum(sizes))
-    for std in (False, True):
+    for std in (0, 1, 2):
         a = emu.frontend(x, 0.078125, freq=0.3, std=std)
         b = emu.frontend(x, 0.078125, freq=0.3, chunks=sizes, std=std)
         assert np.array_equal(a, b)

@@ -40,22 +40,20 @@ def test_msresamp_generic_kernel(cs, orc):
         cs.set_option(5, 0)
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2])
 @pytest.mark.parametrize("rate", [0.3, 0.15, 0.078125, 0.04, 0.02, 0.011])
-def test_msresamp_other_input_pipelines(cs, orc, rate, variant):
-    """CSDR_OPT_FRONTEND_VARIANT: 0 = raw tiles prefetched into registers (two CTAs per SM), 1 = staged in shared
-    memory by cp.async.bulk (three CTAs per SM); the default, 2, copies them asynchronously into the top level's
-    layout and mixes inside the first half-band stage (four CTAs per SM)."""
-    cs.set_option(9, variant)
+def test_msresamp_register_prefetch_kernel(cs, orc, rate):
+    """CSDR_OPT_FRONTEND_VARIANT = 0: k_frontend_std (raw tiles prefetched into registers, separate mixing pass, two
+    CTAs per SM) instead of the default k_frontend_direct (TMA-staged tile read in place, three CTAs per SM)."""
+    cs.set_option(9, 0)
     try:
         x = make_signal(300000, 23)
         ref = orc.MsResamp(rate).execute(x)
         a = np.concatenate(run_pipe(cs, cs.resampler(rate, 60.0), x, [len(x)]))
         b = np.concatenate(run_pipe(cs, cs.resampler(rate, 60.0), x, [1024 * 9, 77]))
         assert np.array_equal(a, b)
-        assert_parity(a, ref, what=f"msresamp (input pipeline {variant}) {rate}")
+        assert_parity(a, ref, what=f"msresamp (k_frontend_std) {rate}")
     finally:
-        cs.set_option(9, 3)
+        cs.set_option(9, 1)
 
 
 @pytest.mark.parametrize("rate", [0.078125, 0.02, 0.625, 0.5, 0.3, 0.15, 0.04, 0.011])
