@@ -325,7 +325,7 @@ int csdr_chain_seek(csdr_chain q, uint64_t n_prior)
 {
     API_BEGIN
     if (q->C > 1) throw CudaError{"chain: seek with a channelizer is not implemented"};
-    if (q->has_resamp) q->fe.cursor = fe_seek(q->fe.geo, n_prior);
+    if (q->has_resamp) { if (q->fe.interp) { q->fe.cursor = FrontendCursor(); q->fe.cursor.n_abs = n_prior; } else q->fe.cursor = fe_seek(q->fe.geo, n_prior); }
     else q->mix_theta = (uint32_t)n_prior * q->mix_dtheta;
     return 0;
     API_END(-1)

@@ -7,6 +7,7 @@
 #include "frontend.cuh"
 #include "frontend_std.cuh"
 #include "frontend_plan.hpp"
+#include "interp.cuh"
 #include "backend.cuh"
 #include "pfb.cuh"
 #include <stdexcept>
@@ -134,6 +135,13 @@ int grid_for(long long n, int block, int sms, int per_sm = 8)
     return (int)std::max<long long>(1, std::min(g, cap));
 }
 
+// launch-sequence helpers shared with the CPU-only emulation take a callable `launch(kernel, grid, block, smem, args...)`
+struct StreamLauncher {
+    cudaStream_t st;
+    template <class... A, class... B>
+    void operator()(void (*k)(A...), dim3 g, dim3 b, size_t sm, B &&...a) const { launch(k, g, b, sm, st, std::forward<B>(a)...); }
+};
+
 // ---------------------------------------------------------------------------------- front end (mix + msresamp)
 struct Frontend {
     design::MsresampPlan ms;
@@ -142,6 +150,7 @@ struct Frontend {
     DevBuf hist[2]; int cur = 0;
     DevBuf bank;
     FrontendCursor cursor;
+    bool interp = false; InterpPlan ip; DevBuf ibuf[2], xmix;      // rate > 1: arbitrary stage first, then half-band interpolators
     int mix_mode = 0; uint32_t theta0 = 0, dtheta = 0; int quantize = 1;
     void (*kernel)(FrontendParams) = k_frontend;
     int ctas_per_sm = 2, fe_threads = 256;
@@ -170,6 +179,27 @@ struct Frontend {
     void init(const Ctx &c, float rate, float As, int streams)
     {
         ms = design::plan_msresamp(rate, As, g_options[CSDR_OPT_RESAMP_FC_OLD] != 0);
+        nstreams = streams;
+        interp = ms.interp;
+        if (interp) {
+            if (ms.S > (unsigned)kMaxStages) throw CudaError{"msresamp: too many half-band stages"};
+            if (2 * ms.m_arb != (unsigned)kHsub) throw CudaError{"msresamp: unexpected arbitrary-stage length"};
+            ip = InterpPlan{};
+            ip.S = (int)ms.S; ip.step = ms.step; ip.bits = (int)ms.bits;
+            for (int st = 0; st < ip.S; st++) {
+                ip.m[st] = (int)ms.st[st].m;
+                if (ip.m[st] > kMaxHbM) throw CudaError{"msresamp: half-band stage too long"};
+                for (int u = 0; u < 2 * ip.m[st]; u++) ip.h1[st][u] = ms.st[st].h1[u];
+            }
+            geo = FrontendGeometry{};
+            geo.hcap = kInterpHcap; geo.base.S = 0; geo.base.step = ms.step;
+            size_t hb = (size_t)geo.hcap * sizeof(float2) * nstreams;
+            for (auto &h : hist) { h.ensure(hb); CK(cudaMemsetAsync(h.p, 0, h.cap, c.stream)); }
+            bank.ensure(ms.bank.size() * sizeof(float));
+            CK(cudaMemcpyAsync(bank.p, ms.bank.data(), ms.bank.size() * sizeof(float), cudaMemcpyHostToDevice, c.stream));
+            c.sync();
+            return;
+        }
         int Tc = 464;
         if (ms.S != 3) {
             // aim for ~4096 input samples per tile, c-count multiple of 8
@@ -200,7 +230,6 @@ struct Frontend {
             default: throw CudaError{"frontend: no direct-read kernel for this stage count"};
             }
         }
-        nstreams = streams;
         size_t hb = (size_t)geo.hcap * sizeof(float2) * nstreams;
         for (auto &h : hist) { h.ensure(hb); CK(cudaMemsetAsync(h.p, 0, h.cap, c.stream)); }
         bank.ensure(ms.bank.size() * sizeof(float));
@@ -211,8 +240,29 @@ struct Frontend {
         if (ctas_per_sm < 1) throw CudaError{"frontend: tile does not fit in shared memory"};
         c.sync();
     }
+    long long run_interp(const Ctx &c, const float2 *x, long long nx, long long x_stride, float2 *y, long long y_stride)
+    {
+        if (nx <= 0) return 0;
+        if (mix_mode) {
+            // mix into a scratch copy first (stream s at s * nx); the carried history then holds mixed samples
+            xmix.ensure(sizeof(float2) * (size_t)nstreams * nx);
+            for (int s = 0; s < nstreams; s++)
+                launch(k_nco_mix, dim3(grid_for(nx, 256, c.sms)), dim3(256), 0, c.stream, x + (long long)s * x_stride,
+                       xmix.as<float2>() + (long long)s * nx, nx, theta0 + (uint32_t)cursor.n_abs * dtheta, dtheta, quantize, mix_mode == 2 ? 1 : 0);
+            x = xmix.as<float2>(); x_stride = nx;
+        }
+        StreamLauncher l{c.stream};
+        auto buf = [&](int slot, size_t bytes) -> void * { ibuf[slot].ensure(bytes); return ibuf[slot].p; };
+        const long long ny = interp_launch(l, buf, ip, bank.as<float>(), nstreams, x, x_stride, hist[cur].as<float2>(), cursor.n_abs, nx, y, y_stride);
+        launch(k_hist_update, dim3((geo.hcap + 255) / 256, nstreams), dim3(256), 0, c.stream,
+               (const float2 *)hist[cur].as<float2>(), hist[cur ^ 1].as<float2>(), x, x_stride, nx, geo.hcap);
+        cur ^= 1;
+        cursor.n_abs += (unsigned long long)nx;
+        return ny;
+    }
     long long max_out(long long nx) const
     {
+        if (interp) return interp_max_out(ip, nx);
         // pushes <= nx/2^S + 1, each push emits at most ceil(2^24/step) outputs
         double pushes = (double)(nx >> ms.S) + 1.0;
         return (long long)std::ceil(pushes * 16777216.0 / (double)ms.step) + 4;
@@ -220,6 +270,7 @@ struct Frontend {
     // x: device, nstreams x nx at x_stride; y: device, y_stride.  Returns outputs per stream.
     long long run(const Ctx &c, const float2 *x, long long nx, long long x_stride, float2 *y, long long y_stride)
     {
+        if (interp) return run_interp(c, x, nx, x_stride, y, y_stride);
         FrontendParams p = geo.base;
         long long ny = fe_prepare_call(geo, cursor, nx, p);
         p.x = x; p.hist = hist[cur].as<float2>(); p.y = y; p.hcap = geo.hcap;

@@ -5,6 +5,7 @@
 #include "frontend.cuh"
 #include "frontend_std.cuh"
 #include "frontend_plan.hpp"
+#include "interp.cuh"
 #include "backend.cuh"
 #include <vector>
 #include <cstdio>
@@ -25,6 +26,39 @@ long long emu_frontend(float rate, float As, int mix_mode, float freq, int quant
                        unsigned long long seek, int allow_std, long long misalign)
 {
     design::MsresampPlan ms = design::plan_msresamp(rate, As);
+    if (ms.interp) {
+        // rate > 1: arbitrary stage + half-band interpolators (interp.cuh), same launch sequence as the product
+        InterpPlan ip;
+        ip.S = (int)ms.S; ip.step = ms.step; ip.bits = (int)ms.bits;
+        for (int st = 0; st < ip.S; st++) { ip.m[st] = (int)ms.st[st].m; for (int u = 0; u < 2 * ip.m[st]; u++) ip.h1[st][u] = ms.st[st].h1[u]; }
+        std::vector<float2> hist[2], xm;
+        hist[0].assign(kInterpHcap, make_float2(0, 0)); hist[1] = hist[0];
+        std::vector<float2> scratch[2];
+        int cur_h = 0;
+        unsigned long long n_abs = seek;
+        long long pos = 0, total = 0;
+        EmuLaunch launch;
+        const unsigned dth = design::nco_constrain(freq);
+        for (int c = 0; c < nchunks; c++) {
+            const long long nx = chunks[c];
+            if (pos + nx > n) return -1;
+            if (nx == 0) continue;
+            const float2 *xc = x + pos;
+            if (mix_mode) {
+                xm.resize((size_t)nx);
+                launch(k_nco_mix, dim3(4), dim3(64), 0, xc, xm.data(), nx, (unsigned)n_abs * dth, dth, quantize, mix_mode == 2 ? 1 : 0);
+                xc = xm.data();
+            }
+            if (total + interp_max_out(ip, nx) > cap) return -1;
+            auto buf = [&](int slot, size_t bytes) -> void * { scratch[slot].resize(bytes / sizeof(float2) + 1); return scratch[slot].data(); };
+            const long long ny = interp_launch(launch, buf, ip, ms.bank.data(), 1, xc, 0, hist[cur_h].data(), n_abs, nx, y + total, 0);
+            launch(k_hist_update, dim3((kInterpHcap + 127) / 128), dim3(128), 0, (const float2 *)hist[cur_h].data(),
+                   hist[cur_h ^ 1].data(), xc, 0LL, nx, kInterpHcap);
+            cur_h ^= 1;
+            n_abs += (unsigned long long)nx; pos += nx; total += ny;
+        }
+        return total;
+    }
     FrontendGeometry g = plan_frontend(ms, Tc, allow_std != 0, allow_std >= 2 ? allow_std - 1 : 0);
     void (*kernel)(FrontendParams) = k_frontend;
     if (g.std_kernel) {

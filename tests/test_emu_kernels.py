@@ -28,6 +28,20 @@ def test_frontend_matches_oracle(orc, emu, rate, As, Tc, nthreads, mix, std):
         assert np.array_equal(emu.frontend(x, rate, As=As, mix_mode=mix, freq=f, Tc=Tc, nthreads=nthreads, std=std, misalign=1), y)
 
 
+@pytest.mark.parametrize("rate,mix", [(1.3, 0), (2.0, 1), (3.7, 2), (9.1, 0), (1.0000001, 0)])
+def test_frontend_interpolation_matches_oracle(orc, emu, rate, mix):
+    """msresamp_crcf with rate > 1: arbitrary stage first, then half-band interpolators (interp.cuh)"""
+    x = make_signal(6000, 17)
+    f = float(np.float32(0.24543693))
+    xm = {0: lambda v: v, 1: orc.Nco(f).mix_down, 2: orc.Nco(f).mix_up}[mix](x)
+    ref = orc.MsResamp(rate).execute(xm)
+    y = emu.frontend(x, rate, mix_mode=mix, freq=f)
+    assert_parity(y, ref, what=f"interpolating msresamp {rate}")
+    sizes = [1, 7, 1000, 3, 2048]
+    sizes.append(len(x) - sum(sizes))
+    assert np.array_equal(emu.frontend(x, rate, mix_mode=mix, freq=f, chunks=sizes), y)
+
+
 def test_frontend_chunk_invariance_is_bit_exact(emu):
     x = make_signal(20000, 8)
     sizes = [1, 7, 1000, 3, 4096, 5000]

@@ -56,6 +56,18 @@ def test_msresamp_register_prefetch_kernel(cs, orc, rate):
         cs.set_option(9, 1)
 
 
+@pytest.mark.parametrize("rate", [1.25, 2.0, 3.7, 10.0])
+def test_msresamp_interpolation(cs, orc, rate):
+    """rate > 1 (MSRESAMP(_interp_execute)): arbitrary stage, then half-band interpolators"""
+    x = make_signal(50000, 31)
+    ref = orc.MsResamp(rate).execute(x)
+    a = np.concatenate(run_pipe(cs, cs.resampler(rate, 60.0), x, [1024]))
+    b = np.concatenate(run_pipe(cs, cs.resampler(rate, 60.0), x, [len(x)]))
+    assert len(a) == len(ref)
+    assert np.array_equal(a, b)
+    assert_parity(a, ref, what=f"msresamp interpolation {rate}")
+
+
 @pytest.mark.parametrize("rate", [0.078125, 0.02, 0.625, 0.5, 0.3, 0.15, 0.04, 0.011])
 def test_msresamp(cs, orc, rate):
     x = make_signal(200000, 12)
