@@ -43,8 +43,11 @@ def run(name, chain, x, steps=5, warmup=2, b_alg=None):
 
 def sig(n, seed, scale=0.3):
     g = torch.Generator(device="cuda").manual_seed(seed)
-    k = torch.arange(n, device="cuda", dtype=torch.float32)
-    x = scale * torch.polar(torch.ones(n, device="cuda"), 0.6 * k + 2.0 * torch.sin(k * 2e-3))
+    k = torch.arange(n, device="cuda", dtype=torch.float64)      # float32 loses integer resolution above 2^24
+    # tone at 0.15 rad/sample (inside the 200 kHz passband after the 100 kHz offset mix), slow FM
+    ph = torch.remainder(0.15 * k + 2.0 * torch.sin(k * 2e-3), 2 * 3.141592653589793).to(torch.float32)
+    del k
+    x = scale * torch.polar(torch.ones(n, device="cuda"), ph)
     x = x + 0.02 * torch.complex(torch.randn(n, generator=g, device="cuda"), torch.randn(n, generator=g, device="cuda"))
     return x.to(torch.complex64)
 
@@ -52,6 +55,7 @@ def sig(n, seed, scale=0.3):
 def main():
     n = 1 << 26
     x = sig(n, 1)
+    torch.cuda.synchronize()       # the chains run on their own streams
     run("C1 mix+msresamp+dcblock (DeNo)", cs.Chain(2.56e6, 1e5, 200e3), x, b_alg=8 + 8 * 0.078125)
     run("C2 + AGC + NBFM", cs.Chain(2.56e6, 1e5, 200e3, cs.DeNBFM(0.3), agc=-40.0), x, b_alg=8 + 4 * 0.078125)
     x3 = sig(1 << 24, 3)
