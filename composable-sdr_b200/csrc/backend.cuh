@@ -354,13 +354,13 @@ __device__ __forceinline__ void agc_step(const BackendParams &p, float &g, float
         g = fminf(g, 1e6f);
     } else {
         // the recurrence closes through g^2, so g^2 is carried as a state of its own and updated with the squared
-        // factor (a second, independent exp2): the dependent chain per sample is FMA -> lg2 -> mul -> ex2 -> mul -> min,
-        // and the gain itself only trails it.  (g2 / g^2 drifts by rounding, ~1e-7 sqrt(samples); it is re-derived from
-        // g at the start of every segment.)
+        // factor: the dependent chain per sample is FMA -> lg2 -> mul -> ex2 -> mul -> mul -> min, and the gain itself
+        // only trails it.  (g2 / g^2 drifts by rounding, ~1e-7 sqrt(samples); it is re-derived from g at the start of
+        // every segment.)
         y2p = fmaf(__fmul_rn(p.alpha, pw), g2, __fmul_rn(p.one_minus_alpha_f, y2p));
         const float lg = be_lg2(y2p);
         const bool ok = y2p > 1e-6f;
-        const float f2 = be_ex2(__fmul_rn(2.0f * p.neg_half_alpha, lg)), f = be_ex2(__fmul_rn(p.neg_half_alpha, lg));
+        const float f = be_ex2(__fmul_rn(p.neg_half_alpha, lg)), f2 = __fmul_rn(f, f);
         g2 = fminf(ok ? __fmul_rn(g2, f2) : g2, 1e12f);
         g = fminf(ok ? __fmul_rn(g, f) : g, 1e6f);
     }
@@ -421,95 +421,78 @@ __device__ __forceinline__ void agc_guess(float e, float &g, float &y2p)
     y2p = 1.0f;
 }
 
-// One thread per segment, segments of any length, powers and gains in global memory (every lane walks its own cache
-// lines): used when the staged kernel below does not apply, and by the repair kernels.
+// One thread per L-sample segment, kAgcT consecutive segments of a lane per CTA.  The threads walk their windows
+// [b0 - W, b1) in lock-step, 32 samples at a time: each warp fetches the 32-sample blocks of its 32 threads with one
+// coalesced 128-byte load per thread-row into a padded shared-memory tile (row stride 33: column access is
+// conflict-free), every thread runs the recurrence over its row, and in the emitting part of the window the rows are
+// overwritten with the gains and written back the same way.  17 KB of shared memory per CTA whatever L and W are, so
+// every chain of a call is resident at once and the kernel is bound by the latency of one window, not by waves.
+constexpr int kAgcT = 128, kAgcB = 32;
 template <bool EXACT>
-__global__ void __launch_bounds__(128) k_agc_chain(const BackendParams p)
+__global__ void __launch_bounds__(kAgcT) k_agc_chain(const BackendParams p)
 {
-    const int lane = blockIdx.y, seg = blockIdx.x * blockDim.x + threadIdx.x;
-    if (seg == 0) { if (lane == 0) { p.bad_count[0] = 0; p.bad_count[1] = 0; } be_save_first(p, lane); }
-    if (seg >= p.nseg) return;
-    const long long t = (long long)lane * p.nseg + seg;
-    const int b0 = seg * p.L, b1 = min(b0 + p.L, p.n);
-    float g, y2p;
-    int w0 = b0 - p.W;
-    if (w0 <= 0) {
-        // the warm-up reaches the chunk start: run from the true carried state (exact)
-        w0 = 0;
-        const LaneState ls = p.lane[lane];
-        g = ls.g; y2p = ls.y2p;
-    } else {
-        const float4 *q = reinterpret_cast<const float4 *>(p.pw + (long long)lane * p.pw_stride + w0);
-        float e = 0.f;
-        for (int i = 0; i < 4; i++) { const float4 v = __ldg(q + i); e += (v.x + v.y) + (v.z + v.w); }
-        agc_guess(e * (1.0f / 16.0f), g, y2p);
-    }
-    agc_run<false, EXACT>(p, lane, g, y2p, w0, b0);  // warm-up, nothing stored
-    SegState s0; s0.g = g; s0.y2p = y2p;
-    p.seg_start[t] = s0;
-    agc_run<true, EXACT>(p, lane, g, y2p, b0, b1);
-    SegState s1; s1.g = g; s1.y2p = y2p;
-    p.seg_end[t] = s1;
-}
-
-// The same, staged through shared memory (L a power of two, W a multiple of L): the CTA's blockDim.x consecutive
-// segments and the warm-up window before them are one contiguous stretch of the power sequence, copied in with
-// coalesced loads; time u (relative to the stretch) lives at index u + u / L, so threads that are L samples apart
-// hit different banks.  All warm-ups first (they read other threads' segments), then every thread overwrites its
-// own segment with the gains, which go back to global memory coalesced.
-template <bool EXACT>
-__global__ void __launch_bounds__(128) k_agc_chain_staged(const BackendParams p, int lgL)
-{
-    CSDR_DYN_SMEM(smem_raw);
-    float *sm = reinterpret_cast<float *>(smem_raw);
-    const int lane = blockIdx.y, T = blockDim.x, tid = threadIdx.x, seg = blockIdx.x * T + tid;
+    __shared__ float sm[kAgcT][kAgcB + 1];
+    const int lane = blockIdx.y, tid = threadIdx.x, w = tid >> 5, l = tid & 31;
+    const int seg0 = blockIdx.x * kAgcT, seg = seg0 + tid;
     if (blockIdx.x == 0 && tid == 0) { if (lane == 0) { p.bad_count[0] = 0; p.bad_count[1] = 0; } be_save_first(p, lane); }
-    const int B0 = blockIdx.x * T * p.L, B1 = min(B0 + T * p.L, p.n);
-    const int tO = B0 - p.W;                                  // time of stretch index 0 (may be negative)
     const float *__restrict__ pw = p.pw + (long long)lane * p.pw_stride;
-    for (int u = max(0, -tO) + tid; u < B1 - tO; u += T) sm[u + (u >> lgL)] = pw[tO + u];
-    __syncthreads();
-    const int b0 = seg * p.L, b1 = min(b0 + p.L, p.n);
+    float *__restrict__ go = p.gpost + (long long)lane * p.pw_stride;
+    const int b0 = seg * p.L;
     const bool live = seg < p.nseg;
-    float g = 1.f, y2p = 1.f;
-    if (live) {
-        int u = b0 - p.W - tO;
-        if (b0 - p.W <= 0) {
-            u = -tO;                                          // time 0: the true carried state (exact)
-            const LaneState ls = p.lane[lane];
-            g = ls.g; y2p = ls.y2p;
-        } else {
-            const float *q = sm + u + (u >> lgL);
-            float e = 0.f;
-            for (int i = 0; i < 16; i++) e += q[i];
-            agc_guess(e * (1.0f / 16.0f), g, y2p);
+    const int nsteps = (p.W + p.L) / kAgcB, wsteps = p.W / kAgcB;
+    float g = 1.f, g2 = 1.f, y2p = 1.f;
+    bool started = false;
+    for (int s = 0; s < nsteps; s++) {
+        // rows of this warp: thread r = 32 w + i, block start u_r = (seg0 + r) L - W + 32 s
+#pragma unroll 4
+        for (int i = 0; i < 32; i++) {
+            const int r = 32 * w + i;
+            const long long u = (long long)(seg0 + r) * p.L - p.W + (long long)s * kAgcB + l;
+            if (u >= 0 && u < p.n) sm[r][l] = pw[u];
         }
-        const int uw = b0 - tO;
-        float g2 = __fmul_rn(g, g);
-        while (u < uw) {                                      // warm-up, one L-block (or what is left of it) at a time
-            const int ue = min(((u >> lgL) + 1) << lgL, uw);
-            const float *q = sm + u + (u >> lgL);
-            const int cnt = ue - u;
-#pragma unroll 8
-            for (int k = 0; k < cnt; k++) agc_step<EXACT>(p, g, g2, y2p, q[k]);
-            u = ue;
+        __syncthreads();
+        const int u0 = b0 - p.W + s * kAgcB;                    // time of this thread's sm[tid][0]
+        const bool emit = s >= wsteps;
+        if (live && u0 >= 0 && u0 < p.n) {
+            if (!started) {
+                started = true;
+                if (b0 - p.W <= 0) { const LaneState ls = p.lane[lane]; g = ls.g; y2p = ls.y2p; }   // time 0: exact
+                else {
+                    float e = 0.f;
+#pragma unroll
+                    for (int k = 0; k < 16; k++) e += sm[tid][k];
+                    agc_guess(e * (1.0f / 16.0f), g, y2p);
+                }
+                g2 = __fmul_rn(g, g);
+            }
+            if (emit && s == wsteps) {
+                SegState s0; s0.g = g; s0.y2p = y2p;
+                p.seg_start[(long long)lane * p.nseg + seg] = s0;
+                g2 = __fmul_rn(g, g);
+            }
+            const int cnt = min(kAgcB, p.n - u0);
+            if (cnt == kAgcB) {
+#pragma unroll
+                for (int k = 0; k < kAgcB; k++) { agc_step<EXACT>(p, g, g2, y2p, sm[tid][k]); if (emit) sm[tid][k] = g; }
+            } else {
+                for (int k = 0; k < cnt; k++) { agc_step<EXACT>(p, g, g2, y2p, sm[tid][k]); if (emit) sm[tid][k] = g; }
+            }
         }
-        SegState s0; s0.g = g; s0.y2p = y2p;
-        p.seg_start[(long long)lane * p.nseg + seg] = s0;
+        __syncthreads();
+        if (emit) {
+#pragma unroll 4
+            for (int i = 0; i < 32; i++) {
+                const int r = 32 * w + i;
+                const long long u = (long long)(seg0 + r) * p.L - p.W + (long long)s * kAgcB + l;
+                if (seg0 + r < p.nseg && u >= 0 && u < p.n) go[u] = sm[r][l];
+            }
+            __syncthreads();
+        }
     }
-    __syncthreads();
     if (live) {
-        const int u = b0 - tO, cnt = b1 - b0;                 // one L-block
-        float *q = sm + u + (u >> lgL);
-        float g2 = __fmul_rn(g, g);
-#pragma unroll 8
-        for (int k = 0; k < cnt; k++) { agc_step<EXACT>(p, g, g2, y2p, q[k]); q[k] = g; }
         SegState s1; s1.g = g; s1.y2p = y2p;
         p.seg_end[(long long)lane * p.nseg + seg] = s1;
     }
-    __syncthreads();
-    float *__restrict__ go = p.gpost + (long long)lane * p.pw_stride;
-    for (int u = p.W + tid; u < B1 - tO; u += T) go[tO + u] = sm[u + (u >> lgL)];
 }
 
 // no AGC: the chain kernel is not run, the first-sample state is saved by a launch of its own
@@ -842,7 +825,16 @@ __global__ void k_lane_sum(const float *__restrict__ in, long long lane_stride, 
     long long stride = (long long)gridDim.x * blockDim.x;
     for (; i < n; i += stride) {
         float acc = in[i];
-        for (int c = 1; c < nlanes; c++) acc = __fadd_rn(acc, in[(long long)c * lane_stride + i]);
+        // same left fold, loads issued eight lanes ahead of the adds
+        int c = 1;
+        for (; c + 8 <= nlanes; c += 8) {
+            float v[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) v[k] = in[(long long)(c + k) * lane_stride + i];
+#pragma unroll
+            for (int k = 0; k < 8; k++) acc = __fadd_rn(acc, v[k]);
+        }
+        for (; c < nlanes; c++) acc = __fadd_rn(acc, in[(long long)c * lane_stride + i]);
         out[i] = acc;
     }
 }
@@ -870,30 +862,10 @@ inline void be_launch_dc(Launch &launch, const DcParams &d, bool apply)
     if (apply) be_launch_prep(launch, d);
 }
 
-// threads per CTA of the staged chain kernel for segment length L (0: not applicable) and its shared memory
-inline int be_chain_threads(int L, int W)
-{
-    if (L < 32 || (L & (L - 1)) || L > 1024 || W % L) return 0;
-    return L <= 128 ? 128 : L == 256 ? 64 : 32;
-}
-inline size_t be_chain_smem(int L, int W, int T)
-{
-    const size_t len = (size_t)W + (size_t)T * L;
-    return (len + len / L + 8) * sizeof(float);
-}
-
 template <bool EXACT, class Launch>
 inline void be_launch_gain(Launch &launch, const BackendParams &b)
 {
-    int T = be_chain_threads(b.L, b.W);
-    if (T && be_chain_smem(b.L, b.W, T) > 200 * 1024) T = 0;
-    if (T) {
-        int lgL = 0;
-        while ((1 << lgL) < b.L) lgL++;
-        launch(k_agc_chain_staged<EXACT>, dim3((b.nseg + T - 1) / T, b.nlanes), dim3(T), be_chain_smem(b.L, b.W, T), b, lgL);
-    } else {
-        launch(k_agc_chain<EXACT>, dim3((b.nseg + 127) / 128, b.nlanes), dim3(128), 0, b);
-    }
+    launch(k_agc_chain<EXACT>, dim3((b.nseg + kAgcT - 1) / kAgcT, b.nlanes), dim3(kAgcT), 0, b);   // L, W: multiples of 32
     // two rounds of verify + parallel refine (a run of consecutive misses needs one round per level of
     // inaccuracy handed down the run; an empty list costs a few microseconds), then the in-order repair
     const dim3 gv((b.nseg + 127) / 128, b.nlanes);

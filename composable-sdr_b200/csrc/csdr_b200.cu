@@ -345,8 +345,7 @@ struct Backend {
         }
         fixups.ensure(3 * sizeof(unsigned long long)); CK(cudaMemsetAsync(fixups.p, 0, fixups.cap, c.stream));
         bad_list.ensure(sizeof(unsigned) * 65536); bad_count.ensure(2 * sizeof(unsigned)); CK(cudaMemsetAsync(bad_count.p, 0, bad_count.cap, c.stream));
-        CK(cudaFuncSetAttribute(k_agc_chain_staged<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        CK(cudaFuncSetAttribute(k_agc_chain_staged<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+
         c.sync();
     }
     struct Launcher {
@@ -428,9 +427,6 @@ struct Backend {
             }
             W = W_cur;
         }
-        // the staged gain-loop kernel wants the warm-up in whole segments
-        if (has_agc && be_chain_threads(L, (W + L - 1) / L * L) && be_chain_smem(L, (W + L - 1) / L * L, be_chain_threads(L, (W + L - 1) / L * L)) <= 200 * 1024)
-            W = (W + L - 1) / L * L;
         last_L = L; last_W = W;
         int ngrp = (n + G - 1) / G, nseg = (n + L - 1) / L, nwords = (n + 31) / 32;
         size_t segs = (size_t)nlanes * nseg;
@@ -523,6 +519,7 @@ struct Channelizer {
     DevBuf hd, tw, xr[2]; int cur = 0;       // xr: [(P-1)*M history | new samples], ping-pong for the history
     int log2M = -1, F = 1;
     size_t smem = 0;
+    void (*tile_kernel)(PfbTileParams) = nullptr; PfbTileParams tp{}; size_t tile_smem = 0;   // M = 2..32, m = 7
 
     void init(const Ctx &c, unsigned M_, unsigned m_, float As_)
     {
@@ -545,6 +542,21 @@ struct Channelizer {
         smem = (size_t)F * M * sizeof(float2) * (log2M >= 0 ? 1 : 2);
         if (smem > 200 * 1024) throw CudaError{"firpfbch: channel count too large for one CTA tile"};
         CK(cudaFuncSetAttribute(k_pfb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        tile_kernel = nullptr;
+        if (log2M >= 1 && (int)M <= kPfbTileMaxM && (int)P == kPfbTileP) {
+            switch (log2M) {
+            case 1: tile_kernel = k_pfb_tile<1>; break;
+            case 2: tile_kernel = k_pfb_tile<2>; break;
+            case 3: tile_kernel = k_pfb_tile<3>; break;
+            case 4: tile_kernel = k_pfb_tile<4>; break;
+            default: tile_kernel = k_pfb_tile<5>; break;
+            }
+            tp = PfbTileParams{};
+            for (unsigned i = 0; i < M / 2; i++) tp.tw[i] = t[i];
+            for (unsigned k = 0; k < P; k++) for (unsigned n = 0; n < M; n++) tp.h[k * M + n] = h[(M - 1 - n) + k * M];
+            tile_smem = (size_t)(kPfbTileF + kPfbTileP - 1) * (M + 2) * sizeof(float2);
+            CK(cudaFuncSetAttribute(tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem));
+        }
         size_t hb = (size_t)(P - 1) * M * sizeof(float2);
         for (auto &b : xr) { b.ensure(hb); CK(cudaMemsetAsync(b.p, 0, b.cap, c.stream)); }
         c.sync();
@@ -570,7 +582,12 @@ struct Channelizer {
         p.xr = xr[cur].as<float2>(); p.y = y; p.y_stride = y_stride;
         p.M = (int)M; p.P = (int)P; p.nf = nf; p.F = F; p.log2M = log2M;
         p.h = hd.as<float>(); p.tw = tw.as<float2>();
-        launch(k_pfb, dim3((nf + F - 1) / F), dim3(256), smem, c.stream, p);
+        if (tile_kernel) {
+            tp.xr = p.xr; tp.y = y; tp.y_stride = y_stride; tp.nf = nf;
+            launch(tile_kernel, dim3((nf + kPfbTileF - 1) / kPfbTileF), dim3(kPfbTileF), tile_smem, c.stream, tp);
+        } else {
+            launch(k_pfb, dim3((nf + F - 1) / F), dim3(256), smem, c.stream, p);
+        }
         int H = (int)hist_samples();
         xr[cur ^ 1].ensure((size_t)H * sizeof(float2));
         launch(k_copy_tail, dim3((H + 255) / 256), dim3(256), 0, c.stream, (const float2 *)xr[cur].as<float2>(),

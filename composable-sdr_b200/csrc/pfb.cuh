@@ -95,6 +95,86 @@ __global__ void __launch_bounds__(256) k_pfb(const PfbParams p)
     }
 }
 
+// ---- small power-of-two M (2..32): one thread per frame -------------------------------------------------------
+// The CTA stages F + P - 1 consecutive frames in shared memory once (coalesced 16-byte loads; rows padded to M + 2
+// samples so that threads one frame apart hit different 16-byte banks).  Thread f then evaluates all M polyphase
+// branches of frame f from P rows (taps straight from the kernel-parameter constant bank, packed FP32 FMAs), runs the
+// M-point DFT in registers (radix-2 DIT, every index a compile-time constant) and stores channel-major: for each
+// channel the warp writes 32 consecutive frames = 256 contiguous bytes.
+constexpr int kPfbTileP = 14;              // 2 m taps per branch (m = 7, Liquid.chs:865)
+constexpr int kPfbTileF = 256;             // frames per CTA = threads per CTA
+constexpr int kPfbTileMaxM = 32;
+
+struct PfbTileParams {
+    const float2 *xr; float2 *y; long long y_stride; int nf;
+    float2 tw[kPfbTileMaxM / 2];           // exp(-j 2 pi t / M)
+    float h[kPfbTileP * kPfbTileMaxM];     // h[k * M + n] = prototype[(M - 1 - n) + k * M]
+};
+
+template <int LM> __host__ __device__ constexpr int pfb_rev(int i)
+{
+    int r = 0;
+    for (int b = 0; b < LM; b++) r |= ((i >> b) & 1) << (LM - 1 - b);
+    return r;
+}
+
+template <int LM>
+__global__ void __launch_bounds__(kPfbTileF) k_pfb_tile(const CSDR_GRID_CONSTANT PfbTileParams p)
+{
+    constexpr int M = 1 << LM, P = kPfbTileP, F = kPfbTileF, RS = M + 2;
+    CSDR_DYN_SMEM(smem_raw);
+    float2 *in = reinterpret_cast<float2 *>(smem_raw);           // [(F + P - 1)][RS]
+    const int t0 = blockIdx.x * F;
+    const int nfr = min(F, p.nf - t0);
+    // rows t0 .. t0 + nfr + P - 2 of xr (row r of xr = history or new frame r - (P-1))
+    {
+        const float4 *src = reinterpret_cast<const float4 *>(p.xr + (long long)t0 * M);
+        const int pairs = (nfr + P - 1) * (M / 2);
+        for (int e = threadIdx.x; e < pairs; e += F) {
+            const int r = e >> (LM - 1), c2 = e & (M / 2 - 1);
+            *reinterpret_cast<float4 *>(in + r * RS + 2 * c2) = src[e];
+        }
+    }
+    __syncthreads();
+    const int f = threadIdx.x;
+    if (f >= nfr) return;
+    float2 a[M];
+#pragma unroll
+    for (int n = 0; n < M; n++) a[n] = cf(0.f, 0.f);
+#pragma unroll
+    for (int k = 0; k < P; k++) {
+        const float4 *row = reinterpret_cast<const float4 *>(in + (f + P - 1 - k) * RS);
+#pragma unroll
+        for (int j = 0; j < M / 2; j++) {
+            const float4 q = row[j];
+            ffma2(a[2 * j], p.h[k * M + 2 * j], cf(q.x, q.y));
+            ffma2(a[2 * j + 1], p.h[k * M + 2 * j + 1], cf(q.z, q.w));
+        }
+    }
+    // M-point forward DFT, radix-2 decimation in time
+    float2 b[M];
+#pragma unroll
+    for (int i = 0; i < M; i++) b[i] = a[pfb_rev<LM>(i)];
+#pragma unroll
+    for (int s = 1; s <= LM; s++) {
+        const int len = 1 << s, half = len >> 1, tws = M / len;
+#pragma unroll
+        for (int grp = 0; grp < M; grp += len) {
+#pragma unroll
+            for (int j = 0; j < half; j++) {
+                const float2 w = p.tw[j * tws];
+                const float2 u = b[grp + j], v = b[grp + j + half];
+                const float tr = v.x * w.x - v.y * w.y, ti = v.x * w.y + v.y * w.x;
+                b[grp + j] = cf(u.x + tr, u.y + ti);
+                b[grp + j + half] = cf(u.x - tr, u.y - ti);
+            }
+        }
+    }
+    float2 *yo = p.y + t0 + f;
+#pragma unroll
+    for (int c = 0; c < M; c++) yo[(long long)c * p.y_stride] = b[c];
+}
+
 // keep the last (P-1)*M pre-rotated samples for the next call: dst[0..H) <- src[n .. n+H)
 __global__ void k_copy_tail(const float2 *__restrict__ src, float2 *__restrict__ dst, long long offset, int count)
 {
