@@ -343,13 +343,14 @@ __device__ __forceinline__ float be_ex2(float x)
     float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r;
 #endif
 }
+struct AgcCoef { float alpha, oma, nha; };          // alpha, 1 - alpha, -alpha / 2: kept in registers by the loops
 template <bool EXACT>
-__device__ __forceinline__ void agc_step(const BackendParams &p, float &g, float &g2, float &y2p, float pw)
+__device__ __forceinline__ void agc_step(const AgcCoef &p, float &g, float &g2, float &y2p, float pw)
 {
     if (EXACT) {
         const float y2 = __fmul_rn(__fmul_rn(g, g), pw);
-        y2p = fmaf(p.one_minus_alpha_f, y2p, __fmul_rn(p.alpha, y2));
-        const float f = expf(p.neg_half_alpha * logf(y2p));
+        y2p = fmaf(p.oma, y2p, __fmul_rn(p.alpha, y2));
+        const float f = expf(p.nha * logf(y2p));
         g *= (y2p > 1e-6f) ? f : 1.0f;
         g = fminf(g, 1e6f);
     } else {
@@ -357,10 +358,10 @@ __device__ __forceinline__ void agc_step(const BackendParams &p, float &g, float
         // factor: the dependent chain per sample is FMA -> lg2 -> mul -> ex2 -> mul -> mul -> min, and the gain itself
         // only trails it.  (g2 / g^2 drifts by rounding, ~1e-7 sqrt(samples); it is re-derived from g at the start of
         // every segment.)
-        y2p = fmaf(__fmul_rn(p.alpha, pw), g2, __fmul_rn(p.one_minus_alpha_f, y2p));
+        y2p = fmaf(__fmul_rn(p.alpha, pw), g2, __fmul_rn(p.oma, y2p));
         const float lg = be_lg2(y2p);
         const bool ok = y2p > 1e-6f;
-        const float f = be_ex2(__fmul_rn(p.neg_half_alpha, lg)), f2 = __fmul_rn(f, f);
+        const float f = be_ex2(__fmul_rn(p.nha, lg)), f2 = __fmul_rn(f, f);
         g2 = fminf(ok ? __fmul_rn(g2, f2) : g2, 1e12f);
         g = fminf(ok ? __fmul_rn(g, f) : g, 1e6f);
     }
@@ -373,6 +374,7 @@ __device__ __forceinline__ void agc_run(const BackendParams &p, int lane, float 
 {
     const float *__restrict__ pw = p.pw + (long long)lane * p.pw_stride;
     float *__restrict__ go = p.gpost + (long long)lane * p.pw_stride;
+    const AgcCoef co{p.alpha, p.one_minus_alpha_f, p.neg_half_alpha};
     int i = i0;
     float g2 = __fmul_rn(g, g);
     if (i + 8 <= i1) {
@@ -383,7 +385,7 @@ __device__ __forceinline__ void agc_run(const BackendParams &p, int lane, float 
             if (i + 16 <= i1) { const float4 *q4 = reinterpret_cast<const float4 *>(pw + i + 8); na = __ldg(q4); nb = __ldg(q4 + 1); }
             float o[8];
 #pragma unroll
-            for (int k = 0; k < 8; k++) { agc_step<EXACT>(p, g, g2, y2p, c[k]); o[k] = g; }
+            for (int k = 0; k < 8; k++) { agc_step<EXACT>(co, g, g2, y2p, c[k]); o[k] = g; }
             if (EMIT) {
                 float4 *o4 = reinterpret_cast<float4 *>(go + i);
                 o4[0] = make_float4(o[0], o[1], o[2], o[3]);
@@ -391,7 +393,7 @@ __device__ __forceinline__ void agc_run(const BackendParams &p, int lane, float 
             }
         }
     }
-    for (; i < i1; i++) { agc_step<EXACT>(p, g, g2, y2p, pw[i]); if (EMIT) go[i] = g; }
+    for (; i < i1; i++) { agc_step<EXACT>(co, g, g2, y2p, pw[i]); if (EMIT) go[i] = g; }
 }
 
 __device__ __forceinline__ bool be_close(float a, float b, float atol = 0.f)
@@ -429,7 +431,7 @@ __device__ __forceinline__ void agc_guess(float e, float &g, float &y2p)
 // every chain of a call is resident at once and the kernel is bound by the latency of one window, not by waves.
 constexpr int kAgcT = 128, kAgcB = 32;
 template <bool EXACT>
-__global__ void __launch_bounds__(kAgcT) k_agc_chain(const BackendParams p)
+__global__ void __launch_bounds__(kAgcT, 5) k_agc_chain(const BackendParams p)
 {
     __shared__ float sm[kAgcT][kAgcB + 1];
     const int lane = blockIdx.y, tid = threadIdx.x, w = tid >> 5, l = tid & 31;
@@ -442,18 +444,36 @@ __global__ void __launch_bounds__(kAgcT) k_agc_chain(const BackendParams p)
     const int nsteps = (p.W + p.L) / kAgcB, wsteps = p.W / kAgcB;
     float g = 1.f, g2 = 1.f, y2p = 1.f;
     bool started = false;
-    for (int s = 0; s < nsteps; s++) {
-        // rows of this warp: thread r = 32 w + i, block start u_r = (seg0 + r) L - W + 32 s
-#pragma unroll 4
-        for (int i = 0; i < 32; i++) {
-            const int r = 32 * w + i;
-            const long long u = (long long)(seg0 + r) * p.L - p.W + (long long)s * kAgcB + l;
-            if (u >= 0 && u < p.n) sm[r][l] = pw[u];
+    // rows of this warp: thread r = 32 w + i, block start u_r = (seg0 + r) L - W + 32 s.  The 32 loads of the NEXT step
+    // are issued before the recurrence of the current one runs, so their latency is never waited for.
+    float nxt[32];
+    const AgcCoef co{p.alpha, p.one_minus_alpha_f, p.neg_half_alpha};
+    const int L = p.L, n = p.n;
+    const int ubase = (seg0 + 32 * w) * L - p.W + l;           // int: n < 2^31
+    // a CTA whose windows lie inside the chunk (all but the first and the last few) skips the bounds checks
+    const bool interior = (seg0 * L - p.W >= 0) && ((seg0 + kAgcT) * L <= n);
+    auto fetch = [&](int s) {
+        const float *q = pw + ubase + s * kAgcB;
+        if (interior) {
+#pragma unroll
+            for (int i = 0; i < 32; i++) nxt[i] = __ldg(q + i * L);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 32; i++) {
+                const int u = ubase + i * L + s * kAgcB;
+                nxt[i] = (u >= 0 && u < n) ? __ldg(pw + u) : 0.f;
+            }
         }
+    };
+    fetch(0);
+    for (int s = 0; s < nsteps; s++) {
+#pragma unroll
+        for (int i = 0; i < 32; i++) sm[32 * w + i][l] = nxt[i];
         __syncthreads();
+        if (s + 1 < nsteps) fetch(s + 1);
         const int u0 = b0 - p.W + s * kAgcB;                    // time of this thread's sm[tid][0]
         const bool emit = s >= wsteps;
-        if (live && u0 >= 0 && u0 < p.n) {
+        if (live && u0 >= 0 && u0 < n) {
             if (!started) {
                 started = true;
                 if (b0 - p.W <= 0) { const LaneState ls = p.lane[lane]; g = ls.g; y2p = ls.y2p; }   // time 0: exact
@@ -470,21 +490,31 @@ __global__ void __launch_bounds__(kAgcT) k_agc_chain(const BackendParams p)
                 p.seg_start[(long long)lane * p.nseg + seg] = s0;
                 g2 = __fmul_rn(g, g);
             }
-            const int cnt = min(kAgcB, p.n - u0);
+            const int cnt = min(kAgcB, n - u0);
             if (cnt == kAgcB) {
+                if (emit) {
 #pragma unroll
-                for (int k = 0; k < kAgcB; k++) { agc_step<EXACT>(p, g, g2, y2p, sm[tid][k]); if (emit) sm[tid][k] = g; }
+                    for (int k = 0; k < kAgcB; k++) { agc_step<EXACT>(co, g, g2, y2p, sm[tid][k]); sm[tid][k] = g; }
+                } else {
+#pragma unroll
+                    for (int k = 0; k < kAgcB; k++) agc_step<EXACT>(co, g, g2, y2p, sm[tid][k]);
+                }
             } else {
-                for (int k = 0; k < cnt; k++) { agc_step<EXACT>(p, g, g2, y2p, sm[tid][k]); if (emit) sm[tid][k] = g; }
+                for (int k = 0; k < cnt; k++) { agc_step<EXACT>(co, g, g2, y2p, sm[tid][k]); if (emit) sm[tid][k] = g; }
             }
         }
         __syncthreads();
         if (emit) {
-#pragma unroll 4
-            for (int i = 0; i < 32; i++) {
-                const int r = 32 * w + i;
-                const long long u = (long long)(seg0 + r) * p.L - p.W + (long long)s * kAgcB + l;
-                if (seg0 + r < p.nseg && u >= 0 && u < p.n) go[u] = sm[r][l];
+            float *q = go + ubase + s * kAgcB;
+            if (interior) {
+#pragma unroll
+                for (int i = 0; i < 32; i++) q[i * L] = sm[32 * w + i][l];
+            } else {
+#pragma unroll
+                for (int i = 0; i < 32; i++) {
+                    const int u = ubase + i * L + s * kAgcB;
+                    if (seg0 + 32 * w + i < p.nseg && u >= 0 && u < n) go[u] = sm[32 * w + i][l];
+                }
             }
             __syncthreads();
         }
