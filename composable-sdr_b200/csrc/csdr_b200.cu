@@ -520,6 +520,7 @@ struct Channelizer {
     int log2M = -1, F = 1;
     size_t smem = 0;
     void (*tile_kernel)(PfbTileParams) = nullptr; PfbTileParams tp{}; size_t tile_smem = 0;   // M = 2..32, m = 7
+    bool ring_ok = false; int ring_ctas = 1;                                                  // M = 128..1024, m = 7
 
     void init(const Ctx &c, unsigned M_, unsigned m_, float As_)
     {
@@ -557,6 +558,12 @@ struct Channelizer {
             tile_smem = (size_t)(kPfbTileF + kPfbTileP - 1) * (M + 2) * sizeof(float2);
             CK(cudaFuncSetAttribute(tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem));
         }
+        ring_ok = log2M >= 7 && M <= 1024 && (int)P == kPfbRingP;
+        if (ring_ok) {
+            CK(cudaFuncSetAttribute(k_pfb_ring, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pfb_ring_smem(1024)));
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ring_ctas, k_pfb_ring, (int)M / kPfbRingCPT, pfb_ring_smem((int)M)));
+            if (ring_ctas < 1) ring_ok = false;
+        }
         size_t hb = (size_t)(P - 1) * M * sizeof(float2);
         for (auto &b : xr) { b.ensure(hb); CK(cudaMemsetAsync(b.p, 0, b.cap, c.stream)); }
         c.sync();
@@ -582,7 +589,17 @@ struct Channelizer {
         p.xr = xr[cur].as<float2>(); p.y = y; p.y_stride = y_stride;
         p.M = (int)M; p.P = (int)P; p.nf = nf; p.F = F; p.log2M = log2M;
         p.h = hd.as<float>(); p.tw = tw.as<float2>();
-        if (tile_kernel) {
+        if (ring_ok) {
+            PfbRingParams rp{};
+            rp.xr = p.xr; rp.y = y; rp.y_stride = y_stride; rp.nf = nf; rp.M = (int)M; rp.log2M = log2M;
+            rp.h = hd.as<float>(); rp.tw = tw.as<float2>();
+            // one wave of CTAs where possible: frames per CTA = nf / (SMs * CTAs per SM), in whole output tiles
+            const int slots = std::max(1, c.sms * ring_ctas);
+            int T = (nf + slots - 1) / slots;
+            T = std::max(2 * kPfbRingTF, (T + kPfbRingTF - 1) / kPfbRingTF * kPfbRingTF);
+            rp.T = T;
+            launch(k_pfb_ring, dim3((nf + T - 1) / T), dim3(M / kPfbRingCPT), pfb_ring_smem((int)M), c.stream, rp);
+        } else if (tile_kernel) {
             tp.xr = p.xr; tp.y = y; tp.y_stride = y_stride; tp.nf = nf;
             launch(tile_kernel, dim3((nf + kPfbTileF - 1) / kPfbTileF), dim3(kPfbTileF), tile_smem, c.stream, tp);
         } else {

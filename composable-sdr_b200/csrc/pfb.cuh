@@ -175,6 +175,111 @@ __global__ void __launch_bounds__(kPfbTileF) k_pfb_tile(const CSDR_GRID_CONSTANT
     for (int c = 0; c < M; c++) yo[(long long)c * p.y_stride] = b[c];
 }
 
+// ---- large power-of-two M (128..1024): a CTA slides over its frames with a ring of P rows ------------------------
+// Shared memory holds the last P = 14 rows of M samples (ring), one M-point DFT buffer and an [M][TF] output tile.
+// Per frame: the new row is loaded once (coalesced), thread i evaluates the four polyphase branches n = i + j M/4
+// (its 4 x 14 taps live in registers for the whole kernel) straight into bit-reversed DFT order, the radix-2 DIT
+// stages run in shared memory, and the frame is parked in the output tile; every TF frames the tile is written out
+// channel-major, TF consecutive frames (64 bytes) per channel.  Each input sample is read from HBM once (plus 13
+// rows of halo per CTA), each output written once.
+constexpr int kPfbRingP = 14, kPfbRingTF = 8, kPfbRingCPT = 4;
+
+struct PfbRingParams {
+    const float2 *xr; float2 *y; long long y_stride;
+    int nf, T;               // frames in this call, frames per CTA (multiple of TF)
+    int M, log2M;
+    const float *h;          // prototype, P*M taps
+    const float2 *tw;        // M twiddles exp(-j 2 pi t / M)
+};
+inline size_t pfb_ring_smem(int M) { return (size_t)M * sizeof(float2) * (kPfbRingP + 1 + (kPfbRingTF + 1)) + (size_t)(M / 2) * sizeof(float2); }
+
+__global__ void __launch_bounds__(256) k_pfb_ring(const PfbRingParams p)
+{
+    constexpr int P = kPfbRingP, TF = kPfbRingTF, CPT = kPfbRingCPT, TFP = TF + 1;
+    CSDR_DYN_SMEM(smem_raw);
+    const int M = p.M, lm = p.log2M, NT = blockDim.x, tid = threadIdx.x;       // NT = M / 4
+    float2 *ring = reinterpret_cast<float2 *>(smem_raw);          // [P][M]
+    float2 *work = ring + P * M;                                   // [M]
+    float2 *obuf = work + M;                                       // [M][TFP]
+    float2 *stw = obuf + M * TFP;                                  // [M/2] twiddles
+    const int t0 = blockIdx.x * p.T, t1 = min(t0 + p.T, p.nf);
+    if (t0 >= t1) return;
+    for (int i = tid; i < M / 2; i += NT) stw[i] = p.tw[i];
+    // taps of this thread's columns: hh[j][k] = h[(M-1-n) + k M], n = tid + j NT
+    float hh[CPT][P];
+#pragma unroll
+    for (int j = 0; j < CPT; j++) {
+        const int n = tid + j * NT;
+#pragma unroll
+        for (int k = 0; k < P; k++) hh[j][k] = p.h[(M - 1 - n) + k * M];
+    }
+    auto load_row = [&](int row) {                                  // xr row -> ring slot row % P
+        const float4 *src = reinterpret_cast<const float4 *>(p.xr + (long long)row * M);
+        float4 *dst = reinterpret_cast<float4 *>(ring + (row % P) * M);
+        for (int e = tid; e < M / 2; e += NT) dst[e] = src[e];
+    };
+    for (int r = t0; r < t0 + P - 1; r++) load_row(r);              // history of the first frame
+    // the row of the NEXT frame travels through registers while the current frame is computed (M / 2 float4 per row,
+    // two per thread)
+    float4 nx0, nx1;
+    auto fetch_row = [&](int row) {
+        const float4 *src = reinterpret_cast<const float4 *>(p.xr + (long long)row * M);
+        nx0 = src[tid]; nx1 = src[tid + NT];
+    };
+    fetch_row(t0 + P - 1);
+    for (int t = t0; t < t1; t++) {
+        const int newest = t + P - 1;
+        {
+            float4 *dst = reinterpret_cast<float4 *>(ring + (newest % P) * M);
+            dst[tid] = nx0; dst[tid + NT] = nx1;
+        }
+        __syncthreads();
+        if (t + 1 < t1) fetch_row(newest + 1);
+        int slot = newest % P;
+        float2 acc[CPT];
+#pragma unroll
+        for (int j = 0; j < CPT; j++) acc[j] = cf(0.f, 0.f);
+#pragma unroll
+        for (int k = 0; k < P; k++) {
+            const float2 *row = ring + slot * M + tid;
+#pragma unroll
+            for (int j = 0; j < CPT; j++) ffma2(acc[j], hh[j][k], row[j * NT]);
+            slot = (slot == 0) ? P - 1 : slot - 1;
+        }
+#pragma unroll
+        for (int j = 0; j < CPT; j++) work[__brev((unsigned)(tid + j * NT)) >> (32 - lm)] = acc[j];
+        __syncthreads();
+        // radix-2 DIT: M/2 butterflies per stage, two per thread
+        for (int s = 1; s <= lm; s++) {
+            const int half = 1 << (s - 1);
+#pragma unroll
+            for (int q = 0; q < 2; q++) {
+                const int b = tid + q * NT;                          // butterfly index < M/2
+                const int jj = b & (half - 1), grp = b >> (s - 1);
+                float2 *a = work + (grp << s) + jj;
+                const float2 w = stw[jj << (lm - s)];
+                const float2 u = a[0], v = a[half];
+                const float tr = v.x * w.x - v.y * w.y, ti = v.x * w.y + v.y * w.x;
+                a[0] = cf(u.x + tr, u.y + ti);
+                a[half] = cf(u.x - tr, u.y - ti);
+            }
+            __syncthreads();
+        }
+        const int tf = (t - t0) & (TF - 1);
+#pragma unroll
+        for (int j = 0; j < CPT; j++) { const int c = tid + j * NT; obuf[c * TFP + tf] = work[c]; }
+        if (tf == TF - 1 || t == t1 - 1) {
+            __syncthreads();
+            const int cnt = tf + 1, tb = t - tf;                    // frames parked in the tile, first of them
+            for (int e = tid; e < M * TF; e += NT) {
+                const int c = e >> 3, f = e & (TF - 1);
+                if (f < cnt) p.y[(long long)c * p.y_stride + tb + f] = obuf[c * TFP + f];
+            }
+        }
+        // the next iteration's load_row writes a slot nobody reads any more; work/obuf hazards are covered by its barrier
+    }
+}
+
 // keep the last (P-1)*M pre-rotated samples for the next call: dst[0..H) <- src[n .. n+H)
 __global__ void k_copy_tail(const float2 *__restrict__ src, float2 *__restrict__ dst, long long offset, int count)
 {
