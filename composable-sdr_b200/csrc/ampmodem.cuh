@@ -74,31 +74,53 @@ __global__ void k_am_lowpass(const AmParams p)
 __device__ __forceinline__ unsigned am_constrain(float theta)
 {
     float pp = (float)((double)theta * 0.159154943091895);
-    float frac = pp - (float)((long long)pp);
-    if (frac < 0.0f) frac = (float)((double)frac + 1.0);
+    float frac = pp - truncf(pp);                      // == pp - (float)((long long)pp): the integer part is exact in float
+    if (frac < 0.0f) frac = __fadd_rn(frac, 1.0f);     // == (float)((double)frac + 1.0): one rounding either way
     float scaled = frac * 4294967296.0f;
     return scaled >= 4294967296.0f ? 0u : (unsigned)scaled;
 }
 
-// carrier PLL, sequential per lane (ampmodem_demod_dsb_pll_carrier)
-__global__ void k_am_pll(const AmParams p)
+// carrier PLL, sequential per lane (ampmodem_demod_dsb_pll_carrier).  The loop is a dependent chain
+// theta -> table -> mix -> constrain -> theta; the sine table sits in shared memory and the lane's samples are fetched
+// eight ahead of the chain so that only the chain's own latency is paid per sample.
+__global__ void __launch_bounds__(32) k_am_pll(const AmParams p)
 {
+    __shared__ float stab[1024];
+    for (int i = threadIdx.x; i < 1024; i += blockDim.x) stab[i] = p.sintab[i];
+    __syncthreads();
     const int lane = blockIdx.x * blockDim.x + threadIdx.x;
     if (lane >= p.nlanes) return;
-    const float2 *xh = p.xh + (long long)lane * p.xh_stride;
+    const float2 *xh = p.xh + (long long)lane * p.xh_stride + (kAmHist - kAmM);
     const float2 *x0 = p.x0 + (long long)lane * p.n;
     float *mh = p.mh + (long long)lane * p.mh_stride + kAmHist;
     unsigned theta = p.pll[2 * lane], dtheta = p.pll[2 * lane + 1];
-    for (int i = 0; i < p.n; i++) {
-        const unsigned idx = ((theta + (1u << 21)) >> 22) & 0x3ffu;
-        const float s = p.sintab[idx], c = p.sintab[(idx + 256) & 0x3ffu];
-        const float2 a = x0[i], b = xh[kAmHist + i - kAmM];
-        const float v0i = __fsub_rn(__fmul_rn(a.y, c), __fmul_rn(a.x, s));
-        const float v1r = __fadd_rn(__fmul_rn(b.x, c), __fmul_rn(b.y, s));
-        dtheta += am_constrain(__fmul_rn(v0i, p.pll_alpha));
-        theta += am_constrain(__fmul_rn(v0i, p.pll_beta));
-        theta += dtheta;
-        mh[i] = v1r * p.inv_mod;
+    const float inv_mod = p.inv_mod, ka = p.pll_alpha, kb = p.pll_beta;
+    constexpr int B = 8;
+    float2 na[B], nb[B];
+#pragma unroll
+    for (int k = 0; k < B; k++) { na[k] = (k < p.n) ? x0[k] : cf(0.f, 0.f); nb[k] = (k < p.n) ? xh[k] : cf(0.f, 0.f); }
+    for (int i = 0; i < p.n; i += B) {
+        float2 ca[B], cb[B];
+#pragma unroll
+        for (int k = 0; k < B; k++) { ca[k] = na[k]; cb[k] = nb[k]; }
+#pragma unroll
+        for (int k = 0; k < B; k++) {
+            const int j = i + B + k;
+            if (j < p.n) { na[k] = x0[j]; nb[k] = xh[j]; }
+        }
+#pragma unroll
+        for (int k = 0; k < B; k++) {
+            if (i + k < p.n) {
+                const unsigned idx = ((theta + (1u << 21)) >> 22) & 0x3ffu;
+                const float s = stab[idx], c = stab[(idx + 256) & 0x3ffu];
+                const float v0i = __fsub_rn(__fmul_rn(ca[k].y, c), __fmul_rn(ca[k].x, s));
+                const float v1r = __fadd_rn(__fmul_rn(cb[k].x, c), __fmul_rn(cb[k].y, s));
+                dtheta += am_constrain(__fmul_rn(v0i, ka));
+                theta += am_constrain(__fmul_rn(v0i, kb));
+                theta += dtheta;
+                mh[i + k] = v1r * inv_mod;
+            }
+        }
     }
     p.pll[2 * lane] = theta; p.pll[2 * lane + 1] = dtheta;
 }
