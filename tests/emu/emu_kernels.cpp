@@ -7,6 +7,7 @@
 #include "frontend_plan.hpp"
 #include "interp.cuh"
 #include "backend.cuh"
+#include "pfb.cuh"
 #include <vector>
 #include <cstdio>
 
@@ -173,6 +174,66 @@ long long emu_backend(int nlanes, long long lane_stride, int has_dc, float dc_al
 }
 
 }  // extern "C"
+
+// firpfbchChannelizer M (pre-rotation NCO + analyzer), fed in chunks of whole frames; y is [M][nf_total] channel-major.
+// kind: 0 generic k_pfb, 1 k_pfb_tile (M = 2..32), 2 k_pfb_ring (M = 128..1024)
+extern "C" long long emu_pfb(int M, int kind, const float2 *x, long long nf_total, const long long *chunk_frames, int nchunks,
+                             float2 *y)
+{
+    const int m = 7, P = 2 * m;
+    std::vector<float> h = design::design_firpfbch((unsigned)M, (unsigned)m, 80.0f);
+    std::vector<float2> tw(M);
+    for (int i = 0; i < M; i++) { tw[i].x = (float)std::cos(-2.0 * design::kPi * i / M); tw[i].y = (float)std::sin(-2.0 * design::kPi * i / M); }
+    int log2M = -1;
+    if (M > 1 && (M & (M - 1)) == 0) { log2M = 0; while ((1 << log2M) < M) log2M++; }
+    const unsigned dth = design::nco_constrain(design::firpfbch_rotation((unsigned)M));
+    unsigned theta = 0;
+    const size_t H = (size_t)(P - 1) * M;
+    std::vector<float2> xr(H, make_float2(0, 0));
+    EmuLaunch launch;
+    long long pos = 0;
+    for (int c = 0; c < nchunks; c++) {
+        const long long nf = chunk_frames[c];
+        if (pos + nf > nf_total) return -1;
+        if (nf == 0) continue;
+        xr.resize(H + (size_t)nf * M);
+        launch(k_nco_mix, dim3(4), dim3(64), 0, x + pos * M, xr.data() + H, nf * M, theta, dth, 1, 0);
+        theta += (unsigned)(nf * M) * dth;
+        if (kind == 1) {
+            PfbTileParams tp{};
+            tp.xr = xr.data(); tp.y = y + pos; tp.y_stride = nf_total; tp.nf = (int)nf;
+            for (int i = 0; i < M / 2; i++) tp.tw[i] = tw[i];
+            for (int k = 0; k < P; k++) for (int n = 0; n < M; n++) tp.h[k * M + n] = h[(M - 1 - n) + k * M];
+            const size_t smem = (size_t)(kPfbTileF + kPfbTileP - 1) * (M + 2) * sizeof(float2);
+            const dim3 g((unsigned)((nf + kPfbTileF - 1) / kPfbTileF)), b(kPfbTileF);
+            switch (log2M) {
+            case 1: launch(k_pfb_tile<1>, g, b, smem, tp); break;
+            case 2: launch(k_pfb_tile<2>, g, b, smem, tp); break;
+            case 3: launch(k_pfb_tile<3>, g, b, smem, tp); break;
+            case 4: launch(k_pfb_tile<4>, g, b, smem, tp); break;
+            case 5: launch(k_pfb_tile<5>, g, b, smem, tp); break;
+            default: return -1;
+            }
+        } else if (kind == 2) {
+            PfbRingParams rp{};
+            rp.xr = xr.data(); rp.y = y + pos; rp.y_stride = nf_total; rp.nf = (int)nf; rp.M = M; rp.log2M = log2M;
+            rp.h = h.data(); rp.tw = tw.data();
+            rp.T = 3 * kPfbRingTF;
+            launch(k_pfb_ring, dim3((unsigned)((nf + rp.T - 1) / rp.T)), dim3(M / kPfbRingCPT), pfb_ring_smem(M), rp);
+        } else {
+            PfbParams p{};
+            p.xr = xr.data(); p.y = y + pos; p.y_stride = nf_total; p.M = M; p.P = P; p.nf = (int)nf; p.F = 8; p.log2M = log2M;
+            p.h = h.data(); p.tw = tw.data();
+            const size_t smem = (size_t)p.F * M * sizeof(float2) * (log2M >= 0 ? 1 : 2);
+            launch(k_pfb, dim3((unsigned)((nf + p.F - 1) / p.F)), dim3(64), smem, p);
+        }
+        // carry the last (P-1) rows
+        std::vector<float2> tail(xr.end() - (long)H, xr.end());
+        xr.assign(tail.begin(), tail.end());
+        pos += nf;
+    }
+    return pos;
+}
 
 // ---- product-side filter design (design.hpp), exported so the CPU suite can compare it with the oracle ----
 extern "C" {

@@ -19,6 +19,8 @@ def load():
         L.emu_backend.argtypes = [C.c_int, C.c_longlong, C.c_int, C.c_float, C.c_int, C.c_float, C.c_int, C.c_float,
                                   C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_longlong, C.c_void_p, C.c_int, C.c_void_p,
                                   C.POINTER(C.c_ulonglong), C.c_void_p]
+        L.emu_pfb.restype = C.c_longlong
+        L.emu_pfb.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_longlong, C.c_void_p, C.c_int, C.c_void_p]
         L.emu_design_nco_constrain.restype = C.c_uint
         L.emu_design_nco_constrain.argtypes = [C.c_float]
         L.emu_design_rotation.restype = C.c_float
@@ -60,6 +62,16 @@ class Emu:
         self.L.emu_backend(nlanes, n, has_dc, 0.0005, has_agc, thr, demod, kf, L, W, G, x.ctypes.data, n, ch.ctypes.data,
                            len(chunks), out.ctypes.data, fx, debug.ctypes.data if debug is not None else None)
         return out, (fx[0], fx[1], fx[2])
+
+    def pfb(self, x, M, kind, chunk_frames=None):
+        """firpfbchChannelizer M through the kernel sources; kind 0 generic, 1 tile (M <= 32), 2 ring (M 128..1024)"""
+        x = np.ascontiguousarray(x, np.complex64)
+        nf = x.size // M
+        ch = np.array([nf] if chunk_frames is None else list(chunk_frames), np.int64)
+        y = np.zeros((M, nf), np.complex64)
+        n = self.L.emu_pfb(M, kind, x.ctypes.data, nf, ch.ctypes.data, len(ch), y.ctypes.data)
+        assert n == nf, "emu_pfb failed"
+        return y
 
     def design_msresamp(self, rate, As=60.0):
         S, step, npfb = C.c_uint(0), C.c_uint(0), C.c_uint(0)
