@@ -855,14 +855,15 @@ __global__ void k_lane_sum(const float *__restrict__ in, long long lane_stride, 
     long long stride = (long long)gridDim.x * blockDim.x;
     for (; i < n; i += stride) {
         float acc = in[i];
-        // same left fold, loads issued eight lanes ahead of the adds
+        // same left fold, loads issued 32 lanes ahead of the adds (few output columns, many lanes: the loop is bound
+        // by how many loads are in flight)
         int c = 1;
-        for (; c + 8 <= nlanes; c += 8) {
-            float v[8];
+        for (; c + 32 <= nlanes; c += 32) {
+            float v[32];
 #pragma unroll
-            for (int k = 0; k < 8; k++) v[k] = in[(long long)(c + k) * lane_stride + i];
+            for (int k = 0; k < 32; k++) v[k] = in[(long long)(c + k) * lane_stride + i];
 #pragma unroll
-            for (int k = 0; k < 8; k++) acc = __fadd_rn(acc, v[k]);
+            for (int k = 0; k < 32; k++) acc = __fadd_rn(acc, v[k]);
         }
         for (; c < nlanes; c++) acc = __fadd_rn(acc, in[(long long)c * lane_stride + i]);
         out[i] = acc;

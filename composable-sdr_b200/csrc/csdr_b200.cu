@@ -561,7 +561,7 @@ struct Channelizer {
         ring_ok = log2M >= 7 && M <= 1024 && (int)P == kPfbRingP;
         if (ring_ok) {
             CK(cudaFuncSetAttribute(k_pfb_ring, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pfb_ring_smem(1024)));
-            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ring_ctas, k_pfb_ring, (int)M / kPfbRingCPT, pfb_ring_smem((int)M)));
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ring_ctas, k_pfb_ring, 2 * (int)M / kPfbRingCPT, pfb_ring_smem((int)M)));
             if (ring_ctas < 1) ring_ok = false;
         }
         size_t hb = (size_t)(P - 1) * M * sizeof(float2);
@@ -598,7 +598,7 @@ struct Channelizer {
             int T = (nf + slots - 1) / slots;
             T = std::max(2 * kPfbRingTF, (T + kPfbRingTF - 1) / kPfbRingTF * kPfbRingTF);
             rp.T = T;
-            launch(k_pfb_ring, dim3((nf + T - 1) / T), dim3(M / kPfbRingCPT), pfb_ring_smem((int)M), c.stream, rp);
+            launch(k_pfb_ring, dim3((nf + T - 1) / T), dim3(2 * M / kPfbRingCPT), pfb_ring_smem((int)M), c.stream, rp);
         } else if (tile_kernel) {
             tp.xr = p.xr; tp.y = y; tp.y_stride = y_stride; tp.nf = nf;
             launch(tile_kernel, dim3((nf + kPfbTileF - 1) / kPfbTileF), dim3(kPfbTileF), tile_smem, c.stream, tp);

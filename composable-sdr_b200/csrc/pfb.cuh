@@ -175,14 +175,16 @@ __global__ void __launch_bounds__(kPfbTileF) k_pfb_tile(const CSDR_GRID_CONSTANT
     for (int c = 0; c < M; c++) yo[(long long)c * p.y_stride] = b[c];
 }
 
-// ---- large power-of-two M (128..1024): a CTA slides over its frames with a ring of P rows ------------------------
-// Shared memory holds the last P = 14 rows of M samples (ring), one M-point DFT buffer and an [M][TF] output tile.
-// Per frame: the new row is loaded once (coalesced), thread i evaluates the four polyphase branches n = i + j M/4
-// (its 4 x 14 taps live in registers for the whole kernel) straight into bit-reversed DFT order, the radix-2 DIT
-// stages run in shared memory, and the frame is parked in the output tile; every TF frames the tile is written out
-// channel-major, TF consecutive frames (64 bytes) per channel.  Each input sample is read from HBM once (plus 13
-// rows of halo per CTA), each output written once.
-constexpr int kPfbRingP = 14, kPfbRingTF = 8, kPfbRingCPT = 4;
+// ---- large power-of-two M (128..1024): a CTA slides over its frames with a ring of rows --------------------------
+// Shared memory holds the last P + 1 = 15 rows of M samples (ring), two M-point DFT buffers and an [M][TF] output
+// tile.  Two frames are processed per iteration by the two halves of the CTA (M/4 threads each): the two new rows are
+// loaded once (coalesced, prefetched through registers one iteration ahead), thread i of a half evaluates the four
+// polyphase branches n = i + j M/4 of its frame (4 x 14 taps in registers for the whole kernel) straight into
+// digit-reversed DFT order, the DFT runs in shared memory (radix-4 DIT stages, one butterfly per thread and stage,
+// plus one radix-2 stage when log2 M is odd), and the frame is parked in the output tile; every TF frames the tile is
+// written out channel-major, TF consecutive frames (64 bytes) per channel.  Each input sample is read from HBM once
+// (plus 13 rows of halo per CTA), each output written once.
+constexpr int kPfbRingP = 14, kPfbRingTF = 8, kPfbRingCPT = 4, kPfbRingRows = kPfbRingP + 1;
 
 struct PfbRingParams {
     const float2 *xr; float2 *y; long long y_stride;
@@ -191,20 +193,34 @@ struct PfbRingParams {
     const float *h;          // prototype, P*M taps
     const float2 *tw;        // M twiddles exp(-j 2 pi t / M)
 };
-inline size_t pfb_ring_smem(int M) { return (size_t)M * sizeof(float2) * (kPfbRingP + 1 + (kPfbRingTF + 1)) + (size_t)(M / 2) * sizeof(float2); }
+inline size_t pfb_ring_smem(int M) { return (size_t)M * sizeof(float2) * (kPfbRingRows + 2 + (kPfbRingTF + 1) + 1); }
 
-__global__ void __launch_bounds__(256) k_pfb_ring(const PfbRingParams p)
+// position of element n in the input order of the mixed-radix DIT below (stage radices 2?, 4, 4, ...; the LAST stage
+// splits n by its lowest base-4 digit): pos = digits of n in reverse order, i.e. the bit reversal of n with the two
+// bits of every base-4 digit swapped back; with odd log2 M the top bit of n (the radix-2 stage) lands in bit 0
+__device__ __forceinline__ int pfb_ring_perm(int n, int lm)
 {
-    constexpr int P = kPfbRingP, TF = kPfbRingTF, CPT = kPfbRingCPT, TFP = TF + 1;
+    const unsigned r = __brev((unsigned)n) >> (32 - lm);
+    if (lm & 1) {
+        const unsigned low = r & 1u, up = r >> 1;
+        return (int)(((((up & 0x55555555u) << 1) | ((up & 0xAAAAAAAAu) >> 1)) << 1) | low);
+    }
+    return (int)(((r & 0x55555555u) << 1) | ((r & 0xAAAAAAAAu) >> 1));
+}
+
+__global__ void __launch_bounds__(512, 1) k_pfb_ring(const PfbRingParams p)
+{
+    constexpr int P = kPfbRingP, TF = kPfbRingTF, CPT = kPfbRingCPT, TFP = TF + 1, RR = kPfbRingRows;
     CSDR_DYN_SMEM(smem_raw);
-    const int M = p.M, lm = p.log2M, NT = blockDim.x, tid = threadIdx.x;       // NT = M / 4
-    float2 *ring = reinterpret_cast<float2 *>(smem_raw);          // [P][M]
-    float2 *work = ring + P * M;                                   // [M]
-    float2 *obuf = work + M;                                       // [M][TFP]
-    float2 *stw = obuf + M * TFP;                                  // [M/2] twiddles
+    const int M = p.M, lm = p.log2M, NT = M / CPT;                // blockDim.x = 2 NT
+    const int half_id = threadIdx.x / NT, tid = threadIdx.x - half_id * NT, gtid = threadIdx.x;
+    float2 *ring = reinterpret_cast<float2 *>(smem_raw);          // [RR][M]
+    float2 *work = ring + RR * M + half_id * M;                    // [2][M]
+    float2 *obuf = ring + RR * M + 2 * M;                          // [M][TFP]
+    float2 *stw = obuf + M * TFP;                                  // [M] twiddles
     const int t0 = blockIdx.x * p.T, t1 = min(t0 + p.T, p.nf);
     if (t0 >= t1) return;
-    for (int i = tid; i < M / 2; i += NT) stw[i] = p.tw[i];
+    for (int i = gtid; i < M; i += 2 * NT) stw[i] = p.tw[i];
     // taps of this thread's columns: hh[j][k] = h[(M-1-n) + k M], n = tid + j NT
     float hh[CPT][P];
 #pragma unroll
@@ -213,70 +229,99 @@ __global__ void __launch_bounds__(256) k_pfb_ring(const PfbRingParams p)
 #pragma unroll
         for (int k = 0; k < P; k++) hh[j][k] = p.h[(M - 1 - n) + k * M];
     }
-    auto load_row = [&](int row) {                                  // xr row -> ring slot row % P
-        const float4 *src = reinterpret_cast<const float4 *>(p.xr + (long long)row * M);
-        float4 *dst = reinterpret_cast<float4 *>(ring + (row % P) * M);
-        for (int e = tid; e < M / 2; e += NT) dst[e] = src[e];
+    // history of the first frame: xr rows t0 .. t0 + P - 2 -> ring slots row % RR
+    for (int r = t0; r < t0 + P - 1; r++) {
+        const float4 *src = reinterpret_cast<const float4 *>(p.xr + (long long)r * M);
+        float4 *dst = reinterpret_cast<float4 *>(ring + (r % RR) * M);
+        for (int e = gtid; e < M / 2; e += 2 * NT) dst[e] = src[e];
+    }
+    // the two rows of the NEXT iteration travel through registers while the current pair of frames is computed:
+    // 2 rows = M float4, 2 NT threads, two float4 each (half h fetches the row of its own frame)
+    float4 nx0 = make_float4(0.f, 0.f, 0.f, 0.f), nx1 = nx0;
+    const long long last_row = (long long)p.nf + P - 2;           // last row that exists in xr
+    auto fetch_rows = [&](int t) {
+        const long long row = (long long)t + P - 1 + half_id;
+        if (row <= last_row) {
+            const float4 *src = reinterpret_cast<const float4 *>(p.xr + row * M);
+            nx0 = src[tid]; nx1 = src[tid + NT];
+        }
     };
-    for (int r = t0; r < t0 + P - 1; r++) load_row(r);              // history of the first frame
-    // the row of the NEXT frame travels through registers while the current frame is computed (M / 2 float4 per row,
-    // two per thread)
-    float4 nx0, nx1;
-    auto fetch_row = [&](int row) {
-        const float4 *src = reinterpret_cast<const float4 *>(p.xr + (long long)row * M);
-        nx0 = src[tid]; nx1 = src[tid + NT];
-    };
-    fetch_row(t0 + P - 1);
-    for (int t = t0; t < t1; t++) {
-        const int newest = t + P - 1;
+    fetch_rows(t0);
+    for (int t = t0; t < t1; t += 2) {
+        const int my_t = t + half_id;                               // this half's frame
+        const bool have = my_t < t1;
         {
-            float4 *dst = reinterpret_cast<float4 *>(ring + (newest % P) * M);
+            float4 *dst = reinterpret_cast<float4 *>(ring + ((t + P - 1 + half_id) % RR) * M);
             dst[tid] = nx0; dst[tid + NT] = nx1;
         }
         __syncthreads();
-        if (t + 1 < t1) fetch_row(newest + 1);
-        int slot = newest % P;
-        float2 acc[CPT];
+        if (t + 2 < t1) fetch_rows(t + 2);
+        if (have) {
+            int slot = (my_t + P - 1) % RR;
+            float2 acc[CPT];
 #pragma unroll
-        for (int j = 0; j < CPT; j++) acc[j] = cf(0.f, 0.f);
+            for (int j = 0; j < CPT; j++) acc[j] = cf(0.f, 0.f);
 #pragma unroll
-        for (int k = 0; k < P; k++) {
-            const float2 *row = ring + slot * M + tid;
+            for (int k = 0; k < P; k++) {
+                const float2 *row = ring + slot * M + tid;
 #pragma unroll
-            for (int j = 0; j < CPT; j++) ffma2(acc[j], hh[j][k], row[j * NT]);
-            slot = (slot == 0) ? P - 1 : slot - 1;
+                for (int j = 0; j < CPT; j++) ffma2(acc[j], hh[j][k], row[j * NT]);
+                slot = (slot == 0) ? RR - 1 : slot - 1;
+            }
+#pragma unroll
+            for (int j = 0; j < CPT; j++) work[pfb_ring_perm(tid + j * NT, lm)] = acc[j];
         }
-#pragma unroll
-        for (int j = 0; j < CPT; j++) work[__brev((unsigned)(tid + j * NT)) >> (32 - lm)] = acc[j];
         __syncthreads();
-        // radix-2 DIT: M/2 butterflies per stage, two per thread
-        for (int s = 1; s <= lm; s++) {
-            const int half = 1 << (s - 1);
+        int s = 0;                                                  // bits done so far
+        if (lm & 1) {
+            // one radix-2 stage on adjacent elements: two butterflies per thread
+            if (have) {
 #pragma unroll
-            for (int q = 0; q < 2; q++) {
-                const int b = tid + q * NT;                          // butterfly index < M/2
-                const int jj = b & (half - 1), grp = b >> (s - 1);
-                float2 *a = work + (grp << s) + jj;
-                const float2 w = stw[jj << (lm - s)];
-                const float2 u = a[0], v = a[half];
-                const float tr = v.x * w.x - v.y * w.y, ti = v.x * w.y + v.y * w.x;
-                a[0] = cf(u.x + tr, u.y + ti);
-                a[half] = cf(u.x - tr, u.y - ti);
+                for (int q = 0; q < 2; q++) {
+                    float2 *a = work + 2 * (tid + q * NT);
+                    const float2 u = a[0], v = a[1];
+                    a[0] = cf(u.x + v.x, u.y + v.y);
+                    a[1] = cf(u.x - v.x, u.y - v.y);
+                }
+            }
+            __syncthreads();
+            s = 1;
+        }
+        for (; s < lm; s += 2) {
+            // radix-4 DIT stage: sub-transforms of length 2^s -> 2^(s+2); one butterfly per thread
+            if (have) {
+                const int quarter = 1 << s, jj = tid & (quarter - 1), grp = tid >> s;
+                float2 *a = work + (grp << (s + 2)) + jj;
+                const int tws = jj << (lm - s - 2);                 // W_{4 quarter}^{jj} = W_M^{jj M / (4 quarter)}
+                const float2 w1 = stw[tws], w2 = stw[2 * tws], w3 = stw[3 * tws];
+                const float2 x0 = a[0], x1 = a[quarter], x2 = a[2 * quarter], x3 = a[3 * quarter];
+                const float2 b1 = cf(x1.x * w1.x - x1.y * w1.y, x1.x * w1.y + x1.y * w1.x);
+                const float2 b2 = cf(x2.x * w2.x - x2.y * w2.y, x2.x * w2.y + x2.y * w2.x);
+                const float2 b3 = cf(x3.x * w3.x - x3.y * w3.y, x3.x * w3.y + x3.y * w3.x);
+                const float2 s02 = cf(x0.x + b2.x, x0.y + b2.y), d02 = cf(x0.x - b2.x, x0.y - b2.y);
+                const float2 s13 = cf(b1.x + b3.x, b1.y + b3.y), d13 = cf(b1.x - b3.x, b1.y - b3.y);
+                a[0] = cf(s02.x + s13.x, s02.y + s13.y);
+                a[quarter] = cf(d02.x + d13.y, d02.y - d13.x);      // d02 - j d13
+                a[2 * quarter] = cf(s02.x - s13.x, s02.y - s13.y);
+                a[3 * quarter] = cf(d02.x - d13.y, d02.y + d13.x);  // d02 + j d13
             }
             __syncthreads();
         }
-        const int tf = (t - t0) & (TF - 1);
+        if (have) {
+            const int tf = (my_t - t0) & (TF - 1);
 #pragma unroll
-        for (int j = 0; j < CPT; j++) { const int c = tid + j * NT; obuf[c * TFP + tf] = work[c]; }
-        if (tf == TF - 1 || t == t1 - 1) {
+            for (int j = 0; j < CPT; j++) { const int c = tid + j * NT; obuf[c * TFP + tf] = work[c]; }
+        }
+        const int last = min(t + 1, t1 - 1);                        // last frame parked so far
+        const int tfl = (last - t0) & (TF - 1);
+        if (tfl == TF - 1 || last == t1 - 1) {
             __syncthreads();
-            const int cnt = tf + 1, tb = t - tf;                    // frames parked in the tile, first of them
-            for (int e = tid; e < M * TF; e += NT) {
+            const int cnt = tfl + 1, tb = last - tfl;               // frames parked in the tile, first of them
+            for (int e = gtid; e < M * TF; e += 2 * NT) {
                 const int c = e >> 3, f = e & (TF - 1);
                 if (f < cnt) p.y[(long long)c * p.y_stride + tb + f] = obuf[c * TFP + f];
             }
         }
-        // the next iteration's load_row writes a slot nobody reads any more; work/obuf hazards are covered by its barrier
     }
 }
 
