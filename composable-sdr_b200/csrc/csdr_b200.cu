@@ -520,7 +520,7 @@ struct Channelizer {
     int log2M = -1, F = 1;
     size_t smem = 0;
     void (*tile_kernel)(PfbTileParams) = nullptr; PfbTileParams tp{}; size_t tile_smem = 0;   // M = 2..32, m = 7
-    bool ring_ok = false; int ring_ctas = 1;                                                  // M = 128..1024, m = 7
+    bool ring_ok = false; int ring_ctas = 1; void (*ring_kernel)(PfbRingParams) = nullptr;                                                 // M = 128..1024, m = 7
 
     void init(const Ctx &c, unsigned M_, unsigned m_, float As_)
     {
@@ -560,8 +560,9 @@ struct Channelizer {
         }
         ring_ok = log2M >= 7 && M <= 1024 && (int)P == kPfbRingP;
         if (ring_ok) {
-            CK(cudaFuncSetAttribute(k_pfb_ring, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pfb_ring_smem(1024)));
-            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ring_ctas, k_pfb_ring, 2 * (int)M / kPfbRingCPT, pfb_ring_smem((int)M)));
+            ring_kernel = pfb_ring_lfz(log2M) == 4 ? k_pfb_ring<4> : k_pfb_ring<5>;
+            CK(cudaFuncSetAttribute(ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pfb_ring_smem((int)M, log2M)));
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ring_ctas, ring_kernel, 2 * (int)M / kPfbRingCPT, pfb_ring_smem((int)M, log2M)));
             if (ring_ctas < 1) ring_ok = false;
         }
         size_t hb = (size_t)(P - 1) * M * sizeof(float2);
@@ -598,7 +599,7 @@ struct Channelizer {
             int T = (nf + slots - 1) / slots;
             T = std::max(2 * kPfbRingTF, (T + kPfbRingTF - 1) / kPfbRingTF * kPfbRingTF);
             rp.T = T;
-            launch(k_pfb_ring, dim3((nf + T - 1) / T), dim3(2 * M / kPfbRingCPT), pfb_ring_smem((int)M), c.stream, rp);
+            launch(ring_kernel, dim3((nf + T - 1) / T), dim3(2 * M / kPfbRingCPT), pfb_ring_smem((int)M, log2M), c.stream, rp);
         } else if (tile_kernel) {
             tp.xr = p.xr; tp.y = y; tp.y_stride = y_stride; tp.nf = nf;
             launch(tile_kernel, dim3((nf + kPfbTileF - 1) / kPfbTileF), dim3(kPfbTileF), tile_smem, c.stream, tp);

@@ -176,14 +176,16 @@ __global__ void __launch_bounds__(kPfbTileF) k_pfb_tile(const CSDR_GRID_CONSTANT
 }
 
 // ---- large power-of-two M (128..1024): a CTA slides over its frames with a ring of rows --------------------------
-// Shared memory holds the last P + 1 = 15 rows of M samples (ring), two M-point DFT buffers and an [M][TF] output
+// Shared memory holds the last P + 1 = 15 rows of M samples (ring), two M-point DFT buffers and a [TF][M] output
 // tile.  Two frames are processed per iteration by the two halves of the CTA (M/4 threads each): the two new rows are
-// loaded once (coalesced, prefetched through registers one iteration ahead), thread i of a half evaluates the four
-// polyphase branches n = i + j M/4 of its frame (4 x 14 taps in registers for the whole kernel) straight into
-// digit-reversed DFT order, the DFT runs in shared memory (radix-4 DIT stages, one butterfly per thread and stage,
-// plus one radix-2 stage when log2 M is odd), and the frame is parked in the output tile; every TF frames the tile is
-// written out channel-major, TF consecutive frames (64 bytes) per channel.  Each input sample is read from HBM once
-// (plus 13 rows of halo per CTA), each output written once.
+// loaded once (coalesced, prefetched through registers one iteration ahead) and thread i of a half evaluates the four
+// polyphase branches n = i + j M/4 of its frame (4 x 14 taps in registers for the whole kernel).  Those four values
+// are exactly the inputs of one radix-4 decimation-in-frequency butterfly, so the first DFT level runs in registers;
+// further radix-4 levels run in shared memory (consecutive threads = consecutive addresses) until the blocks are 16
+// or 32 long, and those are finished as register FFTs, one thread per block (blocks padded by two samples so that the
+// 16-byte loads of neighbouring threads fall into different banks).  DIF leaves the frequencies digit-reversed; the
+// permutation is folded into the (padded) output tile, which is written out every TF frames, TF consecutive frames
+// (64 bytes) per channel.  Each input sample is read from HBM once (plus 13 rows of halo per CTA), each output once.
 constexpr int kPfbRingP = 14, kPfbRingTF = 8, kPfbRingCPT = 4, kPfbRingRows = kPfbRingP + 1;
 
 struct PfbRingParams {
@@ -193,31 +195,40 @@ struct PfbRingParams {
     const float *h;          // prototype, P*M taps
     const float2 *tw;        // M twiddles exp(-j 2 pi t / M)
 };
-inline size_t pfb_ring_smem(int M) { return (size_t)M * sizeof(float2) * (kPfbRingRows + 2 + (kPfbRingTF + 1) + 1); }
-
-// position of element n in the input order of the mixed-radix DIT below (stage radices 2?, 4, 4, ...; the LAST stage
-// splits n by its lowest base-4 digit): pos = digits of n in reverse order, i.e. the bit reversal of n with the two
-// bits of every base-4 digit swapped back; with odd log2 M the top bit of n (the radix-2 stage) lands in bit 0
-__device__ __forceinline__ int pfb_ring_perm(int n, int lm)
+// log2 of the register-FFT size: 4 when log2 M is even, 5 when it is odd
+inline int pfb_ring_lfz(int log2M) { return (log2M & 1) ? 5 : 4; }
+inline size_t pfb_ring_work(int M, int lfz) { return (size_t)M + 2 * ((size_t)M >> lfz); }          // padded DFT buffer
+inline size_t pfb_ring_orow(int M) { return (size_t)M + ((size_t)M >> 4) + 2; }                     // padded tile row
+inline size_t pfb_ring_smem(int M, int log2M)
 {
-    const unsigned r = __brev((unsigned)n) >> (32 - lm);
-    if (lm & 1) {
-        const unsigned low = r & 1u, up = r >> 1;
-        return (int)(((((up & 0x55555555u) << 1) | ((up & 0xAAAAAAAAu) >> 1)) << 1) | low);
-    }
-    return (int)(((r & 0x55555555u) << 1) | ((r & 0xAAAAAAAAu) >> 1));
+    return sizeof(float2) * ((size_t)kPfbRingRows * M + 2 * pfb_ring_work(M, pfb_ring_lfz(log2M)) + kPfbRingTF * pfb_ring_orow(M) + M);
 }
 
+__device__ __forceinline__ float2 pfb_cmul(float2 a, float2 w) { return cf(a.x * w.x - a.y * w.y, a.x * w.y + a.y * w.x); }
+
+// radix-4 DIF butterfly on x[0..3] (inputs N/4 apart), outputs y_q for frequencies = q (mod 4), twiddled by w^q
+__device__ __forceinline__ void pfb_dif4(float2 (&x)[4], float2 w1, float2 w2, float2 w3)
+{
+    const float2 t0 = cf(x[0].x + x[2].x, x[0].y + x[2].y), t1 = cf(x[0].x - x[2].x, x[0].y - x[2].y);
+    const float2 t2 = cf(x[1].x + x[3].x, x[1].y + x[3].y), t3 = cf(x[1].y - x[3].y, x[3].x - x[1].x);   // -j (x1 - x3)
+    x[0] = cf(t0.x + t2.x, t0.y + t2.y);
+    x[1] = pfb_cmul(cf(t1.x + t3.x, t1.y + t3.y), w1);
+    x[2] = pfb_cmul(cf(t0.x - t2.x, t0.y - t2.y), w2);
+    x[3] = pfb_cmul(cf(t1.x - t3.x, t1.y - t3.y), w3);
+}
+
+template <int LFZ>
 __global__ void __launch_bounds__(512, 1) k_pfb_ring(const PfbRingParams p)
 {
-    constexpr int P = kPfbRingP, TF = kPfbRingTF, CPT = kPfbRingCPT, TFP = TF + 1, RR = kPfbRingRows;
+    constexpr int P = kPfbRingP, TF = kPfbRingTF, CPT = kPfbRingCPT, RR = kPfbRingRows, FZ = 1 << LFZ;
     CSDR_DYN_SMEM(smem_raw);
     const int M = p.M, lm = p.log2M, NT = M / CPT;                // blockDim.x = 2 NT
     const int half_id = threadIdx.x / NT, tid = threadIdx.x - half_id * NT, gtid = threadIdx.x;
+    const int WP = M + 2 * (M >> LFZ), OR = M + (M >> 4) + 2;
     float2 *ring = reinterpret_cast<float2 *>(smem_raw);          // [RR][M]
-    float2 *work = ring + RR * M + half_id * M;                    // [2][M]
-    float2 *obuf = ring + RR * M + 2 * M;                          // [M][TFP]
-    float2 *stw = obuf + M * TFP;                                  // [M] twiddles
+    float2 *work = ring + RR * M + half_id * WP;                   // [2][WP], element i at i + 2 (i >> LFZ)
+    float2 *obuf = ring + RR * M + 2 * WP;                         // [TF][OR], channel c at c + (c >> 4)
+    float2 *stw = obuf + TF * OR;                                  // [M] twiddles
     const int t0 = blockIdx.x * p.T, t1 = min(t0 + p.T, p.nf);
     if (t0 >= t1) return;
     for (int i = gtid; i < M; i += 2 * NT) stw[i] = p.tw[i];
@@ -247,6 +258,7 @@ __global__ void __launch_bounds__(512, 1) k_pfb_ring(const PfbRingParams p)
         }
     };
     fetch_rows(t0);
+    const int nlev = (lm - LFZ) / 2;                                // radix-4 levels (the first one in registers)
     for (int t = t0; t < t1; t += 2) {
         const int my_t = t + half_id;                               // this half's frame
         const bool have = my_t < t1;
@@ -268,49 +280,54 @@ __global__ void __launch_bounds__(512, 1) k_pfb_ring(const PfbRingParams p)
                 for (int j = 0; j < CPT; j++) ffma2(acc[j], hh[j][k], row[j * NT]);
                 slot = (slot == 0) ? RR - 1 : slot - 1;
             }
+            // first DIF level: inputs n = tid + j M/4, outputs to the same positions, twiddle W_M^(q tid)
+            pfb_dif4(acc, stw[tid], stw[2 * tid], stw[3 * tid]);
 #pragma unroll
-            for (int j = 0; j < CPT; j++) work[pfb_ring_perm(tid + j * NT, lm)] = acc[j];
+            for (int j = 0; j < CPT; j++) { const int i = tid + j * NT; work[i + 2 * (i >> LFZ)] = acc[j]; }
         }
         __syncthreads();
-        int s = 0;                                                  // bits done so far
-        if (lm & 1) {
-            // one radix-2 stage on adjacent elements: two butterflies per thread
+        for (int lev = 1; lev < nlev; lev++) {
+            // blocks of 4 q: butterfly b = tid -> block b / q, offset jj = b % q, twiddle W_{4q}^(jj) = W_M^(jj M / 4q)
             if (have) {
+                const int lq = lm - 2 * (lev + 1), q = 1 << lq, jj = tid & (q - 1), base = ((tid >> lq) << (lq + 2)) + jj;
+                float2 x[4];
 #pragma unroll
-                for (int q = 0; q < 2; q++) {
-                    float2 *a = work + 2 * (tid + q * NT);
-                    const float2 u = a[0], v = a[1];
-                    a[0] = cf(u.x + v.x, u.y + v.y);
-                    a[1] = cf(u.x - v.x, u.y - v.y);
+                for (int k = 0; k < 4; k++) { const int i = base + k * q; x[k] = work[i + 2 * (i >> LFZ)]; }
+                const int tws = jj << (2 * lev);
+                pfb_dif4(x, stw[tws], stw[2 * tws], stw[3 * tws]);
+#pragma unroll
+                for (int k = 0; k < 4; k++) { const int i = base + k * q; work[i + 2 * (i >> LFZ)] = x[k]; }
+            }
+            __syncthreads();
+        }
+        if (have && tid < (M >> LFZ)) {
+            // FZ-point DFT of block u = tid in registers (radix-2 DIT, natural-order output k); its frequencies are
+            // c = digit-reverse(u) + (M / FZ) k
+            const float4 *src = reinterpret_cast<const float4 *>(work + tid * (FZ + 2));
+            float2 a[FZ], b[FZ];
+#pragma unroll
+            for (int i = 0; i < FZ / 2; i++) { const float4 v = src[i]; a[2 * i] = cf(v.x, v.y); a[2 * i + 1] = cf(v.z, v.w); }
+#pragma unroll
+            for (int i = 0; i < FZ; i++) b[i] = a[pfb_rev<LFZ>(i)];
+#pragma unroll
+            for (int s = 1; s <= LFZ; s++) {
+                const int len = 1 << s, hl = len >> 1;
+#pragma unroll
+                for (int grp = 0; grp < FZ; grp += len) {
+#pragma unroll
+                    for (int j = 0; j < hl; j++) {
+                        const float2 w = stw[(j * (FZ / len)) << (lm - LFZ)];
+                        const float2 u = b[grp + j], v = pfb_cmul(b[grp + j + hl], w);
+                        b[grp + j] = cf(u.x + v.x, u.y + v.y);
+                        b[grp + j + hl] = cf(u.x - v.x, u.y - v.y);
+                    }
                 }
             }
-            __syncthreads();
-            s = 1;
-        }
-        for (; s < lm; s += 2) {
-            // radix-4 DIT stage: sub-transforms of length 2^s -> 2^(s+2); one butterfly per thread
-            if (have) {
-                const int quarter = 1 << s, jj = tid & (quarter - 1), grp = tid >> s;
-                float2 *a = work + (grp << (s + 2)) + jj;
-                const int tws = jj << (lm - s - 2);                 // W_{4 quarter}^{jj} = W_M^{jj M / (4 quarter)}
-                const float2 w1 = stw[tws], w2 = stw[2 * tws], w3 = stw[3 * tws];
-                const float2 x0 = a[0], x1 = a[quarter], x2 = a[2 * quarter], x3 = a[3 * quarter];
-                const float2 b1 = cf(x1.x * w1.x - x1.y * w1.y, x1.x * w1.y + x1.y * w1.x);
-                const float2 b2 = cf(x2.x * w2.x - x2.y * w2.y, x2.x * w2.y + x2.y * w2.x);
-                const float2 b3 = cf(x3.x * w3.x - x3.y * w3.y, x3.x * w3.y + x3.y * w3.x);
-                const float2 s02 = cf(x0.x + b2.x, x0.y + b2.y), d02 = cf(x0.x - b2.x, x0.y - b2.y);
-                const float2 s13 = cf(b1.x + b3.x, b1.y + b3.y), d13 = cf(b1.x - b3.x, b1.y - b3.y);
-                a[0] = cf(s02.x + s13.x, s02.y + s13.y);
-                a[quarter] = cf(d02.x + d13.y, d02.y - d13.x);      // d02 - j d13
-                a[2 * quarter] = cf(s02.x - s13.x, s02.y - s13.y);
-                a[3 * quarter] = cf(d02.x - d13.y, d02.y + d13.x);  // d02 + j d13
-            }
-            __syncthreads();
-        }
-        if (have) {
-            const int tf = (my_t - t0) & (TF - 1);
+            int cr = 0;
+            for (int d = 0, u = tid; d < nlev; d++, u >>= 2) cr = (cr << 2) | (u & 3);   // base-4 digits of u reversed
+            float2 *ob = obuf + ((my_t - t0) & (TF - 1)) * OR;
 #pragma unroll
-            for (int j = 0; j < CPT; j++) { const int c = tid + j * NT; obuf[c * TFP + tf] = work[c]; }
+            for (int k = 0; k < FZ; k++) { const int c = cr + (k << (lm - LFZ)); ob[c + (c >> 4)] = b[k]; }
         }
         const int last = min(t + 1, t1 - 1);                        // last frame parked so far
         const int tfl = (last - t0) & (TF - 1);
@@ -319,9 +336,10 @@ __global__ void __launch_bounds__(512, 1) k_pfb_ring(const PfbRingParams p)
             const int cnt = tfl + 1, tb = last - tfl;               // frames parked in the tile, first of them
             for (int e = gtid; e < M * TF; e += 2 * NT) {
                 const int c = e >> 3, f = e & (TF - 1);
-                if (f < cnt) p.y[(long long)c * p.y_stride + tb + f] = obuf[c * TFP + f];
+                if (f < cnt) p.y[(long long)c * p.y_stride + tb + f] = obuf[f * OR + c + (c >> 4)];
             }
         }
+        // the barrier at the top of the next iteration separates these reads from the next writes of work / obuf
     }
 }
 

@@ -219,7 +219,8 @@ extern "C" long long emu_pfb(int M, int kind, const float2 *x, long long nf_tota
             rp.xr = xr.data(); rp.y = y + pos; rp.y_stride = nf_total; rp.nf = (int)nf; rp.M = M; rp.log2M = log2M;
             rp.h = h.data(); rp.tw = tw.data();
             rp.T = 3 * kPfbRingTF;
-            launch(k_pfb_ring, dim3((unsigned)((nf + rp.T - 1) / rp.T)), dim3(2 * M / kPfbRingCPT), pfb_ring_smem(M), rp);
+            if (pfb_ring_lfz(log2M) == 4) launch(k_pfb_ring<4>, dim3((unsigned)((nf + rp.T - 1) / rp.T)), dim3(2 * M / kPfbRingCPT), pfb_ring_smem(M, log2M), rp);
+            else launch(k_pfb_ring<5>, dim3((unsigned)((nf + rp.T - 1) / rp.T)), dim3(2 * M / kPfbRingCPT), pfb_ring_smem(M, log2M), rp);
         } else {
             PfbParams p{};
             p.xr = xr.data(); p.y = y + pos; p.y_stride = nf_total; p.M = M; p.P = P; p.nf = (int)nf; p.F = 8; p.log2M = log2M;
