@@ -627,6 +627,7 @@ __global__ void k_agc_fixup(const BackendParams p)
 // One sample per thread, one 32-sample word per warp and iteration.  y[n] = y_dc[n] * (gain before sample n);
 // threshold bit = (gain after sample n) < g_thr; discriminator m[n] = arg(conj(y[n-1]) y[n]) / (2 pi kf)
 // (freqdem_demodulate).  Without an AGC the gain is 1 and there are no bits.
+constexpr int kEmitRun = 16;     // consecutive 32-sample words per warp: the previous sample comes from the neighbour lane
 template <bool AGC, bool FM, bool EXACT>
 __global__ void __launch_bounds__(256) k_be_emit(const BackendParams p)
 {
@@ -638,27 +639,42 @@ __global__ void __launch_bounds__(256) k_be_emit(const BackendParams p)
     float2 *__restrict__ oc = (float2 *)p.out + (long long)lane * p.out_lane_stride;
     const float g_thr = p.g_thr, fm_ref = p.fm_ref;
     const int n = p.n, nwords = p.nwords;
-    const int wstep = (int)((gridDim.x * blockDim.x) >> 5);
-    for (int w = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5); w < nwords; w += wstep) {
-        const int i = w * 32 + l;
-        const bool in = i < n;
-        float2 y = cf(0.f, 0.f), yp = cf(0.f, 0.f);
-        float ga = 1.f;
-        if (in) {
-            y = x[i];
+    const int w0 = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * kEmitRun, w1 = min(w0 + kEmitRun, nwords);
+    if (w0 >= nwords) return;                                    // whole warps leave together
+    // sample before the run (lane 31 holds it for the shuffle below): ungated output and the gain after it
+    float2 ylast = cf(0.f, 0.f);
+    float glast = 1.f;
+    {
+        const int i = w0 * 32 - 1;
+        if (i < 0) { ylast = p.y_first[lane]; if (AGC) glast = p.g_first[lane]; }
+        else {
+            ylast = x[i];
             if (AGC) {
-                ga = gp[i];
-                const float g0 = (i == 0) ? p.g_first[lane] : gp[i - 1];
-                y = cf(__fmul_rn(y.x, g0), __fmul_rn(y.y, g0));
-            }
-            if (FM) {
-                if (i == 0) yp = p.y_first[lane];
-                else {
-                    yp = x[i - 1];
-                    if (AGC) { const float g1 = (i == 1) ? p.g_first[lane] : gp[i - 2]; yp = cf(__fmul_rn(yp.x, g1), __fmul_rn(yp.y, g1)); }
-                }
+                glast = gp[i];
+                const float g1 = (i == 0) ? p.g_first[lane] : gp[i - 1];
+                ylast = cf(__fmul_rn(ylast.x, g1), __fmul_rn(ylast.y, g1));
             }
         }
+    }
+    for (int w = w0; w < w1; w++) {
+        const int i = w * 32 + l;
+        const bool in = i < n;
+        float2 y = cf(0.f, 0.f);
+        float ga = 1.f;
+        if (in) { y = x[i]; if (AGC) ga = gp[i]; }
+        // gain before this sample = gain after the previous one: neighbour lane, or the last lane of the previous word
+        float g0 = 1.f;
+        if (AGC) {
+            g0 = __shfl_up_sync(0xffffffffu, ga, 1);
+            if (l == 0) g0 = glast;
+            y = cf(__fmul_rn(y.x, g0), __fmul_rn(y.y, g0));
+        }
+        float2 yp;
+        yp.x = __shfl_up_sync(0xffffffffu, y.x, 1); yp.y = __shfl_up_sync(0xffffffffu, y.y, 1);
+        if (l == 0) yp = ylast;
+        // carry lane 31 to the next word (every lane keeps a copy)
+        ylast.x = __shfl_sync(0xffffffffu, y.x, 31); ylast.y = __shfl_sync(0xffffffffu, y.y, 31);
+        if (AGC) glast = __shfl_sync(0xffffffffu, ga, 31);
         if (AGC) {
             const unsigned ex = __ballot_sync(0xffffffffu, in && ga < g_thr);       // rssi = -20 log10(g) > threshold
             if (l == 0) exb[w] = ex;
@@ -912,7 +928,7 @@ inline void be_launch_gain(Launch &launch, const BackendParams &b)
 template <bool AGC, bool FM, class Launch>
 inline void be_launch_emit(Launch &launch, const BackendParams &b)
 {
-    const dim3 grid((unsigned)std::max(1, std::min(65535, (b.nwords + 127) / 128)), b.nlanes), block(256);   // ~16 words per warp
+    const dim3 grid((unsigned)std::max(1, (b.nwords + 8 * kEmitRun - 1) / (8 * kEmitRun)), b.nlanes), block(256);   // kEmitRun words per warp
     if (b.exact_math) launch(k_be_emit<AGC, FM, true>, grid, block, 0, b);
     else              launch(k_be_emit<AGC, FM, false>, grid, block, 0, b);
 }
