@@ -3,7 +3,7 @@
 
 Workload (BASELINE.json configs[1], "C2"): 2.56 MS/s synthetic CF32 -> offset mix (+100 kHz) -> msresamp to
 200 kHz -> dc blocker -> AGC/squelch (-40 dB) -> NBFM demod (kf 0.3).  A "step" is one pass of the chain over one
-chunk of 2^LOG2N input samples that is already resident in HBM (the chunk is 1 GiB at the default 2^27, far larger
+chunk of 2^LOG2N input samples that is already resident in HBM (the chunk is 2 GiB at the default 2^28, far larger
 than the 126 MB L2, so no L2 flush is needed between steps); stream state carries from step to step.
 
     python bench.py [--gpus N --steps K --warmup W]                 # our CUDA path
@@ -336,7 +336,7 @@ def run_ours(args):
             "warmup": max(args.warmup, 3), "ms_per_step": ms_max / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "C2: 2.56 MS/s CF32 -> mix 100 kHz -> msresamp 200 kHz -> dcblock -> AGC -40 dB -> NBFM",
-                       "chunk_samples": n, "l2": "inputs (1 GiB/step at 2^27) larger than L2, no flush",
+                       "chunk_samples": n, "l2": f"inputs ({n * 8 / 2**30:g} GiB/step) larger than L2, no flush",
                        "sharding": "time segments of one stream per rank (seek + overlap-save warm-up), no collective"},
             "clocks": clk, "gpu_launches": int(launches),
             "e2e": {"value": e2e_val, "unit": "Msamples/s", "h2d_bytes_per_step": ne * 8, "d2h_bytes_per_step": int(nye) * 4,
@@ -370,7 +370,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--log2n", type=int, default=27, help="log2 of the chunk size in samples per step per GPU")
+    ap.add_argument("--log2n", type=int, default=28, help="log2 of the chunk size in samples per step per GPU")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     args = ap.parse_args()
