@@ -14,5 +14,10 @@ if [ "$mode" = "full" ]; then
   echo "== ncu full capture of k_frontend"
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_frontend -s 3 -c 2 -o gpurun_out/prof_frontend -f \
       python bench.py --steps 2 --warmup 3 --log2n 26 --no-cpu > gpurun_out/ncu_full.log 2>&1
+  echo "== ncu full capture of the back-end kernels"
+  for k in k_agc_chain k_be_emit k_be_prep k_dc_local; do
+    timeout 300 ncu --set full --clock-control none -k regex:$k -s 4 -c 1 -o gpurun_out/prof_$k -f \
+        python bench.py --steps 2 --warmup 3 --log2n 26 --no-cpu > gpurun_out/ncu_$k.log 2>&1
+  done
   ls -la gpurun_out
 fi

@@ -72,4 +72,21 @@ json.dump({"kernel": "k_frontend", "chunk_samples": 1 << 26,
            "dram_bytes_read": sum(rd) / len(rd), "dram_bytes_write": sum(wr) / len(wr),
            "source": f"profiles/{tag}_frontend_ncu.txt (ncu --set full, 2^26-sample launch)"},
           open(os.path.join(OUT, "traffic.json"), "w"), indent=1)
+# back-end kernels (one launch each), same metric list
+with open(os.path.join(OUT, f"{tag}_backend_ncu.txt"), "w") as f:
+    f.write("# ncu --set full --clock-control none -k regex:<kernel> -s 4 -c 1 python bench.py --steps 2 --warmup 3 --log2n 26 --no-cpu\n")
+    for k in ("k_agc_chain", "k_be_emit", "k_be_prep", "k_dc_local"):
+        r = os.path.join(G, f"prof_{k}.ncu-rep")
+        if not os.path.exists(r):
+            continue
+        raw = subprocess.run(["ncu", "-i", r, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+        rr = list(csv.reader(io.StringIO(raw)))
+        if len(rr) < 3:
+            continue
+        h2, u2, v2 = rr[0], rr[1], rr[2]
+        f.write(f"## {k}\n")
+        for w in want:
+            if w in h2:
+                i = h2.index(w)
+                f.write(f"{w:92s} {u2[i]:14s} {v2[i]}\n")
 print(open(os.path.join(OUT, f"{tag}_launches.csv")).read())
