@@ -80,7 +80,7 @@ with open(os.path.join(OUT, f"{tag}_backend_ncu.txt"), "w") as f:
         if not os.path.exists(r):
             continue
         raw = subprocess.run(["ncu", "-i", r, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-        rr = list(csv.reader(io.StringIO(raw)))
+        rr = list(csv.reader(raw.splitlines()))
         if len(rr) < 3:
             continue
         h2, u2, v2 = rr[0], rr[1], rr[2]
