@@ -8,6 +8,7 @@
 #include "frontend_std.cuh"
 #include "frontend_plan.hpp"
 #include "interp.cuh"
+#include <cuda.h>
 #include "backend.cuh"
 #include "pfb.cuh"
 #include <stdexcept>
@@ -153,6 +154,7 @@ struct Frontend {
     bool interp = false; InterpPlan ip; DevBuf ibuf[2], xmix;      // rate > 1: arbitrary stage first, then half-band interpolators
     int mix_mode = 0; uint32_t theta0 = 0, dtheta = 0; int quantize = 1;
     void (*kernel)(FrontendParams) = k_frontend;
+    void (*kernel_direct)(FrontendParams, FeTmap) = nullptr;     // k_frontend_direct<S>: needs a tensor map per call
     int ctas_per_sm = 2, fe_threads = 256;
     // optional event timing of k_frontend (bench roofline): pairs recorded on the launching stream
     bool profile = false;
@@ -221,12 +223,12 @@ struct Frontend {
             }
         } else if (geo.std_kernel) {
             switch (ms.S) {
-            case 1: kernel = k_frontend_direct<1>; break;
-            case 2: kernel = k_frontend_direct<2>; break;
-            case 3: kernel = k_frontend_direct<3>; break;
-            case 4: kernel = k_frontend_direct<4>; break;
-            case 5: kernel = k_frontend_direct<5>; break;
-            case 6: kernel = k_frontend_direct<6>; break;
+            case 1: kernel_direct = k_frontend_direct<1>; break;
+            case 2: kernel_direct = k_frontend_direct<2>; break;
+            case 3: kernel_direct = k_frontend_direct<3>; break;
+            case 4: kernel_direct = k_frontend_direct<4>; break;
+            case 5: kernel_direct = k_frontend_direct<5>; break;
+            case 6: kernel_direct = k_frontend_direct<6>; break;
             default: throw CudaError{"frontend: no direct-read kernel for this stage count"};
             }
         }
@@ -234,11 +236,55 @@ struct Frontend {
         for (auto &h : hist) { h.ensure(hb); CK(cudaMemsetAsync(h.p, 0, h.cap, c.stream)); }
         bank.ensure(ms.bank.size() * sizeof(float));
         CK(cudaMemcpyAsync(bank.p, ms.bank.data(), ms.bank.size() * sizeof(float), cudaMemcpyHostToDevice, c.stream));
-        CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)geo.smem_bytes));
         fe_threads = geo.std_kernel ? kFeNT : 256;
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kernel, fe_threads, geo.smem_bytes));
+        if (kernel_direct) {
+            CK(cudaFuncSetAttribute(kernel_direct, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)geo.smem_bytes));
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kernel_direct, fe_threads, geo.smem_bytes));
+        } else {
+            CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)geo.smem_bytes));
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kernel, fe_threads, geo.smem_bytes));
+        }
         if (ctas_per_sm < 1) throw CudaError{"frontend: tile does not fit in shared memory"};
         c.sync();
+    }
+    // Tensor map over the chunk for k_frontend_direct: x viewed as [nstreams][rows][32 floats], rows of 16 samples,
+    // starting at sample tma_r so that every tile starts on a row boundary (tiles are a multiple of 16 samples apart).
+    // Not possible (tma_ok = 0, tiles are then filled by ordinary loads) when that start is not 16-byte aligned.
+    void make_tensor_map(const float2 *x, long long nx, long long x_stride, FrontendParams &p, FeTmap &tm)
+    {
+        typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                     const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+        static EncodeFn encode = nullptr;
+        static bool looked = false;
+        if (!looked) {
+            looked = true;
+            void *fn = nullptr;
+            cudaDriverEntryPointQueryResult qr;
+            if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr) == cudaSuccess && qr == cudaDriverEntryPointSuccess)
+                encode = (EncodeFn)fn;
+        }
+        p.tma_ok = 0; p.tma_r = 0; p.tma_rows = 0;
+        if (!encode || nx < kFeRawRow) return;
+        const FeGeom &G = geo.geom;
+        const long long lo0 = (p.K0 - kHcPad) * (1LL << G.S) + G.d[G.S];          // first tile's first raw sample
+        const long long r = (((lo0 - p.n0) % kFeRawRow) + kFeRawRow) % kFeRawRow;
+        const float2 *base = x + r;
+        const long long rows = (nx - r) / kFeRawRow;
+        if (rows < 1 || (reinterpret_cast<uintptr_t>(base) & 15) != 0) return;
+        if (nstreams > 1 && ((x_stride * (long long)sizeof(float2)) & 15) != 0) return;
+        constexpr int kBoxMax = 256;
+        const int tile_rows = G.n[G.S] / kFeRawRow, nb = (tile_rows + kBoxMax - 1) / kBoxMax, box = tile_rows / nb;
+        cuuint64_t dims[3] = {32, (cuuint64_t)rows, (cuuint64_t)nstreams};
+        cuuint64_t strides[2] = {128, (cuuint64_t)(nstreams > 1 ? x_stride * (long long)sizeof(float2) : rows * 128)};
+        cuuint32_t boxd[3] = {32, (cuuint32_t)box, 1};
+        cuuint32_t estr[3] = {1, 1, 1};
+        static_assert(sizeof(FeTmap) == sizeof(CUtensorMap), "FeTmap mirrors CUtensorMap");
+        const CUresult rc = encode(reinterpret_cast<CUtensorMap *>(&tm), CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void *)base, dims, strides, boxd,
+                                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (rc != CUDA_SUCCESS) return;
+        p.tma_ok = 1; p.tma_r = (int)r; p.tma_rows = rows;
     }
     long long run_interp(const Ctx &c, const float2 *x, long long nx, long long x_stride, float2 *y, long long y_stride)
     {
@@ -287,7 +333,13 @@ struct Frontend {
                 else { CK(cudaEventCreate(&ev.first)); CK(cudaEventCreate(&ev.second)); }
                 CK(cudaEventRecord(ev.first, c.stream));
             }
-            launch(kernel, dim3(gx, nstreams), dim3(fe_threads), geo.smem_bytes, c.stream, p);
+            if (kernel_direct) {
+                FeTmap tm{};
+                make_tensor_map(x, nx, x_stride, p, tm);
+                launch(kernel_direct, dim3(gx, nstreams), dim3(fe_threads), geo.smem_bytes, c.stream, p, tm);
+            } else {
+                launch(kernel, dim3(gx, nstreams), dim3(fe_threads), geo.smem_bytes, c.stream, p);
+            }
             if (profile) { CK(cudaEventRecord(ev.second, c.stream)); ev_pending.push_back(ev); }
         }
         if (nx > 0) {

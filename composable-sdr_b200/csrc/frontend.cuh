@@ -62,6 +62,8 @@ struct FrontendParams {
     unsigned long long ph0;     // resampler phase (liquid's q->phase) before push K0: output o' of this call has
                                 // phase ph0 + o'*step relative to push K0
     int off_bank;               // float offset (in floats) of the bank copy in dynamic smem
+    int tma_ok, tma_r;          // k_frontend_direct: a tensor map covers x from sample tma_r on (rows of 16 samples)
+    long long tma_rows;         // whole rows it covers
     int smem_bytes;
 };
 

@@ -40,17 +40,17 @@ __host__ __device__ constexpr FeGeom fe_make_geom(int S, int Tc, const int *m, i
     // more threads busy but re-read shared memory more often, and shared-memory bandwidth is what binds this kernel
     // (measured: slots 8/4/2 -> 236 us, 8/8/4 -> 227 us per 2^26 samples).
     for (int s = 0; s < S; s++) { g.m[s] = m[s]; g.R[s] = (s == 0 && S > 1) ? 4 : 8; }
-    // raw = 1: the top level is the raw tile itself, linear, as the bulk copy delivers it; the first half-band stage
-    // reads (even, odd) pairs from it with 16-byte loads, kFeTopR outputs per thread slot (odd: conflict-free)
+    // raw = 1: the top level is the raw tile itself as the TMA tensor copy delivers it: whole rows of 16 samples
+    // (128 bytes), 128-byte swizzle, at the start of shared memory (1024-byte aligned).  The first half-band stage
+    // reads (even, odd) pairs from it with 16-byte loads, 8 outputs per thread slot = one row per slot.
     const int direct = (raw == 1 && S > 0) ? 1 : 0;
-    if (direct) g.R[S - 1] = kFeTopR;
     g.n[0] = Tc + kHcPad; g.d[0] = 0;
     for (int L = 0; L < S; L++) {
         const int sh = (L + 1 == S) ? g.shift : 0;
         const int need = 2 * g.n[L] + 4 * g.m[L] - 2 + sh;
         int mult = 2 * g.R[L];
-        if (L + 1 < S && !(direct && L + 2 == S)) mult = ce_max(mult, g.R[L + 1]);
-        if (direct && L + 1 == S) mult = 2;
+        if (L + 1 < S) mult = ce_max(mult, g.R[L + 1]);
+        if (direct && L + 1 == S) mult = (need > 256 * kFeRawRow) ? 2 * kFeRawRow : kFeRawRow;   // one or two TMA boxes of <= 256 rows
         g.n[L + 1] = ce_roundup(need, mult);
         g.d[L + 1] = 2 * g.d[L] + 1 - 4 * g.m[L] - sh;
     }
@@ -60,9 +60,7 @@ __host__ __device__ constexpr FeGeom fe_make_geom(int S, int Tc, const int *m, i
     int sizeA = 0, sizeB = 0, sizeT = 0;
     for (int L = 1; L <= S; L++) {
         if (direct && L == S) {
-            // the last slot may run past n[S-1] outputs; its reads stay inside the buffer
-            const int slots = (g.n[S - 1] + kFeTopR - 1) / kFeTopR;
-            sizeT = ce_roundup(ce_max(g.n[S], 2 * (kFeTopR * slots + 2 * g.m[S - 1] + 1)), 2) + 2;
+            sizeT = ce_roundup(g.n[S], 128);                        // whole 1024-byte swizzle atoms
             continue;
         }
         const int D = g.R[L - 1];
@@ -74,9 +72,9 @@ __host__ __device__ constexpr FeGeom fe_make_geom(int S, int Tc, const int *m, i
         else if (((S - L) & 1) == 0) sizeA = ce_max(sizeA, sz); else sizeB = ce_max(sizeB, sz);
     }
     const int size0 = ce_roundup(g.n[0] + 2, 2);
-    g.off[0] = 0;
+    g.off[0] = priv ? sizeT : 0;                                   // the swizzled tile comes first (alignment)
     for (int L = 1; L <= S; L++) g.off[L] = size0 + sizeT + ((((S - L) & 1) == 0) ? 0 : sizeA);
-    if (priv) g.off[S] = size0;
+    if (priv) g.off[S] = 0;
     g.total_f2 = size0 + sizeT + sizeA + sizeB;
     g.hcap = ce_roundup(((1 << S) - 1) + (kHcPad << S) - g.d[S] + 1, 64);
     return g;

@@ -59,6 +59,11 @@ __device__ __forceinline__ bool fe_tile_is_bulk(const FrontendParams &p, const f
 {
     constexpr int NS = FeStd<S, V>::G.n[S];
     const long long rel0 = lo - p.n0;
+    if (V == 1) {
+        // the tensor map covers whole 16-sample rows of x from sample tma_r on; tiles start on row boundaries
+        const long long rr = rel0 - p.tma_r;
+        return p.tma_ok && rr >= 0 && (rr & (kFeRawRow - 1)) == 0 && (rr / kFeRawRow) + NS / kFeRawRow <= p.tma_rows;
+    }
     return rel0 >= 0 && rel0 + NS <= p.nx && (reinterpret_cast<uintptr_t>(xs + rel0) & 15) == 0;
 }
 
@@ -329,27 +334,35 @@ __global__ void __launch_bounds__(kFeNT, 2) k_frontend_std(const CSDR_GRID_CONST
 }
 
 // =============================================================================================================
-// k_frontend_direct: the raw tile is bulk-copied (TMA) into a linear staging buffer and the first half-band stage reads it
-// there: one 16-byte load fetches the (even, odd) pair -- the even sample is a tap input, the odd one a centre input
-// (the top level starts one sample early, shift = 1) -- and both are multiplied by the NCO phasor in registers.
-// kFeTopR = 7 outputs per thread slot: consecutive slots start 7 pairs apart, so the eight lanes of a quarter-warp
-// hit eight different 16-byte banks.  No mixing pass, no de-interleaving pass, no LSU work for the copy; the lower
-// stages and the resampler are those of k_frontend_std.
+// k_frontend_direct: the raw tile is brought in by ONE TMA tensor copy (rows of 16 samples, 128-byte swizzle) and the
+// first half-band stage reads it where it lands: one 16-byte load fetches the (even, odd) pair -- the even sample is a
+// tap input, the odd one a centre input (the top level starts one sample early, shift = 1) -- and both are multiplied
+// by the NCO phasor in registers.  8 outputs per thread slot = one row per slot: the swizzle puts the same chunk
+// position of eight consecutive rows into eight different banks, so the loads of a quarter-warp are conflict-free, and
+// the results go to the next level with the conflict-free store pattern of fe_stage_c.  No mixing pass, no
+// de-interleaving pass, no LSU work for the copy; the lower stages and the resampler are those of k_frontend_std.
+
+// 16-byte chunk index of pair P in the swizzled tile
+__device__ __forceinline__ int fe_swz(int P) { return (P & ~7) | ((P ^ (P >> 3)) & 7); }
+
 template <int M, int NOUT, bool LAST, int D2, int STR2, int MIX>
 __device__ __forceinline__ void fe_stage_top(const float2 *__restrict__ raw, float2 *__restrict__ out,
                                              const float *__restrict__ g, float zeta, unsigned thb, unsigned dth)
 {
-    constexpr int R = kFeTopR, NSLOTS = (NOUT + R - 1) / R, NC = R + 2 * M - 1;
+    constexpr int R = kFeTopR, NSLOTS = NOUT / R, NC = R + 2 * M - 1;
+    static_assert(R == 8 && NOUT % R == 0 && kFeRawRow == 2 * R, "one slot per 128-byte row");
+    const float4 *src = reinterpret_cast<const float4 *>(raw);
     for (int t = threadIdx.x; t < NSLOTS; t += kFeNT) {
-        // output q = R t + r:  centre = odd sample of pair q + M, tap u = even sample of pair q + u + 1
-        const float4 *src = reinterpret_cast<const float4 *>(raw) + (R * t + 1);
+        // output q = R t + r:  centre = odd sample of pair q + M, tap u = even sample of pair q + u + 1.
+        // Pair 8 t + k sits in row t + (k >> 3), chunk (k & 7) ^ ((t + (k >> 3)) & 7).
         const unsigned ths = thb + (unsigned)(2 * (R * t + 1)) * dth;
         float2 acc[R];
 #pragma unroll
         for (int r = 0; r < R; r++) acc[r] = cf(0.f, 0.f);
 #pragma unroll
         for (int c = 0; c < NC; c++) {
-            const float4 pr = src[c];
+            const int k = c + 1, row = t + (k >> 3);
+            const float4 pr = src[row * 8 + ((k & 7) ^ (row & 7))];
             const float2 v = fe_mix_q<MIX>(cf(pr.x, pr.y), ths + (unsigned)(2 * c) * dth);
 #pragma unroll
             for (int r = 0; r < R; r++) {
@@ -361,13 +374,22 @@ __device__ __forceinline__ void fe_stage_top(const float2 *__restrict__ raw, flo
                 acc[c - (M - 1)].x += e.x; acc[c - (M - 1)].y += e.y;
             }
         }
-        const int q0 = R * t;
+        if constexpr (LAST) {
+            float2 *o = out + t * R;
 #pragma unroll
-        for (int r = 0; r < R; r++) {
-            const int q = q0 + r;
-            if (q < NOUT) {
-                if constexpr (LAST) out[q] = cf(acc[r].x * zeta, acc[r].y * zeta);
-                else out[(q & 1) * (D2 * STR2 + kFePlanePad) + ((q >> 1) & (D2 - 1)) * STR2 + (q >> 1) / D2] = acc[r];
+            for (int r = 0; r < R; r++) o[r] = cf(acc[r].x * zeta, acc[r].y * zeta);
+        } else {
+            // q = R t + r -> plane r & 1, pair p = H t + (r >> 1) (H = R/2) -> sub-array p & (D2-1), index p / D2
+            constexpr int H = R / 2;
+            if constexpr (H >= D2) {
+                float2 *o = out + t * (H / D2);
+#pragma unroll
+                for (int r = 0; r < R; r++) o[(r & 1) * (D2 * STR2 + kFePlanePad) + ((r >> 1) & (D2 - 1)) * STR2 + (r >> 1) / D2] = acc[r];
+            } else {
+                constexpr int K = D2 / H;
+                float2 *o = out + (H * (t & (K - 1))) * STR2 + t / K;
+#pragma unroll
+                for (int r = 0; r < R; r++) o[(r & 1) * (D2 * STR2 + kFePlanePad) + (r >> 1) * STR2] = acc[r];
             }
         }
     }
@@ -396,7 +418,23 @@ __device__ __forceinline__ void fe_fill_staging(const FrontendParams &p, const f
         float2 v = cf(0.f, 0.f);
         if (rel >= 0) { if (rel < p.nx) v = xs[rel]; }
         else if (rel >= -(long long)p.hcap) v = hs[p.hcap + rel];
-        raw[i] = v;
+        raw[2 * fe_swz(i >> 1) + (i & 1)] = v;
+    }
+}
+
+// one tensor copy per tile (two when the tile has more than 256 rows), issued by one thread
+template <int S>
+__device__ __forceinline__ void fe_copy_staging(const FrontendParams &p, const FeTmap *tm, float2 *raw, long long lo,
+                                                unsigned long long *bar)
+{
+    constexpr int ROWS = FeStd<S, 1>::G.n[S] / kFeRawRow, NB = (ROWS + 255) / 256, BOX = ROWS / NB;
+    static_assert(BOX * NB == ROWS && BOX <= 256, "tile = NB boxes of BOX rows");
+    const int row0 = (int)((lo - p.n0 - p.tma_r) / kFeRawRow);
+    if (NB == 1) tma_load_rows(raw, tm, row0, (int)blockIdx.y, ROWS, bar);
+    else {
+        // a barrier phase takes ONE arrival: announce the whole tile with the first box
+        tma_load_rows(raw, tm, row0, (int)blockIdx.y, BOX, bar, ROWS);
+        for (int b = 1; b < NB; b++) tma_load_rows(raw + b * BOX * kFeRawRow, tm, row0 + b * BOX, (int)blockIdx.y, BOX, bar, 0);
     }
 }
 
@@ -406,11 +444,12 @@ __device__ __forceinline__ void fe_fill_staging(const FrontendParams &p, const f
 #define FE_NOFILL 0
 #endif
 template <int S>
-__global__ void __launch_bounds__(kFeNT, 3) k_frontend_direct(const CSDR_GRID_CONSTANT FrontendParams p)
+__global__ void __launch_bounds__(kFeNT, 3) k_frontend_direct(const CSDR_GRID_CONSTANT FrontendParams p, const CSDR_GRID_CONSTANT FeTmap tmap)
 {
     constexpr FeGeom G = FeStd<S, 1>::G;
     constexpr int NS = G.n[S];
-    CSDR_DYN_SMEM(smem_raw);
+    CSDR_DYN_SMEM_1K(smem_raw1k);
+    unsigned char *smem_raw = smem_raw1k;
     float2 *smem = reinterpret_cast<float2 *>(smem_raw);
     float *bank_s = reinterpret_cast<float *>(smem_raw) + 2 * G.total_f2;
     float2 *raw = smem + G.off[S];
@@ -438,7 +477,7 @@ __global__ void __launch_bounds__(kFeNT, 3) k_frontend_direct(const CSDR_GRID_CO
     }
     __syncthreads();
     if ((int)blockIdx.x < p.ntiles) {
-        if (FE_NOFILL) {} else if (s_info[0].bulk) { if (threadIdx.x == 0) bulk_copy_g2s(raw, xs + (s_info[0].lo - p.n0), NS * (unsigned)sizeof(float2), &s_bar); }
+        if (FE_NOFILL) {} else if (s_info[0].bulk) { if (threadIdx.x == 0) fe_copy_staging<S>(p, &tmap, raw, s_info[0].lo, &s_bar); }
         else fe_fill_staging<S>(p, xs, hs, raw, s_info[0].lo);
     }
     __syncthreads();
@@ -462,7 +501,7 @@ __global__ void __launch_bounds__(kFeNT, 3) k_frontend_direct(const CSDR_GRID_CO
         __syncthreads();
         // the staging buffer has been consumed: start fetching the next tile of this CTA
         if (tile + gstep < p.ntiles) {
-            if (FE_NOFILL) {} else if (s_info[nxt].bulk) { if (threadIdx.x == 0) bulk_copy_g2s(raw, xs + (s_info[nxt].lo - p.n0), NS * (unsigned)sizeof(float2), &s_bar); }
+            if (FE_NOFILL) {} else if (s_info[nxt].bulk) { if (threadIdx.x == 0) fe_copy_staging<S>(p, &tmap, raw, s_info[nxt].lo, &s_bar); }
             else fe_fill_staging<S>(p, xs, hs, raw, s_info[nxt].lo);
         }
         // bookkeeping for the tile after next: by a thread of the last warp, which has no slot in the lower stages

@@ -7,10 +7,12 @@
 #ifdef CSDR_EMU
 #include "cuda_emu.h"
 #define CSDR_DYN_SMEM(name) unsigned char *name = ::csdr_emu::dyn_smem()
+#define CSDR_DYN_SMEM_1K(name) unsigned char *name = ::csdr_emu::dyn_smem()
 #define CSDR_GRID_CONSTANT
 #else
 #include <cuda_runtime.h>
 #define CSDR_DYN_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
+#define CSDR_DYN_SMEM_1K(name) extern __shared__ __align__(1024) unsigned char name[]    /* 128-byte-swizzled TMA tiles */
 #define CSDR_GRID_CONSTANT __grid_constant__
 #endif
 
@@ -49,15 +51,47 @@ __device__ __forceinline__ void bulk_wait(unsigned long long *bar, unsigned pari
 }
 #endif
 
+// ---- TMA tensor copy with the 128-byte swizzle: the raw input viewed as rows of 16 samples (128 bytes) ------------
+// A tile of whole rows lands densely in shared memory (1024-byte aligned) with the 16-byte chunk c of row r stored at
+// chunk c ^ (r & 7), so that threads which read the same chunk position of consecutive rows hit different banks.
+// The descriptor is a CUtensorMap built on the host (cuTensorMapEncodeTiled) and passed as a __grid_constant__
+// parameter.  Under the test-only CPU emulation it is a plain (base, rows, stream stride) triple and the copy is a
+// loop that applies the same permutation.
+#ifdef CSDR_EMU
+struct FeTmap { const float2 *base; long long nrows; long long stream_stride; };
+__device__ inline void tma_load_rows(void *dst, const FeTmap *tm, int row0, int stream, int rows, unsigned long long *, int = -1)
+{
+    const float2 *src = tm->base + (long long)stream * tm->stream_stride + (long long)row0 * 16;
+    float2 *d = reinterpret_cast<float2 *>(dst);
+    for (int r = 0; r < rows; r++)
+        for (int c = 0; c < 8; c++)
+            for (int k = 0; k < 2; k++) d[(r * 8 + (c ^ (r & 7))) * 2 + k] = src[r * 16 + c * 2 + k];
+}
+#else
+struct alignas(64) FeTmap { unsigned long long opaque[16]; };
+// announce: rows to announce on the barrier with this copy (-1: this box; 0: announced already by an earlier box)
+__device__ __forceinline__ void tma_load_rows(void *dst, const FeTmap *tm, int row0, int stream, int rows, unsigned long long *bar,
+                                              int announce = -1)
+{
+    (void)rows;
+    if (announce != 0) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+                     "r"((unsigned)(announce < 0 ? rows : announce) * 128u) : "memory");
+    }
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 ::"r"(smem_u32(dst)), "l"(reinterpret_cast<unsigned long long>(tm)), "r"(smem_u32(bar)), "r"(0), "r"(row0), "r"(stream)
+                 : "memory");
+}
+#endif
+
 constexpr int kMaxStages = 12;   // half-band stages (2^12 decimation) supported by the fused front end
 constexpr int kMaxHbM    = 16;   // max half-band semi-length m (2m taps)
 constexpr int kHsub      = 14;   // taps per polyphase branch of the arbitrary resampler (2*7, msresamp.c)
 constexpr int kFePlanePad = 1;   // elements between the even and the odd plane of a level buffer: a thread pair that writes
                                  // (even, odd) samples of the same pair index then hits two different banks
-#ifndef CSDR_FE_TOPR
-#define CSDR_FE_TOPR 7
-#endif
-constexpr int kFeTopR  = CSDR_FE_TOPR;      // outputs per thread slot of a first stage that reads the linear raw tile (k_frontend_direct)
+constexpr int kFeTopR  = 8;           // outputs per thread slot of the first stage of k_frontend_direct = pairs per 128-byte row of the raw tile
+constexpr int kFeRawRow = 16;    // samples per row of the swizzled raw tile
 constexpr int kHcPad     = 16;   // c-rate history carried into every tile (>= kHsub-1, multiple of 8)
 
 __host__ __device__ inline float2 cf(float re, float im) { float2 z; z.x = re; z.y = im; return z; }

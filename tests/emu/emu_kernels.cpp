@@ -62,6 +62,7 @@ long long emu_frontend(float rate, float As, int mix_mode, float freq, int quant
     }
     FrontendGeometry g = plan_frontend(ms, Tc, allow_std != 0, allow_std >= 2 ? allow_std - 1 : 0);
     void (*kernel)(FrontendParams) = k_frontend;
+    void (*kernel_direct)(FrontendParams, FeTmap) = nullptr;
     if (g.std_kernel) {
         nthreads = kFeNT;
         if (g.variant == 0) {
@@ -75,12 +76,12 @@ long long emu_frontend(float rate, float As, int mix_mode, float freq, int quant
             }
         } else {
             switch (ms.S) {
-            case 1: kernel = k_frontend_direct<1>; break;
-            case 2: kernel = k_frontend_direct<2>; break;
-            case 3: kernel = k_frontend_direct<3>; break;
-            case 4: kernel = k_frontend_direct<4>; break;
-            case 5: kernel = k_frontend_direct<5>; break;
-            default: kernel = k_frontend_direct<6>; break;
+            case 1: kernel_direct = k_frontend_direct<1>; break;
+            case 2: kernel_direct = k_frontend_direct<2>; break;
+            case 3: kernel_direct = k_frontend_direct<3>; break;
+            case 4: kernel_direct = k_frontend_direct<4>; break;
+            case 5: kernel_direct = k_frontend_direct<5>; break;
+            default: kernel_direct = k_frontend_direct<6>; break;
             }
         }
     }
@@ -105,7 +106,19 @@ long long emu_frontend(float rate, float As, int mix_mode, float freq, int quant
         p.x_stride = 0; p.y_stride = 0;
         p.mix_mode = mix_mode; p.theta0 = 0; p.dtheta = design::nco_constrain(freq); p.quantize = quantize;
         p.bank = ms.bank.data();
-        if (p.ntiles > 0)
+        if (p.ntiles > 0 && kernel_direct) {
+            // what Frontend::make_tensor_map does: rows of 16 samples from sample r on, 16-byte aligned base
+            FeTmap tm{};
+            const FeGeom &G = g.geom;
+            const long long lo0 = (p.K0 - kHcPad) * (1LL << G.S) + G.d[G.S];
+            const long long r = (((lo0 - p.n0) % kFeRawRow) + kFeRawRow) % kFeRawRow;
+            p.tma_ok = 0; p.tma_r = 0; p.tma_rows = 0;
+            if (nx >= kFeRawRow && (nx - r) / kFeRawRow >= 1 && ((uintptr_t)(p.x + r) & 15) == 0) {
+                tm.base = p.x + r; tm.nrows = (nx - r) / kFeRawRow; tm.stream_stride = 0;
+                p.tma_ok = 1; p.tma_r = (int)r; p.tma_rows = tm.nrows;
+            }
+            csdr_emu::launch(dim3(std::min(p.ntiles, 3)), dim3(nthreads), g.smem_bytes, kernel_direct, p, tm);
+        } else if (p.ntiles > 0)
             csdr_emu::launch(dim3(std::min(p.ntiles, 3)), dim3(nthreads), g.smem_bytes, kernel, p);
         csdr_emu::launch(dim3((g.hcap + 127) / 128), dim3(128), 0, k_hist_update, (const float2 *)hist[cur_h].data(),
                          hist[cur_h ^ 1].data(), x + pos, 0LL, nx, g.hcap);
