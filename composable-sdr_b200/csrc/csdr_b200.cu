@@ -221,6 +221,15 @@ struct Frontend {
             case 6: kernel = k_frontend_std<6>; break;
             default: throw CudaError{"frontend: no specialised kernel for this stage count"};
             }
+        } else if (geo.std_kernel && geo.variant == 2) {
+            switch (ms.S) {
+            case 2: kernel_direct = k_frontend_ws<2>; break;
+            case 3: kernel_direct = k_frontend_ws<3>; break;
+            case 4: kernel_direct = k_frontend_ws<4>; break;
+            case 5: kernel_direct = k_frontend_ws<5>; break;
+            case 6: kernel_direct = k_frontend_ws<6>; break;
+            default: throw CudaError{"frontend: no warp-specialised kernel for this stage count"};
+            }
         } else if (geo.std_kernel) {
             switch (ms.S) {
             case 1: kernel_direct = k_frontend_direct<1>; break;

@@ -22,6 +22,7 @@ struct FeGeom {
     int m[kMaxStages] = {}, R[kMaxStages] = {};
     int d[kMaxStages + 1] = {}, n[kMaxStages + 1] = {}, stride[kMaxStages + 1] = {}, off[kMaxStages + 1] = {};
     int total_f2 = 0;     // float2 elements of all level buffers
+    int off_alt = 0;      // raw = 2: second copy of level S-1 (producer / consumer double buffer)
     int hcap = 0;         // raw-sample history the first tile of a chunk may reach back over
 };
 
@@ -43,7 +44,10 @@ __host__ __device__ constexpr FeGeom fe_make_geom(int S, int Tc, const int *m, i
     // raw = 1: the top level is the raw tile itself as the TMA tensor copy delivers it: whole rows of 16 samples
     // (128 bytes), 128-byte swizzle, at the start of shared memory (1024-byte aligned).  The first half-band stage
     // reads (even, odd) pairs from it with 16-byte loads, 8 outputs per thread slot = one row per slot.
-    const int direct = (raw == 1 && S > 0) ? 1 : 0;
+    // raw = 2 (k_frontend_ws): the same, and level S-1 -- the hand-over between the two warp groups -- is double-buffered
+    // in a region of its own
+    const int direct = ((raw == 1 || raw == 2) && S > 0) ? 1 : 0;
+    const int ws = (raw == 2 && S > 1) ? 1 : 0;
     g.n[0] = Tc + kHcPad; g.d[0] = 0;
     for (int L = 0; L < S; L++) {
         const int sh = (L + 1 == S) ? g.shift : 0;
@@ -57,7 +61,7 @@ __host__ __device__ constexpr FeGeom fe_make_geom(int S, int Tc, const int *m, i
     // the staging buffer is private (the next tile is copied into it while the lower stages of the current tile run);
     // the de-interleaved levels ping-pong between two regions
     const int priv = direct;
-    int sizeA = 0, sizeB = 0, sizeT = 0;
+    int sizeA = 0, sizeB = 0, sizeT = 0, sizeP = 0;
     for (int L = 1; L <= S; L++) {
         if (direct && L == S) {
             sizeT = ce_roundup(g.n[S], 128);                        // whole 1024-byte swizzle atoms
@@ -69,13 +73,15 @@ __host__ __device__ constexpr FeGeom fe_make_geom(int S, int Tc, const int *m, i
         g.stride[L] = st;
         const int sz = ce_roundup(2 * D * st + kFePlanePad, 2);
         if (priv && L == S) sizeT = sz;
+        else if (ws && L == S - 1) sizeP = sz;
         else if (((S - L) & 1) == 0) sizeA = ce_max(sizeA, sz); else sizeB = ce_max(sizeB, sz);
     }
     const int size0 = ce_roundup(g.n[0] + 2, 2);
     g.off[0] = priv ? sizeT : 0;                                   // the swizzled tile comes first (alignment)
-    for (int L = 1; L <= S; L++) g.off[L] = size0 + sizeT + ((((S - L) & 1) == 0) ? 0 : sizeA);
+    for (int L = 1; L <= S; L++) g.off[L] = size0 + sizeT + 2 * sizeP + ((((S - L) & 1) == 0) ? 0 : sizeA);
     if (priv) g.off[S] = 0;
-    g.total_f2 = size0 + sizeT + sizeA + sizeB;
+    if (ws) { g.off[S - 1] = size0 + sizeT; g.off_alt = size0 + sizeT + sizeP; }
+    g.total_f2 = size0 + sizeT + 2 * sizeP + sizeA + sizeB;
     g.hcap = ce_roundup(((1 << S) - 1) + (kHcPad << S) - g.d[S] + 1, 64);
     return g;
 }
@@ -92,10 +98,16 @@ __host__ __device__ constexpr int fe_std_tc_direct(int S)
 {
     return S == 1 ? 1536 : S == 2 ? 768 : S == 3 ? 384 : S == 4 ? 192 : S == 5 ? 64 : 32;
 }
+// variant 2 (k_frontend_ws): smaller tiles so that three CTAs with the double-buffered hand-over level fit an SM
+__host__ __device__ constexpr int fe_std_tc_ws(int S)
+{
+    return S == 2 ? 640 : S == 3 ? 320 : S == 4 ? 160 : S == 5 ? 64 : 32;
+}
 __host__ __device__ constexpr FeGeom fe_make_geom_std(int S, int variant = 0)
 {
     FeStdM mm{};
-    return variant ? fe_make_geom(S, fe_std_tc_direct(S), mm.v, 1, 1) : fe_make_geom(S, fe_std_tc(S), mm.v, 1, 0);
+    return variant == 2 ? fe_make_geom(S, fe_std_tc_ws(S), mm.v, 1, 2)
+         : variant ? fe_make_geom(S, fe_std_tc_direct(S), mm.v, 1, 1) : fe_make_geom(S, fe_std_tc(S), mm.v, 1, 0);
 }
 constexpr int kFeStdMaxS = 6;      // both kernels are instantiated for S = 1..6
 

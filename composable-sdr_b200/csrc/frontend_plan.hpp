@@ -12,7 +12,8 @@ struct FrontendGeometry {
     FrontendParams base;     // geometry + taps filled in; per-call fields zero
     FeGeom geom;
     bool std_kernel = false; // k_frontend_std<S, V> applies (compile-time geometry)
-    int variant = 0;         // 0: k_frontend_std (register prefetch + loader pass), 1: k_frontend_direct (TMA staging read in place)
+    int variant = 0;         // 0: k_frontend_std (register prefetch + loader pass), 1: k_frontend_direct (TMA tile read in place),
+                             // 2: k_frontend_ws (the same, warp-specialised: two groups of warps on different tiles)
     int hcap = 0;            // raw-sample history the kernel may reach back over
     size_t smem_bytes = 0;
     std::string error;
@@ -39,7 +40,7 @@ inline FrontendGeometry plan_frontend(const design::MsresampPlan &ms, int Tc, bo
         if (m[s] != stdm.v[s]) is_std = false;
     }
     g.std_kernel = is_std;
-    g.variant = (is_std && variant != 0) ? 1 : 0;
+    g.variant = (is_std && variant == 2 && S >= 2) ? 2 : (is_std && variant != 0) ? 1 : 0;
     g.geom = is_std ? fe_make_geom_std(S, g.variant) : fe_make_geom(S, Tc, m, 0, 0);
     const FeGeom &G = g.geom;
     p.S = S; p.Tc = G.Tc;

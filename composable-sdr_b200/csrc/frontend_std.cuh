@@ -59,7 +59,7 @@ __device__ __forceinline__ bool fe_tile_is_bulk(const FrontendParams &p, const f
 {
     constexpr int NS = FeStd<S, V>::G.n[S];
     const long long rel0 = lo - p.n0;
-    if (V == 1) {
+    if (V >= 1) {
         // the tensor map covers whole 16-sample rows of x from sample tma_r on; tiles start on row boundaries
         const long long rr = rel0 - p.tma_r;
         return p.tma_ok && rr >= 0 && (rr & (kFeRawRow - 1)) == 0 && (rr / kFeRawRow) + NS / kFeRawRow <= p.tma_rows;
@@ -136,14 +136,14 @@ __device__ __forceinline__ void fe_load_top(const FrontendParams &p, const float
 // ---- one half-band stage with compile-time geometry --------------------------------------------------------
 //   out[q] = C[q+M] + sum_{u<2M} g[u] * T[q+u+SH]     T/C = tap/centre planes (odd/even samples; swapped when the
 //   input level is shifted by one sample), R consecutive outputs per thread slot
-template <int M, int R, int STR, int SH, int NOUT, bool LAST, int D2, int STR2>
+template <int M, int R, int STR, int SH, int NOUT, bool LAST, int D2, int STR2, int NTG = kFeNT>
 __device__ __forceinline__ void fe_stage_c(const float2 *__restrict__ in, float2 *__restrict__ out,
-                                           const float *__restrict__ g, float zeta)
+                                           const float *__restrict__ g, float zeta, int tid = threadIdx.x)
 {
     const float2 *T = in + (SH ? 0 : R * STR + kFePlanePad);
     const float2 *C = in + (SH ? R * STR + kFePlanePad : 0);
     constexpr int NSLOTS = NOUT / R;
-    for (int t = threadIdx.x; t < NSLOTS; t += kFeNT) {
+    for (int t = tid; t < NSLOTS; t += NTG) {
         float2 acc[R];
 #pragma unroll
         for (int r = 0; r < R; r++) acc[r] = C[((M + r) % R) * STR + t + (M + r) / R];
@@ -232,16 +232,17 @@ __device__ __forceinline__ void fe_tile_info(const FrontendParams &p, const floa
 // loads and stay in registers.  Output oA + j has timing phase phA + j*step relative to the tile, belongs to local
 // push (phase >> 24) and uses branch = the next `bits` phase bits.  The first j of a thread is estimated in fp32 and
 // corrected exactly in integers (no division).  Taps come from the padded copy of the bank in shared memory.
-template <int TC>
+template <int TC, int NTG = kFeNT>
 __device__ __forceinline__ void fe_resample_tile(const FrontendParams &p, const float2 *__restrict__ cb, float2 *__restrict__ ys,
-                                                 const FeTileInfo &ti, int npush, const float *__restrict__ bank_s, float rate_f)
+                                                 const FeTileInfo &ti, int npush, const float *__restrict__ bank_s, float rate_f,
+                                                 int tid = threadIdx.x)
 {
     const unsigned mask = (1u << p.bits) - 1u;
     const int sh = 24 - p.bits;
     const unsigned phA = ti.phA;
     const float fA = ti.fA;
     float2 *yo = ys + ti.oA;
-    for (int t = threadIdx.x; t < TC / 2; t += kFeNT) {
+    for (int t = tid; t < TC / 2; t += NTG) {
         if (2 * t >= npush) break;
         float2 w[16];                               // local indices 2t+2 .. 2t+17; push e ends at w[14 + e]
         const float4 *src = reinterpret_cast<const float4 *>(cb + 2 * t + 2);
@@ -345,14 +346,14 @@ __global__ void __launch_bounds__(kFeNT, 2) k_frontend_std(const CSDR_GRID_CONST
 // 16-byte chunk index of pair P in the swizzled tile
 __device__ __forceinline__ int fe_swz(int P) { return (P & ~7) | ((P ^ (P >> 3)) & 7); }
 
-template <int M, int NOUT, bool LAST, int D2, int STR2, int MIX>
+template <int M, int NOUT, bool LAST, int D2, int STR2, int MIX, int NTG = kFeNT>
 __device__ __forceinline__ void fe_stage_top(const float2 *__restrict__ raw, float2 *__restrict__ out,
-                                             const float *__restrict__ g, float zeta, unsigned thb, unsigned dth)
+                                             const float *__restrict__ g, float zeta, unsigned thb, unsigned dth, int tid = threadIdx.x)
 {
     constexpr int R = kFeTopR, NSLOTS = NOUT / R, NC = R + 2 * M - 1;
     static_assert(R == 8 && NOUT % R == 0 && kFeRawRow == 2 * R, "one slot per 128-byte row");
     const float4 *src = reinterpret_cast<const float4 *>(raw);
-    for (int t = threadIdx.x; t < NSLOTS; t += kFeNT) {
+    for (int t = tid; t < NSLOTS; t += NTG) {
         // output q = R t + r:  centre = odd sample of pair q + M, tap u = even sample of pair q + u + 1.
         // Pair 8 t + k sits in row t + (k >> 3), chunk (k & 7) ^ ((t + (k >> 3)) & 7).
         const unsigned ths = thb + (unsigned)(2 * (R * t + 1)) * dth;
@@ -407,13 +408,14 @@ __device__ __forceinline__ void fe_run_top(const FrontendParams &p, float2 *smem
 }
 // staging[i] = raw sample lo + i for a tile the bulk copy cannot fetch (it reaches into the carried history, past
 // the end of the chunk, or the chunk is not 16-byte aligned there)
-template <int S>
+template <int S, int NTG = kFeNT, int V = 1>
 __device__ __forceinline__ void fe_fill_staging(const FrontendParams &p, const float2 *__restrict__ xs,
-                                                const float2 *__restrict__ hs, float2 *__restrict__ raw, long long lo)
+                                                const float2 *__restrict__ hs, float2 *__restrict__ raw, long long lo,
+                                                int tid = threadIdx.x)
 {
-    constexpr int NS = FeStd<S, 1>::G.n[S];
+    constexpr int NS = FeStd<S, V>::G.n[S];
     const long long rel0 = lo - p.n0;
-    for (int i = threadIdx.x; i < NS; i += kFeNT) {
+    for (int i = tid; i < NS; i += NTG) {
         const long long rel = rel0 + i;
         float2 v = cf(0.f, 0.f);
         if (rel >= 0) { if (rel < p.nx) v = xs[rel]; }
@@ -423,11 +425,11 @@ __device__ __forceinline__ void fe_fill_staging(const FrontendParams &p, const f
 }
 
 // one tensor copy per tile (two when the tile has more than 256 rows), issued by one thread
-template <int S>
+template <int S, int V = 1>
 __device__ __forceinline__ void fe_copy_staging(const FrontendParams &p, const FeTmap *tm, float2 *raw, long long lo,
                                                 unsigned long long *bar)
 {
-    constexpr int ROWS = FeStd<S, 1>::G.n[S] / kFeRawRow, NB = (ROWS + 255) / 256, BOX = ROWS / NB;
+    constexpr int ROWS = FeStd<S, V>::G.n[S] / kFeRawRow, NB = (ROWS + 255) / 256, BOX = ROWS / NB;
     static_assert(BOX * NB == ROWS && BOX <= 256, "tile = NB boxes of BOX rows");
     const int row0 = (int)((lo - p.n0 - p.tma_r) / kFeRawRow);
     if (NB == 1) tma_load_rows(raw, tm, row0, (int)blockIdx.y, ROWS, bar);
@@ -520,6 +522,126 @@ __global__ void __launch_bounds__(kFeNT, 3) k_frontend_direct(const CSDR_GRID_CO
         }
         __syncthreads();   // lower levels may be overwritten; a synchronously filled staging buffer is complete
         cur = nxt;
+    }
+}
+
+// =============================================================================================================
+// k_frontend_ws: k_frontend_direct with the CTA split into two groups of four warps that work on DIFFERENT tiles.
+// Group A (producer) runs the first half-band stage of tile i+1 -- the NCO mix, bound by instruction issue -- while
+// group B (consumer) runs the lower stages and the resampler of tile i -- bound by shared memory and short of slots
+// for 256 threads.  The two halves are about the same amount of work, every stage fills at least 75 % of its group,
+// and the hand-over level (S-1) is double-buffered; named barriers (bar.sync / bar.arrive) replace the CTA-wide ones.
+enum { kBarA = 1, kBarB = 2, kBarFull0 = 3, kBarEmpty0 = 5 };       // FULL: 3, 4; EMPTY: 5, 6
+constexpr int kFeWsGroup = 128;
+
+template <int S, int MIX>
+__device__ __forceinline__ void fe_ws_top(const FrontendParams &p, float2 *smem, float2 *dst, unsigned thb, int tid)
+{
+    constexpr FeGeom G = FeStd<S, 2>::G;
+    constexpr int D2 = G.R[S - 2];
+    fe_stage_top<G.m[S - 1], G.n[S - 1], false, D2, G.stride[S - 1], MIX, kFeWsGroup>(smem + G.off[S], dst, p.taps[S - 1], p.zeta,
+                                                                                      thb, p.dtheta, tid);
+}
+template <int S, int s>
+__device__ __forceinline__ void fe_ws_lower(const FrontendParams &p, float2 *smem, const float2 *src, int tid, int full_id)
+{
+    constexpr FeGeom G = FeStd<S, 2>::G;
+    constexpr bool LAST = (s == 0);
+    constexpr int D2 = LAST ? 1 : G.R[LAST ? 0 : s - 1];
+    fe_stage_c<G.m[s], G.R[s], G.stride[s + 1], 0, G.n[s], LAST, D2, G.stride[s], kFeWsGroup>(
+        (s == S - 2) ? src : smem + G.off[s + 1], smem + G.off[s], p.taps[s], p.zeta, tid);
+    named_bar_sync(kBarB, kFeWsGroup);
+    // the hand-over buffer has been consumed by the first lower stage: give it back to the producers
+    if (s == S - 2) named_bar_arrive(kBarEmpty0 + (full_id - kBarFull0), 2 * kFeWsGroup);
+    if constexpr (s > 0) fe_ws_lower<S, s - 1>(p, smem, src, tid, full_id);
+}
+
+template <int S>
+__global__ void __launch_bounds__(2 * kFeWsGroup, 3) k_frontend_ws(const CSDR_GRID_CONSTANT FrontendParams p, const CSDR_GRID_CONSTANT FeTmap tmap)
+{
+    constexpr FeGeom G = FeStd<S, 2>::G;
+    static_assert(S >= 2, "the consumer group needs at least one stage of its own");
+    CSDR_DYN_SMEM_1K(smem_ws1k);
+    unsigned char *smem_raw = smem_ws1k;
+    float2 *smem = reinterpret_cast<float2 *>(smem_raw);
+    float *bank_s = reinterpret_cast<float *>(smem_raw) + 2 * G.total_f2;
+    float2 *raw = smem + G.off[S];
+    __shared__ FeTileInfo s_infoA[3], s_infoB[3];
+    __shared__ __align__(8) unsigned long long s_bar;
+
+    const int npfb = 1 << p.bits;
+    for (int i = threadIdx.x; i < npfb * kHsub; i += 2 * kFeWsGroup) {
+        const int row = i / kHsub, col = i - row * kHsub;
+        bank_s[row * (kHsub + 1) + col] = p.bank[i];
+    }
+    const float2 *xs = p.x + (long long)blockIdx.y * p.x_stride;
+    const float2 *hs = p.hist + (long long)blockIdx.y * p.hcap;
+    float2 *ys = p.y + (long long)blockIdx.y * p.y_stride;
+    const double inv_st = 1.0 / (double)p.step;
+    const float rate_f = 16777216.0f / (float)p.step;
+    const int gstep = (int)gridDim.x, t0 = (int)blockIdx.x;
+    const bool groupA = threadIdx.x < kFeWsGroup;
+    const int tid = groupA ? threadIdx.x : threadIdx.x - kFeWsGroup;
+    if (threadIdx.x == 0) bulk_init(&s_bar);
+    __syncthreads();                                              // bank and barrier ready; from here on the groups part
+
+    if (groupA) {
+        // ---------------- producers: TMA tile -> first stage (mix) -> hand-over buffer
+        unsigned parity = 0;
+        if (tid == 0) {
+            if (t0 < p.ntiles) fe_tile_info<S, 2>(p, xs, t0, inv_st, s_infoA[0]);
+            if (t0 + gstep < p.ntiles) fe_tile_info<S, 2>(p, xs, t0 + gstep, inv_st, s_infoA[1]);
+        }
+        named_bar_sync(kBarA, kFeWsGroup);
+        if (t0 < p.ntiles) {
+            if (s_infoA[0].bulk) { if (tid == 0) fe_copy_staging<S, 2>(p, &tmap, raw, s_infoA[0].lo, &s_bar); }
+            else fe_fill_staging<S, kFeWsGroup, 2>(p, xs, hs, raw, s_infoA[0].lo, tid);
+        }
+        named_bar_sync(kBarA, kFeWsGroup);
+        int cur = 0, it = 0;
+        for (int tile = t0; tile < p.ntiles; tile += gstep, it++) {
+            const int nxt = cur == 2 ? 0 : cur + 1, nxt2 = nxt == 2 ? 0 : nxt + 1, b = it & 1;
+            if (s_infoA[cur].bulk) { bulk_wait(&s_bar, parity); parity ^= 1u; }
+            if (it >= 2) named_bar_sync(kBarEmpty0 + b, 2 * kFeWsGroup);      // consumers are done with this buffer
+            float2 *dst = smem + (b ? G.off_alt : G.off[S - 1]);
+            const unsigned thb = p.theta0 + (unsigned)s_infoA[cur].lo * p.dtheta + (p.quantize ? (1u << 21) : 0u) + kFePhaseBias;
+            if (p.mix_mode == 0)      fe_ws_top<S, 0>(p, smem, dst, thb, tid);
+            else if (p.quantize) { if (p.mix_mode == 1) fe_ws_top<S, 1 | 8>(p, smem, dst, thb, tid);
+                                   else                 fe_ws_top<S, 2 | 8>(p, smem, dst, thb, tid); }
+            else                 { if (p.mix_mode == 1) fe_ws_top<S, 1>(p, smem, dst, thb, tid);
+                                   else                 fe_ws_top<S, 2>(p, smem, dst, thb, tid); }
+            named_bar_sync(kBarA, kFeWsGroup);                     // staging consumed, hand-over buffer complete
+            named_bar_arrive(kBarFull0 + b, 2 * kFeWsGroup);
+            if (tile + gstep < p.ntiles) {
+                if (s_infoA[nxt].bulk) { if (tid == 0) fe_copy_staging<S, 2>(p, &tmap, raw, s_infoA[nxt].lo, &s_bar); }
+                else fe_fill_staging<S, kFeWsGroup, 2>(p, xs, hs, raw, s_infoA[nxt].lo, tid);
+            }
+            if (tid == kFeWsGroup - 32 && tile + 2 * gstep < p.ntiles) fe_tile_info<S, 2>(p, xs, tile + 2 * gstep, inv_st, s_infoA[nxt2]);
+            named_bar_sync(kBarA, kFeWsGroup);                     // a synchronously filled tile / the new info are visible
+            cur = nxt;
+        }
+        // match the consumers' last arrivals so that every barrier phase is complete when the CTA exits
+        for (int k = (it >= 2 ? it - 2 : 0); k < it; k++) named_bar_sync(kBarEmpty0 + (k & 1), 2 * kFeWsGroup);
+    } else {
+        // ---------------- consumers: lower stages + resampler of the tile the producers finished last
+        if (tid == 0) {
+            if (t0 < p.ntiles) fe_tile_info<S, 2>(p, xs, t0, inv_st, s_infoB[0]);
+            if (t0 + gstep < p.ntiles) fe_tile_info<S, 2>(p, xs, t0 + gstep, inv_st, s_infoB[1]);
+        }
+        named_bar_sync(kBarB, kFeWsGroup);
+        int cur = 0, it = 0;
+        for (int tile = t0; tile < p.ntiles; tile += gstep, it++) {
+            const int nxt = cur == 2 ? 0 : cur + 1, nxt2 = nxt == 2 ? 0 : nxt + 1, b = it & 1;
+            named_bar_sync(kBarFull0 + b, 2 * kFeWsGroup);
+            if (tid == kFeWsGroup - 32 && tile + 2 * gstep < p.ntiles) fe_tile_info<S, 2>(p, xs, tile + 2 * gstep, inv_st, s_infoB[nxt2]);
+            fe_ws_lower<S, S - 2>(p, smem, smem + (b ? G.off_alt : G.off[S - 1]), tid, kBarFull0 + b);
+            {
+                const int npush = (int)min((long long)G.Tc, p.K1 - p.K0 - (long long)tile * G.Tc);
+                fe_resample_tile<G.Tc, kFeWsGroup>(p, smem + G.off[0], ys, s_infoB[cur], npush, bank_s, rate_f, tid);
+            }
+            named_bar_sync(kBarB, kFeWsGroup);                     // lower levels may be overwritten; new info visible
+            cur = nxt;
+        }
     }
 }
 

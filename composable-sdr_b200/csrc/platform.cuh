@@ -85,6 +85,16 @@ __device__ __forceinline__ void tma_load_rows(void *dst, const FeTmap *tm, int r
 }
 #endif
 
+// ---- named barriers (bar.sync / bar.arrive id, count): producer / consumer hand-over between two groups of warps ---
+// sync: wait until `count` threads have arrived (this one included); arrive: count this thread and go on.
+#ifdef CSDR_EMU
+__device__ inline void named_bar_sync(int id, int count) { ::csdr_emu::named_barrier(id, count, true); }
+__device__ inline void named_bar_arrive(int id, int count) { ::csdr_emu::named_barrier(id, count, false); }
+#else
+__device__ __forceinline__ void named_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void named_bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+#endif
+
 constexpr int kMaxStages = 12;   // half-band stages (2^12 decimation) supported by the fused front end
 constexpr int kMaxHbM    = 16;   // max half-band semi-length m (2m taps)
 constexpr int kHsub      = 14;   // taps per polyphase branch of the arbitrary resampler (2*7, msresamp.c)

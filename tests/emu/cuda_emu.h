@@ -7,6 +7,8 @@
 // includes or loads it, libcsdr_b200.so is built by nvcc only and fails loudly without a CUDA device.
 #pragma once
 #include <pthread.h>
+#include <mutex>
+#include <condition_variable>
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
@@ -46,6 +48,18 @@ inline unsigned char *g_dyn_smem = nullptr;
 inline unsigned char *dyn_smem() { return g_dyn_smem; }
 inline unsigned long long g_launches = 0;
 
+// named barriers (bar.sync / bar.arrive id, count)
+struct NamedBarrier { std::mutex m; std::condition_variable cv; int count = 0; unsigned gen = 0; };
+inline NamedBarrier g_named[16];
+inline void named_barrier(int id, int expected, bool wait)
+{
+    NamedBarrier &b = g_named[id & 15];
+    std::unique_lock<std::mutex> lk(b.m);
+    const unsigned g = b.gen;
+    if (++b.count == expected) { b.count = 0; b.gen++; b.cv.notify_all(); return; }
+    if (wait) b.cv.wait(lk, [&] { return b.gen != g; });
+}
+
 template <class K, class... Args>
 void launch(dim3 grid, dim3 block, size_t smem_bytes, K kernel, Args... args)
 {
@@ -58,6 +72,7 @@ void launch(dim3 grid, dim3 block, size_t smem_bytes, K kernel, Args... args)
     for (unsigned bz = 0; bz < grid.z; bz++)
     for (unsigned by = 0; by < grid.y; by++)
     for (unsigned bx = 0; bx < grid.x; bx++) {
+        for (auto &nb : g_named) { nb.count = 0; }
         pthread_barrier_init(&g_barrier, nullptr, nthreads);
         const unsigned nwarps = (nthreads + 31) / 32;
         if (nwarps > (unsigned)kMaxWarps) abort();

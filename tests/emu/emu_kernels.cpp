@@ -74,6 +74,14 @@ long long emu_frontend(float rate, float As, int mix_mode, float freq, int quant
             case 5: kernel = k_frontend_std<5>; break;
             default: kernel = k_frontend_std<6>; break;
             }
+        } else if (g.variant == 2) {
+            switch (ms.S) {
+            case 2: kernel_direct = k_frontend_ws<2>; break;
+            case 3: kernel_direct = k_frontend_ws<3>; break;
+            case 4: kernel_direct = k_frontend_ws<4>; break;
+            case 5: kernel_direct = k_frontend_ws<5>; break;
+            default: kernel_direct = k_frontend_ws<6>; break;
+            }
         } else {
             switch (ms.S) {
             case 1: kernel_direct = k_frontend_direct<1>; break;

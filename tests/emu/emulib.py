@@ -47,7 +47,7 @@ class Emu:
         cap = int(2 * np.ceil(rate * x.size)) + 64
         y = np.zeros(cap, np.complex64)
         n = self.L.emu_frontend(rate, As, mix_mode, freq, quantize, Tc, nthreads, x.ctypes.data, x.size, ch.ctypes.data,
-                                len(chunks), y.ctypes.data, cap, seek, int(std), misalign)      # std: 0 generic kernel, 1 k_frontend_std (register prefetch), 2 k_frontend_direct
+                                len(chunks), y.ctypes.data, cap, seek, int(std), misalign)      # std: 0 generic kernel, 1 k_frontend_std (register prefetch), 2 k_frontend_direct, 3 k_frontend_ws
         assert n >= 0, "emu_frontend failed"
         return y[:n]
 

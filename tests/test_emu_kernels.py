@@ -15,7 +15,10 @@ from util import assert_parity, make_signal
     (0.04, 60.0, 0, 256, 0, True), (0.02, 60.0, 0, 256, 1, True), (0.011, 60.0, 0, 256, 1, True),
     # k_frontend_direct<S>, S = 1..6
     (0.3, 60.0, 0, 256, 1, 2), (0.2, 60.0, 0, 256, 2, 2), (0.078125, 60.0, 0, 256, 1, 2), (0.078125, 60.0, 0, 256, 0, 2),
-    (0.04, 60.0, 0, 256, 2, 2), (0.02, 60.0, 0, 256, 1, 2), (0.011, 60.0, 0, 256, 1, 2)])
+    (0.04, 60.0, 0, 256, 2, 2), (0.02, 60.0, 0, 256, 1, 2), (0.011, 60.0, 0, 256, 1, 2),
+    # k_frontend_ws<S> (warp-specialised), S = 2..6
+    (0.2, 60.0, 0, 256, 2, 3), (0.078125, 60.0, 0, 256, 1, 3), (0.078125, 60.0, 0, 256, 0, 3), (0.04, 60.0, 0, 256, 2, 3),
+    (0.02, 60.0, 0, 256, 1, 3), (0.011, 60.0, 0, 256, 1, 3)])
 def test_frontend_matches_oracle(orc, emu, rate, As, Tc, nthreads, mix, std):
     x = make_signal(40000, 7)
     f = float(np.float32(0.24543693))
@@ -46,7 +49,7 @@ def test_frontend_chunk_invariance_is_bit_exact(emu):
     x = make_signal(20000, 8)
     sizes = [1, 7, 1000, 3, 4096, 5000]
     sizes.append(len(x) - sum(sizes))
-    for std in (0, 1, 2):
+    for std in (0, 1, 2, 3):
         a = emu.frontend(x, 0.078125, freq=0.3, std=std)
         b = emu.frontend(x, 0.078125, freq=0.3, chunks=sizes, std=std)
         assert np.array_equal(a, b)

@@ -56,6 +56,21 @@ def test_msresamp_register_prefetch_kernel(cs, orc, rate):
         cs.set_option(9, 1)
 
 
+@pytest.mark.parametrize("rate", [0.3, 0.15, 0.078125, 0.04, 0.02, 0.011])
+def test_msresamp_warp_specialised_kernel(cs, orc, rate):
+    """CSDR_OPT_FRONTEND_VARIANT = 2: k_frontend_ws (producer / consumer warp groups on different tiles)"""
+    cs.set_option(9, 2)
+    try:
+        x = make_signal(300000, 29)
+        ref = orc.MsResamp(rate).execute(x)
+        a = np.concatenate(run_pipe(cs, cs.resampler(rate, 60.0), x, [len(x)]))
+        b = np.concatenate(run_pipe(cs, cs.resampler(rate, 60.0), x, [1024 * 9, 77]))
+        assert np.array_equal(a, b)
+        assert_parity(a, ref, what=f"msresamp (k_frontend_ws) {rate}")
+    finally:
+        cs.set_option(9, 1)
+
+
 @pytest.mark.parametrize("rate", [1.25, 2.0, 3.7, 10.0])
 def test_msresamp_interpolation(cs, orc, rate):
     """rate > 1 (MSRESAMP(_interp_execute)): arbitrary stage, then half-band interpolators"""
