@@ -23,6 +23,7 @@
 // the threshold bits); only the speed depends on the signal.
 #pragma once
 #include "platform.cuh"
+#include "frontend.cuh"     // fe_phasor (optional rotation in k_be_prep)
 #include <algorithm>
 
 namespace csdr {
@@ -81,6 +82,7 @@ struct DcParams {
     float2 *out; long long out_lane_stride;    // dc-blocked samples (nullptr: not wanted)
     float *pw; long long pw_stride;            // |y|^2 (nullptr: not wanted)
     int n, nlanes, G, ngrp, nblk, has_dc;
+    int rot; unsigned rot_theta, rot_dtheta; int rot_quantize;   // rot = 1: multiply the output by conj(NCO phasor) (channelizer pre-rotation)
     double c;                                  // 1 - alpha  (= -a1)
     double cS[5];                              // c^(S d), S = G/32 samples per lane, d = 1, 2, 4, 8, 16
     float a1;
@@ -253,6 +255,14 @@ __global__ void __launch_bounds__(256) k_be_prep(const DcParams p)
                 const float v0i = __fsub_rn(v[q].y, __fmul_rn(p.a1, v1i));
                 v[q] = cf(__fsub_rn(v0r, v1r), __fsub_rn(v0i, v1i));
                 v1r = v0r; v1i = v0i;
+            }
+        }
+        if (p.rot) {
+            // the channelizer's pre-rotation (nco_crcf_mix_block_down, Liquid.chs:847) rides on this pass
+#pragma unroll
+            for (int q = 0; q < S; q++) {
+                const float2 w = fe_phasor(p.rot_theta + (unsigned)(i0 + q) * p.rot_dtheta, p.rot_quantize);
+                v[q] = cf(v[q].x * w.x + v[q].y * w.y, v[q].y * w.x - v[q].x * w.y);
             }
         }
         if (yo) {

@@ -91,7 +91,7 @@ void chain_init(csdr_chain_s *q)
         q->be.has_agc = q->has_agc; q->be.agc_thr = c.agc_thresh_db;
         q->be.demod = (c.demod == CSDR_DEMOD_NBFM) ? 1 : 0; q->be.kf = c.kf > 0 ? c.kf : 0.3f;
         q->be.init(q->ctx, (int)q->C);
-        q->left.ensure(sizeof(float2) * q->C);
+        q->left.ensure(sizeof(float2) * 2 * q->C);          // < C rotated left-over samples (+ a partial chunk appended)
     }
     if (c.demod == CSDR_DEMOD_AM) q->am.init(q->ctx.stream, am_lanes, 0.8f, g_options[CSDR_OPT_AMPMODEM_PLL] != 0);
     q->out_ptrs.resize((size_t)q->nstreams * q->nout);
@@ -188,33 +188,31 @@ size_t chain_run_device(csdr_chain_s *q, const float2 *xd, size_t nx, size_t x_s
         return (size_t)nr;
     }
 
-    // ---- channelizer path: wide-band dc blocker (in place on r if it is our scratch, else into scratch)
+    // ---- channelizer path: wide-band dc blocker; its output pass also applies the channelizer's pre-rotation
+    // (Liquid.chs:847) and writes straight into the channelizer's input slot, behind the (already rotated) left-over
     const unsigned C = q->C;
-    float2 *w = nullptr;
-    if (nr) {
-        if (r == q->r.as<float2>()) w = q->r.as<float2>();
-        else { q->r.ensure(sizeof(float2) * (size_t)nr); w = q->r.as<float2>(); }
-        q->dcb.run_dc_only(c, r, 0, w, 0, (int)nr);
-    }
     const size_t tot = q->nleft + (size_t)nr, nf = tot / C, used = nf * C;
     if (nf > out_cap) throw CudaError{"chain: output capacity too small"};
+    float2 *dst = nullptr;
     if (nf) {
-        // pre-rotate [left-over | new] into the channelizer input (Liquid.chs:847)
-        float2 *slot = q->ch.input_slot(c, used);
-        if (q->nleft) {
-            launch(k_nco_mix, dim3(1), dim3(256), 0, c.stream, (const float2 *)q->left.as<float2>(), slot, (long long)q->nleft,
-                   q->rot_theta, q->rot_dtheta, q->quantize, 0);
-            q->rot_theta += (uint32_t)q->nleft * q->rot_dtheta;
-        }
-        const size_t take = used - q->nleft;
-        launch(k_nco_mix, dim3(grid_for((long long)take, 256, c.sms)), dim3(256), 0, c.stream, (const float2 *)w, slot + q->nleft,
-               (long long)take, q->rot_theta, q->rot_dtheta, q->quantize, 0);
-        q->rot_theta += (uint32_t)take * q->rot_dtheta;
+        float2 *slot = q->ch.input_slot(c, tot);
+        if (q->nleft) CK(cudaMemcpyAsync(slot, q->left.p, sizeof(float2) * q->nleft, cudaMemcpyDeviceToDevice, c.stream));
+        dst = slot + q->nleft;
+    } else if (nr) {
+        // not even one frame yet (tot < C): append to the left-over
+        dst = q->left.as<float2>() + q->nleft;
+    }
+    if (nr) {
+        q->dcb.run_dc_only(c, r, 0, dst, 0, (int)nr, true, q->rot_theta, q->rot_dtheta, q->quantize);
+        q->rot_theta += (uint32_t)nr * q->rot_dtheta;
+    }
+    if (nf) {
+        float2 *slot = dst - q->nleft;
         q->chan.ensure(sizeof(float2) * used);
         q->ch.run(c, (int)nf, q->chan.as<float2>(), (long long)nf);
-        // remaining < C samples wait for the next call
+        // remaining < C (rotated) samples wait for the next call
         const size_t rem = tot - used;
-        if (rem) CK(cudaMemcpyAsync(q->left.p, w + take, sizeof(float2) * rem, cudaMemcpyDeviceToDevice, c.stream));
+        if (rem) CK(cudaMemcpyAsync(q->left.p, slot + used, sizeof(float2) * rem, cudaMemcpyDeviceToDevice, c.stream));
         q->nleft = rem;
         // per-channel agc -> demod
         void *dem = nullptr;
@@ -240,8 +238,6 @@ size_t chain_run_device(csdr_chain_s *q, const float2 *xd, size_t nx, size_t x_s
                 CK(cudaMemcpyAsync(q->out_ptrs[ch], (char *)dem + (size_t)ch * nf * q->esz, q->esz * nf, cudaMemcpyDeviceToDevice, c.stream));
         }
     } else if (nr) {
-        // not even one frame yet: append to the left-over buffer
-        CK(cudaMemcpyAsync(q->left.as<float2>() + q->nleft, w, sizeof(float2) * (size_t)nr, cudaMemcpyDeviceToDevice, c.stream));
         q->nleft = tot;
     }
     return nf;

@@ -450,10 +450,13 @@ struct Backend {
         return d;
     }
     // dc blocker only, out may alias in
-    void run_dc_only(const Ctx &c, const float2 *in, long long in_stride, float2 *out, long long out_stride, int n)
+    // rot: also multiply by the conjugate NCO phasor (theta0 + i * dtheta), the channelizer's pre-rotation
+    void run_dc_only(const Ctx &c, const float2 *in, long long in_stride, float2 *out, long long out_stride, int n,
+                     bool rot = false, uint32_t rot_theta = 0, uint32_t rot_dtheta = 0, int rot_quantize = 1)
     {
         if (n <= 0) return;
         DcParams d = dc_params(in, in_stride, out, out_stride, n);
+        d.rot = rot ? 1 : 0; d.rot_theta = rot_theta; d.rot_dtheta = rot_dtheta; d.rot_quantize = rot_quantize;
         Launcher l{c.stream};
         be_launch_dc(l, d, true);
     }
