@@ -209,7 +209,9 @@ size_t chain_run_device(csdr_chain_s *q, const float2 *xd, size_t nx, size_t x_s
     if (nf) {
         float2 *slot = dst - q->nleft;
         q->chan.ensure(sizeof(float2) * used);
-        q->ch.run(c, (int)nf, q->chan.as<float2>(), (long long)nf);
+        long long pw_stride = 0;
+        float *pw = q->has_agc ? q->be.pw_target((int)nf, &pw_stride) : nullptr;     // the channelizer writes |y|^2 as well
+        q->ch.run(c, (int)nf, q->chan.as<float2>(), (long long)nf, pw, pw_stride);
         // remaining < C (rotated) samples wait for the next call
         const size_t rem = tot - used;
         if (rem) CK(cudaMemcpyAsync(q->left.p, slot + used, sizeof(float2) * rem, cudaMemcpyDeviceToDevice, c.stream));

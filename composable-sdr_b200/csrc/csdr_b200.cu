@@ -370,6 +370,7 @@ struct Backend {
     int L = 512, W = 384, G = 128; bool fixed_L = false;
     DevBuf lane, Vloc, carry, powA, ss, se, fs, fe, exbits, gatebits, sgnr, sgni, prev_gate, prev_sign, first_bad, bad_list, bad_count, fixups;
     DevBuf ydc, pwbuf, gpost, g_first, y_first;
+    int pw_ready_n = -1;       // the producer of the input has already written its power for a call of this many samples
     int FW = 3; unsigned long long last_refined = 0; int last_L = 0, last_W = 0;
     // self-tuning warm-up: the counters of every call are copied to pinned memory asynchronously; the next call looks
     // at them (no synchronisation) and lengthens / shortens the warm-up
@@ -460,6 +461,17 @@ struct Backend {
         Launcher l{c.stream};
         be_launch_dc(l, d, true);
     }
+    // Where the producer of the next run()'s input (n samples per lane, no dc blocker here) may write |x|^2 itself:
+    // returns the power array and its lane stride; run() then skips its own power pass.
+    float *pw_target(int n, long long *stride)
+    {
+        if (!has_agc || has_dc || n <= 0) return nullptr;
+        const long long pws = ((long long)n + 3) / 4 * 4;
+        pwbuf.ensure(sizeof(float) * (size_t)nlanes * pws); gpost.ensure(sizeof(float) * (size_t)nlanes * pws);
+        pw_ready_n = n;
+        *stride = pws;
+        return pwbuf.as<float>();
+    }
     // [dc] -> [agc+gate] -> [fm]; out: float (demod) or float2
     void run(const Ctx &c, const float2 *in, long long in_stride, void *out, long long out_stride, int n)
     {
@@ -522,7 +534,8 @@ struct Backend {
                 d.pw = pwbuf.as<float>(); d.pw_stride = pws;
             }
             if (has_dc) be_launch_dc(l, d, true);
-            else if (has_agc) be_launch_prep(l, d);
+            else if (has_agc && pw_ready_n != n) be_launch_prep(l, d);
+            pw_ready_n = -1;
         }
         b.in = in; b.in_lane_stride = in_stride; b.out = out; b.out_lane_stride = out_stride;
         b.n = n; b.nlanes = nlanes; b.L = L; b.W = W; b.G = G; b.nseg = nseg; b.ngrp = ngrp;
@@ -647,16 +660,19 @@ struct Channelizer {
         }
         return xr[cur].as<float2>() + hist_samples();
     }
-    void run(const Ctx &c, int nf, float2 *y, long long y_stride)
+    // pw (optional): also write |y|^2 there, [M][pw_stride] (saves the per-channel back end its power pass)
+    void run(const Ctx &c, int nf, float2 *y, long long y_stride, float *pw = nullptr, long long pw_stride = 0)
     {
         if (nf <= 0) return;
         PfbParams p{};
+        p.pw = pw; p.pw_stride = pw_stride;
         p.xr = xr[cur].as<float2>(); p.y = y; p.y_stride = y_stride;
         p.M = (int)M; p.P = (int)P; p.nf = nf; p.F = F; p.log2M = log2M;
         p.h = hd.as<float>(); p.tw = tw.as<float2>();
         if (ring_ok) {
             PfbRingParams rp{};
             rp.xr = p.xr; rp.y = y; rp.y_stride = y_stride; rp.nf = nf; rp.M = (int)M; rp.log2M = log2M;
+            rp.pw = pw; rp.pw_stride = pw_stride;
             rp.h = hd.as<float>(); rp.tw = tw.as<float2>();
             // one wave of CTAs where possible: frames per CTA = nf / (SMs * CTAs per SM), in whole output tiles
             const int slots = std::max(1, c.sms * ring_ctas);
@@ -665,7 +681,7 @@ struct Channelizer {
             rp.T = T;
             launch(ring_kernel, dim3((nf + T - 1) / T), dim3(2 * M / kPfbRingCPT), pfb_ring_smem((int)M, log2M), c.stream, rp);
         } else if (tile_kernel) {
-            tp.xr = p.xr; tp.y = y; tp.y_stride = y_stride; tp.nf = nf;
+            tp.xr = p.xr; tp.y = y; tp.y_stride = y_stride; tp.nf = nf; tp.pw = pw; tp.pw_stride = pw_stride;
             launch(tile_kernel, dim3((nf + kPfbTileF - 1) / kPfbTileF), dim3(kPfbTileF), tile_smem, c.stream, tp);
         } else {
             launch(k_pfb, dim3((nf + F - 1) / F), dim3(256), smem, c.stream, p);

@@ -14,6 +14,9 @@
 
 namespace csdr {
 
+// power of a channel sample exactly as k_be_prep computes it
+__device__ __forceinline__ float pfb_power(float2 v) { return __fadd_rn(__fmul_rn(v.x, v.x), __fmul_rn(v.y, v.y)); }
+
 struct PfbParams {
     const float2 *xr;       // pre-rotated samples: xr[0 .. (P-1)*M) = history frames, then nf*M new samples
     float2 *y;              // [M][y_stride] channel-major output, frame t at column t
@@ -22,6 +25,7 @@ struct PfbParams {
     int log2M;              // >= 0 when M is a power of two, else -1
     const float *h;         // prototype, P*M taps
     const float2 *tw;       // M twiddles exp(-j 2 pi t / M)
+    float *pw; long long pw_stride;   // optional: |y|^2, same layout (input of the per-channel AGC gain loop)
 };
 
 __device__ __forceinline__ unsigned pfb_bitrev(unsigned v, int bits) { return bits ? (__brev(v) >> (32 - bits)) : 0u; }
@@ -91,7 +95,9 @@ __global__ void __launch_bounds__(256) k_pfb(const PfbParams p)
     // transposed store: consecutive threads -> consecutive frames of one channel
     for (int e = threadIdx.x; e < M * nfr; e += blockDim.x) {
         const int c = e / nfr, f = e - c * nfr;
-        p.y[(long long)c * p.y_stride + t0 + f] = buf[f * M + c];
+        const float2 v = buf[f * M + c];
+        p.y[(long long)c * p.y_stride + t0 + f] = v;
+        if (p.pw) p.pw[(long long)c * p.pw_stride + t0 + f] = pfb_power(v);
     }
 }
 
@@ -107,6 +113,7 @@ constexpr int kPfbTileMaxM = 32;
 
 struct PfbTileParams {
     const float2 *xr; float2 *y; long long y_stride; int nf;
+    float *pw; long long pw_stride;        // optional: |y|^2, same layout
     float2 tw[kPfbTileMaxM / 2];           // exp(-j 2 pi t / M)
     float h[kPfbTileP * kPfbTileMaxM];     // h[k * M + n] = prototype[(M - 1 - n) + k * M]
 };
@@ -173,6 +180,11 @@ __global__ void __launch_bounds__(kPfbTileF) k_pfb_tile(const CSDR_GRID_CONSTANT
     float2 *yo = p.y + t0 + f;
 #pragma unroll
     for (int c = 0; c < M; c++) yo[(long long)c * p.y_stride] = b[c];
+    if (p.pw) {
+        float *po = p.pw + t0 + f;
+#pragma unroll
+        for (int c = 0; c < M; c++) po[(long long)c * p.pw_stride] = pfb_power(b[c]);
+    }
 }
 
 // ---- large power-of-two M (128..1024): a CTA slides over its frames with a ring of rows --------------------------
@@ -190,6 +202,7 @@ constexpr int kPfbRingP = 14, kPfbRingTF = 8, kPfbRingCPT = 4, kPfbRingRows = kP
 
 struct PfbRingParams {
     const float2 *xr; float2 *y; long long y_stride;
+    float *pw; long long pw_stride;        // optional: |y|^2, same layout
     int nf, T;               // frames in this call, frames per CTA (multiple of TF)
     int M, log2M;
     const float *h;          // prototype, P*M taps
@@ -336,7 +349,11 @@ __global__ void __launch_bounds__(512, 1) k_pfb_ring(const PfbRingParams p)
             const int cnt = tfl + 1, tb = last - tfl;               // frames parked in the tile, first of them
             for (int e = gtid; e < M * TF; e += 2 * NT) {
                 const int c = e >> 3, f = e & (TF - 1);
-                if (f < cnt) p.y[(long long)c * p.y_stride + tb + f] = obuf[f * OR + c + (c >> 4)];
+                if (f < cnt) {
+                    const float2 v = obuf[f * OR + c + (c >> 4)];
+                    p.y[(long long)c * p.y_stride + tb + f] = v;
+                    if (p.pw) p.pw[(long long)c * p.pw_stride + tb + f] = pfb_power(v);
+                }
             }
         }
         // the barrier at the top of the next iteration separates these reads from the next writes of work / obuf
