@@ -52,6 +52,19 @@ def sig(n, seed, scale=0.3):
     return x.to(torch.complex64)
 
 
+def sig_am(n, seed, sr=10e6, fc=1e6 + 437.0, amp=0.4, index=0.8, tone=1e3):
+    """config-5 stream: AM carrier (index 0.8, 1 kHz tone) 437 Hz off the mixer frequency, plus noise"""
+    import math
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    k = torch.arange(n, device="cuda", dtype=torch.float64)
+    env = (amp * (1.0 + index * torch.cos(2 * math.pi * tone / sr * k))).to(torch.float32)
+    ph = torch.remainder(2 * math.pi * fc / sr * k, 2 * math.pi).to(torch.float32)
+    del k
+    x = torch.polar(env, ph)
+    x = x + 0.02 * torch.complex(torch.randn(n, generator=g, device="cuda"), torch.randn(n, generator=g, device="cuda"))
+    return x.to(torch.complex64)
+
+
 def main():
     n = 1 << 26
     x = sig(n, 1)
@@ -64,7 +77,8 @@ def main():
     run("C4 1024-ch PFB + AGC + NBFM + mix", cs.Chain(1e9, demod=cs.DeNBFM(0.3), agc=-40.0, channels=1024, mix_channels=True),
         sig(1 << 24, 4, 3e-4), b_alg=8.004)
     S = 64
-    x5 = torch.stack([sig(1 << 20, 50 + s) for s in range(S)])
+    x5 = torch.stack([sig_am(1 << 20, 50 + s, fc=1e6 + 437.0 + 3.0 * s) for s in range(S)])
+    torch.cuda.synchronize()
     run("C5 64 streams x 2^20: mix+msresamp+AGC+AM", cs.Chain(10e6, 1e6, 200e3, cs.DeAM(), agc=-40.0, nstreams=S), x5,
         steps=3, warmup=1, b_alg=8.08)
 

@@ -4,9 +4,9 @@ ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "scripts"))
 import torch
 import composable_sdr_b200 as cs
-from bench_configs import sig
+from bench_configs import sig_am
 S, n = 64, 1 << 20
-x = torch.stack([sig(n, 10 + s) for s in range(S)])
+x = torch.stack([sig_am(n, 10 + s, fc=1e6 + 437.0 + 3.0 * s) for s in range(S)])
 torch.cuda.synchronize()
 ch = cs.Chain(10e6, 1e6, 200e3, cs.DeAM(), agc=-40.0, nstreams=S)
 cap = ch.max_output(n)
