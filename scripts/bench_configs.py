@@ -76,10 +76,10 @@ def main():
     run("C3 16-ch PFB, DeNo, no AGC", cs.Chain(2.56e6, channels=16), x3, b_alg=16)
     run("C4 1024-ch PFB + AGC + NBFM + mix", cs.Chain(1e9, demod=cs.DeNBFM(0.3), agc=-40.0, channels=1024, mix_channels=True),
         sig(1 << 24, 4, 3e-4), b_alg=8.004)
-    S = 64
-    x5 = torch.stack([sig_am(1 << 20, 50 + s, fc=1e6 + 437.0 + 3.0 * s) for s in range(S)])
+    S = 256
+    x5 = torch.stack([sig_am(1 << 18, 50 + s, fc=1e6 + 437.0 + 3.0 * (s % 64)) for s in range(S)])
     torch.cuda.synchronize()
-    run("C5 64 streams x 2^20: mix+msresamp+AGC+AM", cs.Chain(10e6, 1e6, 200e3, cs.DeAM(), agc=-40.0, nstreams=S), x5,
+    run("C5 256 streams x 2^18: mix+msresamp+AGC+AM", cs.Chain(10e6, 1e6, 200e3, cs.DeAM(), agc=-40.0, nstreams=S), x5,
         steps=3, warmup=1, b_alg=8.08)
 
 

@@ -19,5 +19,10 @@ if [ "$mode" = "full" ]; then
     timeout 300 ncu --set full --clock-control none -k regex:$k -s 4 -c 1 -o gpurun_out/prof_$k -f \
         python bench.py --steps 2 --warmup 3 --log2n 26 --no-cpu > gpurun_out/ncu_$k.log 2>&1
   done
+  echo "== ncu full capture of the channelizer kernels (configs 3 and 4)"
+  timeout 300 ncu --set full --clock-control none -k regex:k_pfb_tile -s 2 -c 1 -o gpurun_out/prof_k_pfb_tile -f \
+      python scripts/prof_c3.py 16 agc > gpurun_out/ncu_k_pfb_tile.log 2>&1
+  timeout 300 ncu --set full --clock-control none -k regex:k_pfb_ring -s 2 -c 1 -o gpurun_out/prof_k_pfb_ring -f \
+      python scripts/prof_c3.py 1024 agc > gpurun_out/ncu_k_pfb_ring.log 2>&1
   ls -la gpurun_out
 fi

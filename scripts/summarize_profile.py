@@ -74,8 +74,9 @@ json.dump({"kernel": "k_frontend", "chunk_samples": 1 << 26,
           open(os.path.join(OUT, "traffic.json"), "w"), indent=1)
 # back-end kernels (one launch each), same metric list
 with open(os.path.join(OUT, f"{tag}_backend_ncu.txt"), "w") as f:
-    f.write("# ncu --set full --clock-control none -k regex:<kernel> -s 4 -c 1 python bench.py --steps 2 --warmup 3 --log2n 26 --no-cpu\n")
-    for k in ("k_agc_chain", "k_be_emit", "k_be_prep", "k_dc_local"):
+    f.write("# ncu --set full --clock-control none -k regex:<kernel> -s 4 -c 1 python bench.py --steps 2 --warmup 3 --log2n 26 --no-cpu\n"
+            "# (k_pfb_*: python scripts/prof_c3.py 16|1024 agc, 2^24 input samples)\n")
+    for k in ("k_agc_chain", "k_be_emit", "k_be_prep", "k_dc_local", "k_pfb_tile", "k_pfb_ring"):
         r = os.path.join(G, f"prof_{k}.ncu-rep")
         if not os.path.exists(r):
             continue
