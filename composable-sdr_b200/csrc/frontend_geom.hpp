@@ -92,8 +92,8 @@ __host__ __device__ constexpr int fe_std_tc(int S)
 {
     return S == 1 ? 1792 : S == 2 ? 896 : S == 3 ? 400 : S == 4 ? 208 : S == 5 ? 96 : 48;
 }
-// variant 1 (k_frontend_direct): bulk copy (TMA) into a linear staging buffer that IS the top level; the first stage
-// reads pairs from it and mixes in registers; three CTAs per SM
+// variant 1 (k_frontend_direct): TMA tensor copy into a swizzled tile that IS the top level; the first stage reads
+// pairs from it and mixes in registers; three CTAs per SM
 __host__ __device__ constexpr int fe_std_tc_direct(int S)
 {
     return S == 1 ? 1536 : S == 2 ? 768 : S == 3 ? 384 : S == 4 ? 192 : S == 5 ? 64 : 32;

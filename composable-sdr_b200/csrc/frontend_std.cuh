@@ -4,11 +4,13 @@
 // base register + immediate, loop trip counts are constants and the half-band taps are read straight from the
 // kernel-parameter constant bank by the FFMAs.  Other plans use the generic k_frontend.
 //
-// Two kernels share the stage, bookkeeping and resampler code:
-//   k_frontend_direct<S> (default): the raw tile is bulk-copied (TMA, cp.async.bulk + mbarrier) one tile ahead into a
-//       linear staging buffer and the first half-band stage reads it there, mixing in registers.  3 CTAs per SM.
-//   k_frontend_std<S>: raw samples are prefetched into registers one tile ahead, mixed and written de-interleaved by a
-//       separate loader pass.  2 CTAs per SM.  Kept as the cross-check of the direct kernel (CSDR_OPT_FRONTEND_VARIANT).
+// Three kernels share the stage, bookkeeping and resampler code (CSDR_OPT_FRONTEND_VARIANT):
+//   k_frontend_direct<S> (1, default): the raw tile arrives one tile ahead by a TMA tensor copy (cp.async.bulk.tensor,
+//       128-byte swizzle, mbarrier) and the first half-band stage reads it where it lands, mixing in registers.
+//       3 CTAs per SM.
+//   k_frontend_std<S> (0): raw samples are prefetched into registers one tile ahead, mixed and written de-interleaved
+//       by a separate loader pass.  2 CTAs per SM.  Kept as the cross-check of the direct kernel.
+//   k_frontend_ws<S> (2): the direct kernel split into producer / consumer warp groups (measured slower; experiment).
 #pragma once
 #include "frontend.cuh"
 
