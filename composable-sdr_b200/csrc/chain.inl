@@ -23,7 +23,7 @@ struct csdr_chain_s {
     unsigned long long fixups_seen = 0, fixups_last = 0;
     // second stream: the back end of part i runs while the front end filters part i+1 (and host copies overlap)
     cudaStream_t copy_stream = nullptr; cudaEvent_t ev_copy[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
-    cudaStream_t be_stream = nullptr;
+    cudaStream_t be_stream = nullptr, d2h_stream = nullptr;
     std::vector<cudaEvent_t> ev_pool;
     DevBuf xpipe[2];
     cudaEvent_t event(size_t i)
@@ -43,6 +43,7 @@ struct csdr_chain_s {
         if (ctx.stream) cudaStreamSynchronize(ctx.stream);
         if (copy_stream) { cudaStreamSynchronize(copy_stream); cudaStreamDestroy(copy_stream); }
         if (be_stream) { cudaStreamSynchronize(be_stream); cudaStreamDestroy(be_stream); }
+        if (d2h_stream) { cudaStreamSynchronize(d2h_stream); cudaStreamDestroy(d2h_stream); }
         for (auto e : ev_pool) if (e) cudaEventDestroy(e);
         for (auto e : ev_copy) if (e) cudaEventDestroy(e);
         for (auto e : ev_done) if (e) cudaEventDestroy(e);
@@ -300,8 +301,42 @@ int csdr_chain_process(csdr_chain q, const csdr_cf32 *x, size_t nx, size_t x_str
         for (size_t i = 0; i < nptr; i++) q->out_ptrs[i] = outs[i];
     }
     size_t n = 0;
+    constexpr size_t kPart = (size_t)1 << 23;                      // 64 MiB of CF32 per pipelined part
     if (nx == 0 || is_device_ptr(x)) {
         n = chain_run_device(q, (const float2 *)x, nx, x_stride, any_host_out ? cap_each : out_cap);
+    } else if (S == 1 && nx >= 2 * kPart) {
+        // large host chunk: the stream is fed in parts, the host->device copy of part i+1 (copy stream) and the
+        // device->host copy of part i-1's results (third stream) overlap the kernels of part i (PCIe is full duplex)
+        if (!q->d2h_stream) CK(cudaStreamCreateWithFlags(&q->d2h_stream, cudaStreamNonBlocking));
+        q->xin.ensure(sizeof(float2) * nx);
+        const size_t nparts = (nx + kPart - 1) / kPart, cap = any_host_out ? cap_each : out_cap;
+        constexpr size_t kEv = 128;                                   // event-pool indices of this path
+        CK(cudaEventRecord(q->event(kEv - 1), c.stream));              // earlier work on the handle may still read xin
+        CK(cudaStreamWaitEvent(q->copy_stream, q->event(kEv - 1), 0));
+        for (size_t i = 0; i < nparts; i++) {
+            const size_t off = i * kPart, cnt = std::min(kPart, nx - off);
+            CK(cudaMemcpyAsync(q->xin.as<float2>() + off, (const float2 *)x + off, cnt * sizeof(float2), cudaMemcpyHostToDevice, q->copy_stream));
+            CK(cudaEventRecord(q->event(kEv + 2 * i), q->copy_stream));
+        }
+        const std::vector<void *> base = q->out_ptrs;
+        for (size_t i = 0; i < nparts; i++) {
+            const size_t off = i * kPart, cnt = std::min(kPart, nx - off);
+            CK(cudaStreamWaitEvent(c.stream, q->event(kEv + 2 * i), 0));
+            for (size_t k = 0; k < nptr; k++) q->out_ptrs[k] = (char *)base[k] + n * q->esz;
+            const size_t ni = chain_run_device(q, q->xin.as<float2>() + off, cnt, cnt, cap - n);
+            if (any_host_out && ni) {
+                CK(cudaEventRecord(q->event(kEv + 2 * i + 1), c.stream));
+                CK(cudaStreamWaitEvent(q->d2h_stream, q->event(kEv + 2 * i + 1), 0));
+                for (size_t k = 0; k < nptr; k++)
+                    CK(cudaMemcpyAsync((char *)outs[k] + n * q->esz, q->out_ptrs[k], ni * q->esz,
+                                       is_device_ptr(outs[k]) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, q->d2h_stream));
+            }
+            n += ni;
+        }
+        q->out_ptrs = base;
+        if (any_host_out) { CK(cudaStreamSynchronize(q->d2h_stream)); c.sync(); }
+        if (n_out) *n_out = n;
+        return 0;
     } else {
         // host input: one asynchronous copy per stream into contiguous device staging
         q->xin.ensure(sizeof(float2) * nx * S);

@@ -68,6 +68,16 @@ def test_config2_large_chunk(cs, orc):
     finally:
         cs.set_option(7, 0)
     assert_parity(y2, ref, rel=REL_TOL_AFTER_DCBLOCK, period=per, what="config 2, 2^24-sample chunk, overlapped")
+    # a host chunk this large is fed in pipelined parts (copy of part i+1 under the kernels of part i); a ragged
+    # length leaves a short last part, and the same samples resident on the device take the single-launch path
+    import torch
+    m = (1 << 24) + 12345
+    xr = np.concatenate([x, x[:12345]])
+    yh = cs.Chain(2.56e6, 1e5, 200e3, cs.DeNBFM(0.3), agc=-40.0).process(xr)[0]
+    yd = cs.Chain(2.56e6, 1e5, 200e3, cs.DeNBFM(0.3), agc=-40.0).process(torch.from_numpy(xr).cuda())[0].cpu().numpy()
+    assert len(yh) == len(yd) and abs(len(yh) - m * 5 / 64) <= 1
+    assert_parity(yh[:len(ref)], ref, rel=REL_TOL_AFTER_DCBLOCK, period=per, what="pipelined host chunk")
+    assert_parity(yh, yd, rel=REL_TOL_AFTER_DCBLOCK, period=per, what="pipelined host chunk vs device chunk")
 
 
 def test_config3_channelizer_per_channel_fm(cs, orc):
