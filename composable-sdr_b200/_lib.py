@@ -10,7 +10,8 @@ LIB_PATH = os.path.join(HERE, "libcsdr_b200.so")
 class ChainCfg(C.Structure):
     _fields_ = [("samplerate", C.c_double), ("offset_hz", C.c_double), ("bandwidth_hz", C.c_double),
                 ("demod", C.c_int), ("kf", C.c_float), ("agc_thresh_db", C.c_float),
-                ("channels", C.c_uint), ("mix", C.c_int), ("nstreams", C.c_uint), ("device", C.c_int)]
+                ("channels", C.c_uint), ("mix", C.c_int), ("nstreams", C.c_uint), ("device", C.c_int),
+                ("decim", C.c_uint)]
 
 
 # every symbol include/csdr_b200.h declares: name -> (restype, argtypes)
@@ -46,6 +47,11 @@ SIGNATURES = {
     "csdr_freqdem_demodulate_block": (None, [_vp, _vp, _u, _vp]),
     "csdr_ampmodem_create": (_vp, [_f, _i, _i]), "csdr_ampmodem_destroy": (None, [_vp]),
     "csdr_ampmodem_print": (None, [_vp]), "csdr_ampmodem_demodulate_block": (None, [_vp, _vp, _u, _vp]),
+    "csdr_iirfilt_rrrf_create_prototype": (_vp, [_i, _i, _i, _u, _f, _f, _f, _f]), "csdr_iirfilt_rrrf_destroy": (None, [_vp]),
+    "csdr_iirfilt_rrrf_print": (None, [_vp]), "csdr_iirfilt_rrrf_execute_block": (None, [_vp, _vp, _u, _vp]),
+    "csdr_iirfilt_rrrf_coefficients": (_u, [_vp, _vp, _vp]),
+    "csdr_firdecim_rrrf_create_kaiser": (_vp, [_u, _u, _f]), "csdr_firdecim_rrrf_destroy": (None, [_vp]),
+    "csdr_firdecim_rrrf_print": (None, [_vp]), "csdr_firdecim_rrrf_execute_block": (None, [_vp, _vp, _u, _vp]),
     "csdr_chain_create": (_vp, [C.POINTER(ChainCfg)]), "csdr_chain_destroy": (_i, [_vp]),
     "csdr_chain_print": (None, [_vp]), "csdr_chain_num_outputs": (_u, [_vp]),
     "csdr_chain_out_elem_size": (_sz, [_vp]), "csdr_chain_max_output": (_sz, [_vp, _sz]),

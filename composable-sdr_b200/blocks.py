@@ -15,7 +15,8 @@ from ._lib import CsdrError, ChainCfg  # noqa: F401
 
 __all__ = ["Pipe", "Fold", "compose", "unPipe", "addPipe", "takeNArr", "compact", "mux", "mix", "distribute_",
            "mixDown", "mixUp", "resampler", "dcBlocker", "firpfbchChannelizer", "automaticGainControl",
-           "fmDemodulator", "amDemodulator", "listSink", "DeNo", "DeNBFM", "DeAM", "Chain", "sdrProcess",
+           "fmDemodulator", "amDemodulator", "iirFilter", "firDecimator", "wbFMDemodulator", "listSink", "DeNo", "DeNBFM",
+           "DeAM", "DeWBFM", "Chain", "sdrProcess",
            "CsdrError", "kernel_launches", "set_option", "device_count", "PinnedBuffer"]
 
 
@@ -388,6 +389,43 @@ def amDemodulator():
                   _same_size(lambda L: L.csdr_ampmodem_demodulate_block, np.float32), "amDemodulator")
 
 
+def _as_f32(a):
+    if _is_torch(a):
+        import torch
+        return a.to(torch.float32).contiguous()
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def iirFilter(n, fc, f0, ap, as_):
+    """Liquid.chs:644-650: iirfilt_rrrf_create_prototype 0 0 0 n fc f0 ap as (Butterworth low-pass, sections)."""
+    def process(L, h, a):
+        a = _as_f32(a)
+        y = _empty_like_kind(a, len(a), np.float32)
+        L.csdr_iirfilt_rrrf_execute_block(h, _ptr(a), len(a), _ptr(y))
+        return y
+    return _block(lambda L: L.csdr_iirfilt_rrrf_create_prototype(0, 0, 0, n, fc, f0, ap, as_),
+                  lambda L, h: L.csdr_iirfilt_rrrf_destroy(h), process, "iirFilter")
+
+
+def firDecimator(m):
+    """Liquid.chs:487-503: firdecim_rrrf_create_kaiser m 10 60; an array of length n gives n div m samples, the
+    remainder of the array is dropped like in the reference."""
+    def process(L, h, a):
+        a = _as_f32(a)
+        n = len(a) // m
+        y = _empty_like_kind(a, n, np.float32)
+        if n:
+            L.csdr_firdecim_rrrf_execute_block(h, _ptr(a), n, _ptr(y))
+        return y
+    return _block(lambda L: L.csdr_firdecim_rrrf_create_kaiser(m, 10, 60.0), lambda L, h: L.csdr_firdecim_rrrf_destroy(h),
+                  process, "firDecimator")
+
+
+def wbFMDemodulator(quad_rate, decim):
+    """Liquid.chs:652-656."""
+    return firDecimator(decim) * iirFilter(2, float(np.float32(5000.0 / quad_rate)), 0.0, 10.0, 10.0) * fmDemodulator(0.6)
+
+
 # --------------------------------------------------------------------------------------------- the app graph
 class DeNo:
     code = 0
@@ -404,6 +442,15 @@ class DeNBFM:
 class DeAM:
     code = 2
     kf = 0.0
+
+
+class DeWBFM:
+    """DeWBFM decim (apps/SoapySDR.hs:253-260): wbFMDemodulator outBW decim"""
+    code = 3
+    kf = 0.6
+
+    def __init__(self, decim):
+        self.decim = int(decim)
 
 
 def sdrProcess(src, samplerate, offset=0.0, bandwidth=0.0, numsamples=None, demod=None, agc=0.0, channels=1,
@@ -424,6 +471,8 @@ def sdrProcess(src, samplerate, offset=0.0, bandwidth=0.0, numsamples=None, demo
         dem = fmDemodulator(demod.kf) * agc_p
     elif isinstance(demod, DeAM):
         dem = amDemodulator() * agc_p
+    elif isinstance(demod, DeWBFM):
+        dem = wbFMDemodulator(bandwidth if bandwidth else samplerate, demod.decim) * agc_p
     else:
         dem = agc_p
     nch, m = channels, 4
@@ -450,7 +499,8 @@ class Chain:
         demod = demod or DeNo()
         self.L = _lib.load()
         self.cfg = ChainCfg(float(samplerate), float(offset), float(bandwidth), demod.code, float(demod.kf), float(agc),
-                            int(channels), int(bool(mix_channels)), int(nstreams), int(device))
+                            int(channels), int(bool(mix_channels)), int(nstreams), int(device),
+                            int(getattr(demod, "decim", 0)))
         self.h = _lib.check_handle(self.L.csdr_chain_create(C.byref(self.cfg)), "csdr_chain_create")
         self.nout = int(self.L.csdr_chain_num_outputs(self.h))
         self.nstreams = max(1, int(nstreams))

@@ -17,6 +17,8 @@ struct csdr_chain_s {
     Backend dcb;         // C > 1: the single wide-band dc blocker
     Channelizer ch; uint32_t rot_theta = 0, rot_dtheta = 0;
     AmDemod am;
+    WbfmTail wb; bool has_wb = false;       // DeWBFM: de-emphasis + decimator behind the discriminator
+    DevBuf wbout;
     DevBuf xin, r, left, chan, dem, amout, outstage;
     size_t nleft = 0;
     std::vector<void *> out_ptrs;
@@ -59,7 +61,9 @@ void chain_init(csdr_chain_s *q)
     q->C = c.channels > 1 ? c.channels : 1;
     q->nstreams = c.nstreams > 1 ? c.nstreams : 1;
     if (q->C > 1 && q->nstreams > 1) throw CudaError{"chain: channelizer with nstreams > 1 is not implemented"};
-    if (c.demod < 0 || c.demod > 2) throw CudaError{"chain: unknown demodulator"};
+    if (c.demod < 0 || c.demod > 3) throw CudaError{"chain: unknown demodulator"};
+    q->has_wb = c.demod == CSDR_DEMOD_WBFM;
+    if (q->has_wb && c.decim > 4096) throw CudaError{"chain: DeWBFM decimation must be in [1, 4096]"};
     if (c.demod == CSDR_DEMOD_NBFM && !(c.kf > 0.0f)) throw CudaError{"chain: DeNBFM needs kf > 0"};
     q->nout = (q->C > 1 && !c.mix) ? q->C : 1;
     q->esz = c.demod ? sizeof(float) : sizeof(float2);
@@ -81,7 +85,7 @@ void chain_init(csdr_chain_s *q)
     if (q->C == 1) {
         q->be.has_dc = true; q->be.dc_alpha = 0.0005f;
         q->be.has_agc = q->has_agc; q->be.agc_thr = c.agc_thresh_db;
-        q->be.demod = (c.demod == CSDR_DEMOD_NBFM) ? 1 : 0; q->be.kf = c.kf > 0 ? c.kf : 0.3f;
+        q->be.demod = (c.demod == CSDR_DEMOD_NBFM || q->has_wb) ? 1 : 0; q->be.kf = q->has_wb ? 0.6f : c.kf > 0 ? c.kf : 0.3f;
         q->be.init(q->ctx, (int)q->nstreams);
     } else {
         q->dcb.has_dc = true; q->dcb.dc_alpha = 0.0005f;
@@ -90,11 +94,13 @@ void chain_init(csdr_chain_s *q)
         q->rot_dtheta = design::nco_constrain(design::firpfbch_rotation(q->C));
         q->be.has_dc = false;
         q->be.has_agc = q->has_agc; q->be.agc_thr = c.agc_thresh_db;
-        q->be.demod = (c.demod == CSDR_DEMOD_NBFM) ? 1 : 0; q->be.kf = c.kf > 0 ? c.kf : 0.3f;
+        q->be.demod = (c.demod == CSDR_DEMOD_NBFM || q->has_wb) ? 1 : 0; q->be.kf = q->has_wb ? 0.6f : c.kf > 0 ? c.kf : 0.3f;
         q->be.init(q->ctx, (int)q->C);
         q->left.ensure(sizeof(float2) * 2 * q->C);          // < C rotated left-over samples (+ a partial chunk appended)
     }
     if (c.demod == CSDR_DEMOD_AM) q->am.init(q->ctx.stream, am_lanes, 0.8f, g_options[CSDR_OPT_AMPMODEM_PLL] != 0);
+    // wbFMDemodulator outBW decim (SoapySDR.hs:257): the quadrature rate is the resampler's output rate
+    if (q->has_wb) q->wb.init(q->ctx, c.bandwidth_hz != 0.0 ? c.bandwidth_hz : c.samplerate, c.decim > 1 ? c.decim : 1, am_lanes);
     q->out_ptrs.resize((size_t)q->nstreams * q->nout);
     CK(cudaStreamCreateWithFlags(&q->copy_stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&q->be_stream, cudaStreamNonBlocking));
@@ -108,6 +114,7 @@ size_t chain_max_out(const csdr_chain_s *q, size_t nx)
 {
     size_t n = q->has_resamp ? (size_t)q->fe.max_out((long long)nx) : nx;
     if (q->C > 1) n = (n + q->nleft) / q->C + 1;
+    if (q->has_wb) n = q->wb.max_out(n) + 1;
     return n;
 }
 
@@ -121,7 +128,7 @@ size_t chain_run_device(csdr_chain_s *q, const float2 *xd, size_t nx, size_t x_s
     // stream while the front end filters part i+1.  Measured on B200 it does not pay (0.87 ms vs 0.79 ms per 2^27
     // samples): the persistent front-end grid leaves room for one back-end CTA per SM, and the back end needs the
     // whole machine to hide the latency of its recurrences.  Off by default.
-    if (q->C == 1 && S == 1 && q->has_resamp && q->cfg.demod != CSDR_DEMOD_AM && nx >= ((size_t)1 << 23) &&
+    if (q->C == 1 && S == 1 && q->has_resamp && q->cfg.demod != CSDR_DEMOD_AM && !q->has_wb && nx >= ((size_t)1 << 23) &&
         g_options[CSDR_OPT_OVERLAP] != 0) {
         // few, large parts: the back end of a part is latency bound (~0.15 ms almost regardless of its size)
         size_t nparts = nx >= ((size_t)1 << 28) ? 4 : 2;
@@ -164,7 +171,7 @@ size_t chain_run_device(csdr_chain_s *q, const float2 *xd, size_t nx, size_t x_s
     if (nr > 0x7fffffffLL) throw CudaError{"chain: chunk too large"};
 
     if (q->C == 1) {
-        if ((size_t)nr > out_cap) throw CudaError{"chain: output capacity too small"};
+        if ((q->has_wb ? q->wb.max_out((size_t)nr) : (size_t)nr) > out_cap) throw CudaError{"chain: output capacity too small"};
         if (nr == 0) return 0;
         // out_ptrs are per-stream device buffers; the back end wants one base + stride
         const bool contiguous = (S == 1);
@@ -178,6 +185,18 @@ size_t chain_run_device(csdr_chain_s *q, const float2 *xd, size_t nx, size_t x_s
             if (!contiguous)
                 for (unsigned s = 0; s < S; s++)
                     CK(cudaMemcpyAsync(q->out_ptrs[s], dst + (size_t)s * nr, sizeof(float) * nr, cudaMemcpyDeviceToDevice, c.stream));
+        } else if (q->has_wb) {
+            // agc -> freqdem (kf 0.6) -> de-emphasis -> decimator
+            q->dem.ensure(sizeof(float) * (size_t)nr * S);
+            q->be.run(c, r, r_stride, q->dem.p, nr, (int)nr);
+            const size_t nb = q->wb.max_out((size_t)nr);
+            if (nb > out_cap) throw CudaError{"chain: output capacity too small"};
+            float *dst = contiguous ? (float *)q->out_ptrs[0] : (q->wbout.ensure(sizeof(float) * (nb + 1) * S), q->wbout.as<float>());
+            q->wb.run(c, q->dem.as<float>(), nr, (int)nr, dst, (long long)nb);
+            if (!contiguous && nb)
+                for (unsigned s = 0; s < S; s++)
+                    CK(cudaMemcpyAsync(q->out_ptrs[s], dst + (size_t)s * nb, sizeof(float) * nb, cudaMemcpyDeviceToDevice, c.stream));
+            return nb;
         } else {
             void *dst = q->out_ptrs[0];
             if (!contiguous) { q->dem.ensure(q->esz * (size_t)nr * S); dst = q->dem.p; }
@@ -193,7 +212,7 @@ size_t chain_run_device(csdr_chain_s *q, const float2 *xd, size_t nx, size_t x_s
     // (Liquid.chs:847) and writes straight into the channelizer's input slot, behind the (already rotated) left-over
     const unsigned C = q->C;
     const size_t tot = q->nleft + (size_t)nr, nf = tot / C, used = nf * C;
-    if (nf > out_cap) throw CudaError{"chain: output capacity too small"};
+    if ((q->has_wb ? q->wb.max_out(nf) : nf) > out_cap) throw CudaError{"chain: output capacity too small"};
     float2 *dst = nullptr;
     if (nf) {
         float2 *slot = q->ch.input_slot(c, tot);
@@ -231,19 +250,28 @@ size_t chain_run_device(csdr_chain_s *q, const float2 *xd, size_t nx, size_t x_s
             q->be.run(c, q->chan.as<float2>(), (long long)nf, q->dem.p, (long long)nf, (int)nf);
             dem = q->dem.p;
         }
+        size_t nfo = nf;                               // samples per channel behind the demodulator
+        if (q->has_wb) {
+            nfo = q->wb.max_out(nf);
+            q->wbout.ensure(sizeof(float) * (nfo + 1) * C);
+            q->wb.run(c, (const float *)dem, (long long)nf, (int)nf, q->wbout.as<float>(), (long long)nfo);
+            dem = q->wbout.p;
+        }
+        if (nfo == 0) return 0;
         if (q->cfg.mix) {
             // mix = foldl1 (zipWith (+)) over channels 1..C (Trans.hs:119-122); cf32 is summed as 2 floats
-            const long long nfl = (long long)nf * (long long)(q->esz / sizeof(float));
+            const long long nfl = (long long)nfo * (long long)(q->esz / sizeof(float));
             launch(k_lane_sum, dim3(grid_for(nfl, 256, c.sms)), dim3(256), 0, c.stream, (const float *)dem, nfl, (int)C,
                    (float *)q->out_ptrs[0], nfl);
         } else {
             for (unsigned ch = 0; ch < C; ch++)
-                CK(cudaMemcpyAsync(q->out_ptrs[ch], (char *)dem + (size_t)ch * nf * q->esz, q->esz * nf, cudaMemcpyDeviceToDevice, c.stream));
+                CK(cudaMemcpyAsync(q->out_ptrs[ch], (char *)dem + (size_t)ch * nfo * q->esz, q->esz * nfo, cudaMemcpyDeviceToDevice, c.stream));
         }
+        return nfo;
     } else if (nr) {
         q->nleft = tot;
     }
-    return nf;
+    return 0;
 }
 
 }  // namespace
@@ -358,6 +386,7 @@ int csdr_chain_seek(csdr_chain q, uint64_t n_prior)
 {
     API_BEGIN
     if (q->C > 1) throw CudaError{"chain: seek with a channelizer is not implemented"};
+    if (q->has_wb) throw CudaError{"chain: seek with DeWBFM is not implemented"};
     if (q->has_resamp) { if (q->fe.interp) { q->fe.cursor = FrontendCursor(); q->fe.cursor.n_abs = n_prior; } else q->fe.cursor = fe_seek(q->fe.geo, n_prior); }
     else q->mix_theta = (uint32_t)n_prior * q->mix_dtheta;
     return 0;

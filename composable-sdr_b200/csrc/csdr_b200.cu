@@ -14,6 +14,7 @@
 #include <stdexcept>
 #include <string>
 #include "ampmodem.cuh"
+#include "wbfm.cuh"
 
 #include <atomic>
 #include <cstdio>
@@ -694,6 +695,104 @@ struct Channelizer {
     }
 };
 
+// ---------------------------------------------------------------------------------- wide-band FM tail (real-valued)
+// iirfilt_rrrf in second-order sections: per section three launches (wbfm.cuh); state (v1, v2) per lane on the device
+struct Iir2Filter {
+    std::vector<design::Sos> sos; int lanes = 1;
+    DevBuf state, qtab, segz, segin;
+    void init(const Ctx &c, const std::vector<design::Sos> &s, int lanes_)
+    {
+        sos = s; lanes = lanes_;
+        state.ensure(sizeof(float2) * sos.size() * lanes);
+        CK(cudaMemsetAsync(state.p, 0, sizeof(float2) * sos.size() * lanes, c.stream));
+        std::vector<double> q(sos.size() * 128);
+        for (size_t i = 0; i < sos.size(); i++) iir2_q_table(sos[i].a[1], sos[i].a[2], q.data() + i * 128);
+        qtab.ensure(q.size() * sizeof(double));
+        CK(cudaMemcpyAsync(qtab.p, q.data(), q.size() * sizeof(double), cudaMemcpyHostToDevice, c.stream));
+        c.sync();
+    }
+    // y may be x (every thread reads its samples before it writes them)
+    void run(const Ctx &c, const float *x, long long x_stride, float *y, long long y_stride, int n)
+    {
+        if (n <= 0) return;
+        for (size_t i = 0; i < sos.size(); i++) {
+            Iir2Params p{};
+            p.x = i ? y : x; p.x_stride = i ? y_stride : x_stride; p.y = y; p.y_stride = y_stride;
+            iir2_plan(p, sos[i].b, sos[i].a, n);
+            segz.ensure(sizeof(double2) * (size_t)p.nseg * lanes);
+            segin.ensure(sizeof(double2) * (size_t)p.nseg * lanes);
+            p.seg_z = segz.as<double2>(); p.seg_in = segin.as<double2>();
+            p.Q = qtab.as<double>() + i * 128;
+            p.state = state.as<float2>() + i * lanes;
+            iir2_launch(StreamLauncher{c.stream}, p, lanes);
+        }
+    }
+};
+
+// firdecim_rrrf as a stream: whole blocks of M samples are consumed as they arrive.  Device layout of a call, per
+// lane:  z = [ Lh-1 samples of history | < M pending | the call's new samples ]; the producer writes the new samples
+// straight into input_slot().
+struct FirDecimator {
+    unsigned M = 1; int Lh = 0, lanes = 1;
+    DevBuf h, hist, z; long long z_stride = 0; size_t fill = 0;
+    long long hist_stride() const { return (long long)Lh - 1 + M; }
+    void init(const Ctx &c, unsigned M_, unsigned m, float As, int lanes_)
+    {
+        M = M_; lanes = lanes_;
+        std::vector<float> taps = design::design_firdecim(M, m, As);
+        Lh = (int)taps.size();
+        h.ensure(taps.size() * sizeof(float));
+        CK(cudaMemcpyAsync(h.p, taps.data(), taps.size() * sizeof(float), cudaMemcpyHostToDevice, c.stream));
+        hist.ensure(sizeof(float) * hist_stride() * lanes);
+        CK(cudaMemsetAsync(hist.p, 0, sizeof(float) * hist_stride() * lanes, c.stream));
+        c.sync();
+    }
+    float *input_slot(const Ctx &c, int n, long long *stride)
+    {
+        const int head = Lh - 1 + (int)fill;
+        z_stride = ((long long)head + n + 3) & ~3LL;
+        z.ensure(sizeof(float) * (size_t)z_stride * lanes);
+        launch(k_rows_copy, dim3((head + 255) / 256, lanes), dim3(256), 0, c.stream, (const float *)hist.as<float>(), hist_stride(), 0LL,
+               z.as<float>(), z_stride, 0LL, head);
+        *stride = z_stride;
+        return z.as<float>() + head;
+    }
+    // after n new samples were written to input_slot(): y[lane][0 .. blocks) ; returns blocks
+    int run(const Ctx &c, int n, float *y, long long y_stride)
+    {
+        const size_t tot = fill + (size_t)n;
+        const int nb = (int)(tot / M);
+        FirDecimParams p{};
+        p.z = z.as<float>(); p.z_stride = z_stride; p.y = y; p.y_stride = y_stride; p.h = h.as<float>();
+        p.nout = nb; p.M = (int)M; p.Lh = Lh;
+        firdecim_launch(StreamLauncher{c.stream}, p, lanes, c.sms * 8);
+        fill = tot - (size_t)nb * M;
+        const int keep = Lh - 1 + (int)fill;
+        launch(k_rows_copy, dim3((keep + 255) / 256, lanes), dim3(256), 0, c.stream, (const float *)z.as<float>(), z_stride,
+               (long long)nb * M, hist.as<float>(), hist_stride(), 0LL, keep);
+        return nb;
+    }
+};
+
+// wbFMDemodulator's tail after freqdem (Liquid.chs:652-656): de-emphasis, then the output decimator
+struct WbfmTail {
+    Iir2Filter deemph; FirDecimator dec;
+    void init(const Ctx &c, double quad_rate, unsigned decim, int lanes)
+    {
+        deemph.init(c, design::butter_lowpass_sos(2, (float)(5000.0 / quad_rate)), lanes);
+        dec.init(c, decim, 10, 60.0f, lanes);
+    }
+    size_t max_out(size_t n) const { return (n + dec.fill) / dec.M; }
+    // fm: [lanes][n] demodulated samples; y: [lanes][>= max_out(n)]
+    int run(const Ctx &c, const float *fm, long long fm_stride, int n, float *y, long long y_stride)
+    {
+        long long zs = 0;
+        float *slot = dec.input_slot(c, n, &zs);
+        deemph.run(c, fm, fm_stride, slot, zs, n);
+        return dec.run(c, n, y, y_stride);
+    }
+};
+
 }  // namespace
 
 // ------------------------------------------------------------------------------------------ handles
@@ -712,6 +811,8 @@ struct csdr_agc_s {
 };
 struct csdr_freqdem_s { Ctx ctx; Staging st; float kf, ref; float2 prev; csdr_freqdem_s() : ctx(-1) { prev.x = prev.y = 0; } };
 struct csdr_ampmodem_s { Ctx ctx; Staging st; AmDemod am; csdr_ampmodem_s() : ctx(-1) {} };
+struct csdr_iirfilt_rrrf_s { Ctx ctx; Staging st; Iir2Filter f; csdr_iirfilt_rrrf_s() : ctx(-1) {} };
+struct csdr_firdecim_s { Ctx ctx; Staging st; FirDecimator d; csdr_firdecim_s() : ctx(-1) {} };
 
 #define API_BEGIN clear_err(); try {
 #define API_END(ret_fail)                                                    \
@@ -1017,6 +1118,77 @@ void csdr_ampmodem_demodulate_block(csdr_ampmodem q, const csdr_cf32 *r, unsigne
     q->am.run(q->ctx.stream, rd, 0, md, 0, (int)n);
     g_launches.fetch_add(q->am.take_launches());
     q->st.finish(q->ctx, m, md, (size_t)n * sizeof(float));
+    API_END_VOID
+}
+
+// ---------------------------------------------------------------- iirfilt_rrrf (Butterworth low-pass prototype)
+csdr_iirfilt_rrrf csdr_iirfilt_rrrf_create_prototype(int ftype, int btype, int format, unsigned order, float fc, float f0,
+                                                     float ap, float as)
+{
+    API_BEGIN
+    (void)f0; (void)ap; (void)as;
+    if (ftype != 0 || btype != 0 || format != 0)
+        throw CudaError{"iirfilt_rrrf_create_prototype: only Butterworth / low-pass / second-order sections (0, 0, 0) is implemented"};
+    if (order < 1 || order > 16) throw CudaError{"iirfilt_rrrf_create_prototype: order must be in [1, 16]"};
+    if (!(fc > 0.0f && fc < 0.5f)) throw CudaError{"iirfilt_rrrf_create_prototype: cutoff must be in (0, 0.5)"};
+    std::unique_ptr<csdr_iirfilt_rrrf_s> q(new csdr_iirfilt_rrrf_s());
+    q->f.init(q->ctx, design::butter_lowpass_sos(order, fc), 1);
+    return q.release();
+    API_END(nullptr)
+}
+void csdr_iirfilt_rrrf_destroy(csdr_iirfilt_rrrf q) { delete q; }
+void csdr_iirfilt_rrrf_print(csdr_iirfilt_rrrf q)
+{
+    printf("iir filter [sos]:\n");
+    for (size_t i = 0; i < q->f.sos.size(); i++) {
+        const design::Sos &s = q->f.sos[i];
+        printf("  section %zu: b = %12.8f %12.8f %12.8f   a = %12.8f %12.8f %12.8f\n", i, s.b[0], s.b[1], s.b[2], s.a[0], s.a[1], s.a[2]);
+    }
+}
+unsigned csdr_iirfilt_rrrf_coefficients(csdr_iirfilt_rrrf q, float *b, float *a)
+{
+    for (size_t i = 0; i < q->f.sos.size(); i++)
+        for (int j = 0; j < 3; j++) { if (b) b[3 * i + j] = q->f.sos[i].b[j]; if (a) a[3 * i + j] = q->f.sos[i].a[j]; }
+    return (unsigned)q->f.sos.size();
+}
+void csdr_iirfilt_rrrf_execute_block(csdr_iirfilt_rrrf q, const float *x, unsigned n, float *y)
+{
+    API_BEGIN
+    if (!n) return;
+    q->ctx.use();
+    const float *xd = (const float *)q->st.to_dev(q->ctx, x, (size_t)n * sizeof(float));
+    float *yd = (float *)q->st.out_dev(y, (size_t)n * sizeof(float));
+    q->f.run(q->ctx, xd, 0, yd, 0, (int)n);
+    q->st.finish(q->ctx, y, yd, (size_t)n * sizeof(float));
+    API_END_VOID
+}
+
+// ---------------------------------------------------------------- firdecim_rrrf
+csdr_firdecim csdr_firdecim_rrrf_create_kaiser(unsigned M, unsigned m, float as)
+{
+    API_BEGIN
+    if (M < 1 || M > 4096) throw CudaError{"firdecim_rrrf_create_kaiser: decimation factor must be in [1, 4096]"};
+    if (m < 1 || (size_t)2 * M * m + 1 > 40000) throw CudaError{"firdecim_rrrf_create_kaiser: filter too long"};
+    std::unique_ptr<csdr_firdecim_s> q(new csdr_firdecim_s());
+    q->d.init(q->ctx, M, m, as, 1);
+    return q.release();
+    API_END(nullptr)
+}
+void csdr_firdecim_rrrf_destroy(csdr_firdecim q) { delete q; }
+void csdr_firdecim_rrrf_print(csdr_firdecim q) { printf("firdecim_rrrf: M = %u, %d taps\n", q->d.M, q->d.Lh); }
+void csdr_firdecim_rrrf_execute_block(csdr_firdecim q, const float *x, unsigned n, float *y)
+{
+    API_BEGIN
+    if (!n) return;
+    q->ctx.use();
+    const size_t nin = (size_t)n * q->d.M;
+    if (nin > 0x7fffffffULL) throw CudaError{"firdecim_rrrf_execute_block: block too large"};
+    long long zs = 0;
+    float *slot = q->d.input_slot(q->ctx, (int)nin, &zs);
+    CK(cudaMemcpyAsync(slot, x, nin * sizeof(float), cudaMemcpyDefault, q->ctx.stream));
+    float *yd = (float *)q->st.out_dev(y, (size_t)n * sizeof(float));
+    q->d.run(q->ctx, (int)nin, yd, 0);
+    q->st.finish(q->ctx, y, yd, (size_t)n * sizeof(float));
     API_END_VOID
 }
 

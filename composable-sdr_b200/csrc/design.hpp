@@ -11,6 +11,7 @@
 #include <cstdint>
 #include <cstring>
 #include <vector>
+#include <complex>
 #include <algorithm>
 
 namespace csdr { namespace design {
@@ -147,6 +148,57 @@ inline float firpfbch_rotation(unsigned C)
     off = off * 2.0f;
     off = off * (float)kPi;
     return -off;
+}
+
+// ---- iirfilt_rrrf_create_prototype: Butterworth low-pass as second-order sections ---------------------
+// liquid_iirdes for (LIQUID_IIRDES_BUTTER, LOWPASS, SOS), all in float32 like liquid: analog poles on the unit
+// circle, pre-warp m = tan(pi fc), bilinear map z = (1 + m s) / (1 - m s) with all zeros at z = -1, one section
+// per conjugate pole pair (a real pole last), the gain spread evenly over the sections' numerators.
+// Reference: iirfiltCreate (Liquid.chs:629-633); wbFMDemodulator uses order 2, fc = 5000 / quadRate.
+struct Sos { float b[3], a[3]; };
+inline std::vector<Sos> butter_lowpass_sos(unsigned order, float fc)
+{
+    typedef std::complex<float> cf32;
+    const unsigned r = order % 2, L = (order - r) / 2;
+    std::vector<cf32> pd;
+    const float m = std::tan((float)kPi * fc);
+    cf32 G(1.0f, 0.0f);
+    auto map_pole = [&](cf32 pa) {
+        const cf32 pm = pa * m, one(1.0f, 0.0f);
+        const cf32 z = (one + pm) / (one - pm);
+        pd.push_back(z);
+        G *= (one - z) / cf32(2.0f, 0.0f);          // (1 - p) / (1 - zero), zero = -1
+    };
+    for (unsigned i = 0; i < L; i++) {
+        const float th = (float)(2 * (i + 1) + order - 1) * (float)kPi / (float)(2 * order);
+        map_pole(cf32(std::cos(th), std::sin(th)));
+        map_pole(cf32(std::cos(th), -std::sin(th)));
+    }
+    if (r) map_pole(cf32(-1.0f, 0.0f));
+    const float k = std::pow(G.real(), 1.0f / (float)(L + r));
+    std::vector<Sos> out;
+    for (unsigned i = 0; i < L; i++) {
+        const cf32 p0 = -pd[2 * i], p1 = -pd[2 * i + 1];
+        Sos s;
+        s.a[0] = 1.0f; s.a[1] = (p0 + p1).real(); s.a[2] = (p0 * p1).real();
+        s.b[0] = k; s.b[1] = 2.0f * k; s.b[2] = k;
+        out.push_back(s);
+    }
+    if (r) {
+        Sos s;
+        s.a[0] = 1.0f; s.a[1] = -pd[order - 1].real(); s.a[2] = 0.0f;
+        s.b[0] = k; s.b[1] = k; s.b[2] = 0.0f;
+        out.push_back(s);
+    }
+    return out;
+}
+
+// ---- firdecim_rrrf_create_kaiser: 2 M m + 1 taps, fc = 0.5 / M, stored reversed (firdecim_create) ----------
+inline std::vector<float> design_firdecim(unsigned M, unsigned m, float As)
+{
+    std::vector<float> h = firdes_kaiser(2 * M * m + 1, 0.5f / (float)M, As, 0.0f);
+    std::reverse(h.begin(), h.end());
+    return h;
 }
 
 // ---- agc: smallest gain for which rssi = -20 log10(g) is NOT above the threshold ---------------------

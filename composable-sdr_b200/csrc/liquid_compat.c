@@ -61,3 +61,18 @@ void *ampmodem_create(float mod_index, int type, int suppressed) { return csdr_a
 void ampmodem_destroy(void *q) { csdr_ampmodem_destroy((csdr_ampmodem)q); }
 void ampmodem_print(void *q) { csdr_ampmodem_print((csdr_ampmodem)q); }
 void ampmodem_demodulate_block(void *q, cf *r, unsigned n, float *m) { csdr_ampmodem_demodulate_block((csdr_ampmodem)q, r, n, m); }
+
+/* Liquid.chs:612-627 */
+void *iirfilt_rrrf_create_prototype(int ftype, int btype, int format, unsigned order, float fc, float f0, float ap, float as)
+{
+    return csdr_iirfilt_rrrf_create_prototype(ftype, btype, format, order, fc, f0, ap, as);
+}
+void iirfilt_rrrf_destroy(void *q) { csdr_iirfilt_rrrf_destroy((csdr_iirfilt_rrrf)q); }
+void iirfilt_rrrf_print(void *q) { csdr_iirfilt_rrrf_print((csdr_iirfilt_rrrf)q); }
+void iirfilt_rrrf_execute_block(void *q, float *x, unsigned n, float *y) { csdr_iirfilt_rrrf_execute_block((csdr_iirfilt_rrrf)q, x, n, y); }
+
+/* Liquid.chs:473-485 */
+void *firdecim_rrrf_create_kaiser(unsigned M, unsigned m, float as) { return csdr_firdecim_rrrf_create_kaiser(M, m, as); }
+void firdecim_rrrf_destroy(void *q) { csdr_firdecim_rrrf_destroy((csdr_firdecim)q); }
+void firdecim_rrrf_print(void *q) { csdr_firdecim_rrrf_print((csdr_firdecim)q); }
+void firdecim_rrrf_execute_block(void *q, float *x, unsigned n, float *y) { csdr_firdecim_rrrf_execute_block((csdr_firdecim)q, x, n, y); }

@@ -142,12 +142,34 @@ void     csdr_ampmodem_destroy(csdr_ampmodem q);
 void     csdr_ampmodem_print(csdr_ampmodem q);
 void     csdr_ampmodem_demodulate_block(csdr_ampmodem q, const csdr_cf32 *r, unsigned n, float *m);
 
+/* ---------------------------------------------------------------- iirfilt_rrrf (de-emphasis) ---- *
+ * replaces Liquid.chs:610-627 (iirfilt_rrrf_create_prototype/_print/_execute_block/_destroy); the reference calls
+ * create_prototype 0 0 0 n fc f0 ap as = Butterworth, low-pass, second-order sections (Liquid.chs:629-633), the only
+ * family implemented (anything else: NULL + csdr_last_error). */
+typedef struct csdr_iirfilt_rrrf_s *csdr_iirfilt_rrrf;
+csdr_iirfilt_rrrf csdr_iirfilt_rrrf_create_prototype(int ftype, int btype, int format, unsigned order, float fc, float f0,
+                                                     float ap, float as);
+void     csdr_iirfilt_rrrf_destroy(csdr_iirfilt_rrrf q);
+void     csdr_iirfilt_rrrf_print(csdr_iirfilt_rrrf q);
+void     csdr_iirfilt_rrrf_execute_block(csdr_iirfilt_rrrf q, const float *x, unsigned n, float *y);
+/* extension: the sections' coefficients, b and a as [sections][3]; returns the number of sections */
+unsigned csdr_iirfilt_rrrf_coefficients(csdr_iirfilt_rrrf q, float *b, float *a);
+
+/* ---------------------------------------------------------------- firdecim_rrrf (output decimator) ---- *
+ * replaces Liquid.chs:471-485 (firdecim_rrrf_create_kaiser/_print/_execute_block/_destroy).
+ * execute_block: n blocks of M input samples -> n output samples (Liquid.chs:497-500). */
+typedef struct csdr_firdecim_s *csdr_firdecim;
+csdr_firdecim csdr_firdecim_rrrf_create_kaiser(unsigned M, unsigned m, float as);
+void     csdr_firdecim_rrrf_destroy(csdr_firdecim q);
+void     csdr_firdecim_rrrf_print(csdr_firdecim q);
+void     csdr_firdecim_rrrf_execute_block(csdr_firdecim q, const float *x, unsigned n, float *y);
+
 /* ---------------------------------------------------------------- fused chain ---- *
  * The whole of sdrProcess (apps/SoapySDR.hs:181-283) behind one handle:
  *   offset mix -> msresamp(bw/sr, 60 dB) -> dcBlocker(5e-4) -> [firpfbch(C,7,80) ->] C x (agc -> demod) [-> mix]
  * One handle = `nstreams` independent streams with identical parameters (the reference would run one process
  * per stream). */
-enum { CSDR_DEMOD_NONE = 0, CSDR_DEMOD_NBFM = 1, CSDR_DEMOD_AM = 2 };
+enum { CSDR_DEMOD_NONE = 0, CSDR_DEMOD_NBFM = 1, CSDR_DEMOD_AM = 2, CSDR_DEMOD_WBFM = 3 };
 typedef struct {
     double   samplerate;     /* -s */
     double   offset_hz;      /* --offset */
@@ -159,6 +181,8 @@ typedef struct {
     int      mix;            /* -m */
     unsigned nstreams;       /* 0/1 = single stream */
     int      device;         /* CUDA device ordinal, -1 = current */
+    unsigned decim;          /* DeWBFM decim: wbFMDemodulator (kf 0.6, de-emphasis at 5 kHz of the quadrature rate = -b,
+                                firdecim by decim; Liquid.chs:652-656, SoapySDR.hs:253-260); 0/1 = no decimation */
 } csdr_chain_cfg;
 typedef struct csdr_chain_s *csdr_chain;
 csdr_chain csdr_chain_create(const csdr_chain_cfg *cfg);

@@ -717,6 +717,126 @@ void orc_hs_firpfbch_chan(orc_firpfbch fb, orc_nco nco, unsigned C, const orc_cf
     free(dx); free(tmp);
 }
 
+/* ==========================================================================================
+ * iirfilt_rrrf from a Butterworth prototype, second-order sections -- liquid src/filter/src/iirdes.c
+ * (liquid_iirdes, butter_azpkf, bilinear_zpkf, iirdes_dzpk2sosf), iirfilt.c (create_sos / execute_sos) and
+ * iirfiltsos.c (direct form II).  Reference: iirfiltCreate = iirfilt_rrrf_create_prototype 0 0 0 n fc f0 ap as
+ * (Liquid.chs:629-633: Butterworth, low-pass, SOS); wbFMDemodulator uses n = 2, fc = 5000/quadRate
+ * (Liquid.chs:653-656).  Only that family (ftype 0, btype 0, format 0) is restated.   Confidence M.
+ * ========================================================================================== */
+typedef struct { float re, im; } cplx;
+static cplx c_mk(float re, float im) { cplx z; z.re = re; z.im = im; return z; }
+static cplx c_add(cplx a, cplx b) { return c_mk(a.re + b.re, a.im + b.im); }
+static cplx c_sub(cplx a, cplx b) { return c_mk(a.re - b.re, a.im - b.im); }
+static cplx c_mul(cplx a, cplx b) { return c_mk(a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re); }
+static cplx c_div(cplx a, cplx b)
+{
+    float d = b.re * b.re + b.im * b.im;
+    return c_mk((a.re * b.re + a.im * b.im) / d, (a.im * b.re - a.re * b.im) / d);
+}
+#define ORC_IIR_MAX_SOS 8
+struct orc_iirfilt_rrrf_s { unsigned nsos; float b[ORC_IIR_MAX_SOS][3], a[ORC_IIR_MAX_SOS][3], v[ORC_IIR_MAX_SOS][3]; };
+
+orc_iirfilt_rrrf orc_iirfilt_rrrf_create_prototype(int ftype, int btype, int format, unsigned n, float fc, float f0,
+                                                   float Ap, float As)
+{
+    (void)f0; (void)Ap; (void)As;
+    if (ftype != 0 || btype != 0 || format != 0 || n == 0 || n > 2 * ORC_IIR_MAX_SOS || !(fc > 0.0f && fc < 0.5f)) return NULL;
+    unsigned r = n % 2, L = (n - r) / 2, i, k = 0;
+    /* butter_azpkf: poles on the unit circle of the left half plane, in conjugate pairs; no zeros; gain 1 */
+    cplx pa[2 * ORC_IIR_MAX_SOS], pd[2 * ORC_IIR_MAX_SOS], zd[2 * ORC_IIR_MAX_SOS];
+    for (i = 0; i < L; i++) {
+        float theta = (float)(2 * (i + 1) + n - 1) * (float)M_PI / (float)(2 * n);
+        pa[k++] = c_mk(cosf(theta), sinf(theta));
+        pa[k++] = c_mk(cosf(theta), -sinf(theta));
+    }
+    if (r) pa[k++] = c_mk(-1.0f, 0.0f);
+    /* iirdes_freqprewarp (low-pass): m = tan(pi fc);  bilinear_zpkf: z = (1 + m s)/(1 - m s), zeros at -1 */
+    float m = tanf((float)M_PI * fc);
+    cplx G = c_mk(1.0f, 0.0f);
+    for (i = 0; i < n; i++) {
+        cplx pm = c_mk(pa[i].re * m, pa[i].im * m);
+        zd[i] = c_mk(-1.0f, 0.0f);
+        pd[i] = c_div(c_add(c_mk(1.0f, 0.0f), pm), c_sub(c_mk(1.0f, 0.0f), pm));
+        G = c_mul(G, c_div(c_sub(c_mk(1.0f, 0.0f), pd[i]), c_sub(c_mk(1.0f, 0.0f), zd[i])));
+    }
+    float kd = G.re;
+    /* iirdes_dzpk2sosf: one section per conjugate pair (pairs already adjacent), a real pole last; the gain is
+     * spread evenly over the sections' feed-forward coefficients */
+    orc_iirfilt_rrrf q = (orc_iirfilt_rrrf)calloc(1, sizeof(*q));
+    q->nsos = L + r;
+    float kk = powf(kd, 1.0f / (float)(L + r));
+    for (i = 0; i < L; i++) {
+        cplx p0 = c_mk(-pd[2 * i].re, -pd[2 * i].im), p1 = c_mk(-pd[2 * i + 1].re, -pd[2 * i + 1].im);
+        cplx z0 = c_mk(-zd[2 * i].re, -zd[2 * i].im), z1 = c_mk(-zd[2 * i + 1].re, -zd[2 * i + 1].im);
+        q->a[i][0] = 1.0f; q->a[i][1] = c_add(p0, p1).re; q->a[i][2] = c_mul(p0, p1).re;
+        q->b[i][0] = 1.0f; q->b[i][1] = c_add(z0, z1).re; q->b[i][2] = c_mul(z0, z1).re;
+    }
+    if (r) {
+        q->a[L][0] = 1.0f; q->a[L][1] = -pd[n - 1].re; q->a[L][2] = 0.0f;
+        q->b[L][0] = 1.0f; q->b[L][1] = -zd[n - 1].re; q->b[L][2] = 0.0f;
+    }
+    for (i = 0; i < L + r; i++) { q->b[i][0] *= kk; q->b[i][1] *= kk; q->b[i][2] *= kk; }
+    return q;
+}
+void orc_iirfilt_rrrf_destroy(orc_iirfilt_rrrf q) { free(q); }
+unsigned orc_iirfilt_rrrf_coeffs(orc_iirfilt_rrrf q, float *b, float *a)
+{
+    for (unsigned i = 0; i < q->nsos; i++) for (int j = 0; j < 3; j++) { b[3 * i + j] = q->b[i][j]; a[3 * i + j] = q->a[i][j]; }
+    return q->nsos;
+}
+void orc_iirfilt_rrrf_execute_block(orc_iirfilt_rrrf q, const float *x, unsigned n, float *y)
+{
+    for (unsigned i = 0; i < n; i++) {
+        float t = x[i];
+        for (unsigned s = 0; s < q->nsos; s++) {
+            /* iirfiltsos_execute_df2 */
+            float *v = q->v[s], *b = q->b[s], *a = q->a[s];
+            v[2] = v[1]; v[1] = v[0];
+            v[0] = t - a[1] * v[1] - a[2] * v[2];
+            t = b[0] * v[0] + b[1] * v[1] + b[2] * v[2];
+        }
+        y[i] = t;
+    }
+}
+
+/* ==========================================================================================
+ * firdecim_rrrf -- liquid src/filter/src/firdecim.c.  create_kaiser(M, m, As): h_len = 2 M m + 1,
+ * fc = 0.5/M, Kaiser prototype; execute: push the M samples of a block, the output is the dot product taken
+ * right after the FIRST of them went in.  Reference: firdecimCreate m = firdecim_rrrf_create_kaiser m 10 60
+ * (Liquid.chs:487-492); firDecim runs length `div` m blocks per array (Liquid.chs:497-500).   Confidence M.
+ * ========================================================================================== */
+struct orc_firdecim_s { unsigned M, h_len; float *h, *w; };
+orc_firdecim orc_firdecim_rrrf_create_kaiser(unsigned M, unsigned m, float As)
+{
+    if (M < 1 || m < 1) return NULL;
+    orc_firdecim q = (orc_firdecim)calloc(1, sizeof(*q));
+    q->M = M; q->h_len = 2 * M * m + 1;
+    float *hf = (float *)calloc(q->h_len, sizeof(float));
+    orc_firdes_kaiser(q->h_len, 0.5f / (float)M, As, 0.0f, hf);
+    q->h = (float *)calloc(q->h_len, sizeof(float));
+    for (unsigned i = 0; i < q->h_len; i++) q->h[i] = hf[q->h_len - i - 1];   /* firdecim_create: reversed */
+    q->w = (float *)calloc(q->h_len, sizeof(float));                            /* window, oldest first */
+    free(hf);
+    return q;
+}
+void orc_firdecim_rrrf_destroy(orc_firdecim q) { if (q) { free(q->h); free(q->w); free(q); } }
+const float *orc_firdecim_rrrf_taps(orc_firdecim q, unsigned *h_len) { *h_len = q->h_len; return q->h; }
+void orc_firdecim_rrrf_execute_block(orc_firdecim q, const float *x, unsigned n, float *y)
+{
+    for (unsigned k = 0; k < n; k++) {
+        for (unsigned i = 0; i < q->M; i++) {
+            memmove(q->w, q->w + 1, (q->h_len - 1) * sizeof(float));
+            q->w[q->h_len - 1] = x[(size_t)k * q->M + i];
+            if (i == 0) {
+                float r = 0.0f;
+                for (unsigned j = 0; j < q->h_len; j++) r += q->h[j] * q->w[j];
+                y[k] = r;
+            }
+        }
+    }
+}
+
 /* ============================================================================================
  * The whole chain, apps/SoapySDR.hs:181-283.  Order: offset mix -> resampler -> dcBlocker ->
  * [channelizer ->] per-channel (agc -> demod) [-> mix sum].  `compact` only re-chunks, so the chain is
@@ -729,6 +849,7 @@ struct orc_chain_s {
     orc_iirfilt dc;
     orc_firpfbch fb; orc_nco fb_nco;
     orc_agc *agc; orc_freqdem *fm; orc_ampmodem *am;
+    orc_iirfilt_rrrf *deemph; orc_firdecim *dec; float *dec_left; unsigned *dec_fill;   /* DeWBFM tail per channel */
     orc_cf32 *frame_buf; size_t frame_fill;          /* < C leftover samples */
 };
 
@@ -757,6 +878,13 @@ orc_chain orc_chain_create(const orc_chain_cfg *cfg)
     q->agc = (orc_agc *)calloc(q->C, sizeof(orc_agc));
     q->fm = (orc_freqdem *)calloc(q->C, sizeof(orc_freqdem));
     q->am = (orc_ampmodem *)calloc(q->C, sizeof(orc_ampmodem));
+    q->deemph = (orc_iirfilt_rrrf *)calloc(q->C, sizeof(orc_iirfilt_rrrf));
+    q->dec = (orc_firdecim *)calloc(q->C, sizeof(orc_firdecim));
+    if (cfg->demod == 3) {
+        q->cfg.decim = cfg->decim ? cfg->decim : 1;
+        q->dec_left = (float *)calloc((size_t)q->C * q->cfg.decim, sizeof(float));
+        q->dec_fill = (unsigned *)calloc(q->C, sizeof(unsigned));
+    }
     for (unsigned c = 0; c < q->C; c++) {
         if (cfg->agc_thresh_db != 0.0f) {
             /* agcCreate, Liquid.chs:707-717 */
@@ -769,6 +897,14 @@ orc_chain orc_chain_create(const orc_chain_cfg *cfg)
         }
         if (cfg->demod == 1) q->fm[c] = orc_freqdem_create(cfg->kf);
         if (cfg->demod == 2) q->am[c] = orc_ampmodem_create(0.8f, 0, 0);
+        if (cfg->demod == 3) {
+            /* wbFMDemodulator quadRate decim (Liquid.chs:652-656), quadRate = outBW (SoapySDR.hs:257):
+             * firDecimator decim . iirFilter 2 (5000/quadRate) 0 10 10 . fmDemodulator 0.6 */
+            double quad = cfg->bandwidth_hz != 0.0 ? cfg->bandwidth_hz : cfg->samplerate;
+            q->fm[c] = orc_freqdem_create(0.6f);
+            q->deemph[c] = orc_iirfilt_rrrf_create_prototype(0, 0, 0, 2, (float)(5000.0 / quad), 0.0f, 10.0f, 10.0f);
+            q->dec[c] = orc_firdecim_rrrf_create_kaiser(q->cfg.decim, 10, 60.0f);
+        }
     }
     return q;
 }
@@ -783,19 +919,38 @@ void orc_chain_destroy(orc_chain q)
         if (q->agc[c]) orc_agc_crcf_destroy(q->agc[c]);
         if (q->fm[c]) orc_freqdem_destroy(q->fm[c]);
         if (q->am[c]) orc_ampmodem_destroy(q->am[c]);
+        if (q->deemph[c]) orc_iirfilt_rrrf_destroy(q->deemph[c]);
+        if (q->dec[c]) orc_firdecim_rrrf_destroy(q->dec[c]);
     }
+    free(q->deemph); free(q->dec); free(q->dec_left); free(q->dec_fill);
     free(q->agc); free(q->fm); free(q->am); free(q->frame_buf); free(q);
 }
 unsigned orc_chain_num_outputs(orc_chain q) { return q->nout; }
 
-/* per-channel demod = (fm|am|id) . agc  (SoapySDR.hs:236-272) */
-static void chain_demod(orc_chain q, unsigned c, const orc_cf32 *x, unsigned n, orc_cf32 *tmp, void *out)
+/* per-channel demod = (fm|am|wbfm|id) . agc  (SoapySDR.hs:236-272); returns the number of samples written.
+ * DeWBFM restated as a stream: the decimator consumes whole blocks of `decim` samples as they become available
+ * (the reference drops the remainder of every array, Liquid.chs:497-500, which ties its output to the chunking). */
+static size_t chain_demod(orc_chain q, unsigned c, const orc_cf32 *x, unsigned n, orc_cf32 *tmp, void *out)
 {
     const orc_cf32 *s = x;
     if (q->agc[c]) { orc_hs_agc_execute_block(q->agc[c], x, n, tmp); s = tmp; }
     if (q->cfg.demod == 1)      orc_freqdem_demodulate_block(q->fm[c], s, n, (float *)out);
     else if (q->cfg.demod == 2) orc_ampmodem_demodulate_block(q->am[c], s, n, (float *)out);
+    else if (q->cfg.demod == 3) {
+        const unsigned M = q->cfg.decim, fill = q->dec_fill[c];
+        float *buf = (float *)malloc(((size_t)fill + n + 1) * sizeof(float));
+        memcpy(buf, q->dec_left + (size_t)c * M, fill * sizeof(float));
+        orc_freqdem_demodulate_block(q->fm[c], s, n, buf + fill);
+        orc_iirfilt_rrrf_execute_block(q->deemph[c], buf + fill, n, buf + fill);
+        const unsigned tot = fill + n, nb = tot / M;
+        orc_firdecim_rrrf_execute_block(q->dec[c], buf, nb, (float *)out);
+        q->dec_fill[c] = tot - nb * M;
+        memcpy(q->dec_left + (size_t)c * M, buf + (size_t)nb * M, q->dec_fill[c] * sizeof(float));
+        free(buf);
+        return nb;
+    }
     else                        memcpy(out, s, n * sizeof(orc_cf32));
+    return n;
 }
 
 int orc_chain_process(orc_chain q, const orc_cf32 *x, size_t nx, void *const *outs, size_t cap, size_t *n_out)
@@ -825,9 +980,8 @@ int orc_chain_process(orc_chain q, const orc_cf32 *x, size_t nx, void *const *ou
         if (C == 1) {
             if (produced + nr > cap) { rc = -1; break; }
             orc_cf32 *tmp = (orc_cf32 *)malloc((nr ? nr : 1) * sizeof(orc_cf32));
-            chain_demod(q, 0, r, nr, tmp, (char *)outs[0] + produced * esz);
+            produced += chain_demod(q, 0, r, nr, tmp, (char *)outs[0] + produced * esz);
             free(tmp);
-            produced += nr;
         } else {
             /* assemble whole frames: leftover + new */
             size_t tot = q->frame_fill + nr, nf = tot / C;
@@ -840,24 +994,25 @@ int orc_chain_process(orc_chain q, const orc_cf32 *x, size_t nx, void *const *ou
                 orc_cf32 *tmp = (orc_cf32 *)malloc(nf * sizeof(orc_cf32));
                 orc_hs_firpfbch_chan(q->fb, q->fb_nco, C, buf, (unsigned)(nf * C), ch);
                 void *dem = malloc(nf * sizeof(orc_cf32));
+                size_t nd = 0;                       /* samples per channel after the demodulator (< nf for DeWBFM) */
                 for (unsigned c = 0; c < C; c++) {
                     if (!q->cfg.mix) {
-                        chain_demod(q, c, ch + nf * c, (unsigned)nf, tmp, (char *)outs[c] + produced * esz);
+                        nd = chain_demod(q, c, ch + nf * c, (unsigned)nf, tmp, (char *)outs[c] + produced * esz);
                     } else {
                         /* mix = foldl1 (zipWith (+)) over channels 1..C (Trans.hs:119-122) */
-                        chain_demod(q, c, ch + nf * c, (unsigned)nf, tmp, dem);
+                        nd = chain_demod(q, c, ch + nf * c, (unsigned)nf, tmp, dem);
                         char *o = (char *)outs[0] + produced * esz;
-                        if (c == 0) memcpy(o, dem, nf * esz);
-                        else if (q->cfg.demod) { float *of = (float *)o, *df = (float *)dem; for (size_t i = 0; i < nf; i++) of[i] = of[i] + df[i]; }
-                        else { orc_cf32 *oc = (orc_cf32 *)o, *dc = (orc_cf32 *)dem; for (size_t i = 0; i < nf; i++) { oc[i].re = oc[i].re + dc[i].re; oc[i].im = oc[i].im + dc[i].im; } }
+                        if (c == 0) memcpy(o, dem, nd * esz);
+                        else if (q->cfg.demod) { float *of = (float *)o, *df = (float *)dem; for (size_t i = 0; i < nd; i++) of[i] = of[i] + df[i]; }
+                        else { orc_cf32 *oc = (orc_cf32 *)o, *dc = (orc_cf32 *)dem; for (size_t i = 0; i < nd; i++) { oc[i].re = oc[i].re + dc[i].re; oc[i].im = oc[i].im + dc[i].im; } }
                     }
                 }
                 free(dem); free(ch); free(tmp);
+                produced += nd;
             }
             q->frame_fill = tot - nf * C;
             memcpy(q->frame_buf, buf + nf * C, q->frame_fill * sizeof(orc_cf32));
             free(buf);
-            produced += nf;
         }
     }
     free(a); free(b);

@@ -118,6 +118,21 @@ orc_ampmodem orc_ampmodem_create(float mod_index, int type, int suppressed_carri
 void     orc_ampmodem_destroy(orc_ampmodem q);
 void     orc_ampmodem_demodulate_block(orc_ampmodem q, const orc_cf32 *r, unsigned n, float *m);
 
+/* ---- iirfilt_rrrf (Butterworth low-pass prototype in second-order sections), Liquid.chs:610-633 ---- */
+typedef struct orc_iirfilt_rrrf_s *orc_iirfilt_rrrf;
+orc_iirfilt_rrrf orc_iirfilt_rrrf_create_prototype(int ftype, int btype, int format, unsigned n, float fc, float f0,
+                                                   float Ap, float As);   /* NULL unless ftype = btype = format = 0 */
+void     orc_iirfilt_rrrf_destroy(orc_iirfilt_rrrf q);
+unsigned orc_iirfilt_rrrf_coeffs(orc_iirfilt_rrrf q, float *b, float *a);   /* [nsos][3] each; returns nsos */
+void     orc_iirfilt_rrrf_execute_block(orc_iirfilt_rrrf q, const float *x, unsigned n, float *y);
+
+/* ---- firdecim_rrrf, Liquid.chs:471-503 ---- */
+typedef struct orc_firdecim_s *orc_firdecim;
+orc_firdecim orc_firdecim_rrrf_create_kaiser(unsigned M, unsigned m, float As);
+void     orc_firdecim_rrrf_destroy(orc_firdecim q);
+const float *orc_firdecim_rrrf_taps(orc_firdecim q, unsigned *h_len);
+void     orc_firdecim_rrrf_execute_block(orc_firdecim q, const float *x, unsigned n, float *y);   /* n blocks of M -> n */
+
 /* ---- Haskell-side glue restated (reference src/ComposableSDR/Liquid.chs, Trans.hs) ---- */
 /* agcExecuteBlock, Liquid.chs:693-705: per-sample execute + squelch gate (status != 3 -> 0) */
 void     orc_hs_agc_execute_block(orc_agc q, const orc_cf32 *x, unsigned n, orc_cf32 *y);
@@ -129,11 +144,12 @@ typedef struct {
     double   samplerate;      /* -s   */
     double   offset_hz;       /* --offset (Float in the reference) */
     double   bandwidth_hz;    /* -b, 0 = no resampler */
-    int      demod;           /* 0 DeNo, 1 DeNBFM kf, 2 DeAM */
+    int      demod;           /* 0 DeNo, 1 DeNBFM kf, 2 DeAM, 3 DeWBFM decim (kf 0.6, de-emphasis, decimator) */
     float    kf;
     float    agc_thresh_db;   /* -a, 0 = no AGC */
     unsigned channels;        /* -c */
     int      mix;             /* -m */
+    unsigned decim;           /* DeWBFM: output decimation */
 } orc_chain_cfg;
 typedef struct orc_chain_s *orc_chain;
 orc_chain orc_chain_create(const orc_chain_cfg *cfg);

@@ -26,7 +26,7 @@ def build(force=False):
 class ChainCfg(C.Structure):
     _fields_ = [("samplerate", C.c_double), ("offset_hz", C.c_double), ("bandwidth_hz", C.c_double),
                 ("demod", C.c_int), ("kf", C.c_float), ("agc_thresh_db", C.c_float),
-                ("channels", C.c_uint), ("mix", C.c_int)]
+                ("channels", C.c_uint), ("mix", C.c_int), ("decim", C.c_uint)]
 
 
 _lib = None
@@ -57,6 +57,11 @@ def _declare(L):
         "orc_nco_crcf_step": (None, [vp]),
         "orc_nco_crcf_mix_block_down": (None, [vp, vp, vp, u]), "orc_nco_crcf_mix_block_up": (None, [vp, vp, vp, u]),
         "orc_nco_sintab": (C.POINTER(C.c_float), []),
+        "orc_iirfilt_rrrf_create_prototype": (vp, [i, i, i, u, f, f, f, f]), "orc_iirfilt_rrrf_destroy": (None, [vp]),
+        "orc_iirfilt_rrrf_coeffs": (u, [vp, vp, vp]), "orc_iirfilt_rrrf_execute_block": (None, [vp, vp, u, vp]),
+        "orc_firdecim_rrrf_create_kaiser": (vp, [u, u, f]), "orc_firdecim_rrrf_destroy": (None, [vp]),
+        "orc_firdecim_rrrf_taps": (C.POINTER(C.c_float), [vp, C.POINTER(u)]),
+        "orc_firdecim_rrrf_execute_block": (None, [vp, vp, u, vp]),
         "orc_msresamp_crcf_create": (vp, [f, f]), "orc_msresamp_crcf_destroy": (None, [vp]),
         "orc_msresamp_crcf_get_rate": (f, [vp]),
         "orc_msresamp_crcf_execute": (None, [vp, vp, u, vp, C.POINTER(u)]),
@@ -335,16 +340,75 @@ class AmpModem:
         return y
 
 
-DEMOD_NO, DEMOD_NBFM, DEMOD_AM = 0, 1, 2
+DEMOD_NO, DEMOD_NBFM, DEMOD_AM, DEMOD_WBFM = 0, 1, 2, 3
+
+
+class IirFiltRRRF:
+    """liquid iirfilt_rrrf_create_prototype, Butterworth low-pass in second-order sections (reference: iirFilter,
+    Liquid.chs:629-650)."""
+
+    def __init__(self, order, fc, f0=0.0, ap=10.0, as_=10.0):
+        self.L = lib()
+        self.h = self.L.orc_iirfilt_rrrf_create_prototype(0, 0, 0, order, fc, f0, ap, as_)
+        if not self.h:
+            raise ValueError("iirfilt_rrrf_create_prototype: unsupported prototype")
+
+    def close(self):
+        if self.h:
+            self.L.orc_iirfilt_rrrf_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def coeffs(self):
+        b = np.zeros(24, np.float32)
+        a = np.zeros(24, np.float32)
+        n = self.L.orc_iirfilt_rrrf_coeffs(self.h, b.ctypes.data, a.ctypes.data)
+        return b[:3 * n].reshape(n, 3), a[:3 * n].reshape(n, 3)
+
+    def execute(self, x):
+        x = np.ascontiguousarray(x, np.float32)
+        y = np.empty_like(x)
+        self.L.orc_iirfilt_rrrf_execute_block(self.h, x.ctypes.data, x.size, y.ctypes.data)
+        return y
+
+
+class FirDecim:
+    """liquid firdecim_rrrf_create_kaiser (reference: firDecimator, Liquid.chs:487-503)."""
+
+    def __init__(self, M, m=10, As=60.0):
+        self.L = lib()
+        self.M = int(M)
+        self.h = self.L.orc_firdecim_rrrf_create_kaiser(self.M, m, As)
+
+    def close(self):
+        if self.h:
+            self.L.orc_firdecim_rrrf_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def taps(self):
+        n = C.c_uint(0)
+        p = self.L.orc_firdecim_rrrf_taps(self.h, C.byref(n))
+        return np.ctypeslib.as_array(p, (n.value,)).copy()
+
+    def execute(self, x):
+        """whole blocks of M samples only (len(x) // M outputs), like firDecim (Liquid.chs:497-500)"""
+        x = np.ascontiguousarray(x, np.float32)
+        n = x.size // self.M
+        y = np.empty(n, np.float32)
+        self.L.orc_firdecim_rrrf_execute_block(self.h, x.ctypes.data, n, y.ctypes.data)
+        return y
 
 
 class Chain:
     """sdrProcess (apps/SoapySDR.hs:181-283) as one sequential object."""
 
     def __init__(self, samplerate, offset_hz=0.0, bandwidth_hz=0.0, demod=DEMOD_NO, kf=0.3, agc_thresh_db=0.0,
-                 channels=1, mix=False, fast=False):
+                 channels=1, mix=False, fast=False, decim=1):
         self.L = lib(fast)
-        self.cfg = ChainCfg(samplerate, offset_hz, bandwidth_hz, demod, kf, agc_thresh_db, channels, int(mix))
+        self.cfg = ChainCfg(samplerate, offset_hz, bandwidth_hz, demod, kf, agc_thresh_db, channels, int(mix), int(decim))
         self.h = self.L.orc_chain_create(C.byref(self.cfg))
         self.nout = self.L.orc_chain_num_outputs(self.h)
         self.dtype = np.float32 if demod else np.complex64

@@ -8,6 +8,7 @@
 #include "interp.cuh"
 #include "backend.cuh"
 #include "pfb.cuh"
+#include "wbfm.cuh"
 #include <vector>
 #include <cstdio>
 
@@ -255,6 +256,51 @@ extern "C" long long emu_pfb(int M, int kind, const float2 *x, long long nf_tota
         pos += nf;
     }
     return pos;
+}
+
+// wbFMDemodulator's tail (de-emphasis sections + firdecim), `lanes` independent sequences x[lane][n_total] fed in
+// chunks; y is [lanes][n_total / M].  order/fc: the Butterworth prototype.  Returns outputs per lane.
+extern "C" long long emu_wbfm_tail(int lanes, unsigned order, float fc, unsigned M, const float *x, long long n_total,
+                                   const long long *chunks, int nchunks, float *y, float *b_out, float *a_out)
+{
+    std::vector<design::Sos> sos = design::butter_lowpass_sos(order, fc);
+    for (size_t i = 0; i < sos.size(); i++) for (int j = 0; j < 3; j++) { if (b_out) b_out[3 * i + j] = sos[i].b[j]; if (a_out) a_out[3 * i + j] = sos[i].a[j]; }
+    std::vector<float> h = design::design_firdecim(M, 10, 60.0f);
+    const int Lh = (int)h.size();
+    const long long hs = Lh - 1 + M, ycap = n_total / M;
+    std::vector<float> hist((size_t)hs * lanes, 0.0f);
+    std::vector<float2> state(sos.size() * lanes, make_float2(0, 0));
+    std::vector<double> qtab(sos.size() * 128);
+    for (size_t i = 0; i < sos.size(); i++) iir2_q_table(sos[i].a[1], sos[i].a[2], qtab.data() + i * 128);
+    EmuLaunch launch;
+    long long pos = 0, produced = 0; size_t fill = 0;
+    for (int c = 0; c < nchunks; c++) {
+        const int n = (int)chunks[c];
+        if (pos + n > n_total) return -1;
+        if (n == 0) continue;
+        const int head = Lh - 1 + (int)fill;
+        const long long zs = ((long long)head + n + 3) & ~3LL;
+        std::vector<float> z((size_t)zs * lanes, 0.0f);
+        launch(k_rows_copy, dim3((head + 63) / 64, lanes), dim3(64), 0, (const float *)hist.data(), hs, 0LL, z.data(), zs, 0LL, head);
+        for (size_t i = 0; i < sos.size(); i++) {
+            Iir2Params p{};
+            p.x = i ? z.data() + head : x + pos; p.x_stride = i ? zs : n_total; p.y = z.data() + head; p.y_stride = zs;
+            iir2_plan(p, sos[i].b, sos[i].a, n);
+            std::vector<double2> sz((size_t)p.nseg * lanes), si((size_t)p.nseg * lanes);
+            p.seg_z = sz.data(); p.seg_in = si.data(); p.Q = qtab.data() + i * 128; p.state = state.data() + i * lanes;
+            iir2_launch(launch, p, lanes);
+        }
+        const size_t tot = fill + (size_t)n;
+        const int nb = (int)(tot / M);
+        FirDecimParams fp{};
+        fp.z = z.data(); fp.z_stride = zs; fp.y = y + produced; fp.y_stride = ycap; fp.h = h.data(); fp.nout = nb; fp.M = (int)M; fp.Lh = Lh;
+        firdecim_launch(launch, fp, lanes, 3);
+        fill = tot - (size_t)nb * M;
+        const int keep = Lh - 1 + (int)fill;
+        launch(k_rows_copy, dim3((keep + 63) / 64, lanes), dim3(64), 0, (const float *)z.data(), zs, (long long)nb * M, hist.data(), hs, 0LL, keep);
+        pos += n; produced += nb;
+    }
+    return produced;
 }
 
 // ---- product-side filter design (design.hpp), exported so the CPU suite can compare it with the oracle ----

@@ -21,6 +21,9 @@ def load():
                                   C.POINTER(C.c_ulonglong), C.c_void_p]
         L.emu_pfb.restype = C.c_longlong
         L.emu_pfb.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_longlong, C.c_void_p, C.c_int, C.c_void_p]
+        L.emu_wbfm_tail.restype = C.c_longlong
+        L.emu_wbfm_tail.argtypes = [C.c_int, C.c_uint, C.c_float, C.c_uint, C.c_void_p, C.c_longlong, C.c_void_p, C.c_int,
+                                    C.c_void_p, C.c_void_p, C.c_void_p]
         L.emu_design_nco_constrain.restype = C.c_uint
         L.emu_design_nco_constrain.argtypes = [C.c_float]
         L.emu_design_rotation.restype = C.c_float
@@ -72,6 +75,20 @@ class Emu:
         n = self.L.emu_pfb(M, kind, x.ctypes.data, nf, ch.ctypes.data, len(ch), y.ctypes.data)
         assert n == nf, "emu_pfb failed"
         return y
+
+    def wbfm_tail(self, x, order, fc, M, chunks=None):
+        """x: [lanes, n] float32 -> ([lanes, n_out] de-emphasised and decimated, b [nsos, 3], a [nsos, 3])"""
+        x = np.ascontiguousarray(np.atleast_2d(x), np.float32)
+        lanes, n = x.shape
+        ch = np.array([n] if chunks is None else list(chunks), np.int64)
+        y = np.zeros((lanes, n // M), np.float32)
+        nsos = (order + 1) // 2
+        b = np.zeros((nsos, 3), np.float32)
+        a = np.zeros((nsos, 3), np.float32)
+        k = self.L.emu_wbfm_tail(lanes, order, fc, M, x.ctypes.data, n, ch.ctypes.data, len(ch), y.ctypes.data,
+                                 b.ctypes.data, a.ctypes.data)
+        assert k >= 0, "emu_wbfm_tail failed"
+        return y[:, :k], b, a
 
     def design_msresamp(self, rate, As=60.0):
         S, step, npfb = C.c_uint(0), C.c_uint(0), C.c_uint(0)

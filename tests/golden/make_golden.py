@@ -53,6 +53,11 @@ def main():
     x3 = synth.config3(1 << 14)
     v["c3_x"] = x3
     v["c3_y"] = np.stack(O.Chain(2.56e6, 0.0, 0.0, O.DEMOD_NBFM, 0.3, -40.0, 16, False).process(x3))
+    # wide-band FM tail
+    xr = np.ascontiguousarray(x.real)
+    v["iirfilt_butter2_0p025"] = O.IirFiltRRRF(2, 0.025).execute(xr)
+    v["firdecim4"] = O.FirDecim(4).execute(xr)
+    v["c2_wbfm4_y"] = O.Chain(2.56e6, 1e5, 200e3, O.DEMOD_WBFM, 0.6, -40.0, decim=4).process(xs)[0]
     np.savez_compressed(os.path.join(HERE, "oracle_vectors.npz"), **v)
     print({k: a.shape for k, a in v.items()})
 

@@ -40,7 +40,10 @@ def test_liquid_compat_aliases(cs):
               "agc_crcf_squelch_set_threshold", "agc_crcf_squelch_set_timeout", "agc_crcf_execute_block",
               "agc_crcf_get_rssi", "agc_crcf_squelch_get_status", "agc_crcf_destroy", "freqdem_create",
               "freqdem_print", "freqdem_demodulate_block", "freqdem_destroy", "ampmodem_create", "ampmodem_print",
-              "ampmodem_demodulate_block", "ampmodem_destroy"]          # the hot-path imports of Liquid.chs
+              "ampmodem_demodulate_block", "ampmodem_destroy",          # the hot-path imports of Liquid.chs
+              "iirfilt_rrrf_create_prototype", "iirfilt_rrrf_print", "iirfilt_rrrf_execute_block", "iirfilt_rrrf_destroy",
+              "firdecim_rrrf_create_kaiser", "firdecim_rrrf_print", "firdecim_rrrf_execute_block",
+              "firdecim_rrrf_destroy"]                                  # + the wbFMDemodulator tail
     missing = [s for s in liquid if not hasattr(L, s)]
     assert not missing, missing
 

@@ -116,3 +116,26 @@ def test_channelizer_kernels_match_oracle(orc, emu, M, kind):
     assert_parity(y, ref, what=f"channelizer M={M} kind={kind}")
     chunks = [1, 13, nf - 40, 26]
     assert_parity(emu.pfb(x, M, kind, chunks), ref, what=f"channelizer M={M} kind={kind}, chunked")
+
+
+@pytest.mark.parametrize("order,fc,M", [(2, 0.025, 4), (2, 0.005, 5), (5, 0.1, 1), (2, 0.2, 16)])
+def test_wbfm_tail_kernels_match_oracle(orc, emu, order, fc, M):
+    """k_iir2_seg / k_iir2_carry / k_iir2_apply (affine scans of the de-emphasis sections) + k_firdecim against the
+    oracle's sequential iirfilt_rrrf -> firdecim_rrrf, whole and in ragged chunks, two lanes"""
+    n = 6000 + M * 7 + 3
+    rng = np.random.default_rng(5)
+    x = (rng.standard_normal((2, n)) + np.array([[0.3], [-0.2]])).astype(np.float32)
+    ref = []
+    for lane in range(2):
+        f, d = orc.IirFiltRRRF(order, fc), orc.FirDecim(M)
+        ref.append(d.execute(f.execute(x[lane])))
+        bo, ao = f.coeffs()
+    y, b, a = emu.wbfm_tail(x, order, fc, M)
+    # (float32 design: 1 - pole cancels for narrow cut-offs, the two complex divisions round differently)
+    assert np.abs(b - bo).max() <= 2e-5 * np.abs(bo).max() and np.abs(a - ao).max() <= 2e-6
+    assert y.shape[1] == n // M
+    for lane in range(2):
+        assert_parity(y[lane], ref[lane], what=f"wbfm tail order={order} fc={fc} M={M}")
+    yc, _, _ = emu.wbfm_tail(x, order, fc, M, chunks=[1, 255, 257, 1000, 3, n - 1516])
+    for lane in range(2):
+        assert_parity(yc[lane], ref[lane], what=f"wbfm tail order={order} fc={fc} M={M}, chunked")

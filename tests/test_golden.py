@@ -39,6 +39,11 @@ def test_oracle_reproduces_its_vectors(orc, vec):
     assert np.array_equal(orc.FreqDem(0.3).execute(x), vec["freqdem_0p3"])
     y = orc.Chain(2.56e6, 1e5, 200e3, orc.DEMOD_NBFM, 0.3, -40.0).process(vec["c2_x"])[0]
     assert np.array_equal(y, vec["c2_y"])
+    xr = np.ascontiguousarray(x.real)
+    assert np.array_equal(orc.IirFiltRRRF(2, 0.025).execute(xr), vec["iirfilt_butter2_0p025"])
+    assert np.array_equal(orc.FirDecim(4).execute(xr), vec["firdecim4"])
+    y = orc.Chain(2.56e6, 1e5, 200e3, orc.DEMOD_WBFM, 0.6, -40.0, decim=4).process(vec["c2_x"])[0]
+    assert np.array_equal(y, vec["c2_wbfm4_y"])
 
 
 @pytest.mark.gpu
@@ -56,6 +61,15 @@ def test_gpu_blocks_against_golden(cs, vec):
     assert_parity(np.concatenate(run(cs.resampler(0.3, 60.0))), vec["msresamp_0p3"], what="msresamp 0.3")
     assert_parity(np.concatenate(run(cs.dcBlocker())), vec["dcblock"], what="dcblock")
     assert_parity(np.concatenate(run(cs.fmDemodulator(0.3))), vec["freqdem_0p3"], rel=2e-4, what="freqdem")
+    xr = np.ascontiguousarray(x.real)
+
+    def run_real(pipe, sizes):
+        process, cleanup = cs.unPipe(pipe)
+        out = list(process(chunked(xr, list(sizes))))
+        cleanup()
+        return np.concatenate(out)
+    assert_parity(run_real(cs.iirFilter(2, 0.025, 0.0, 10.0, 10.0), (1024, 333)), vec["iirfilt_butter2_0p025"], what="iirfilt_rrrf")
+    assert_parity(run_real(cs.firDecimator(4), (1024, 332)), vec["firdecim4"], what="firdecim_rrrf")
 
 
 @pytest.mark.gpu
@@ -63,6 +77,8 @@ def test_gpu_chain_against_golden(cs, vec):
     y = cs.Chain(2.56e6, 1e5, 200e3, cs.DeNBFM(0.3), agc=-40.0).process(vec["c2_x"])[0]
     assert np.array_equal(y == 0, vec["c2_y"] == 0)
     assert_parity(y, vec["c2_y"], rel=REL_TOL_AFTER_DCBLOCK, what="config 2 golden")
+    w = cs.Chain(2.56e6, 1e5, 200e3, cs.DeWBFM(4), agc=-40.0).process(vec["c2_x"])[0]
+    assert_parity(w, vec["c2_wbfm4_y"], rel=REL_TOL_AFTER_DCBLOCK, what="config 2 with DeWBFM 4, golden")
     outs = cs.Chain(2.56e6, demod=cs.DeNBFM(0.3), agc=-40.0, channels=16).process(vec["c3_x"])
     for c in range(16):
         assert_parity(outs[c], vec["c3_y"][c], rel=3e-4, what=f"config 3 golden channel {c}")

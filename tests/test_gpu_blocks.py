@@ -215,3 +215,43 @@ def test_unfused_app_graph_config1(cs, orc):
     ref = orc.Chain(2.56e6, 1e5, 200e3).process(x)[0][:30000]
     y = cs.sdrProcess(chunked(x, [1024]), 2.56e6, offset=1e5, bandwidth=200e3, numsamples=30000)
     assert_parity(y, ref, what="unfused config 1")
+
+
+@pytest.mark.parametrize("order,fc", [(2, 0.025), (2, 0.005), (5, 0.1)])
+def test_iirfilt_rrrf_butterworth(cs, orc, order, fc):
+    """iirFilter n fc 0 10 10 (Liquid.chs:644-650): design and the parallel-scan execution against the sequential
+    direct form II, across chunk sizes that are not multiples of the 256-sample segments"""
+    x = np.random.default_rng(31).standard_normal(300000).astype(np.float32) + np.float32(0.25)
+    o = orc.IirFiltRRRF(order, fc)
+    ref = o.execute(x)
+    y = np.concatenate(run_pipe(cs, cs.iirFilter(order, fc, 0.0, 10.0, 10.0), x, [1024, 9999, 1, 255, 100001]))
+    assert_parity(y, ref, what=f"iirfilt_rrrf order {order} fc {fc}")
+    L = cs._lib.load()
+    h = L.csdr_iirfilt_rrrf_create_prototype(0, 0, 0, order, fc, 0.0, 10.0, 10.0)
+    b = np.zeros(((order + 1) // 2, 3), np.float32)
+    a = np.zeros_like(b)
+    assert L.csdr_iirfilt_rrrf_coefficients(h, b.ctypes.data, a.ctypes.data) == (order + 1) // 2
+    L.csdr_iirfilt_rrrf_destroy(h)
+    bo, ao = o.coeffs()
+    assert np.abs(b - bo).max() <= 2e-5 * np.abs(bo).max() and np.abs(a - ao).max() <= 2e-6
+    # only the family the reference asks for exists; anything else fails loudly
+    assert not L.csdr_iirfilt_rrrf_create_prototype(1, 0, 0, 2, fc, 0.0, 10.0, 10.0)
+    assert b"Butterworth" in L.csdr_last_error()
+
+
+@pytest.mark.parametrize("M", [1, 4, 10])
+def test_firdecim_rrrf(cs, orc, M):
+    """firDecimator m (Liquid.chs:487-503): arrays whose length is a multiple of m (the reference drops the rest)"""
+    x = np.random.default_rng(32).standard_normal(40000 * M).astype(np.float32)
+    ref = orc.FirDecim(M).execute(x)
+    y = np.concatenate(run_pipe(cs, cs.firDecimator(M), x, [1024 * M, 3 * M, 7777 * M]))
+    assert_parity(y, ref, what=f"firdecim_rrrf M={M}")
+
+
+def test_unfused_wbfm_demodulator(cs, orc):
+    """wbFMDemodulator quadRate decim = firDecimator . iirFilter . fmDemodulator 0.6 (Liquid.chs:652-656), block by
+    block with the reference's 1024-sample arrays"""
+    x = keyed_fm(200 * 1024, 23)
+    ref = orc.FirDecim(4).execute(orc.IirFiltRRRF(2, np.float32(5000.0 / 200e3)).execute(orc.FreqDem(0.6).execute(x)))
+    y = np.concatenate(run_pipe(cs, cs.wbFMDemodulator(200e3, 4), x, [1024]))
+    assert_parity(y, ref, rel=2e-4, what="wbFMDemodulator")

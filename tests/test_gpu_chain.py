@@ -186,3 +186,37 @@ def test_full_size_properties_on_device(cs):
     # the demodulated tone: 1 kHz at deviation 50 kHz -> amplitude (dev/fs_out)/kf
     seg = a[100000:200000].double()
     assert 0.75 < seg.abs().max().item() < 1.05            # (dev / fs_out) / kf = 0.833 plus noise
+
+
+def test_wbfm_tail_in_the_chain(cs, orc):
+    """DeWBFM decim: agc -> freqdem 0.6 -> de-emphasis (2nd-order Butterworth at 5 kHz of the quadrature
+    rate) -> firdecim, single stream whole / ragged chunks, two streams, and per channel behind the channelizer"""
+    x = cs.synth.config2(1 << 21)
+    ref = orc.Chain(2.56e6, 1e5, 200e3, orc.DEMOD_WBFM, 0.6, -40.0, decim=4).process(x)[0]
+    per = 1.0 / 0.6 * 0.01                      # a 2 pi slip of the discriminator after the de-emphasis: not periodic any more
+    del per
+    y = run_chain(cs.Chain(2.56e6, 1e5, 200e3, cs.DeWBFM(4), agc=-40.0), x, [1 << 21])[0]
+    assert len(y) == len(ref) == (1 << 21) * 5 // 64 // 4
+    assert_parity(y, ref, rel=REL_TOL_AFTER_DCBLOCK, what="DeWBFM 4")
+    y = run_chain(cs.Chain(2.56e6, 1e5, 200e3, cs.DeWBFM(4), agc=-40.0), x, [300001, 1024, 77])[0]
+    assert_parity(y, ref, rel=REL_TOL_AFTER_DCBLOCK, what="DeWBFM 4 (ragged chunks)")
+    # decimation 5 does not divide the chunk's output: pending samples wait in the handle
+    ref5 = orc.Chain(2.56e6, 1e5, 200e3, orc.DEMOD_WBFM, 0.6, -40.0, decim=5).process(x)[0]
+    y = run_chain(cs.Chain(2.56e6, 1e5, 200e3, cs.DeWBFM(5), agc=-40.0), x, [123457])[0]
+    assert_parity(y, ref5, rel=REL_TOL_AFTER_DCBLOCK, what="DeWBFM 5 (ragged chunks)")
+    # two streams in one handle
+    x2 = np.stack([x[:1 << 19], x[1 << 19:1 << 20]])
+    outs = run_chain(cs.Chain(2.56e6, 1e5, 200e3, cs.DeWBFM(4), agc=-40.0, nstreams=2), x2, [1 << 18, 99999])
+    for s in range(2):
+        r = orc.Chain(2.56e6, 1e5, 200e3, orc.DEMOD_WBFM, 0.6, -40.0, decim=4).process(x2[s])[0]
+        assert_parity(outs[s], r, rel=REL_TOL_AFTER_DCBLOCK, what=f"DeWBFM 4, stream {s}")
+    # behind the channelizer: one tail per channel, and the --mix sum of the tails
+    x3 = cs.synth.config3(1 << 19)
+    r3 = orc.Chain(2.56e6, 0.0, 0.0, orc.DEMOD_WBFM, 0.6, -40.0, 16, False, decim=4).process(x3)
+    o3 = run_chain(cs.Chain(2.56e6, demod=cs.DeWBFM(4), agc=-40.0, channels=16), x3, [1 << 18, 5000, 100000])
+    assert len(o3) == 16
+    for c in range(16):
+        assert_parity(o3[c], r3[c], rel=REL_TOL_FM_NOISE, what=f"DeWBFM 4 behind -c 16, channel {c}")
+    r3m = orc.Chain(2.56e6, 0.0, 0.0, orc.DEMOD_WBFM, 0.6, -40.0, 16, True, decim=4).process(x3)[0]
+    o3m = run_chain(cs.Chain(2.56e6, demod=cs.DeWBFM(4), agc=-40.0, channels=16, mix_channels=True), x3, [1 << 19])[0]
+    assert_parity(o3m, r3m, rel=REL_TOL_FM_NOISE, what="DeWBFM 4 behind -c 16 --mix")

@@ -144,3 +144,46 @@ def test_chain_matches_block_composition(orc):
     ch = orc.Chain(2.56e6, 1e5, 200e3, orc.DEMOD_NBFM, 0.3, -40.0)
     got = np.concatenate([ch.process(x[i:i + 7000])[0] for i in range(0, len(x), 7000)])
     assert np.array_equal(got, ref)
+
+
+@pytest.mark.parametrize("order,fc", [(2, 0.025), (2, 5000.0 / 1.0e6), (3, 0.1), (6, 0.2)])
+def test_iirdes_butterworth_matches_scipy(orc, order, fc):
+    """the restated liquid_iirdes (Butterworth, low-pass, second-order sections) against an independent
+    implementation of the same textbook design: scipy.signal.butter with the bilinear pre-warp"""
+    ss = pytest.importorskip("scipy.signal")
+    f = orc.IirFiltRRRF(order, fc)
+    b, a = f.coeffs()
+    sos = np.concatenate([b, a], axis=1).astype(np.float64)
+    w, h = ss.sosfreqz(sos, worN=512)
+    _, href = ss.freqz(*ss.butter(order, 2 * fc), worN=512)
+    assert np.abs(h - href).max() <= 2e-4
+    x = np.random.default_rng(3).standard_normal(4000).astype(np.float32)
+    y = f.execute(x)
+    assert np.abs(y - ss.lfilter(*ss.butter(order, 2 * fc), x.astype(np.float64))).max() <= 2e-4 * np.abs(y).max()
+
+
+def test_firdecim_is_a_decimated_convolution(orc):
+    """firdecim_rrrf: 2 M m + 1 Kaiser taps, output k = the convolution sampled at input k M"""
+    for M in (1, 4, 5):
+        d = orc.FirDecim(M)
+        h = d.taps()
+        assert len(h) == 2 * M * 10 + 1 and np.allclose(h, h[::-1], atol=1e-7) and abs(h.sum() - M) < 0.02 * M
+        x = np.random.default_rng(M).standard_normal(1000 * M + 3).astype(np.float32)
+        y = np.concatenate([d.execute(x[:400 * M]), d.execute(x[400 * M:])])
+        full = np.convolve(x.astype(np.float64), h.astype(np.float64))
+        n = 400 + (len(x) - 400 * M) // M
+        assert len(y) == n
+        assert np.abs(y - full[0:n * M:M]).max() <= 1e-5 * np.abs(full).max()
+
+
+def test_chain_wbfm_matches_block_composition(orc):
+    """orc.Chain with DeWBFM == fm 0.6 -> iirFilter 2 (5000/quadRate) -> firDecimator decim after the agc
+    (Liquid.chs:652-656), the decimator fed as a stream"""
+    x = make_signal(60000, 6)
+    f = float(np.float32(2) * np.float32(np.pi) * np.float32(1e5) / np.float32(2.56e6))
+    fm = orc.FreqDem(0.6).execute(orc.Agc(-40.0).execute(orc.DcBlocker().execute(
+        orc.MsResamp(np.float32(200e3 / 2.56e6)).execute(orc.Nco(f).mix_down(x)))))
+    ref = orc.FirDecim(4).execute(orc.IirFiltRRRF(2, np.float32(5000.0 / 200e3)).execute(fm))
+    ch = orc.Chain(2.56e6, 1e5, 200e3, orc.DEMOD_WBFM, 0.6, -40.0, decim=4)
+    got = np.concatenate([ch.process(x[i:i + 7001])[0] for i in range(0, len(x), 7001)])
+    assert np.array_equal(got, ref)
