@@ -71,6 +71,7 @@ def main():
     torch.cuda.synchronize()       # the chains run on their own streams
     run("C1 mix+msresamp+dcblock (DeNo)", cs.Chain(2.56e6, 1e5, 200e3), x, b_alg=8 + 8 * 0.078125)
     run("C2 + AGC + NBFM", cs.Chain(2.56e6, 1e5, 200e3, cs.DeNBFM(0.3), agc=-40.0), x, b_alg=8 + 4 * 0.078125)
+    run("C2w + AGC + WBFM decim 4 (SURVEY 8f N2)", cs.Chain(2.56e6, 1e5, 200e3, cs.DeWBFM(4), agc=-40.0), x, b_alg=8 + 1 * 0.078125)
     x3 = sig(1 << 24, 3)
     run("C3 16-ch PFB + per-channel AGC + NBFM", cs.Chain(2.56e6, demod=cs.DeNBFM(0.3), agc=-40.0, channels=16), x3, b_alg=12)
     run("C3 16-ch PFB, DeNo, no AGC", cs.Chain(2.56e6, channels=16), x3, b_alg=16)
