@@ -47,6 +47,9 @@ SIGNATURES = {
     "csdr_freqdem_demodulate_block": (None, [_vp, _vp, _u, _vp]),
     "csdr_ampmodem_create": (_vp, [_f, _i, _i]), "csdr_ampmodem_destroy": (None, [_vp]),
     "csdr_ampmodem_print": (None, [_vp]), "csdr_ampmodem_demodulate_block": (None, [_vp, _vp, _u, _vp]),
+    "csdr_firpfbch2_crcf_create_kaiser": (_vp, [_i, _u, _u, _f]), "csdr_firpfbch2_crcf_destroy": (None, [_vp]),
+    "csdr_firpfbch2_crcf_print": (None, [_vp]), "csdr_firpfbch2_crcf_execute": (None, [_vp, _vp, _vp]),
+    "csdr_firpfbch2_taps": (_i, [_vp, _vp]), "csdr_firpfbch2_execute_block": (_i, [_vp, _vp, _u, _vp]),
     "csdr_iirfilt_rrrf_create_prototype": (_vp, [_i, _i, _i, _u, _f, _f, _f, _f]), "csdr_iirfilt_rrrf_destroy": (None, [_vp]),
     "csdr_iirfilt_rrrf_print": (None, [_vp]), "csdr_iirfilt_rrrf_execute_block": (None, [_vp, _vp, _u, _vp]),
     "csdr_iirfilt_rrrf_coefficients": (_u, [_vp, _vp, _vp]),

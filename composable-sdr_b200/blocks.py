@@ -14,7 +14,7 @@ from . import _lib
 from ._lib import CsdrError, ChainCfg  # noqa: F401
 
 __all__ = ["Pipe", "Fold", "compose", "unPipe", "addPipe", "takeNArr", "compact", "mux", "mix", "distribute_",
-           "mixDown", "mixUp", "resampler", "dcBlocker", "firpfbchChannelizer", "automaticGainControl",
+           "mixDown", "mixUp", "resampler", "dcBlocker", "firpfbchChannelizer", "firpfbch2Channelizer", "automaticGainControl",
            "fmDemodulator", "amDemodulator", "iirFilter", "firDecimator", "wbFMDemodulator", "listSink", "DeNo", "DeNBFM",
            "DeAM", "DeWBFM", "Chain", "sdrProcess",
            "CsdrError", "kernel_launches", "set_option", "device_count", "PinnedBuffer"]
@@ -354,6 +354,20 @@ def firpfbchChannelizer(n):
         _post_sync(a)
         return [y[nf * j: nf * (j + 1)] for j in range(n)]
     return Pipe(_Fb, process, lambda r: r.close())
+
+
+def firpfbch2Channelizer(n, m=7, as_=80.0):
+    """The 2x oversampled analyzer (liquid firpfbch2_crcf; not in the reference): an array of k n/2
+    samples gives a list of n channel arrays of k samples each (channel rate = 2 / n of the input rate)."""
+    def process(L, h, a):
+        a = _as_cf32(a)
+        nf = len(a) // (n // 2)
+        y = _empty_like_kind(a, max(nf * n, 1), np.complex64)
+        if nf and L.csdr_firpfbch2_execute_block(h, _ptr(a), len(a), _ptr(y)) != 0:
+            raise CsdrError("firpfbch2Channelizer: " + _lib.last_error())
+        return [y[nf * j: nf * (j + 1)] for j in range(n)]
+    return _block(lambda L: L.csdr_firpfbch2_crcf_create_kaiser(0, n, m, as_), lambda L, h: L.csdr_firpfbch2_crcf_destroy(h),
+                  process, "firpfbch2Channelizer")
 
 
 def automaticGainControl(tres):

@@ -599,11 +599,12 @@ struct Channelizer {
     size_t smem = 0;
     void (*tile_kernel)(PfbTileParams) = nullptr; PfbTileParams tp{}; size_t tile_smem = 0;   // M = 2..32, m = 7
     bool ring_ok = false; int ring_ctas = 1; void (*ring_kernel)(PfbRingParams) = nullptr;                                                 // M = 128..1024, m = 7
+    bool over2 = false; unsigned long long frames_done = 0;     // firpfbch2 analyzer: hop M/2, generic kernel
 
-    void init(const Ctx &c, unsigned M_, unsigned m_, float As_)
+    void init(const Ctx &c, unsigned M_, unsigned m_, float As_, bool over2_ = false)
     {
-        M = M_; m = m_; As = As_; P = 2 * m;
-        h = design::design_firpfbch(M, m, As);
+        M = M_; m = m_; As = As_; P = 2 * m; over2 = over2_;
+        h = over2 ? design::design_firpfbch2(M, m, As) : design::design_firpfbch(M, m, As);
         hd.ensure(h.size() * sizeof(float));
         CK(cudaMemcpyAsync(hd.p, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice, c.stream));
         std::vector<float2> t(M);
@@ -622,7 +623,7 @@ struct Channelizer {
         if (smem > 200 * 1024) throw CudaError{"firpfbch: channel count too large for one CTA tile"};
         CK(cudaFuncSetAttribute(k_pfb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         tile_kernel = nullptr;
-        if (log2M >= 1 && (int)M <= kPfbTileMaxM && (int)P == kPfbTileP) {
+        if (!over2 && log2M >= 1 && (int)M <= kPfbTileMaxM && (int)P == kPfbTileP) {
             switch (log2M) {
             case 1: tile_kernel = k_pfb_tile<1>; break;
             case 2: tile_kernel = k_pfb_tile<2>; break;
@@ -636,19 +637,20 @@ struct Channelizer {
             tile_smem = (size_t)(kPfbTileF + kPfbTileP - 1) * (M + 2) * sizeof(float2);
             CK(cudaFuncSetAttribute(tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem));
         }
-        ring_ok = log2M >= 7 && M <= 1024 && (int)P == kPfbRingP;
+        ring_ok = !over2 && log2M >= 7 && M <= 1024 && (int)P == kPfbRingP;
         if (ring_ok) {
             ring_kernel = pfb_ring_lfz(log2M) == 4 ? k_pfb_ring<4> : k_pfb_ring<5>;
             CK(cudaFuncSetAttribute(ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pfb_ring_smem((int)M, log2M)));
             CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ring_ctas, ring_kernel, 2 * (int)M / kPfbRingCPT, pfb_ring_smem((int)M, log2M)));
             if (ring_ctas < 1) ring_ok = false;
         }
-        size_t hb = (size_t)(P - 1) * M * sizeof(float2);
+        size_t hb = hist_samples() * sizeof(float2);
         for (auto &b : xr) { b.ensure(hb); CK(cudaMemsetAsync(b.p, 0, b.cap, c.stream)); }
         c.sync();
     }
-    size_t hist_samples() const { return (size_t)(P - 1) * M; }
-    // where the caller must place n = nf*M pre-rotated samples before calling run()
+    unsigned hop() const { return over2 ? M / 2 : M; }
+    size_t hist_samples() const { return (size_t)(P - 1) * M + (over2 ? M / 2 : 0); }
+    // where the caller must place n = nf*hop() (pre-rotated) samples before calling run()
     float2 *input_slot(const Ctx &c, size_t n)
     {
         size_t need = (hist_samples() + n) * sizeof(float2);
@@ -670,6 +672,8 @@ struct Channelizer {
         p.xr = xr[cur].as<float2>(); p.y = y; p.y_stride = y_stride;
         p.M = (int)M; p.P = (int)P; p.nf = nf; p.F = F; p.log2M = log2M;
         p.h = hd.as<float>(); p.tw = tw.as<float2>();
+        p.hop = (int)hop(); p.over2 = over2 ? 1 : 0; p.parity0 = (int)(frames_done & 1); p.scale = 1.0f / (float)M;
+        frames_done += (unsigned long long)nf;
         if (ring_ok) {
             PfbRingParams rp{};
             rp.xr = p.xr; rp.y = y; rp.y_stride = y_stride; rp.nf = nf; rp.M = (int)M; rp.log2M = log2M;
@@ -690,7 +694,7 @@ struct Channelizer {
         int H = (int)hist_samples();
         xr[cur ^ 1].ensure((size_t)H * sizeof(float2));
         launch(k_copy_tail, dim3((H + 255) / 256), dim3(256), 0, c.stream, (const float2 *)xr[cur].as<float2>(),
-               xr[cur ^ 1].as<float2>(), (long long)nf * M, H);
+               xr[cur ^ 1].as<float2>(), (long long)nf * hop(), H);
         cur ^= 1;
     }
 };
@@ -804,6 +808,7 @@ struct csdr_nco_s {
 struct csdr_msresamp_s { Ctx ctx; Staging st; Frontend fe; csdr_msresamp_s() : ctx(-1) {} };
 struct csdr_iirfilt_s { Ctx ctx; Staging st; Backend be; float alpha; csdr_iirfilt_s() : ctx(-1) {} };
 struct csdr_firpfbch_s { Ctx ctx; Staging st; Channelizer ch; DevBuf tmp; csdr_firpfbch_s() : ctx(-1) {} };
+struct csdr_firpfbch2_s { Ctx ctx; Staging st; Channelizer ch; csdr_firpfbch2_s() : ctx(-1) {} };
 struct csdr_agc_s {
     Ctx ctx; Staging st; Backend be; bool started = false;
     float bw = 1e-2f, g = 1.0f, thr = 0.0f; unsigned timeout = 100; int mode = SQ_DISABLED;
@@ -996,6 +1001,43 @@ int csdr_firpfbch_execute_block(csdr_firpfbch q, csdr_nco nco, const csdr_cf32 *
 void csdr_firpfbch_crcf_analyzer_execute(csdr_firpfbch q, const csdr_cf32 *x, csdr_cf32 *y)
 {
     csdr_firpfbch_execute_block(q, nullptr, x, q->ch.M, y);
+}
+
+// ---------------------------------------------------------------- firpfbch2_crcf (2x oversampled analyzer)
+csdr_firpfbch2 csdr_firpfbch2_crcf_create_kaiser(int type, unsigned M, unsigned m, float As)
+{
+    API_BEGIN
+    if (type != 0) throw CudaError{"firpfbch2_crcf_create_kaiser: only LIQUID_ANALYZER (0) is implemented"};
+    if (M < 2 || (M & 1) || m < 1) throw CudaError{"firpfbch2_crcf_create_kaiser: need an even M >= 2 and m >= 1"};
+    std::unique_ptr<csdr_firpfbch2_s> q(new csdr_firpfbch2_s());
+    q->ch.init(q->ctx, M, m, As, true);
+    return q.release();
+    API_END(nullptr)
+}
+void csdr_firpfbch2_crcf_destroy(csdr_firpfbch2 q) { delete q; }
+void csdr_firpfbch2_crcf_print(csdr_firpfbch2 q)
+{
+    printf("firpfbch2_crcf: analyzer, channels: %u, semi-length: %u, %zu taps\n", q->ch.M, q->ch.m, q->ch.h.size());
+}
+int csdr_firpfbch2_taps(csdr_firpfbch2 q, float *h) { memcpy(h, q->ch.h.data(), q->ch.h.size() * sizeof(float)); return 0; }
+int csdr_firpfbch2_execute_block(csdr_firpfbch2 q, const csdr_cf32 *x, unsigned n, csdr_cf32 *y)
+{
+    API_BEGIN
+    q->ctx.use();
+    const unsigned M = q->ch.M, M2 = M / 2, nf = n / M2;
+    if (!nf) return 0;
+    const size_t bytes_in = (size_t)nf * M2 * sizeof(float2), bytes_out = (size_t)nf * M * sizeof(float2);
+    float2 *yd = (float2 *)q->st.out_dev(y, bytes_out);
+    float2 *slot = q->ch.input_slot(q->ctx, (size_t)nf * M2);
+    CK(cudaMemcpyAsync(slot, x, bytes_in, cudaMemcpyDefault, q->ctx.stream));
+    q->ch.run(q->ctx, (int)nf, yd, nf);
+    q->st.finish(q->ctx, y, yd, bytes_out);
+    return 0;
+    API_END(-1)
+}
+void csdr_firpfbch2_crcf_execute(csdr_firpfbch2 q, const csdr_cf32 *x, csdr_cf32 *y)
+{
+    csdr_firpfbch2_execute_block(q, x, q->ch.M / 2, y);
 }
 
 // ---------------------------------------------------------------- agc_crcf

@@ -140,6 +140,16 @@ inline std::vector<float> design_firpfbch(unsigned M, unsigned m, float As)
     h.resize((size_t)2 * M * m);
     return h;
 }
+// firpfbch2_crcf_create_kaiser (analyzer): 2 M m + 1 taps at fc = 1/M, scaled to sum M, the first 2 M m used
+inline std::vector<float> design_firpfbch2(unsigned M, unsigned m, float As)
+{
+    std::vector<float> h = firdes_kaiser(2 * M * m + 1, 1.0f / (float)M, As);
+    float sum = 0.0f;
+    for (float v : h) sum += v;
+    for (float &v : h) v = v * (float)M / sum;
+    h.resize((size_t)2 * M * m);
+    return h;
+}
 // reference pre-rotation frequency, evaluated in float32 like the Haskell expression (Liquid.chs:817)
 inline float firpfbch_rotation(unsigned C)
 {

@@ -76,3 +76,9 @@ void *firdecim_rrrf_create_kaiser(unsigned M, unsigned m, float as) { return csd
 void firdecim_rrrf_destroy(void *q) { csdr_firdecim_rrrf_destroy((csdr_firdecim)q); }
 void firdecim_rrrf_print(void *q) { csdr_firdecim_rrrf_print((csdr_firdecim)q); }
 void firdecim_rrrf_execute_block(void *q, float *x, unsigned n, float *y) { csdr_firdecim_rrrf_execute_block((csdr_firdecim)q, x, n, y); }
+
+/* liquid's firpfbch2_crcf analyzer (not imported by the reference) */
+void *firpfbch2_crcf_create_kaiser(int type, unsigned M, unsigned m, float As) { return csdr_firpfbch2_crcf_create_kaiser(type, M, m, As); }
+void firpfbch2_crcf_destroy(void *q) { csdr_firpfbch2_crcf_destroy((csdr_firpfbch2)q); }
+void firpfbch2_crcf_print(void *q) { csdr_firpfbch2_crcf_print((csdr_firpfbch2)q); }
+void firpfbch2_crcf_execute(void *q, cf *x, cf *y) { csdr_firpfbch2_crcf_execute((csdr_firpfbch2)q, x, y); }

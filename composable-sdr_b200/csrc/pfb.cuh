@@ -26,6 +26,9 @@ struct PfbParams {
     const float *h;         // prototype, P*M taps
     const float2 *tw;       // M twiddles exp(-j 2 pi t / M)
     float *pw; long long pw_stride;   // optional: |y|^2, same layout (input of the per-channel AGC gain loop)
+    int hop;                // input samples per frame: M (firpfbch), M/2 (firpfbch2, history (P-1) M + M/2)
+    int over2, parity0;     // firpfbch2 analyzer: y_t[c] *= (-1)^(c t) exp(-j 2 pi c / M) / M, t counted from parity0
+    float scale;
 };
 
 __device__ __forceinline__ unsigned pfb_bitrev(unsigned v, int bits) { return bits ? (__brev(v) >> (32 - bits)) : 0u; }
@@ -44,7 +47,7 @@ __global__ void __launch_bounds__(256) k_pfb(const PfbParams p)
     // polyphase filter: X[f][n]; consecutive threads -> consecutive n (coalesced reads of xr, h)
     for (int e = threadIdx.x; e < total; e += blockDim.x) {
         const int f = e / M, n = e - f * M;
-        const float2 *src = p.xr + (long long)(t0 + f + P - 1) * M + n;     // newest sample of this branch
+        const float2 *src = p.xr + (long long)(P - 1) * M + (long long)(t0 + f) * p.hop + n;     // newest sample of this branch
         const float *hh = p.h + (M - 1 - n);
         float ar = 0.f, ai = 0.f;
         for (int k = 0; k < P; k++) {
@@ -95,11 +98,27 @@ __global__ void __launch_bounds__(256) k_pfb(const PfbParams p)
     // transposed store: consecutive threads -> consecutive frames of one channel
     for (int e = threadIdx.x; e < M * nfr; e += blockDim.x) {
         const int c = e / nfr, f = e - c * nfr;
-        const float2 v = buf[f * M + c];
+        float2 v = buf[f * M + c];
+        if (p.over2) {
+            // firpfbch2: the analyzer's backward DFT over the window slots and its alternating commutator, folded
+            // into a per-channel factor of the forward DFT (closed form at the top of the firpfbch2 section below)
+            const float2 w = p.tw[c];
+            const float sg = ((p.parity0 + t0 + f) & c & 1) ? -p.scale : p.scale;
+            v = cf((v.x * w.x - v.y * w.y) * sg, (v.x * w.y + v.y * w.x) * sg);
+        }
         p.y[(long long)c * p.y_stride + t0 + f] = v;
         if (p.pw) p.pw[(long long)c * p.pw_stride + t0 + f] = pfb_power(v);
     }
 }
+
+// ---- firpfbch2_crcf analyzer (2x oversampled: M/2 samples in, M channels out per frame) -----------
+// liquid's sequential object (src/multichannel/src/firpfbch2.c: two half-frames of windows filled alternately, branch
+// i reading window (offset + i) mod M, backward DFT, 1/M) has the closed form, with n_t = (t+1) M/2 samples received:
+//   u_t[s] = sum_{a<P} h[M a + s] x[n_t - 1 - s - a M]              (the polyphase sums of the last P M samples)
+//   y_t[c] = (1/M) (-1)^(c t) sum_s u_t[s] exp(+j 2 pi s c / M)
+// With n = M-1-s the sums are exactly k_pfb's X_t[n] on a window that advances by M/2, and
+//   y_t[c] = (1/M) (-1)^(c t) exp(-j 2 pi c / M) * sum_n X_t[n] exp(-j 2 pi c n / M)
+// so k_pfb runs it with hop = M/2 and the factor applied in its store (over2 = 1).
 
 // ---- small power-of-two M (2..32): one thread per frame -------------------------------------------------------
 // The CTA stages F + P - 1 consecutive frames in shared memory once (coalesced 16-byte loads; rows padded to M + 2

@@ -108,6 +108,19 @@ int      csdr_firpfbch_taps(csdr_firpfbch q, float *h /* 2*M*m */);
  * y[M][nframes].  The n % M tail samples are consumed by the NCO and dropped, as the reference does. */
 int      csdr_firpfbch_execute_block(csdr_firpfbch q, csdr_nco nco, const csdr_cf32 *x, unsigned n, csdr_cf32 *y);
 
+/* ---------------------------------------------------------------- firpfbch2_crcf ---- *
+ * liquid's 2x oversampled analyzer (M/2 samples in, M channels out per frame).  The reference does NOT import it
+ * (its channelizer is firpfbch_crcf, Liquid.chs:730-742); offered as the alternative channelizer block the
+ * task names, with liquid's signatures so that a future Liquid.chs import would bind it 1:1. */
+typedef struct csdr_firpfbch2_s *csdr_firpfbch2;
+csdr_firpfbch2 csdr_firpfbch2_crcf_create_kaiser(int type /* 0 analyzer */, unsigned M /* even */, unsigned m, float As);
+void     csdr_firpfbch2_crcf_destroy(csdr_firpfbch2 q);
+void     csdr_firpfbch2_crcf_print(csdr_firpfbch2 q);
+void     csdr_firpfbch2_crcf_execute(csdr_firpfbch2 q, const csdr_cf32 *x /* M/2 */, csdr_cf32 *y /* M */);
+int      csdr_firpfbch2_taps(csdr_firpfbch2 q, float *h /* 2*M*m */);
+/* coarse entry point: nframes = n / (M/2) frames in one call, channel-major y[M][nframes] */
+int      csdr_firpfbch2_execute_block(csdr_firpfbch2 q, const csdr_cf32 *x, unsigned n, csdr_cf32 *y);
+
 /* ---------------------------------------------------------------- agc_crcf ---- *
  * replaces Liquid.chs:660-691 */
 typedef struct csdr_agc_s *csdr_agc;

@@ -534,6 +534,64 @@ void orc_firpfbch_crcf_analyzer_execute(orc_firpfbch q, const orc_cf32 *x, orc_c
 }
 
 /* ============================================================================================
+ * firpfbch2_crcf analyzer -- liquid src/multichannel/src/firpfbch2.c (2x oversampled: M/2 samples in, M out).
+ * NOT called by the reference (which uses firpfbch_crcf, Liquid.chs:730-742); restated because the task's
+ * north star names it.  create_kaiser: 2 M m + 1 Kaiser taps at fc = 1/M (analyzer), scaled to
+ * sum M; create: branch n = taps h[n + i M] reversed; execute_analyzer: the M/2 new samples go into windows
+ * base-1 .. base-M/2 (base = M/2 on even frames, M on odd ones), branch i filters window (offset + i) mod M
+ * (offset = 0 / M/2), backward DFT, scale 1/M.   Confidence M.
+ * ========================================================================================== */
+struct orc_firpfbch2_s { unsigned M, M2, p; float *h, *hsub; win_cf *w; int flag; orc_cf32 *X; };
+orc_firpfbch2 orc_firpfbch2_crcf_create_kaiser(int type, unsigned M, unsigned m, float As)
+{
+    if (type != 0 || M < 2 || (M & 1) || m == 0) return NULL;
+    orc_firpfbch2 q = (orc_firpfbch2)calloc(1, sizeof(*q));
+    q->M = M; q->M2 = M / 2; q->p = 2 * m;
+    unsigned h_len = 2 * M * m + 1;
+    q->h = (float *)malloc(h_len * sizeof(float));
+    orc_firdes_kaiser(h_len, 1.0f / (float)M, As, 0.0f, q->h);
+    float sum = 0.0f;
+    for (unsigned i = 0; i < h_len; i++) sum += q->h[i];
+    for (unsigned i = 0; i < h_len; i++) q->h[i] = q->h[i] * (float)M / sum;
+    q->hsub = (float *)malloc((size_t)M * q->p * sizeof(float));
+    q->w = (win_cf *)calloc(M, sizeof(win_cf));
+    for (unsigned n = 0; n < M; n++) {
+        for (unsigned i = 0; i < q->p; i++) q->hsub[n * q->p + (q->p - i - 1)] = q->h[M * i + n];
+        win_init(&q->w[n], q->p);
+    }
+    q->X = (orc_cf32 *)calloc(M, sizeof(orc_cf32));
+    return q;
+}
+void orc_firpfbch2_crcf_destroy(orc_firpfbch2 q)
+{
+    if (!q) return;
+    for (unsigned i = 0; i < q->M; i++) win_free(&q->w[i]);
+    free(q->w); free(q->h); free(q->hsub); free(q->X); free(q);
+}
+const float *orc_firpfbch2_taps(orc_firpfbch2 q, unsigned *h_len) { if (h_len) *h_len = q->M * q->p; return q->h; }
+void orc_firpfbch2_crcf_execute(orc_firpfbch2 q, const orc_cf32 *x, orc_cf32 *y)
+{
+    const unsigned M = q->M, M2 = q->M2;
+    const unsigned base = q->flag ? M : M2, offset = q->flag ? M2 : 0;
+    for (unsigned i = 0; i < M2; i++) win_push(&q->w[base - i - 1], x[i]);
+    for (unsigned i = 0; i < M; i++) {
+        unsigned b = (offset + i) % M;
+        q->X[b] = dot_rc(q->hsub + i * q->p, q->w[b].v, q->p);
+    }
+    for (unsigned k = 0; k < M; k++) {
+        double sr = 0.0, si = 0.0;
+        for (unsigned n = 0; n < M; n++) {
+            double a = 2.0 * M_PI * (double)(((unsigned long long)k * n) % M) / (double)M;
+            double wr = cos(a), wi = sin(a);
+            sr += q->X[n].re * wr - q->X[n].im * wi;
+            si += q->X[n].re * wi + q->X[n].im * wr;
+        }
+        y[k] = cmk((float)sr / (float)M, (float)si / (float)M);
+    }
+    q->flag = 1 - q->flag;
+}
+
+/* ============================================================================================
  * agc_crcf -- liquid src/agc/src/agc.c.  Reference: agcCreate/agcExecuteBlock, Liquid.chs:693-717
  * ========================================================================================== */
 enum { SQ_UNKNOWN = 0, SQ_ENABLED, SQ_RISE, SQ_SIGNALHI, SQ_FALL, SQ_SIGNALLO, SQ_TIMEOUT, SQ_DISABLED };

@@ -118,6 +118,13 @@ orc_ampmodem orc_ampmodem_create(float mod_index, int type, int suppressed_carri
 void     orc_ampmodem_destroy(orc_ampmodem q);
 void     orc_ampmodem_demodulate_block(orc_ampmodem q, const orc_cf32 *r, unsigned n, float *m);
 
+/* ---- firpfbch2_crcf analyzer (2x oversampled; not called by the reference) ---- */
+typedef struct orc_firpfbch2_s *orc_firpfbch2;
+orc_firpfbch2 orc_firpfbch2_crcf_create_kaiser(int type, unsigned M, unsigned m, float As);   /* type 0 = analyzer, M even */
+void     orc_firpfbch2_crcf_destroy(orc_firpfbch2 q);
+const float *orc_firpfbch2_taps(orc_firpfbch2 q, unsigned *h_len);                            /* 2 M m used taps */
+void     orc_firpfbch2_crcf_execute(orc_firpfbch2 q, const orc_cf32 *x /* M/2 */, orc_cf32 *y /* M */);
+
 /* ---- iirfilt_rrrf (Butterworth low-pass prototype in second-order sections), Liquid.chs:610-633 ---- */
 typedef struct orc_iirfilt_rrrf_s *orc_iirfilt_rrrf;
 orc_iirfilt_rrrf orc_iirfilt_rrrf_create_prototype(int ftype, int btype, int format, unsigned n, float fc, float f0,

@@ -57,6 +57,9 @@ def _declare(L):
         "orc_nco_crcf_step": (None, [vp]),
         "orc_nco_crcf_mix_block_down": (None, [vp, vp, vp, u]), "orc_nco_crcf_mix_block_up": (None, [vp, vp, vp, u]),
         "orc_nco_sintab": (C.POINTER(C.c_float), []),
+        "orc_firpfbch2_crcf_create_kaiser": (vp, [i, u, u, f]), "orc_firpfbch2_crcf_destroy": (None, [vp]),
+        "orc_firpfbch2_taps": (C.POINTER(C.c_float), [vp, C.POINTER(u)]),
+        "orc_firpfbch2_crcf_execute": (None, [vp, vp, vp]),
         "orc_iirfilt_rrrf_create_prototype": (vp, [i, i, i, u, f, f, f, f]), "orc_iirfilt_rrrf_destroy": (None, [vp]),
         "orc_iirfilt_rrrf_coeffs": (u, [vp, vp, vp]), "orc_iirfilt_rrrf_execute_block": (None, [vp, vp, u, vp]),
         "orc_firdecim_rrrf_create_kaiser": (vp, [u, u, f]), "orc_firdecim_rrrf_destroy": (None, [vp]),
@@ -341,6 +344,39 @@ class AmpModem:
 
 
 DEMOD_NO, DEMOD_NBFM, DEMOD_AM, DEMOD_WBFM = 0, 1, 2, 3
+
+
+class Firpfbch2:
+    """liquid firpfbch2_crcf analyzer (2x oversampled; M/2 in, M out).  Not called by the reference."""
+
+    def __init__(self, nch, m=7, As=80.0):
+        self.L = lib()
+        self.M = int(nch)
+        self.h = self.L.orc_firpfbch2_crcf_create_kaiser(0, self.M, m, As)
+        if not self.h:
+            raise ValueError("firpfbch2_crcf_create_kaiser: M must be even")
+
+    def close(self):
+        if self.h:
+            self.L.orc_firpfbch2_crcf_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def taps(self):
+        n = C.c_uint(0)
+        p = self.L.orc_firpfbch2_taps(self.h, C.byref(n))
+        return np.ctypeslib.as_array(p, (n.value,)).copy()
+
+    def execute(self, x):
+        """whole frames of M/2 samples -> [M][2 len(x) / M] channel-major"""
+        x = _cf(x)
+        M2 = self.M // 2
+        nf = x.size // M2
+        y = np.empty((nf, self.M), np.complex64)
+        for t in range(nf):
+            self.L.orc_firpfbch2_crcf_execute(self.h, x[t * M2:].ctypes.data, y[t].ctypes.data)
+        return np.ascontiguousarray(y.T)
 
 
 class IirFiltRRRF:

@@ -246,7 +246,7 @@ extern "C" long long emu_pfb(int M, int kind, const float2 *x, long long nf_tota
         } else {
             PfbParams p{};
             p.xr = xr.data(); p.y = y + pos; p.y_stride = nf_total; p.M = M; p.P = P; p.nf = (int)nf; p.F = 8; p.log2M = log2M;
-            p.h = h.data(); p.tw = tw.data();
+            p.h = h.data(); p.tw = tw.data(); p.hop = M;
             const size_t smem = (size_t)p.F * M * sizeof(float2) * (log2M >= 0 ? 1 : 2);
             launch(k_pfb, dim3((unsigned)((nf + p.F - 1) / p.F)), dim3(64), smem, p);
         }
@@ -301,6 +301,39 @@ extern "C" long long emu_wbfm_tail(int lanes, unsigned order, float fc, unsigned
         pos += n; produced += nb;
     }
     return produced;
+}
+
+// firpfbch2 analyzer (k_pfb with hop M/2): x = nf_total * M/2 samples fed in chunks of whole frames; y [M][nf_total]
+extern "C" long long emu_pfb2(int M, const float2 *x, long long nf_total, const long long *chunk_frames, int nchunks, float2 *y,
+                              float *taps)
+{
+    const int m = 7, P = 2 * m, M2 = M / 2;
+    std::vector<float> h = design::design_firpfbch2((unsigned)M, (unsigned)m, 80.0f);
+    if (taps) memcpy(taps, h.data(), h.size() * sizeof(float));
+    std::vector<float2> tw(M);
+    for (int i = 0; i < M; i++) { tw[i].x = (float)std::cos(-2.0 * design::kPi * i / M); tw[i].y = (float)std::sin(-2.0 * design::kPi * i / M); }
+    int log2M = -1;
+    if (M > 1 && (M & (M - 1)) == 0) { log2M = 0; while ((1 << log2M) < M) log2M++; }
+    const size_t H = (size_t)(P - 1) * M + M2;
+    std::vector<float2> xr(H, make_float2(0, 0));
+    EmuLaunch launch;
+    long long pos = 0;
+    for (int c = 0; c < nchunks; c++) {
+        const long long nf = chunk_frames[c];
+        if (pos + nf > nf_total) return -1;
+        if (nf == 0) continue;
+        xr.resize(H + (size_t)nf * M2);
+        memcpy(xr.data() + H, x + pos * M2, (size_t)nf * M2 * sizeof(float2));
+        PfbParams p{};
+        p.xr = xr.data(); p.y = y + pos; p.y_stride = nf_total; p.M = M; p.P = P; p.nf = (int)nf; p.F = 8; p.log2M = log2M;
+        p.h = h.data(); p.tw = tw.data(); p.hop = M2; p.over2 = 1; p.parity0 = (int)(pos & 1); p.scale = 1.0f / (float)M;
+        const size_t smem = (size_t)p.F * M * sizeof(float2) * (log2M >= 0 ? 1 : 2);
+        launch(k_pfb, dim3((unsigned)((nf + p.F - 1) / p.F)), dim3(64), smem, p);
+        std::vector<float2> tail(xr.end() - (long)H, xr.end());
+        xr.assign(tail.begin(), tail.end());
+        pos += nf;
+    }
+    return pos;
 }
 
 // ---- product-side filter design (design.hpp), exported so the CPU suite can compare it with the oracle ----

@@ -21,6 +21,8 @@ def load():
                                   C.POINTER(C.c_ulonglong), C.c_void_p]
         L.emu_pfb.restype = C.c_longlong
         L.emu_pfb.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_longlong, C.c_void_p, C.c_int, C.c_void_p]
+        L.emu_pfb2.restype = C.c_longlong
+        L.emu_pfb2.argtypes = [C.c_int, C.c_void_p, C.c_longlong, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.emu_wbfm_tail.restype = C.c_longlong
         L.emu_wbfm_tail.argtypes = [C.c_int, C.c_uint, C.c_float, C.c_uint, C.c_void_p, C.c_longlong, C.c_void_p, C.c_int,
                                     C.c_void_p, C.c_void_p, C.c_void_p]
@@ -75,6 +77,17 @@ class Emu:
         n = self.L.emu_pfb(M, kind, x.ctypes.data, nf, ch.ctypes.data, len(ch), y.ctypes.data)
         assert n == nf, "emu_pfb failed"
         return y
+
+    def pfb2(self, x, M, chunk_frames=None):
+        """firpfbch2 analyzer: ([M, nf] channel-major, the 2 M m taps)"""
+        x = np.ascontiguousarray(x, np.complex64)
+        nf = x.size // (M // 2)
+        ch = np.array([nf] if chunk_frames is None else list(chunk_frames), np.int64)
+        y = np.zeros((M, nf), np.complex64)
+        taps = np.zeros(2 * M * 7, np.float32)
+        n = self.L.emu_pfb2(M, x.ctypes.data, nf, ch.ctypes.data, len(ch), y.ctypes.data, taps.ctypes.data)
+        assert n == nf, "emu_pfb2 failed"
+        return y, taps
 
     def wbfm_tail(self, x, order, fc, M, chunks=None):
         """x: [lanes, n] float32 -> ([lanes, n_out] de-emphasised and decimated, b [nsos, 3], a [nsos, 3])"""

@@ -43,7 +43,9 @@ def test_liquid_compat_aliases(cs):
               "ampmodem_demodulate_block", "ampmodem_destroy",          # the hot-path imports of Liquid.chs
               "iirfilt_rrrf_create_prototype", "iirfilt_rrrf_print", "iirfilt_rrrf_execute_block", "iirfilt_rrrf_destroy",
               "firdecim_rrrf_create_kaiser", "firdecim_rrrf_print", "firdecim_rrrf_execute_block",
-              "firdecim_rrrf_destroy"]                                  # + the wbFMDemodulator tail
+              "firdecim_rrrf_destroy",                                  # + the wbFMDemodulator tail
+              "firpfbch2_crcf_create_kaiser", "firpfbch2_crcf_print", "firpfbch2_crcf_execute",
+              "firpfbch2_crcf_destroy"]                                 # + the oversampled analyzer
     missing = [s for s in liquid if not hasattr(L, s)]
     assert not missing, missing
 

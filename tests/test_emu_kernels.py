@@ -139,3 +139,18 @@ def test_wbfm_tail_kernels_match_oracle(orc, emu, order, fc, M):
     yc, _, _ = emu.wbfm_tail(x, order, fc, M, chunks=[1, 255, 257, 1000, 3, n - 1516])
     for lane in range(2):
         assert_parity(yc[lane], ref[lane], what=f"wbfm tail order={order} fc={fc} M={M}, chunked")
+
+
+@pytest.mark.parametrize("M", [2, 16, 20, 64])
+def test_firpfbch2_kernel_matches_oracle(orc, emu, M):
+    """k_pfb with a hop of M/2 and the oversampled analyzer's per-channel factor against the oracle's sequential
+    firpfbch2 object (alternating window halves, backward DFT), whole and in chunks of odd frame counts"""
+    nf = 201
+    x = make_signal(M // 2 * nf, 23)
+    o = orc.Firpfbch2(M)
+    ref = o.execute(x)
+    y, taps = emu.pfb2(x, M)
+    assert np.abs(taps - o.taps()).max() <= 2e-6 * np.abs(taps).max()
+    assert_parity(y, ref, what=f"firpfbch2 M={M}")
+    y, _ = emu.pfb2(x, M, [1, 13, nf - 41, 27])
+    assert_parity(y, ref, what=f"firpfbch2 M={M}, chunked")

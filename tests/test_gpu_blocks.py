@@ -255,3 +255,24 @@ def test_unfused_wbfm_demodulator(cs, orc):
     ref = orc.FirDecim(4).execute(orc.IirFiltRRRF(2, np.float32(5000.0 / 200e3)).execute(orc.FreqDem(0.6).execute(x)))
     y = np.concatenate(run_pipe(cs, cs.wbFMDemodulator(200e3, 4), x, [1024]))
     assert_parity(y, ref, rel=2e-4, what="wbFMDemodulator")
+
+
+@pytest.mark.parametrize("M", [2, 16, 20, 1024])
+def test_firpfbch2_oversampled_analyzer(cs, orc, M):
+    """firpfbch2_crcf (2x oversampled): coarse block call in chunks of odd and even frame counts, and
+    liquid's per-frame execute, against the oracle's sequential object"""
+    nf = 45 if M >= 1024 else 400
+    x = make_signal(M // 2 * nf, 29)
+    ref = orc.Firpfbch2(M).execute(x)
+    M2 = M // 2
+    outs = run_pipe(cs, cs.firpfbch2Channelizer(M), x, [M2 * 7, M2 * 30, M2])
+    y = np.stack([np.concatenate([o[c] for o in outs]) for c in range(M)])
+    assert_parity(y, ref, what=f"firpfbch2 M={M}")
+    L = cs._lib.load()
+    h = L.csdr_firpfbch2_crcf_create_kaiser(0, M, 7, 80.0)
+    fr = np.zeros((5, M), np.complex64)
+    for t in range(5):
+        L.csdr_firpfbch2_crcf_execute(h, x[t * M2:].ctypes.data, fr[t].ctypes.data)
+    L.csdr_firpfbch2_crcf_destroy(h)
+    assert_parity(fr.T, ref[:, :5], what=f"firpfbch2 M={M}, frame by frame")
+    assert not L.csdr_firpfbch2_crcf_create_kaiser(0, 7, 7, 80.0) and b"even" in L.csdr_last_error()

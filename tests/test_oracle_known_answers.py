@@ -187,3 +187,20 @@ def test_chain_wbfm_matches_block_composition(orc):
     ch = orc.Chain(2.56e6, 1e5, 200e3, orc.DEMOD_WBFM, 0.6, -40.0, decim=4)
     got = np.concatenate([ch.process(x[i:i + 7001])[0] for i in range(0, len(x), 7001)])
     assert np.array_equal(got, ref)
+
+
+@pytest.mark.parametrize("M", [8, 20])
+def test_firpfbch2_tone_lands_in_bin_at_twice_the_channel_rate(orc, M):
+    """the 2x oversampled analyzer: M/2 samples per frame, a tone at channel k's centre comes out of channel k with unit
+    gain as a constant phasor (the commutator's alternation removes the (-1)^k per frame), its neighbours 6 dB down
+    (cut-off 1/M), the rest suppressed"""
+    k, nf = 3, 300
+    n = np.arange(M // 2 * nf)
+    x = np.exp(2j * np.pi * k / M * n).astype(np.complex64)
+    y = orc.Firpfbch2(M).execute(x)
+    mag = np.abs(y[:, -1])
+    assert abs(mag[k] - 1.0) < 2e-3
+    assert abs(mag[k - 1] - 0.5) < 5e-3 and abs(mag[k + 1] - 0.5) < 5e-3
+    others = [c for c in range(M) if c not in (k - 1, k, k + 1)]
+    assert mag[others].max() < 1e-3
+    assert np.abs(y[k, -1] - y[k, -2]) < 1e-4
