@@ -59,6 +59,7 @@ SIGNATURES = {
     "csdr_chain_print": (None, [_vp]), "csdr_chain_num_outputs": (_u, [_vp]),
     "csdr_chain_out_elem_size": (_sz, [_vp]), "csdr_chain_max_output": (_sz, [_vp, _sz]),
     "csdr_chain_process": (_i, [_vp, _vp, _sz, _sz, C.POINTER(_vp), _sz, C.POINTER(_sz)]),
+    "csdr_chain_run_file": (_i, [_vp, C.c_char_p, C.c_char_p, C.c_uint64, _sz, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "csdr_chain_seek": (_i, [_vp, C.c_uint64]), "csdr_chain_warmup_len": (_sz, [_vp]),
     "csdr_chain_cuda_stream": (_vp, [_vp]), "csdr_chain_profile": (_i, [_vp, _i]),
     "csdr_chain_frontend_ms": (C.c_double, [_vp, C.POINTER(C.c_uint64)]), "csdr_chain_agc_fixups": (C.c_uint64, [_vp]),

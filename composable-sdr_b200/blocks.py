@@ -538,6 +538,16 @@ class Chain:
     def cuda_stream(self):
         return int(self.L.csdr_chain_cuda_stream(self.h) or 0)
 
+    def run_file(self, in_path, out_name, numsamples=0, chunk=0):
+        """soapy-sdr --filename in_path -n numsamples --output out_name: CF32 file in, <out_name>.cf32 / _chK.cf32 /
+        .f32 out (apps/SoapySDR.hs:209-240).  Returns (input samples consumed, samples written per output file)."""
+        n_in, n_out = C.c_uint64(0), C.c_uint64(0)
+        rc = self.L.csdr_chain_run_file(self.h, str(in_path).encode(), str(out_name).encode(), int(numsamples), int(chunk),
+                                        C.byref(n_in), C.byref(n_out))
+        if rc != 0:
+            raise CsdrError("csdr_chain_run_file: " + _lib.last_error())
+        return n_in.value, n_out.value
+
     def seek(self, n_prior):
         if self.L.csdr_chain_seek(self.h, int(n_prior)) != 0:
             raise CsdrError("csdr_chain_seek: " + _lib.last_error())

@@ -382,6 +382,78 @@ int csdr_chain_process(csdr_chain q, const csdr_cf32 *x, size_t nx, size_t x_str
     API_END(-1)
 }
 
+// ---- CF32 file in, raw sample files out: readFromFile (Source.chs:259-271: raw interleaved
+// little-endian float32 I/Q pairs, read in arrays of `chunk` samples), takeNArr numsamples behind the resampler
+// (SoapySDR.hs:207), fileSink = FS.writeChunks (Sink.hs:29-34) with the app's names: <name>.cf32, or <name>_ch<K>.cf32
+// (K from 1) behind the channelizer without --mix (SoapySDR.hs:222-240).  Demodulated outputs are written as raw
+// float32 (.f32); the reference wraps them in AU/WAV containers through libsndfile, which is outside this path.
+// The next chunk is read and the previous results are written by helper threads while the chain runs.
+int csdr_chain_run_file(csdr_chain q, const char *in_path, const char *out_name, uint64_t numsamples, size_t chunk,
+                        uint64_t *n_in, uint64_t *n_out)
+{
+    API_BEGIN
+    if (!in_path || !out_name) throw CudaError{"chain_run_file: null path"};
+    if (q->nstreams != 1) throw CudaError{"chain_run_file: one stream per file"};
+    q->ctx.use();
+    if (chunk == 0) chunk = (size_t)1 << 24;
+    struct File { FILE *f = nullptr; ~File() { if (f) fclose(f); } };
+    struct Pinned { void *p = nullptr; ~Pinned() { if (p) cudaFreeHost(p); } };
+    File fin; fin.f = fopen(in_path, "rb");
+    if (!fin.f) throw CudaError{std::string("chain_run_file: cannot open ") + in_path};
+    const unsigned nout = q->nout;
+    const char *ext = q->esz == sizeof(float2) ? ".cf32" : ".f32";
+    std::vector<File> fout(nout);
+    for (unsigned k = 0; k < nout; k++) {
+        const std::string name = nout == 1 ? std::string(out_name) + ext : std::string(out_name) + "_ch" + std::to_string(k + 1) + ext;
+        fout[k].f = fopen(name.c_str(), "wb");
+        if (!fout[k].f) throw CudaError{"chain_run_file: cannot create " + name};
+    }
+    // takeNArr counts samples behind the resampler: numsamples / C frames per channel, / decim behind the decimator
+    uint64_t limit = ~0ULL;
+    if (numsamples) {
+        limit = numsamples / q->C;
+        if (q->has_wb) limit /= q->wb.dec.M;
+    }
+    const size_t cap = chain_max_out(q, chunk) + 8;
+    Pinned xin[2], yout[2];
+    for (int i = 0; i < 2; i++) {
+        CK(cudaHostAlloc(&xin[i].p, chunk * sizeof(float2), cudaHostAllocDefault));
+        CK(cudaHostAlloc(&yout[i].p, (size_t)nout * cap * q->esz, cudaHostAllocDefault));
+    }
+    auto read_chunk = [&](int i) { return fread(xin[i].p, sizeof(float2), chunk, fin.f); };
+    uint64_t produced = 0, consumed = 0;
+    std::future<size_t> rd = std::async(std::launch::async, read_chunk, 0);
+    std::future<bool> wr;
+    for (int i = 0; produced < limit; i ^= 1) {
+        const size_t nx = rd.get();
+        if (nx == 0) break;
+        rd = std::async(std::launch::async, read_chunk, i ^ 1);
+        std::vector<void *> outs(nout);
+        for (unsigned k = 0; k < nout; k++) outs[k] = (char *)yout[i].p + (size_t)k * cap * q->esz;
+        size_t n = 0;
+        if (csdr_chain_process(q, (const csdr_cf32 *)xin[i].p, nx, nx, outs.data(), cap, &n) != 0) {
+            if (wr.valid()) wr.get();
+            rd.get();
+            return -1;                                      // csdr_last_error() holds the reason
+        }
+        consumed += nx;
+        const size_t take = (size_t)std::min<uint64_t>(n, limit - produced);
+        if (wr.valid() && !wr.get()) { rd.get(); throw CudaError{"chain_run_file: write failed"}; }
+        wr = std::async(std::launch::async, [&fout, outs, take, nout, esz = q->esz]() {
+            for (unsigned k = 0; k < nout; k++)
+                if (take && fwrite(outs[k], esz, take, fout[k].f) != take) return false;
+            return true;
+        });
+        produced += take;
+    }
+    if (rd.valid()) rd.get();
+    if (wr.valid() && !wr.get()) throw CudaError{"chain_run_file: write failed"};
+    if (n_in) *n_in = consumed;
+    if (n_out) *n_out = produced;
+    return 0;
+    API_END(-1)
+}
+
 int csdr_chain_seek(csdr_chain q, uint64_t n_prior)
 {
     API_BEGIN

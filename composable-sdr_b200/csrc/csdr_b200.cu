@@ -17,6 +17,7 @@
 #include "wbfm.cuh"
 
 #include <atomic>
+#include <future>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>

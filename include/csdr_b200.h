@@ -210,6 +210,15 @@ size_t   csdr_chain_max_output(csdr_chain q, size_t nx); /* upper bound of sampl
  * overlapped with compute).  Returns 0 on success. */
 int      csdr_chain_process(csdr_chain q, const csdr_cf32 *x, size_t nx, size_t x_stride,
                             void *const *outs, size_t out_cap, size_t *n_out);
+/* File to file(s): the source and sinks either side of the path as apps/SoapySDR.hs wires them --
+ * readFromFile (Source.chs:259-271: raw interleaved little-endian float32 I/Q, arrays of `chunk` samples; 0 = 2^24),
+ * takeNArr numsamples behind the resampler (SoapySDR.hs:207; 0 = the whole file), fileSink (Sink.hs:29-34) named
+ * <out_name>.cf32, or <out_name>_ch<K>.cf32 (K = 1..C) behind the channelizer without --mix (SoapySDR.hs:222-240).
+ * Demodulated outputs are raw float32 files (.f32) instead of the reference's libsndfile AU/WAV containers.
+ * Reading, the chain and writing overlap (pinned staging buffers).  *n_in: input samples consumed, *n_out: samples
+ * written per output file. */
+int      csdr_chain_run_file(csdr_chain q, const char *in_path, const char *out_name, uint64_t numsamples, size_t chunk,
+                             uint64_t *n_in, uint64_t *n_out);
 /* Seed the stream position for time-segment sharding: declare that `n_prior` input samples precede the next
  * call (NCO phase, half-band block alignment and resampler timing are closed-form in the sample index).  The
  * caller feeds csdr_chain_warmup_len() samples of real history first and discards the outputs they produce. */
