@@ -30,7 +30,8 @@ def build(force=False, verbose=False):
     srcs = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC))]
     srcs.append(os.path.join(HERE, "..", "include", "csdr_b200.h"))
     if force or _stale(LIB, srcs):
-        cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
+        # CSDR_NVCC_EXTRA: extra -D flags of the timing experiments (scripts/exp_*.py); never set in a normal build
+        cmd = [nvcc_path()] + NVCC_FLAGS + os.environ.get("CSDR_NVCC_EXTRA", "").split() + (["-Xptxas", "-v"] if verbose else []) + \
               ["-o", LIB, os.path.join(CSRC, "csdr_b200.cu")]
         subprocess.check_call(cmd)
     compat_src = os.path.join(CSRC, "liquid_compat.c")

@@ -93,10 +93,16 @@ __host__ __device__ constexpr int fe_std_tc(int S)
     return S == 1 ? 1792 : S == 2 ? 896 : S == 3 ? 400 : S == 4 ? 208 : S == 5 ? 96 : 48;
 }
 // variant 1 (k_frontend_direct): TMA tensor copy into a swizzled tile that IS the top level; the first stage reads
-// pairs from it and mixes in registers; three CTAs per SM
+// pairs from it and mixes in registers.  Tiles of ~6500 raw samples (96 KB of shared memory, two CTAs per SM): the
+// filter halo (368 raw samples for S = 3) and the per-tile barriers weigh half as much as with 3440-sample tiles and
+// three CTAs (measured 314 vs 328 us per 2^27 samples; 784 and up fall off a cliff, 640 is slower)
 __host__ __device__ constexpr int fe_std_tc_direct(int S)
 {
-    return S == 1 ? 1536 : S == 2 ? 768 : S == 3 ? 384 : S == 4 ? 192 : S == 5 ? 64 : 32;
+#ifdef CSDR_FE_TC3      // tile-size experiments: output samples per tile for S = 3 (scaled for the other S)
+    return S == 1 ? 4 * CSDR_FE_TC3 : S == 2 ? 2 * CSDR_FE_TC3 : S == 3 ? CSDR_FE_TC3 : S == 4 ? CSDR_FE_TC3 / 2 : S == 5 ? 64 : 32;
+#else
+    return S == 1 ? 3072 : S == 2 ? 1536 : S == 3 ? 768 : S == 4 ? 384 : S == 5 ? 64 : 32;
+#endif
 }
 // variant 2 (k_frontend_ws): smaller tiles so that three CTAs with the double-buffered hand-over level fit an SM
 __host__ __device__ constexpr int fe_std_tc_ws(int S)

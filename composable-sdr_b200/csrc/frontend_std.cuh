@@ -447,8 +447,11 @@ __device__ __forceinline__ void fe_copy_staging(const FrontendParams &p, const F
 #else
 #define FE_NOFILL 0
 #endif
+#ifndef CSDR_FE_MINB
+#define CSDR_FE_MINB 2
+#endif
 template <int S>
-__global__ void __launch_bounds__(kFeNT, 3) k_frontend_direct(const CSDR_GRID_CONSTANT FrontendParams p, const CSDR_GRID_CONSTANT FeTmap tmap)
+__global__ void __launch_bounds__(kFeNT, CSDR_FE_MINB) k_frontend_direct(const CSDR_GRID_CONSTANT FrontendParams p, const CSDR_GRID_CONSTANT FeTmap tmap)
 {
     constexpr FeGeom G = FeStd<S, 1>::G;
     constexpr int NS = G.n[S];

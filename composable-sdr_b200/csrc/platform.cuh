@@ -63,9 +63,12 @@ __device__ inline void tma_load_rows(void *dst, const FeTmap *tm, int row0, int 
 {
     const float2 *src = tm->base + (long long)stream * tm->stream_stride + (long long)row0 * 16;
     float2 *d = reinterpret_cast<float2 *>(dst);
+    // like the hardware, the swizzle is a function of the shared-memory ADDRESS (bits 7-9 of the row's address), so a
+    // second box that starts at a row which is not a multiple of 8 continues the pattern of the first
+    const int phase = (int)((reinterpret_cast<uintptr_t>(dst) >> 7) & 7);
     for (int r = 0; r < rows; r++)
         for (int c = 0; c < 8; c++)
-            for (int k = 0; k < 2; k++) d[(r * 8 + (c ^ (r & 7))) * 2 + k] = src[r * 16 + c * 2 + k];
+            for (int k = 0; k < 2; k++) d[(r * 8 + (c ^ ((r + phase) & 7))) * 2 + k] = src[r * 16 + c * 2 + k];
 }
 #else
 struct alignas(64) FeTmap { unsigned long long opaque[16]; };

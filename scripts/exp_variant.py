@@ -4,6 +4,9 @@ ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "scripts"))
 import torch
 import composable_sdr_b200 as cs
+if os.environ.get("CSDR_EXP_LIB"):                 # a variant library built with CSDR_NVCC_EXTRA (see exp_build.sh)
+    from composable_sdr_b200 import _lib
+    _lib.LIB_PATH = os.path.abspath(os.environ["CSDR_EXP_LIB"])
 from bench_configs import sig
 n = 1 << 27
 x = sig(n, 1)

@@ -67,8 +67,8 @@ void launch(dim3 grid, dim3 block, size_t smem_bytes, K kernel, Args... args)
     g_blockDim = {block.x, block.y, block.z};
     g_gridDim = {grid.x, grid.y, grid.z};
     unsigned nthreads = block.x * block.y * block.z;
-    std::vector<unsigned char> smem(smem_bytes + 64);
-    g_dyn_smem = (unsigned char *)(((uintptr_t)smem.data() + 15) & ~(uintptr_t)15);
+    std::vector<unsigned char> smem(smem_bytes + 1024 + 64);          // 1024-byte aligned like the swizzled TMA tiles need
+    g_dyn_smem = (unsigned char *)(((uintptr_t)smem.data() + 1023) & ~(uintptr_t)1023);
     for (unsigned bz = 0; bz < grid.z; bz++)
     for (unsigned by = 0; by < grid.y; by++)
     for (unsigned bx = 0; bx < grid.x; bx++) {
