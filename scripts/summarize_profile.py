@@ -72,8 +72,11 @@ json.dump({"kernel": "k_frontend", "chunk_samples": 1 << 26,
            "dram_bytes_read": sum(rd) / len(rd), "dram_bytes_write": sum(wr) / len(wr),
            "source": f"profiles/{tag}_frontend_ncu.txt (ncu --set full, 2^26-sample launch)"},
           open(os.path.join(OUT, "traffic.json"), "w"), indent=1)
-# back-end kernels (one launch each), same metric list
-with open(os.path.join(OUT, f"{tag}_backend_ncu.txt"), "w") as f:
+# back-end kernels (one launch each), same metric list; kept as is when this gpurun call captured none of them
+_be = ("k_agc_chain", "k_be_emit", "k_be_prep", "k_dc_local", "k_pfb_tile", "k_pfb_ring")
+with open(os.path.join(OUT, f"{tag}_backend_ncu.txt"),
+          "w" if any(os.path.exists(os.path.join(G, f"prof_{k}.ncu-rep")) for k in _be) else "a") as f:
+  if f.mode == "w":
     f.write("# ncu --set full --clock-control none -k regex:<kernel> -s 4 -c 1 python bench.py --steps 2 --warmup 3 --log2n 26 --no-cpu\n"
             "# (k_pfb_*: python scripts/prof_c3.py 16|1024 agc, 2^24 input samples)\n")
     for k in ("k_agc_chain", "k_be_emit", "k_be_prep", "k_dc_local", "k_pfb_tile", "k_pfb_ring"):
