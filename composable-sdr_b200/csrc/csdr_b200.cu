@@ -247,7 +247,7 @@ struct Frontend {
         for (auto &h : hist) { h.ensure(hb); CK(cudaMemsetAsync(h.p, 0, h.cap, c.stream)); }
         bank.ensure(ms.bank.size() * sizeof(float));
         CK(cudaMemcpyAsync(bank.p, ms.bank.data(), ms.bank.size() * sizeof(float), cudaMemcpyHostToDevice, c.stream));
-        fe_threads = geo.std_kernel ? kFeNT : 256;
+        fe_threads = !geo.std_kernel ? 256 : geo.variant == 2 ? 2 * kFeWsGroup : kFeNT;
         if (kernel_direct) {
             CK(cudaFuncSetAttribute(kernel_direct, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)geo.smem_bytes));
             CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kernel_direct, fe_threads, geo.smem_bytes));

@@ -13,7 +13,7 @@
 namespace csdr {
 
 #ifndef CSDR_FE_NT
-#define CSDR_FE_NT 256
+#define CSDR_FE_NT 384
 #endif
 constexpr int kFeNT = CSDR_FE_NT;   // threads per CTA of the compile-time-geometry kernels
 
@@ -40,7 +40,13 @@ __host__ __device__ constexpr FeGeom fe_make_geom(int S, int Tc, const int *m, i
     // outputs per thread slot: 8 everywhere but the last (longest, lowest-rate) stage.  Fewer outputs per slot keep
     // more threads busy but re-read shared memory more often, and shared-memory bandwidth is what binds this kernel
     // (measured: slots 8/4/2 -> 236 us, 8/8/4 -> 227 us per 2^26 samples).
-    for (int s = 0; s < S; s++) { g.m[s] = m[s]; g.R[s] = (s == 0 && S > 1) ? 4 : 8; }
+#ifndef CSDR_FE_R0          // slot-width experiments (scripts/exp_build.sh): last stage / middle stages
+#define CSDR_FE_R0 4
+#endif
+#ifndef CSDR_FE_R1
+#define CSDR_FE_R1 8
+#endif
+    for (int s = 0; s < S; s++) { g.m[s] = m[s]; g.R[s] = (s == 0 && S > 1) ? CSDR_FE_R0 : (s == S - 1) ? 8 : CSDR_FE_R1; }
     // raw = 1: the top level is the raw tile itself as the TMA tensor copy delivers it: whole rows of 16 samples
     // (128 bytes), 128-byte swizzle, at the start of shared memory (1024-byte aligned).  The first half-band stage
     // reads (even, odd) pairs from it with 16-byte loads, 8 outputs per thread slot = one row per slot.
@@ -93,15 +99,18 @@ __host__ __device__ constexpr int fe_std_tc(int S)
     return S == 1 ? 1792 : S == 2 ? 896 : S == 3 ? 400 : S == 4 ? 208 : S == 5 ? 96 : 48;
 }
 // variant 1 (k_frontend_direct): TMA tensor copy into a swizzled tile that IS the top level; the first stage reads
-// pairs from it and mixes in registers.  Tiles of ~6500 raw samples (96 KB of shared memory, two CTAs per SM): the
-// filter halo (368 raw samples for S = 3) and the per-tile barriers weigh half as much as with 3440-sample tiles and
-// three CTAs (measured 314 vs 328 us per 2^27 samples; 784 and up fall off a cliff, 640 is slower)
+// pairs from it and mixes in registers.  Tiles of ~6100 raw samples (two CTAs of 384 threads per SM, 80 registers):
+// the tile is as large as the first stage can finish in ONE round of thread slots (n[S-1] / 8 <= 384) and the
+// resampler in one round of push pairs (Tc / 2 <= 384), so no warp runs two slots back to back while others idle.
+// Measured per 2^27 samples: 3440-sample tiles, three CTAs of 256: 328 us; 6528-sample tiles, two CTAs of 256
+// (two rounds in the first stage): 315; 6144-sample tiles, two CTAs of 384: 300; 416 threads with 6528: 307;
+// 352 with 5632: 313; narrower slots in the lower stages (more threads busy, more shared-memory reads): 313-322.
 __host__ __device__ constexpr int fe_std_tc_direct(int S)
 {
 #ifdef CSDR_FE_TC3      // tile-size experiments: output samples per tile for S = 3 (scaled for the other S)
     return S == 1 ? 4 * CSDR_FE_TC3 : S == 2 ? 2 * CSDR_FE_TC3 : S == 3 ? CSDR_FE_TC3 : S == 4 ? CSDR_FE_TC3 / 2 : S == 5 ? 64 : 32;
 #else
-    return S == 1 ? 3072 : S == 2 ? 1536 : S == 3 ? 768 : S == 4 ? 384 : S == 5 ? 64 : 32;
+    return S == 1 ? 2880 : S == 2 ? 1440 : S == 3 ? 720 : S == 4 ? 336 : S == 5 ? 144 : 32;
 #endif
 }
 // variant 2 (k_frontend_ws): smaller tiles so that three CTAs with the double-buffered hand-over level fit an SM

@@ -65,7 +65,7 @@ long long emu_frontend(float rate, float As, int mix_mode, float freq, int quant
     void (*kernel)(FrontendParams) = k_frontend;
     void (*kernel_direct)(FrontendParams, FeTmap) = nullptr;
     if (g.std_kernel) {
-        nthreads = kFeNT;
+        nthreads = g.variant == 2 ? 2 * kFeWsGroup : kFeNT;
         if (g.variant == 0) {
             switch (ms.S) {
             case 1: kernel = k_frontend_std<1>; break;
