@@ -21,7 +21,11 @@ SIGNATURES = {
     "csdr_device_count": (_i, []), "csdr_set_device": (_i, [_i]),
     "csdr_host_alloc": (_vp, [_sz]), "csdr_host_free": (None, [_vp]),
     "csdr_kernel_launches": (C.c_uint64, []), "csdr_synchronize": (_i, []),
-    "csdr_set_option": (_i, [_i, _i]), "csdr_get_option": (_i, [_i]),
+    "csdr_set_option": (_i, [_i, _i]), "csdr_get_option": (_i, [_i]), "csdr_handle_kind": (_i, [_vp]),
+    "csdr_nco_crcf_adjust_frequency": (None, [_vp, _f]), "csdr_nco_crcf_adjust_phase": (None, [_vp, _f]),
+    "csdr_nco_crcf_step": (None, [_vp]), "csdr_nco_crcf_reset": (None, [_vp]), "csdr_nco_crcf_get_phase": (_f, [_vp]),
+    "csdr_nco_crcf_get_frequency": (_f, [_vp]), "csdr_nco_crcf_cexpf": (None, [_vp, _vp]),
+    "csdr_nco_crcf_pll_set_bandwidth": (None, [_vp, _f]), "csdr_nco_crcf_pll_step": (None, [_vp, _f]),
     "csdr_nco_crcf_create": (_vp, [_i]), "csdr_nco_crcf_destroy": (None, [_vp]), "csdr_nco_crcf_print": (None, [_vp]),
     "csdr_nco_crcf_set_frequency": (None, [_vp, _f]), "csdr_nco_crcf_set_phase": (None, [_vp, _f]),
     "csdr_nco_crcf_get_phase_word": (C.c_uint32, [_vp]), "csdr_nco_crcf_get_freq_word": (C.c_uint32, [_vp]),

@@ -37,7 +37,7 @@ def build(force=False, verbose=False):
     compat_src = os.path.join(CSRC, "liquid_compat.c")
     if force or _stale(COMPAT, [compat_src, LIB]):
         subprocess.check_call(["gcc", "-O2", "-fPIC", "-shared", "-o", COMPAT, compat_src,
-                               "-L" + HERE, "-lcsdr_b200", "-Wl,-rpath,$ORIGIN"])
+                               "-L" + HERE, "-lcsdr_b200", "-ldl", "-Wl,-rpath,$ORIGIN"])
     return LIB
 
 

@@ -5,7 +5,7 @@
 // `compact` only re-chunks (Trans.hs:58-85): here whole frames of C samples are consumed as they arrive and the
 // < C left-over samples wait in the handle.  Included at the end of csdr_b200.cu.
 
-struct csdr_chain_s {
+struct csdr_chain_s : Tagged {
     Ctx ctx;
     csdr_chain_cfg cfg;
     unsigned C = 1, nstreams = 1, nout = 1;
@@ -38,7 +38,7 @@ struct csdr_chain_s {
         return ev_pool[i];
     }
 
-    csdr_chain_s(const csdr_chain_cfg &c) : ctx(c.device), cfg(c) {}
+    csdr_chain_s(const csdr_chain_cfg &c) : Tagged(TAG_CHAIN), ctx(c.device), cfg(c) {}
     ~csdr_chain_s()
     {
         cudaSetDevice(ctx.device);
@@ -288,13 +288,14 @@ csdr_chain csdr_chain_create(const csdr_chain_cfg *cfg)
     return q.release();
     API_END(nullptr)
 }
-int csdr_chain_destroy(csdr_chain q) { delete q; return 0; }
-unsigned csdr_chain_num_outputs(csdr_chain q) { return q->nout; }
-size_t csdr_chain_out_elem_size(csdr_chain q) { return q->esz; }
-size_t csdr_chain_max_output(csdr_chain q, size_t nx) { return chain_max_out(q, nx); }
-void *csdr_chain_cuda_stream(csdr_chain q) { return (void *)q->ctx.stream; }
+int csdr_chain_destroy(csdr_chain q) { if (!q) return 0; REQUIRE(q, TAG_CHAIN, -1); delete q; return 0; }
+unsigned csdr_chain_num_outputs(csdr_chain q) { REQUIRE(q, TAG_CHAIN, 0); return q->nout; }
+size_t csdr_chain_out_elem_size(csdr_chain q) { REQUIRE(q, TAG_CHAIN, 0); return q->esz; }
+size_t csdr_chain_max_output(csdr_chain q, size_t nx) { REQUIRE(q, TAG_CHAIN, 0); return chain_max_out(q, nx); }
+void * csdr_chain_cuda_stream(csdr_chain q) { REQUIRE(q, TAG_CHAIN, nullptr); return (void *)q->ctx.stream; }
 void csdr_chain_print(csdr_chain q)
 {
+    REQUIRE(q, TAG_CHAIN, );
     const csdr_chain_cfg &c = q->cfg;
     printf("csdr_b200 chain: sr %.1f offset %.1f bw %.1f demod %d kf %.3f agc %.1f dB channels %u mix %d streams %u\n",
            c.samplerate, c.offset_hz, c.bandwidth_hz, c.demod, c.kf, c.agc_thresh_db, q->C, c.mix, q->nstreams);
@@ -312,6 +313,7 @@ int csdr_chain_process(csdr_chain q, const csdr_cf32 *x, size_t nx, size_t x_str
                        size_t *n_out)
 {
     if (n_out) *n_out = 0;
+    REQUIRE(q, TAG_CHAIN, -1);
     API_BEGIN
     q->ctx.use();
     const Ctx &c = q->ctx;
@@ -391,6 +393,7 @@ int csdr_chain_process(csdr_chain q, const csdr_cf32 *x, size_t nx, size_t x_str
 int csdr_chain_run_file(csdr_chain q, const char *in_path, const char *out_name, uint64_t numsamples, size_t chunk,
                         uint64_t *n_in, uint64_t *n_out)
 {
+    REQUIRE(q, TAG_CHAIN, -1);
     API_BEGIN
     if (!in_path || !out_name) throw CudaError{"chain_run_file: null path"};
     if (q->nstreams != 1) throw CudaError{"chain_run_file: one stream per file"};
@@ -456,6 +459,7 @@ int csdr_chain_run_file(csdr_chain q, const char *in_path, const char *out_name,
 
 int csdr_chain_seek(csdr_chain q, uint64_t n_prior)
 {
+    REQUIRE(q, TAG_CHAIN, -1);
     API_BEGIN
     if (q->C > 1) throw CudaError{"chain: seek with a channelizer is not implemented"};
     if (q->has_wb) throw CudaError{"chain: seek with DeWBFM is not implemented"};
@@ -466,6 +470,7 @@ int csdr_chain_seek(csdr_chain q, uint64_t n_prior)
 }
 size_t csdr_chain_warmup_len(csdr_chain q)
 {
+    REQUIRE(q, TAG_CHAIN, 0);
     // front-end FIR history + dc blocker settling (0.9995^k < 1e-9 after ~41.5k post-resample samples) + AGC
     double r = q->has_resamp ? (double)q->fe.ms.rate : 1.0;
     size_t w = (size_t)(q->has_resamp ? q->fe.geo.hcap : 0) + (size_t)std::ceil(45000.0 / r);
@@ -473,6 +478,7 @@ size_t csdr_chain_warmup_len(csdr_chain q)
 }
 int csdr_chain_profile(csdr_chain q, int enable)
 {
+    REQUIRE(q, TAG_CHAIN, -1);
     API_BEGIN
     q->fe.collect(q->ctx);
     q->fe.profile = enable != 0;
@@ -482,6 +488,7 @@ int csdr_chain_profile(csdr_chain q, int enable)
 }
 double csdr_chain_frontend_ms(csdr_chain q, uint64_t *launches)
 {
+    REQUIRE(q, TAG_CHAIN, -1.0);
     API_BEGIN
     q->fe.collect(q->ctx);
     if (launches) *launches = q->fe.prof_launches;
@@ -490,6 +497,7 @@ double csdr_chain_frontend_ms(csdr_chain q, uint64_t *launches)
 }
 uint64_t csdr_chain_agc_fixups(csdr_chain q)
 {
+    REQUIRE(q, TAG_CHAIN, 0);
     API_BEGIN
     unsigned long long v = q->be.read_fixups(q->ctx);
     unsigned long long d = v - q->fixups_seen;
@@ -499,6 +507,7 @@ uint64_t csdr_chain_agc_fixups(csdr_chain q)
 }
 int csdr_chain_agc_counters(csdr_chain q, uint64_t out[3])
 {
+    REQUIRE(q, TAG_CHAIN, -1);
     API_BEGIN
     unsigned long long v[3] = {0, 0, 0};
     CK(cudaMemcpyAsync(v, q->be.fixups.p, sizeof(v), cudaMemcpyDeviceToHost, q->ctx.stream));
@@ -509,6 +518,7 @@ int csdr_chain_agc_counters(csdr_chain q, uint64_t out[3])
 }
 int csdr_chain_agc_plan(csdr_chain q, int out[2])
 {
+    REQUIRE(q, TAG_CHAIN, -1);
     API_BEGIN
     out[0] = q->be.last_L; out[1] = q->be.last_W;
     return 0;

@@ -17,6 +17,7 @@
 #include "wbfm.cuh"
 
 #include <atomic>
+#include <map>
 #include <future>
 #include <cstdio>
 #include <cstdlib>
@@ -130,6 +131,22 @@ struct Staging {
         c.sync();
     }
 };
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-function (and per-device) limit shared by every handle that uses
+// the kernel: it is only ever RAISED, so that a later handle with a smaller tile cannot starve an earlier one.
+template <class K>
+void raise_dyn_smem(K kernel, size_t bytes)
+{
+    static std::mutex mu;
+    static std::map<std::pair<const void *, int>, size_t> seen;
+    int dev = 0;
+    CK(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lk(mu);
+    size_t &cur = seen[{reinterpret_cast<const void *>(kernel), dev}];
+    if (bytes <= cur) return;
+    CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    cur = bytes;
+}
 
 int grid_for(long long n, int block, int sms, int per_sm = 8)
 {
@@ -249,10 +266,10 @@ struct Frontend {
         CK(cudaMemcpyAsync(bank.p, ms.bank.data(), ms.bank.size() * sizeof(float), cudaMemcpyHostToDevice, c.stream));
         fe_threads = !geo.std_kernel ? 256 : geo.variant == 2 ? 2 * kFeWsGroup : kFeNT;
         if (kernel_direct) {
-            CK(cudaFuncSetAttribute(kernel_direct, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)geo.smem_bytes));
+            raise_dyn_smem(kernel_direct, geo.smem_bytes);
             CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kernel_direct, fe_threads, geo.smem_bytes));
         } else {
-            CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)geo.smem_bytes));
+            raise_dyn_smem(kernel, geo.smem_bytes);
             CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kernel, fe_threads, geo.smem_bytes));
         }
         if (ctas_per_sm < 1) throw CudaError{"frontend: tile does not fit in shared memory"};
@@ -622,7 +639,7 @@ struct Channelizer {
         if (F > 256) F = 256;
         smem = (size_t)F * M * sizeof(float2) * (log2M >= 0 ? 1 : 2);
         if (smem > 200 * 1024) throw CudaError{"firpfbch: channel count too large for one CTA tile"};
-        CK(cudaFuncSetAttribute(k_pfb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        raise_dyn_smem(k_pfb, smem);
         tile_kernel = nullptr;
         if (!over2 && log2M >= 1 && (int)M <= kPfbTileMaxM && (int)P == kPfbTileP) {
             switch (log2M) {
@@ -636,12 +653,12 @@ struct Channelizer {
             for (unsigned i = 0; i < M / 2; i++) tp.tw[i] = t[i];
             for (unsigned k = 0; k < P; k++) for (unsigned n = 0; n < M; n++) tp.h[k * M + n] = h[(M - 1 - n) + k * M];
             tile_smem = (size_t)(kPfbTileF + kPfbTileP - 1) * (M + 2) * sizeof(float2);
-            CK(cudaFuncSetAttribute(tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem));
+            raise_dyn_smem(tile_kernel, tile_smem);
         }
         ring_ok = !over2 && log2M >= 7 && M <= 1024 && (int)P == kPfbRingP;
         if (ring_ok) {
             ring_kernel = pfb_ring_lfz(log2M) == 4 ? k_pfb_ring<4> : k_pfb_ring<5>;
-            CK(cudaFuncSetAttribute(ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pfb_ring_smem((int)M, log2M)));
+            raise_dyn_smem(ring_kernel, pfb_ring_smem((int)M, log2M));
             CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ring_ctas, ring_kernel, 2 * (int)M / kPfbRingCPT, pfb_ring_smem((int)M, log2M)));
             if (ring_ctas < 1) ring_ok = false;
         }
@@ -801,24 +818,43 @@ struct WbfmTail {
 }  // namespace
 
 // ------------------------------------------------------------------------------------------ handles
-struct csdr_nco_s {
+// Every handle starts with a tag word: the liquid-named alias library (liquid_compat.c) uses it to tell a handle of this
+// library from an object created by the real libliquid where a liquid family has constructors on both sides
+// (iirfilt_crcf_create_prototype stays liquid's, Liquid.chs:553-571), and the C ABI uses it to reject foreign pointers.
+constexpr uint64_t kTagBase = 0x4353445242323030ULL;      // "CSDRB200"
+enum { TAG_NCO = 1, TAG_MSRESAMP, TAG_IIRFILT, TAG_FIRPFBCH, TAG_FIRPFBCH2, TAG_AGC, TAG_FREQDEM, TAG_AMPMODEM, TAG_IIRFILT_RRRF,
+       TAG_FIRDECIM, TAG_CHAIN };
+struct Tagged { uint64_t tag; explicit Tagged(int kind) : tag(kTagBase + (uint64_t)kind) {} ~Tagged() { tag = 0; } };
+struct csdr_nco_s : Tagged {
     Ctx ctx; Staging st; int type; uint32_t theta = 0, dtheta = 0;
-    csdr_nco_s(int t) : ctx(-1), type(t) {}
+    float pll_alpha = 0.1f, pll_beta = 0.31622776f;        // NCO_PLL_BANDWIDTH_DEFAULT = 0.1, beta = sqrt(alpha) (liquid nco.c)
+    csdr_nco_s(int t) : Tagged(TAG_NCO), ctx(-1), type(t) {}
     int quantize() const { return (type == 1 && g_options[CSDR_OPT_VCO_DIRECT]) ? 0 : 1; }
 };
-struct csdr_msresamp_s { Ctx ctx; Staging st; Frontend fe; csdr_msresamp_s() : ctx(-1) {} };
-struct csdr_iirfilt_s { Ctx ctx; Staging st; Backend be; float alpha; csdr_iirfilt_s() : ctx(-1) {} };
-struct csdr_firpfbch_s { Ctx ctx; Staging st; Channelizer ch; DevBuf tmp; csdr_firpfbch_s() : ctx(-1) {} };
-struct csdr_firpfbch2_s { Ctx ctx; Staging st; Channelizer ch; csdr_firpfbch2_s() : ctx(-1) {} };
-struct csdr_agc_s {
+struct csdr_msresamp_s : Tagged { Ctx ctx; Staging st; Frontend fe; csdr_msresamp_s() : Tagged(TAG_MSRESAMP), ctx(-1) {} };
+struct csdr_iirfilt_s : Tagged { Ctx ctx; Staging st; Backend be; float alpha; csdr_iirfilt_s() : Tagged(TAG_IIRFILT), ctx(-1) {} };
+struct csdr_firpfbch_s : Tagged { Ctx ctx; Staging st; Channelizer ch; DevBuf tmp; csdr_firpfbch_s() : Tagged(TAG_FIRPFBCH), ctx(-1) {} };
+struct csdr_firpfbch2_s : Tagged { Ctx ctx; Staging st; Channelizer ch; csdr_firpfbch2_s() : Tagged(TAG_FIRPFBCH2), ctx(-1) {} };
+struct csdr_agc_s : Tagged {
     Ctx ctx; Staging st; Backend be; bool started = false;
     float bw = 1e-2f, g = 1.0f, thr = 0.0f; unsigned timeout = 100; int mode = SQ_DISABLED;
-    csdr_agc_s() : ctx(-1) {}
+    csdr_agc_s() : Tagged(TAG_AGC), ctx(-1) {}
 };
-struct csdr_freqdem_s { Ctx ctx; Staging st; float kf, ref; float2 prev; csdr_freqdem_s() : ctx(-1) { prev.x = prev.y = 0; } };
-struct csdr_ampmodem_s { Ctx ctx; Staging st; AmDemod am; csdr_ampmodem_s() : ctx(-1) {} };
-struct csdr_iirfilt_rrrf_s { Ctx ctx; Staging st; Iir2Filter f; csdr_iirfilt_rrrf_s() : ctx(-1) {} };
-struct csdr_firdecim_s { Ctx ctx; Staging st; FirDecimator d; csdr_firdecim_s() : ctx(-1) {} };
+struct csdr_freqdem_s : Tagged { Ctx ctx; Staging st; float kf, ref; float2 prev; csdr_freqdem_s() : Tagged(TAG_FREQDEM), ctx(-1) { prev.x = prev.y = 0; } };
+struct csdr_ampmodem_s : Tagged { Ctx ctx; Staging st; AmDemod am; csdr_ampmodem_s() : Tagged(TAG_AMPMODEM), ctx(-1) {} };
+struct csdr_iirfilt_rrrf_s : Tagged { Ctx ctx; Staging st; Iir2Filter f; csdr_iirfilt_rrrf_s() : Tagged(TAG_IIRFILT_RRRF), ctx(-1) {} };
+struct csdr_firdecim_s : Tagged { Ctx ctx; Staging st; FirDecimator d; csdr_firdecim_s() : Tagged(TAG_FIRDECIM), ctx(-1) {} };
+
+namespace {
+// NULL / foreign handle: report instead of dereferencing (create() returns NULL on failure, e.g. without a CUDA device)
+bool bad_handle(const void *q, int kind, const char *what)
+{
+    if (q && static_cast<const Tagged *>(q)->tag == kTagBase + (uint64_t)kind) return false;
+    set_err(std::string(what) + (q ? ": not a handle of this library (or already destroyed)" : ": NULL handle"));
+    return true;
+}
+}  // namespace
+#define REQUIRE(q, kind, ret) do { if (bad_handle((q), (kind), __func__)) return ret; } while (0)
 
 #define API_BEGIN clear_err(); try {
 #define API_END(ret_fail)                                                    \
@@ -852,15 +888,16 @@ csdr_nco csdr_nco_crcf_create(int type)
 {
     API_BEGIN return new csdr_nco_s(type); API_END(nullptr)
 }
-void csdr_nco_crcf_destroy(csdr_nco q) { delete q; }
+void csdr_nco_crcf_destroy(csdr_nco q) { if (!q) return; REQUIRE(q, TAG_NCO, ); delete q; }
 void csdr_nco_crcf_print(csdr_nco q)
 {
+    REQUIRE(q, TAG_NCO, );
     if (q) printf("nco [phase: 0x%.8x rad, freq: 0x%.8x rad/sample]\n", q->theta, q->dtheta);
 }
-void csdr_nco_crcf_set_frequency(csdr_nco q, float dtheta) { q->dtheta = design::nco_constrain(dtheta); }
-void csdr_nco_crcf_set_phase(csdr_nco q, float theta) { q->theta = design::nco_constrain(theta); }
-uint32_t csdr_nco_crcf_get_phase_word(csdr_nco q) { return q->theta; }
-uint32_t csdr_nco_crcf_get_freq_word(csdr_nco q) { return q->dtheta; }
+void csdr_nco_crcf_set_frequency(csdr_nco q, float dtheta) { REQUIRE(q, TAG_NCO, ); q->dtheta = design::nco_constrain(dtheta); }
+void csdr_nco_crcf_set_phase(csdr_nco q, float theta) { REQUIRE(q, TAG_NCO, ); q->theta = design::nco_constrain(theta); }
+uint32_t csdr_nco_crcf_get_phase_word(csdr_nco q) { REQUIRE(q, TAG_NCO, 0); return q->theta; }
+uint32_t csdr_nco_crcf_get_freq_word(csdr_nco q) { REQUIRE(q, TAG_NCO, 0); return q->dtheta; }
 static void nco_mix(csdr_nco q, const csdr_cf32 *x, csdr_cf32 *y, unsigned n, int up)
 {
     API_BEGIN
@@ -875,8 +912,56 @@ static void nco_mix(csdr_nco q, const csdr_cf32 *x, csdr_cf32 *y, unsigned n, in
     q->st.finish(q->ctx, y, yd, bytes);
     API_END_VOID
 }
-void csdr_nco_crcf_mix_block_down(csdr_nco q, const csdr_cf32 *x, csdr_cf32 *y, unsigned n) { nco_mix(q, x, y, n, 0); }
-void csdr_nco_crcf_mix_block_up(csdr_nco q, const csdr_cf32 *x, csdr_cf32 *y, unsigned n) { nco_mix(q, x, y, n, 1); }
+// ---- the scalar members of liquid's nco_crcf family (nco.c, uint32 phase): the reference's stereo-FM pilot PLL
+// (pllCreate / pllStep, Liquid.chs:959-988) calls them on handles made by nco_crcf_create, so a library that
+// answers to nco_crcf_create has to answer to all of them.  Pure host arithmetic on the handle's phase / frequency words.
+// NCO(_get_phase): 2.0f*M_PI*(float)theta / (float)(1LLU<<32), evaluated in double, returned as float
+static float nco_word_to_rad(uint32_t w) { return (float)(2.0 * design::kPi * (double)(float)w / 4294967296.0); }
+void csdr_nco_crcf_adjust_frequency(csdr_nco q, float df) { REQUIRE(q, TAG_NCO, ); q->dtheta += design::nco_constrain(df); }
+void csdr_nco_crcf_adjust_phase(csdr_nco q, float dphi) { REQUIRE(q, TAG_NCO, ); q->theta += design::nco_constrain(dphi); }
+void csdr_nco_crcf_step(csdr_nco q) { REQUIRE(q, TAG_NCO, ); q->theta += q->dtheta; }
+void csdr_nco_crcf_reset(csdr_nco q) { REQUIRE(q, TAG_NCO, ); q->theta = 0; q->dtheta = 0; }
+float csdr_nco_crcf_get_phase(csdr_nco q) { REQUIRE(q, TAG_NCO, 0.0f); return nco_word_to_rad(q->theta); }
+float csdr_nco_crcf_get_frequency(csdr_nco q)
+{
+    REQUIRE(q, TAG_NCO, 0.0f);
+    const float d = nco_word_to_rad(q->dtheta);
+    return d > (float)design::kPi ? d - 2.0f * (float)design::kPi : d;
+}
+void csdr_nco_crcf_cexpf(csdr_nco q, csdr_cf32 *y)
+{
+    REQUIRE(q, TAG_NCO, );
+    if (!y) return;
+    if (q->quantize()) {
+        // NCO(_index): round the phase to 1024 table levels; sintab[i] = sinf(2 pi i / 1024), cos = sintab[i + 256]
+        const unsigned i = ((q->theta + (1u << 21)) >> 22) & 0x3ffu;
+        y->im = sinf((float)(2.0 * design::kPi * (double)i / 1024.0));
+        y->re = sinf((float)(2.0 * design::kPi * (double)((i + 256u) & 0x3ffu) / 1024.0));
+    } else {
+        const float th = nco_word_to_rad(q->theta);
+        y->re = cosf(th); y->im = sinf(th);
+    }
+}
+void csdr_nco_crcf_pll_set_bandwidth(csdr_nco q, float bw)
+{
+    REQUIRE(q, TAG_NCO, );
+    if (bw < 0.0f) { set_err("nco_crcf_pll_set_bandwidth: bandwidth must be positive"); return; }
+    q->pll_alpha = bw; q->pll_beta = sqrtf(bw);
+}
+void csdr_nco_crcf_pll_step(csdr_nco q, float dphi)
+{
+    REQUIRE(q, TAG_NCO, );
+    q->dtheta += design::nco_constrain(dphi * q->pll_alpha);      // adjust_frequency
+    q->theta += design::nco_constrain(dphi * q->pll_beta);        // adjust_phase
+}
+int csdr_handle_kind(const void *h)
+{
+    if (!h) return 0;
+    const uint64_t t = static_cast<const Tagged *>(h)->tag;
+    return (t > kTagBase && t <= kTagBase + TAG_CHAIN) ? (int)(t - kTagBase) : 0;
+}
+void csdr_nco_crcf_mix_block_down(csdr_nco q, const csdr_cf32 *x, csdr_cf32 *y, unsigned n) { REQUIRE(q, TAG_NCO, ); nco_mix(q, x, y, n, 0); }
+void csdr_nco_crcf_mix_block_up(csdr_nco q, const csdr_cf32 *x, csdr_cf32 *y, unsigned n) { REQUIRE(q, TAG_NCO, ); nco_mix(q, x, y, n, 1); }
 
 // ---------------------------------------------------------------- msresamp_crcf
 csdr_msresamp csdr_msresamp_crcf_create(float r, float As)
@@ -888,10 +973,11 @@ csdr_msresamp csdr_msresamp_crcf_create(float r, float As)
     return q.release();
     API_END(nullptr)
 }
-void csdr_msresamp_crcf_destroy(csdr_msresamp q) { delete q; }
-float csdr_msresamp_crcf_get_rate(csdr_msresamp q) { return q->fe.ms.rate; }
+void csdr_msresamp_crcf_destroy(csdr_msresamp q) { if (!q) return; REQUIRE(q, TAG_MSRESAMP, ); delete q; }
+float csdr_msresamp_crcf_get_rate(csdr_msresamp q) { REQUIRE(q, TAG_MSRESAMP, 0.0f); return q->fe.ms.rate; }
 void csdr_msresamp_crcf_print(csdr_msresamp q)
 {
+    REQUIRE(q, TAG_MSRESAMP, );
     const auto &ms = q->fe.ms;
     printf("multi-stage resampler (csdr_b200)\n  composite rate      : %12.10f\n", ms.rate);
     printf("  type                : %s\n", ms.interp ? "interp" : "decim");
@@ -901,6 +987,7 @@ void csdr_msresamp_crcf_print(csdr_msresamp q)
 }
 void csdr_msresamp_crcf_execute(csdr_msresamp q, const csdr_cf32 *x, unsigned nx, csdr_cf32 *y, unsigned *ny)
 {
+    REQUIRE(q, TAG_MSRESAMP, );
     if (ny) *ny = 0;
     API_BEGIN
     q->ctx.use();
@@ -912,17 +999,19 @@ void csdr_msresamp_crcf_execute(csdr_msresamp q, const csdr_cf32 *x, unsigned nx
     if (ny) *ny = (unsigned)n;
     API_END_VOID
 }
-unsigned csdr_msresamp_num_stages(csdr_msresamp q) { return q->fe.ms.S; }
-unsigned csdr_msresamp_stage_m(csdr_msresamp q, unsigned s) { return s < q->fe.ms.S ? q->fe.ms.st[s].m : 0; }
+unsigned csdr_msresamp_num_stages(csdr_msresamp q) { REQUIRE(q, TAG_MSRESAMP, 0); return q->fe.ms.S; }
+unsigned csdr_msresamp_stage_m(csdr_msresamp q, unsigned s) { REQUIRE(q, TAG_MSRESAMP, 0); return s < q->fe.ms.S ? q->fe.ms.st[s].m : 0; }
 int csdr_msresamp_stage_taps(csdr_msresamp q, unsigned s, float *h1)
 {
+    REQUIRE(q, TAG_MSRESAMP, -1);
     if (s >= q->fe.ms.S) return -1;
     memcpy(h1, q->fe.ms.st[s].h1.data(), q->fe.ms.st[s].h1.size() * sizeof(float));
     return 0;
 }
-uint32_t csdr_msresamp_resamp_step(csdr_msresamp q) { return q->fe.ms.step; }
+uint32_t csdr_msresamp_resamp_step(csdr_msresamp q) { REQUIRE(q, TAG_MSRESAMP, 0); return q->fe.ms.step; }
 int csdr_msresamp_resamp_bank(csdr_msresamp q, float *bank, unsigned *npfb)
 {
+    REQUIRE(q, TAG_MSRESAMP, -1);
     if (npfb) *npfb = q->fe.ms.npfb;
     if (bank) memcpy(bank, q->fe.ms.bank.data(), q->fe.ms.bank.size() * sizeof(float));
     return 0;
@@ -939,13 +1028,15 @@ csdr_iirfilt csdr_iirfilt_crcf_create_dc_blocker(float alpha)
     return q.release();
     API_END(nullptr)
 }
-void csdr_iirfilt_crcf_destroy(csdr_iirfilt q) { delete q; }
+void csdr_iirfilt_crcf_destroy(csdr_iirfilt q) { if (!q) return; REQUIRE(q, TAG_IIRFILT, ); delete q; }
 void csdr_iirfilt_crcf_print(csdr_iirfilt q)
 {
+    REQUIRE(q, TAG_IIRFILT, );
     printf("iir filter [normal]:\n  b :   %12.8f %12.8f\n  a :   %12.8f %12.8f\n", 1.0f, -1.0f, 1.0f, -1.0f + q->alpha);
 }
 void csdr_iirfilt_crcf_execute_block(csdr_iirfilt q, const csdr_cf32 *x, unsigned n, csdr_cf32 *y)
 {
+    REQUIRE(q, TAG_IIRFILT, );
     API_BEGIN
     if (!n) return;
     q->ctx.use();
@@ -968,15 +1059,17 @@ csdr_firpfbch csdr_firpfbch_crcf_create_kaiser(int type, unsigned M, unsigned m,
     return q.release();
     API_END(nullptr)
 }
-void csdr_firpfbch_crcf_destroy(csdr_firpfbch q) { delete q; }
+void csdr_firpfbch_crcf_destroy(csdr_firpfbch q) { if (!q) return; REQUIRE(q, TAG_FIRPFBCH, ); delete q; }
 void csdr_firpfbch_crcf_print(csdr_firpfbch q)
 {
+    REQUIRE(q, TAG_FIRPFBCH, );
     printf("firpfbch (analyzer) [%u channels]:\n", q->ch.M);
     for (size_t i = 0; i < q->ch.h.size(); i++) printf("  h[%3zu] = %12.8f + %12.8f*j\n", i, q->ch.h[i], 0.0f);
 }
-int csdr_firpfbch_taps(csdr_firpfbch q, float *h) { memcpy(h, q->ch.h.data(), q->ch.h.size() * sizeof(float)); return 0; }
+int csdr_firpfbch_taps(csdr_firpfbch q, float *h) { REQUIRE(q, TAG_FIRPFBCH, -1); memcpy(h, q->ch.h.data(), q->ch.h.size() * sizeof(float)); return 0; }
 int csdr_firpfbch_execute_block(csdr_firpfbch q, csdr_nco nco, const csdr_cf32 *x, unsigned n, csdr_cf32 *y)
 {
+    REQUIRE(q, TAG_FIRPFBCH, -1);
     API_BEGIN
     if (!n) return 0;
     q->ctx.use();
@@ -988,6 +1081,7 @@ int csdr_firpfbch_execute_block(csdr_firpfbch q, csdr_nco nco, const csdr_cf32 *
     // pre-rotate the whole chunk (Liquid.chs:847), tail included, into the channelizer's input slot
     float2 *slot = q->ch.input_slot(q->ctx, (size_t)nf * M + M);
     if (nco) {
+        if (bad_handle(nco, TAG_NCO, "csdr_firpfbch_execute_block (nco)")) return -1;
         launch(k_nco_mix, dim3(grid_for(n, 256, q->ctx.sms)), dim3(256), 0, q->ctx.stream, xd, slot, (long long)n,
                nco->theta, nco->dtheta, nco->quantize(), 0);
         nco->theta += (uint32_t)n * nco->dtheta;
@@ -1001,6 +1095,7 @@ int csdr_firpfbch_execute_block(csdr_firpfbch q, csdr_nco nco, const csdr_cf32 *
 }
 void csdr_firpfbch_crcf_analyzer_execute(csdr_firpfbch q, const csdr_cf32 *x, csdr_cf32 *y)
 {
+    REQUIRE(q, TAG_FIRPFBCH, );
     csdr_firpfbch_execute_block(q, nullptr, x, q->ch.M, y);
 }
 
@@ -1015,14 +1110,16 @@ csdr_firpfbch2 csdr_firpfbch2_crcf_create_kaiser(int type, unsigned M, unsigned 
     return q.release();
     API_END(nullptr)
 }
-void csdr_firpfbch2_crcf_destroy(csdr_firpfbch2 q) { delete q; }
+void csdr_firpfbch2_crcf_destroy(csdr_firpfbch2 q) { if (!q) return; REQUIRE(q, TAG_FIRPFBCH2, ); delete q; }
 void csdr_firpfbch2_crcf_print(csdr_firpfbch2 q)
 {
+    REQUIRE(q, TAG_FIRPFBCH2, );
     printf("firpfbch2_crcf: analyzer, channels: %u, semi-length: %u, %zu taps\n", q->ch.M, q->ch.m, q->ch.h.size());
 }
-int csdr_firpfbch2_taps(csdr_firpfbch2 q, float *h) { memcpy(h, q->ch.h.data(), q->ch.h.size() * sizeof(float)); return 0; }
+int csdr_firpfbch2_taps(csdr_firpfbch2 q, float *h) { REQUIRE(q, TAG_FIRPFBCH2, -1); memcpy(h, q->ch.h.data(), q->ch.h.size() * sizeof(float)); return 0; }
 int csdr_firpfbch2_execute_block(csdr_firpfbch2 q, const csdr_cf32 *x, unsigned n, csdr_cf32 *y)
 {
+    REQUIRE(q, TAG_FIRPFBCH2, -1);
     API_BEGIN
     q->ctx.use();
     const unsigned M = q->ch.M, M2 = M / 2, nf = n / M2;
@@ -1038,6 +1135,7 @@ int csdr_firpfbch2_execute_block(csdr_firpfbch2 q, const csdr_cf32 *x, unsigned 
 }
 void csdr_firpfbch2_crcf_execute(csdr_firpfbch2 q, const csdr_cf32 *x, csdr_cf32 *y)
 {
+    REQUIRE(q, TAG_FIRPFBCH2, );
     csdr_firpfbch2_execute_block(q, x, q->ch.M / 2, y);
 }
 
@@ -1046,7 +1144,7 @@ csdr_agc csdr_agc_crcf_create(void)
 {
     API_BEGIN return new csdr_agc_s(); API_END(nullptr)
 }
-void csdr_agc_crcf_destroy(csdr_agc q) { delete q; }
+void csdr_agc_crcf_destroy(csdr_agc q) { if (!q) return; REQUIRE(q, TAG_AGC, ); delete q; }
 static void agc_push_config(csdr_agc q)
 {
     // (re)build the device state from the host-side configuration; called lazily before the first execute
@@ -1059,15 +1157,17 @@ static void agc_push_config(csdr_agc q)
 static LaneState agc_lane(csdr_agc q) { agc_push_config(q); return q->be.read_lane(q->ctx, 0); }
 void csdr_agc_crcf_print(csdr_agc q)
 {
+    REQUIRE(q, TAG_AGC, );
     API_BEGIN
     LaneState l = agc_lane(q);
     printf("agc [rssi: %12.4f dB, output gain: %.3f dB, bw: %12.4e, locked: no, squelch: %s]:\n",
            -20 * log10((double)l.g), 0.0, q->bw, q->mode == SQ_DISABLED ? "disabled" : "enabled");
     API_END_VOID
 }
-void csdr_agc_crcf_set_bandwidth(csdr_agc q, float bt) { q->bw = bt; if (q->started) q->be.agc_bw = bt; }
+void csdr_agc_crcf_set_bandwidth(csdr_agc q, float bt) { REQUIRE(q, TAG_AGC, ); q->bw = bt; if (q->started) q->be.agc_bw = bt; }
 void csdr_agc_crcf_set_signal_level(csdr_agc q, float x2)
 {
+    REQUIRE(q, TAG_AGC, );
     API_BEGIN
     q->g = 1.0f / x2;
     if (q->started) { LaneState l = q->be.read_lane(q->ctx, 0); l.g = q->g; l.y2p = 1.0f; q->be.write_lane(q->ctx, 0, l); }
@@ -1075,19 +1175,22 @@ void csdr_agc_crcf_set_signal_level(csdr_agc q, float x2)
 }
 void csdr_agc_crcf_squelch_enable(csdr_agc q)
 {
+    REQUIRE(q, TAG_AGC, );
     API_BEGIN
     q->mode = SQ_ENABLED;
     if (q->started) { q->be.squelch = true; LaneState l = q->be.read_lane(q->ctx, 0); l.mode = SQ_ENABLED; q->be.write_lane(q->ctx, 0, l); }
     API_END_VOID
 }
-void csdr_agc_crcf_squelch_set_threshold(csdr_agc q, float t) { q->thr = t; if (q->started) q->be.agc_thr = t; }
-void csdr_agc_crcf_squelch_set_timeout(csdr_agc q, unsigned t) { q->timeout = t; if (q->started) q->be.agc_timeout = t; }
+void csdr_agc_crcf_squelch_set_threshold(csdr_agc q, float t) { REQUIRE(q, TAG_AGC, ); q->thr = t; if (q->started) q->be.agc_thr = t; }
+void csdr_agc_crcf_squelch_set_timeout(csdr_agc q, unsigned t) { REQUIRE(q, TAG_AGC, ); q->timeout = t; if (q->started) q->be.agc_timeout = t; }
 float csdr_agc_crcf_get_rssi(csdr_agc q)
 {
+    REQUIRE(q, TAG_AGC, 0.0f);
     API_BEGIN LaneState l = agc_lane(q); return (float)(-20 * log10((double)l.g)); API_END(0.0f)
 }
 int csdr_agc_crcf_squelch_get_status(csdr_agc q)
 {
+    REQUIRE(q, TAG_AGC, -1);
     API_BEGIN LaneState l = agc_lane(q); return l.mode; API_END(0)
 }
 static int agc_exec(csdr_agc q, const csdr_cf32 *x, unsigned n, csdr_cf32 *y, bool gate)
@@ -1107,8 +1210,8 @@ static int agc_exec(csdr_agc q, const csdr_cf32 *x, unsigned n, csdr_cf32 *y, bo
     return 0;
     API_END(-1)
 }
-void csdr_agc_crcf_execute_block(csdr_agc q, const csdr_cf32 *x, unsigned n, csdr_cf32 *y) { agc_exec(q, x, n, y, false); }
-int csdr_agc_squelch_execute_block(csdr_agc q, const csdr_cf32 *x, unsigned n, csdr_cf32 *y) { return agc_exec(q, x, n, y, true); }
+void csdr_agc_crcf_execute_block(csdr_agc q, const csdr_cf32 *x, unsigned n, csdr_cf32 *y) { REQUIRE(q, TAG_AGC, ); agc_exec(q, x, n, y, false); }
+int csdr_agc_squelch_execute_block(csdr_agc q, const csdr_cf32 *x, unsigned n, csdr_cf32 *y) { REQUIRE(q, TAG_AGC, -1); return agc_exec(q, x, n, y, true); }
 
 // ---------------------------------------------------------------- freqdem
 csdr_freqdem csdr_freqdem_create(float kf)
@@ -1120,10 +1223,11 @@ csdr_freqdem csdr_freqdem_create(float kf)
     return q.release();
     API_END(nullptr)
 }
-void csdr_freqdem_destroy(csdr_freqdem q) { delete q; }
-void csdr_freqdem_print(csdr_freqdem q) { printf("freqdem:\n    mod. factor :   %8.4f\n", q->kf); }
+void csdr_freqdem_destroy(csdr_freqdem q) { if (!q) return; REQUIRE(q, TAG_FREQDEM, ); delete q; }
+void csdr_freqdem_print(csdr_freqdem q) { REQUIRE(q, TAG_FREQDEM, ); printf("freqdem:\n    mod. factor :   %8.4f\n", q->kf); }
 void csdr_freqdem_demodulate_block(csdr_freqdem q, const csdr_cf32 *r, unsigned n, float *m)
 {
+    REQUIRE(q, TAG_FREQDEM, );
     API_BEGIN
     if (!n) return;
     q->ctx.use();
@@ -1146,13 +1250,15 @@ csdr_ampmodem csdr_ampmodem_create(float mod_index, int type, int suppressed)
     return q.release();
     API_END(nullptr)
 }
-void csdr_ampmodem_destroy(csdr_ampmodem q) { delete q; }
+void csdr_ampmodem_destroy(csdr_ampmodem q) { if (!q) return; REQUIRE(q, TAG_AMPMODEM, ); delete q; }
 void csdr_ampmodem_print(csdr_ampmodem q)
 {
+    REQUIRE(q, TAG_AMPMODEM, );
     printf("ampmodem:\n    type            :   double side-band\n    supp. carrier   :   no\n    mod. index      :   %-8.4f\n", q->am.mod_index);
 }
 void csdr_ampmodem_demodulate_block(csdr_ampmodem q, const csdr_cf32 *r, unsigned n, float *m)
 {
+    REQUIRE(q, TAG_AMPMODEM, );
     API_BEGIN
     if (!n) return;
     q->ctx.use();
@@ -1179,9 +1285,10 @@ csdr_iirfilt_rrrf csdr_iirfilt_rrrf_create_prototype(int ftype, int btype, int f
     return q.release();
     API_END(nullptr)
 }
-void csdr_iirfilt_rrrf_destroy(csdr_iirfilt_rrrf q) { delete q; }
+void csdr_iirfilt_rrrf_destroy(csdr_iirfilt_rrrf q) { if (!q) return; REQUIRE(q, TAG_IIRFILT_RRRF, ); delete q; }
 void csdr_iirfilt_rrrf_print(csdr_iirfilt_rrrf q)
 {
+    REQUIRE(q, TAG_IIRFILT_RRRF, );
     printf("iir filter [sos]:\n");
     for (size_t i = 0; i < q->f.sos.size(); i++) {
         const design::Sos &s = q->f.sos[i];
@@ -1190,12 +1297,14 @@ void csdr_iirfilt_rrrf_print(csdr_iirfilt_rrrf q)
 }
 unsigned csdr_iirfilt_rrrf_coefficients(csdr_iirfilt_rrrf q, float *b, float *a)
 {
+    REQUIRE(q, TAG_IIRFILT_RRRF, 0);
     for (size_t i = 0; i < q->f.sos.size(); i++)
         for (int j = 0; j < 3; j++) { if (b) b[3 * i + j] = q->f.sos[i].b[j]; if (a) a[3 * i + j] = q->f.sos[i].a[j]; }
     return (unsigned)q->f.sos.size();
 }
 void csdr_iirfilt_rrrf_execute_block(csdr_iirfilt_rrrf q, const float *x, unsigned n, float *y)
 {
+    REQUIRE(q, TAG_IIRFILT_RRRF, );
     API_BEGIN
     if (!n) return;
     q->ctx.use();
@@ -1217,10 +1326,11 @@ csdr_firdecim csdr_firdecim_rrrf_create_kaiser(unsigned M, unsigned m, float as)
     return q.release();
     API_END(nullptr)
 }
-void csdr_firdecim_rrrf_destroy(csdr_firdecim q) { delete q; }
-void csdr_firdecim_rrrf_print(csdr_firdecim q) { printf("firdecim_rrrf: M = %u, %d taps\n", q->d.M, q->d.Lh); }
+void csdr_firdecim_rrrf_destroy(csdr_firdecim q) { if (!q) return; REQUIRE(q, TAG_FIRDECIM, ); delete q; }
+void csdr_firdecim_rrrf_print(csdr_firdecim q) { REQUIRE(q, TAG_FIRDECIM, ); printf("firdecim_rrrf: M = %u, %d taps\n", q->d.M, q->d.Lh); }
 void csdr_firdecim_rrrf_execute_block(csdr_firdecim q, const float *x, unsigned n, float *y)
 {
+    REQUIRE(q, TAG_FIRDECIM, );
     API_BEGIN
     if (!n) return;
     q->ctx.use();

@@ -5,9 +5,26 @@
  * imports to the GPU blocks with no source change; every other liquid symbol still comes from libliquid.
  * (Kept in a separate library so that libcsdr_b200.so can be loaded next to a real libliquid for A/B checks.)
  */
+#define _GNU_SOURCE
 #include "../../include/csdr_b200.h"
+#include <dlfcn.h>
+#include <stdio.h>
 
 typedef csdr_cf32 cf;
+
+/* A liquid family is either shadowed WHOLE -- every function the reference can reach on a handle of that type
+ * (nco_crcf: create, print, set_frequency, pll_set_bandwidth, pll_step, step, cexpf, get_phase, set_phase, mix_block_*,
+ * destroy; Liquid.chs:746-780) -- or, where liquid keeps a constructor of its own (iirfilt_crcf_create_prototype,
+ * Liquid.chs:553-571, used by iirCFilter), the shared members look at the handle's tag word and pass foreign objects on
+ * to the next definition in link order, i.e. the real libliquid. */
+#define FORWARD_FOREIGN(q, name, proto, args)                                                        \
+    if (csdr_handle_kind(q) == 0) {                                                                   \
+        static void (*next) proto = 0;                                                                \
+        if (!next) next = (void (*) proto)dlsym(RTLD_NEXT, name);                                     \
+        if (next) next args;                                                                          \
+        else fprintf(stderr, "csdr_liquid_compat: %s called with a foreign handle and no libliquid behind it\n", name); \
+        return;                                                                                       \
+    }
 
 /* Liquid.chs:746-780 */
 void *nco_crcf_create(int type) { return csdr_nco_crcf_create(type); }
@@ -15,6 +32,15 @@ void nco_crcf_destroy(void *q) { csdr_nco_crcf_destroy((csdr_nco)q); }
 void nco_crcf_print(void *q) { csdr_nco_crcf_print((csdr_nco)q); }
 void nco_crcf_set_frequency(void *q, float f) { csdr_nco_crcf_set_frequency((csdr_nco)q, f); }
 void nco_crcf_set_phase(void *q, float p) { csdr_nco_crcf_set_phase((csdr_nco)q, p); }
+void nco_crcf_adjust_frequency(void *q, float df) { csdr_nco_crcf_adjust_frequency((csdr_nco)q, df); }
+void nco_crcf_adjust_phase(void *q, float dphi) { csdr_nco_crcf_adjust_phase((csdr_nco)q, dphi); }
+void nco_crcf_step(void *q) { csdr_nco_crcf_step((csdr_nco)q); }
+void nco_crcf_reset(void *q) { csdr_nco_crcf_reset((csdr_nco)q); }
+float nco_crcf_get_phase(void *q) { return csdr_nco_crcf_get_phase((csdr_nco)q); }
+float nco_crcf_get_frequency(void *q) { return csdr_nco_crcf_get_frequency((csdr_nco)q); }
+void nco_crcf_cexpf(void *q, cf *y) { csdr_nco_crcf_cexpf((csdr_nco)q, y); }
+void nco_crcf_pll_set_bandwidth(void *q, float bw) { csdr_nco_crcf_pll_set_bandwidth((csdr_nco)q, bw); }
+void nco_crcf_pll_step(void *q, float dphi) { csdr_nco_crcf_pll_step((csdr_nco)q, dphi); }
 void nco_crcf_mix_block_down(void *q, cf *x, cf *y, unsigned n) { csdr_nco_crcf_mix_block_down((csdr_nco)q, x, y, n); }
 void nco_crcf_mix_block_up(void *q, cf *x, cf *y, unsigned n) { csdr_nco_crcf_mix_block_up((csdr_nco)q, x, y, n); }
 
@@ -27,9 +53,21 @@ void msresamp_crcf_execute(void *q, cf *x, unsigned nx, cf *y, unsigned *ny) { c
 
 /* Liquid.chs:550-567 */
 void *iirfilt_crcf_create_dc_blocker(float alpha) { return csdr_iirfilt_crcf_create_dc_blocker(alpha); }
-void iirfilt_crcf_destroy(void *q) { csdr_iirfilt_crcf_destroy((csdr_iirfilt)q); }
-void iirfilt_crcf_print(void *q) { csdr_iirfilt_crcf_print((csdr_iirfilt)q); }
-void iirfilt_crcf_execute_block(void *q, cf *x, unsigned n, cf *y) { csdr_iirfilt_crcf_execute_block((csdr_iirfilt)q, x, n, y); }
+void iirfilt_crcf_destroy(void *q)
+{
+    FORWARD_FOREIGN(q, "iirfilt_crcf_destroy", (void *), (q))
+    csdr_iirfilt_crcf_destroy((csdr_iirfilt)q);
+}
+void iirfilt_crcf_print(void *q)
+{
+    FORWARD_FOREIGN(q, "iirfilt_crcf_print", (void *), (q))
+    csdr_iirfilt_crcf_print((csdr_iirfilt)q);
+}
+void iirfilt_crcf_execute_block(void *q, cf *x, unsigned n, cf *y)
+{
+    FORWARD_FOREIGN(q, "iirfilt_crcf_execute_block", (void *, cf *, unsigned, cf *), (q, x, n, y))
+    csdr_iirfilt_crcf_execute_block((csdr_iirfilt)q, x, n, y);
+}
 
 /* Liquid.chs:732-742 */
 void *firpfbch_crcf_create_kaiser(int type, unsigned M, unsigned m, float As) { return csdr_firpfbch_crcf_create_kaiser(type, M, m, As); }

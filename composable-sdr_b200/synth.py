@@ -89,3 +89,30 @@ def config5(n, nstreams, sr=10e6):
     for s in range(nstreams):
         out[s] = noise(n, 0.02, 500 + s) + am_carrier(n, sr, 1e6 + 437.0 + 3.0 * s, 0.4 + 0.002 * s, 0.8, 1e3 + 10 * s)
     return out
+
+
+def _example3(n, sr, offset, bw, channels, active, noise_sigma, stream):
+    x = noise(n, noise_sigma, stream)
+    k = np.arange(n, dtype=np.float64)
+    for i, c in enumerate(active):
+        f0 = offset + (c - (channels - 1) / 2.0) / channels * bw
+        car = fm_carrier(n, sr, f0, 0.01 + 0.004 * i, 0.1 * bw / channels, bw / channels / 40.0)
+        if i % 3 == 1:
+            # slow raised-cosine fading (period 12 ms) through the squelch threshold: the gate opens and closes without
+            # key clicks (an abrupt on/off splatters into every channel and drives liquid's gain loop into its frozen
+            # state, where one-ulp differences persist for ever)
+            car = car * (0.5 - 0.5 * np.cos(2 * np.pi * k / (0.012 * sr))).astype(np.float32) ** 4
+        x = x + car
+    return x.astype(np.complex64)
+
+
+def example3(n, sr=3.2e6, bw=1.6e6, channels=20, active=(2, 5, 9, 10, 14, 18), noise_sigma=1e-5):
+    """README example 3 (README.md:182-193: -s 3.2e6 -b 1.6e6 -a -50 -c 20 --demod DeNo): carriers at some channel
+    centres of the RESAMPLED band, f_k = (k - (C-1)/2)/C * bw, in front of the resampler; the rest of the band holds
+    noise far below the squelch threshold (the analyzer shows a tone of amplitude A as ~A*C)."""
+    return _example3(n, sr, 0.0, bw, channels, active, noise_sigma, 30)
+
+
+def example3_offset(n, sr=2.56e6, offset=1e5, bw=1.28e6, channels=16, active=(1, 4, 7, 8, 12, 15), noise_sigma=1e-5):
+    """as example3 with an offset mix in front: the carriers sit at offset + the channel centres of the resampled band"""
+    return _example3(n, sr, offset, bw, channels, active, noise_sigma, 31)

@@ -55,6 +55,10 @@ enum {
                                      read in place by the first half-band stage (3 CTAs/SM); 0 register prefetch + mixing
                                      pass (2 CTAs/SM); 2 as 1, warp-specialised (producer / consumer warp groups) */
 };
+/* 0 if h is not a live handle of this library, else its kind (1 nco, 2 msresamp, 3 iirfilt_crcf, 4 firpfbch, 5 firpfbch2,
+ * 6 agc, 7 freqdem, 8 ampmodem, 9 iirfilt_rrrf, 10 firdecim, 11 chain).  Every entry point checks its handle this way: a
+ * NULL or foreign pointer sets csdr_last_error() and returns instead of being dereferenced. */
+int         csdr_handle_kind(const void *h);
 int         csdr_set_option(int opt, int value);
 int         csdr_get_option(int opt);
 
@@ -68,6 +72,18 @@ void     csdr_nco_crcf_set_frequency(csdr_nco q, float dtheta);
 void     csdr_nco_crcf_set_phase(csdr_nco q, float theta);
 uint32_t csdr_nco_crcf_get_phase_word(csdr_nco q);
 uint32_t csdr_nco_crcf_get_freq_word(csdr_nco q);
+/* the rest of the family the reference binds (Liquid.chs:755-770: pll_set_bandwidth, pll_step, step, cexpf, get_phase --
+ * the stereo-FM pilot PLL, Liquid.chs:959-988, drives them per sample on handles from nco_crcf_create) plus liquid's
+ * other scalar members: host arithmetic on the handle's uint32 phase / frequency words (liquid nco.c) */
+void     csdr_nco_crcf_adjust_frequency(csdr_nco q, float df);
+void     csdr_nco_crcf_adjust_phase(csdr_nco q, float dphi);
+void     csdr_nco_crcf_step(csdr_nco q);
+void     csdr_nco_crcf_reset(csdr_nco q);
+float    csdr_nco_crcf_get_phase(csdr_nco q);
+float    csdr_nco_crcf_get_frequency(csdr_nco q);
+void     csdr_nco_crcf_cexpf(csdr_nco q, csdr_cf32 *y);
+void     csdr_nco_crcf_pll_set_bandwidth(csdr_nco q, float bw);
+void     csdr_nco_crcf_pll_step(csdr_nco q, float dphi);
 void     csdr_nco_crcf_mix_block_down(csdr_nco q, const csdr_cf32 *x, csdr_cf32 *y, unsigned n);
 void     csdr_nco_crcf_mix_block_up(csdr_nco q, const csdr_cf32 *x, csdr_cf32 *y, unsigned n);
 

@@ -175,6 +175,12 @@ static void nco_pll_step(orc_nco q, float dphi)
     q->d_theta += nco_constrain(dphi * q->alpha);
     q->theta   += nco_constrain(dphi * q->beta);
 }
+/* the scalar members the reference's pilot PLL drives per sample (pllCreate / pllStep, Liquid.chs:959-988) */
+void orc_nco_crcf_pll_set_bandwidth(orc_nco q, float bw) { nco_pll_set_bandwidth(q, bw); }
+void orc_nco_crcf_pll_step(orc_nco q, float dphi) { nco_pll_step(q, dphi); }
+/* NCO(_get_phase): 2.0f*M_PI*(float)theta / (float)(1LLU<<32), evaluated in double, returned as float */
+float orc_nco_crcf_get_phase(orc_nco q) { return (float)(2.0 * M_PI * (double)(float)q->theta / 4294967296.0); }
+void orc_nco_crcf_cexpf(orc_nco q, orc_cf32 *y) { float s, c; nco_sincos(q, &s, &c); y->re = c; y->im = s; }
 static inline orc_cf32 nco_mix_down1(const struct orc_nco_s *q, orc_cf32 x)
 {
     float s, c; nco_sincos(q, &s, &c);

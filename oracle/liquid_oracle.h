@@ -58,6 +58,10 @@ void     orc_nco_crcf_set_phase(orc_nco q, float theta);
 uint32_t orc_nco_crcf_get_phase_word(orc_nco q);
 uint32_t orc_nco_crcf_get_freq_word(orc_nco q);
 void     orc_nco_crcf_step(orc_nco q);
+void     orc_nco_crcf_pll_set_bandwidth(orc_nco q, float bw);
+void     orc_nco_crcf_pll_step(orc_nco q, float dphi);
+float    orc_nco_crcf_get_phase(orc_nco q);
+void     orc_nco_crcf_cexpf(orc_nco q, orc_cf32 *y);
 void     orc_nco_crcf_mix_block_down(orc_nco q, const orc_cf32 *x, orc_cf32 *y, unsigned n);
 void     orc_nco_crcf_mix_block_up(orc_nco q, const orc_cf32 *x, orc_cf32 *y, unsigned n);
 const float *orc_nco_sintab(void);   /* the 1024-entry table, sinf(2*pi*i/1024) */

@@ -54,7 +54,8 @@ def _declare(L):
         "orc_nco_crcf_create": (vp, [i]), "orc_nco_crcf_destroy": (None, [vp]),
         "orc_nco_crcf_set_frequency": (None, [vp, f]), "orc_nco_crcf_set_phase": (None, [vp, f]),
         "orc_nco_crcf_get_phase_word": (C.c_uint32, [vp]), "orc_nco_crcf_get_freq_word": (C.c_uint32, [vp]),
-        "orc_nco_crcf_step": (None, [vp]),
+        "orc_nco_crcf_step": (None, [vp]), "orc_nco_crcf_pll_set_bandwidth": (None, [vp, f]),
+        "orc_nco_crcf_pll_step": (None, [vp, f]), "orc_nco_crcf_get_phase": (f, [vp]), "orc_nco_crcf_cexpf": (None, [vp, vp]),
         "orc_nco_crcf_mix_block_down": (None, [vp, vp, vp, u]), "orc_nco_crcf_mix_block_up": (None, [vp, vp, vp, u]),
         "orc_nco_sintab": (C.POINTER(C.c_float), []),
         "orc_firpfbch2_crcf_create_kaiser": (vp, [i, u, u, f]), "orc_firpfbch2_crcf_destroy": (None, [vp]),

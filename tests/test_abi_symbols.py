@@ -31,7 +31,11 @@ def test_liquid_compat_aliases(cs):
     from composable_sdr_b200 import build
     L = C.CDLL(build.COMPAT)
     liquid = ["nco_crcf_create", "nco_crcf_set_frequency", "nco_crcf_mix_block_down", "nco_crcf_mix_block_up",
-              "nco_crcf_print", "nco_crcf_destroy", "msresamp_crcf_create", "msresamp_crcf_print",
+              "nco_crcf_print", "nco_crcf_destroy",
+              # the whole nco_crcf family the reference can reach on such a handle (Liquid.chs:755-770, fmsPll)
+              "nco_crcf_pll_set_bandwidth", "nco_crcf_pll_step", "nco_crcf_step", "nco_crcf_cexpf", "nco_crcf_get_phase",
+              "nco_crcf_set_phase", "nco_crcf_adjust_frequency", "nco_crcf_adjust_phase", "nco_crcf_get_frequency",
+              "nco_crcf_reset", "msresamp_crcf_create", "msresamp_crcf_print",
               "msresamp_crcf_get_rate", "msresamp_crcf_execute", "msresamp_crcf_destroy",
               "iirfilt_crcf_create_dc_blocker", "iirfilt_crcf_print", "iirfilt_crcf_execute_block",
               "iirfilt_crcf_destroy", "firpfbch_crcf_create_kaiser", "firpfbch_crcf_print",
@@ -48,6 +52,30 @@ def test_liquid_compat_aliases(cs):
               "firpfbch2_crcf_destroy"]                                 # + the oversampled analyzer
     missing = [s for s in liquid if not hasattr(L, s)]
     assert not missing, missing
+
+
+def test_foreign_and_null_handles_are_rejected_not_dereferenced(cs, capfd):
+    """create() returns NULL without a CUDA device: every entry point must survive that NULL (and a pointer that is
+    not one of its handles) and say so through csdr_last_error().  The alias library passes foreign iirfilt_crcf
+    objects (iirfilt_crcf_create_prototype stays liquid's, Liquid.chs:553-571) on to the next library in link order."""
+    from composable_sdr_b200 import _lib, build
+    L = _lib.load()
+    foreign = C.create_string_buffer(256)          # stands in for an object made by the real libliquid
+    for h in (None, C.addressof(foreign)):
+        assert L.csdr_handle_kind(h) == 0
+        L.csdr_agc_crcf_set_bandwidth(h, 0.1)
+        assert "csdr_agc_crcf_set_bandwidth" in _lib.last_error()
+        L.csdr_nco_crcf_set_frequency(h, 0.1)
+        assert L.csdr_nco_crcf_get_phase(h) == 0.0
+        assert L.csdr_agc_crcf_squelch_get_status(h) == -1
+        assert L.csdr_chain_max_output(h, 1000) == 0
+        n = C.c_size_t(7)
+        assert L.csdr_chain_process(h, None, 0, 0, None, 0, C.byref(n)) == -1 and n.value == 0
+        assert "handle" in _lib.last_error()
+    A = C.CDLL(build.COMPAT)
+    A.iirfilt_crcf_print.argtypes = [C.c_void_p]
+    A.iirfilt_crcf_print(C.addressof(foreign))      # no libliquid here: reported on stderr, not executed as ours
+    assert "foreign handle" in capfd.readouterr().err
 
 
 def test_no_cpu_fallback(cs):
