@@ -461,19 +461,43 @@ int csdr_chain_seek(csdr_chain q, uint64_t n_prior)
 {
     REQUIRE(q, TAG_CHAIN, -1);
     API_BEGIN
-    if (q->C > 1) throw CudaError{"chain: seek with a channelizer is not implemented"};
     if (q->has_wb) throw CudaError{"chain: seek with DeWBFM is not implemented"};
-    if (q->has_resamp) { if (q->fe.interp) { q->fe.cursor = FrontendCursor(); q->fe.cursor.n_abs = n_prior; } else q->fe.cursor = fe_seek(q->fe.geo, n_prior); }
-    else q->mix_theta = (uint32_t)n_prior * q->mix_dtheta;
+    q->ctx.use();
+    // samples behind the resampler that precede the new position (closed form: fe_seek)
+    unsigned long long o_prior = n_prior;
+    if (q->has_resamp) {
+        if (q->fe.interp) {
+            if (q->C > 1) throw CudaError{"chain: seek with a channelizer behind an interpolating resampler is not implemented"};
+            q->fe.cursor = FrontendCursor(); q->fe.cursor.n_abs = n_prior;
+        } else {
+            q->fe.cursor = fe_seek(q->fe.geo, n_prior);
+            const unsigned __int128 span = (unsigned __int128)(n_prior >> q->fe.geo.base.S) << 24, st = q->fe.geo.base.step;
+            o_prior = (unsigned long long)((span + st - 1) / st);
+        }
+    } else q->mix_theta = (uint32_t)n_prior * q->mix_dtheta;
+    if (q->C > 1) {
+        // channelizer: the pre-rotation NCO (Liquid.chs:817-821, 847) has advanced by o_prior samples; frames stay on the
+        // stream's own grid (sample index = 0 mod C), so the o_prior mod C samples of the frame the new position falls into
+        // count as already waiting (zeros: that frame and the 13 that still see the empty history belong to the warm-up)
+        q->rot_theta = (uint32_t)o_prior * q->rot_dtheta;
+        q->nleft = (size_t)(o_prior % q->C);
+        CK(cudaMemsetAsync(q->left.p, 0, q->left.cap, q->ctx.stream));
+        for (auto &b : q->ch.xr) if (b.p) CK(cudaMemsetAsync(b.p, 0, q->ch.hist_samples() * sizeof(float2), q->ctx.stream));
+        q->ctx.sync();
+    }
     return 0;
     API_END(-1)
 }
 size_t csdr_chain_warmup_len(csdr_chain q)
 {
     REQUIRE(q, TAG_CHAIN, 0);
-    // front-end FIR history + dc blocker settling (0.9995^k < 1e-9 after ~41.5k post-resample samples) + AGC
+    // front-end FIR history + dc blocker settling (0.9995^k < 1e-9 after ~41.5k post-resample samples) + AGC; behind a
+    // channelizer the per-channel loops run at 1/C of that rate: 13 frames of filterbank history, the gain loop's
+    // settling (~400 samples) and the squelch FSM's memory (timeout + 8 samples) per channel
     double r = q->has_resamp ? (double)q->fe.ms.rate : 1.0;
-    size_t w = (size_t)(q->has_resamp ? q->fe.geo.hcap : 0) + (size_t)std::ceil(45000.0 / r);
+    double post = 45000.0;
+    if (q->C > 1) post += (double)q->C * (14.0 + 512.0 + (double)q->be.agc_timeout + 8.0);
+    size_t w = (size_t)(q->has_resamp ? q->fe.geo.hcap : 0) + (size_t)std::ceil(post / r);
     return w;
 }
 int csdr_chain_profile(csdr_chain q, int enable)

@@ -12,14 +12,18 @@ timing and, if the caller wants everything on one rank, the gather of the output
 """
 
 
-def time_segments(total, world):
-    """[(start, stop)] of `world` contiguous segments covering [0, total)."""
-    base, rem = divmod(int(total), int(world))
+def time_segments(total, world, align=1):
+    """[(start, stop)] of `world` contiguous segments covering [0, total); every interior boundary is a multiple of
+    `align` input samples (channelizer chains: a whole number of frames, so that each frame has one owner)."""
+    total, world, align = int(total), int(world), max(1, int(align))
+    units = total // align
+    base, rem = divmod(units, world)
     out, pos = [], 0
     for r in range(world):
-        n = base + (1 if r < rem else 0)
-        out.append((pos, pos + n))
-        pos += n
+        n = (base + (1 if r < rem else 0)) * align
+        stop = total if r == world - 1 else pos + n
+        out.append((pos, stop))
+        pos = stop
     return out
 
 
@@ -28,12 +32,38 @@ def stream_shard(nstreams, world, rank):
     return list(range(rank, nstreams, world))
 
 
-def shard_input_range(total, world, rank, warmup):
+def shard_input_range(total, world, rank, warmup, align=1):
     """(seek_position, first_input_sample, stop_sample, samples_to_discard_from) for a time-segment shard:
     the rank feeds input[first:stop] after seeking to `first`; inputs before `start` are warm-up."""
-    start, stop = time_segments(total, world)[rank]
+    start, stop = time_segments(total, world, align)[rank]
     first = max(0, start - int(warmup))
     return first, first, stop, start
+
+
+def frame_alignment(channels, rate_num=1, rate_den=1):
+    """input samples per whole number of channelizer frames when the resampler's rate is rate_num / rate_den exactly
+    (1/1 = no resampler): a boundary at a multiple of it falls on a frame boundary of the stream"""
+    c = max(1, int(channels)) * int(rate_den)
+    return c // _gcd(c, int(rate_num))
+
+
+def _gcd(a, b):
+    while b:
+        a, b = b, a % b
+    return a
+
+
+def seek_shard(chain, start, feed, drop_outputs=True):
+    """Position `chain` (a fresh composable_sdr_b200.Chain) at input sample `start` of its stream: seek to start - warm-up,
+    run the warm-up history through it -- `feed(first, start)` must return those input samples, numpy or torch -- and
+    discard what it produces.  Returns the number of warm-up samples fed."""
+    warm = min(int(start), chain.warmup_len())
+    if start <= 0:
+        return 0
+    chain.seek(start - warm)
+    if warm:
+        chain.process(feed(start - warm, start))
+    return warm
 
 
 def gather_counts(dist, n_local, device=None):

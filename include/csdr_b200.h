@@ -236,8 +236,10 @@ int      csdr_chain_process(csdr_chain q, const csdr_cf32 *x, size_t nx, size_t 
 int      csdr_chain_run_file(csdr_chain q, const char *in_path, const char *out_name, uint64_t numsamples, size_t chunk,
                              uint64_t *n_in, uint64_t *n_out);
 /* Seed the stream position for time-segment sharding: declare that `n_prior` input samples precede the next
- * call (NCO phase, half-band block alignment and resampler timing are closed-form in the sample index).  The
- * caller feeds csdr_chain_warmup_len() samples of real history first and discards the outputs they produce. */
+ * call (NCO phase, half-band block alignment, resampler timing and -- behind a channelizer -- the pre-rotation phase
+ * and the frame grid are closed-form in the sample index).  The caller feeds csdr_chain_warmup_len() samples of real
+ * history first and discards the outputs they produce.  With a channelizer the shard should start on a frame boundary
+ * of the stream (resampler output index = 0 mod C), so that every frame is produced by exactly one shard. */
 int      csdr_chain_seek(csdr_chain q, uint64_t n_prior);
 size_t   csdr_chain_warmup_len(csdr_chain q);
 /* the CUDA stream (cudaStream_t) the chain launches on, for event timing by the caller */

@@ -234,6 +234,50 @@ def test_time_segment_sharding_matches_single_stream(cs, orc):
     assert_parity(y[n_warm:], ref[n_before + n_warm:], rel=REL_TOL_AFTER_DCBLOCK, what="time-segment shard")
 
 
+def test_channelizer_time_segment_sharding(cs, orc):
+    """multi-GPU partitioning of the channelizer chains (time segments, every shard produces all channels
+    of its frames): a shard that seeks to a frame boundary minus the warm-up equals the single-stream result -- with the
+    resampler in front (README example 3 shape, 20 channels: the frame grid follows the resampler's output index) and
+    for the bare 64-channel filterbank with --mix"""
+    from composable_sdr_b200 import shard
+    n = 1 << 22
+    x = cs.synth.example3(n)
+    ref = orc.Chain(3.2e6, 0.0, 1.6e6, orc.DEMOD_NO, 0.0, -50.0, 20, False).process(x)
+    align = shard.frame_alignment(20, 1, 2)
+    assert align == 40
+    (a0, a1), (b0, b1) = shard.time_segments(n, 2, align)
+    assert a0 == 0 and a1 == b0 and b1 == n and b0 % align == 0
+    first = cs.Chain(3.2e6, 0.0, 1.6e6, agc=-50.0, channels=20).process(x[a0:a1])
+    second = cs.Chain(3.2e6, 0.0, 1.6e6, agc=-50.0, channels=20)
+    warm = shard.seek_shard(second, b0, lambda i, j: x[i:j])
+    assert 0 < warm < b0
+    tail = second.process(x[b0:b1])
+    outs = [np.concatenate([u, v]) for u, v in zip(first, tail)]
+    _assert_channels(outs, ref, "example 3, two time shards", fm=False, rel=1e-4)
+    # a shard that does NOT start on a frame boundary still lands on the stream's frame grid: the frame its start falls
+    # into is completed by its first samples (the warm-up supplied the frame's head)
+    odd = b0 + 2 * 7                      # 7 resampler outputs into a frame
+    third = cs.Chain(3.2e6, 0.0, 1.6e6, agc=-50.0, channels=20)
+    shard.seek_shard(third, odd, lambda i, j: x[i:j])
+    t3 = third.process(x[odd:b1])
+    k0 = b0 // 40
+    for c in (2, 9, 14):
+        assert len(t3[c]) == len(ref[c]) - k0
+        assert_parity(t3[c][64:], ref[c][k0 + 64:], what=f"unaligned shard start, channel {c}")
+    # 64 channels, --mix, FM, no resampler
+    x = cs.synth.config4(1 << 21, channels=64, active=8, sr=1e8)
+    refm = orc.Chain(1e8, 0.0, 0.0, orc.DEMOD_NBFM, 0.3, -40.0, 64, True).process(x)[0]
+    (a0, a1), (b0, b1) = shard.time_segments(len(x), 2, shard.frame_alignment(64))
+    mk = lambda: cs.Chain(1e8, demod=cs.DeNBFM(0.3), agc=-40.0, channels=64, mix_channels=True)
+    ya = mk().process(x[a0:a1])[0]
+    sh = mk()
+    shard.seek_shard(sh, b0, lambda i, j: x[i:j])
+    yb = sh.process(x[b0:b1])[0]
+    y = np.concatenate([ya, yb])
+    assert len(y) == len(refm)
+    assert snr_db(y[512:], refm[512:]) >= 60.0
+
+
 def test_full_size_properties_on_device(cs):
     """BASELINE-size chunk (2^26 samples, device resident): exact output count, linearity of the front end,
     chunk invariance, and few AGC speculation misses."""

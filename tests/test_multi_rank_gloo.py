@@ -63,6 +63,12 @@ def test_time_segments_cover_the_stream():
         assert segs[0][0] == 0 and segs[-1][1] == total
         assert all(a[1] == b[0] for a, b in zip(segs, segs[1:]))
     assert shard.stream_shard(10, 4, 1) == [1, 5, 9]
+    # channelizer chains: interior boundaries on whole frames
+    for total, world, align in [(1000, 3, 64), (1 << 24, 8, 1024), (100, 4, 40)]:
+        segs = shard.time_segments(total, world, align)
+        assert segs[0][0] == 0 and segs[-1][1] == total
+        assert all(a[1] == b[0] and a[1] % align == 0 for a, b in zip(segs, segs[1:]))
+    assert shard.frame_alignment(1024) == 1024 and shard.frame_alignment(20, 1, 2) == 40 and shard.frame_alignment(16, 5, 64) == 1024
 
 
 @pytest.mark.timeout(300)
