@@ -10,15 +10,14 @@
 //      per group, fp64) and scans the groups of a CTA, k_dc_carry scans the CTAs: the exact filter state at every
 //      group boundary is then one multiply-add away.
 //   2. k_be_prep (one warp per group): dc-blocked samples y_dc[n] and their power p[n] = |y_dc[n]|^2.
-//   3. k_agc_chain: the gain loop sees its input only through p[n]  (|x g|^2 = g^2 p), so the chain is
+//   3. k_agc_emit: the gain loop sees its input only through p[n]  (|x g|^2 = g^2 p), so the chain is
 //      g^2 p -> one-pole filter -> g *= y2'^(-alpha/2): ~11 instructions per sample.  The loop is contractive, so
-//      L-sample segments are run speculatively after a W-sample warm-up, each by its own thread, writing the gain
-//      after every sample; start states are verified against the predecessors' end states, misses are refined in
-//      parallel and, as a last resort, repaired in stream order (k_agc_verify / k_agc_refine / k_agc_fixup).
-//   4. k_be_emit (one sample per thread, one 32-sample word per warp): ungated output y = y_dc g, discriminator
-//      value, "rssi > threshold" bit and sign bits by warp ballot.
-//   5. the squelch state machine never feeds back into the gain and is resolved EXACTLY on one threshold bit per
-//      sample (k_backend_fsm*); the gate is applied last as a mask (k_backend_gate).
+//      L-sample segments are run speculatively after a W-sample warm-up, each by its own thread.  The gains of every
+//      32-sample block stay in shared memory and the CTA emits them at once (one sample per thread, one 32-sample word
+//      per warp): ungated output y = y_dc g, discriminator value, "rssi > threshold" bit and sign bits by warp ballot.
+//   4. k_be_finish (one cooperative launch): start states are verified against the predecessors' end states, misses
+//      are refined in parallel and, as a last resort, repaired in stream order; the squelch state machine never feeds
+//      back into the gain and is resolved EXACTLY on one threshold bit per sample; the gate is applied last as a mask.
 // The result equals the sequential loop to within the stated tolerance in all cases (gate positions exactly, given
 // the threshold bits); only the speed depends on the signal.
 #pragma once
@@ -53,8 +52,11 @@ struct BackendParams {
     int gate;                                  // 1: zero the output unless squelch status == SIGNALHI (Liquid.chs:700-704)
     LaneState *lane;
     const float2 *ydc; long long ydc_stride;   // dc-blocked samples (= in when there is no dc blocker)
-    const float *pw; float *gpost; long long pw_stride;   // [nlanes][pw_stride] power, gain AFTER each sample
+    const float *pw; long long pw_stride;      // [nlanes][pw_stride] power of the dc-blocked samples
     float *g_first; float2 *y_first;           // [nlanes] gain / ungated output before the chunk's first sample
+    float2 *y_end;                             // [nlanes] ungated output of the chunk's last sample
+    float2 *seg_ylast;                         // [nlanes][nseg] ungated output of every segment's last sample
+    unsigned *barrier;                         // [4] grid barrier of k_be_finish: arrivals, generation, exit count
     SegState *seg_start, *seg_end;             // [nlanes][nseg] gain-loop state at segment boundaries
     int nwords, FW;                            // 32-sample words per lane; FSM replay length in segments
     unsigned *exbits, *gatebits;               // [nlanes][nwords] threshold-exceeded / gate-open bit per sample
@@ -65,7 +67,8 @@ struct BackendParams {
     unsigned *prev_gate;                       // [nlanes] gate of the sample before this chunk
     unsigned *first_bad;                       // [nlanes][2] first segment whose start state does not continue its
                                                // predecessor (gain loop, squelch FSM); 0xffffffff = none
-    unsigned *bad_list; unsigned *bad_count; unsigned bad_cap;   // segments to refine after the first verification
+    unsigned *bad_list; unsigned *bad_count; unsigned bad_cap;   // [2][bad_cap] segments to refine after the first / second
+                                               // verification; [3] counters: round 0, round 1, squelch-FSM misses
     unsigned long long *fixups;                // [3] segments re-run in order: gain loop, squelch FSM; refined in parallel
 };
 
@@ -377,35 +380,6 @@ __device__ __forceinline__ void agc_step(const AgcCoef &p, float &g, float &g2, 
     }
 }
 
-// run samples [i0, i1) of one lane's power sequence; EMIT: store the gain after every sample.  i0 is a multiple
-// of 4; powers are fetched eight at a time, one block ahead of the recurrence.
-template <bool EMIT, bool EXACT>
-__device__ __forceinline__ void agc_run(const BackendParams &p, int lane, float &g, float &y2p, int i0, int i1)
-{
-    const float *__restrict__ pw = p.pw + (long long)lane * p.pw_stride;
-    float *__restrict__ go = p.gpost + (long long)lane * p.pw_stride;
-    const AgcCoef co{p.alpha, p.one_minus_alpha_f, p.neg_half_alpha};
-    int i = i0;
-    float g2 = __fmul_rn(g, g);
-    if (i + 8 <= i1) {
-        const float4 *p4 = reinterpret_cast<const float4 *>(pw + i);
-        float4 na = __ldg(p4), nb = __ldg(p4 + 1);
-        for (; i + 8 <= i1; i += 8) {
-            const float c[8] = {na.x, na.y, na.z, na.w, nb.x, nb.y, nb.z, nb.w};
-            if (i + 16 <= i1) { const float4 *q4 = reinterpret_cast<const float4 *>(pw + i + 8); na = __ldg(q4); nb = __ldg(q4 + 1); }
-            float o[8];
-#pragma unroll
-            for (int k = 0; k < 8; k++) { agc_step<EXACT>(co, g, g2, y2p, c[k]); o[k] = g; }
-            if (EMIT) {
-                float4 *o4 = reinterpret_cast<float4 *>(go + i);
-                o4[0] = make_float4(o[0], o[1], o[2], o[3]);
-                o4[1] = make_float4(o[4], o[5], o[6], o[7]);
-            }
-        }
-    }
-    for (; i < i1; i++) { agc_step<EXACT>(co, g, g2, y2p, pw[i]); if (EMIT) go[i] = g; }
-}
-
 __device__ __forceinline__ bool be_close(float a, float b, float atol = 0.f)
 {
     return fabsf(a - b) <= 1e-5f * fmaxf(fabsf(a), fabsf(b)) + atol;   // fp32 rounding keeps two runs ~1e-6 apart
@@ -433,22 +407,67 @@ __device__ __forceinline__ void agc_guess(float e, float &g, float &y2p)
     y2p = 1.0f;
 }
 
+// ------------------------------------------------------------------------------------------ emission of one word
+// 32 consecutive samples of a lane, one per thread of a warp: ungated output y = y_dc * (gain before the sample),
+// threshold bit = (gain after the sample) < g_thr, sign bits, discriminator m = arg(conj(y[n-1]) y[n]) / (2 pi kf)
+// (freqdem_demodulate) or the cf32 sample itself.  `yprev0`: ungated output of the sample before the word (lane 0).
+// Returns this lane's y (the caller carries the last one to the next word).
+template <bool AGC, bool FM, bool EXACT>
+__device__ __forceinline__ float2 be_emit_word(const BackendParams &p, int lane_id, int u0, bool in, float2 xv, float g0, float ga,
+                                               float2 yprev0)
+{
+    const int l = threadIdx.x & 31;
+    float2 y = xv;
+    if (AGC) y = cf(__fmul_rn(xv.x, g0), __fmul_rn(xv.y, g0));
+    float2 yp;
+    yp.x = __shfl_up_sync(0xffffffffu, y.x, 1); yp.y = __shfl_up_sync(0xffffffffu, y.y, 1);
+    if (l == 0) yp = yprev0;
+    if (AGC) {
+        const long long wd = (long long)lane_id * p.nwords + (u0 >> 5);
+        const unsigned ex = __ballot_sync(0xffffffffu, in && ga < p.g_thr);       // rssi = -20 log10(g) > threshold
+        if (l == 0) p.exbits[wd] = ex;
+        if (FM) {
+            const unsigned sr = __ballot_sync(0xffffffffu, in && (__float_as_int(y.x) < 0));
+            const unsigned si = __ballot_sync(0xffffffffu, in && (__float_as_int(y.y) < 0));
+            if (l == 0) { p.sgnr[wd] = sr; p.sgni[wd] = si; }
+        }
+    }
+    if (in) {
+        const int u = u0 + l;
+        if (FM) {
+            const float re = __fadd_rn(__fmul_rn(yp.x, y.x), __fmul_rn(yp.y, y.y));
+            const float im = __fsub_rn(__fmul_rn(yp.x, y.y), __fmul_rn(yp.y, y.x));
+            ((float *)p.out + (long long)lane_id * p.out_lane_stride)[u] = (EXACT ? atan2f(im, re) : be_atan2(im, re)) * p.fm_ref;
+        } else {
+            ((float2 *)p.out + (long long)lane_id * p.out_lane_stride)[u] = y;
+        }
+        if (u == p.n - 1) p.y_end[lane_id] = y;             // freqdem's r_prime for the next call (lane state, set by k_be_finish)
+    }
+    return y;
+}
+
+// ------------------------------------------------------------------------------------------ gain loop + emission
 // One thread per L-sample segment, kAgcT consecutive segments of a lane per CTA.  The threads walk their windows
 // [b0 - W, b1) in lock-step, 32 samples at a time: each warp fetches the 32-sample blocks of its 32 threads with one
 // coalesced 128-byte load per thread-row into a padded shared-memory tile (row stride 33: column access is
-// conflict-free), every thread runs the recurrence over its row, and in the emitting part of the window the rows are
-// overwritten with the gains and written back the same way.  17 KB of shared memory per CTA whatever L and W are, so
-// every chain of a call is resident at once and the kernel is bound by the latency of one window, not by waves.
+// conflict-free) and every thread runs the recurrence over its row.  In the emitting part of the window the rows are
+// overwritten with the gains, and the CTA turns them into output right away: warp w takes rows 32 w .. 32 w + 31, one
+// 32-sample word per row and iteration, lane = sample (coalesced 256-byte reads of y_dc, coalesced stores): the gains
+// never travel through HBM.  17 KB of shared memory per CTA whatever L and W are, so every chain of a call is resident at
+// once and the kernel is bound by the latency of one window, not by waves.
+// The first sample of a segment takes its gain and its predecessor's output from the segment's OWN warm-up (verified to
+// 1e-5 against the predecessor's end state by k_be_finish; typically equal to ~1e-7).
 constexpr int kAgcT = 128, kAgcB = 32;
-template <bool EXACT>
-__global__ void __launch_bounds__(kAgcT, 5) k_agc_chain(const BackendParams p)
+template <bool EXACT, bool FM>
+__global__ void __launch_bounds__(kAgcT, 4) k_agc_emit(const BackendParams p)
 {
     __shared__ float sm[kAgcT][kAgcB + 1];
+    __shared__ float s_g0[kAgcT];                 // gain before the first sample of the row's current block
+    __shared__ float2 s_yl[kAgcT];                // ungated output of the sample before the row's current block
     const int lane = blockIdx.y, tid = threadIdx.x, w = tid >> 5, l = tid & 31;
     const int seg0 = blockIdx.x * kAgcT, seg = seg0 + tid;
-    if (blockIdx.x == 0 && tid == 0) { if (lane == 0) { p.bad_count[0] = 0; p.bad_count[1] = 0; } be_save_first(p, lane); }
     const float *__restrict__ pw = p.pw + (long long)lane * p.pw_stride;
-    float *__restrict__ go = p.gpost + (long long)lane * p.pw_stride;
+    const float2 *__restrict__ x = p.ydc + (long long)lane * p.ydc_stride;
     const int b0 = seg * p.L;
     const bool live = seg < p.nseg;
     const int nsteps = (p.W + p.L) / kAgcB, wsteps = p.W / kAgcB;
@@ -483,6 +502,7 @@ __global__ void __launch_bounds__(kAgcT, 5) k_agc_chain(const BackendParams p)
         if (s + 1 < nsteps) fetch(s + 1);
         const int u0 = b0 - p.W + s * kAgcB;                    // time of this thread's sm[tid][0]
         const bool emit = s >= wsteps;
+        const bool rec = emit || s == wsteps - 1;               // the last warm-up block records its gains as well (below)
         if (live && u0 >= 0 && u0 < n) {
             if (!started) {
                 started = true;
@@ -500,9 +520,10 @@ __global__ void __launch_bounds__(kAgcT, 5) k_agc_chain(const BackendParams p)
                 p.seg_start[(long long)lane * p.nseg + seg] = s0;
                 g2 = __fmul_rn(g, g);
             }
+            if (emit) s_g0[tid] = g;
             const int cnt = min(kAgcB, n - u0);
             if (cnt == kAgcB) {
-                if (emit) {
+                if (rec) {
 #pragma unroll
                     for (int k = 0; k < kAgcB; k++) { agc_step<EXACT>(co, g, g2, y2p, sm[tid][k]); sm[tid][k] = g; }
                 } else {
@@ -510,20 +531,37 @@ __global__ void __launch_bounds__(kAgcT, 5) k_agc_chain(const BackendParams p)
                     for (int k = 0; k < kAgcB; k++) agc_step<EXACT>(co, g, g2, y2p, sm[tid][k]);
                 }
             } else {
-                for (int k = 0; k < cnt; k++) { agc_step<EXACT>(co, g, g2, y2p, sm[tid][k]); if (emit) sm[tid][k] = g; }
+                for (int k = 0; k < cnt; k++) { agc_step<EXACT>(co, g, g2, y2p, sm[tid][k]); if (rec) sm[tid][k] = g; }
             }
+        }
+        if (s == wsteps - 1 && live && b0 < n) {
+            // ungated output of the sample before the segment: y[b0-1] = y_dc[b0-1] * (gain before it = gain after b0-2,
+            // recorded just now).  Segment 0 continues the previous call (lane state).
+            if (b0 == 0) { const LaneState ls = p.lane[lane]; s_yl[tid] = cf(ls.fm_re, ls.fm_im); }
+            else { const float2 xv = x[b0 - 1]; const float gb = sm[tid][kAgcB - 2]; s_yl[tid] = cf(__fmul_rn(xv.x, gb), __fmul_rn(xv.y, gb)); }
         }
         __syncthreads();
         if (emit) {
-            float *q = go + ubase + s * kAgcB;
-            if (interior) {
-#pragma unroll
-                for (int i = 0; i < 32; i++) q[i * L] = sm[32 * w + i][l];
-            } else {
-#pragma unroll
-                for (int i = 0; i < 32; i++) {
-                    const int u = ubase + i * L + s * kAgcB;
-                    if (seg0 + 32 * w + i < p.nseg && u >= 0 && u < n) go[u] = sm[32 * w + i][l];
+            const int eb = (s - wsteps) * kAgcB;                    // offset of this block inside every segment
+#pragma unroll 4
+            for (int i = 0; i < 32; i++) {
+                const int row = 32 * w + i, rseg = seg0 + row;
+                const int ub = rseg * L + eb;                       // first sample of the row's block (multiple of 32)
+                if (rseg >= p.nseg || ub >= n) break;               // warp-uniform; rows are in increasing time order
+                const int u = ub + l;
+                const bool in = interior || u < n;
+                float2 xv = cf(0.f, 0.f);
+                if (in) xv = x[u];
+                const float ga = sm[row][l];
+                const float gprev = sm[row][l ? l - 1 : 0];
+                const float g0 = l ? gprev : s_g0[row];
+                const float2 yprev0 = s_yl[row];
+                __syncwarp();
+                const float2 y = be_emit_word<true, FM, EXACT>(p, lane, ub, in, xv, g0, ga, yprev0);
+                const int lastl = min(31, n - 1 - ub);
+                if (l == lastl) {
+                    s_yl[row] = y;
+                    if (eb + kAgcB >= L || ub + 32 >= n) p.seg_ylast[(long long)lane * p.nseg + rseg] = y;   // segment's last sample
                 }
             }
             __syncthreads();
@@ -535,194 +573,52 @@ __global__ void __launch_bounds__(kAgcT, 5) k_agc_chain(const BackendParams p)
     }
 }
 
-// no AGC: the chain kernel is not run, the first-sample state is saved by a launch of its own
+// no AGC: the first-sample state is saved by a launch of its own
 __global__ void k_be_first(const BackendParams p)
 {
     const int lane = blockIdx.x * blockDim.x + threadIdx.x;
     if (lane < p.nlanes) be_save_first(p, lane);
 }
 
-// grid-wide verification of the gain speculation.  round 0 / 1: collect the segments whose start state does not
-// continue their predecessor's end state (list for k_agc_refine; each round has its own counter, zeroed by the chain
-// kernel); round 2: first such segment per lane, for the in-order repair.
-__global__ void k_agc_verify(const BackendParams p, int round)
-{
-    const int lane = blockIdx.y, seg = blockIdx.x * blockDim.x + threadIdx.x;
-    if (seg == 0 || seg >= p.nseg) return;
-    const long long t = (long long)lane * p.nseg + seg;
-    if (be_match(p.seg_start[t], p.seg_end[t - 1])) return;
-    if (round < 2) {
-        const unsigned idx = atomicAdd(p.bad_count + round, 1u);
-        if (idx < p.bad_cap) p.bad_list[idx] = (unsigned)t;
-    } else {
-        atomicMin(&p.first_bad[2 * lane], (unsigned)seg);
-    }
-}
-
-// second chance, in parallel: a start state that is slightly off (the warm-up met an un-damped stretch of the
-// loop) is replaced by the predecessor's END state, which is accurate because the predecessor's own L samples
-// damped its error; the segment is re-run from there.  (A predecessor that is being refined at the same time may
-// be read before or after its update: both values are valid to well below the tolerance.)
-template <bool EXACT>
-__global__ void __launch_bounds__(128) k_agc_refine(const BackendParams p, int round)
-{
-    const unsigned count = min(p.bad_count[round], p.bad_cap);
-    for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < count; idx += gridDim.x * blockDim.x) {
-        const long long t = p.bad_list[idx];
-        const int lane = (int)(t / p.nseg), seg = (int)(t - (long long)lane * p.nseg);
-        const SegState pe = p.seg_end[t - 1];
-        float g = pe.g, y2p = pe.y2p;
-        const int b0 = seg * p.L, b1 = min(b0 + p.L, p.n);
-        p.seg_start[t] = pe;
-        agc_run<true, EXACT>(p, lane, g, y2p, b0, b1);
-        SegState s1; s1.g = g; s1.y2p = y2p;
-        p.seg_end[t] = s1;
-    }
-    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(p.fixups + 2, (unsigned long long)count);
-}
-
-// one CTA per lane: re-run the misses in stream order (rare), store the lane's gain state
-template <bool EXACT>
-__global__ void k_agc_fixup(const BackendParams p)
-{
-    const int lane = blockIdx.x;
-    __shared__ unsigned s_next;
-    __shared__ int s_cur;
-    SegState *E = p.seg_end + (long long)lane * p.nseg;
-    const SegState *S0 = p.seg_start + (long long)lane * p.nseg;
-    bool first = true;
-    if (threadIdx.x == 0) s_cur = 1;
-    __syncthreads();
-    while (true) {
-        if (threadIdx.x == 0) s_next = first ? p.first_bad[2 * lane] : 0xffffffffu;
-        __syncthreads();
-        if (!first) {
-            // after a repair: parallel search for the next segment >= s_cur that does not continue its predecessor
-            const int cur = s_cur;
-            for (int j = cur + threadIdx.x; j < p.nseg; j += blockDim.x)
-                if (!be_match(S0[j], E[j - 1])) { atomicMin(&s_next, (unsigned)j); break; }
-            __syncthreads();
-        }
-        first = false;
-        const unsigned nxt = s_next;
-        if (nxt == 0xffffffffu) break;
-        if (threadIdx.x == 0) {
-            int seg = (int)nxt;
-            unsigned long long redone = 0;
-            while (seg < p.nseg) {
-                const SegState pe = E[seg - 1];
-                if (be_match(S0[seg], pe)) break;
-                float g = pe.g, y2p = pe.y2p;
-                const int b0 = seg * p.L, b1 = min(b0 + p.L, p.n);
-                agc_run<true, EXACT>(p, lane, g, y2p, b0, b1);
-                SegState s1; s1.g = g; s1.y2p = y2p;
-                E[seg] = s1;
-                redone++;
-                seg++;      // the successor is re-checked against the new end state on the next iteration
-            }
-            s_cur = seg;
-            atomicAdd(p.fixups, redone);
-        }
-        __syncthreads();
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const SegState e = E[p.nseg - 1];
-        p.lane[lane].g = e.g; p.lane[lane].y2p = e.y2p;
-        p.first_bad[2 * lane] = 0xffffffffu;
-    }
-}
-
-// ------------------------------------------------------------------------------------------ emission
-// One sample per thread, one 32-sample word per warp and iteration.  y[n] = y_dc[n] * (gain before sample n);
-// threshold bit = (gain after sample n) < g_thr; discriminator m[n] = arg(conj(y[n-1]) y[n]) / (2 pi kf)
-// (freqdem_demodulate).  Without an AGC the gain is 1 and there are no bits.
+// ------------------------------------------------------------------------------------------ emission without AGC
+// One sample per thread, one 32-sample word per warp and iteration; gain 1, no bits.
 constexpr int kEmitRun = 16;     // consecutive 32-sample words per warp: the previous sample comes from the neighbour lane
-template <bool AGC, bool FM, bool EXACT>
+template <bool FM, bool EXACT>
 __global__ void __launch_bounds__(256) k_be_emit(const BackendParams p)
 {
     const int lane = blockIdx.y, l = threadIdx.x & 31;
     const float2 *__restrict__ x = p.ydc + (long long)lane * p.ydc_stride;
-    const float *__restrict__ gp = p.gpost + (long long)lane * p.pw_stride;
-    unsigned *exb = p.exbits + (long long)lane * p.nwords, *sgr = p.sgnr + (long long)lane * p.nwords, *sgi = p.sgni + (long long)lane * p.nwords;
-    float *__restrict__ of = (float *)p.out + (long long)lane * p.out_lane_stride;
-    float2 *__restrict__ oc = (float2 *)p.out + (long long)lane * p.out_lane_stride;
-    const float g_thr = p.g_thr, fm_ref = p.fm_ref;
     const int n = p.n, nwords = p.nwords;
     const int w0 = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * kEmitRun, w1 = min(w0 + kEmitRun, nwords);
     if (w0 >= nwords) return;                                    // whole warps leave together
-    // sample before the run (lane 31 holds it for the shuffle below): ungated output and the gain after it
-    float2 ylast = cf(0.f, 0.f);
-    float glast = 1.f;
-    {
-        const int i = w0 * 32 - 1;
-        if (i < 0) { ylast = p.y_first[lane]; if (AGC) glast = p.g_first[lane]; }
-        else {
-            ylast = x[i];
-            if (AGC) {
-                glast = gp[i];
-                const float g1 = (i == 0) ? p.g_first[lane] : gp[i - 1];
-                ylast = cf(__fmul_rn(ylast.x, g1), __fmul_rn(ylast.y, g1));
-            }
-        }
-    }
+    float2 ylast = (w0 == 0) ? p.y_first[lane] : x[w0 * 32 - 1];
     for (int w = w0; w < w1; w++) {
         const int i = w * 32 + l;
         const bool in = i < n;
-        float2 y = cf(0.f, 0.f);
-        float ga = 1.f;
-        if (in) { y = x[i]; if (AGC) ga = gp[i]; }
-        // gain before this sample = gain after the previous one: neighbour lane, or the last lane of the previous word
-        float g0 = 1.f;
-        if (AGC) {
-            g0 = __shfl_up_sync(0xffffffffu, ga, 1);
-            if (l == 0) g0 = glast;
-            y = cf(__fmul_rn(y.x, g0), __fmul_rn(y.y, g0));
-        }
-        float2 yp;
-        yp.x = __shfl_up_sync(0xffffffffu, y.x, 1); yp.y = __shfl_up_sync(0xffffffffu, y.y, 1);
-        if (l == 0) yp = ylast;
-        // carry lane 31 to the next word (every lane keeps a copy)
+        const float2 xv = in ? x[i] : cf(0.f, 0.f);
+        const float2 y = be_emit_word<false, FM, EXACT>(p, lane, w * 32, in, xv, 1.f, 1.f, ylast);
+        if (in && i == n - 1) { p.lane[lane].fm_re = y.x; p.lane[lane].fm_im = y.y; }      // (read by k_be_first, an earlier launch)
         ylast.x = __shfl_sync(0xffffffffu, y.x, 31); ylast.y = __shfl_sync(0xffffffffu, y.y, 31);
-        if (AGC) glast = __shfl_sync(0xffffffffu, ga, 31);
-        if (AGC) {
-            const unsigned ex = __ballot_sync(0xffffffffu, in && ga < g_thr);       // rssi = -20 log10(g) > threshold
-            if (l == 0) exb[w] = ex;
-            if (FM) {
-                const unsigned sr = __ballot_sync(0xffffffffu, in && (__float_as_int(y.x) < 0));
-                const unsigned si = __ballot_sync(0xffffffffu, in && (__float_as_int(y.y) < 0));
-                if (l == 0) { sgr[w] = sr; sgi[w] = si; }
-            }
-        }
-        if (in) {
-            if (FM) {
-                const float re = __fadd_rn(__fmul_rn(yp.x, y.x), __fmul_rn(yp.y, y.y));
-                const float im = __fsub_rn(__fmul_rn(yp.x, y.y), __fmul_rn(yp.y, y.x));
-                of[i] = (EXACT ? atan2f(im, re) : be_atan2(im, re)) * fm_ref;
-            } else {
-                oc[i] = y;
-            }
-            if (i == n - 1) { p.lane[lane].fm_re = y.x; p.lane[lane].fm_im = y.y; }
-        }
     }
 }
 
-// ---- squelch FSM on the threshold bits
+// ------------------------------------------------------------------------------------------ squelch FSM on the bits
 struct FsmState { int mode; unsigned timer; };
 __device__ __forceinline__ bool fsm_same(const FsmState &a, const FsmState &b)
 {
     return a.mode == b.mode && (a.mode != SQ_SIGNALLO || a.timer == b.timer);
 }
 
-// run the FSM over bits [i0, i1) of a lane; when gate != nullptr write one gate bit (mode == SIGNALHI) per sample
-__device__ __forceinline__ void fsm_run(const BackendParams &p, const unsigned *bits, unsigned *gate, FsmState &s,
+// run the FSM over bits [i0, i1) of a lane (bits[w - wbase] = word w); when gate != nullptr write one gate bit
+// (mode == SIGNALHI) per sample
+__device__ __forceinline__ void fsm_run(const BackendParams &p, const unsigned *bits, int wbase, unsigned *gate, FsmState &s,
                                         int i0, int i1)
 {
     int i = i0;
     while (i < i1) {
         const int w = i >> 5, lo = i & 31, cnt = min(32 - lo, i1 - i);
         const unsigned full = (cnt == 32) ? 0xffffffffu : ((1u << cnt) - 1u);
-        const unsigned word = (bits[w] >> lo) & full;
+        const unsigned word = (bits[w - wbase] >> lo) & full;
         unsigned gw = 0;
         if (word == full && s.mode == SQ_SIGNALHI) gw = full;                              // stays open
         else if (word == 0 && s.mode == SQ_ENABLED) gw = 0;                                // stays closed
@@ -741,121 +637,320 @@ __device__ __forceinline__ void fsm_run(const BackendParams &p, const unsigned *
     }
 }
 
-__global__ void __launch_bounds__(128) k_backend_fsm(const BackendParams p)
-{
-    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= (long long)p.nlanes * p.nseg) return;
-    const int lane = (int)(t / p.nseg), seg = (int)(t - (long long)lane * p.nseg);
-    const unsigned *bits = p.exbits + (long long)lane * p.nwords;
-    unsigned *gate = p.gatebits + (long long)lane * p.nwords;
-    const int b0 = seg * p.L, b1 = min(b0 + p.L, p.n);
-    FsmState s;
-    int w0 = b0 - p.FW * p.L;
-    if (w0 <= 0) { w0 = 0; s.mode = p.lane[lane].mode; s.timer = p.lane[lane].timer; }   // exact
-    else { s.mode = SQ_ENABLED; s.timer = 0; }
-    fsm_run(p, bits, nullptr, s, w0, b0);
-    p.fsm_start[t] = s;
-    fsm_run(p, bits, gate, s, b0, b1);
-    p.fsm_end[t] = s;
-}
+// ------------------------------------------------------------------------------------------ k_be_finish
+// Everything behind the fused gain/emission kernel, in ONE cooperative launch (all CTAs co-resident, software grid
+// barrier between phases):
+//   A  verify the gain speculation (segments whose start state does not continue their predecessor's end state are
+//      listed) and resolve the squelch FSM speculatively on the threshold bits (every segment replays timeout + 8 bits)
+//   -- only if the list is not empty (digital silence, an un-damped stretch of the loop): refine the listed segments in
+//      parallel from their predecessors' end states (two rounds), repair what is left in stream order, redo A's FSM pass
+//   B  verify the FSM speculation; misses (a measure-zero coincidence of the time-out with a threshold crossing) are
+//      repaired in stream order
+//   C  apply the gate (Liquid.chs:700-704) to the output, store the lanes' states, reset the counters
+// Under the test-only CPU emulation (CTAs run one after the other) the phases are launched one by one instead.
+constexpr int kFinT = 256;
+constexpr int kFinWords = 8320;                 // shared staging: threshold words of 256 segments + replay, or a segment's gains
+enum { FIN_A = 0, FIN_R0, FIN_V1, FIN_R1, FIN_V2, FIN_FIX, FIN_A2, FIN_B, FIN_BFIX, FIN_C, FIN_NPHASE };
 
-__global__ void k_backend_fsm_verify(const BackendParams p)
+__device__ __forceinline__ void be_grid_barrier(unsigned *bar, unsigned nblocks)
 {
-    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= (long long)p.nlanes * p.nseg) return;
-    const int lane = (int)(t / p.nseg), seg = (int)(t - (long long)lane * p.nseg);
-    if (seg > 0 && !fsm_same(p.fsm_start[t], p.fsm_end[t - 1])) atomicMin(&p.first_bad[2 * lane + 1], (unsigned)seg);
-}
-
-__global__ void k_backend_fsm_fix(const BackendParams p)
-{
-    const int lane = blockIdx.x;
-    __shared__ unsigned s_next;
-    __shared__ int s_cur;
-    FsmState *E = p.fsm_end + (long long)lane * p.nseg;
-    const FsmState *S0 = p.fsm_start + (long long)lane * p.nseg;
-    const unsigned *bits = p.exbits + (long long)lane * p.nwords;
-    unsigned *gate = p.gatebits + (long long)lane * p.nwords;
-    bool first = true;
-    if (threadIdx.x == 0) s_cur = 1;
     __syncthreads();
-    while (true) {
-        if (threadIdx.x == 0) s_next = first ? p.first_bad[2 * lane + 1] : 0xffffffffu;
-        __syncthreads();
-        if (!first) {
-            const int cur = s_cur;
-            for (int j = cur + threadIdx.x; j < p.nseg; j += blockDim.x)
-                if (!fsm_same(S0[j], E[j - 1])) { atomicMin(&s_next, (unsigned)j); break; }
-            __syncthreads();
-        }
-        first = false;
-        const unsigned nxt = s_next;
-        if (nxt == 0xffffffffu) break;
-        if (threadIdx.x == 0) {
-            int seg = (int)nxt;
-            unsigned long long redone = 0;
-            while (seg < p.nseg) {
-                FsmState s = E[seg - 1];
-                if (fsm_same(S0[seg], s)) break;
-                const int b0 = seg * p.L, b1 = min(b0 + p.L, p.n);
-                fsm_run(p, bits, gate, s, b0, b1);
-                E[seg] = s;
-                redone++;
-                seg++;
-            }
-            s_cur = seg;
-            atomicAdd(p.fixups + 1, redone);
-        }
-        __syncthreads();
+#ifndef CSDR_EMU
+    if (threadIdx.x == 0) {
+        volatile unsigned *vb = bar;
+        const unsigned gen = vb[1];
+        __threadfence();
+        if (atomicAdd(&bar[0], 1u) == nblocks - 1) { vb[0] = 0; __threadfence(); atomicAdd(&bar[1], 1u); }
+        else { while (vb[1] == gen) {} }
+        __threadfence();
     }
+    __syncthreads();
+#else
+    (void)bar; (void)nblocks;
+#endif
+}
+
+// Re-run one segment from `st` (the predecessor's end state) and emit it again; CTA-cooperative: thread 0 runs the
+// recurrence into shared memory, then every warp emits whole words.  s_g: L + 1 floats.
+template <bool EXACT>
+__device__ void be_redo_segment(const BackendParams &p, int lane, int seg, SegState st, float *s_g)
+{
+    const int b0 = seg * p.L, b1 = min(b0 + p.L, p.n), len = b1 - b0;
+    const float *__restrict__ pw = p.pw + (long long)lane * p.pw_stride;
+    const float2 *__restrict__ x = p.ydc + (long long)lane * p.ydc_stride;
+    const long long t = (long long)lane * p.nseg + seg;
     __syncthreads();
     if (threadIdx.x == 0) {
-        // gate of the last sample of the previous chunk, needed by the discriminator's first sample
-        p.prev_gate[lane] = (p.lane[lane].mode == SQ_SIGNALHI) ? 1u : 0u;
-        const FsmState e = E[p.nseg - 1];
-        p.lane[lane].mode = e.mode; p.lane[lane].timer = e.timer;
-        p.first_bad[2 * lane + 1] = 0xffffffffu;
+        const AgcCoef co{p.alpha, p.one_minus_alpha_f, p.neg_half_alpha};
+        float g = st.g, y2p = st.y2p, g2 = __fmul_rn(g, g);
+        p.seg_start[t] = st;
+        s_g[0] = g;
+        for (int i = 0; i < len; i++) { agc_step<EXACT>(co, g, g2, y2p, pw[b0 + i]); s_g[i + 1] = g; }
+        SegState s1; s1.g = g; s1.y2p = y2p;
+        p.seg_end[t] = s1;
     }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5, l = threadIdx.x & 31;
+    const float2 yprev_seg = (seg == 0) ? p.y_first[lane] : p.seg_ylast[t - 1];
+    for (int wd = warp; wd * 32 < len; wd += nwarps) {
+        const int idx = wd * 32 + l, u = b0 + idx;
+        const bool in = idx < len;
+        const float2 xv = in ? x[u] : cf(0.f, 0.f);
+        const float g0 = in ? s_g[idx] : 1.f, ga = in ? s_g[idx + 1] : 1.f;
+        // output of the sample before the word: from this segment's own gains, or the predecessor's last sample
+        float2 yp0 = yprev_seg;
+        if (wd > 0) { const float2 xp = x[b0 + wd * 32 - 1]; const float gp = s_g[wd * 32 - 1]; yp0 = cf(__fmul_rn(xp.x, gp), __fmul_rn(xp.y, gp)); }
+        float2 y;
+        if (p.demod == 1) y = be_emit_word<true, true, EXACT>(p, lane, b0 + wd * 32, in, xv, g0, ga, yp0);
+        else              y = be_emit_word<true, false, EXACT>(p, lane, b0 + wd * 32, in, xv, g0, ga, yp0);
+        if (idx == len - 1) p.seg_ylast[t] = y;
+    }
+    __syncthreads();
 }
 
-// apply the gate.  One thread per 32 samples.  cf32 output: closed samples become 0+0j (Liquid.chs:704).
-// Discriminator output: m[i] = arg(conj(r'[i-1]) r'[i]) with r' the GATED samples; when either neighbour is closed the
-// product is a signed zero whose argument is 0 or +-pi exactly as in the sequential code, so those values are
-// recomputed here from the sign bits of the ungated samples.
-__global__ void k_backend_gate(const BackendParams p)
+template <bool EXACT>
+__global__ void __launch_bounds__(kFinT, 2) k_be_finish(const BackendParams p, int phase_lo, int phase_hi)
 {
-    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= (long long)p.nlanes * p.nwords) return;
-    const int lane = (int)(t / p.nwords), w = (int)(t - (long long)lane * p.nwords);
-    const unsigned *gate = p.gatebits + (long long)lane * p.nwords;
-    const int i0 = w * 32, cnt = min(32, p.n - i0);
-    const unsigned full = (cnt == 32) ? 0xffffffffu : ((1u << cnt) - 1u);
-    const unsigned g = gate[w] & full;
-    if (p.demod != 1) {
-        if (g == full) return;
-        float2 *oc = (float2 *)p.out + (long long)lane * p.out_lane_stride + i0;
-        for (int b = 0; b < cnt; b++)
-            if (!((g >> b) & 1u)) oc[b] = cf(0.f, 0.f);
-        return;
+    __shared__ unsigned s_buf[kFinWords];
+    __shared__ unsigned s_next;
+    __shared__ int s_cur;
+    const int tid = threadIdx.x, nthr = gridDim.x * blockDim.x, gtid = blockIdx.x * blockDim.x + tid;
+    const long long nsegs = (long long)p.nlanes * p.nseg;
+    const int blocks_per_lane = (p.nseg + kFinT - 1) / kFinT;
+    const bool stage_ok = (long long)(p.FW + kFinT) * p.L / 32 <= kFinWords;
+
+    bool pending = false;                        // a phase has run since the last grid barrier
+    for (int ph = phase_lo; ph <= phase_hi; ph++) {
+        if (pending) { be_grid_barrier(p.barrier, gridDim.x); pending = false; }
+        // phases that only exist to repair a failed speculation are skipped (same decision in every CTA: the counters
+        // are complete, no phase has run since the last barrier)
+        const unsigned cnt0 = p.bad_count[0];
+        if ((ph >= FIN_R0 && ph <= FIN_A2) && cnt0 == 0) continue;
+        if (ph == FIN_R1 && p.bad_count[1] == 0) continue;
+        if (ph == FIN_BFIX && p.bad_count[2] == 0) continue;
+        pending = true;
+
+        if (ph == FIN_A || ph == FIN_V1 || ph == FIN_V2) {
+            // ---- gain speculation: start state of every segment against its predecessor's end state
+            const int round = ph == FIN_A ? 0 : ph == FIN_V1 ? 1 : 2;
+            for (long long t = gtid; t < nsegs; t += nthr) {
+                const int seg = (int)(t % p.nseg);
+                if (seg == 0 || be_match(p.seg_start[t], p.seg_end[t - 1])) continue;
+                if (round < 2) {
+                    const unsigned idx = atomicAdd(p.bad_count + round, 1u);
+                    if (idx < p.bad_cap) p.bad_list[(long long)round * p.bad_cap + idx] = (unsigned)t;
+                } else {
+                    atomicMin(&p.first_bad[2 * (int)(t / p.nseg)], (unsigned)seg);
+                }
+            }
+        }
+        if (ph == FIN_A) {
+            // what the chunk's first sample needs from the previous call, before the lane states are overwritten
+            for (int lane = gtid; lane < p.nlanes; lane += nthr) {
+                be_save_first(p, lane);
+                p.prev_gate[lane] = (p.lane[lane].mode == SQ_SIGNALHI) ? 1u : 0u;
+            }
+        }
+        if (ph == FIN_R0 || ph == FIN_R1) {
+            // ---- second chance, in parallel: a start state that is slightly off (the warm-up met an un-damped stretch
+            // of the loop) is replaced by the predecessor's END state, which is accurate because the predecessor's own L
+            // samples damped its error; the segment is re-run and re-emitted from there, one CTA per segment.
+            const int round = ph == FIN_R0 ? 0 : 1;
+            const unsigned count = min(p.bad_count[round], p.bad_cap);
+            for (unsigned idx = blockIdx.x; idx < count; idx += gridDim.x) {
+                const long long t = p.bad_list[(long long)round * p.bad_cap + idx];
+                const int lane = (int)(t / p.nseg), seg = (int)(t - (long long)lane * p.nseg);
+                be_redo_segment<EXACT>(p, lane, seg, p.seg_end[t - 1], reinterpret_cast<float *>(s_buf));
+            }
+            if (blockIdx.x == 0 && tid == 0) atomicAdd(p.fixups + 2, (unsigned long long)count);
+        }
+        if (ph == FIN_FIX) {
+            // ---- last resort: re-run the remaining misses of a lane in stream order (a gain frozen by digital silence)
+            for (int lane = blockIdx.x; lane < p.nlanes; lane += gridDim.x) {
+                SegState *E = p.seg_end + (long long)lane * p.nseg;
+                const SegState *S0 = p.seg_start + (long long)lane * p.nseg;
+                bool first = true;
+                if (tid == 0) s_cur = 1;
+                __syncthreads();
+                while (true) {
+                    if (tid == 0) s_next = first ? p.first_bad[2 * lane] : 0xffffffffu;
+                    __syncthreads();
+                    if (!first) {
+                        // after a repair: parallel search for the next segment >= s_cur that does not continue its predecessor
+                        const int cur = s_cur;
+                        for (int j = cur + tid; j < p.nseg; j += blockDim.x)
+                            if (!be_match(S0[j], E[j - 1])) { atomicMin(&s_next, (unsigned)j); break; }
+                        __syncthreads();
+                    }
+                    first = false;
+                    const unsigned nxt = s_next;
+                    if (nxt == 0xffffffffu) break;
+                    int seg = (int)nxt;
+                    unsigned long long redone = 0;
+                    while (seg < p.nseg) {
+                        __syncthreads();
+                        const SegState pe = E[seg - 1];
+                        if (be_match(S0[seg], pe)) break;       // uniform: every thread reads the same two states
+                        be_redo_segment<EXACT>(p, lane, seg, pe, reinterpret_cast<float *>(s_buf));
+                        redone++;
+                        seg++;      // the successor is re-checked against the new end state on the next iteration
+                    }
+                    __syncthreads();
+                    if (tid == 0) { s_cur = seg; atomicAdd(p.fixups, redone); }
+                    __syncthreads();
+                }
+                __syncthreads();
+            }
+        }
+        if (ph == FIN_A || ph == FIN_A2) {
+            // ---- squelch FSM, speculative: 256 consecutive segments of a lane per CTA; their threshold words and the
+            // FW segments of replay in front of them are staged in shared memory with coalesced loads
+            for (int item = blockIdx.x; item < p.nlanes * blocks_per_lane; item += gridDim.x) {
+                const int lane = item / blocks_per_lane, sb = (item - lane * blocks_per_lane) * kFinT;
+                const unsigned *bits = p.exbits + (long long)lane * p.nwords;
+                unsigned *gate = p.gatebits + (long long)lane * p.nwords;
+                const int wlo = max(0, (sb - p.FW) * (p.L / 32)), whi = min(p.nwords, (sb + kFinT) * (p.L / 32));
+                __syncthreads();
+                if (stage_ok) for (int wd = wlo + tid; wd < whi; wd += blockDim.x) s_buf[wd - wlo] = bits[wd];
+                __syncthreads();
+                const int seg = sb + tid;
+                if (seg < p.nseg) {
+                    const long long t = (long long)lane * p.nseg + seg;
+                    const int b0 = seg * p.L, b1 = min(b0 + p.L, p.n);
+                    FsmState s;
+                    int w0 = b0 - p.FW * p.L;
+                    if (w0 <= 0) { w0 = 0; s.mode = p.lane[lane].mode; s.timer = p.lane[lane].timer; }   // exact
+                    else { s.mode = SQ_ENABLED; s.timer = 0; }
+                    const unsigned *src = stage_ok ? s_buf : bits;
+                    const int wbase = stage_ok ? wlo : 0;
+                    fsm_run(p, src, wbase, nullptr, s, w0, b0);
+                    p.fsm_start[t] = s;
+                    fsm_run(p, src, wbase, gate, s, b0, b1);
+                    p.fsm_end[t] = s;
+                }
+            }
+        }
+        if (ph == FIN_B) {
+            for (long long t = gtid; t < nsegs; t += nthr) {
+                const int seg = (int)(t % p.nseg);
+                if (seg > 0 && !fsm_same(p.fsm_start[t], p.fsm_end[t - 1])) {
+                    atomicMin(&p.first_bad[2 * (int)(t / p.nseg) + 1], (unsigned)seg);
+                    atomicAdd(p.bad_count + 2, 1u);
+                }
+            }
+        }
+        if (ph == FIN_BFIX) {
+            for (int lane = blockIdx.x; lane < p.nlanes; lane += gridDim.x) {
+                FsmState *E = p.fsm_end + (long long)lane * p.nseg;
+                const FsmState *S0 = p.fsm_start + (long long)lane * p.nseg;
+                const unsigned *bits = p.exbits + (long long)lane * p.nwords;
+                unsigned *gate = p.gatebits + (long long)lane * p.nwords;
+                bool first = true;
+                if (tid == 0) s_cur = 1;
+                __syncthreads();
+                while (true) {
+                    if (tid == 0) s_next = first ? p.first_bad[2 * lane + 1] : 0xffffffffu;
+                    __syncthreads();
+                    if (!first) {
+                        const int cur = s_cur;
+                        for (int j = cur + tid; j < p.nseg; j += blockDim.x)
+                            if (!fsm_same(S0[j], E[j - 1])) { atomicMin(&s_next, (unsigned)j); break; }
+                        __syncthreads();
+                    }
+                    first = false;
+                    const unsigned nxt = s_next;
+                    if (nxt == 0xffffffffu) break;
+                    if (tid == 0) {
+                        int seg = (int)nxt;
+                        unsigned long long redone = 0;
+                        while (seg < p.nseg) {
+                            FsmState s = E[seg - 1];
+                            if (fsm_same(S0[seg], s)) break;
+                            const int b0 = seg * p.L, b1 = min(b0 + p.L, p.n);
+                            fsm_run(p, bits, 0, gate, s, b0, b1);
+                            E[seg] = s;
+                            redone++;
+                            seg++;
+                        }
+                        s_cur = seg;
+                        atomicAdd(p.fixups + 1, redone);
+                    }
+                    __syncthreads();
+                }
+                __syncthreads();
+            }
+        }
+        if (ph == FIN_C) {
+            // ---- gate.  cf32 output: closed samples become 0+0j (Liquid.chs:704).  Discriminator output: m[i] =
+            // arg(conj(r'[i-1]) r'[i]) with r' the GATED samples; when either neighbour is closed the product is a signed
+            // zero whose argument is 0 or +-pi exactly as in the sequential code, so those values are recomputed here
+            // from the sign bits of the ungated samples.  One warp per run of 32 words, lane = sample.
+            if (p.gate) {
+                const int l = tid & 31, warp = gtid >> 5, nwarp = nthr >> 5;
+                const int runs_per_lane = (p.nwords + 31) / 32;
+                for (long long item = warp; item < (long long)p.nlanes * runs_per_lane; item += nwarp) {
+                    const int lane = (int)(item / runs_per_lane), wd0 = (int)(item - (long long)lane * runs_per_lane) * 32;
+                    const unsigned *gate = p.gatebits + (long long)lane * p.nwords;
+                    const int wd = wd0 + l;
+                    const bool have = wd < p.nwords;
+                    const int cntw = have ? min(32, p.n - wd * 32) : 0;
+                    const unsigned fullw = (cntw == 32) ? 0xffffffffu : ((1u << cntw) - 1u);
+                    const unsigned gw = have ? (gate[wd] & fullw) : 0u;
+                    const unsigned gtop = have ? (wd ? (gate[wd - 1] >> 31) : p.prev_gate[lane]) : 0u;
+                    unsigned srw = 0, siw = 0, srt = 0, sit = 0;
+                    if (p.demod == 1 && have) {
+                        const unsigned *sr = p.sgnr + (long long)lane * p.nwords, *si = p.sgni + (long long)lane * p.nwords;
+                        srw = sr[wd]; siw = si[wd];
+                        srt = wd ? (sr[wd - 1] >> 31) : (p.prev_sign[lane] & 1u);
+                        sit = wd ? (si[wd - 1] >> 31) : ((p.prev_sign[lane] >> 1) & 1u);
+                    }
+                    const int nw = min(32, p.nwords - wd0);
+                    for (int j = 0; j < nw; j++) {
+                        const unsigned g = __shfl_sync(0xffffffffu, gw, j), full = __shfl_sync(0xffffffffu, fullw, j);
+                        const int i = (wd0 + j) * 32 + l;
+                        const bool in = (full >> l) & 1u;
+                        if (p.demod != 1) {
+                            if (g == full) continue;
+                            if (in && !((g >> l) & 1u)) ((float2 *)p.out + (long long)lane * p.out_lane_stride)[i] = cf(0.f, 0.f);
+                            continue;
+                        }
+                        const unsigned gprev = (g << 1) | __shfl_sync(0xffffffffu, gtop, j);
+                        if ((g & gprev & full) == full) continue;            // every sample and its predecessor are open
+                        float *of = (float *)p.out + (long long)lane * p.out_lane_stride;
+                        if (g == 0 && (gprev & full) == 0) { if (in) of[i] = 0.f; continue; }     // closed throughout: arg(+0 + j0) = 0
+                        const unsigned r = __shfl_sync(0xffffffffu, srw, j), im = __shfl_sync(0xffffffffu, siw, j);
+                        const unsigned rprev = (r << 1) | __shfl_sync(0xffffffffu, srt, j), iprev = (im << 1) | __shfl_sync(0xffffffffu, sit, j);
+                        const bool open = (g >> l) & 1u, popen = (gprev >> l) & 1u;
+                        if (!in || (open && popen)) continue;
+                        // unit-magnitude stand-ins carry the signs; a closed sample is +0+0j
+                        const float yr = open ? (((r >> l) & 1u) ? -1.f : 1.f) : 0.f;
+                        const float yi = open ? (((im >> l) & 1u) ? -1.f : 1.f) : 0.f;
+                        const float fr = popen ? (((rprev >> l) & 1u) ? -1.f : 1.f) : 0.f;
+                        const float fi = popen ? (((iprev >> l) & 1u) ? -1.f : 1.f) : 0.f;
+                        const float re = __fadd_rn(__fmul_rn(fr, yr), __fmul_rn(fi, yi));
+                        const float ii = __fsub_rn(__fmul_rn(fr, yi), __fmul_rn(fi, yr));
+                        of[i] = atan2f(ii, re) * p.fm_ref;
+                    }
+                }
+            }
+            // lane states for the next call (nobody reads the old ones any more: the barrier in front of this phase)
+            for (int lane = gtid; lane < p.nlanes; lane += nthr) {
+                const SegState e = p.seg_end[(long long)lane * p.nseg + p.nseg - 1];
+                const FsmState f = p.fsm_end[(long long)lane * p.nseg + p.nseg - 1];
+                const float2 y = p.y_end[lane];
+                LaneState &ls = p.lane[lane];
+                ls.g = e.g; ls.y2p = e.y2p; ls.mode = f.mode; ls.timer = f.timer; ls.fm_re = y.x; ls.fm_im = y.y;
+                p.first_bad[2 * lane] = 0xffffffffu; p.first_bad[2 * lane + 1] = 0xffffffffu;
+            }
+        }
     }
-    const unsigned gprev = (g << 1) | (w ? (gate[w - 1] >> 31) : p.prev_gate[lane]);
-    if ((g & gprev & full) == full) return;              // every sample and its predecessor are open
-    const unsigned *sr = p.sgnr + (long long)lane * p.nwords, *si = p.sgni + (long long)lane * p.nwords;
-    const unsigned r = sr[w], im = si[w];
-    const unsigned rprev = (r << 1) | (w ? (sr[w - 1] >> 31) : (p.prev_sign[lane] & 1u));
-    const unsigned iprev = (im << 1) | (w ? (si[w - 1] >> 31) : ((p.prev_sign[lane] >> 1) & 1u));
-    float *of = (float *)p.out + (long long)lane * p.out_lane_stride + i0;
-    for (int b = 0; b < cnt; b++) {
-        const bool open = (g >> b) & 1u, popen = (gprev >> b) & 1u;
-        if (open && popen) continue;
-        // unit-magnitude stand-ins carry the signs; a closed sample is +0+0j
-        const float yr = open ? (((r >> b) & 1u) ? -1.f : 1.f) : 0.f;
-        const float yi = open ? (((im >> b) & 1u) ? -1.f : 1.f) : 0.f;
-        const float fr = popen ? (((rprev >> b) & 1u) ? -1.f : 1.f) : 0.f;
-        const float fi = popen ? (((iprev >> b) & 1u) ? -1.f : 1.f) : 0.f;
-        const float re = __fadd_rn(__fmul_rn(fr, yr), __fmul_rn(fi, yi));
-        const float ii = __fsub_rn(__fmul_rn(fr, yi), __fmul_rn(fi, yr));
-        of[b] = atan2f(ii, re) * p.fm_ref;
+    // counters for the next call: by the last CTA to get here (every CTA has read them by then)
+    if (phase_hi == FIN_C) {
+        __syncthreads();
+        if (tid == 0) {
+            __threadfence();
+            if (atomicAdd(&p.barrier[2], 1u) == gridDim.x - 1) { p.bad_count[0] = 0; p.bad_count[1] = 0; p.bad_count[2] = 0; p.barrier[2] = 0; }
+        }
     }
 }
 
@@ -919,49 +1014,24 @@ inline void be_launch_dc(Launch &launch, const DcParams &d, bool apply)
     if (apply) be_launch_prep(launch, d);
 }
 
-template <bool EXACT, class Launch>
-inline void be_launch_gain(Launch &launch, const BackendParams &b)
-{
-    launch(k_agc_chain<EXACT>, dim3((b.nseg + kAgcT - 1) / kAgcT, b.nlanes), dim3(kAgcT), 0, b);   // L, W: multiples of 32
-    // two rounds of verify + parallel refine (a run of consecutive misses needs one round per level of
-    // inaccuracy handed down the run; an empty list costs a few microseconds), then the in-order repair
-    const dim3 gv((b.nseg + 127) / 128, b.nlanes);
-    launch(k_agc_verify, gv, dim3(128), 0, b, 0);
-    launch.debug_after_verify(b);
-    launch(k_agc_refine<EXACT>, dim3(64), dim3(128), 0, b, 0);
-    launch(k_agc_verify, gv, dim3(128), 0, b, 1);
-    launch(k_agc_refine<EXACT>, dim3(64), dim3(128), 0, b, 1);
-    launch(k_agc_verify, gv, dim3(128), 0, b, 2);
-    launch(k_agc_fixup<EXACT>, dim3(b.nlanes), dim3(128), 0, b);
-}
-
-template <bool AGC, bool FM, class Launch>
-inline void be_launch_emit(Launch &launch, const BackendParams &b)
-{
-    const dim3 grid((unsigned)std::max(1, (b.nwords + 8 * kEmitRun - 1) / (8 * kEmitRun)), b.nlanes), block(256);   // kEmitRun words per warp
-    if (b.exact_math) launch(k_be_emit<AGC, FM, true>, grid, block, 0, b);
-    else              launch(k_be_emit<AGC, FM, false>, grid, block, 0, b);
-}
-
-// everything after the dc/power pass: gain loop, emission, squelch FSM, gate
+// everything after the dc/power pass: gain loop + emission, then verification / squelch FSM / gate in one cooperative launch
+// (`launch.coop(kernel, block, params, phase_lo, phase_hi)` sizes the grid to what is co-resident; the CPU emulation runs
+// the phases one by one)
 template <class Launch>
 inline void be_launch(Launch &launch, const BackendParams &b)
 {
-    const long long segs = (long long)b.nlanes * b.nseg;
-    const unsigned gb = (unsigned)((segs + 127) / 128);
     if (b.has_agc) {
-        if (b.exact_math) be_launch_gain<true>(launch, b); else be_launch_gain<false>(launch, b);
-        if (b.demod == 1) be_launch_emit<true, true>(launch, b); else be_launch_emit<true, false>(launch, b);
-        launch(k_backend_fsm, dim3(gb), dim3(128), 0, b);
-        launch(k_backend_fsm_verify, dim3(gb), dim3(128), 0, b);
-        launch(k_backend_fsm_fix, dim3(b.nlanes), dim3(128), 0, b);
-        if (b.gate) {
-            const long long words = (long long)b.nlanes * b.nwords;
-            launch(k_backend_gate, dim3((unsigned)((words + 127) / 128)), dim3(128), 0, b);
-        }
+        const dim3 grid((b.nseg + kAgcT - 1) / kAgcT, b.nlanes), block(kAgcT);      // L, W: multiples of 32
+        if (b.exact_math) { if (b.demod == 1) launch(k_agc_emit<true, true>, grid, block, 0, b); else launch(k_agc_emit<true, false>, grid, block, 0, b); }
+        else              { if (b.demod == 1) launch(k_agc_emit<false, true>, grid, block, 0, b); else launch(k_agc_emit<false, false>, grid, block, 0, b); }
+        launch.debug_after_verify(b);
+        if (b.exact_math) launch.coop(k_be_finish<true>, dim3(kFinT), b, (int)FIN_A, (int)FIN_C);
+        else              launch.coop(k_be_finish<false>, dim3(kFinT), b, (int)FIN_A, (int)FIN_C);
     } else {
         launch(k_be_first, dim3((b.nlanes + 127) / 128), dim3(128), 0, b);
-        if (b.demod == 1) be_launch_emit<false, true>(launch, b); else be_launch_emit<false, false>(launch, b);
+        const dim3 grid((unsigned)std::max(1, (b.nwords + 8 * kEmitRun - 1) / (8 * kEmitRun)), b.nlanes), block(256);   // kEmitRun words per warp
+        if (b.exact_math) { if (b.demod == 1) launch(k_be_emit<true, true>, grid, block, 0, b); else launch(k_be_emit<false, true>, grid, block, 0, b); }
+        else              { if (b.demod == 1) launch(k_be_emit<true, false>, grid, block, 0, b); else launch(k_be_emit<false, false>, grid, block, 0, b); }
     }
 }
 

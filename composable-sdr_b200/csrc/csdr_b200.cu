@@ -26,6 +26,7 @@
 #include <mutex>
 #include <stdexcept>
 #include <string>
+#include <tuple>
 #include <vector>
 
 using namespace csdr;
@@ -54,6 +55,29 @@ void launch(void (*k)(Args...), dim3 grid, dim3 block, size_t smem, cudaStream_t
     k<<<grid, block, smem, st>>>(std::forward<Act>(a)...);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     CK(cudaGetLastError());
+}
+
+// cooperative launch (all CTAs co-resident: the kernel synchronises the grid itself): as many CTAs as fit, at most `want`
+template <class... Args, class... Act>
+void launch_coop(void (*k)(Args...), int want, dim3 block, cudaStream_t st, int sms, Act &&...a)
+{
+    static std::mutex mu;
+    static std::map<std::pair<const void *, int>, int> per_sm;
+    int dev = 0, occ = 0;
+    CK(cudaGetDevice(&dev));
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        int &v = per_sm[{reinterpret_cast<const void *>(k), dev}];
+        if (v == 0) { CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k, (int)block.x, 0)); if (v < 1) throw CudaError{"cooperative kernel does not fit on an SM"}; }
+        occ = v;
+    }
+    const int grid = std::max(1, std::min(want, occ * sms));
+    std::tuple<std::decay_t<Args>...> vals(std::forward<Act>(a)...);
+    void *argv[sizeof...(Args)];
+    size_t i = 0;
+    std::apply([&](auto &...v) { ((argv[i++] = (void *)&v), ...); }, vals);
+    CK(cudaLaunchCooperativeKernel(reinterpret_cast<const void *>(k), dim3(grid), block, argv, 0, st));
+    g_launches.fetch_add(1, std::memory_order_relaxed);
 }
 
 struct DevBuf {
@@ -388,18 +412,21 @@ struct Backend {
     float kf = 0.3f;
     int L = 512, W = 384, G = 128; bool fixed_L = false;
     DevBuf lane, Vloc, carry, powA, ss, se, fs, fe, exbits, gatebits, sgnr, sgni, prev_gate, prev_sign, first_bad, bad_list, bad_count, fixups;
-    DevBuf ydc, pwbuf, gpost, g_first, y_first;
+    DevBuf ydc, pwbuf, g_first, y_first, y_end, seg_ylast, barrier;
     int pw_ready_n = -1;       // the producer of the input has already written its power for a call of this many samples
     int FW = 3; unsigned long long last_refined = 0; int last_L = 0, last_W = 0;
     // self-tuning warm-up: the counters of every call are copied to pinned memory asynchronously; the next call looks
     // at them (no synchronisation) and lengthens / shortens the warm-up
-    unsigned long long *h_counters = nullptr; cudaEvent_t ev_counters = nullptr; bool counters_pending = false;
-    unsigned long long seen[3] = {0, 0, 0}; int W_cur = 0, calm_calls = 0; long long last_nseg = 1;
-    ~Backend() { if (h_counters) cudaFreeHost(h_counters); if (ev_counters) cudaEventDestroy(ev_counters); }
+    // self-tuning warm-up, deterministic: the counters of every call are copied to one of two pinned slots; call k waits for
+    // the copy of call k-2 (one call always stays in flight) and lengthens / shortens the warm-up from it
+    unsigned long long *h_counters = nullptr; cudaEvent_t ev_counters[2] = {nullptr, nullptr}; unsigned long long calls = 0;
+    unsigned long long seen[3] = {0, 0, 0}; int W_cur = 0, calm_calls = 0; long long nseg_of[2] = {1, 1};
+    int sms = 148;
+    ~Backend() { if (h_counters) cudaFreeHost(h_counters); for (auto e : ev_counters) if (e) cudaEventDestroy(e); }
 
     void init(const Ctx &c, int lanes, float g0 = 1000.0f, int mode0 = SQ_ENABLED)
     {
-        nlanes = lanes;
+        nlanes = lanes; sms = c.sms;
         // segment and warm-up lengths in whole 32-sample words (one warp handles a dc group, one ballot a word)
         L = (std::max(64, g_options[CSDR_OPT_AGC_SEGMENT]) + 31) / 32 * 32; W = (std::max(32, g_options[CSDR_OPT_AGC_WARMUP]) + 31) / 32 * 32;
         fixed_L = g_options[CSDR_OPT_AGC_SEGMENT] != 512;      // an explicit setting is taken literally
@@ -425,12 +452,16 @@ struct Backend {
             c.sync();
         }
         fixups.ensure(3 * sizeof(unsigned long long)); CK(cudaMemsetAsync(fixups.p, 0, fixups.cap, c.stream));
-        bad_list.ensure(sizeof(unsigned) * 65536); bad_count.ensure(2 * sizeof(unsigned)); CK(cudaMemsetAsync(bad_count.p, 0, bad_count.cap, c.stream));
+        bad_list.ensure(sizeof(unsigned) * 2 * 65536); bad_count.ensure(4 * sizeof(unsigned)); CK(cudaMemsetAsync(bad_count.p, 0, bad_count.cap, c.stream));
+        barrier.ensure(4 * sizeof(unsigned)); CK(cudaMemsetAsync(barrier.p, 0, barrier.cap, c.stream));
+        y_end.ensure(sizeof(float2) * nlanes); CK(cudaMemsetAsync(y_end.p, 0, y_end.cap, c.stream));
 
         c.sync();
     }
     struct Launcher {
-        cudaStream_t st;
+        cudaStream_t st; int sms;
+        template <class... Args, class... Act>
+        void coop(void (*k)(Args...), dim3 block, Act &&...a) const { launch_coop(k, 2 * sms, block, st, sms, std::forward<Act>(a)...); }
         // CSDR_OPT_DEBUG: print the first speculation misses (start state vs predecessor's end state)
         void debug_after_verify(const BackendParams &b) const
         {
@@ -445,7 +476,7 @@ struct Backend {
             for (unsigned i = 0; i < show; i++) {
                 SegState a, e;
                 CK(cudaMemcpy(&a, b.seg_start + lst[i], sizeof(a), cudaMemcpyDeviceToHost));
-                CK(cudaMemcpy(&e, b.seg_end + lst[i] - 1, sizeof(e), cudaMemcpyDeviceToHost));
+                CK(cudaMemcpy(&e, b.seg_end + lst[i] - 1, sizeof(e), cudaMemcpyDeviceToHost));     // (the list is filled by k_be_finish: previous call's)
                 fprintf(stderr, "  seg %u: start g=%.9g y2p=%.9g | pred end g=%.9g y2p=%.9g | rel %.3g %.3g\n", lst[i], a.g, a.y2p, e.g,
                         e.y2p, fabs(a.g - e.g) / fmax(a.g, e.g), fabs(a.y2p - e.y2p) / fmax(a.y2p, e.y2p));
             }
@@ -477,7 +508,7 @@ struct Backend {
         if (n <= 0) return;
         DcParams d = dc_params(in, in_stride, out, out_stride, n);
         d.rot = rot ? 1 : 0; d.rot_theta = rot_theta; d.rot_dtheta = rot_dtheta; d.rot_quantize = rot_quantize;
-        Launcher l{c.stream};
+        Launcher l{c.stream, sms};
         be_launch_dc(l, d, true);
     }
     // Where the producer of the next run()'s input (n samples per lane, no dc blocker here) may write |x|^2 itself:
@@ -486,7 +517,7 @@ struct Backend {
     {
         if (!has_agc || has_dc || n <= 0) return nullptr;
         const long long pws = ((long long)n + 3) / 4 * 4;
-        pwbuf.ensure(sizeof(float) * (size_t)nlanes * pws); gpost.ensure(sizeof(float) * (size_t)nlanes * pws);
+        pwbuf.ensure(sizeof(float) * (size_t)nlanes * pws);
         pw_ready_n = n;
         *stride = pws;
         return pwbuf.as<float>();
@@ -499,7 +530,13 @@ struct Backend {
     void run_on(cudaStream_t st, const float2 *in, long long in_stride, void *out, long long out_stride, int n)
     {
         if (n <= 0) return;
-        Launcher l{st};
+        Launcher l{st, sms};
+        if (has_dc && !has_agc && demod == 0) {
+            // dc blocker only (config 1): the output pass writes the caller's buffer directly
+            DcParams d = dc_params(in, in_stride, (float2 *)out, out_stride, n);
+            be_launch_dc(l, d, true);
+            return;
+        }
         // segment length: the per-segment recurrences are latency bound, so aim for >= ~64k concurrent chains
         // (shorter segments = more chains but relatively more warm-up work); whole 32-sample words
         int L = this->L;
@@ -507,17 +544,19 @@ struct Backend {
             while (L > 64 && L % 64 == 0 && (long long)nlanes * ((n + L - 1) / L) < 65536) L /= 2;
         }
         int W = this->W;
+        const int slot = (int)(calls & 1);
         if (has_agc && !fixed_L) {
             if (!h_counters) {
-                CK(cudaHostAlloc((void **)&h_counters, 3 * sizeof(unsigned long long), cudaHostAllocDefault));
-                CK(cudaEventCreateWithFlags(&ev_counters, cudaEventDisableTiming));
+                CK(cudaHostAlloc((void **)&h_counters, 2 * 3 * sizeof(unsigned long long), cudaHostAllocDefault));
+                for (auto &e : ev_counters) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming | cudaEventBlockingSync));
                 W_cur = this->W;
             }
-            if (counters_pending && cudaEventQuery(ev_counters) == cudaSuccess) {
-                counters_pending = false;
-                const unsigned long long seq = h_counters[0] - seen[0], refined = h_counters[2] - seen[2];
-                seen[0] = h_counters[0]; seen[1] = h_counters[1]; seen[2] = h_counters[2];
-                if (seq > 0 || refined * 200 > (unsigned long long)last_nseg) { W_cur = std::min(W_cur * 2, 6144); calm_calls = 0; }
+            if (calls >= 2) {
+                CK(cudaEventSynchronize(ev_counters[slot]));           // counters as they stood after call k-2
+                const unsigned long long *hc = h_counters + 3 * slot;
+                const unsigned long long seq = hc[0] - seen[0], refined = hc[2] - seen[2];
+                seen[0] = hc[0]; seen[1] = hc[1]; seen[2] = hc[2];
+                if (seq > 0 || refined * 200 > (unsigned long long)nseg_of[slot]) { W_cur = std::min(W_cur * 2, 6144); calm_calls = 0; }
                 else if (refined == 0 && ++calm_calls >= 8 && W_cur > this->W) { W_cur /= 2; calm_calls = 0; }
             }
             W = W_cur;
@@ -549,7 +588,7 @@ struct Backend {
                 b.ydc = ydc.as<float2>(); b.ydc_stride = pws;
             }
             if (has_agc) {
-                pwbuf.ensure(sizeof(float) * (size_t)nlanes * pws); gpost.ensure(sizeof(float) * (size_t)nlanes * pws);
+                pwbuf.ensure(sizeof(float) * (size_t)nlanes * pws);
                 d.pw = pwbuf.as<float>(); d.pw_stride = pws;
             }
             if (has_dc) be_launch_dc(l, d, true);
@@ -565,8 +604,10 @@ struct Backend {
         b.squelch_enabled = squelch ? 1 : 0; b.gate = gate ? 1 : 0;
         b.exact_math = g_options[CSDR_OPT_AGC_EXACT_MATH] ? 1 : 0;
         b.lane = lane.as<LaneState>(); b.seg_start = ss.as<SegState>(); b.seg_end = se.as<SegState>();
-        b.pw = pwbuf.as<float>(); b.gpost = gpost.as<float>(); b.pw_stride = pws;
+        b.pw = pwbuf.as<float>(); b.pw_stride = pws;
         b.g_first = g_first.as<float>(); b.y_first = y_first.as<float2>();
+        seg_ylast.ensure(sizeof(float2) * segs);
+        b.y_end = y_end.as<float2>(); b.seg_ylast = seg_ylast.as<float2>(); b.barrier = barrier.as<unsigned>();
         b.nwords = nwords;
         // the FSM forgets its entry state after timeout + 4 samples: replay that many bits (in whole segments)
         b.FW = (int)std::min<unsigned>(64u, (agc_timeout + 8 + (unsigned)L - 1) / (unsigned)L);
@@ -578,12 +619,12 @@ struct Backend {
         b.bad_list = bad_list.as<unsigned>(); b.bad_count = bad_count.as<unsigned>(); b.bad_cap = 65536;
         b.fixups = fixups.as<unsigned long long>();
         be_launch(l, b);
-        if (has_agc && !fixed_L && !counters_pending) {
-            CK(cudaMemcpyAsync(h_counters, fixups.p, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-            CK(cudaEventRecord(ev_counters, st));
-            counters_pending = true;
-            last_nseg = (long long)nlanes * nseg;
+        if (has_agc && !fixed_L) {
+            CK(cudaMemcpyAsync(h_counters + 3 * slot, fixups.p, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+            CK(cudaEventRecord(ev_counters[slot], st));
+            nseg_of[slot] = (long long)nlanes * nseg;
         }
+        calls++;
     }
     unsigned long long read_fixups(const Ctx &c)
     {

@@ -17,6 +17,12 @@ using namespace csdr;
 struct EmuLaunch {
     template <class K, class... A> void operator()(K k, dim3 g, dim3 b, size_t smem, A... a) const { csdr_emu::launch(g, b, smem, k, a...); }
     void debug_after_verify(const BackendParams &) const {}
+    // cooperative kernel: CTAs run one after the other here, so the phases (separated by grid barriers on the GPU) are
+    // launched one by one; every phase decides for itself whether it has anything to do
+    template <class K> void coop(K k, dim3 b, const BackendParams &p, int lo, int hi) const
+    {
+        for (int ph = lo; ph <= hi; ph++) csdr_emu::launch(dim3(3), b, 0, k, p, ph, ph);
+    }
 };
 
 extern "C" {
@@ -156,11 +162,13 @@ long long emu_backend(int nlanes, long long lane_stride, int has_dc, float dc_al
         std::vector<SegState> ss((size_t)nlanes * nseg), se((size_t)nlanes * nseg);
         std::vector<FsmState> fs((size_t)nlanes * nseg), fe((size_t)nlanes * nseg);
         std::vector<float2> ydc((size_t)nlanes * pws), yfirst(nlanes);
-        std::vector<float> pw((size_t)nlanes * pws), gpost((size_t)nlanes * pws), gfirst(nlanes);
+        std::vector<float> pw((size_t)nlanes * pws), gfirst(nlanes);
+        std::vector<float2> yend(nlanes), sylast((size_t)nlanes * nseg);
+        unsigned barrier[4] = {0, 0, 0, 0};
         int nwords = (nx + 31) / 32;
         std::vector<unsigned> exb((size_t)nlanes * nwords), gb((size_t)nlanes * nwords), pg(nlanes, 0), ps(nlanes, 0);
-        std::vector<unsigned> sgr((size_t)nlanes * nwords), sgi((size_t)nlanes * nwords), fb(2 * nlanes, 0xffffffffu), blist(4096);
-        unsigned bcount[2] = {0, 0};
+        std::vector<unsigned> sgr((size_t)nlanes * nwords), sgi((size_t)nlanes * nwords), fb(2 * nlanes, 0xffffffffu), blist(2 * 4096);
+        unsigned bcount[4] = {0, 0, 0, 0};
         DcParams d{};
         d.in = x + pos; d.in_lane_stride = lane_stride; d.n = nx; d.nlanes = nlanes; d.G = G; d.ngrp = ngrp; d.nblk = nblk;
         d.has_dc = has_dc; d.out = has_dc ? ydc.data() : nullptr; d.out_lane_stride = pws;
@@ -182,7 +190,8 @@ long long emu_backend(int nlanes, long long lane_stride, int has_dc, float dc_al
         b.squelch_enabled = 1; b.gate = 1;
         b.lane = lane.data(); b.seg_start = ss.data(); b.seg_end = se.data();
         b.ydc = has_dc ? ydc.data() : x + pos; b.ydc_stride = has_dc ? pws : lane_stride;
-        b.pw = pw.data(); b.gpost = gpost.data(); b.pw_stride = pws; b.g_first = gfirst.data(); b.y_first = yfirst.data();
+        b.pw = pw.data(); b.pw_stride = pws; b.g_first = gfirst.data(); b.y_first = yfirst.data();
+        b.y_end = yend.data(); b.seg_ylast = sylast.data(); b.barrier = barrier;
         b.nwords = nwords; b.FW = (1000 + 8 + L - 1) / L;
         b.exbits = exb.data(); b.gatebits = gb.data(); b.fsm_start = fs.data(); b.fsm_end = fe.data();
         b.prev_gate = pg.data(); b.prev_sign = ps.data(); b.sgnr = sgr.data(); b.sgni = sgi.data();
