@@ -6,8 +6,8 @@
 //
 // Parallelisation over TIME (the reference is one sequential loop per stream).  Only the AGC gain is a genuinely
 // sequential, non-linear recurrence; everything else is arranged around it as coalesced, fully parallel passes:
-//   1. dc blocker (linear recurrence): k_dc_local reduces every G-sample group to its zero-state response (one warp
-//      per group, fp64) and scans the groups of a CTA, k_dc_carry scans the CTAs: the exact filter state at every
+//   1. dc blocker (linear recurrence): k_dc_scan reduces every G-sample group to its zero-state response (one warp
+//      per group, fp64), scans the groups of a CTA and looks back over the preceding CTAs: the exact filter state at every
 //      group boundary is then one multiply-add away.
 //   2. k_be_prep (one warp per group): dc-blocked samples y_dc[n] and their power p[n] = |y_dc[n]|^2.
 //   3. k_agc_emit: the gain loop sees its input only through p[n]  (|x g|^2 = g^2 p), so the chain is
@@ -73,10 +73,8 @@ struct BackendParams {
 };
 
 // ------------------------------------------------------------------------------------------ dc blocker
-// v[n] = x[n] + c v[n-1] (c = 1 - alpha), y[n] = v[n] - v[n-1].  The state at every G-sample group boundary is
-//   V(j) = Vloc[j-1] + carry[b] * A^k ,   A = c^G, b = (j-1) / kDcGB, k = (j-1) % kDcGB + 1
-// Vloc = in-block inclusive scan of the groups' zero-state responses (k_dc_local: kDcGB groups per CTA, one warp per
-// group, each lane G/32 consecutive samples), carry[b] = state at the start of block b (k_dc_carry), all fp64.
+// v[n] = x[n] + c v[n-1] (c = 1 - alpha), y[n] = v[n] - v[n-1]: a linear recurrence, evaluated in fp64 as affine maps
+// (k_dc_scan below); the float32 recurrence of iirfilt then runs over G/32 samples per lane from the exact state.
 constexpr int kDcGB = 64;
 constexpr int kDcWarps = 8;
 
@@ -89,23 +87,17 @@ struct DcParams {
     double c;                                  // 1 - alpha  (= -a1)
     double cS[5];                              // c^(S d), S = G/32 samples per lane, d = 1, 2, 4, 8, 16
     float a1;
-    double2 *Vloc;                             // [nlanes][ngrp]  block-local state at the END of group j
-    double2 *carry;                            // [nlanes][nblk]  state at the start of block b
-    const double *powA;                        // [kDcGB + 1]     A^k
-    LaneState *lane;
+    const double *powA;                        // [kDcGB + 1]     A^k, A = c^G
+    // k_dc_scan: blocks of kDcGB groups publish their zero-state response and look back over their predecessors
+    double2 *agg;                              // [nlanes][nblk]  zero-state response of block b (fp64)
+    unsigned *flag;                            // [nlanes][nblk]  == epoch once agg is valid
+    unsigned epoch;                            // this call's number (flags of earlier calls are stale)
+    unsigned *ticket;                          // [2] next block to hand out, CTAs that have left (reset by the last one)
+    const double *powAB; int depth;            // [depth + 1] (c^(G kDcGB))^k; blocks further back than `depth` have decayed
+                                               // below 1e-13 of the state
+    const float2 *dc_in; float2 *dc_out;       // [nlanes] filter state v1 before the chunk / after it (two buffers: blocks
+                                               // of one launch read the old state while the last block writes the new one)
 };
-
-__device__ __forceinline__ double2 dc_state_at(const double2 *Vloc, const double2 *carry, const double *powA,
-                                               int ngrp, int nblk, int lane, int j)
-{
-    // filter state before group j (= after j groups)
-    const double2 *cl = carry + (long long)lane * nblk;
-    if (j == 0) return cl[0];
-    const int b = (j - 1) / kDcGB, k = (j - 1) - b * kDcGB + 1;
-    const double2 v = Vloc[(long long)lane * ngrp + (j - 1)], cb = cl[b];
-    const double a = powA[k];
-    return make_double2(v.x + cb.x * a, v.y + cb.y * a);
-}
 
 // the S = G/32 consecutive samples of this lane in group j (zero past the end of the chunk); 16-byte loads when the
 // lane's samples are 16-byte aligned
@@ -139,155 +131,181 @@ __device__ __forceinline__ void dc_warp_scan(double &ar, double &ai, double &m, 
     (void)cS;
 }
 
+// One pass over the samples: a CTA takes blocks of kDcGB groups (8192 samples at G = 128) in stream order (ticket),
+//   1. loads the block into registers (a warp per run of 8 groups, 4 samples per lane and group) and reduces it to its
+//      zero-state response (fp64 warp scans, then a scan over the 64 groups in shared memory), publishes that,
+//   2. looks back: the filter state before the block is  sum_k AB^(k-1) agg[b-k]  (+ AB^b x the state carried from the
+//      previous call), AB = c^8192 = 0.017 for alpha = 5e-4, so `depth` = 7 predecessors settle it to 1e-13,
+//   3. gives every lane the exact state before its samples, runs iirfilt's float32 recurrence over them and writes the
+//      dc-blocked samples (optionally pre-rotated for the channelizer) and their power.
+// Each sample is read once and written once; nothing else travels through HBM.  out may alias in.
 template <int S>
-__global__ void __launch_bounds__(32 * kDcWarps) k_dc_local(const DcParams p)
+__global__ void __launch_bounds__(32 * kDcWarps, 2) k_dc_scan(const DcParams p)
 {
     constexpr int GW = kDcGB / kDcWarps;               // groups per warp
-    __shared__ double sr[kDcGB], si[kDcGB];
-    const int lane = blockIdx.y, t = threadIdx.x, w = t >> 5, l = t & 31;
-    const float2 *x = p.in + (long long)lane * p.in_lane_stride;
+    __shared__ double sr[kDcGB], si[kDcGB];            // zero-state response at the END of each group, block-local
+    __shared__ double s_red[2][kDcWarps];
+    __shared__ double s_cr, s_ci;
+    __shared__ int s_ticket;
+    const int t = threadIdx.x, w = t >> 5, l = t & 31;
     const double A = p.powA[1];
-    double Rr = 0.0, Ri = 0.0;                          // zero-state response of this warp's run of groups
-    for (int k = 0; k < GW; k++) {
-        const int j = blockIdx.x * kDcGB + w * GW + k;
-        float2 v[S];
-        dc_load<S>(x, (j < p.ngrp) ? p.n : 0, j * p.G + l * S, v);
-        double ar = 0.0, ai = 0.0;
+    const int total = p.nlanes * p.nblk;
+    while (true) {
+        if (t == 0) s_ticket = (int)atomicAdd(p.ticket, 1u);
+        __syncthreads();
+        const int tk = s_ticket;
+        if (tk >= total) break;
+        const int lane = tk / p.nblk, b = tk - lane * p.nblk;
+        const float2 *__restrict__ x = p.in + (long long)lane * p.in_lane_stride;
+        float2 v[GW][S];
+        // ---- 1. load + reduce
+        double Rr = 0.0, Ri = 0.0;                          // zero-state response of this warp's run of groups
 #pragma unroll
-        for (int q = 0; q < S; q++) { ar = ar * p.c + (double)v[q].x; ai = ai * p.c + (double)v[q].y; }
-        double m = p.cS[0];
-        dc_warp_scan(ar, ai, m, p.cS);
-        const double Tr = __shfl_sync(0xffffffffu, ar, 31), Ti = __shfl_sync(0xffffffffu, ai, 31);
-        Rr = Rr * A + Tr; Ri = Ri * A + Ti;
-        if (l == 0) { sr[w * GW + k] = Rr; si[w * GW + k] = Ri; }
-    }
-    __syncthreads();
-    if (t < kDcGB) {
-        const int j = blockIdx.x * kDcGB + t, tw = t / GW, tk = t - tw * GW;
-        // state at the start of warp tw's run inside this block
-        double pr = 0.0, pi = 0.0;
-        for (int q = 0; q < tw; q++) {
-            const double a = p.powA[GW * (tw - 1 - q)];
-            pr += sr[q * GW + GW - 1] * a; pi += si[q * GW + GW - 1] * a;
-        }
-        const double a = p.powA[tk + 1];
-        if (j < p.ngrp) p.Vloc[(long long)lane * p.ngrp + j] = make_double2(sr[t] + pr * a, si[t] + pi * a);
-    }
-}
-
-// one CTA per lane: carries of the blocks (affine scan, 1024 blocks per round), then the state after the last
-// sample goes into the lane state
-__global__ void __launch_bounds__(1024) k_dc_carry(const DcParams p)
-{
-    const int lane = blockIdx.x, t = threadIdx.x;
-    __shared__ double sm[1024], sr[1024], si[1024];
-    __shared__ double cr, ci;
-    double2 *cl = p.carry + (long long)lane * p.nblk;
-    if (t == 0) { cr = (double)p.lane[lane].dc_re; ci = (double)p.lane[lane].dc_im; }
-    __syncthreads();
-    const double AB = p.powA[kDcGB];
-    for (int base = 0; base < p.nblk; base += 1024) {
-        const int b = base + t;
-        // map of block b: s -> AB s + (zero-state response of the whole block)
-        double m = AB, ar = 0.0, ai = 0.0;
-        const int jl = (b + 1) * kDcGB - 1;
-        if (b < p.nblk && jl < p.ngrp) { const double2 v = p.Vloc[(long long)lane * p.ngrp + jl]; ar = v.x; ai = v.y; }
-        sm[t] = m; sr[t] = ar; si[t] = ai;
-        __syncthreads();
-        for (int d = 1; d < 1024; d <<= 1) {
-            double pm = 1.0, pr = 0.0, pi = 0.0;
-            if (t >= d) { pm = sm[t - d]; pr = sr[t - d]; pi = si[t - d]; }
-            __syncthreads();
-            if (t >= d) { ar += pr * m; ai += pi * m; m *= pm; sm[t] = m; sr[t] = ar; si[t] = ai; }
-            __syncthreads();
-        }
-        // carry[b] = state at the START of block b: the inclusive map of blocks base..b-1 applied to the round's carry
-        if (b < p.nblk) {
-            if (t == 0) cl[b] = make_double2(cr, ci);
-            else cl[b] = make_double2(sr[t - 1] + cr * sm[t - 1], si[t - 1] + ci * sm[t - 1]);
+        for (int k = 0; k < GW; k++) {
+            const int j = b * kDcGB + w * GW + k;
+            dc_load<S>(x, (j < p.ngrp) ? p.n : 0, j * p.G + l * S, v[k]);
+            double ar = 0.0, ai = 0.0;
+#pragma unroll
+            for (int q = 0; q < S; q++) { ar = ar * p.c + (double)v[k][q].x; ai = ai * p.c + (double)v[k][q].y; }
+            double m = p.cS[0];
+            dc_warp_scan(ar, ai, m, p.cS);
+            const double Tr = __shfl_sync(0xffffffffu, ar, 31), Ti = __shfl_sync(0xffffffffu, ai, 31);
+            Rr = Rr * A + Tr; Ri = Ri * A + Ti;
+            if (l == 0) { sr[w * GW + k] = Rr; si[w * GW + k] = Ri; }
         }
         __syncthreads();
-        if (t == 1023) { const double nr = ar + cr * m, ni = ai + ci * m; cr = nr; ci = ni; }
+        double vr = 0.0, vi = 0.0;
+        if (t < kDcGB) {
+            const int tw = t / GW, tkk = t - tw * GW;
+            // state at the start of warp tw's run inside this block
+            double pr = 0.0, pi = 0.0;
+            for (int q = 0; q < tw; q++) {
+                const double a = p.powA[GW * (tw - 1 - q)];
+                pr += sr[q * GW + GW - 1] * a; pi += si[q * GW + GW - 1] * a;
+            }
+            const double a = p.powA[tkk + 1];
+            vr = sr[t] + pr * a; vi = si[t] + pi * a;
+        }
         __syncthreads();
+        if (t < kDcGB) { sr[t] = vr; si[t] = vi; }
+        if (t == kDcGB - 1) {
+            p.agg[tk] = make_double2(vr, vi);
+            __threadfence();
+            *((volatile unsigned *)(p.flag + tk)) = p.epoch;
+        }
+        // ---- 2. look back (thread k waits for block b - 1 - k, b - 1 - k - 256, ...)
+        double cr = 0.0, ci = 0.0;
+        for (int k = t; k < p.depth && k < b; k += blockDim.x) {
+            const int src = tk - 1 - k;
+            while (*((volatile unsigned *)(p.flag + src)) != p.epoch) {}
+            __threadfence();
+            const volatile double *ap = reinterpret_cast<const volatile double *>(p.agg + src);
+            const double ax = ap[0], ay = ap[1];
+            const double m = p.powAB[k];
+            cr += ax * m; ci += ay * m;
+        }
+        if (t == 0 && b <= p.depth) { const float2 v0 = p.dc_in[lane]; const double m = p.powAB[b]; cr += (double)v0.x * m; ci += (double)v0.y * m; }
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) { cr += __shfl_xor_sync(0xffffffffu, cr, d); ci += __shfl_xor_sync(0xffffffffu, ci, d); }
+        if (l == 0) { s_red[0][w] = cr; s_red[1][w] = ci; }
+        __syncthreads();
+        if (t == 0) {
+            double a = 0.0, bb = 0.0;
+            for (int q = 0; q < kDcWarps; q++) { a += s_red[0][q]; bb += s_red[1][q]; }
+            s_cr = a; s_ci = bb;
+        }
+        __syncthreads();
+        const double carry_r = s_cr, carry_i = s_ci;
+        // ---- 3. apply
+        float2 *__restrict__ yo = p.out ? p.out + (long long)lane * p.out_lane_stride : nullptr;
+        float *__restrict__ wo = p.pw ? p.pw + (long long)lane * p.pw_stride : nullptr;
+#pragma unroll
+        for (int k = 0; k < GW; k++) {
+            const int jl = w * GW + k, j = b * kDcGB + jl;
+            if (j >= p.ngrp) break;                                           // warp-uniform
+            const int i0 = j * p.G + l * S;
+            double ar = 0.0, ai = 0.0;
+#pragma unroll
+            for (int q = 0; q < S; q++) { ar = ar * p.c + (double)v[k][q].x; ai = ai * p.c + (double)v[k][q].y; }
+            double m = p.cS[0];
+            dc_warp_scan(ar, ai, m, p.cS);
+            // state before group j, then before this lane's samples
+            const double pa = p.powA[jl];
+            const double Vr = (jl ? sr[jl - 1] : 0.0) + carry_r * pa, Vi = (jl ? si[jl - 1] : 0.0) + carry_i * pa;
+            double er = __shfl_up_sync(0xffffffffu, ar, 1), ei = __shfl_up_sync(0xffffffffu, ai, 1), em = __shfl_up_sync(0xffffffffu, m, 1);
+            if (l == 0) { er = 0.0; ei = 0.0; em = 1.0; }
+            float v1r = (float)(er + Vr * em), v1i = (float)(ei + Vi * em);
+#pragma unroll
+            for (int q = 0; q < S; q++) {
+                if (i0 + q < p.n) {
+                    const float v0r = __fsub_rn(v[k][q].x, __fmul_rn(p.a1, v1r));
+                    const float v0i = __fsub_rn(v[k][q].y, __fmul_rn(p.a1, v1i));
+                    v[k][q] = cf(__fsub_rn(v0r, v1r), __fsub_rn(v0i, v1i));
+                    v1r = v0r; v1i = v0i;
+                }
+            }
+            // the lane that holds the chunk's last sample stores the filter state for the next call
+            if (i0 < p.n && i0 + S >= p.n) p.dc_out[lane] = cf(v1r, v1i);
+            if (p.rot) {
+                // the channelizer's pre-rotation (nco_crcf_mix_block_down, Liquid.chs:847) rides on this pass
+#pragma unroll
+                for (int q = 0; q < S; q++) {
+                    const float2 ph = fe_phasor(p.rot_theta + (unsigned)(i0 + q) * p.rot_dtheta, p.rot_quantize);
+                    v[k][q] = cf(v[k][q].x * ph.x + v[k][q].y * ph.y, v[k][q].y * ph.x - v[k][q].x * ph.y);
+                }
+            }
+            if (yo) {
+                float2 *y = yo + i0;
+                if (S == 4 && i0 + S <= p.n && (reinterpret_cast<uintptr_t>(y) & 15) == 0) {
+                    reinterpret_cast<float4 *>(y)[0] = make_float4(v[k][0].x, v[k][0].y, v[k][1 % S].x, v[k][1 % S].y);
+                    reinterpret_cast<float4 *>(y)[1] = make_float4(v[k][2 % S].x, v[k][2 % S].y, v[k][3 % S].x, v[k][3 % S].y);
+                } else {
+#pragma unroll
+                    for (int q = 0; q < S; q++) if (i0 + q < p.n) y[q] = v[k][q];
+                }
+            }
+            if (wo) {
+                float *wp = wo + i0;
+                float e[S];
+#pragma unroll
+                for (int q = 0; q < S; q++) e[q] = __fadd_rn(__fmul_rn(v[k][q].x, v[k][q].x), __fmul_rn(v[k][q].y, v[k][q].y));
+                if (S == 4 && i0 + S <= p.n) *reinterpret_cast<float4 *>(wp) = make_float4(e[0], e[1 % S], e[2 % S], e[3 % S]);   // pw_stride % 4 == 0
+                else {
+#pragma unroll
+                    for (int q = 0; q < S; q++) if (i0 + q < p.n) wp[q] = e[q];
+                }
+            }
+        }
+        __syncthreads();      // sr / si / s_ticket are reused by the next block
     }
+    // tickets for the next launch: reset by the last CTA to leave
     if (t == 0) {
-        // state after n samples: restart from the last full-group boundary
-        const int jf = p.n / p.G;
-        const double2 v = dc_state_at(p.Vloc, p.carry, p.powA, p.ngrp, p.nblk, lane, jf);
-        float v1r = (float)v.x, v1i = (float)v.y;
-        const float2 *x = p.in + (long long)lane * p.in_lane_stride;
-        for (int i = jf * p.G; i < p.n; i++) {
-            const float2 s = x[i];
-            v1r = __fsub_rn(s.x, __fmul_rn(p.a1, v1r));
-            v1i = __fsub_rn(s.y, __fmul_rn(p.a1, v1i));
-        }
-        p.lane[lane].dc_re = v1r; p.lane[lane].dc_im = v1i;
+        __threadfence();
+        if (atomicAdd(p.ticket + 1, 1u) == gridDim.x - 1) { p.ticket[0] = 0; p.ticket[1] = 0; }
     }
 }
 
-// dc-blocked samples and/or their power, one warp per group: the filter state before each lane's samples comes from
-// the exact group-boundary state and a warp scan, then every lane runs the float32 recurrence of iirfilt over its
-// own G/32 samples.  out may alias in (every lane reads its samples before it writes them).
+// power of the samples (no dc blocker in this back end: per-channel lanes behind a channelizer whose kernels did not
+// write it themselves), one warp per group
 template <int S>
 __global__ void __launch_bounds__(256) k_be_prep(const DcParams p)
 {
     const int lane = blockIdx.y, l = threadIdx.x & 31;
     const float2 *__restrict__ x = p.in + (long long)lane * p.in_lane_stride;
-    float2 *__restrict__ yo = p.out ? p.out + (long long)lane * p.out_lane_stride : nullptr;
-    float *__restrict__ wo = p.pw ? p.pw + (long long)lane * p.pw_stride : nullptr;
+    float *__restrict__ wo = p.pw + (long long)lane * p.pw_stride;
     const int jstep = (int)((gridDim.x * blockDim.x) >> 5);
-    // several groups per warp: the pointer set-up above is paid once
     for (int j = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5); j < p.ngrp; j += jstep) {     // warp-uniform
         const int i0 = j * p.G + l * S;
         float2 v[S];
         dc_load<S>(x, p.n, i0, v);
-        if (p.has_dc) {
-            double ar = 0.0, ai = 0.0;
+        float *w = wo + i0;
+        float e[S];
 #pragma unroll
-            for (int q = 0; q < S; q++) { ar = ar * p.c + (double)v[q].x; ai = ai * p.c + (double)v[q].y; }
-            double m = p.cS[0];
-            dc_warp_scan(ar, ai, m, p.cS);
-            // state before this lane's samples = map of lanes 0..l-1 applied to the group's entry state
-            const double2 V = dc_state_at(p.Vloc, p.carry, p.powA, p.ngrp, p.nblk, lane, j);
-            double er = __shfl_up_sync(0xffffffffu, ar, 1), ei = __shfl_up_sync(0xffffffffu, ai, 1), em = __shfl_up_sync(0xffffffffu, m, 1);
-            if (l == 0) { er = 0.0; ei = 0.0; em = 1.0; }
-            float v1r = (float)(er + V.x * em), v1i = (float)(ei + V.y * em);
+        for (int q = 0; q < S; q++) e[q] = __fadd_rn(__fmul_rn(v[q].x, v[q].x), __fmul_rn(v[q].y, v[q].y));
+        if (S == 4 && i0 + S <= p.n) *reinterpret_cast<float4 *>(w) = make_float4(e[0], e[1 % S], e[2 % S], e[3 % S]);   // pw_stride % 4 == 0
+        else {
 #pragma unroll
-            for (int q = 0; q < S; q++) {
-                const float v0r = __fsub_rn(v[q].x, __fmul_rn(p.a1, v1r));
-                const float v0i = __fsub_rn(v[q].y, __fmul_rn(p.a1, v1i));
-                v[q] = cf(__fsub_rn(v0r, v1r), __fsub_rn(v0i, v1i));
-                v1r = v0r; v1i = v0i;
-            }
-        }
-        if (p.rot) {
-            // the channelizer's pre-rotation (nco_crcf_mix_block_down, Liquid.chs:847) rides on this pass
-#pragma unroll
-            for (int q = 0; q < S; q++) {
-                const float2 w = fe_phasor(p.rot_theta + (unsigned)(i0 + q) * p.rot_dtheta, p.rot_quantize);
-                v[q] = cf(v[q].x * w.x + v[q].y * w.y, v[q].y * w.x - v[q].x * w.y);
-            }
-        }
-        if (yo) {
-            float2 *y = yo + i0;
-            if (S == 4 && i0 + S <= p.n && (reinterpret_cast<uintptr_t>(y) & 15) == 0) {
-                reinterpret_cast<float4 *>(y)[0] = make_float4(v[0].x, v[0].y, v[1 % S].x, v[1 % S].y);
-                reinterpret_cast<float4 *>(y)[1] = make_float4(v[2 % S].x, v[2 % S].y, v[3 % S].x, v[3 % S].y);
-            } else {
-#pragma unroll
-                for (int q = 0; q < S; q++) if (i0 + q < p.n) y[q] = v[q];
-            }
-        }
-        if (wo) {
-            float *w = wo + i0;
-            float e[S];
-#pragma unroll
-            for (int q = 0; q < S; q++) e[q] = __fadd_rn(__fmul_rn(v[q].x, v[q].x), __fmul_rn(v[q].y, v[q].y));
-            if (S == 4 && i0 + S <= p.n) *reinterpret_cast<float4 *>(w) = make_float4(e[0], e[1 % S], e[2 % S], e[3 % S]);   // pw_stride % 4 == 0
-            else {
-#pragma unroll
-                for (int q = 0; q < S; q++) if (i0 + q < p.n) w[q] = e[q];
-            }
+            for (int q = 0; q < S; q++) if (i0 + q < p.n) w[q] = e[q];
         }
     }
 }
@@ -458,12 +476,15 @@ __device__ __forceinline__ float2 be_emit_word(const BackendParams &p, int lane_
 // The first sample of a segment takes its gain and its predecessor's output from the segment's OWN warm-up (verified to
 // 1e-5 against the predecessor's end state by k_be_finish; typically equal to ~1e-7).
 constexpr int kAgcT = 128, kAgcB = 32;
+constexpr size_t kAgcSmem = sizeof(float) * kAgcT * (kAgcB + 1) + sizeof(float) * kAgcT + sizeof(float2) * kAgcT + sizeof(float2) * kAgcT * kAgcB;
 template <bool EXACT, bool FM>
 __global__ void __launch_bounds__(kAgcT, 4) k_agc_emit(const BackendParams p)
 {
-    __shared__ float sm[kAgcT][kAgcB + 1];
-    __shared__ float s_g0[kAgcT];                 // gain before the first sample of the row's current block
-    __shared__ float2 s_yl[kAgcT];                // ungated output of the sample before the row's current block
+    CSDR_DYN_SMEM(smem_raw);
+    float (*sm)[kAgcB + 1] = reinterpret_cast<float (*)[kAgcB + 1]>(smem_raw);            // powers -> gains, one row per segment
+    float *s_g0 = reinterpret_cast<float *>(smem_raw) + kAgcT * (kAgcB + 1);                // gain before the first sample of the row's current block
+    float2 *s_yl = reinterpret_cast<float2 *>(s_g0 + kAgcT);                                 // ungated output of the sample before the row's current block
+    float2 *s_x = s_yl + kAgcT;                                                              // [kAgcT][kAgcB] dc-blocked samples of the current block
     const int lane = blockIdx.y, tid = threadIdx.x, w = tid >> 5, l = tid & 31;
     const int seg0 = blockIdx.x * kAgcT, seg = seg0 + tid;
     const float *__restrict__ pw = p.pw + (long long)lane * p.pw_stride;
@@ -494,14 +515,34 @@ __global__ void __launch_bounds__(kAgcT, 4) k_agc_emit(const BackendParams p)
             }
         }
     };
+    // the samples the emission of a step needs (rows of this warp) are copied into shared memory asynchronously at the
+    // START of the step and arrive while the recurrence runs: two rows (2 x 256 bytes) per instruction
+    const bool x_aligned = (reinterpret_cast<uintptr_t>(x) & 15) == 0;
+    auto stage_x = [&](int eb) {
+        if (interior && x_aligned) {
+#pragma unroll
+            for (int it = 0; it < 16; it++) {
+                const int row = 32 * w + 2 * it + (l >> 4), c2 = 2 * (l & 15);
+                cp_async16(s_x + row * kAgcB + c2, x + (long long)(seg0 + row) * L + eb + c2);
+            }
+        } else {
+            for (int i = 0; i < 32; i++) {
+                const int row = 32 * w + i;
+                const long long u = (long long)(seg0 + row) * L + eb + l;
+                s_x[row * kAgcB + l] = (seg0 + row < p.nseg && u < n) ? x[u] : cf(0.f, 0.f);
+            }
+        }
+        cp_async_commit();
+    };
     fetch(0);
     for (int s = 0; s < nsteps; s++) {
 #pragma unroll
         for (int i = 0; i < 32; i++) sm[32 * w + i][l] = nxt[i];
+        const bool emit = s >= wsteps;
+        if (emit) stage_x((s - wsteps) * kAgcB);
         __syncthreads();
         if (s + 1 < nsteps) fetch(s + 1);
         const int u0 = b0 - p.W + s * kAgcB;                    // time of this thread's sm[tid][0]
-        const bool emit = s >= wsteps;
         const bool rec = emit || s == wsteps - 1;               // the last warm-up block records its gains as well (below)
         if (live && u0 >= 0 && u0 < n) {
             if (!started) {
@@ -540,6 +581,7 @@ __global__ void __launch_bounds__(kAgcT, 4) k_agc_emit(const BackendParams p)
             if (b0 == 0) { const LaneState ls = p.lane[lane]; s_yl[tid] = cf(ls.fm_re, ls.fm_im); }
             else { const float2 xv = x[b0 - 1]; const float gb = sm[tid][kAgcB - 2]; s_yl[tid] = cf(__fmul_rn(xv.x, gb), __fmul_rn(xv.y, gb)); }
         }
+        if (emit) cp_async_wait_all();
         __syncthreads();
         if (emit) {
             const int eb = (s - wsteps) * kAgcB;                    // offset of this block inside every segment
@@ -550,8 +592,7 @@ __global__ void __launch_bounds__(kAgcT, 4) k_agc_emit(const BackendParams p)
                 if (rseg >= p.nseg || ub >= n) break;               // warp-uniform; rows are in increasing time order
                 const int u = ub + l;
                 const bool in = interior || u < n;
-                float2 xv = cf(0.f, 0.f);
-                if (in) xv = x[u];
+                const float2 xv = s_x[row * kAgcB + l];
                 const float ga = sm[row][l];
                 const float gprev = sm[row][l ? l - 1 : 0];
                 const float g0 = l ? gprev : s_g0[row];
@@ -1002,16 +1043,14 @@ inline void be_launch_prep(Launch &launch, const DcParams &d)
     else if (d.G == 64) launch(k_be_prep<2>, grid, block, 0, d);
     else                launch(k_be_prep<1>, grid, block, 0, d);
 }
-// group-boundary states (and the lane's final state); apply: also the dc-blocked samples / powers d asks for
+// dc blocker in one pass (states, dc-blocked samples, power): persistent CTAs, `max_ctas` of them
 template <class Launch>
-inline void be_launch_dc(Launch &launch, const DcParams &d, bool apply)
+inline void be_launch_dc(Launch &launch, const DcParams &d, int max_ctas)
 {
-    const dim3 grid(d.nblk, d.nlanes), block(32 * kDcWarps);
-    if (d.G == 128)     launch(k_dc_local<4>, grid, block, 0, d);
-    else if (d.G == 64) launch(k_dc_local<2>, grid, block, 0, d);
-    else                launch(k_dc_local<1>, grid, block, 0, d);
-    launch(k_dc_carry, dim3(d.nlanes), dim3(1024), 0, d);
-    if (apply) be_launch_prep(launch, d);
+    const dim3 grid((unsigned)std::max(1, std::min(max_ctas, d.nblk * d.nlanes))), block(32 * kDcWarps);
+    if (d.G == 128)     launch(k_dc_scan<4>, grid, block, 0, d);
+    else if (d.G == 64) launch(k_dc_scan<2>, grid, block, 0, d);
+    else                launch(k_dc_scan<1>, grid, block, 0, d);
 }
 
 // everything after the dc/power pass: gain loop + emission, then verification / squelch FSM / gate in one cooperative launch
@@ -1022,8 +1061,8 @@ inline void be_launch(Launch &launch, const BackendParams &b)
 {
     if (b.has_agc) {
         const dim3 grid((b.nseg + kAgcT - 1) / kAgcT, b.nlanes), block(kAgcT);      // L, W: multiples of 32
-        if (b.exact_math) { if (b.demod == 1) launch(k_agc_emit<true, true>, grid, block, 0, b); else launch(k_agc_emit<true, false>, grid, block, 0, b); }
-        else              { if (b.demod == 1) launch(k_agc_emit<false, true>, grid, block, 0, b); else launch(k_agc_emit<false, false>, grid, block, 0, b); }
+        if (b.exact_math) { if (b.demod == 1) launch(k_agc_emit<true, true>, grid, block, kAgcSmem, b); else launch(k_agc_emit<true, false>, grid, block, kAgcSmem, b); }
+        else              { if (b.demod == 1) launch(k_agc_emit<false, true>, grid, block, kAgcSmem, b); else launch(k_agc_emit<false, false>, grid, block, kAgcSmem, b); }
         launch.debug_after_verify(b);
         if (b.exact_math) launch.coop(k_be_finish<true>, dim3(kFinT), b, (int)FIN_A, (int)FIN_C);
         else              launch.coop(k_be_finish<false>, dim3(kFinT), b, (int)FIN_A, (int)FIN_C);

@@ -411,7 +411,7 @@ struct Backend {
     float agc_bw = 0.1f, agc_thr = 0.f; unsigned agc_timeout = 1000; bool squelch = true, gate = true;
     float kf = 0.3f;
     int L = 512, W = 384, G = 128; bool fixed_L = false;
-    DevBuf lane, Vloc, carry, powA, ss, se, fs, fe, exbits, gatebits, sgnr, sgni, prev_gate, prev_sign, first_bad, bad_list, bad_count, fixups;
+    DevBuf lane, dc_agg, dc_flag, dc_ticket, dc_state[2], powA, powAB, ss, se, fs, fe, exbits, gatebits, sgnr, sgni, prev_gate, prev_sign, first_bad, bad_list, bad_count, fixups;
     DevBuf ydc, pwbuf, g_first, y_first, y_end, seg_ylast, barrier;
     int pw_ready_n = -1;       // the producer of the input has already written its power for a call of this many samples
     int FW = 3; unsigned long long last_refined = 0; int last_L = 0, last_W = 0;
@@ -421,7 +421,7 @@ struct Backend {
     // the copy of call k-2 (one call always stays in flight) and lengthens / shortens the warm-up from it
     unsigned long long *h_counters = nullptr; cudaEvent_t ev_counters[2] = {nullptr, nullptr}; unsigned long long calls = 0;
     unsigned long long seen[3] = {0, 0, 0}; int W_cur = 0, calm_calls = 0; long long nseg_of[2] = {1, 1};
-    int sms = 148;
+    int sms = 148, dc_cur = 0, dc_depth = 1; unsigned dc_epoch = 0;
     ~Backend() { if (h_counters) cudaFreeHost(h_counters); for (auto e : ev_counters) if (e) cudaEventDestroy(e); }
 
     void init(const Ctx &c, int lanes, float g0 = 1000.0f, int mode0 = SQ_ENABLED)
@@ -439,7 +439,7 @@ struct Backend {
         prev_gate.ensure(sizeof(unsigned) * nlanes); CK(cudaMemsetAsync(prev_gate.p, 0, prev_gate.cap, c.stream));
         prev_sign.ensure(sizeof(unsigned) * nlanes); CK(cudaMemsetAsync(prev_sign.p, 0, prev_sign.cap, c.stream));
         first_bad.ensure(sizeof(unsigned) * 2 * nlanes); CK(cudaMemsetAsync(first_bad.p, 0xff, first_bad.cap, c.stream));
-        // A^k, A = c^G, for the dc blocker's group-boundary states
+        // A^k, A = c^G, for the dc blocker's group-boundary states; AB^k, AB = A^kDcGB, for the look-back over blocks
         {
             const double cc = -(double)(-1.0f + dc_alpha);
             double A = 1.0;
@@ -449,7 +449,26 @@ struct Backend {
             for (int k = 1; k <= kDcGB; k++) pw[k] = pw[k - 1] * A;
             powA.ensure(sizeof(double) * pw.size());
             CK(cudaMemcpyAsync(powA.p, pw.data(), sizeof(double) * pw.size(), cudaMemcpyHostToDevice, c.stream));
+            const double AB = pw[kDcGB];
+            dc_depth = 1;
+            if (AB > 0.0 && AB < 1.0) dc_depth = (int)std::min(65536.0, std::ceil(std::log(1e-13) / std::log(AB)));
+            else if (AB >= 1.0) dc_depth = 65536;
+            dc_depth = std::max(1, dc_depth);
+            std::vector<double> pb((size_t)dc_depth + 1);
+            pb[0] = 1.0;
+            for (int k = 1; k <= dc_depth; k++) pb[k] = pb[k - 1] * AB;
+            powAB.ensure(sizeof(double) * pb.size());
+            CK(cudaMemcpyAsync(powAB.p, pb.data(), sizeof(double) * pb.size(), cudaMemcpyHostToDevice, c.stream));
+            dc_ticket.ensure(2 * sizeof(unsigned)); CK(cudaMemsetAsync(dc_ticket.p, 0, dc_ticket.cap, c.stream));
+            for (auto &d : dc_state) { d.ensure(sizeof(float2) * nlanes); CK(cudaMemsetAsync(d.p, 0, d.cap, c.stream)); }
             c.sync();
+        }
+        if (has_agc) {
+            int per_sm = 0;
+            raise_dyn_smem(k_agc_emit<false, false>, kAgcSmem); raise_dyn_smem(k_agc_emit<false, true>, kAgcSmem);
+            raise_dyn_smem(k_agc_emit<true, false>, kAgcSmem); raise_dyn_smem(k_agc_emit<true, true>, kAgcSmem);
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_agc_emit<false, true>, kAgcT, kAgcSmem));
+            agc_slots = std::max(1, per_sm) * c.sms;
         }
         fixups.ensure(3 * sizeof(unsigned long long)); CK(cudaMemsetAsync(fixups.p, 0, fixups.cap, c.stream));
         bad_list.ensure(sizeof(unsigned) * 2 * 65536); bad_count.ensure(4 * sizeof(unsigned)); CK(cudaMemsetAsync(bad_count.p, 0, bad_count.cap, c.stream));
@@ -487,18 +506,41 @@ struct Backend {
             launch(k, grid, block, smem, st, std::forward<Act>(a)...);
         }
     };
-    DcParams dc_params(const float2 *in, long long in_stride, float2 *out, long long out_stride, int n)
+    int agc_slots = 0;           // CTAs of k_agc_emit that are resident at once (whole device)
+    int pick_segment(int n, int W) const
+    {
+        const long long slots = std::max(1, agc_slots);
+        long long best_cost = -1; int best = 256;
+        for (int L = 64; L <= 1024; L += 32) {
+            const long long nseg = ((long long)n + L - 1) / L;
+            const long long ctas = (long long)nlanes * ((nseg + kAgcT - 1) / kAgcT);
+            const long long cost = ((ctas + slots - 1) / slots) * (long long)(W + L);
+            if (best_cost < 0 || cost <= best_cost) { best_cost = cost; best = L; }
+        }
+        return best;
+    }
+    DcParams dc_params(const float2 *in, long long in_stride, float2 *out, long long out_stride, int n, cudaStream_t st)
     {
         DcParams d{};
         d.in = in; d.in_lane_stride = in_stride; d.out = out; d.out_lane_stride = out_stride;
         d.n = n; d.nlanes = nlanes; d.G = G; d.ngrp = (n + G - 1) / G; d.nblk = (d.ngrp + kDcGB - 1) / kDcGB;
         d.a1 = -1.0f + dc_alpha; d.c = -(double)d.a1; d.has_dc = 1;
         { double cs = 1.0; for (int i = 0; i < G / 32; i++) cs *= d.c; for (int k = 0; k < 5; k++) { d.cS[k] = cs; cs *= cs; } }
-        Vloc.ensure(sizeof(double2) * (size_t)nlanes * d.ngrp);
-        carry.ensure(sizeof(double2) * (size_t)nlanes * d.nblk);
-        d.Vloc = Vloc.as<double2>(); d.carry = carry.as<double2>(); d.powA = powA.as<double>();
-        d.lane = lane.as<LaneState>();
+        d.powA = powA.as<double>(); d.powAB = powAB.as<double>(); d.depth = dc_depth;
         return d;
+    }
+    // one pass of k_dc_scan over d (look-back buffers, ticket, the two copies of the carried filter state)
+    template <class L> void launch_dc(L &l, DcParams &d, cudaStream_t st)
+    {
+        const size_t blocks = (size_t)nlanes * d.nblk;
+        dc_agg.ensure(sizeof(double2) * blocks);
+        dc_flag.ensure_zero(sizeof(unsigned) * blocks, st);
+        d.agg = dc_agg.as<double2>(); d.flag = dc_flag.as<unsigned>(); d.ticket = dc_ticket.as<unsigned>();
+        if (++dc_epoch == 0) { CK(cudaMemsetAsync(dc_flag.p, 0, dc_flag.cap, st)); dc_epoch = 1; }
+        d.epoch = dc_epoch;
+        d.dc_in = dc_state[dc_cur].as<float2>(); d.dc_out = dc_state[dc_cur ^ 1].as<float2>();
+        dc_cur ^= 1;
+        be_launch_dc(l, d, 2 * sms);
     }
     // dc blocker only, out may alias in
     // rot: also multiply by the conjugate NCO phasor (theta0 + i * dtheta), the channelizer's pre-rotation
@@ -506,10 +548,10 @@ struct Backend {
                      bool rot = false, uint32_t rot_theta = 0, uint32_t rot_dtheta = 0, int rot_quantize = 1)
     {
         if (n <= 0) return;
-        DcParams d = dc_params(in, in_stride, out, out_stride, n);
+        DcParams d = dc_params(in, in_stride, out, out_stride, n, c.stream);
         d.rot = rot ? 1 : 0; d.rot_theta = rot_theta; d.rot_dtheta = rot_dtheta; d.rot_quantize = rot_quantize;
         Launcher l{c.stream, sms};
-        be_launch_dc(l, d, true);
+        launch_dc(l, d, c.stream);
     }
     // Where the producer of the next run()'s input (n samples per lane, no dc blocker here) may write |x|^2 itself:
     // returns the power array and its lane stride; run() then skips its own power pass.
@@ -533,16 +575,15 @@ struct Backend {
         Launcher l{st, sms};
         if (has_dc && !has_agc && demod == 0) {
             // dc blocker only (config 1): the output pass writes the caller's buffer directly
-            DcParams d = dc_params(in, in_stride, (float2 *)out, out_stride, n);
-            be_launch_dc(l, d, true);
+            DcParams d = dc_params(in, in_stride, (float2 *)out, out_stride, n, st);
+            launch_dc(l, d, st);
             return;
         }
-        // segment length: the per-segment recurrences are latency bound, so aim for >= ~64k concurrent chains
-        // (shorter segments = more chains but relatively more warm-up work); whole 32-sample words
+        // segment length: every chain of a wave is resident at once and a wave lasts one window (W + L samples), so the
+        // cost of a call is  waves x (W + L);  the multiple of 32 in [64, 1024] that minimises it is taken (ties: longer
+        // segments = less redundant warm-up work)
         int L = this->L;
-        if (has_agc && !fixed_L) {
-            while (L > 64 && L % 64 == 0 && (long long)nlanes * ((n + L - 1) / L) < 65536) L /= 2;
-        }
+        if (has_agc && !fixed_L) L = pick_segment(n, this->W_cur > 0 ? this->W_cur : this->W);
         int W = this->W;
         const int slot = (int)(calls & 1);
         if (has_agc && !fixed_L) {
@@ -574,7 +615,7 @@ struct Backend {
         b.ydc = in; b.ydc_stride = in_stride;
         {
             // dc blocker (states, then samples) and the power sequence the gain loop runs on
-            DcParams d = dc_params(in, in_stride, nullptr, 0, n);
+            DcParams d = dc_params(in, in_stride, nullptr, 0, n, st);
             d.has_dc = has_dc ? 1 : 0;
             if (has_dc) {
                 ydc.ensure(sizeof(float2) * (size_t)nlanes * pws);
@@ -591,7 +632,7 @@ struct Backend {
                 pwbuf.ensure(sizeof(float) * (size_t)nlanes * pws);
                 d.pw = pwbuf.as<float>(); d.pw_stride = pws;
             }
-            if (has_dc) be_launch_dc(l, d, true);
+            if (has_dc) launch_dc(l, d, st);
             else if (has_agc && pw_ready_n != n) be_launch_prep(l, d);
             pw_ready_n = -1;
         }

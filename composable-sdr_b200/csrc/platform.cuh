@@ -88,6 +88,20 @@ __device__ __forceinline__ void tma_load_rows(void *dst, const FeTmap *tm, int r
 }
 #endif
 
+// ---- asynchronous global -> shared copies (cp.async, SASS LDGSTS): issued early, waited for just before use --------
+#ifdef CSDR_EMU
+__device__ inline void cp_async16(void *dst, const void *src) { memcpy(dst, src, 16); }
+__device__ inline void cp_async_commit() {}
+__device__ inline void cp_async_wait_all() {}
+#else
+__device__ __forceinline__ void cp_async16(void *dst, const void *src)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+#endif
+
 // ---- named barriers (bar.sync / bar.arrive id, count): producer / consumer hand-over between two groups of warps ---
 // sync: wait until `count` threads have arrived (this one included); arrive: count this thread and go on.
 #ifdef CSDR_EMU

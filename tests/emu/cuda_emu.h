@@ -122,6 +122,7 @@ template <class T> static inline T __shfl_up_sync(unsigned, T v, unsigned d)
     const int src = (int)::csdr_emu::t_lane - (int)d;
     return ::csdr_emu::warp_exchange(v, src < 0 ? (int)::csdr_emu::t_lane : src);      // lanes below d keep their own value
 }
+template <class T> static inline T __shfl_xor_sync(unsigned, T v, int m) { return ::csdr_emu::warp_exchange(v, (int)(::csdr_emu::t_lane ^ (unsigned)m)); }
 static inline unsigned __ballot_sync(unsigned, int pred)
 {
     using namespace ::csdr_emu;

@@ -151,14 +151,19 @@ long long emu_backend(int nlanes, long long lane_stride, int has_dc, float dc_al
     std::vector<LaneState> lane(nlanes);
     for (auto &l : lane) { l.dc_re = l.dc_im = 0; l.g = 1000.0f; l.y2p = 1.0f; l.mode = SQ_ENABLED; l.timer = 0; l.fm_re = l.fm_im = 0; }
     unsigned long long fixups2[3] = {0, 0, 0};
+    std::vector<float2> dcst[2];
+    dcst[0].assign(nlanes, make_float2(0, 0)); dcst[1] = dcst[0];
+    int dc_cur = 0; unsigned epoch = 0;
     long long pos = 0;
     for (int c = 0; c < nchunks; c++) {
         int nx = (int)chunks[c];
         if (nx == 0) continue;
         int ngrp = (nx + G - 1) / G, nseg = (nx + L - 1) / L, nblk = (ngrp + kDcGB - 1) / kDcGB;
         const long long pws = (nx + 3) / 4 * 4;
-        std::vector<double2> Vloc((size_t)nlanes * ngrp), carry((size_t)nlanes * nblk);
-        std::vector<double> powA(kDcGB + 1);
+        std::vector<double2> agg((size_t)nlanes * nblk);
+        std::vector<unsigned> flag((size_t)nlanes * nblk, 0u);
+        unsigned ticket[2] = {0, 0};
+        std::vector<double> powA(kDcGB + 1), powAB;
         std::vector<SegState> ss((size_t)nlanes * nseg), se((size_t)nlanes * nseg);
         std::vector<FsmState> fs((size_t)nlanes * nseg), fe((size_t)nlanes * nseg);
         std::vector<float2> ydc((size_t)nlanes * pws), yfirst(nlanes);
@@ -173,12 +178,20 @@ long long emu_backend(int nlanes, long long lane_stride, int has_dc, float dc_al
         d.in = x + pos; d.in_lane_stride = lane_stride; d.n = nx; d.nlanes = nlanes; d.G = G; d.ngrp = ngrp; d.nblk = nblk;
         d.has_dc = has_dc; d.out = has_dc ? ydc.data() : nullptr; d.out_lane_stride = pws;
         d.pw = has_agc ? pw.data() : nullptr; d.pw_stride = pws;
-        d.a1 = -1.0f + dc_alpha; d.c = -(double)d.a1; d.Vloc = Vloc.data(); d.carry = carry.data(); d.lane = lane.data();
+        d.a1 = -1.0f + dc_alpha; d.c = -(double)d.a1; d.agg = agg.data(); d.flag = flag.data(); d.ticket = ticket; d.epoch = ++epoch;
+        d.dc_in = dcst[dc_cur].data(); d.dc_out = dcst[dc_cur ^ 1].data();
         { double A = 1.0; for (int i = 0; i < G; i++) A *= d.c; powA[0] = 1.0; for (int k = 1; k <= kDcGB; k++) powA[k] = powA[k - 1] * A; }
+        {
+            const double AB = powA[kDcGB];
+            d.depth = std::max(1, (int)std::ceil(std::log(1e-13) / std::log(AB)));
+            powAB.assign((size_t)d.depth + 1, 1.0);
+            for (int k = 1; k <= d.depth; k++) powAB[k] = powAB[k - 1] * AB;
+            d.powAB = powAB.data();
+        }
         { double cs = 1.0; for (int i = 0; i < G / 32; i++) cs *= d.c; for (int k = 0; k < 5; k++) { d.cS[k] = cs; cs *= cs; } }
         d.powA = powA.data();
         EmuLaunch launch;
-        if (has_dc) be_launch_dc(launch, d, true);
+        if (has_dc) { be_launch_dc(launch, d, 3); dc_cur ^= 1; }
         else if (has_agc) be_launch_prep(launch, d);
         BackendParams b{};
         b.in = x + pos; b.in_lane_stride = lane_stride;
