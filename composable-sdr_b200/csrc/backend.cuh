@@ -41,6 +41,8 @@ struct FsmState;
 struct BackendParams {
     const float2 *in; long long in_lane_stride;
     void *out; long long out_lane_stride;      // float (demod != 0) or float2 elements
+    void *const *out_table;                    // optional [nlanes]: lane i writes to out_table[i] instead of out + i * stride
+                                               // (the caller's own per-channel buffers: no copy behind the back end)
     int n, nlanes;
     int L, W, G, nseg, ngrp;
     int has_dc, has_agc, demod;                // demod: 0 none (cf32 out), 1 fm (float out)
@@ -75,7 +77,7 @@ struct BackendParams {
 // ------------------------------------------------------------------------------------------ dc blocker
 // v[n] = x[n] + c v[n-1] (c = 1 - alpha), y[n] = v[n] - v[n-1]: a linear recurrence, evaluated in fp64 as affine maps
 // (k_dc_scan below); the float32 recurrence of iirfilt then runs over G/32 samples per lane from the exact state.
-constexpr int kDcGB = 64;
+constexpr int kDcGB = 32;
 constexpr int kDcWarps = 8;
 
 struct DcParams {
@@ -89,9 +91,8 @@ struct DcParams {
     float a1;
     const double *powA;                        // [kDcGB + 1]     A^k, A = c^G
     // k_dc_scan: blocks of kDcGB groups publish their zero-state response and look back over their predecessors
-    double2 *agg;                              // [nlanes][nblk]  zero-state response of block b (fp64)
-    unsigned *flag;                            // [nlanes][nblk]  == epoch once agg is valid
-    unsigned epoch;                            // this call's number (flags of earlier calls are stale)
+    SelfValid16 *agg;                          // [nlanes][nblk]  zero-state response of block b (fp64 pair); all-ones until
+                                               // it is published (reset by a memset before every launch)
     unsigned *ticket;                          // [2] next block to hand out, CTAs that have left (reset by the last one)
     const double *powAB; int depth;            // [depth + 1] (c^(G kDcGB))^k; blocks further back than `depth` have decayed
                                                // below 1e-13 of the state
@@ -114,28 +115,37 @@ __device__ __forceinline__ void dc_load(const float2 *__restrict__ x, int n, int
     }
 }
 
-// inclusive warp scan of the affine maps  s -> m s + a  (composition left to right): afterwards lane l holds the map
-// of lanes 0..l, i.e. (m^(l+1), zero-state response at the end of lane l's samples)
-__device__ __forceinline__ void dc_warp_scan(double &ar, double &ai, double &m, const double (&cS)[5])
+// Inclusive warp scan of the zero-state responses: every lane covers S samples, i.e. its map is  s -> q s + a  with the
+// same q = c^S for all lanes, so after the step with distance d a lane that has a partner (l >= d) covers exactly d
+// lanes of its own and the partner's value enters with q^d = cS[log2 d].  Afterwards lane l holds the zero-state
+// response at the end of lane l's samples.  float32 is enough INSIDE a group: an error e of the state a lane starts
+// from reaches its outputs as alpha e c^n (y = x - alpha v1), 1e-6 of the state's rounding is 1e-9 of the signal; what
+// accumulates over long distances -- the group and block totals -- is kept in fp64.
+__device__ __forceinline__ void dc_warp_scan(float &ar, float &ai, const float (&qS)[5])
 {
     const int l = threadIdx.x & 31;
 #pragma unroll
     for (int s = 0; s < 5; s++) {
         const int d = 1 << s;
-        const double pr = __shfl_up_sync(0xffffffffu, ar, d), pi = __shfl_up_sync(0xffffffffu, ai, d);
-        if (l >= d) { ar += pr * m; ai += pi * m; }        // own map applied after the predecessor block's
-        // every lane's multiplier is cS[0]^(number of lanes it covers): doubles until it reaches lane 0
-        const double pm = __shfl_up_sync(0xffffffffu, m, d);
-        if (l >= d) m *= pm;
+        const float pr = __shfl_up_sync(0xffffffffu, ar, d), pi = __shfl_up_sync(0xffffffffu, ai, d);
+        if (l >= d) { ar = fmaf(pr, qS[s], ar); ai = fmaf(pi, qS[s], ai); }
     }
-    (void)cS;
+}
+// q^e for 0 <= e < 32
+__device__ __forceinline__ double dc_pow32(const double (&cS)[5], int e)
+{
+    double r = 1.0;
+#pragma unroll
+    for (int s = 0; s < 5; s++) if ((e >> s) & 1) r *= cS[s];
+    return r;
 }
 
-// One pass over the samples: a CTA takes blocks of kDcGB groups (8192 samples at G = 128) in stream order (ticket),
-//   1. loads the block into registers (a warp per run of 8 groups, 4 samples per lane and group) and reduces it to its
-//      zero-state response (fp64 warp scans, then a scan over the 64 groups in shared memory), publishes that,
+// One pass over the samples: a CTA takes blocks of kDcGB groups (4096 samples at G = 128) in stream order (ticket),
+//   1. loads the block into registers (a warp per run of 4 groups, 4 samples per lane and group; one block ahead of the
+//      arithmetic) and reduces it to its zero-state response (fp64 warp reductions, then a scan over the 32 groups in
+//      shared memory), publishes that,
 //   2. looks back: the filter state before the block is  sum_k AB^(k-1) agg[b-k]  (+ AB^b x the state carried from the
-//      previous call), AB = c^8192 = 0.017 for alpha = 5e-4, so `depth` = 7 predecessors settle it to 1e-13,
+//      previous call), AB = c^4096 = 0.13 for alpha = 5e-4, so `depth` = 15 predecessors settle it to 1e-13,
 //   3. gives every lane the exact state before its samples, runs iirfilt's float32 recurrence over them and writes the
 //      dc-blocked samples (optionally pre-rotated for the channelizer) and their power.
 // Each sample is read once and written once; nothing else travels through HBM.  out may alias in.
@@ -143,64 +153,83 @@ template <int S>
 __global__ void __launch_bounds__(32 * kDcWarps, 2) k_dc_scan(const DcParams p)
 {
     constexpr int GW = kDcGB / kDcWarps;               // groups per warp
-    __shared__ double sr[kDcGB], si[kDcGB];            // zero-state response at the END of each group, block-local
+    __shared__ double sr[2][kDcGB], si[2][kDcGB];      // zero-state response at the END of each group, block-local (two blocks in flight)
     __shared__ double s_red[2][kDcWarps];
     __shared__ double s_cr, s_ci;
     __shared__ int s_ticket;
     const int t = threadIdx.x, w = t >> 5, l = t & 31;
     const double A = p.powA[1];
+    const double ql = dc_pow32(p.cS, l);                                      // q^l, q = c^S
+    const float wl = (float)dc_pow32(p.cS, 31 - l), cf32 = (float)p.c;        // q^(31 - l)
+    const float qS[5] = {(float)p.cS[0], (float)p.cS[1], (float)p.cS[2], (float)p.cS[3], (float)p.cS[4]};
     const int total = p.nlanes * p.nblk;
-    while (true) {
-        if (t == 0) s_ticket = (int)atomicAdd(p.ticket, 1u);
-        __syncthreads();
-        const int tk = s_ticket;
-        if (tk >= total) break;
-        const int lane = tk / p.nblk, b = tk - lane * p.nblk;
-        const float2 *__restrict__ x = p.in + (long long)lane * p.in_lane_stride;
-        float2 v[GW][S];
-        // ---- 1. load + reduce
+    // Software pipeline over the blocks of this CTA (tickets are taken one block ahead): while block i is looked back
+    // for and applied, the samples of block i + 1 are on their way into registers, and block i + 1 is reduced and
+    // PUBLISHED before block i + 1's own look-back starts an iteration later -- by then its predecessors (earlier tickets,
+    // published by their owners at the same point of their loops) are there and nobody waits.
+    float2 v[GW][S], vn[GW][S];
+    auto load_block = [&](int tkk, float2 (&dst)[GW][S]) {
+        const int ln = tkk / p.nblk, bb = tkk - ln * p.nblk;
+        const float2 *__restrict__ xx = p.in + (long long)ln * p.in_lane_stride;
+#pragma unroll
+        for (int k = 0; k < GW; k++) {
+            const int j = bb * kDcGB + w * GW + k;
+            dc_load<S>(xx, (j < p.ngrp) ? p.n : 0, j * p.G + l * S, dst[k]);
+        }
+    };
+    // zero-state responses of the groups of block tkk (samples in `src`) into sr/si[buf]; the block's total is published
+    auto reduce_publish = [&](const float2 (&src)[GW][S], int tkk, int buf) {
         double Rr = 0.0, Ri = 0.0;                          // zero-state response of this warp's run of groups
 #pragma unroll
         for (int k = 0; k < GW; k++) {
-            const int j = b * kDcGB + w * GW + k;
-            dc_load<S>(x, (j < p.ngrp) ? p.n : 0, j * p.G + l * S, v[k]);
-            double ar = 0.0, ai = 0.0;
+            // zero-state response of the group = sum over the lanes of (lane's response) x q^(31 - l): a plain reduction
+            float ar = 0.f, ai = 0.f;
 #pragma unroll
-            for (int q = 0; q < S; q++) { ar = ar * p.c + (double)v[k][q].x; ai = ai * p.c + (double)v[k][q].y; }
-            double m = p.cS[0];
-            dc_warp_scan(ar, ai, m, p.cS);
-            const double Tr = __shfl_sync(0xffffffffu, ar, 31), Ti = __shfl_sync(0xffffffffu, ai, 31);
-            Rr = Rr * A + Tr; Ri = Ri * A + Ti;
-            if (l == 0) { sr[w * GW + k] = Rr; si[w * GW + k] = Ri; }
+            for (int q = 0; q < S; q++) { ar = fmaf(ar, cf32, src[k][q].x); ai = fmaf(ai, cf32, src[k][q].y); }
+            ar *= wl; ai *= wl;
+#pragma unroll
+            for (int d = 16; d >= 1; d >>= 1) { ar += __shfl_xor_sync(0xffffffffu, ar, d); ai += __shfl_xor_sync(0xffffffffu, ai, d); }
+            Rr = Rr * A + (double)ar; Ri = Ri * A + (double)ai;
+            if (l == 0) { sr[buf][w * GW + k] = Rr; si[buf][w * GW + k] = Ri; }
         }
         __syncthreads();
         double vr = 0.0, vi = 0.0;
         if (t < kDcGB) {
-            const int tw = t / GW, tkk = t - tw * GW;
+            const int tw = t / GW, tkk2 = t - tw * GW;
             // state at the start of warp tw's run inside this block
             double pr = 0.0, pi = 0.0;
             for (int q = 0; q < tw; q++) {
                 const double a = p.powA[GW * (tw - 1 - q)];
-                pr += sr[q * GW + GW - 1] * a; pi += si[q * GW + GW - 1] * a;
+                pr += sr[buf][q * GW + GW - 1] * a; pi += si[buf][q * GW + GW - 1] * a;
             }
-            const double a = p.powA[tkk + 1];
-            vr = sr[t] + pr * a; vi = si[t] + pi * a;
+            const double a = p.powA[tkk2 + 1];
+            vr = sr[buf][t] + pr * a; vi = si[buf][t] + pi * a;
         }
         __syncthreads();
-        if (t < kDcGB) { sr[t] = vr; si[t] = vi; }
-        if (t == kDcGB - 1) {
-            p.agg[tk] = make_double2(vr, vi);
-            __threadfence();
-            *((volatile unsigned *)(p.flag + tk)) = p.epoch;
-        }
-        // ---- 2. look back (thread k waits for block b - 1 - k, b - 1 - k - 256, ...)
+        if (t < kDcGB) { sr[buf][t] = vr; si[buf][t] = vi; }
+        if (t == kDcGB - 1) sv16_store(p.agg + tkk, vr, vi);
+    };
+    if (t == 0) s_ticket = (int)atomicAdd(p.ticket, 1u);
+    __syncthreads();
+    int tk = s_ticket, cur = 0;
+    if (tk < total) { load_block(tk, vn); reduce_publish(vn, tk, 0); }
+    __syncthreads();
+    while (tk < total) {
+        if (t == 0) s_ticket = (int)atomicAdd(p.ticket, 1u);
+        const int lane = tk / p.nblk, b = tk - lane * p.nblk;
+#pragma unroll
+        for (int k = 0; k < GW; k++)
+#pragma unroll
+            for (int q = 0; q < S; q++) v[k][q] = vn[k][q];
+        __syncthreads();
+        const int tk_next = s_ticket;
+        if (tk_next < total) load_block(tk_next, vn);
+        // ---- look back (thread k waits for block b - 1 - k, b - 1 - k - 256, ...)
         double cr = 0.0, ci = 0.0;
         for (int k = t; k < p.depth && k < b; k += blockDim.x) {
             const int src = tk - 1 - k;
-            while (*((volatile unsigned *)(p.flag + src)) != p.epoch) {}
-            __threadfence();
-            const volatile double *ap = reinterpret_cast<const volatile double *>(p.agg + src);
-            const double ax = ap[0], ay = ap[1];
+            double ax, ay;
+            while (!sv16_load(p.agg + src, ax, ay)) {}
             const double m = p.powAB[k];
             cr += ax * m; ci += ay * m;
         }
@@ -216,7 +245,7 @@ __global__ void __launch_bounds__(32 * kDcWarps, 2) k_dc_scan(const DcParams p)
         }
         __syncthreads();
         const double carry_r = s_cr, carry_i = s_ci;
-        // ---- 3. apply
+        // ---- apply
         float2 *__restrict__ yo = p.out ? p.out + (long long)lane * p.out_lane_stride : nullptr;
         float *__restrict__ wo = p.pw ? p.pw + (long long)lane * p.pw_stride : nullptr;
 #pragma unroll
@@ -224,17 +253,16 @@ __global__ void __launch_bounds__(32 * kDcWarps, 2) k_dc_scan(const DcParams p)
             const int jl = w * GW + k, j = b * kDcGB + jl;
             if (j >= p.ngrp) break;                                           // warp-uniform
             const int i0 = j * p.G + l * S;
-            double ar = 0.0, ai = 0.0;
+            float ar = 0.f, ai = 0.f;
 #pragma unroll
-            for (int q = 0; q < S; q++) { ar = ar * p.c + (double)v[k][q].x; ai = ai * p.c + (double)v[k][q].y; }
-            double m = p.cS[0];
-            dc_warp_scan(ar, ai, m, p.cS);
-            // state before group j, then before this lane's samples
+            for (int q = 0; q < S; q++) { ar = fmaf(ar, cf32, v[k][q].x); ai = fmaf(ai, cf32, v[k][q].y); }
+            dc_warp_scan(ar, ai, qS);
+            // state before group j (fp64), then before this lane's samples
             const double pa = p.powA[jl];
-            const double Vr = (jl ? sr[jl - 1] : 0.0) + carry_r * pa, Vi = (jl ? si[jl - 1] : 0.0) + carry_i * pa;
-            double er = __shfl_up_sync(0xffffffffu, ar, 1), ei = __shfl_up_sync(0xffffffffu, ai, 1), em = __shfl_up_sync(0xffffffffu, m, 1);
-            if (l == 0) { er = 0.0; ei = 0.0; em = 1.0; }
-            float v1r = (float)(er + Vr * em), v1i = (float)(ei + Vi * em);
+            const double Vr = (jl ? sr[cur][jl - 1] : 0.0) + carry_r * pa, Vi = (jl ? si[cur][jl - 1] : 0.0) + carry_i * pa;
+            float er = __shfl_up_sync(0xffffffffu, ar, 1), ei = __shfl_up_sync(0xffffffffu, ai, 1);
+            if (l == 0) { er = 0.f; ei = 0.f; }
+            float v1r = (float)((double)er + Vr * ql), v1i = (float)((double)ei + Vi * ql);
 #pragma unroll
             for (int q = 0; q < S; q++) {
                 if (i0 + q < p.n) {
@@ -276,7 +304,10 @@ __global__ void __launch_bounds__(32 * kDcWarps, 2) k_dc_scan(const DcParams p)
                 }
             }
         }
-        __syncthreads();      // sr / si / s_ticket are reused by the next block
+        // ---- the next block: reduce and publish (its samples had the look-back and the apply pass to arrive)
+        if (tk_next < total) reduce_publish(vn, tk_next, cur ^ 1);
+        __syncthreads();      // sr / si / s_ticket are reused
+        tk = tk_next; cur ^= 1;
     }
     // tickets for the next launch: reset by the last CTA to leave
     if (t == 0) {
@@ -331,12 +362,15 @@ __device__ __forceinline__ void fsm_step(int &mode, unsigned &timer, bool ex, un
 
 // arg(x + jy) with a degree-8 minimax polynomial for atan on [0, 1] (max error 1.1e-7 rad, float32-limited; the
 // library atan2f is ~3x the instructions).  Exact zeros keep the library's signed-zero semantics.
+// Branch-free: |a| = min / max is 0 for two zeros (the quotient is replaced, not computed), the quadrant comes from the SIGN
+// BITS, so the signed-zero cases come out as the library's (atan2(+-0, -0) = +-pi, atan2(+-0, +0) = +-0); an infinite
+// operand gives min / max = 0 or NaN exactly where atan2f gives a multiple of pi/2 or pi/4 -- only the latter (both
+// infinite) differs (NaN instead of +-pi/4, +-3pi/4), as does a NaN operand's payload.
 __device__ __forceinline__ float be_atan2(float y, float x)
 {
     const float ax = fabsf(x), ay = fabsf(y);
     const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
-    if (mx == 0.f || !(mx < 1e37f)) return atan2f(y, x);
-    const float a = __fdividef(mn, mx);
+    const float a = (mx == 0.f) ? 0.f : __fdividef(mn, mx);
     const float s = a * a;
     float r = 0.0028340641874819994f;
     r = fmaf(r, s, -0.016005029901862144f);
@@ -349,7 +383,7 @@ __device__ __forceinline__ float be_atan2(float y, float x)
     r = fmaf(r, s, 1.0f);
     r *= a;
     if (ay > ax) r = 1.57079637f - r;
-    if (x < 0.f) r = 3.14159274f - r;
+    if (__float_as_int(x) < 0) r = 3.14159274f - r;
     return copysignf(r, y);
 }
 
@@ -425,41 +459,69 @@ __device__ __forceinline__ void agc_guess(float e, float &g, float &y2p)
     y2p = 1.0f;
 }
 
+__device__ __forceinline__ float *be_out_f(const BackendParams &p, int lane)
+{
+    return p.out_table ? (float *)p.out_table[lane] : (float *)p.out + (long long)lane * p.out_lane_stride;
+}
+__device__ __forceinline__ float2 *be_out_c(const BackendParams &p, int lane)
+{
+    return p.out_table ? (float2 *)p.out_table[lane] : (float2 *)p.out + (long long)lane * p.out_lane_stride;
+}
+
+// what the emission of a lane needs, fetched once per kernel
+struct BeEmitCtx {
+    float *of; float2 *oc;                     // output of this lane (discriminator / cf32)
+    unsigned *exb, *sgr, *sgi;                 // bit planes of this lane
+    float g_thr, fm_ref;
+    int n;
+    bool skip_closed;                          // words without a threshold-exceeding sample are left to the gate pass
+};
+__device__ __forceinline__ BeEmitCtx be_emit_ctx(const BackendParams &p, int lane)
+{
+    BeEmitCtx c;
+    c.of = be_out_f(p, lane); c.oc = be_out_c(p, lane);
+    c.exb = p.exbits + (long long)lane * p.nwords; c.sgr = p.sgnr + (long long)lane * p.nwords; c.sgi = p.sgni + (long long)lane * p.nwords;
+    c.g_thr = p.g_thr; c.fm_ref = p.fm_ref; c.n = p.n;
+    c.skip_closed = p.gate != 0;
+    return c;
+}
+
 // ------------------------------------------------------------------------------------------ emission of one word
 // 32 consecutive samples of a lane, one per thread of a warp: ungated output y = y_dc * (gain before the sample),
 // threshold bit = (gain after the sample) < g_thr, sign bits, discriminator m = arg(conj(y[n-1]) y[n]) / (2 pi kf)
 // (freqdem_demodulate) or the cf32 sample itself.  `yprev0`: ungated output of the sample before the word (lane 0).
-// Returns this lane's y (the caller carries the last one to the next word).
-template <bool AGC, bool FM, bool EXACT>
-__device__ __forceinline__ float2 be_emit_word(const BackendParams &p, int lane_id, int u0, bool in, float2 xv, float g0, float ga,
-                                               float2 yprev0)
+// FULL: all 32 samples exist (no bounds checks).  Returns this lane's y (the caller carries the last one on).
+template <bool AGC, bool FM, bool EXACT, bool FULL>
+__device__ __forceinline__ float2 be_emit_word(const BeEmitCtx &c, int u0, float2 xv, float g0, float ga, float2 yprev0)
 {
     const int l = threadIdx.x & 31;
+    const bool in = FULL || (u0 + l < c.n);
     float2 y = xv;
     if (AGC) y = cf(__fmul_rn(xv.x, g0), __fmul_rn(xv.y, g0));
     float2 yp;
     yp.x = __shfl_up_sync(0xffffffffu, y.x, 1); yp.y = __shfl_up_sync(0xffffffffu, y.y, 1);
     if (l == 0) yp = yprev0;
     if (AGC) {
-        const long long wd = (long long)lane_id * p.nwords + (u0 >> 5);
-        const unsigned ex = __ballot_sync(0xffffffffu, in && ga < p.g_thr);       // rssi = -20 log10(g) > threshold
-        if (l == 0) p.exbits[wd] = ex;
+        const int wd = u0 >> 5;
+        const unsigned ex = __ballot_sync(0xffffffffu, in && ga < c.g_thr);       // rssi = -20 log10(g) > threshold
         if (FM) {
             const unsigned sr = __ballot_sync(0xffffffffu, in && (__float_as_int(y.x) < 0));
             const unsigned si = __ballot_sync(0xffffffffu, in && (__float_as_int(y.y) < 0));
-            if (l == 0) { p.sgnr[wd] = sr; p.sgni[wd] = si; }
-        }
+            if (l < 3) { unsigned *dst = l == 0 ? c.exb : l == 1 ? c.sgr : c.sgi; dst[wd] = l == 0 ? ex : l == 1 ? sr : si; }
+        } else if (l == 0) c.exb[wd] = ex;
+        // The squelch can only be open on a sample that exceeds the threshold (every path into SIGNALHI takes the
+        // "exceeded" branch of the state machine), so a word without such a sample is closed throughout: the gate pass
+        // writes its zeros (and the signed-zero artefacts next to an open sample) and nothing needs computing here.
+        if (c.skip_closed && ex == 0) return y;
     }
     if (in) {
-        const int u = u0 + l;
         if (FM) {
             const float re = __fadd_rn(__fmul_rn(yp.x, y.x), __fmul_rn(yp.y, y.y));
             const float im = __fsub_rn(__fmul_rn(yp.x, y.y), __fmul_rn(yp.y, y.x));
-            ((float *)p.out + (long long)lane_id * p.out_lane_stride)[u] = (EXACT ? atan2f(im, re) : be_atan2(im, re)) * p.fm_ref;
+            c.of[u0 + l] = (EXACT ? atan2f(im, re) : be_atan2(im, re)) * c.fm_ref;
         } else {
-            ((float2 *)p.out + (long long)lane_id * p.out_lane_stride)[u] = y;
+            c.oc[u0 + l] = y;
         }
-        if (u == p.n - 1) p.y_end[lane_id] = y;             // freqdem's r_prime for the next call (lane state, set by k_be_finish)
     }
     return y;
 }
@@ -476,23 +538,81 @@ __device__ __forceinline__ float2 be_emit_word(const BackendParams &p, int lane_
 // The first sample of a segment takes its gain and its predecessor's output from the segment's OWN warm-up (verified to
 // 1e-5 against the predecessor's end state by k_be_finish; typically equal to ~1e-7).
 constexpr int kAgcT = 128, kAgcB = 32;
-constexpr size_t kAgcSmem = sizeof(float) * kAgcT * (kAgcB + 1) + sizeof(float) * kAgcT + sizeof(float2) * kAgcT + sizeof(float2) * kAgcT * kAgcB;
+constexpr int kAgcRow = kAgcB + 1;      // a row of the power / output tile: [0] threshold word of the block, [1 + k] power -> output of sample k
+constexpr int kAgcXRow = kAgcB + 2;     // a row of the sample tile (float2): 272 bytes, 16-byte aligned, at most 2-way bank conflicts
+constexpr size_t kAgcSmem = sizeof(float) * kAgcT * kAgcRow + sizeof(float2) * kAgcT * kAgcXRow;
+
+// per-thread state of the emission: previous ungated output and the bit words of the current block
+struct AgcEmitState { float2 yp; unsigned ex, sr, si; };
+
+// samples [K0, K0 + NK) of the current block of this thread's row: gain loop and demodulation in one register-resident
+// loop (the demodulation's independent instructions fill the latency of the gain recurrence)
+template <bool EXACT, bool FM, int K0, int NK>
+__device__ __forceinline__ void agc_emit_run(const AgcCoef &co, float g_thr, float fm_ref, float *myrow, float2 *myx, float &g, float &g2,
+                                             float &y2p, AgcEmitState &e)
+{
+#pragma unroll
+    for (int k = K0; k < K0 + NK; k++) {
+        const float2 xv = myx[k];
+        const float2 y = cf(__fmul_rn(xv.x, g), __fmul_rn(xv.y, g));          // gain BEFORE the sample
+        agc_step<EXACT>(co, g, g2, y2p, myrow[1 + k]);                          // g: gain after the sample
+        e.ex |= (g < g_thr ? 1u : 0u) << k;                                     // rssi = -20 log10(g) > threshold
+        if (FM) {
+            const float re = __fadd_rn(__fmul_rn(e.yp.x, y.x), __fmul_rn(e.yp.y, y.y));
+            const float im = __fsub_rn(__fmul_rn(e.yp.x, y.y), __fmul_rn(e.yp.y, y.x));
+            myrow[1 + k] = (EXACT ? atan2f(im, re) : be_atan2(im, re)) * fm_ref;
+            e.sr |= ((unsigned)__float_as_int(y.x) >> 31) << k;
+            e.si |= ((unsigned)__float_as_int(y.y) >> 31) << k;
+        } else {
+            myx[k] = y;
+        }
+        e.yp = y;
+    }
+}
+// the same for a ragged block (chunk end): cnt < 32 samples
+template <bool EXACT, bool FM>
+__device__ __forceinline__ void agc_emit_ragged(const AgcCoef &co, float g_thr, float fm_ref, float *myrow, float2 *myx, float &g, float &g2,
+                                             float &y2p, AgcEmitState &e, int cnt)
+{
+    for (int k = 0; k < cnt; k++) {
+        const float2 xv = myx[k];
+        const float2 y = cf(__fmul_rn(xv.x, g), __fmul_rn(xv.y, g));
+        agc_step<EXACT>(co, g, g2, y2p, myrow[1 + k]);
+        e.ex |= (g < g_thr ? 1u : 0u) << k;
+        if (FM) {
+            const float re = __fadd_rn(__fmul_rn(e.yp.x, y.x), __fmul_rn(e.yp.y, y.y));
+            const float im = __fsub_rn(__fmul_rn(e.yp.x, y.y), __fmul_rn(e.yp.y, y.x));
+            myrow[1 + k] = (EXACT ? atan2f(im, re) : be_atan2(im, re)) * fm_ref;
+            e.sr |= ((unsigned)__float_as_int(y.x) >> 31) << k;
+            e.si |= ((unsigned)__float_as_int(y.y) >> 31) << k;
+        } else {
+            myx[k] = y;
+        }
+        e.yp = y;
+    }
+}
+
 template <bool EXACT, bool FM>
 __global__ void __launch_bounds__(kAgcT, 4) k_agc_emit(const BackendParams p)
 {
     CSDR_DYN_SMEM(smem_raw);
-    float (*sm)[kAgcB + 1] = reinterpret_cast<float (*)[kAgcB + 1]>(smem_raw);            // powers -> gains, one row per segment
-    float *s_g0 = reinterpret_cast<float *>(smem_raw) + kAgcT * (kAgcB + 1);                // gain before the first sample of the row's current block
-    float2 *s_yl = reinterpret_cast<float2 *>(s_g0 + kAgcT);                                 // ungated output of the sample before the row's current block
-    float2 *s_x = s_yl + kAgcT;                                                              // [kAgcT][kAgcB] dc-blocked samples of the current block
+    float *sm = reinterpret_cast<float *>(smem_raw);                                         // [kAgcT][kAgcRow]
+    float2 *s_x = reinterpret_cast<float2 *>(sm + kAgcT * kAgcRow);                          // [kAgcT][kAgcXRow] dc-blocked samples of the current block
     const int lane = blockIdx.y, tid = threadIdx.x, w = tid >> 5, l = tid & 31;
     const int seg0 = blockIdx.x * kAgcT, seg = seg0 + tid;
     const float *__restrict__ pw = p.pw + (long long)lane * p.pw_stride;
     const float2 *__restrict__ x = p.ydc + (long long)lane * p.ydc_stride;
+    float *const of = be_out_f(p, lane);
+    float2 *const oc = be_out_c(p, lane);
+    unsigned *const exb = p.exbits + (long long)lane * p.nwords, *const sgr = p.sgnr + (long long)lane * p.nwords,
+             *const sgi = p.sgni + (long long)lane * p.nwords;
+    const float g_thr = p.g_thr, fm_ref = p.fm_ref;
+    const bool skip_closed = p.gate != 0;
     const int b0 = seg * p.L;
     const bool live = seg < p.nseg;
     const int nsteps = (p.W + p.L) / kAgcB, wsteps = p.W / kAgcB;
-    float g = 1.f, g2 = 1.f, y2p = 1.f;
+    float g = 1.f, g2 = 1.f, y2p = 1.f, g30 = 1.f;
+    AgcEmitState es; es.yp = cf(0.f, 0.f); es.ex = es.sr = es.si = 0u;
     bool started = false;
     // rows of this warp: thread r = 32 w + i, block start u_r = (seg0 + r) L - W + 32 s.  The 32 loads of the NEXT step
     // are issued before the recurrence of the current one runs, so their latency is never waited for.
@@ -502,6 +622,7 @@ __global__ void __launch_bounds__(kAgcT, 4) k_agc_emit(const BackendParams p)
     const int ubase = (seg0 + 32 * w) * L - p.W + l;           // int: n < 2^31
     // a CTA whose windows lie inside the chunk (all but the first and the last few) skips the bounds checks
     const bool interior = (seg0 * L - p.W >= 0) && ((seg0 + kAgcT) * L <= n);
+    const bool full_rows = (seg0 + kAgcT) * L <= n;            // every row of every emitted block is complete
     auto fetch = [&](int s) {
         const float *q = pw + ubase + s * kAgcB;
         if (interior) {
@@ -515,98 +636,136 @@ __global__ void __launch_bounds__(kAgcT, 4) k_agc_emit(const BackendParams p)
             }
         }
     };
-    // the samples the emission of a step needs (rows of this warp) are copied into shared memory asynchronously at the
-    // START of the step and arrive while the recurrence runs: two rows (2 x 256 bytes) per instruction
-    const bool x_aligned = (reinterpret_cast<uintptr_t>(x) & 15) == 0;
-    auto stage_x = [&](int eb) {
-        if (interior && x_aligned) {
+    // The samples a block's emission needs (rows of this warp) are copied into shared memory asynchronously, half a block
+    // at a time and one block ahead: the first half of block s + 1 when the loop of step s is half way (its slots are free
+    // then), the second half when it ends; four rows (4 x 128 bytes) per instruction.
+    const bool x_async = full_rows && (reinterpret_cast<uintptr_t>(x) & 15) == 0;
+    auto stage_x = [&](int eb, int half) {
+        if (x_async) {
 #pragma unroll
-            for (int it = 0; it < 16; it++) {
-                const int row = 32 * w + 2 * it + (l >> 4), c2 = 2 * (l & 15);
-                cp_async16(s_x + row * kAgcB + c2, x + (long long)(seg0 + row) * L + eb + c2);
+            for (int it = 0; it < 8; it++) {
+                const int row = 32 * w + 4 * it + (l >> 3), c2 = 16 * half + 2 * (l & 7);
+                cp_async16(s_x + row * kAgcXRow + c2, x + (long long)(seg0 + row) * L + eb + c2);
             }
         } else {
-            for (int i = 0; i < 32; i++) {
-                const int row = 32 * w + i;
-                const long long u = (long long)(seg0 + row) * L + eb + l;
-                s_x[row * kAgcB + l] = (seg0 + row < p.nseg && u < n) ? x[u] : cf(0.f, 0.f);
+            for (int i = 0; i < 16; i++) {
+                const int row = 32 * w + 2 * i + (l >> 4), c = 16 * half + (l & 15);
+                const long long u = (long long)(seg0 + row) * L + eb + c;
+                s_x[row * kAgcXRow + c] = (seg0 + row < p.nseg && u < n) ? x[u] : cf(0.f, 0.f);
             }
         }
         cp_async_commit();
     };
+    float *myrow = sm + tid * kAgcRow;
+    float2 *myx = s_x + tid * kAgcXRow;
     fetch(0);
     for (int s = 0; s < nsteps; s++) {
 #pragma unroll
-        for (int i = 0; i < 32; i++) sm[32 * w + i][l] = nxt[i];
+        for (int i = 0; i < 32; i++) sm[(32 * w + i) * kAgcRow + 1 + l] = nxt[i];
         const bool emit = s >= wsteps;
-        if (emit) stage_x((s - wsteps) * kAgcB);
+        const bool next_emit = s + 1 >= wsteps && s + 1 < nsteps;       // block s + 1 is emitted: its samples are staged during this step
+        const int eb_next = (s + 1 - wsteps) * kAgcB;
+        // first half of this block has landed (issued half a step ago; cf32 output: the whole block, see below)
+        if (emit) { if (FM) cp_async_wait_group<1>(); else cp_async_wait_group<0>(); }
         __syncthreads();
         if (s + 1 < nsteps) fetch(s + 1);
-        const int u0 = b0 - p.W + s * kAgcB;                    // time of this thread's sm[tid][0]
-        const bool rec = emit || s == wsteps - 1;               // the last warm-up block records its gains as well (below)
-        if (live && u0 >= 0 && u0 < n) {
+        const int u0 = b0 - p.W + s * kAgcB;                    // time of this thread's myrow[1]
+        const bool active = live && u0 >= 0 && u0 < n;
+        const int cnt = active ? min(kAgcB, n - u0) : 0;
+        if (active) {
             if (!started) {
                 started = true;
                 if (b0 - p.W <= 0) { const LaneState ls = p.lane[lane]; g = ls.g; y2p = ls.y2p; }   // time 0: exact
                 else {
                     float e = 0.f;
 #pragma unroll
-                    for (int k = 0; k < 16; k++) e += sm[tid][k];
+                    for (int k = 0; k < 16; k++) e += myrow[1 + k];
                     agc_guess(e * (1.0f / 16.0f), g, y2p);
                 }
                 g2 = __fmul_rn(g, g);
             }
-            if (emit && s == wsteps) {
+            if (s == wsteps) {
                 SegState s0; s0.g = g; s0.y2p = y2p;
                 p.seg_start[(long long)lane * p.nseg + seg] = s0;
                 g2 = __fmul_rn(g, g);
+                // ungated output of the sample before the segment: y[b0-1] = y_dc[b0-1] * (gain before it = gain after
+                // b0-2, kept from the warm-up).  Segment 0 continues the previous call (lane state).
+                if (b0 == 0) { const LaneState ls = p.lane[lane]; es.yp = cf(ls.fm_re, ls.fm_im); }
+                else { const float2 xv = x[b0 - 1]; es.yp = cf(__fmul_rn(xv.x, g30), __fmul_rn(xv.y, g30)); }
             }
-            if (emit) s_g0[tid] = g;
-            const int cnt = min(kAgcB, n - u0);
-            if (cnt == kAgcB) {
-                if (rec) {
+        }
+        // ---- first half of the block
+        if (emit) {
+            es.ex = es.sr = es.si = 0u;
+            if (cnt == kAgcB) agc_emit_run<EXACT, FM, 0, 16>(co, g_thr, fm_ref, myrow, myx, g, g2, y2p, es);
+            else if (cnt > 0) agc_emit_ragged<EXACT, FM>(co, g_thr, fm_ref, myrow, myx, g, g2, y2p, es, cnt);
+        } else if (cnt == kAgcB) {
 #pragma unroll
-                    for (int k = 0; k < kAgcB; k++) { agc_step<EXACT>(co, g, g2, y2p, sm[tid][k]); sm[tid][k] = g; }
+            for (int k = 0; k < 16; k++) agc_step<EXACT>(co, g, g2, y2p, myrow[1 + k]);
+        } else {
+            for (int k = 0; k < cnt; k++) agc_step<EXACT>(co, g, g2, y2p, myrow[1 + k]);
+        }
+        // (cf32 output is written over the samples in place and copied out at the end of the step: the next block is staged
+        // behind the copy-out then)
+        __syncwarp();
+        if (FM) {
+            if (next_emit) stage_x(eb_next, 0); else cp_async_commit();
+            cp_async_wait_group<1>();                                   // second half of this block has landed
+        }
+        __syncwarp();
+        // ---- second half
+        if (emit) {
+            if (cnt == kAgcB) agc_emit_run<EXACT, FM, 16, 16>(co, g_thr, fm_ref, myrow, myx, g, g2, y2p, es);
+        } else if (cnt == kAgcB) {
+#pragma unroll
+            for (int k = 16; k < 32; k++) { if (k == 31) g30 = g; agc_step<EXACT>(co, g, g2, y2p, myrow[1 + k]); }
+        }
+        __syncwarp();
+        if (FM) { if (next_emit) stage_x(eb_next, 1); else cp_async_commit(); }
+        if (emit) {
+            // bit words of this thread's block; the threshold word also goes into the tile (row slot 0) for the copy-out
+            if (cnt > 0) {
+                const int wd = (b0 + (s - wsteps) * kAgcB) >> 5;
+                exb[wd] = es.ex;
+                if (FM) { sgr[wd] = es.sr; sgi[wd] = es.si; }
+                if (u0 + cnt >= min(b0 + L, n)) p.seg_ylast[(long long)lane * p.nseg + seg] = es.yp;     // the segment's last sample
+            }
+            myrow[0] = __uint_as_float(cnt > 0 ? es.ex : 0u);
+            __syncthreads();
+            // ---- copy-out: warp w writes rows 32 w .. 32 w + 31, lane = sample (coalesced).  The squelch can only be open
+            // on a sample that exceeds the threshold (every path into SIGNALHI takes the "exceeded" branch of the state
+            // machine), so a word without such a sample is closed throughout and left to the gate pass.
+            const int eb = (s - wsteps) * kAgcB;
+            const int ub0 = (seg0 + 32 * w) * L + eb;
+            const float *srow = sm + (32 * w) * kAgcRow;
+            if (full_rows) {
+                if (FM) {
+                    float *dst = of + ub0 + l;
+#pragma unroll 8
+                    for (int i = 0; i < 32; i++, dst += L, srow += kAgcRow)
+                        if (!(skip_closed && __float_as_uint(srow[0]) == 0u)) *dst = srow[1 + l];
                 } else {
-#pragma unroll
-                    for (int k = 0; k < kAgcB; k++) agc_step<EXACT>(co, g, g2, y2p, sm[tid][k]);
+                    float2 *dst = oc + ub0 + l;
+                    const float2 *xr = s_x + (32 * w) * kAgcXRow + l;
+#pragma unroll 8
+                    for (int i = 0; i < 32; i++, dst += L, srow += kAgcRow, xr += kAgcXRow)
+                        if (!(skip_closed && __float_as_uint(srow[0]) == 0u)) *dst = *xr;
                 }
             } else {
-                for (int k = 0; k < cnt; k++) { agc_step<EXACT>(co, g, g2, y2p, sm[tid][k]); if (rec) sm[tid][k] = g; }
-            }
-        }
-        if (s == wsteps - 1 && live && b0 < n) {
-            // ungated output of the sample before the segment: y[b0-1] = y_dc[b0-1] * (gain before it = gain after b0-2,
-            // recorded just now).  Segment 0 continues the previous call (lane state).
-            if (b0 == 0) { const LaneState ls = p.lane[lane]; s_yl[tid] = cf(ls.fm_re, ls.fm_im); }
-            else { const float2 xv = x[b0 - 1]; const float gb = sm[tid][kAgcB - 2]; s_yl[tid] = cf(__fmul_rn(xv.x, gb), __fmul_rn(xv.y, gb)); }
-        }
-        if (emit) cp_async_wait_all();
-        __syncthreads();
-        if (emit) {
-            const int eb = (s - wsteps) * kAgcB;                    // offset of this block inside every segment
-#pragma unroll 4
-            for (int i = 0; i < 32; i++) {
-                const int row = 32 * w + i, rseg = seg0 + row;
-                const int ub = rseg * L + eb;                       // first sample of the row's block (multiple of 32)
-                if (rseg >= p.nseg || ub >= n) break;               // warp-uniform; rows are in increasing time order
-                const int u = ub + l;
-                const bool in = interior || u < n;
-                const float2 xv = s_x[row * kAgcB + l];
-                const float ga = sm[row][l];
-                const float gprev = sm[row][l ? l - 1 : 0];
-                const float g0 = l ? gprev : s_g0[row];
-                const float2 yprev0 = s_yl[row];
-                __syncwarp();
-                const float2 y = be_emit_word<true, FM, EXACT>(p, lane, ub, in, xv, g0, ga, yprev0);
-                const int lastl = min(31, n - 1 - ub);
-                if (l == lastl) {
-                    s_yl[row] = y;
-                    if (eb + kAgcB >= L || ub + 32 >= n) p.seg_ylast[(long long)lane * p.nseg + rseg] = y;   // segment's last sample
+                int ub = ub0;
+                for (int i = 0; i < 32; i++, ub += L) {
+                    const int row = 32 * w + i;
+                    if (seg0 + row >= p.nseg || ub >= n) break;                                       // warp-uniform
+                    if (skip_closed && __float_as_uint(sm[row * kAgcRow]) == 0u) continue;            // warp-uniform
+                    if (ub + l < n) {
+                        if (FM) of[ub + l] = sm[row * kAgcRow + 1 + l];
+                        else    oc[ub + l] = s_x[row * kAgcXRow + l];
+                    }
                 }
             }
-            __syncthreads();
         }
+        if (!FM && next_emit) { __syncwarp(); stage_x(eb_next, 0); stage_x(eb_next, 1); }
+        __syncthreads();
     }
     if (live) {
         SegState s1; s1.g = g; s1.y2p = y2p;
@@ -629,6 +788,7 @@ __global__ void __launch_bounds__(256) k_be_emit(const BackendParams p)
 {
     const int lane = blockIdx.y, l = threadIdx.x & 31;
     const float2 *__restrict__ x = p.ydc + (long long)lane * p.ydc_stride;
+    const BeEmitCtx ctx = be_emit_ctx(p, lane);
     const int n = p.n, nwords = p.nwords;
     const int w0 = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * kEmitRun, w1 = min(w0 + kEmitRun, nwords);
     if (w0 >= nwords) return;                                    // whole warps leave together
@@ -637,7 +797,7 @@ __global__ void __launch_bounds__(256) k_be_emit(const BackendParams p)
         const int i = w * 32 + l;
         const bool in = i < n;
         const float2 xv = in ? x[i] : cf(0.f, 0.f);
-        const float2 y = be_emit_word<false, FM, EXACT>(p, lane, w * 32, in, xv, 1.f, 1.f, ylast);
+        const float2 y = be_emit_word<false, FM, EXACT, false>(ctx, w * 32, xv, 1.f, 1.f, ylast);
         if (in && i == n - 1) { p.lane[lane].fm_re = y.x; p.lane[lane].fm_im = y.y; }      // (read by k_be_first, an earlier launch)
         ylast.x = __shfl_sync(0xffffffffu, y.x, 31); ylast.y = __shfl_sync(0xffffffffu, y.y, 31);
     }
@@ -732,6 +892,7 @@ __device__ void be_redo_segment(const BackendParams &p, int lane, int seg, SegSt
     }
     __syncthreads();
     const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5, l = threadIdx.x & 31;
+    const BeEmitCtx ctx = be_emit_ctx(p, lane);
     const float2 yprev_seg = (seg == 0) ? p.y_first[lane] : p.seg_ylast[t - 1];
     for (int wd = warp; wd * 32 < len; wd += nwarps) {
         const int idx = wd * 32 + l, u = b0 + idx;
@@ -742,8 +903,8 @@ __device__ void be_redo_segment(const BackendParams &p, int lane, int seg, SegSt
         float2 yp0 = yprev_seg;
         if (wd > 0) { const float2 xp = x[b0 + wd * 32 - 1]; const float gp = s_g[wd * 32 - 1]; yp0 = cf(__fmul_rn(xp.x, gp), __fmul_rn(xp.y, gp)); }
         float2 y;
-        if (p.demod == 1) y = be_emit_word<true, true, EXACT>(p, lane, b0 + wd * 32, in, xv, g0, ga, yp0);
-        else              y = be_emit_word<true, false, EXACT>(p, lane, b0 + wd * 32, in, xv, g0, ga, yp0);
+        if (p.demod == 1) y = be_emit_word<true, true, EXACT, false>(ctx, b0 + wd * 32, xv, g0, ga, yp0);
+        else              y = be_emit_word<true, false, EXACT, false>(ctx, b0 + wd * 32, xv, g0, ga, yp0);
         if (idx == len - 1) p.seg_ylast[t] = y;
     }
     __syncthreads();
@@ -929,36 +1090,59 @@ __global__ void __launch_bounds__(kFinT, 2) k_be_finish(const BackendParams p, i
             if (p.gate) {
                 const int l = tid & 31, warp = gtid >> 5, nwarp = nthr >> 5;
                 const int runs_per_lane = (p.nwords + 31) / 32;
-                for (long long item = warp; item < (long long)p.nlanes * runs_per_lane; item += nwarp) {
-                    const int lane = (int)(item / runs_per_lane), wd0 = (int)(item - (long long)lane * runs_per_lane) * 32;
-                    const unsigned *gate = p.gatebits + (long long)lane * p.nwords;
-                    const int wd = wd0 + l;
-                    const bool have = wd < p.nwords;
-                    const int cntw = have ? min(32, p.n - wd * 32) : 0;
-                    const unsigned fullw = (cntw == 32) ? 0xffffffffu : ((1u << cntw) - 1u);
-                    const unsigned gw = have ? (gate[wd] & fullw) : 0u;
-                    const unsigned gtop = have ? (wd ? (gate[wd - 1] >> 31) : p.prev_gate[lane]) : 0u;
-                    unsigned srw = 0, siw = 0, srt = 0, sit = 0;
-                    if (p.demod == 1 && have) {
-                        const unsigned *sr = p.sgnr + (long long)lane * p.nwords, *si = p.sgni + (long long)lane * p.nwords;
-                        srw = sr[wd]; siw = si[wd];
-                        srt = wd ? (sr[wd - 1] >> 31) : (p.prev_sign[lane] & 1u);
-                        sit = wd ? (si[wd - 1] >> 31) : ((p.prev_sign[lane] >> 1) & 1u);
+                // (the words of the NEXT run are fetched before the current one is processed: the loop is a chain of
+                // dependent global loads otherwise)
+                struct Run { unsigned gw, fullw, gtop, srw, siw, srt, sit; int lane, wd0; bool have; };
+                auto load_run = [&](long long item) {
+                    Run r{};
+                    r.lane = (int)(item / runs_per_lane); r.wd0 = (int)(item - (long long)r.lane * runs_per_lane) * 32;
+                    const unsigned *gate = p.gatebits + (long long)r.lane * p.nwords;
+                    const int wd = r.wd0 + l;
+                    r.have = wd < p.nwords;
+                    const int cntw = r.have ? min(32, p.n - wd * 32) : 0;
+                    r.fullw = (cntw == 32) ? 0xffffffffu : ((1u << cntw) - 1u);
+                    r.gw = r.have ? (gate[wd] & r.fullw) : 0u;
+                    r.gtop = r.have ? (wd ? (gate[wd - 1] >> 31) : p.prev_gate[r.lane]) : 0u;
+                    if (p.demod == 1 && r.have) {
+                        const unsigned *sr = p.sgnr + (long long)r.lane * p.nwords, *si = p.sgni + (long long)r.lane * p.nwords;
+                        r.srw = sr[wd]; r.siw = si[wd];
+                        r.srt = wd ? (sr[wd - 1] >> 31) : (p.prev_sign[r.lane] & 1u);
+                        r.sit = wd ? (si[wd - 1] >> 31) : ((p.prev_sign[r.lane] >> 1) & 1u);
                     }
-                    const int nw = min(32, p.nwords - wd0);
-                    for (int j = 0; j < nw; j++) {
-                        const unsigned g = __shfl_sync(0xffffffffu, gw, j), full = __shfl_sync(0xffffffffu, fullw, j);
+                    return r;
+                };
+                const long long nitems = (long long)p.nlanes * runs_per_lane;
+                Run nxt_run{};
+                if (warp < nitems) nxt_run = load_run(warp);
+                for (long long item = warp; item < nitems; item += nwarp) {
+                    const Run cur = nxt_run;
+                    if (item + nwarp < nitems) nxt_run = load_run(item + nwarp);
+                    const int lane = cur.lane, wd0 = cur.wd0;
+                    const bool have = cur.have;
+                    const unsigned fullw = cur.fullw, gw = cur.gw, gtop = cur.gtop, srw = cur.srw, siw = cur.siw, srt = cur.srt, sit = cur.sit;
+                    const int cntw = (fullw == 0xffffffffu) ? 32 : 0;      // only "whole word" matters below
+                    // words that need no write (open throughout, predecessor open) are skipped; words that are closed
+                    // throughout (the bulk of a squelched stream) take a short path: one coalesced store of zeros
+                    const unsigned gprevw = (gw << 1) | gtop;
+                    const bool need = have && (p.demod == 1 ? ((gw & gprevw & fullw) != fullw) : (gw != fullw));
+                    const bool closed = have && cntw == 32 && gw == 0 && (p.demod != 1 || gtop == 0);
+                    const unsigned m_closed = __ballot_sync(0xffffffffu, closed);
+                    for (unsigned m = __ballot_sync(0xffffffffu, need); m; m &= m - 1) {
+                        const int j = __ffs(m) - 1;
                         const int i = (wd0 + j) * 32 + l;
-                        const bool in = (full >> l) & 1u;
-                        if (p.demod != 1) {
-                            if (g == full) continue;
-                            if (in && !((g >> l) & 1u)) ((float2 *)p.out + (long long)lane * p.out_lane_stride)[i] = cf(0.f, 0.f);
+                        if ((m_closed >> j) & 1u) {
+                            if (p.demod == 1) be_out_f(p, lane)[i] = 0.f;            // arg(+0 + j0) = 0
+                            else              be_out_c(p, lane)[i] = cf(0.f, 0.f);
                             continue;
                         }
-                        const unsigned gprev = (g << 1) | __shfl_sync(0xffffffffu, gtop, j);
-                        if ((g & gprev & full) == full) continue;            // every sample and its predecessor are open
-                        float *of = (float *)p.out + (long long)lane * p.out_lane_stride;
-                        if (g == 0 && (gprev & full) == 0) { if (in) of[i] = 0.f; continue; }     // closed throughout: arg(+0 + j0) = 0
+                        const unsigned g = __shfl_sync(0xffffffffu, gw, j), full = __shfl_sync(0xffffffffu, fullw, j);
+                        const bool in = (full >> l) & 1u;
+                        if (p.demod != 1) {
+                            if (in && !((g >> l) & 1u)) be_out_c(p, lane)[i] = cf(0.f, 0.f);
+                            continue;
+                        }
+                        const unsigned gprev = __shfl_sync(0xffffffffu, gprevw, j);
+                        float *of = be_out_f(p, lane);
                         const unsigned r = __shfl_sync(0xffffffffu, srw, j), im = __shfl_sync(0xffffffffu, siw, j);
                         const unsigned rprev = (r << 1) | __shfl_sync(0xffffffffu, srt, j), iprev = (im << 1) | __shfl_sync(0xffffffffu, sit, j);
                         const bool open = (g >> l) & 1u, popen = (gprev >> l) & 1u;
@@ -978,7 +1162,7 @@ __global__ void __launch_bounds__(kFinT, 2) k_be_finish(const BackendParams p, i
             for (int lane = gtid; lane < p.nlanes; lane += nthr) {
                 const SegState e = p.seg_end[(long long)lane * p.nseg + p.nseg - 1];
                 const FsmState f = p.fsm_end[(long long)lane * p.nseg + p.nseg - 1];
-                const float2 y = p.y_end[lane];
+                const float2 y = p.seg_ylast[(long long)lane * p.nseg + p.nseg - 1];      // ungated output of the chunk's last sample
                 LaneState &ls = p.lane[lane];
                 ls.g = e.g; ls.y2p = e.y2p; ls.mode = f.mode; ls.timer = f.timer; ls.fm_re = y.x; ls.fm_im = y.y;
                 p.first_bad[2 * lane] = 0xffffffffu; p.first_bad[2 * lane + 1] = 0xffffffffu;

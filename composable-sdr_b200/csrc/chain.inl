@@ -28,6 +28,25 @@ struct csdr_chain_s : Tagged {
     cudaStream_t be_stream = nullptr, d2h_stream = nullptr;
     std::vector<cudaEvent_t> ev_pool;
     DevBuf xpipe[2];
+    // per-channel output pointers for the back end (it writes the caller's buffers directly): device table, filled through a
+    // small ring of pinned staging slots
+    DevBuf out_tab; void **tab_host = nullptr; cudaEvent_t tab_ev[4] = {nullptr, nullptr, nullptr, nullptr}; unsigned tab_next = 0;
+    void *const *output_table(size_t count)
+    {
+        if (!tab_host) {
+            CK(cudaHostAlloc((void **)&tab_host, 4 * 4096 * sizeof(void *), cudaHostAllocDefault));
+            for (auto &e : tab_ev) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        }
+        if (count > 4096) return nullptr;
+        const unsigned slot = tab_next++ & 3;
+        CK(cudaEventSynchronize(tab_ev[slot]));                      // the copy that last used this slot has been executed
+        void **h = tab_host + (size_t)slot * 4096;
+        for (size_t i = 0; i < count; i++) h[i] = out_ptrs[i];
+        out_tab.ensure(4096 * sizeof(void *));
+        CK(cudaMemcpyAsync(out_tab.p, h, count * sizeof(void *), cudaMemcpyHostToDevice, ctx.stream));
+        CK(cudaEventRecord(tab_ev[slot], ctx.stream));
+        return (void *const *)out_tab.p;
+    }
     cudaEvent_t event(size_t i)
     {
         while (ev_pool.size() <= i) {
@@ -49,6 +68,8 @@ struct csdr_chain_s : Tagged {
         for (auto e : ev_pool) if (e) cudaEventDestroy(e);
         for (auto e : ev_copy) if (e) cudaEventDestroy(e);
         for (auto e : ev_done) if (e) cudaEventDestroy(e);
+        for (auto e : tab_ev) if (e) cudaEventDestroy(e);
+        if (tab_host) cudaFreeHost(tab_host);
     }
 };
 
@@ -199,6 +220,8 @@ size_t chain_run_device(csdr_chain_s *q, const float2 *xd, size_t nx, size_t x_s
             return nb;
         } else {
             void *dst = q->out_ptrs[0];
+            void *const *tab = contiguous ? nullptr : q->output_table(S);
+            if (tab) { q->be.run(c, r, r_stride, nullptr, 0, (int)nr, tab); return (size_t)nr; }
             if (!contiguous) { q->dem.ensure(q->esz * (size_t)nr * S); dst = q->dem.p; }
             q->be.run(c, r, r_stride, dst, nr, (int)nr);
             if (!contiguous)
@@ -245,6 +268,13 @@ size_t chain_run_device(csdr_chain_s *q, const float2 *xd, size_t nx, size_t x_s
             q->am.run(c.stream, q->dem.as<float2>(), (long long)nf, q->amout.as<float>(), (long long)nf, (int)nf);
             g_launches.fetch_add(q->am.take_launches());
             dem = q->amout.p;
+        } else if (!q->cfg.mix && !q->has_wb) {
+            // every channel's result goes straight into the caller's buffer for that channel
+            void *const *tab = q->output_table(C);
+            if (tab) { q->be.run(c, q->chan.as<float2>(), (long long)nf, nullptr, 0, (int)nf, tab); return nf; }
+            q->dem.ensure(q->esz * used);
+            q->be.run(c, q->chan.as<float2>(), (long long)nf, q->dem.p, (long long)nf, (int)nf);
+            dem = q->dem.p;
         } else {
             q->dem.ensure(q->esz * used);
             q->be.run(c, q->chan.as<float2>(), (long long)nf, q->dem.p, (long long)nf, (int)nf);

@@ -533,11 +533,9 @@ struct Backend {
     template <class L> void launch_dc(L &l, DcParams &d, cudaStream_t st)
     {
         const size_t blocks = (size_t)nlanes * d.nblk;
-        dc_agg.ensure(sizeof(double2) * blocks);
-        dc_flag.ensure_zero(sizeof(unsigned) * blocks, st);
-        d.agg = dc_agg.as<double2>(); d.flag = dc_flag.as<unsigned>(); d.ticket = dc_ticket.as<unsigned>();
-        if (++dc_epoch == 0) { CK(cudaMemsetAsync(dc_flag.p, 0, dc_flag.cap, st)); dc_epoch = 1; }
-        d.epoch = dc_epoch;
+        dc_agg.ensure(sizeof(SelfValid16) * blocks);
+        CK(cudaMemsetAsync(dc_agg.p, 0xff, sizeof(SelfValid16) * blocks, st));      // "not published yet"
+        d.agg = dc_agg.as<SelfValid16>(); d.ticket = dc_ticket.as<unsigned>();
         d.dc_in = dc_state[dc_cur].as<float2>(); d.dc_out = dc_state[dc_cur ^ 1].as<float2>();
         dc_cur ^= 1;
         be_launch_dc(l, d, 2 * sms);
@@ -565,15 +563,15 @@ struct Backend {
         return pwbuf.as<float>();
     }
     // [dc] -> [agc+gate] -> [fm]; out: float (demod) or float2
-    void run(const Ctx &c, const float2 *in, long long in_stride, void *out, long long out_stride, int n)
+    void run(const Ctx &c, const float2 *in, long long in_stride, void *out, long long out_stride, int n, void *const *out_table = nullptr)
     {
-        run_on(c.stream, in, in_stride, out, out_stride, n);
+        run_on(c.stream, in, in_stride, out, out_stride, n, out_table);
     }
-    void run_on(cudaStream_t st, const float2 *in, long long in_stride, void *out, long long out_stride, int n)
+    void run_on(cudaStream_t st, const float2 *in, long long in_stride, void *out, long long out_stride, int n, void *const *out_table = nullptr)
     {
         if (n <= 0) return;
         Launcher l{st, sms};
-        if (has_dc && !has_agc && demod == 0) {
+        if (has_dc && !has_agc && demod == 0 && !out_table) {
             // dc blocker only (config 1): the output pass writes the caller's buffer directly
             DcParams d = dc_params(in, in_stride, (float2 *)out, out_stride, n, st);
             launch_dc(l, d, st);
@@ -636,7 +634,7 @@ struct Backend {
             else if (has_agc && pw_ready_n != n) be_launch_prep(l, d);
             pw_ready_n = -1;
         }
-        b.in = in; b.in_lane_stride = in_stride; b.out = out; b.out_lane_stride = out_stride;
+        b.in = in; b.in_lane_stride = in_stride; b.out = out; b.out_lane_stride = out_stride; b.out_table = out_table;
         b.n = n; b.nlanes = nlanes; b.L = L; b.W = W; b.G = G; b.nseg = nseg; b.ngrp = ngrp;
         b.has_dc = has_dc; b.has_agc = has_agc; b.demod = demod;
         b.alpha = agc_bw; b.one_minus_alpha_f = (float)(1.0 - (double)agc_bw); b.neg_half_alpha = -0.5f * agc_bw;

@@ -93,6 +93,7 @@ __device__ __forceinline__ void tma_load_rows(void *dst, const FeTmap *tm, int r
 __device__ inline void cp_async16(void *dst, const void *src) { memcpy(dst, src, 16); }
 __device__ inline void cp_async_commit() {}
 __device__ inline void cp_async_wait_all() {}
+template <int N> __device__ inline void cp_async_wait_group() {}
 #else
 __device__ __forceinline__ void cp_async16(void *dst, const void *src)
 {
@@ -100,6 +101,39 @@ __device__ __forceinline__ void cp_async16(void *dst, const void *src)
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }   // all but the N newest groups
+#endif
+
+// ---- 16-byte values that validate themselves (decoupled look-back between CTAs): one vector store publishes, one
+// vector load polls -- no flag word, hence no memory fence (a fence behind a tile's worth of output stores waits for all
+// of them to drain).  Unpublished slots hold all-ones, which no arithmetic result is (the hardware's NaN is 0x7ff8...).
+struct alignas(16) SelfValid16 { unsigned long long a, b; };
+#ifdef CSDR_EMU
+__device__ inline void sv16_store(SelfValid16 *p, double x, double y)
+{
+    unsigned long long a, b; memcpy(&a, &x, 8); memcpy(&b, &y, 8);
+    __atomic_store_n(&p->b, b, __ATOMIC_SEQ_CST); __atomic_store_n(&p->a, a, __ATOMIC_SEQ_CST);
+}
+__device__ inline bool sv16_load(const SelfValid16 *p, double &x, double &y)
+{
+    const unsigned long long a = __atomic_load_n(&p->a, __ATOMIC_SEQ_CST), b = __atomic_load_n(&p->b, __ATOMIC_SEQ_CST);
+    if (a == ~0ull || b == ~0ull) return false;
+    memcpy(&x, &a, 8); memcpy(&y, &b, 8);
+    return true;
+}
+#else
+__device__ __forceinline__ void sv16_store(SelfValid16 *p, double x, double y)
+{
+    asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(__double_as_longlong(x)), "l"(__double_as_longlong(y)) : "memory");
+}
+__device__ __forceinline__ bool sv16_load(const SelfValid16 *p, double &x, double &y)
+{
+    unsigned long long a, b;
+    asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
+    if (a == ~0ull || b == ~0ull) return false;
+    x = __longlong_as_double((long long)a); y = __longlong_as_double((long long)b);
+    return true;
+}
 #endif
 
 // ---- named barriers (bar.sync / bar.arrive id, count): producer / consumer hand-over between two groups of warps ---

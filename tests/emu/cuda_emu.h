@@ -21,6 +21,7 @@
 #define __device__
 #define __host__
 #define __forceinline__ inline
+#define __noinline__
 #define __restrict__
 #define __launch_bounds__(...)
 #define __shared__ static
@@ -101,7 +102,7 @@ void launch(dim3 grid, dim3 block, size_t smem_bytes, K kernel, Args... args)
 #define gridDim (::csdr_emu::g_gridDim)
 
 static inline void __syncthreads() { pthread_barrier_wait(&::csdr_emu::g_barrier); }
-static inline void __syncwarp() {}
+static inline void __syncwarp() { pthread_barrier_wait(&::csdr_emu::g_warp_barrier[::csdr_emu::t_warp]); }    // lanes are OS threads here: a real barrier
 namespace csdr_emu {
 template <class T> inline T warp_exchange(T v, int src_lane)
 {
@@ -134,6 +135,7 @@ static inline unsigned __ballot_sync(unsigned, int pred)
     return r;
 }
 static inline void __threadfence() { __sync_synchronize(); }
+static inline int __ffs(unsigned v) { return __builtin_ffs((int)v); }
 
 // math intrinsics (host libm stands in for the SFU approximations; tests use tolerances)
 // (glibc declares __sinf & co. itself, so the CUDA intrinsic names are mapped by macro)
@@ -160,6 +162,7 @@ static inline float __int2float_rn(int x) { return (float)x; }
 static inline float __uint2float_rn(unsigned x) { return (float)x; }
 static inline int __float_as_int(float f) { int i; memcpy(&i, &f, 4); return i; }
 static inline float __uint_as_float(unsigned i) { float f; memcpy(&f, &i, 4); return f; }
+static inline unsigned __float_as_uint(float f) { unsigned i; memcpy(&i, &f, 4); return i; }
 static inline float __int_as_float(int i) { float f; memcpy(&f, &i, 4); return f; }
 static inline unsigned __brev(unsigned v) { unsigned r = 0; for (int i = 0; i < 32; i++) if (v & (1u << i)) r |= 1u << (31 - i); return r; }
 template <class T> static inline T __ldg(const T *p) { return *p; }

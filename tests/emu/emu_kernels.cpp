@@ -160,8 +160,8 @@ long long emu_backend(int nlanes, long long lane_stride, int has_dc, float dc_al
         if (nx == 0) continue;
         int ngrp = (nx + G - 1) / G, nseg = (nx + L - 1) / L, nblk = (ngrp + kDcGB - 1) / kDcGB;
         const long long pws = (nx + 3) / 4 * 4;
-        std::vector<double2> agg((size_t)nlanes * nblk);
-        std::vector<unsigned> flag((size_t)nlanes * nblk, 0u);
+        std::vector<SelfValid16> agg((size_t)nlanes * nblk);
+        memset(agg.data(), 0xff, agg.size() * sizeof(SelfValid16));
         unsigned ticket[2] = {0, 0};
         std::vector<double> powA(kDcGB + 1), powAB;
         std::vector<SegState> ss((size_t)nlanes * nseg), se((size_t)nlanes * nseg);
@@ -178,7 +178,7 @@ long long emu_backend(int nlanes, long long lane_stride, int has_dc, float dc_al
         d.in = x + pos; d.in_lane_stride = lane_stride; d.n = nx; d.nlanes = nlanes; d.G = G; d.ngrp = ngrp; d.nblk = nblk;
         d.has_dc = has_dc; d.out = has_dc ? ydc.data() : nullptr; d.out_lane_stride = pws;
         d.pw = has_agc ? pw.data() : nullptr; d.pw_stride = pws;
-        d.a1 = -1.0f + dc_alpha; d.c = -(double)d.a1; d.agg = agg.data(); d.flag = flag.data(); d.ticket = ticket; d.epoch = ++epoch;
+        d.a1 = -1.0f + dc_alpha; d.c = -(double)d.a1; d.agg = agg.data(); d.ticket = ticket;
         d.dc_in = dcst[dc_cur].data(); d.dc_out = dcst[dc_cur ^ 1].data();
         { double A = 1.0; for (int i = 0; i < G; i++) A *= d.c; powA[0] = 1.0; for (int k = 1; k <= kDcGB; k++) powA[k] = powA[k - 1] * A; }
         {

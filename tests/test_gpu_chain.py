@@ -216,8 +216,8 @@ def test_config5_batch_of_streams_am(cs, orc):
 
     liquid's DSB demodulator is a carrier PLL through a 1024-level phase quantiser: a perturbation of its INPUT by 1e-7
     (137 dB below the signal) moves the oracle's own output by -60 dB -- measured below on the oracle alone -- so the
-    chain is held (a) to 80 dB in front of the demodulator, (b) to 80 dB through the demodulator when it is fed the
-    oracle's samples, and (c) end to end to what that sensitivity allows."""
+    chain is held (a) to 80 dB in front of the demodulator, and (b) through the demodulator block alone, fed the
+    oracle's samples, and (c) end to end, to what that sensitivity allows."""
     S, n = 8, 1 << 21
     x = cs.synth.config5(n, S)
     skip = 15000                     # AGC attack + carrier PLL pull-in (437 Hz offset, loop bandwidth 1e-3)
@@ -234,16 +234,18 @@ def test_config5_batch_of_streams_am(cs, orc):
         assert np.array_equal(pres[s] == 0, pre == 0)
         assert_parity(pres[s][64:], pre[64:], rel=REL_TOL_AFTER_DCBLOCK, what=f"config 5 stream {s}, AGC output")
         if s < 2:
-            # (b) the demodulator block on the oracle's own samples
-            am = cs.amDemodulator()
-            r = am._start()
-            yb = np.concatenate([am._process(r, pre[:20000]), am._process(r, pre[20000:])])
-            am._done(r)
-            assert_parity(yb[skip:], ref[skip:], rel=3e-4, what=f"config 5 stream {s}, ampmodem on the oracle's samples")
             # (c) the oracle's own sensitivity to a 1e-7 perturbation of the demodulator's input
             pert = (pre * (1 + 1e-7 * (g.standard_normal(pre.size) + 1j * g.standard_normal(pre.size)))).astype(np.complex64)
             floor_db = snr_db(orc.AmpModem(0.8).execute(pert)[skip:], ref[skip:])
             assert 50.0 < floor_db < 75.0, floor_db
+            # (b) the demodulator block on the oracle's own samples: its 51-tap filters sum in a different order (1e-7),
+            # which is such a perturbation
+            am = cs.amDemodulator()
+            r = am._start()
+            yb = np.concatenate([am._process(r, pre[:20000]), am._process(r, pre[20000:])])
+            am._done(r)
+            assert snr_db(yb[skip:], ref[skip:]) >= floor_db - 6.0
+            assert_parity(yb[skip:], ref[skip:], rel=1e-2, snr=50.0, what=f"config 5 stream {s}, ampmodem on the oracle's samples")
         got = snr_db(outs[s][skip:], ref[skip:])
         assert got >= 55.0, f"config 5 stream {s}: SNR {got:.1f} dB"
         assert_parity(outs[s][skip:], ref[skip:], rel=1e-2, snr=55.0, what=f"config 5 stream {s}")
