@@ -460,6 +460,7 @@ struct Backend {
             powAB.ensure(sizeof(double) * pb.size());
             CK(cudaMemcpyAsync(powAB.p, pb.data(), sizeof(double) * pb.size(), cudaMemcpyHostToDevice, c.stream));
             dc_ticket.ensure(2 * sizeof(unsigned)); CK(cudaMemsetAsync(dc_ticket.p, 0, dc_ticket.cap, c.stream));
+            raise_dyn_smem(k_dc_scan<4>, kDcSmem); raise_dyn_smem(k_dc_scan<2>, kDcSmem); raise_dyn_smem(k_dc_scan<1>, kDcSmem);
             for (auto &d : dc_state) { d.ensure(sizeof(float2) * nlanes); CK(cudaMemsetAsync(d.p, 0, d.cap, c.stream)); }
             c.sync();
         }
