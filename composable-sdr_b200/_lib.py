@@ -11,7 +11,7 @@ class ChainCfg(C.Structure):
     _fields_ = [("samplerate", C.c_double), ("offset_hz", C.c_double), ("bandwidth_hz", C.c_double),
                 ("demod", C.c_int), ("kf", C.c_float), ("agc_thresh_db", C.c_float),
                 ("channels", C.c_uint), ("mix", C.c_int), ("nstreams", C.c_uint), ("device", C.c_int),
-                ("decim", C.c_uint)]
+                ("decim", C.c_uint), ("channelizer", C.c_int)]
 
 
 # every symbol include/csdr_b200.h declares: name -> (restype, argtypes)

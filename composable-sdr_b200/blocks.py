@@ -509,12 +509,12 @@ class Chain:
     """csdr_chain_*: the whole of sdrProcess behind one handle (device-resident state, fused kernels)."""
 
     def __init__(self, samplerate, offset=0.0, bandwidth=0.0, demod=None, agc=0.0, channels=1, mix_channels=False,
-                 nstreams=1, device=-1):
+                 nstreams=1, device=-1, channelizer=0):
         demod = demod or DeNo()
         self.L = _lib.load()
         self.cfg = ChainCfg(float(samplerate), float(offset), float(bandwidth), demod.code, float(demod.kf), float(agc),
                             int(channels), int(bool(mix_channels)), int(nstreams), int(device),
-                            int(getattr(demod, "decim", 0)))
+                            int(getattr(demod, "decim", 0)), int(channelizer))
         self.h = _lib.check_handle(self.L.csdr_chain_create(C.byref(self.cfg)), "csdr_chain_create")
         self.nout = int(self.L.csdr_chain_num_outputs(self.h))
         self.nstreams = max(1, int(nstreams))

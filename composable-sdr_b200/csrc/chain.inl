@@ -8,7 +8,8 @@
 struct csdr_chain_s : Tagged {
     Ctx ctx;
     csdr_chain_cfg cfg;
-    unsigned C = 1, nstreams = 1, nout = 1;
+    unsigned C = 1, nstreams = 1, nout = 1, hop = 1;        // hop: input samples per channelizer frame (C, or C/2 oversampled)
+    bool over2 = false;
     size_t esz = 8;
     bool has_resamp = false, has_mix = false, has_agc = false;
     int mix_mode = 0; uint32_t mix_theta = 0, mix_dtheta = 0; int quantize = 1;
@@ -80,6 +81,10 @@ void chain_init(csdr_chain_s *q)
     const csdr_chain_cfg &c = q->cfg;
     if (!(c.samplerate > 0)) throw CudaError{"chain: samplerate must be positive"};
     q->C = c.channels > 1 ? c.channels : 1;
+    q->over2 = q->C > 1 && c.channelizer == CSDR_CHANNELIZER_FIRPFBCH2;
+    if (c.channelizer != CSDR_CHANNELIZER_FIRPFBCH && c.channelizer != CSDR_CHANNELIZER_FIRPFBCH2) throw CudaError{"chain: unknown channelizer"};
+    if (q->over2 && (q->C & 1)) throw CudaError{"chain: firpfbch2 needs an even channel count"};
+    q->hop = q->over2 ? q->C / 2 : q->C;
     q->nstreams = c.nstreams > 1 ? c.nstreams : 1;
     if (q->C > 1 && q->nstreams > 1) throw CudaError{"chain: channelizer with nstreams > 1 is not implemented"};
     if (c.demod < 0 || c.demod > 3) throw CudaError{"chain: unknown demodulator"};
@@ -111,8 +116,8 @@ void chain_init(csdr_chain_s *q)
     } else {
         q->dcb.has_dc = true; q->dcb.dc_alpha = 0.0005f;
         q->dcb.init(q->ctx, 1);
-        q->ch.init(q->ctx, q->C, 7, 80.0f);
-        q->rot_dtheta = design::nco_constrain(design::firpfbch_rotation(q->C));
+        q->ch.init(q->ctx, q->C, 7, 80.0f, q->over2);
+        q->rot_dtheta = q->over2 ? 0u : design::nco_constrain(design::firpfbch_rotation(q->C));
         q->be.has_dc = false;
         q->be.has_agc = q->has_agc; q->be.agc_thr = c.agc_thresh_db;
         q->be.demod = (c.demod == CSDR_DEMOD_NBFM || q->has_wb) ? 1 : 0; q->be.kf = q->has_wb ? 0.6f : c.kf > 0 ? c.kf : 0.3f;
@@ -134,7 +139,7 @@ void chain_init(csdr_chain_s *q)
 size_t chain_max_out(const csdr_chain_s *q, size_t nx)
 {
     size_t n = q->has_resamp ? (size_t)q->fe.max_out((long long)nx) : nx;
-    if (q->C > 1) n = (n + q->nleft) / q->C + 1;
+    if (q->C > 1) n = (n + q->nleft) / q->hop + 1;
     if (q->has_wb) n = q->wb.max_out(n) + 1;
     return n;
 }
@@ -233,8 +238,8 @@ size_t chain_run_device(csdr_chain_s *q, const float2 *xd, size_t nx, size_t x_s
 
     // ---- channelizer path: wide-band dc blocker; its output pass also applies the channelizer's pre-rotation
     // (Liquid.chs:847) and writes straight into the channelizer's input slot, behind the (already rotated) left-over
-    const unsigned C = q->C;
-    const size_t tot = q->nleft + (size_t)nr, nf = tot / C, used = nf * C;
+    const unsigned C = q->C, hop = q->hop;
+    const size_t tot = q->nleft + (size_t)nr, nf = tot / hop, used_in = nf * hop, used = nf * C;
     if ((q->has_wb ? q->wb.max_out(nf) : nf) > out_cap) throw CudaError{"chain: output capacity too small"};
     float2 *dst = nullptr;
     if (nf) {
@@ -246,7 +251,7 @@ size_t chain_run_device(csdr_chain_s *q, const float2 *xd, size_t nx, size_t x_s
         dst = q->left.as<float2>() + q->nleft;
     }
     if (nr) {
-        q->dcb.run_dc_only(c, r, 0, dst, 0, (int)nr, true, q->rot_theta, q->rot_dtheta, q->quantize);
+        q->dcb.run_dc_only(c, r, 0, dst, 0, (int)nr, !q->over2, q->rot_theta, q->rot_dtheta, q->quantize);
         q->rot_theta += (uint32_t)nr * q->rot_dtheta;
     }
     if (nf) {
@@ -256,8 +261,8 @@ size_t chain_run_device(csdr_chain_s *q, const float2 *xd, size_t nx, size_t x_s
         float *pw = q->has_agc ? q->be.pw_target((int)nf, &pw_stride) : nullptr;     // the channelizer writes |y|^2 as well
         q->ch.run(c, (int)nf, q->chan.as<float2>(), (long long)nf, pw, pw_stride);
         // remaining < C (rotated) samples wait for the next call
-        const size_t rem = tot - used;
-        if (rem) CK(cudaMemcpyAsync(q->left.p, slot + used, sizeof(float2) * rem, cudaMemcpyDeviceToDevice, c.stream));
+        const size_t rem = tot - used_in;
+        if (rem) CK(cudaMemcpyAsync(q->left.p, slot + used_in, sizeof(float2) * rem, cudaMemcpyDeviceToDevice, c.stream));
         q->nleft = rem;
         // per-channel agc -> demod
         void *dem = nullptr;
@@ -492,6 +497,7 @@ int csdr_chain_seek(csdr_chain q, uint64_t n_prior)
     REQUIRE(q, TAG_CHAIN, -1);
     API_BEGIN
     if (q->has_wb) throw CudaError{"chain: seek with DeWBFM is not implemented"};
+    if (q->over2) throw CudaError{"chain: seek with the firpfbch2 channelizer is not implemented"};
     q->ctx.use();
     // samples behind the resampler that precede the new position (closed form: fe_seek)
     unsigned long long o_prior = n_prior;

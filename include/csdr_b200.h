@@ -212,7 +212,12 @@ typedef struct {
     int      device;         /* CUDA device ordinal, -1 = current */
     unsigned decim;          /* DeWBFM decim: wbFMDemodulator (kf 0.6, de-emphasis at 5 kHz of the quadrature rate = -b,
                                 firdecim by decim; Liquid.chs:652-656, SoapySDR.hs:253-260); 0/1 = no decimation */
+    int      channelizer;    /* CSDR_CHANNELIZER_*: 0 = firpfbch_crcf + pre-rotation, what the reference runs (Liquid.chs:811-866);
+                                1 = firpfbch2_crcf, liquid's 2x oversampled analyzer (channels even; a frame is channels/2
+                                samples, every channel comes out at 2/channels of the input rate, channel c centred on
+                                c/channels of the sample rate, no pre-rotation) */
 } csdr_chain_cfg;
+enum { CSDR_CHANNELIZER_FIRPFBCH = 0, CSDR_CHANNELIZER_FIRPFBCH2 = 1 };
 typedef struct csdr_chain_s *csdr_chain;
 csdr_chain csdr_chain_create(const csdr_chain_cfg *cfg);
 int      csdr_chain_destroy(csdr_chain q);

@@ -912,6 +912,7 @@ struct orc_chain_s {
     orc_msresamp rs;
     orc_iirfilt dc;
     orc_firpfbch fb; orc_nco fb_nco;
+    orc_firpfbch2 fb2;                               /* cfg.channelizer == 1 */
     orc_agc *agc; orc_freqdem *fm; orc_ampmodem *am;
     orc_iirfilt_rrrf *deemph; orc_firdecim *dec; float *dec_left; unsigned *dec_fill;   /* DeWBFM tail per channel */
     orc_cf32 *frame_buf; size_t frame_fill;          /* < C leftover samples */
@@ -931,7 +932,10 @@ orc_chain orc_chain_create(const orc_chain_cfg *cfg)
     }
     if (cfg->bandwidth_hz != 0.0) q->rs = orc_msresamp_crcf_create((float)(cfg->bandwidth_hz / cfg->samplerate), 60.0f);
     q->dc = orc_iirfilt_crcf_create_dc_blocker(0.0005f);
-    if (q->C > 1) {
+    if (q->C > 1 && cfg->channelizer == 1) {
+        q->fb2 = orc_firpfbch2_crcf_create_kaiser(0, q->C, 7, 80.0f);
+        q->frame_buf = (orc_cf32 *)calloc(q->C, sizeof(orc_cf32));
+    } else if (q->C > 1) {
         q->fb = orc_firpfbch_crcf_create_kaiser(0, q->C, 7, 80.0f);
         q->fb_nco = orc_nco_crcf_create(1);
         /* offset = -0.5*(n-1)/n*2*pi in Float (Liquid.chs:817) */
@@ -979,6 +983,7 @@ void orc_chain_destroy(orc_chain q)
     if (q->rs) orc_msresamp_crcf_destroy(q->rs);
     orc_iirfilt_crcf_destroy(q->dc);
     if (q->fb) { orc_firpfbch_crcf_destroy(q->fb); orc_nco_crcf_destroy(q->fb_nco); }
+    if (q->fb2) orc_firpfbch2_crcf_destroy(q->fb2);
     for (unsigned c = 0; c < q->C; c++) {
         if (q->agc[c]) orc_agc_crcf_destroy(q->agc[c]);
         if (q->fm[c]) orc_freqdem_destroy(q->fm[c]);
@@ -1047,8 +1052,9 @@ int orc_chain_process(orc_chain q, const orc_cf32 *x, size_t nx, void *const *ou
             produced += chain_demod(q, 0, r, nr, tmp, (char *)outs[0] + produced * esz);
             free(tmp);
         } else {
-            /* assemble whole frames: leftover + new */
-            size_t tot = q->frame_fill + nr, nf = tot / C;
+            /* assemble whole frames: leftover + new (a frame of the oversampled analyzer is C/2 input samples) */
+            const size_t hop = q->fb2 ? C / 2 : C;
+            size_t tot = q->frame_fill + nr, nf = tot / hop;
             orc_cf32 *buf = (orc_cf32 *)malloc((tot ? tot : 1) * sizeof(orc_cf32));
             memcpy(buf, q->frame_buf, q->frame_fill * sizeof(orc_cf32));
             memcpy(buf + q->frame_fill, r, nr * sizeof(orc_cf32));
@@ -1056,6 +1062,14 @@ int orc_chain_process(orc_chain q, const orc_cf32 *x, size_t nx, void *const *ou
             if (nf) {
                 orc_cf32 *ch = (orc_cf32 *)malloc(nf * C * sizeof(orc_cf32));
                 orc_cf32 *tmp = (orc_cf32 *)malloc(nf * sizeof(orc_cf32));
+                if (q->fb2) {
+                    orc_cf32 *fr = (orc_cf32 *)malloc(C * sizeof(orc_cf32));
+                    for (size_t t = 0; t < nf; t++) {
+                        orc_firpfbch2_crcf_execute(q->fb2, buf + t * hop, fr);
+                        for (unsigned c = 0; c < C; c++) ch[nf * c + t] = fr[c];
+                    }
+                    free(fr);
+                } else
                 orc_hs_firpfbch_chan(q->fb, q->fb_nco, C, buf, (unsigned)(nf * C), ch);
                 void *dem = malloc(nf * sizeof(orc_cf32));
                 size_t nd = 0;                       /* samples per channel after the demodulator (< nf for DeWBFM) */
@@ -1074,8 +1088,8 @@ int orc_chain_process(orc_chain q, const orc_cf32 *x, size_t nx, void *const *ou
                 free(dem); free(ch); free(tmp);
                 produced += nd;
             }
-            q->frame_fill = tot - nf * C;
-            memcpy(q->frame_buf, buf + nf * C, q->frame_fill * sizeof(orc_cf32));
+            q->frame_fill = tot - nf * hop;
+            memcpy(q->frame_buf, buf + nf * hop, q->frame_fill * sizeof(orc_cf32));
             free(buf);
         }
     }

@@ -161,6 +161,8 @@ typedef struct {
     unsigned channels;        /* -c */
     int      mix;             /* -m */
     unsigned decim;           /* DeWBFM: output decimation */
+    int      channelizer;     /* 0: firpfbch_crcf + pre-rotation (the reference, Liquid.chs:811-866); 1: firpfbch2_crcf (2x
+                                 oversampled analyzer, M/2 samples in, M channels out per frame, no pre-rotation) */
 } orc_chain_cfg;
 typedef struct orc_chain_s *orc_chain;
 orc_chain orc_chain_create(const orc_chain_cfg *cfg);

@@ -26,7 +26,7 @@ def build(force=False):
 class ChainCfg(C.Structure):
     _fields_ = [("samplerate", C.c_double), ("offset_hz", C.c_double), ("bandwidth_hz", C.c_double),
                 ("demod", C.c_int), ("kf", C.c_float), ("agc_thresh_db", C.c_float),
-                ("channels", C.c_uint), ("mix", C.c_int), ("decim", C.c_uint)]
+                ("channels", C.c_uint), ("mix", C.c_int), ("decim", C.c_uint), ("channelizer", C.c_int)]
 
 
 _lib = None
@@ -443,14 +443,14 @@ class Chain:
     """sdrProcess (apps/SoapySDR.hs:181-283) as one sequential object."""
 
     def __init__(self, samplerate, offset_hz=0.0, bandwidth_hz=0.0, demod=DEMOD_NO, kf=0.3, agc_thresh_db=0.0,
-                 channels=1, mix=False, fast=False, decim=1):
+                 channels=1, mix=False, fast=False, decim=1, channelizer=0):
         self.L = lib(fast)
-        self.cfg = ChainCfg(samplerate, offset_hz, bandwidth_hz, demod, kf, agc_thresh_db, channels, int(mix), int(decim))
+        self.cfg = ChainCfg(samplerate, offset_hz, bandwidth_hz, demod, kf, agc_thresh_db, channels, int(mix), int(decim), int(channelizer))
         self.h = self.L.orc_chain_create(C.byref(self.cfg))
         self.nout = self.L.orc_chain_num_outputs(self.h)
         self.dtype = np.float32 if demod else np.complex64
         r = (bandwidth_hz / samplerate) if bandwidth_hz else 1.0
-        self._ratio = r / max(1, channels)
+        self._ratio = r / max(1, channels) * (2 if channelizer else 1)
 
     def close(self):
         if self.h:

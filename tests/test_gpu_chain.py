@@ -251,6 +251,28 @@ def test_config5_batch_of_streams_am(cs, orc):
         assert_parity(outs[s][skip:], ref[skip:], rel=1e-2, snr=55.0, what=f"config 5 stream {s}")
 
 
+def test_chain_with_the_oversampled_channelizer(cs, orc):
+    """channelizer = firpfbch2_crcf (liquid's 2x oversampled analyzer as the chain's channelizer block):
+    16 channels at 2/16 of the input rate each, per-channel AGC + NBFM, ragged chunks (left-overs of less than half a
+    frame), and the --mix sum, against the oracle's chain with the sequential firpfbch2 object"""
+    x = cs.synth.config3(1 << 20)
+    ref = orc.Chain(2.56e6, 0.0, 0.0, orc.DEMOD_NBFM, 0.3, -40.0, 16, False, channelizer=1).process(x)
+    outs = run_chain(cs.Chain(2.56e6, demod=cs.DeNBFM(0.3), agc=-40.0, channels=16, channelizer=1), x, [1 << 19, 65536 + 3, 5, 1 << 20])
+    assert len(outs) == 16 and len(outs[0]) == len(ref[0]) == (1 << 20) // 8
+    _assert_channels(outs, ref, "firpfbch2 chain", fm=True, rel=REL_TOL_FM_NOISE)
+    refc = orc.Chain(2.56e6, 0.0, 0.0, orc.DEMOD_NO, 0.0, 0.0, 16, False, channelizer=1).process(x[:1 << 18])
+    outc = run_chain(cs.Chain(2.56e6, channels=16, channelizer=1), x[:1 << 18], [100000, 7])
+    for c in range(16):
+        assert_parity(outc[c], refc[c], what=f"firpfbch2 chain, DeNo channel {c}")
+    # 20 channels (not a power of two) behind the resampler, as in README example 3
+    x3 = cs.synth.example3(1 << 20)
+    r3 = orc.Chain(3.2e6, 0.0, 1.6e6, orc.DEMOD_NO, 0.0, 0.0, 20, False, channelizer=1).process(x3)
+    o3 = run_chain(cs.Chain(3.2e6, 0.0, 1.6e6, channels=20, channelizer=1), x3, [300001, 1 << 20])
+    for c in range(20):
+        assert len(o3[c]) == len(r3[c]) == (1 << 20) // 2 // 10
+        assert_parity(o3[c], r3[c], rel=2e-4, what=f"firpfbch2 chain behind the resampler, channel {c}")
+
+
 def test_time_segment_sharding_matches_single_stream(cs, orc):
     """multi-GPU partitioning of one long stream: a shard seeks to its start minus the warm-up, feeds
     the warm-up history, drops the outputs it produces, and then equals the single-stream result."""

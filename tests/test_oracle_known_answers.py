@@ -204,3 +204,17 @@ def test_firpfbch2_tone_lands_in_bin_at_twice_the_channel_rate(orc, M):
     others = [c for c in range(M) if c not in (k - 1, k, k + 1)]
     assert mag[others].max() < 1e-3
     assert np.abs(y[k, -1] - y[k, -2]) < 1e-4
+
+
+def test_oracle_chain_with_the_oversampled_channelizer(orc):
+    """cfg.channelizer = 1 (firpfbch2_crcf in the chain: SURVEY 8f N1): the chain restatement equals its blocks composed
+    by hand -- dc blocker, frames of M/2 samples through the sequential firpfbch2 object, per-channel agc + freqdem"""
+    import composable_sdr_b200.synth as synth
+    M = 16
+    x = synth.config3(1 << 15, channels=M)
+    outs = orc.Chain(2.56e6, 0.0, 0.0, orc.DEMOD_NBFM, 0.3, -40.0, M, False, channelizer=1).process(x)
+    assert len(outs) == M and len(outs[0]) == 2 * len(x) // M
+    ch = orc.Firpfbch2(M).execute(orc.DcBlocker().execute(x))
+    for c in (0, 3, 8, 15):
+        ref = orc.FreqDem(0.3).execute(orc.Agc(-40.0).execute(ch[c]))
+        assert np.array_equal(outs[c], ref)
