@@ -698,6 +698,7 @@ struct Channelizer {
     size_t smem = 0;
     void (*tile_kernel)(PfbTileParams) = nullptr; PfbTileParams tp{}; size_t tile_smem = 0;   // M = 2..32, m = 7
     bool ring_ok = false; int ring_ctas = 1; void (*ring_kernel)(PfbRingParams) = nullptr;                                                 // M = 128..1024, m = 7
+    bool stream_ok = false; int stream_ctas = 1; DevBuf perm; void (*stream_kernel)(PfbStreamParams) = nullptr;                                                                              // M = 128..1024, m = 7 (default)
     bool over2 = false; unsigned long long frames_done = 0;     // firpfbch2 analyzer: hop M/2, generic kernel
 
     void init(const Ctx &c, unsigned M_, unsigned m_, float As_, bool over2_ = false)
@@ -743,6 +744,18 @@ struct Channelizer {
             CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ring_ctas, ring_kernel, 2 * (int)M / kPfbRingCPT, pfb_ring_smem((int)M, log2M)));
             if (ring_ctas < 1) ring_ok = false;
         }
+        stream_ok = !over2 && log2M >= 7 && M <= 1024 && (int)P == kPfbStP && g_options[CSDR_OPT_PFB_VARIANT] == 0;
+        if (stream_ok) {
+            std::vector<unsigned short> pm(M);
+            pfb_stream_perm((int)M, pm.data());
+            perm.ensure(M * sizeof(unsigned short));
+            CK(cudaMemcpyAsync(perm.p, pm.data(), M * sizeof(unsigned short), cudaMemcpyHostToDevice, c.stream));
+            stream_kernel = log2M == 7 ? k_pfb_stream<7> : log2M == 8 ? k_pfb_stream<8> : log2M == 9 ? k_pfb_stream<9> : k_pfb_stream<10>;
+            raise_dyn_smem(stream_kernel, pfb_stream_smem((int)M));
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&stream_ctas, stream_kernel, (int)M, pfb_stream_smem((int)M)));
+            if (stream_ctas < 1) stream_ok = false;
+            c.sync();
+        }
         size_t hb = hist_samples() * sizeof(float2);
         for (auto &b : xr) { b.ensure(hb); CK(cudaMemsetAsync(b.p, 0, b.cap, c.stream)); }
         c.sync();
@@ -773,7 +786,17 @@ struct Channelizer {
         p.h = hd.as<float>(); p.tw = tw.as<float2>();
         p.hop = (int)hop(); p.over2 = over2 ? 1 : 0; p.parity0 = (int)(frames_done & 1); p.scale = 1.0f / (float)M;
         frames_done += (unsigned long long)nf;
-        if (ring_ok) {
+        if (stream_ok) {
+            PfbStreamParams sp{};
+            sp.xr = p.xr; sp.y = y; sp.y_stride = y_stride; sp.pw = pw; sp.pw_stride = pw_stride; sp.nf = nf; sp.M = (int)M; sp.log2M = log2M;
+            sp.h = hd.as<float>(); sp.tw = tw.as<float2>(); sp.perm = perm.as<unsigned short>();
+            // one wave of CTAs where possible: frames per CTA = nf / (SMs * CTAs per SM), in whole output tiles
+            const int slots = std::max(1, c.sms * stream_ctas);
+            int T = (nf + slots - 1) / slots;
+            T = std::max(2 * kPfbStTF, (T + kPfbStTF - 1) / kPfbStTF * kPfbStTF);
+            sp.T = T;
+            launch(stream_kernel, dim3((nf + T - 1) / T), dim3(M), pfb_stream_smem((int)M), c.stream, sp);
+        } else if (ring_ok) {
             PfbRingParams rp{};
             rp.xr = p.xr; rp.y = y; rp.y_stride = y_stride; rp.nf = nf; rp.M = (int)M; rp.log2M = log2M;
             rp.pw = pw; rp.pw_stride = pw_stride;

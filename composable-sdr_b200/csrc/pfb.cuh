@@ -379,6 +379,190 @@ __global__ void __launch_bounds__(512, 1) k_pfb_ring(const PfbRingParams p)
     }
 }
 
+// ---- large power-of-two M (128..1024), one thread per polyphase branch --------------------------------------------
+// Thread n of the CTA (M threads) owns branch n: its 14 taps and a sliding window of the branch's last samples live in
+// REGISTERS, so the polyphase filter reads every input sample once from HBM (coalesced rows of M samples) and nothing
+// from shared memory.  Four frames are filtered per iteration (17 window samples, static indices, one shift by four);
+// their M-point DFTs run in shared memory as in-place radix-4 decimation-in-frequency passes with all M threads busy
+// (4 frames x M/4 butterflies; an odd log2 M starts with one radix-2 pass), on a layout padded by one element per 16 so
+// that the short-stride passes at the end stay (nearly) conflict-free.  The last pass writes straight into the
+// transposed output tile (frequency of a position: `perm`, computed on the host by following the passes), which is
+// flushed every 8 frames: 64 contiguous bytes per channel.  The loads of the next four frames are issued before the DFT
+// passes and land while they run.
+constexpr int kPfbStP = 14, kPfbStFI = 4, kPfbStTF = 8;
+struct PfbStreamParams {
+    const float2 *xr; float2 *y; long long y_stride;
+    float *pw; long long pw_stride;        // optional: |y|^2, same layout
+    int nf, T;                             // frames in this call, frames per CTA (multiple of kPfbStTF)
+    int M, log2M;
+    const float *h;                        // prototype, P*M taps
+    const float2 *tw;                      // M twiddles exp(-j 2 pi t / M)
+    const unsigned short *perm;            // [M] frequency held by position p behind the DIF passes
+};
+inline size_t pfb_stream_wp(int M) { return (size_t)M + ((size_t)M >> 4); }
+inline size_t pfb_stream_orow(int M) { return (size_t)M + ((size_t)M >> 4) + 2; }
+// twiddles: one contiguous table per pass (3 x N/4 entries W_N^(q j), q = 1..3; M/2 entries for the radix-2 pass), so that
+// consecutive butterflies read consecutive entries (a shared table of W_M^t is read with strides 4, 16, 64, ...: 16-way
+// bank conflicts in the short passes)
+inline size_t pfb_stream_ntw(int M) { return 2 * (size_t)M; }
+inline size_t pfb_stream_smem(int M)
+{
+    return sizeof(float2) * (kPfbStFI * pfb_stream_wp(M) + kPfbStTF * pfb_stream_orow(M) + pfb_stream_ntw(M)) + sizeof(unsigned short) * (size_t)M;
+}
+// frequency held by every position after the in-place DIF passes (radix-2 first when log2 M is odd, then radix-4)
+inline void pfb_stream_perm(int M, unsigned short *perm)
+{
+    struct Job { int base, N, f0, s; };
+    Job stack[64]; int sp = 0;
+    stack[sp++] = Job{0, M, 0, 1};
+    while (sp) {
+        const Job j = stack[--sp];
+        if (j.N == 1) { perm[j.base] = (unsigned short)(j.f0 & (M - 1)); continue; }
+        int lg = 0; while ((1 << lg) < j.N) lg++;
+        const int r = (lg & 1) ? 2 : 4;
+        for (int q = 0; q < r; q++) stack[sp++] = Job{j.base + q * (j.N / r), j.N / r, j.f0 + j.s * q, j.s * r};
+    }
+}
+
+// one radix-4 DIF pass over blocks of N (compile time) and every shorter one behind it, down to N = 16
+template <int N, int M>
+__device__ __forceinline__ void pfb_stream_passes(float2 *wf, const float2 *tp, int bq)
+{
+    if constexpr (N > 4) {
+        constexpr int Q = N >> 2;
+        int j = bq & (Q - 1), base = (bq / Q) * N + j;
+        if constexpr (N == 16 && M >= 256) {
+            // 16 consecutive butterflies take the same j of 16 consecutive blocks: on the padded layout their elements are 17
+            // apart (16 different banks) and they share their twiddles; j-fastest order would put four of them on one bank
+            j = (bq >> 4) & 3;
+            base = (((bq & 15) | ((bq >> 6) << 4)) << 4) + j;
+        }
+        float2 x[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) { const int i = base + k * Q; x[k] = wf[i + (i >> 4)]; }
+        pfb_dif4(x, tp[j], tp[Q + j], tp[2 * Q + j]);
+#pragma unroll
+        for (int k = 0; k < 4; k++) { const int i = base + k * Q; wf[i + (i >> 4)] = x[k]; }
+        __syncthreads();
+        pfb_stream_passes<(N >> 2), M>(wf, tp + 3 * Q, bq);
+    }
+}
+
+template <int LM>
+__global__ void __launch_bounds__(1 << LM, 1) k_pfb_stream(const PfbStreamParams p)
+{
+    constexpr int P = kPfbStP, FI = kPfbStFI, TF = kPfbStTF;
+    CSDR_DYN_SMEM(smem_raw);
+    constexpr int M = 1 << LM, lm = LM;
+    const int n = threadIdx.x;                                      // blockDim.x = M
+    constexpr int WP = M + (M >> 4), OR = M + (M >> 4) + 2;
+    float2 *work = reinterpret_cast<float2 *>(smem_raw);            // [FI][WP], element i at i + (i >> 4)
+    float2 *obuf = work + FI * WP;                                  // [TF][OR], channel c at c + (c >> 4)
+    float2 *stw = obuf + TF * OR;                                   // per-pass twiddle tables, < 2 M entries in all
+    unsigned short *sperm = reinterpret_cast<unsigned short *>(stw + 2 * M);
+    const int t0 = blockIdx.x * p.T, t1 = min(t0 + p.T, p.nf);
+    if (t0 >= t1) return;
+    sperm[n] = p.perm[n];
+    {
+        // radix-2 pass (odd log2 M): W_M^b, b < M/2; then for N = M (or M/2), N/4, ..., 16: W_N^(q j), q = 1..3, j < N/4
+        int off = 0, N = M;
+        if (lm & 1) { if (n < (M >> 1)) stw[n] = p.tw[n]; off = M >> 1; N = M >> 1; }
+        for (; N > 4; N >>= 2) {
+            const int Q = N >> 2;
+            for (int e = n; e < 3 * Q; e += M) { const int q = e / Q + 1, j = e - (q - 1) * Q; stw[off + e] = p.tw[(q * j * (M / N)) & (M - 1)]; }
+            off += 3 * Q;
+        }
+    }
+    // taps of this thread's branch: hh[k] = h[(M-1-n) + k M]
+    float hh[P];
+#pragma unroll
+    for (int k = 0; k < P; k++) hh[k] = p.h[(M - 1 - n) + k * M];
+    // window: w[j] = sample of row (t + j) of xr in column n, t = first frame of the iteration (row r of xr = history or new
+    // frame r - (P-1)); frame t + f needs rows t + f .. t + f + P - 1
+    float2 w[P - 1 + FI];
+    const long long last_row = (long long)p.nf + P - 2;             // last row that exists in xr
+    const float2 *col = p.xr + n;
+#pragma unroll
+    for (int j = 0; j < P - 1 + FI; j++) {
+        const long long row = (long long)t0 + j;
+        w[j] = (row <= last_row) ? __ldg(col + row * M) : cf(0.f, 0.f);
+    }
+    constexpr int QB = M >> 2;                                      // butterflies per frame and radix-4 pass
+    const int fi = n / QB, bq = n - fi * QB;                        // this thread's frame and butterfly in the radix-4 passes
+    float2 *wf = work + fi * WP;
+    __syncthreads();
+    for (int t = t0; t < t1; t += FI) {
+        // ---- polyphase filter: four frames from registers
+#pragma unroll
+        for (int f = 0; f < FI; f++) {
+            float2 acc = cf(0.f, 0.f);
+#pragma unroll
+            for (int k = 0; k < P; k++) ffma2(acc, hh[k], w[P - 1 + f - k]);
+            work[f * WP + n + (n >> 4)] = acc;
+        }
+        // shift the window by four frames and fetch the next four rows (they land while the DFT passes run)
+#pragma unroll
+        for (int j = 0; j < P - 1; j++) w[j] = w[j + FI];
+#pragma unroll
+        for (int f = 0; f < FI; f++) {
+            const long long row = (long long)t + FI + P - 1 + f;
+            w[P - 1 + f] = (row <= last_row && t + FI < t1) ? __ldg(col + row * M) : cf(0.f, 0.f);
+        }
+        __syncthreads();
+        // ---- DFT passes, in place (every block size a compile-time constant)
+        if constexpr (lm & 1) {
+            // radix-2: 4 frames x M/2 butterflies, two per thread
+#pragma unroll
+            for (int r = 0; r < 2; r++) {
+                const int e = n + r * M, f2 = e / (M >> 1), b = e - f2 * (M >> 1);
+                float2 *wr = work + f2 * WP;
+                const int i0 = b, i1 = b + (M >> 1);
+                const float2 a = wr[i0 + (i0 >> 4)], c = wr[i1 + (i1 >> 4)];
+                wr[i0 + (i0 >> 4)] = cf(a.x + c.x, a.y + c.y);
+                wr[i1 + (i1 >> 4)] = pfb_cmul(cf(a.x - c.x, a.y - c.y), stw[b]);
+            }
+            __syncthreads();
+            pfb_stream_passes<(M >> 1), M>(wf, stw + (M >> 1), bq);
+        } else {
+            pfb_stream_passes<M, M>(wf, stw, bq);
+        }
+        {
+            // last pass (N = 4, no twiddles): results go into the transposed output tile
+            const int base = bq * 4;
+            float2 x[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) { const int i = base + k; x[k] = wf[i + (i >> 4)]; }
+            {
+                const float2 a0 = cf(x[0].x + x[2].x, x[0].y + x[2].y), a1 = cf(x[0].x - x[2].x, x[0].y - x[2].y);
+                const float2 a2 = cf(x[1].x + x[3].x, x[1].y + x[3].y), a3 = cf(x[1].y - x[3].y, x[3].x - x[1].x);   // -j (x1 - x3)
+                x[0] = cf(a0.x + a2.x, a0.y + a2.y); x[1] = cf(a1.x + a3.x, a1.y + a3.y);
+                x[2] = cf(a0.x - a2.x, a0.y - a2.y); x[3] = cf(a1.x - a3.x, a1.y - a3.y);
+            }
+            const int my_t = t + fi;
+            if (my_t < t1) {
+                float2 *ob = obuf + ((my_t - t0) & (TF - 1)) * OR;
+#pragma unroll
+                for (int k = 0; k < 4; k++) { const int c = sperm[base + k]; ob[c + (c >> 4)] = x[k]; }
+            }
+        }
+        const int last = min(t + FI - 1, t1 - 1);                   // last frame parked so far
+        const int tfl = (last - t0) & (TF - 1);
+        if (tfl == TF - 1 || last == t1 - 1) {
+            __syncthreads();
+            const int cnt = tfl + 1, tb = last - tfl;               // frames parked in the tile, first of them
+            for (int e = n; e < M * TF; e += M) {
+                const int c = e >> 3, f = e & (TF - 1);
+                if (f < cnt) {
+                    const float2 v = obuf[f * OR + c + (c >> 4)];
+                    p.y[(long long)c * p.y_stride + tb + f] = v;
+                    if (p.pw) p.pw[(long long)c * p.pw_stride + tb + f] = pfb_power(v);
+                }
+            }
+        }
+        __syncthreads();          // work / obuf are rewritten by the next iteration
+    }
+}
+
 // keep the last (P-1)*M pre-rotated samples for the next call: dst[0..H) <- src[n .. n+H)
 __global__ void k_copy_tail(const float2 *__restrict__ src, float2 *__restrict__ dst, long long offset, int count)
 {

@@ -51,6 +51,8 @@ enum {
     CSDR_OPT_AGC_EXACT_MATH = 6,  /* 1: library expf/logf/atan2f in the AGC/discriminator loop instead of the SFU forms */
     CSDR_OPT_OVERLAP = 7,         /* 1: overlap the back end of part i with the front end of part i+1 (2 streams) */
     CSDR_OPT_DEBUG = 8,           /* 1: print AGC speculation diagnostics to stderr (synchronises) */
+    CSDR_OPT_PFB_VARIANT = 10,    /* channelizer kernel for M = 128..1024: 0 (default) one thread per polyphase branch, window in
+                                     registers; 1 the ring-buffer kernel (cross-check) */
     CSDR_OPT_FRONTEND_VARIANT = 9 /* front-end kernel for the standard half-band plan: 1 (default) raw tile by TMA tensor copy,
                                      read in place by the first half-band stage (3 CTAs/SM); 0 register prefetch + mixing
                                      pass (2 CTAs/SM); 2 as 1, warp-specialised (producer / consumer warp groups) */

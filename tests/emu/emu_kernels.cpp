@@ -258,6 +258,21 @@ extern "C" long long emu_pfb(int M, int kind, const float2 *x, long long nf_tota
             case 5: launch(k_pfb_tile<5>, g, b, smem, tp); break;
             default: return -1;
             }
+        } else if (kind == 3) {
+            PfbStreamParams sp{};
+            std::vector<unsigned short> pm(M);
+            pfb_stream_perm(M, pm.data());
+            sp.xr = xr.data(); sp.y = y + pos; sp.y_stride = nf_total; sp.nf = (int)nf; sp.M = M; sp.log2M = log2M;
+            sp.h = h.data(); sp.tw = tw.data(); sp.perm = pm.data();
+            sp.T = 3 * kPfbStTF;
+            const dim3 gs((unsigned)((nf + sp.T - 1) / sp.T)), bs(M);
+            switch (log2M) {
+            case 7: launch(k_pfb_stream<7>, gs, bs, pfb_stream_smem(M), sp); break;
+            case 8: launch(k_pfb_stream<8>, gs, bs, pfb_stream_smem(M), sp); break;
+            case 9: launch(k_pfb_stream<9>, gs, bs, pfb_stream_smem(M), sp); break;
+            case 10: launch(k_pfb_stream<10>, gs, bs, pfb_stream_smem(M), sp); break;
+            default: return -1;
+            }
         } else if (kind == 2) {
             PfbRingParams rp{};
             rp.xr = xr.data(); rp.y = y + pos; rp.y_stride = nf_total; rp.nf = (int)nf; rp.M = M; rp.log2M = log2M;
