@@ -124,7 +124,7 @@ void chain_init(csdr_chain_s *q)
         q->be.init(q->ctx, (int)q->C);
         q->left.ensure(sizeof(float2) * 2 * q->C);          // < C rotated left-over samples (+ a partial chunk appended)
     }
-    if (c.demod == CSDR_DEMOD_AM) q->am.init(q->ctx.stream, am_lanes, 0.8f, g_options[CSDR_OPT_AMPMODEM_PLL] != 0);
+    if (c.demod == CSDR_DEMOD_AM) { q->am.init(q->ctx.stream, am_lanes, 0.8f, g_options[CSDR_OPT_AMPMODEM_PLL] != 0); q->am.spec = g_options[CSDR_OPT_AM_PLL_SEQUENTIAL] == 0; }
     // wbFMDemodulator outBW decim (SoapySDR.hs:257): the quadrature rate is the resampler's output rate
     if (q->has_wb) q->wb.init(q->ctx, c.bandwidth_hz != 0.0 ? c.bandwidth_hz : c.samplerate, c.decim > 1 ? c.decim : 1, am_lanes);
     q->out_ptrs.resize((size_t)q->nstreams * q->nout);

@@ -1350,6 +1350,7 @@ csdr_ampmodem csdr_ampmodem_create(float mod_index, int type, int suppressed)
     if (type != 0 || suppressed != 0) throw CudaError{"ampmodem_create: only DSB with carrier (type 0, suppressed 0) is implemented"};
     std::unique_ptr<csdr_ampmodem_s> q(new csdr_ampmodem_s());
     q->am.init(q->ctx.stream, 1, mod_index, g_options[CSDR_OPT_AMPMODEM_PLL] != 0);
+    q->am.spec = g_options[CSDR_OPT_AM_PLL_SEQUENTIAL] == 0;
     CK(cudaStreamSynchronize(q->ctx.stream));
     return q.release();
     API_END(nullptr)

@@ -14,7 +14,7 @@ for row in csv.DictReader(lines):
     u = row["Metric Unit"]
     v = v / 1e3 if u in ("ns", "nsecond") else v * 1e3 if u in ("ms", "msecond") else v
     agg.setdefault(row["Kernel Name"], []).append(v)
-ours = {k: v for k, v in agg.items() if "csdr::" in k}
+ours = {k: v for k, v in agg.items() if "csdr::" in k or " k_" in (" " + k) or k.startswith("k_")}
 tot = sum(sum(v) for v in ours.values())
 if len(sys.argv) > 2:
     print("# " + sys.argv[2])
