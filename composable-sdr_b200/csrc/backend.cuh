@@ -521,8 +521,11 @@ __device__ __forceinline__ float2 be_emit_word(const BeEmitCtx &c, int u0, float
         } else if (l == 0) c.exb[wd] = ex;
         // The squelch can only be open on a sample that exceeds the threshold (every path into SIGNALHI takes the
         // "exceeded" branch of the state machine), so a word without such a sample is closed throughout: the gate pass
-        // writes its zeros (and the signed-zero artefacts next to an open sample) and nothing needs computing here.
-        if (c.skip_closed && ex == 0) return y;
+        // only has to fix the signed-zero artefact next to an open sample; zeros are written here.
+        if (c.skip_closed && ex == 0) {
+            if (in) { if (FM) c.of[u0 + l] = 0.f; else c.oc[u0 + l] = cf(0.f, 0.f); }
+            return y;
+        }
     }
     if (in) {
         if (FM) {
@@ -748,28 +751,31 @@ __global__ void __launch_bounds__(kAgcT, 4) k_agc_emit(const BackendParams p)
             const int eb = (s - wsteps) * kAgcB;
             const int ub0 = (seg0 + 32 * w) * L + eb;
             const float *srow = sm + (32 * w) * kAgcRow;
+            // (a word without a threshold-exceeding sample is closed throughout -- the squelch can only be open on a sample
+            // that exceeds the threshold: every path into SIGNALHI takes the "exceeded" branch of the state machine -- so it
+            // is written as zeros right here and the gate pass does not have to touch it)
             if (full_rows) {
                 if (FM) {
                     float *dst = of + ub0 + l;
 #pragma unroll 8
                     for (int i = 0; i < 32; i++, dst += L, srow += kAgcRow)
-                        if (!(skip_closed && __float_as_uint(srow[0]) == 0u)) *dst = srow[1 + l];
+                        *dst = (skip_closed && __float_as_uint(srow[0]) == 0u) ? 0.f : srow[1 + l];
                 } else {
                     float2 *dst = oc + ub0 + l;
                     const float2 *xr = s_x + (32 * w) * kAgcXRow + l;
 #pragma unroll 8
                     for (int i = 0; i < 32; i++, dst += L, srow += kAgcRow, xr += kAgcXRow)
-                        if (!(skip_closed && __float_as_uint(srow[0]) == 0u)) *dst = *xr;
+                        *dst = (skip_closed && __float_as_uint(srow[0]) == 0u) ? cf(0.f, 0.f) : *xr;
                 }
             } else {
                 int ub = ub0;
                 for (int i = 0; i < 32; i++, ub += L) {
                     const int row = 32 * w + i;
                     if (seg0 + row >= p.nseg || ub >= n) break;                                       // warp-uniform
-                    if (skip_closed && __float_as_uint(sm[row * kAgcRow]) == 0u) continue;            // warp-uniform
+                    const bool zero = skip_closed && __float_as_uint(sm[row * kAgcRow]) == 0u;        // warp-uniform
                     if (ub + l < n) {
-                        if (FM) of[ub + l] = sm[row * kAgcRow + 1 + l];
-                        else    oc[ub + l] = s_x[row * kAgcXRow + l];
+                        if (FM) of[ub + l] = zero ? 0.f : sm[row * kAgcRow + 1 + l];
+                        else    oc[ub + l] = zero ? cf(0.f, 0.f) : s_x[row * kAgcXRow + l];
                     }
                 }
             }
@@ -1102,7 +1108,7 @@ __global__ void __launch_bounds__(kFinT, 2) k_be_finish(const BackendParams p, i
                 const int runs_per_lane = (p.nwords + 31) / 32;
                 // (the words of the NEXT run are fetched before the current one is processed: the loop is a chain of
                 // dependent global loads otherwise)
-                struct Run { unsigned gw, fullw, gtop, srw, siw, srt, sit; int lane, wd0; bool have; };
+                struct Run { unsigned gw, fullw, gtop, srw, siw, srt, sit, exw; int lane, wd0; bool have; };
                 auto load_run = [&](long long item) {
                     Run r{};
                     r.lane = (int)(item / runs_per_lane); r.wd0 = (int)(item - (long long)r.lane * runs_per_lane) * 32;
@@ -1113,6 +1119,7 @@ __global__ void __launch_bounds__(kFinT, 2) k_be_finish(const BackendParams p, i
                     r.fullw = (cntw == 32) ? 0xffffffffu : ((1u << cntw) - 1u);
                     r.gw = r.have ? (gate[wd] & r.fullw) : 0u;
                     r.gtop = r.have ? (wd ? (gate[wd - 1] >> 31) : p.prev_gate[r.lane]) : 0u;
+                    r.exw = r.have ? p.exbits[(long long)r.lane * p.nwords + wd] : 0u;
                     if (p.demod == 1 && r.have) {
                         const unsigned *sr = p.sgnr + (long long)r.lane * p.nwords, *si = p.sgni + (long long)r.lane * p.nwords;
                         r.srw = sr[wd]; r.siw = si[wd];
@@ -1134,7 +1141,9 @@ __global__ void __launch_bounds__(kFinT, 2) k_be_finish(const BackendParams p, i
                     // words that need no write (open throughout, predecessor open) are skipped; words that are closed
                     // throughout (the bulk of a squelched stream) take a short path: one coalesced store of zeros
                     const unsigned gprevw = (gw << 1) | gtop;
-                    const bool need = have && (p.demod == 1 ? ((gw & gprevw & fullw) != fullw) : (gw != fullw));
+                    // (words without a threshold-exceeding sample were written as zeros by the emission already)
+                    const bool zeroed = cur.exw == 0u && gw == 0u && (p.demod != 1 || gtop == 0u);
+                    const bool need = have && !zeroed && (p.demod == 1 ? ((gw & gprevw & fullw) != fullw) : (gw != fullw));
                     const bool closed = have && cntw == 32 && gw == 0 && (p.demod != 1 || gtop == 0);
                     const unsigned m_closed = __ballot_sync(0xffffffffu, closed);
                     for (unsigned m = __ballot_sync(0xffffffffu, need); m; m &= m - 1) {

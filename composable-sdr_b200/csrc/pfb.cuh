@@ -173,8 +173,11 @@ __global__ void __launch_bounds__(kPfbTileF) k_pfb_tile(const CSDR_GRID_CONSTANT
 #pragma unroll
         for (int j = 0; j < M / 2; j++) {
             const float4 q = row[j];
-            ffma2(a[2 * j], p.h[k * M + 2 * j], cf(q.x, q.y));
-            ffma2(a[2 * j + 1], p.h[k * M + 2 * j + 1], cf(q.z, q.w));
+            // (scalar FMAs take the tap straight from the constant bank; the packed form needs it copied into a register
+            // pair first: three instructions instead of two)
+            const float h0 = p.h[k * M + 2 * j], h1 = p.h[k * M + 2 * j + 1];
+            a[2 * j].x = fmaf(h0, q.x, a[2 * j].x); a[2 * j].y = fmaf(h0, q.y, a[2 * j].y);
+            a[2 * j + 1].x = fmaf(h1, q.z, a[2 * j + 1].x); a[2 * j + 1].y = fmaf(h1, q.w, a[2 * j + 1].y);
         }
     }
     // M-point forward DFT, radix-2 decimation in time
