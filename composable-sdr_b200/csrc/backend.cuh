@@ -77,8 +77,18 @@ struct BackendParams {
 // ------------------------------------------------------------------------------------------ dc blocker
 // v[n] = x[n] + c v[n-1] (c = 1 - alpha), y[n] = v[n] - v[n-1]: a linear recurrence, evaluated in fp64 as affine maps
 // (k_dc_scan below); the float32 recurrence of iirfilt then runs over G/32 samples per lane from the exact state.
-constexpr int kDcGB = 64;
-constexpr int kDcWarps = 8;
+#ifndef CSDR_DC_GB          // block-geometry experiments (scripts/exp_build.sh): groups per block, warps and CTAs per SM
+#define CSDR_DC_GB 64
+#endif
+#ifndef CSDR_DC_WARPS
+#define CSDR_DC_WARPS 8
+#endif
+#ifndef CSDR_DC_MINB
+#define CSDR_DC_MINB 2
+#endif
+constexpr int kDcGB = CSDR_DC_GB;
+constexpr int kDcWarps = CSDR_DC_WARPS;
+constexpr int kDcMinB = CSDR_DC_MINB;
 
 struct DcParams {
     const float2 *in; long long in_lane_stride;
@@ -153,7 +163,7 @@ __device__ __forceinline__ double dc_pow32(const double (&cS)[5], int e)
 // Each sample is read once and written once; nothing else travels through HBM.  out may alias in.
 constexpr size_t kDcSmem = sizeof(float2) * kDcGB * 128;       // the staged block (G <= 128)
 template <int S>
-__global__ void __launch_bounds__(32 * kDcWarps, 2) k_dc_scan(const DcParams p)
+__global__ void __launch_bounds__(32 * kDcWarps, kDcMinB) k_dc_scan(const DcParams p)
 {
     constexpr int GW = kDcGB / kDcWarps;               // groups per warp
     CSDR_DYN_SMEM(smem_raw);

@@ -539,7 +539,7 @@ struct Backend {
         d.agg = dc_agg.as<SelfValid16>(); d.ticket = dc_ticket.as<unsigned>();
         d.dc_in = dc_state[dc_cur].as<float2>(); d.dc_out = dc_state[dc_cur ^ 1].as<float2>();
         dc_cur ^= 1;
-        be_launch_dc(l, d, 2 * sms);
+        be_launch_dc(l, d, kDcMinB * sms);
     }
     // dc blocker only, out may alias in
     // rot: also multiply by the conjugate NCO phasor (theta0 + i * dtheta), the channelizer's pre-rotation

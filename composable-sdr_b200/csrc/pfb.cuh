@@ -144,6 +144,25 @@ template <int LM> __host__ __device__ constexpr int pfb_rev(int i)
     return r;
 }
 
+// Radix-2 DIT butterflies of an M-point DFT held in registers, every index a template constant: butterfly i of stage s,
+// then the next one (the nested-loop form was left partly rolled by the compiler, which then indexed the register array
+// through chains of predicated moves: 28 % of the kernel's instructions).  Twiddles 1 and -j cost no multiplication.
+template <int LM, int s, int i>
+__device__ __forceinline__ void pfb_dit_bf(float2 (&b)[1 << LM], const float2 *__restrict__ tw)
+{
+    constexpr int M = 1 << LM, half = 1 << (s - 1), j = i & (half - 1), lo = ((i >> (s - 1)) << s) + j, hi = lo + half;
+    constexpr int t = j * (M >> s);                        // twiddle exp(-j 2 pi t / M)
+    const float2 u = b[lo], v = b[hi];
+    float2 r;
+    if constexpr (t == 0) r = v;
+    else if constexpr (4 * t == M) r = cf(v.y, -v.x);
+    else { const float2 w = tw[t]; r = cf(v.x * w.x - v.y * w.y, v.x * w.y + v.y * w.x); }
+    b[lo] = cf(u.x + r.x, u.y + r.y);
+    b[hi] = cf(u.x - r.x, u.y - r.y);
+    if constexpr (i + 1 < M / 2) pfb_dit_bf<LM, s, i + 1>(b, tw);
+    else if constexpr (s < LM) pfb_dit_bf<LM, s + 1, 0>(b, tw);
+}
+
 template <int LM>
 __global__ void __launch_bounds__(kPfbTileF) k_pfb_tile(const CSDR_GRID_CONSTANT PfbTileParams p)
 {
@@ -184,21 +203,7 @@ __global__ void __launch_bounds__(kPfbTileF) k_pfb_tile(const CSDR_GRID_CONSTANT
     float2 b[M];
 #pragma unroll
     for (int i = 0; i < M; i++) b[i] = a[pfb_rev<LM>(i)];
-#pragma unroll
-    for (int s = 1; s <= LM; s++) {
-        const int len = 1 << s, half = len >> 1, tws = M / len;
-#pragma unroll
-        for (int grp = 0; grp < M; grp += len) {
-#pragma unroll
-            for (int j = 0; j < half; j++) {
-                const float2 w = p.tw[j * tws];
-                const float2 u = b[grp + j], v = b[grp + j + half];
-                const float tr = v.x * w.x - v.y * w.y, ti = v.x * w.y + v.y * w.x;
-                b[grp + j] = cf(u.x + tr, u.y + ti);
-                b[grp + j + half] = cf(u.x - tr, u.y - ti);
-            }
-        }
-    }
+    pfb_dit_bf<LM, 1, 0>(b, p.tw);
     float2 *yo = p.y + t0 + f;
 #pragma unroll
     for (int c = 0; c < M; c++) yo[(long long)c * p.y_stride] = b[c];
