@@ -78,13 +78,13 @@ struct BackendParams {
 // v[n] = x[n] + c v[n-1] (c = 1 - alpha), y[n] = v[n] - v[n-1]: a linear recurrence, evaluated in fp64 as affine maps
 // (k_dc_scan below); the float32 recurrence of iirfilt then runs over G/32 samples per lane from the exact state.
 #ifndef CSDR_DC_GB          // block-geometry experiments (scripts/exp_build.sh): groups per block, warps and CTAs per SM
-#define CSDR_DC_GB 64
+#define CSDR_DC_GB 8
 #endif
 #ifndef CSDR_DC_WARPS
-#define CSDR_DC_WARPS 8
+#define CSDR_DC_WARPS 2
 #endif
 #ifndef CSDR_DC_MINB
-#define CSDR_DC_MINB 2
+#define CSDR_DC_MINB 8
 #endif
 constexpr int kDcGB = CSDR_DC_GB;
 constexpr int kDcWarps = CSDR_DC_WARPS;
@@ -150,16 +150,25 @@ __device__ __forceinline__ double dc_pow32(const double (&cS)[5], int e)
     return r;
 }
 
-// One pass over the samples: a CTA takes blocks of kDcGB groups (8192 samples at G = 128) in stream order (ticket).
+// One pass over the samples: a CTA takes blocks of kDcGB groups (1024 samples at G = 128) in stream order (ticket).
+// Small CTAs (two warps, eight per SM): the block-wide steps below are separated by barriers that idle the whole CTA, so
+// many small CTAs overlap them better than a few large ones (measured per 2^27 samples: 64 groups x 8 warps 540 us,
+// 16 x 4 503 us, 8 x 2 472 us).
 //   0. The block arrives in shared memory by ONE bulk copy (cp.async.bulk, mbarrier completion) issued while the previous
 //      block is still being worked on: no registers, no load instructions, HBM latency hidden.
 //   1. Every lane takes its 4 consecutive samples, a float32 warp scan gives each lane the zero-state response up to its
-//      samples (kept in registers) and the group's total; the totals of the block's 64 groups are combined in fp64 and
+//      samples (kept in registers) and the group's total; the totals of the block's groups are combined in fp64 and
 //      the block's zero-state response is published (a self-validating 16-byte value: no flag, no fence).
 //   2. Look-back: the filter state before the block is  sum_k AB^(k-1) agg[b-k]  (+ AB^b x the state carried from the
-//      previous call), AB = c^8192 = 0.017 for alpha = 5e-4, so `depth` = 7 predecessors settle it to 1e-13.
+//      previous call), AB = c^1024 = 0.60 for alpha = 5e-4, so `depth` = 59 predecessors settle it to 1e-13 (one
+//      16-byte load per thread, all in flight at once).
 //   3. Every lane gets the exact state before its samples, runs iirfilt's float32 recurrence over them and writes the
 //      dc-blocked samples (optionally pre-rotated for the channelizer) and their power.
+// The loop is software-pipelined over two blocks: steps 0-1 of the CTA's NEXT block run before steps 2-3 of the current
+// one, so every block's response has been published a whole block time before anybody looks back for it (with the steps
+// in order the CTAs fall into lock-step with the slowest of their seven predecessors: 26 % of the kernel's time, measured
+// by taking the wait out).  Both blocks' samples stay in registers; the one staging tile is refilled for the block after
+// next while the scan and the output pass run.
 // Each sample is read once and written once; nothing else travels through HBM.  out may alias in.
 constexpr size_t kDcSmem = sizeof(float2) * kDcGB * 128;       // the staged block (G <= 128)
 template <int S>
@@ -168,7 +177,7 @@ __global__ void __launch_bounds__(32 * kDcWarps, kDcMinB) k_dc_scan(const DcPara
     constexpr int GW = kDcGB / kDcWarps;               // groups per warp
     CSDR_DYN_SMEM(smem_raw);
     float2 *tile = reinterpret_cast<float2 *>(smem_raw);
-    __shared__ double sr[kDcGB], si[kDcGB];            // zero-state response at the END of each group, block-local
+    __shared__ double sr[2][kDcGB], si[2][kDcGB];      // zero-state response at the END of each group, block-local (current / next block)
     __shared__ double s_red[2][kDcWarps];
     __shared__ double s_cr, s_ci;
     __shared__ int s_ticket;
@@ -188,17 +197,12 @@ __global__ void __launch_bounds__(32 * kDcWarps, kDcMinB) k_dc_scan(const DcPara
         return (long long)(bb + 1) * blk <= p.n && (reinterpret_cast<uintptr_t>(block_src(tkk)) & 15) == 0;
     };
     unsigned parity = 0;
-    if (t == 0) { bulk_init(&s_bar); s_ticket = (int)atomicAdd(p.ticket, 1u); }
-    __syncthreads();
-    int tk = s_ticket;
-    if (t == 0 && tk < total && block_bulk(tk)) bulk_copy_g2s(tile, block_src(tk), (unsigned)(blk * sizeof(float2)), &s_bar);
-    __syncthreads();
-    while (tk < total) {
-        const int lane = tk / p.nblk, b = tk - lane * p.nblk;
-        const bool bulk = block_bulk(tk);
-        // ---- 0. samples into registers
-        float2 v[GW][S];
-        if (bulk) {
+    // ---- 0. samples of block tkk into registers (from the staged tile, or straight from global memory)
+    auto load_block = [&](int tkk, float2 (&v)[GW][S]) {
+#ifdef CSDR_EMU
+        __syncthreads();                                    // the emulated bulk copy is a memcpy by thread 0
+#endif
+        if (block_bulk(tkk)) {
             bulk_wait(&s_bar, parity); parity ^= 1u;
 #pragma unroll
             for (int k = 0; k < GW; k++) {
@@ -208,6 +212,7 @@ __global__ void __launch_bounds__(32 * kDcWarps, kDcMinB) k_dc_scan(const DcPara
                 if (S == 1) v[k][0] = tile[(w * GW + k) * p.G + l];
             }
         } else {
+            const int lane = tkk / p.nblk, b = tkk - lane * p.nblk;
             const float2 *__restrict__ xx = p.in + (long long)lane * p.in_lane_stride;
 #pragma unroll
             for (int k = 0; k < GW; k++) {
@@ -215,12 +220,9 @@ __global__ void __launch_bounds__(32 * kDcWarps, kDcMinB) k_dc_scan(const DcPara
                 dc_load<S>(xx, (j < p.ngrp) ? p.n : 0, j * p.G + l * S, v[k]);
             }
         }
-        if (t == 0) s_ticket = (int)atomicAdd(p.ticket, 1u);
-        __syncthreads();                                    // the staged block has been read by everybody
-        const int tk_next = s_ticket;
-        if (t == 0 && tk_next < total && block_bulk(tk_next)) bulk_copy_g2s(tile, block_src(tk_next), (unsigned)(blk * sizeof(float2)), &s_bar);
-        // ---- 1. scan (float32 inside a group, fp64 across groups)
-        float er[GW], ei[GW];                               // zero-state response BEFORE this lane's samples, per group
+    };
+    // ---- 1. scan of a block held in registers (float32 inside a group, fp64 across groups); publishes its response
+    auto scan_block = [&](int tkk, const float2 (&v)[GW][S], float (&er)[GW], float (&ei)[GW], double *srb, double *sib) {
         double Rr = 0.0, Ri = 0.0;                          // zero-state response of this warp's run of groups
 #pragma unroll
         for (int k = 0; k < GW; k++) {
@@ -232,7 +234,7 @@ __global__ void __launch_bounds__(32 * kDcWarps, kDcMinB) k_dc_scan(const DcPara
             if (l == 0) { er[k] = 0.f; ei[k] = 0.f; }
             const float Tr = __shfl_sync(0xffffffffu, ar, 31), Ti = __shfl_sync(0xffffffffu, ai, 31);
             Rr = Rr * A + (double)Tr; Ri = Ri * A + (double)Ti;
-            if (l == 0) { sr[w * GW + k] = Rr; si[w * GW + k] = Ri; }
+            if (l == 0) { srb[w * GW + k] = Rr; sib[w * GW + k] = Ri; }
         }
         __syncthreads();
         double vr = 0.0, vi = 0.0;
@@ -242,20 +244,60 @@ __global__ void __launch_bounds__(32 * kDcWarps, kDcMinB) k_dc_scan(const DcPara
             double pr = 0.0, pi = 0.0;
             for (int q = 0; q < tw; q++) {
                 const double a = p.powA[GW * (tw - 1 - q)];
-                pr += sr[q * GW + GW - 1] * a; pi += si[q * GW + GW - 1] * a;
+                pr += srb[q * GW + GW - 1] * a; pi += sib[q * GW + GW - 1] * a;
             }
             const double a = p.powA[tkk2 + 1];
-            vr = sr[t] + pr * a; vi = si[t] + pi * a;
+            vr = srb[t] + pr * a; vi = sib[t] + pi * a;
         }
         __syncthreads();
-        if (t < kDcGB) { sr[t] = vr; si[t] = vi; }
-        if (t == kDcGB - 1) sv16_store(p.agg + tk, vr, vi);
+        if (t < kDcGB) { srb[t] = vr; sib[t] = vi; }
+        if (t == kDcGB - 1) sv16_store(p.agg + tkk, vr, vi);
+    };
+    // the staged tile has been read by everybody: take the next ticket and start its copy
+    auto next_ticket = [&]() {
+        if (t == 0) s_ticket = (int)atomicAdd(p.ticket, 1u);
+        __syncthreads();
+        const int tkk = s_ticket;
+        if (t == 0 && tkk < total && block_bulk(tkk)) bulk_copy_g2s(tile, block_src(tkk), (unsigned)(blk * sizeof(float2)), &s_bar);
+        return tkk;
+    };
+
+    if (t == 0) bulk_init(&s_bar);
+    __syncthreads();
+    int tk = next_ticket();
+    float2 v[GW][S];
+    float er[GW], ei[GW];
+    int cb = 0;                                               // which half of sr / si belongs to the current block
+    int tk_next = total;
+    if (tk < total) {
+        load_block(tk, v);
+        __syncthreads();                                      // (s_ticket has been read by everybody)
+        tk_next = next_ticket();
+        scan_block(tk, v, er, ei, sr[0], si[0]);
+    }
+    while (tk < total) {
+        const int lane = tk / p.nblk, b = tk - lane * p.nblk;
+        const bool bulk = block_bulk(tk);
+        // ---- steps 0-1 of the next block
+        float2 vn[GW][S];
+        float ern[GW], ein[GW];
+        int tk_next2 = total;
+        if (tk_next < total) {
+            load_block(tk_next, vn);
+            __syncthreads();
+            tk_next2 = next_ticket();
+            scan_block(tk_next, vn, ern, ein, sr[cb ^ 1], si[cb ^ 1]);
+        }
         // ---- 2. look back (thread k waits for block b - 1 - k, b - 1 - k - 256, ...)
         double cr = 0.0, ci = 0.0;
         for (int k = t; k < p.depth && k < b; k += blockDim.x) {
             const int src = tk - 1 - k;
             double ax, ay;
+#if defined(CSDR_DC_SKIP) && (CSDR_DC_SKIP & 2)
+            sv16_load(p.agg + src, ax, ay);
+#else
             while (!sv16_load(p.agg + src, ax, ay)) {}
+#endif
             const double m = p.powAB[k];
             cr += ax * m; ci += ay * m;
         }
@@ -265,7 +307,7 @@ __global__ void __launch_bounds__(32 * kDcWarps, kDcMinB) k_dc_scan(const DcPara
             for (int d = 16; d >= 1; d >>= 1) { cr += __shfl_xor_sync(0xffffffffu, cr, d); ci += __shfl_xor_sync(0xffffffffu, ci, d); }
         }
         if (l == 0) { s_red[0][w] = cr; s_red[1][w] = ci; }
-        __syncthreads();
+        __syncthreads();                                    // (also: sr / si of the current block are complete)
         if (t == 0) {
             double a = 0.0, bb = 0.0;
             for (int q = 0; q < kDcWarps; q++) { a += s_red[0][q]; bb += s_red[1][q]; }
@@ -273,6 +315,7 @@ __global__ void __launch_bounds__(32 * kDcWarps, kDcMinB) k_dc_scan(const DcPara
         }
         __syncthreads();
         const double carry_r = s_cr, carry_i = s_ci;
+        const double *srb = sr[cb], *sib = si[cb];
         // ---- 3. apply
         float2 *__restrict__ yo = p.out ? p.out + (long long)lane * p.out_lane_stride : nullptr;
         float *__restrict__ wo = p.pw ? p.pw + (long long)lane * p.pw_stride : nullptr;
@@ -283,7 +326,7 @@ __global__ void __launch_bounds__(32 * kDcWarps, kDcMinB) k_dc_scan(const DcPara
             const int i0 = j * p.G + l * S;
             // state before group j (fp64), then before this lane's samples
             const double pa = p.powA[jl];
-            const double Vr = (jl ? sr[jl - 1] : 0.0) + carry_r * pa, Vi = (jl ? si[jl - 1] : 0.0) + carry_i * pa;
+            const double Vr = (jl ? srb[jl - 1] : 0.0) + carry_r * pa, Vi = (jl ? sib[jl - 1] : 0.0) + carry_i * pa;
             float v1r = (float)((double)er[k] + Vr * ql), v1i = (float)((double)ei[k] + Vi * ql);
 #pragma unroll
             for (int q = 0; q < S; q++) {
@@ -296,7 +339,11 @@ __global__ void __launch_bounds__(32 * kDcWarps, kDcMinB) k_dc_scan(const DcPara
             }
             // the lane that holds the chunk's last sample stores the filter state for the next call
             if (i0 < p.n && i0 + S >= p.n) p.dc_out[lane] = cf(v1r, v1i);
+#if defined(CSDR_DC_SKIP) && (CSDR_DC_SKIP & 1)
+            if (false) {
+#else
             if (p.rot) {
+#endif
                 // the channelizer's pre-rotation (nco_crcf_mix_block_down, Liquid.chs:847) rides on this pass
 #pragma unroll
                 for (int q = 0; q < S; q++) {
@@ -304,7 +351,11 @@ __global__ void __launch_bounds__(32 * kDcWarps, kDcMinB) k_dc_scan(const DcPara
                     v[k][q] = cf(v[k][q].x * ph.x + v[k][q].y * ph.y, v[k][q].y * ph.x - v[k][q].x * ph.y);
                 }
             }
+#if defined(CSDR_DC_SKIP) && (CSDR_DC_SKIP & 4)
+            if (yo && v[k][0].x == 1.2345e-30f) {
+#else
             if (yo) {
+#endif
                 float2 *y = yo + i0;
                 if (S == 4 && (bulk || i0 + S <= p.n) && (reinterpret_cast<uintptr_t>(y) & 15) == 0) {
                     reinterpret_cast<float4 *>(y)[0] = make_float4(v[k][0].x, v[k][0].y, v[k][1 % S].x, v[k][1 % S].y);
@@ -326,8 +377,15 @@ __global__ void __launch_bounds__(32 * kDcWarps, kDcMinB) k_dc_scan(const DcPara
                 }
             }
         }
-        __syncthreads();      // sr / si / s_ticket are reused by the next block
-        tk = tk_next;
+        __syncthreads();      // s_red / s_cr and this block's half of sr / si are reused
+        // the next block becomes the current one
+#pragma unroll
+        for (int k = 0; k < GW; k++) {
+            er[k] = ern[k]; ei[k] = ein[k];
+#pragma unroll
+            for (int q = 0; q < S; q++) v[k][q] = vn[k][q];
+        }
+        tk = tk_next; tk_next = tk_next2; cb ^= 1;
     }
     // tickets for the next launch: reset by the last CTA to leave
     if (t == 0) {
