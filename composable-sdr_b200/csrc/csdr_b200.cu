@@ -723,7 +723,7 @@ struct Channelizer {
         if (smem > 200 * 1024) throw CudaError{"firpfbch: channel count too large for one CTA tile"};
         raise_dyn_smem(k_pfb, smem);
         tile_kernel = nullptr;
-        if (!over2 && log2M >= 1 && (int)M <= kPfbTileMaxM && (int)P == kPfbTileP) {
+        if (log2M >= (over2 ? 2 : 1) && (int)M <= kPfbTileMaxM && (int)P == kPfbTileP) {
             switch (log2M) {
             case 1: tile_kernel = k_pfb_tile<1>; break;
             case 2: tile_kernel = k_pfb_tile<2>; break;
@@ -744,7 +744,7 @@ struct Channelizer {
             CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ring_ctas, ring_kernel, 2 * (int)M / kPfbRingCPT, pfb_ring_smem((int)M, log2M)));
             if (ring_ctas < 1) ring_ok = false;
         }
-        stream_ok = !over2 && log2M >= 7 && M <= 1024 && (int)P == kPfbStP && g_options[CSDR_OPT_PFB_VARIANT] == 0;
+        stream_ok = log2M >= 7 && M <= 1024 && (int)P == kPfbStP && (over2 || g_options[CSDR_OPT_PFB_VARIANT] == 0);
         if (stream_ok) {
             std::vector<unsigned short> pm(M);
             pfb_stream_perm((int)M, pm.data());
@@ -786,32 +786,45 @@ struct Channelizer {
         p.h = hd.as<float>(); p.tw = tw.as<float2>();
         p.hop = (int)hop(); p.over2 = over2 ? 1 : 0; p.parity0 = (int)(frames_done & 1); p.scale = 1.0f / (float)M;
         frames_done += (unsigned long long)nf;
-        if (stream_ok) {
-            PfbStreamParams sp{};
-            sp.xr = p.xr; sp.y = y; sp.y_stride = y_stride; sp.pw = pw; sp.pw_stride = pw_stride; sp.nf = nf; sp.M = (int)M; sp.log2M = log2M;
-            sp.h = hd.as<float>(); sp.tw = tw.as<float2>(); sp.perm = perm.as<unsigned short>();
-            // one wave of CTAs where possible: frames per CTA = nf / (SMs * CTAs per SM), in whole output tiles
-            const int slots = std::max(1, c.sms * stream_ctas);
-            int T = (nf + slots - 1) / slots;
-            T = std::max(2 * kPfbStTF, (T + kPfbStTF - 1) / kPfbStTF * kPfbStTF);
-            sp.T = T;
-            launch(stream_kernel, dim3((nf + T - 1) / T), dim3(M), pfb_stream_smem((int)M), c.stream, sp);
-        } else if (ring_ok) {
-            PfbRingParams rp{};
-            rp.xr = p.xr; rp.y = y; rp.y_stride = y_stride; rp.nf = nf; rp.M = (int)M; rp.log2M = log2M;
-            rp.pw = pw; rp.pw_stride = pw_stride;
-            rp.h = hd.as<float>(); rp.tw = tw.as<float2>();
-            // one wave of CTAs where possible: frames per CTA = nf / (SMs * CTAs per SM), in whole output tiles
-            const int slots = std::max(1, c.sms * ring_ctas);
-            int T = (nf + slots - 1) / slots;
-            T = std::max(2 * kPfbRingTF, (T + kPfbRingTF - 1) / kPfbRingTF * kPfbRingTF);
-            rp.T = T;
-            launch(ring_kernel, dim3((nf + T - 1) / T), dim3(2 * M / kPfbRingCPT), pfb_ring_smem((int)M, log2M), c.stream, rp);
-        } else if (tile_kernel) {
-            tp.xr = p.xr; tp.y = y; tp.y_stride = y_stride; tp.nf = nf; tp.pw = pw; tp.pw_stride = pw_stride;
-            launch(tile_kernel, dim3((nf + kPfbTileF - 1) / kPfbTileF), dim3(kPfbTileF), tile_smem, c.stream, tp);
-        } else {
-            launch(k_pfb, dim3((nf + F - 1) / F), dim3(256), smem, c.stream, p);
+        // firpfbch2 on the fast kernels: its even frames are the critically sampled filterbank on xr, its odd frames the same
+        // filterbank on xr + M/2 (window of frame t starts at t M/2); two passes, output columns interleaved, and the sign
+        // (-1)^(c t) of the per-channel factor is constant within a pass
+        const int npass = (over2 && (stream_ok || tile_kernel)) ? 2 : 1;
+        for (int e = 0; e < npass; e++) {
+            const int nfp = npass == 2 ? (nf - e + 1) / 2 : nf;
+            if (nfp <= 0) continue;
+            const float2 *xin = p.xr + (npass == 2 ? (size_t)e * (M / 2) : 0);
+            const int ocs = npass, oco = e, o2 = npass == 2 ? 1 : 0;
+            const float sc_even = p.scale, sc_odd = ((p.parity0 + e) & 1) ? -p.scale : p.scale;
+            if (stream_ok) {
+                PfbStreamParams sp{};
+                sp.xr = xin; sp.y = y; sp.y_stride = y_stride; sp.pw = pw; sp.pw_stride = pw_stride; sp.nf = nfp; sp.M = (int)M; sp.log2M = log2M;
+                sp.h = hd.as<float>(); sp.tw = tw.as<float2>(); sp.perm = perm.as<unsigned short>();
+                sp.ocs = ocs; sp.oco = oco; sp.over2 = o2; sp.sc_even = sc_even; sp.sc_odd = sc_odd;
+                // one wave of CTAs where possible: frames per CTA = nf / (SMs * CTAs per SM), in whole output tiles
+                const int slots = std::max(1, c.sms * stream_ctas);
+                int T = (nfp + slots - 1) / slots;
+                T = std::max(2 * kPfbStTF, (T + kPfbStTF - 1) / kPfbStTF * kPfbStTF);
+                sp.T = T;
+                launch(stream_kernel, dim3((nfp + T - 1) / T), dim3(M), pfb_stream_smem((int)M), c.stream, sp);
+            } else if (ring_ok) {
+                PfbRingParams rp{};
+                rp.xr = p.xr; rp.y = y; rp.y_stride = y_stride; rp.nf = nf; rp.M = (int)M; rp.log2M = log2M;
+                rp.pw = pw; rp.pw_stride = pw_stride;
+                rp.h = hd.as<float>(); rp.tw = tw.as<float2>();
+                // one wave of CTAs where possible: frames per CTA = nf / (SMs * CTAs per SM), in whole output tiles
+                const int slots = std::max(1, c.sms * ring_ctas);
+                int T = (nf + slots - 1) / slots;
+                T = std::max(2 * kPfbRingTF, (T + kPfbRingTF - 1) / kPfbRingTF * kPfbRingTF);
+                rp.T = T;
+                launch(ring_kernel, dim3((nf + T - 1) / T), dim3(2 * M / kPfbRingCPT), pfb_ring_smem((int)M, log2M), c.stream, rp);
+            } else if (tile_kernel) {
+                tp.xr = xin; tp.y = y; tp.y_stride = y_stride; tp.nf = nfp; tp.pw = pw; tp.pw_stride = pw_stride;
+                tp.ocs = ocs; tp.oco = oco; tp.over2 = o2; tp.sc_even = sc_even; tp.sc_odd = sc_odd;
+                launch(tile_kernel, dim3((nfp + kPfbTileF - 1) / kPfbTileF), dim3(kPfbTileF), tile_smem, c.stream, tp);
+            } else {
+                launch(k_pfb, dim3((nf + F - 1) / F), dim3(256), smem, c.stream, p);
+            }
         }
         int H = (int)hist_samples();
         xr[cur ^ 1].ensure((size_t)H * sizeof(float2));

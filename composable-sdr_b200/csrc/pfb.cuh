@@ -133,6 +133,9 @@ constexpr int kPfbTileMaxM = 32;
 struct PfbTileParams {
     const float2 *xr; float2 *y; long long y_stride; int nf;
     float *pw; long long pw_stride;        // optional: |y|^2, same layout
+    int ocs, oco;                          // frame f is output column f * ocs + oco (firpfbch2: the even / odd frames of the
+                                           // half-frame hop are two critically sampled passes, ocs = 2)
+    int over2; float sc_even, sc_odd;      // firpfbch2: y[c] *= exp(-j 2 pi c / M) * (c even ? sc_even : sc_odd)
     float2 tw[kPfbTileMaxM / 2];           // exp(-j 2 pi t / M)
     float h[kPfbTileP * kPfbTileMaxM];     // h[k * M + n] = prototype[(M - 1 - n) + k * M]
 };
@@ -204,11 +207,22 @@ __global__ void __launch_bounds__(kPfbTileF) k_pfb_tile(const CSDR_GRID_CONSTANT
 #pragma unroll
     for (int i = 0; i < M; i++) b[i] = a[pfb_rev<LM>(i)];
     pfb_dit_bf<LM, 1, 0>(b, p.tw);
-    float2 *yo = p.y + t0 + f;
+    if (p.over2) {
+        // firpfbch2: the analyzer's backward DFT over the window slots and its alternating commutator are a per-channel
+        // factor of the forward DFT (closed form at the top of the firpfbch2 section); W^(c + M/2) = -W^c
+#pragma unroll
+        for (int c = 0; c < M; c++) {
+            const float2 w = p.tw[c & (M / 2 - 1)];
+            const float sc = ((c & 1) ? p.sc_odd : p.sc_even) * ((M > 1 && c >= M / 2) ? -1.f : 1.f);
+            b[c] = cf((b[c].x * w.x - b[c].y * w.y) * sc, (b[c].x * w.y + b[c].y * w.x) * sc);
+        }
+    }
+    const long long col = (long long)(t0 + f) * p.ocs + p.oco;
+    float2 *yo = p.y + col;
 #pragma unroll
     for (int c = 0; c < M; c++) yo[(long long)c * p.y_stride] = b[c];
     if (p.pw) {
-        float *po = p.pw + t0 + f;
+        float *po = p.pw + col;
 #pragma unroll
         for (int c = 0; c < M; c++) po[(long long)c * p.pw_stride] = pfb_power(b[c]);
     }
@@ -406,6 +420,8 @@ struct PfbStreamParams {
     const float *h;                        // prototype, P*M taps
     const float2 *tw;                      // M twiddles exp(-j 2 pi t / M)
     const unsigned short *perm;            // [M] frequency held by position p behind the DIF passes
+    int ocs, oco;                          // frame f is output column f * ocs + oco (firpfbch2: two passes, ocs = 2)
+    int over2; float sc_even, sc_odd;      // firpfbch2: y[c] *= exp(-j 2 pi c / M) * (c even ? sc_even : sc_odd)
 };
 inline size_t pfb_stream_wp(int M) { return (size_t)M + ((size_t)M >> 4); }
 inline size_t pfb_stream_orow(int M) { return (size_t)M + ((size_t)M >> 4) + 2; }
@@ -561,9 +577,15 @@ __global__ void __launch_bounds__(1 << LM, 1) k_pfb_stream(const PfbStreamParams
             for (int e = n; e < M * TF; e += M) {
                 const int c = e >> 3, f = e & (TF - 1);
                 if (f < cnt) {
-                    const float2 v = obuf[f * OR + c + (c >> 4)];
-                    p.y[(long long)c * p.y_stride + tb + f] = v;
-                    if (p.pw) p.pw[(long long)c * p.pw_stride + tb + f] = pfb_power(v);
+                    float2 v = obuf[f * OR + c + (c >> 4)];
+                    if (p.over2) {
+                        const float2 w = __ldg(p.tw + c);
+                        const float sc = (c & 1) ? p.sc_odd : p.sc_even;
+                        v = cf((v.x * w.x - v.y * w.y) * sc, (v.x * w.y + v.y * w.x) * sc);
+                    }
+                    const long long col = (long long)(tb + f) * p.ocs + p.oco;
+                    p.y[(long long)c * p.y_stride + col] = v;
+                    if (p.pw) p.pw[(long long)c * p.pw_stride + col] = pfb_power(v);
                 }
             }
         }

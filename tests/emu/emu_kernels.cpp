@@ -245,7 +245,7 @@ extern "C" long long emu_pfb(int M, int kind, const float2 *x, long long nf_tota
         theta += (unsigned)(nf * M) * dth;
         if (kind == 1) {
             PfbTileParams tp{};
-            tp.xr = xr.data(); tp.y = y + pos; tp.y_stride = nf_total; tp.nf = (int)nf;
+            tp.xr = xr.data(); tp.y = y + pos; tp.y_stride = nf_total; tp.nf = (int)nf; tp.ocs = 1;
             for (int i = 0; i < M / 2; i++) tp.tw[i] = tw[i];
             for (int k = 0; k < P; k++) for (int n = 0; n < M; n++) tp.h[k * M + n] = h[(M - 1 - n) + k * M];
             const size_t smem = (size_t)(kPfbTileF + kPfbTileP - 1) * (M + 2) * sizeof(float2);
@@ -263,7 +263,7 @@ extern "C" long long emu_pfb(int M, int kind, const float2 *x, long long nf_tota
             std::vector<unsigned short> pm(M);
             pfb_stream_perm(M, pm.data());
             sp.xr = xr.data(); sp.y = y + pos; sp.y_stride = nf_total; sp.nf = (int)nf; sp.M = M; sp.log2M = log2M;
-            sp.h = h.data(); sp.tw = tw.data(); sp.perm = pm.data();
+            sp.h = h.data(); sp.tw = tw.data(); sp.perm = pm.data(); sp.ocs = 1;
             sp.T = 3 * kPfbStTF;
             const dim3 gs((unsigned)((nf + sp.T - 1) / sp.T)), bs(M);
             switch (log2M) {
