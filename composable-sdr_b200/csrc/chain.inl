@@ -400,6 +400,7 @@ int csdr_chain_process(csdr_chain q, const csdr_cf32 *x, size_t nx, size_t x_str
         }
         q->out_ptrs = base;
         if (any_host_out) { CK(cudaStreamSynchronize(q->d2h_stream)); c.sync(); }
+        else CK(cudaEventSynchronize(q->event(kEv + 2 * (nparts - 1))));   // the caller may reuse x: its last part has been copied
         if (n_out) *n_out = n;
         return 0;
     } else {
@@ -407,7 +408,9 @@ int csdr_chain_process(csdr_chain q, const csdr_cf32 *x, size_t nx, size_t x_str
         q->xin.ensure(sizeof(float2) * nx * S);
         CK(cudaMemcpy2DAsync(q->xin.p, nx * sizeof(float2), x, x_stride * sizeof(float2), nx * sizeof(float2), S,
                              cudaMemcpyHostToDevice, c.stream));
+        CK(cudaEventRecord(q->event(127), c.stream));
         n = chain_run_device(q, q->xin.as<float2>(), nx, nx, any_host_out ? cap_each : out_cap);
+        if (!any_host_out) CK(cudaEventSynchronize(q->event(127)));       // pinned x: the copy is asynchronous, the caller may reuse x
     }
     if (any_host_out) {
         for (size_t i = 0; i < nptr; i++)

@@ -206,7 +206,9 @@ __global__ void __launch_bounds__(kPfbTileF) k_pfb_tile(const CSDR_GRID_CONSTANT
     float2 b[M];
 #pragma unroll
     for (int i = 0; i < M; i++) b[i] = a[pfb_rev<LM>(i)];
+#ifndef CSDR_PFB_SKIP_DFT       // ablation (profiles/r02_tensorcore_question.txt): what a DFT that costs nothing would gain
     pfb_dit_bf<LM, 1, 0>(b, p.tw);
+#endif
     if (p.over2) {
         // firpfbch2: the analyzer's backward DFT over the window slots and its alternating commutator are a per-channel
         // factor of the forward DFT (closed form at the top of the firpfbch2 section); W^(c + M/2) = -W^c
