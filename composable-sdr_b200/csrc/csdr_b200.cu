@@ -696,7 +696,7 @@ struct Channelizer {
     DevBuf hd, tw, xr[2]; int cur = 0;       // xr: [(P-1)*M history | new samples], ping-pong for the history
     int log2M = -1, F = 1;
     size_t smem = 0;
-    void (*tile_kernel)(PfbTileParams) = nullptr; PfbTileParams tp{}; size_t tile_smem = 0;   // M = 2..32, m = 7
+    void (*tile_kernel)(PfbTileParams) = nullptr; PfbTileParams tp{}; size_t tile_smem = 0; bool tile_two = false;   // M = 2..32, m = 7
     bool ring_ok = false; int ring_ctas = 1; void (*ring_kernel)(PfbRingParams) = nullptr;                                                 // M = 128..1024, m = 7
     bool stream_ok = false; int stream_ctas = 1; DevBuf perm; void (*stream_kernel)(PfbStreamParams) = nullptr;                                                                              // M = 128..1024, m = 7 (default)
     bool over2 = false; unsigned long long frames_done = 0;     // firpfbch2 analyzer: hop M/2, generic kernel
@@ -731,10 +731,13 @@ struct Channelizer {
             case 4: tile_kernel = k_pfb_tile<4>; break;
             default: tile_kernel = k_pfb_tile<5>; break;
             }
+            // M = 8, 16: two frames per thread (half the shared-memory reads); option CSDR_OPT_PFB_VARIANT = 2 keeps k_pfb_tile
+            tile_two = (log2M == 3 || log2M == 4) && g_options[CSDR_OPT_PFB_VARIANT] != 2;
+            if (tile_two) tile_kernel = log2M == 3 ? k_pfb_tile2<3> : k_pfb_tile2<4>;
             tp = PfbTileParams{};
             for (unsigned i = 0; i < M / 2; i++) tp.tw[i] = t[i];
             for (unsigned k = 0; k < P; k++) for (unsigned n = 0; n < M; n++) tp.h[k * M + n] = h[(M - 1 - n) + k * M];
-            tile_smem = (size_t)(kPfbTileF + kPfbTileP - 1) * (M + 2) * sizeof(float2);
+            tile_smem = (size_t)(kPfbTileF + kPfbTileP - 1) * (M + (tile_two ? 0 : 2)) * sizeof(float2);
             raise_dyn_smem(tile_kernel, tile_smem);
         }
         ring_ok = !over2 && log2M >= 7 && M <= 1024 && (int)P == kPfbRingP;
@@ -821,7 +824,7 @@ struct Channelizer {
             } else if (tile_kernel) {
                 tp.xr = xin; tp.y = y; tp.y_stride = y_stride; tp.nf = nfp; tp.pw = pw; tp.pw_stride = pw_stride;
                 tp.ocs = ocs; tp.oco = oco; tp.over2 = o2; tp.sc_even = sc_even; tp.sc_odd = sc_odd;
-                launch(tile_kernel, dim3((nfp + kPfbTileF - 1) / kPfbTileF), dim3(kPfbTileF), tile_smem, c.stream, tp);
+                launch(tile_kernel, dim3((nfp + kPfbTileF - 1) / kPfbTileF), dim3(tile_two ? kPfbTileF / 2 : kPfbTileF), tile_smem, c.stream, tp);
             } else {
                 launch(k_pfb, dim3((nf + F - 1) / F), dim3(256), smem, c.stream, p);
             }

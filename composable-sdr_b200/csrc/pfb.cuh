@@ -230,6 +230,100 @@ __global__ void __launch_bounds__(kPfbTileF) k_pfb_tile(const CSDR_GRID_CONSTANT
     }
 }
 
+// ---- M = 8, 16: two frames per thread ----------------------------------------------------------------------------
+// k_pfb_tile is bound by the shared-memory data pipe: every frame reads its 14 rows (81 % of the pipe's peak at M = 16,
+// profiles/r02_tensorcore_question.txt).  Here thread t evaluates frames 2t and 2t + 1 together: row 2t + j is tap 13 - j
+// of the first and tap 14 - j of the second, so 15 rows are read for two frames instead of 28.  Rows are stored unpadded
+// with an XOR swizzle of their 16-byte chunks (chunk q of the tile at (q & ~7) | ((q & 7) ^ ((q >> 3 >> (log2 M - 3)) & 7)):
+// the eight threads of a quarter-warp, two rows apart, hit eight different 16-byte bank groups, and so do the staging
+// stores.  The two frames of a thread are neighbours in the channel-major output: one 16-byte store per channel.
+template <int LM> __device__ __forceinline__ int pfb_tile2_phys(int q) { return (q & ~7) | ((q & 7) ^ (((q >> 3) >> (LM - 3)) & 7)); }
+
+template <int LM>
+__global__ void __launch_bounds__(kPfbTileF / 2) k_pfb_tile2(const CSDR_GRID_CONSTANT PfbTileParams p)
+{
+    static_assert(LM == 3 || LM == 4, "two frames per thread: 4 M accumulator registers");
+    constexpr int M = 1 << LM, P = kPfbTileP, F = kPfbTileF, CH = M / 2;      // CH 16-byte chunks (sample pairs) per row
+    CSDR_DYN_SMEM(smem_raw);
+    float4 *in4 = reinterpret_cast<float4 *>(smem_raw);           // [(F + P - 1) * CH] chunks, swizzled
+    const int t0 = blockIdx.x * F;
+    const int nfr = min(F, p.nf - t0);
+    {
+        const float4 *src = reinterpret_cast<const float4 *>(p.xr + (long long)t0 * M);
+        const int chunks = (nfr + P - 1) * CH;
+        for (int e = threadIdx.x; e < chunks; e += F / 2) in4[pfb_tile2_phys<LM>(e)] = src[e];
+    }
+    __syncthreads();
+    const int t = threadIdx.x, f = 2 * t;
+    if (f >= nfr) return;
+    float2 a[M], b[M];                                              // polyphase sums of frames f and f + 1
+#pragma unroll
+    for (int n = 0; n < M; n++) { a[n] = cf(0.f, 0.f); b[n] = cf(0.f, 0.f); }
+#pragma unroll
+    for (int j = 0; j < P + 1; j++) {
+        // row f + j: tap P - 1 - j of frame f (j < P), tap P - j of frame f + 1 (j >= 1)
+        const int q0 = (f + j) * CH;
+#pragma unroll
+        for (int c = 0; c < CH; c++) {
+            const float4 q = in4[pfb_tile2_phys<LM>(q0 + c)];
+            if (j < P) {
+                const float h0 = p.h[(P - 1 - j) * M + 2 * c], h1 = p.h[(P - 1 - j) * M + 2 * c + 1];
+                a[2 * c].x = fmaf(h0, q.x, a[2 * c].x); a[2 * c].y = fmaf(h0, q.y, a[2 * c].y);
+                a[2 * c + 1].x = fmaf(h1, q.z, a[2 * c + 1].x); a[2 * c + 1].y = fmaf(h1, q.w, a[2 * c + 1].y);
+            }
+            if (j >= 1) {
+                const float h0 = p.h[(P - j) * M + 2 * c], h1 = p.h[(P - j) * M + 2 * c + 1];
+                b[2 * c].x = fmaf(h0, q.x, b[2 * c].x); b[2 * c].y = fmaf(h0, q.y, b[2 * c].y);
+                b[2 * c + 1].x = fmaf(h1, q.z, b[2 * c + 1].x); b[2 * c + 1].y = fmaf(h1, q.w, b[2 * c + 1].y);
+            }
+        }
+    }
+    // the two M-point DFTs (bit-reversed input order, then the radix-2 butterflies of k_pfb_tile)
+    float2 ya[M], yb[M];
+#pragma unroll
+    for (int i = 0; i < M; i++) { ya[i] = a[pfb_rev<LM>(i)]; yb[i] = b[pfb_rev<LM>(i)]; }
+    pfb_dit_bf<LM, 1, 0>(ya, p.tw);
+    pfb_dit_bf<LM, 1, 0>(yb, p.tw);
+    if (p.over2) {
+#pragma unroll
+        for (int c = 0; c < M; c++) {
+            const float2 w = p.tw[c & (M / 2 - 1)];
+            const float sc = ((c & 1) ? p.sc_odd : p.sc_even) * ((c >= M / 2) ? -1.f : 1.f);
+            ya[c] = cf((ya[c].x * w.x - ya[c].y * w.y) * sc, (ya[c].x * w.y + ya[c].y * w.x) * sc);
+            yb[c] = cf((yb[c].x * w.x - yb[c].y * w.y) * sc, (yb[c].x * w.y + yb[c].y * w.x) * sc);
+        }
+    }
+    const bool two = f + 1 < nfr;
+    const long long col = (long long)(t0 + f) * p.ocs + p.oco;
+    float2 *yo = p.y + col;
+    // frames f and f + 1 are neighbouring columns: one 16-byte store per channel where the layout allows it
+    const bool vec = two && p.ocs == 1 && ((reinterpret_cast<uintptr_t>(yo) | (uintptr_t)(p.y_stride * sizeof(float2))) & 15) == 0;
+    if (vec) {
+#pragma unroll
+        for (int c = 0; c < M; c++) *reinterpret_cast<float4 *>(yo + (long long)c * p.y_stride) = make_float4(ya[c].x, ya[c].y, yb[c].x, yb[c].y);
+    } else {
+#pragma unroll
+        for (int c = 0; c < M; c++) {
+            yo[(long long)c * p.y_stride] = ya[c];
+            if (two) yo[(long long)c * p.y_stride + p.ocs] = yb[c];
+        }
+    }
+    if (p.pw) {
+        float *po = p.pw + col;
+        const bool vec2 = two && p.ocs == 1 && ((reinterpret_cast<uintptr_t>(po) | (uintptr_t)(p.pw_stride * sizeof(float))) & 7) == 0;
+        if (vec2) {
+#pragma unroll
+            for (int c = 0; c < M; c++) *reinterpret_cast<float2 *>(po + (long long)c * p.pw_stride) = cf(pfb_power(ya[c]), pfb_power(yb[c]));
+        } else {
+#pragma unroll
+            for (int c = 0; c < M; c++) {
+                po[(long long)c * p.pw_stride] = pfb_power(ya[c]);
+                if (two) po[(long long)c * p.pw_stride + p.ocs] = pfb_power(yb[c]);
+            }
+        }
+    }
+}
+
 // ---- large power-of-two M (128..1024): a CTA slides over its frames with a ring of rows --------------------------
 // Shared memory holds the last P + 1 = 15 rows of M samples (ring), two M-point DFT buffers and a [TF][M] output
 // tile.  Two frames are processed per iteration by the two halves of the CTA (M/4 threads each): the two new rows are
