@@ -50,28 +50,44 @@ __global__ void k_am_stage_in(const AmParams p)
     }
 }
 
+// The two 51-tap FIRs: kAmR consecutive outputs per thread, the taps in registers, every staged sample read once per
+// thread and used by up to kAmR accumulators.  Output r takes its taps oldest sample first (liquid's dotprod order):
+// sample j of the thread's window is tap r + 50 - j of output r.  Tile element e sits at e + (e >> 2): consecutive
+// threads (4 elements apart) then start 5 elements apart, which is conflict-free for 4- and 8-byte accesses.
+constexpr int kAmR = 4, kAmTile = 256 * kAmR;
+__device__ __forceinline__ int am_pad(int e) { return e + (e >> 2); }
+
 // x0[i] = sum_k h_lp[k] * xh[50 + i - k]
-__global__ void k_am_lowpass(const AmParams p)
+__global__ void __launch_bounds__(256) k_am_lowpass(const AmParams p)
 {
-    __shared__ float2 tile[256 + kAmHist];
-    __shared__ float h[kAmTaps];
+    __shared__ float2 tile[kAmTile + kAmHist + (kAmTile + kAmHist) / 4 + 1];
     const int lane = blockIdx.y;
     const float2 *xh = p.xh + (long long)lane * p.xh_stride;
-    if (threadIdx.x < kAmTaps) h[threadIdx.x] = p.h_lp[threadIdx.x];
-    for (int base = blockIdx.x * 256; base < p.n; base += gridDim.x * 256) {
+    float h[kAmTaps];
+#pragma unroll
+    for (int k = 0; k < kAmTaps; k++) h[k] = p.h_lp[k];
+    for (int base = blockIdx.x * kAmTile; base < p.n; base += gridDim.x * kAmTile) {
         __syncthreads();
-        for (int j = threadIdx.x; j < 256 + kAmHist; j += blockDim.x)
-            tile[j] = (base + j < p.n + kAmHist) ? xh[base + j] : cf(0.f, 0.f);
+        for (int j = threadIdx.x; j < kAmTile + kAmHist; j += blockDim.x)
+            tile[am_pad(j)] = (base + j < p.n + kAmHist) ? xh[base + j] : cf(0.f, 0.f);
         __syncthreads();
-        const int i = base + threadIdx.x;
-        if (i < p.n) {
-            float ar = 0.f, ai = 0.f;
-            // oldest sample first (liquid dotprod order)
-            for (int k = kAmTaps - 1; k >= 0; k--) {
-                float2 v = tile[threadIdx.x + kAmHist - k];
-                ar += h[k] * v.x; ai += h[k] * v.y;
+        const int o = threadIdx.x * kAmR;
+        if (base + o < p.n) {
+            float ar[kAmR], ai[kAmR];
+#pragma unroll
+            for (int r = 0; r < kAmR; r++) { ar[r] = 0.f; ai[r] = 0.f; }
+#pragma unroll
+            for (int j = 0; j < kAmHist + kAmR; j++) {
+                const float2 v = tile[am_pad(o + j)];
+#pragma unroll
+                for (int r = 0; r < kAmR; r++) {
+                    const int k = r + kAmHist - j;
+                    if (k >= 0 && k < kAmTaps) { ar[r] += h[k] * v.x; ai[r] += h[k] * v.y; }
+                }
             }
-            p.x0[(long long)lane * p.n + i] = cf(ar, ai);
+            float2 *dst = p.x0 + (long long)lane * p.n + base + o;
+#pragma unroll
+            for (int r = 0; r < kAmR; r++) if (base + o + r < p.n) dst[r] = cf(ar[r], ai[r]);
         }
     }
 }
@@ -233,24 +249,36 @@ __global__ void __launch_bounds__(32) k_am_pll_fix(const AmParams p)
 }
 
 // y[i] = out_scale * sum_k h_dc[k] * mh[50 + i - k]
-__global__ void k_am_dcfir(const AmParams p)
+__global__ void __launch_bounds__(256) k_am_dcfir(const AmParams p)
 {
-    __shared__ float tile[256 + kAmHist];
-    __shared__ float h[kAmTaps];
+    __shared__ float tile[kAmTile + kAmHist + (kAmTile + kAmHist) / 4 + 1];
     const int lane = blockIdx.y;
     const float *mh = p.mh + (long long)lane * p.mh_stride;
     float *y = p.y + (long long)lane * p.y_stride;
-    if (threadIdx.x < kAmTaps) h[threadIdx.x] = p.h_dc[threadIdx.x];
-    for (int base = blockIdx.x * 256; base < p.n; base += gridDim.x * 256) {
+    float h[kAmTaps];
+#pragma unroll
+    for (int k = 0; k < kAmTaps; k++) h[k] = p.h_dc[k];
+    for (int base = blockIdx.x * kAmTile; base < p.n; base += gridDim.x * kAmTile) {
         __syncthreads();
-        for (int j = threadIdx.x; j < 256 + kAmHist; j += blockDim.x)
-            tile[j] = (base + j < p.n + kAmHist) ? mh[base + j] : 0.f;
+        for (int j = threadIdx.x; j < kAmTile + kAmHist; j += blockDim.x)
+            tile[am_pad(j)] = (base + j < p.n + kAmHist) ? mh[base + j] : 0.f;
         __syncthreads();
-        const int i = base + threadIdx.x;
-        if (i < p.n) {
-            float acc = 0.f;
-            for (int k = kAmTaps - 1; k >= 0; k--) acc += h[k] * tile[threadIdx.x + kAmHist - k];
-            y[i] = acc * p.out_scale;
+        const int o = threadIdx.x * kAmR;
+        if (base + o < p.n) {
+            float acc[kAmR];
+#pragma unroll
+            for (int r = 0; r < kAmR; r++) acc[r] = 0.f;
+#pragma unroll
+            for (int j = 0; j < kAmHist + kAmR; j++) {
+                const float v = tile[am_pad(o + j)];
+#pragma unroll
+                for (int r = 0; r < kAmR; r++) {
+                    const int k = r + kAmHist - j;
+                    if (k >= 0 && k < kAmTaps) acc[r] += h[k] * v;
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < kAmR; r++) if (base + o + r < p.n) y[base + o + r] = acc[r] * p.out_scale;
         }
     }
 }
@@ -340,9 +368,10 @@ struct AmDemod {
         p.use_pll = use_pll ? 1 : 0;
         p.out_scale = use_pll ? 1.0f : 1.0f / mod_index;
         int gx = std::max(1, std::min((n + 255) / 256, 2048));
+        const int gf = std::max(1, std::min((n + kAmTile - 1) / kAmTile, 2048));      // the FIR kernels: kAmTile outputs per CTA
         k_am_stage_in<<<dim3(gx, nlanes), 256, 0, st>>>(p); launches++;
         if (use_pll) {
-            k_am_lowpass<<<dim3(gx, nlanes), 256, 0, st>>>(p); launches++;
+            k_am_lowpass<<<dim3(gf, nlanes), 256, 0, st>>>(p); launches++;
             // segments of 2048 samples behind a 512-sample pull-in when there are enough of them to matter
             p.pll_L = 2048; p.pll_W = 512; p.pll_nseg = (n + p.pll_L - 1) / p.pll_L;
             if (spec && p.pll_nseg >= 4) {
@@ -358,7 +387,7 @@ struct AmDemod {
                 k_am_pll<<<(nlanes + 31) / 32, 32, 0, st>>>(p); launches++;
             }
         }
-        k_am_dcfir<<<dim3(gx, nlanes), 256, 0, st>>>(p); launches++;
+        k_am_dcfir<<<dim3(gf, nlanes), 256, 0, st>>>(p); launches++;
         k_am_tail<<<nlanes, 64, 0, st>>>(p, (float2 *)d_xtmp, (float *)d_mtmp, 0); launches++;
         k_am_tail<<<nlanes, 64, 0, st>>>(p, (float2 *)d_xtmp, (float *)d_mtmp, 1); launches++;
         ck(cudaGetLastError(), "ampmodem launch");
