@@ -413,15 +413,17 @@ def per_config(torch, cs, dist, rank, world, local, args, peak):
               8.0 + 4.0 / 1024, world * n, m, "weak",
               "frame-aligned time segments per rank; --mix is a per-rank sum over all 1024 channels, no collective", 5)
         ch.close(); del x, ch; cleanup()
-    if "C4b" in want and world == 1:
+    if "C4b" in want:
         # the channelizer the task names: liquid's 2x oversampled firpfbch2_crcf analyzer (frames of C/2 samples, every channel
-        # at 2/C of the input rate) in place of the reference's firpfbch_crcf; single GPU only (no seek for it yet)
+        # at 2/C of the input rate) in place of the reference's firpfbch_crcf
         n = 1 << args.log2n_c4b
         x = channelizer_input(torch, n, 1024, 64, 1e-4, 7e-4, 3e-5, 400 + rank)
         ch = cs.Chain(1e9, demod=cs.DeNBFM(KF), agc=AGC_DB, channels=1024, mix_channels=True, device=local, channelizer=1)
-        m = measure_config(torch, cs, dist, rank, world, local, ch, x, 5, args.warmup)
+        m = measure_config(torch, cs, dist, rank, world, local, ch, x, 5, args.warmup, seek_to=rank * steps_total(5) * n,
+                           align=shard.frame_alignment(1024))
         entry("C4b", "C4b: 1 GS/s CF32 -> dcblock -> firpfbch2 1024 channels (2x oversampled) -> per-channel AGC -40 dB + NBFM -> --mix (sum), "
-              "1 F32 output at twice C4's rate", 8.0 + 8.0 / 1024, n, m, "weak", "single GPU", 5)
+              "1 F32 output at twice C4's rate", 8.0 + 8.0 / 1024, world * n, m, "weak",
+              "frame-aligned time segments per rank; --mix is a per-rank sum, no collective", 5)
         ch.close(); del x, ch; cleanup()
     if "C5" in want:
         n = 1 << args.log2n_c5
@@ -600,7 +602,7 @@ def main():
     ap.add_argument("--configs", default="C1,C3,C4,C4b,C5", help="other configs measured in the same run (per_config); '' = none")
     ap.add_argument("--log2n-c3", type=int, default=28, help="log2 of the config-3 chunk (samples per step per GPU)")
     ap.add_argument("--log2n-c4", type=int, default=30, help="log2 of the config-4 chunk (samples per step per GPU)")
-    ap.add_argument("--log2n-c4b", type=int, default=28, help="log2 of the firpfbch2 variant of config 4 (single GPU only)")
+    ap.add_argument("--log2n-c4b", type=int, default=28, help="log2 of the firpfbch2 variant of config 4 (samples per step per GPU)")
     ap.add_argument("--log2n-c5", type=int, default=22, help="log2 of the config-5 chunk per stream (256 streams in all)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)

@@ -373,7 +373,10 @@ struct AmDemod {
         if (use_pll) {
             k_am_lowpass<<<dim3(gf, nlanes), 256, 0, st>>>(p); launches++;
             // segments of 2048 samples behind a 512-sample pull-in when there are enough of them to matter
-            p.pll_L = 2048; p.pll_W = 512; p.pll_nseg = (n + p.pll_L - 1) / p.pll_L;
+#ifndef CSDR_AM_PLL_L
+#define CSDR_AM_PLL_L 2048
+#endif
+            p.pll_L = CSDR_AM_PLL_L; p.pll_W = 512; p.pll_nseg = (n + p.pll_L - 1) / p.pll_L;
             if (spec && p.pll_nseg >= 4) {
                 const size_t need = (size_t)nlanes * p.pll_nseg * 2 * sizeof(unsigned) * 2;
                 if (need > seg_cap) { if (d_seg) cudaFree(d_seg); ck(cudaMalloc(&d_seg, need + need / 4), "cudaMalloc"); seg_cap = need + need / 4; }

@@ -500,7 +500,6 @@ int csdr_chain_seek(csdr_chain q, uint64_t n_prior)
     REQUIRE(q, TAG_CHAIN, -1);
     API_BEGIN
     if (q->has_wb) throw CudaError{"chain: seek with DeWBFM is not implemented"};
-    if (q->over2) throw CudaError{"chain: seek with the firpfbch2 channelizer is not implemented"};
     q->ctx.use();
     // samples behind the resampler that precede the new position (closed form: fe_seek)
     unsigned long long o_prior = n_prior;
@@ -518,8 +517,11 @@ int csdr_chain_seek(csdr_chain q, uint64_t n_prior)
         // channelizer: the pre-rotation NCO (Liquid.chs:817-821, 847) has advanced by o_prior samples; frames stay on the
         // stream's own grid (sample index = 0 mod C), so the o_prior mod C samples of the frame the new position falls into
         // count as already waiting (zeros: that frame and the 13 that still see the empty history belong to the warm-up)
+        // (firpfbch2: frames of C/2 samples, no pre-rotation; the sign (-1)^(c t) of its per-channel factor follows the absolute
+        // frame index, so the filterbank's frame counter restarts at the number of whole frames in front of the position)
         q->rot_theta = (uint32_t)o_prior * q->rot_dtheta;
-        q->nleft = (size_t)(o_prior % q->C);
+        q->nleft = (size_t)(o_prior % q->hop);
+        q->ch.frames_done = o_prior / q->hop;
         CK(cudaMemsetAsync(q->left.p, 0, q->left.cap, q->ctx.stream));
         for (auto &b : q->ch.xr) if (b.p) CK(cudaMemsetAsync(b.p, 0, q->ch.hist_samples() * sizeof(float2), q->ctx.stream));
         q->ctx.sync();
@@ -535,7 +537,7 @@ size_t csdr_chain_warmup_len(csdr_chain q)
     // settling (~400 samples) and the squelch FSM's memory (timeout + 8 samples) per channel
     double r = q->has_resamp ? (double)q->fe.ms.rate : 1.0;
     double post = 45000.0;
-    if (q->C > 1) post += (double)q->C * (14.0 + 512.0 + (double)q->be.agc_timeout + 8.0);
+    if (q->C > 1) post += (double)q->hop * (28.0 + 512.0 + (double)q->be.agc_timeout + 8.0);
     size_t w = (size_t)(q->has_resamp ? q->fe.geo.hcap : 0) + (size_t)std::ceil(post / r);
     return w;
 }

@@ -343,6 +343,27 @@ def test_channelizer_time_segment_sharding(cs, orc):
     assert snr_db(y[512:], refm[512:]) >= 60.0
 
 
+def test_firpfbch2_time_segment_sharding(cs, orc):
+    """the channelizer the task names (firpfbch2_crcf, frames of C/2 samples) shards by time segments as well: the frame
+    grid and the sign (-1)^(c t) of its per-channel factor follow the absolute position, for a shard that starts on an
+    even frame, on an odd frame and inside a frame"""
+    from composable_sdr_b200 import shard
+    x = cs.synth.config4(1 << 21, channels=64, active=8, sr=1e8)
+    ref = orc.Chain(1e8, 0.0, 0.0, orc.DEMOD_NO, 0.0, -40.0, 64, False, channelizer=1).process(x)
+    mk = lambda: cs.Chain(1e8, agc=-40.0, channels=64, channelizer=1)
+    hop = 32
+    for start in ((1 << 20), (1 << 20) + hop, (1 << 20) + hop + 5):
+        sh = mk()
+        warm = shard.seek_shard(sh, start, lambda i, j: x[i:j])
+        assert 0 < warm < start
+        outs = sh.process(x[start:])
+        k0 = start // hop                                    # whole frames in front of the shard
+        for c in (0, 1, 31, 32, 63):
+            assert len(outs[c]) == len(ref[c]) - k0
+            assert_parity(outs[c][64:], ref[c][k0 + 64:], what=f"firpfbch2 shard at {start}, channel {c}")
+        sh.close()
+
+
 def test_full_size_properties_on_device(cs):
     """BASELINE-size chunk (2^26 samples, device resident): exact output count, linearity of the front end,
     chunk invariance, and few AGC speculation misses."""
