@@ -26,7 +26,9 @@ for r, ln in zip(rows, lines_of):
 ti, ts = sum(inst.values()), sum(smp.values())
 src = {}
 print(f"{out[names[k]][:100]}  {ti/1e6:.2f}M warp instructions")
-for ln, c in inst.most_common(top):
+order = smp if os.environ.get("NCU_LINES_BY") == "samples" else inst      # NCU_LINES_BY=samples: rank by stall samples
+for ln, _ in order.most_common(top):
+    c = inst[ln]
     if ln and ln[0] not in src:
         p = [os.path.join(d, ln[0]) for d in ("composable-sdr_b200/csrc",) if os.path.exists(os.path.join(d, ln[0]))]
         src[ln[0]] = open(p[0]).read().splitlines() if p else []
