@@ -1303,6 +1303,55 @@ __global__ void k_lane_sum(const float *__restrict__ in, long long lane_stride, 
     }
 }
 
+// The same fold over the back end's own gated output, without reading what the gate has closed: a 32-sample word whose gate
+// bits are all zero (and, for the discriminator, whose predecessor sample is closed too: next to an open sample a closed one
+// is arg(+-0 +- j0) = 0 or +-pi, not 0) holds exact zeros, so the fold skips it (x + 0 = x) -- a wide-band
+// input with few occupied channels is mostly closed words (config 4: 64 of 1024 channels carry a signal).  fpw = floats per
+// sample (1 discriminator, 2 cf32); all threads of a warp look at the same gate word (one broadcast load).
+__global__ void __launch_bounds__(256) k_lane_sum_gated(const float *__restrict__ in, long long lane_stride, int nlanes, float *__restrict__ out,
+                                                        long long nsamp, const unsigned *__restrict__ gate, int nwords,
+                                                        const unsigned *__restrict__ prev_gate, int fpw, int need_prev)
+{
+    // one warp per 32-sample word: lane k inspects the gate word of channel c0 + k, the ballot lists the channels that have
+    // to be read, and those are added in channel order (four loads in flight)
+    const int l = threadIdx.x & 31;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarp = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long wd = warp; wd < nwords; wd += nwarp) {
+        const long long sidx = wd * 32 + l;
+        const bool valid = sidx < nsamp;
+        float a0 = 0.f, a1 = 0.f;
+        for (int c0 = 0; c0 < nlanes; c0 += 32) {
+            const int c = c0 + l;
+            unsigned g = 0u;
+            if (c < nlanes) {
+                const unsigned *gl = gate + (long long)c * nwords;
+                g = gl[wd];
+                if (need_prev) g |= wd ? (gl[wd - 1] >> 31) : prev_gate[c];
+            }
+            unsigned m = __ballot_sync(0xffffffffu, g != 0u);
+            while (m) {
+                int ch[4]; int cnt = 0;
+#pragma unroll
+                for (int k = 0; k < 4; k++) if (m) { ch[k] = c0 + __ffs(m) - 1; m &= m - 1; cnt = k + 1; } else ch[k] = 0;
+                if (fpw == 2) {
+                    float2 v[4];
+#pragma unroll
+                    for (int k = 0; k < 4; k++) v[k] = (k < cnt && valid) ? reinterpret_cast<const float2 *>(in + (long long)ch[k] * lane_stride)[sidx] : cf(0.f, 0.f);
+#pragma unroll
+                    for (int k = 0; k < 4; k++) if (k < cnt) { a0 = __fadd_rn(a0, v[k].x); a1 = __fadd_rn(a1, v[k].y); }
+                } else {
+                    float v[4];
+#pragma unroll
+                    for (int k = 0; k < 4; k++) v[k] = (k < cnt && valid) ? in[(long long)ch[k] * lane_stride + sidx] : 0.f;
+#pragma unroll
+                    for (int k = 0; k < 4; k++) if (k < cnt) a0 = __fadd_rn(a0, v[k]);
+                }
+            }
+        }
+        if (valid) { if (fpw == 2) reinterpret_cast<float2 *>(out)[sidx] = cf(a0, a1); else out[sidx] = a0; }
+    }
+}
+
 // ------------------------------------------------------------------------------------------ launch sequences
 // `launch(kernel, grid, block, smem_bytes, args...)` is supplied by the caller (CUDA stream launcher in
 // csdr_b200.cu, thread emulator in the CPU-only tests) so that both run the same sequence with the same grids.

@@ -296,8 +296,15 @@ size_t chain_run_device(csdr_chain_s *q, const float2 *xd, size_t nx, size_t x_s
         if (q->cfg.mix) {
             // mix = foldl1 (zipWith (+)) over channels 1..C (Trans.hs:119-122); cf32 is summed as 2 floats
             const long long nfl = (long long)nfo * (long long)(q->esz / sizeof(float));
-            launch(k_lane_sum, dim3(grid_for(nfl, 256, c.sms)), dim3(256), 0, c.stream, (const float *)dem, nfl, (int)C,
-                   (float *)q->out_ptrs[0], nfl);
+            // summands straight from the gated back end: closed words are exact zeros and are not read
+            const bool gated = dem == q->dem.p && q->be.has_agc && q->be.gate && q->cfg.demod != CSDR_DEMOD_AM && !q->has_wb && q->be.last_nwords > 0;
+            if (gated)
+                launch(k_lane_sum_gated, dim3(grid_for((long long)q->be.last_nwords * 32, 256, c.sms)), dim3(256), 0, c.stream, (const float *)dem, nfl,
+                       (int)C, (float *)q->out_ptrs[0], (long long)nfo, (const unsigned *)q->be.gatebits.as<unsigned>(), q->be.last_nwords,
+                       (const unsigned *)q->be.prev_gate.as<unsigned>(), (int)(q->esz / sizeof(float)), q->be.demod == 1 ? 1 : 0);
+            else
+                launch(k_lane_sum, dim3(grid_for(nfl, 256, c.sms)), dim3(256), 0, c.stream, (const float *)dem, nfl, (int)C,
+                       (float *)q->out_ptrs[0], nfl);
         } else {
             for (unsigned ch = 0; ch < C; ch++)
                 CK(cudaMemcpyAsync(q->out_ptrs[ch], (char *)dem + (size_t)ch * nfo * q->esz, q->esz * nfo, cudaMemcpyDeviceToDevice, c.stream));

@@ -414,7 +414,7 @@ struct Backend {
     DevBuf lane, dc_agg, dc_flag, dc_ticket, dc_state[2], powA, powAB, ss, se, fs, fe, exbits, gatebits, sgnr, sgni, prev_gate, prev_sign, first_bad, bad_list, bad_count, fixups;
     DevBuf ydc, pwbuf, g_first, y_first, y_end, seg_ylast, barrier;
     int pw_ready_n = -1;       // the producer of the input has already written its power for a call of this many samples
-    int FW = 3; unsigned long long last_refined = 0; int last_L = 0, last_W = 0;
+    int FW = 3; unsigned long long last_refined = 0; int last_L = 0, last_W = 0, last_nwords = 0;
     // self-tuning warm-up: the counters of every call are copied to pinned memory asynchronously; the next call looks
     // at them (no synchronisation) and lengthens / shortens the warm-up
     // self-tuning warm-up, deterministic: the counters of every call are copied to one of two pinned slots; call k waits for
@@ -603,6 +603,7 @@ struct Backend {
         }
         last_L = L; last_W = W;
         int ngrp = (n + G - 1) / G, nseg = (n + L - 1) / L, nwords = (n + 31) / 32;
+        last_nwords = has_agc ? nwords : 0;
         size_t segs = (size_t)nlanes * nseg;
         ss.ensure(sizeof(SegState) * segs); se.ensure(sizeof(SegState) * segs);
         fs.ensure(sizeof(FsmState) * segs); fe.ensure(sizeof(FsmState) * segs);
