@@ -740,6 +740,25 @@ struct Channelizer {
             for (unsigned k = 0; k < P; k++) for (unsigned n = 0; n < M; n++) tp.h[k * M + n] = h[(M - 1 - n) + k * M];
             tile_smem = (size_t)(kPfbTileF + kPfbTileP - 1) * (M + (tile_two ? 0 : 2)) * sizeof(float2);
             raise_dyn_smem(tile_kernel, tile_smem);
+        } else if (log2M < 0 && M % 2 == 0 && M <= 24 && (int)P == kPfbTileP && (!over2 || M % 4 == 0)) {
+            // even channel counts that are not powers of two (the reference's published run: 20): register DFT by one radix-2
+            // split; firpfbch2 needs xr + M/2 on a 16-byte boundary
+            switch (M) {
+            case 6: tile_kernel = k_pfb_tile_any<6>; break;
+            case 10: tile_kernel = k_pfb_tile_any<10>; break;
+            case 12: tile_kernel = k_pfb_tile_any<12>; break;
+            case 14: tile_kernel = k_pfb_tile_any<14>; break;
+            case 18: tile_kernel = k_pfb_tile_any<18>; break;
+            case 20: tile_kernel = k_pfb_tile_any<20>; break;
+            case 22: tile_kernel = k_pfb_tile_any<22>; break;
+            default: tile_kernel = k_pfb_tile_any<24>; break;
+            }
+            tile_two = false;
+            tp = PfbTileParams{};
+            for (unsigned i = 0; i < M / 2; i++) tp.tw[i] = t[i];
+            for (unsigned k = 0; k < P; k++) for (unsigned n = 0; n < M; n++) tp.h[k * M + n] = h[(M - 1 - n) + k * M];
+            tile_smem = (size_t)(kPfbTileF + kPfbTileP - 1) * (M + 2) * sizeof(float2);
+            raise_dyn_smem(tile_kernel, tile_smem);
         }
         ring_ok = !over2 && log2M >= 7 && M <= 1024 && (int)P == kPfbRingP;
         if (ring_ok) {

@@ -230,6 +230,94 @@ __global__ void __launch_bounds__(kPfbTileF) k_pfb_tile(const CSDR_GRID_CONSTANT
     }
 }
 
+// ---- even M <= 24 that is not a power of two (the reference's published run has 20 channels, README.md:182-193) -----
+// k_pfb_tile with the register DFT as one radix-2 split and two direct M/2-point DFTs: y[c] = E[c] + W^c O[c],
+// y[c + M/2] = E[c] - W^c O[c]; every twiddle exponent is a template constant (table in the constant bank, W^(t + M/2) = -W^t;
+// 1, -1, -j, +j cost no multiplication).  M^2/2 + M complex MACs per frame (220 at M = 20), all in registers.
+template <int M, int t>
+__device__ __forceinline__ void pfb_mac_tw(float2 &acc, float2 a, const float2 *__restrict__ tw)
+{
+    constexpr int tt = ((t % M) + M) % M;
+    if constexpr (tt == 0) { acc.x += a.x; acc.y += a.y; }
+    else if constexpr (2 * tt == M) { acc.x -= a.x; acc.y -= a.y; }
+    else if constexpr (4 * tt == M) { acc.x += a.y; acc.y -= a.x; }
+    else if constexpr (4 * tt == 3 * M) { acc.x -= a.y; acc.y += a.x; }
+    else if constexpr (tt < M / 2) { const float2 w = tw[tt]; acc.x += a.x * w.x - a.y * w.y; acc.y += a.x * w.y + a.y * w.x; }
+    else { const float2 w = tw[tt - M / 2]; acc.x -= a.x * w.x - a.y * w.y; acc.y -= a.x * w.y + a.y * w.x; }
+}
+template <int M, int c, int n>
+__device__ __forceinline__ void pfb_dft_half(const float2 (&a)[M], float2 &e, float2 &o, const float2 *__restrict__ tw)
+{
+    pfb_mac_tw<M, 2 * c * n>(e, a[2 * n], tw);
+    pfb_mac_tw<M, 2 * c * n>(o, a[2 * n + 1], tw);
+    if constexpr (n + 1 < M / 2) pfb_dft_half<M, c, n + 1>(a, e, o, tw);
+}
+template <int M, int c>
+__device__ __forceinline__ void pfb_dft_any(const float2 (&a)[M], float2 (&y)[M], const float2 *__restrict__ tw)
+{
+    float2 e = cf(0.f, 0.f), o = cf(0.f, 0.f), t = cf(0.f, 0.f);
+    pfb_dft_half<M, c, 0>(a, e, o, tw);
+    pfb_mac_tw<M, c>(t, o, tw);
+    y[c] = cf(e.x + t.x, e.y + t.y);
+    y[c + M / 2] = cf(e.x - t.x, e.y - t.y);
+    if constexpr (c + 1 < M / 2) pfb_dft_any<M, c + 1>(a, y, tw);
+}
+
+template <int M>
+__global__ void __launch_bounds__(kPfbTileF) k_pfb_tile_any(const CSDR_GRID_CONSTANT PfbTileParams p)
+{
+    static_assert(M % 2 == 0 && M <= kPfbTileMaxM, "even channel counts up to 32");
+    constexpr int P = kPfbTileP, F = kPfbTileF, RS = M + 2, H = M / 2;
+    CSDR_DYN_SMEM(smem_raw);
+    float2 *in = reinterpret_cast<float2 *>(smem_raw);           // [(F + P - 1)][RS]
+    const int t0 = blockIdx.x * F;
+    const int nfr = min(F, p.nf - t0);
+    {
+        const float4 *src = reinterpret_cast<const float4 *>(p.xr + (long long)t0 * M);
+        const int pairs = (nfr + P - 1) * H;
+        for (int e = threadIdx.x; e < pairs; e += F) {
+            const int r = e / H, c2 = e - r * H;
+            *reinterpret_cast<float4 *>(in + r * RS + 2 * c2) = src[e];
+        }
+    }
+    __syncthreads();
+    const int f = threadIdx.x;
+    if (f >= nfr) return;
+    float2 a[M];
+#pragma unroll
+    for (int n = 0; n < M; n++) a[n] = cf(0.f, 0.f);
+#pragma unroll
+    for (int k = 0; k < P; k++) {
+        const float4 *row = reinterpret_cast<const float4 *>(in + (f + P - 1 - k) * RS);
+#pragma unroll
+        for (int j = 0; j < H; j++) {
+            const float4 q = row[j];
+            const float h0 = p.h[k * M + 2 * j], h1 = p.h[k * M + 2 * j + 1];
+            a[2 * j].x = fmaf(h0, q.x, a[2 * j].x); a[2 * j].y = fmaf(h0, q.y, a[2 * j].y);
+            a[2 * j + 1].x = fmaf(h1, q.z, a[2 * j + 1].x); a[2 * j + 1].y = fmaf(h1, q.w, a[2 * j + 1].y);
+        }
+    }
+    float2 b[M];
+    pfb_dft_any<M, 0>(a, b, p.tw);
+    if (p.over2) {
+#pragma unroll
+        for (int c = 0; c < M; c++) {
+            const float2 w = p.tw[c % H];
+            const float sc = ((c & 1) ? p.sc_odd : p.sc_even) * ((c >= H) ? -1.f : 1.f);
+            b[c] = cf((b[c].x * w.x - b[c].y * w.y) * sc, (b[c].x * w.y + b[c].y * w.x) * sc);
+        }
+    }
+    const long long col = (long long)(t0 + f) * p.ocs + p.oco;
+    float2 *yo = p.y + col;
+#pragma unroll
+    for (int c = 0; c < M; c++) yo[(long long)c * p.y_stride] = b[c];
+    if (p.pw) {
+        float *po = p.pw + col;
+#pragma unroll
+        for (int c = 0; c < M; c++) po[(long long)c * p.pw_stride] = pfb_power(b[c]);
+    }
+}
+
 // ---- M = 8, 16: two frames per thread ----------------------------------------------------------------------------
 // k_pfb_tile is bound by the shared-memory data pipe: every frame reads its 14 rows (81 % of the pipe's peak at M = 16,
 // profiles/r02_tensorcore_question.txt).  Here thread t evaluates frames 2t and 2t + 1 together: row 2t + j is tap 13 - j

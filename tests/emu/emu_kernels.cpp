@@ -243,14 +243,19 @@ extern "C" long long emu_pfb(int M, int kind, const float2 *x, long long nf_tota
         xr.resize(H + (size_t)nf * M);
         launch(k_nco_mix, dim3(4), dim3(64), 0, x + pos * M, xr.data() + H, nf * M, theta, dth, 1, 0);
         theta += (unsigned)(nf * M) * dth;
-        if (kind == 1 || kind == 4) {
+        if (kind == 1 || kind == 4 || kind == 5) {
             PfbTileParams tp{};
             tp.xr = xr.data(); tp.y = y + pos; tp.y_stride = nf_total; tp.nf = (int)nf; tp.ocs = 1;
             for (int i = 0; i < M / 2; i++) tp.tw[i] = tw[i];
             for (int k = 0; k < P; k++) for (int n = 0; n < M; n++) tp.h[k * M + n] = h[(M - 1 - n) + k * M];
             const size_t smem = (size_t)(kPfbTileF + kPfbTileP - 1) * (M + 2) * sizeof(float2);
             const dim3 g((unsigned)((nf + kPfbTileF - 1) / kPfbTileF)), b(kPfbTileF);
-            if (kind == 4) {                // two frames per thread (M = 8, 16)
+            if (kind == 5) {                // even M that is not a power of two
+                if (M == 20) launch(k_pfb_tile_any<20>, g, b, smem, tp);
+                else if (M == 12) launch(k_pfb_tile_any<12>, g, b, smem, tp);
+                else if (M == 6) launch(k_pfb_tile_any<6>, g, b, smem, tp);
+                else return -1;
+            } else if (kind == 4) {                // two frames per thread (M = 8, 16)
                 const dim3 b2(kPfbTileF / 2);
                 if (log2M == 3) launch(k_pfb_tile2<3>, g, b2, smem, tp);
                 else if (log2M == 4) launch(k_pfb_tile2<4>, g, b2, smem, tp);

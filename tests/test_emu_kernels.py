@@ -106,9 +106,9 @@ def test_backend_speculation_misses_are_repaired(orc, emu):
     assert_parity(out[0], ref, what="frozen gain")
 
 
-@pytest.mark.parametrize("M,kind", [(16, 0), (20, 0), (4, 1), (16, 1), (32, 1), (8, 4), (16, 4), (128, 2), (256, 2), (512, 2), (128, 3), (256, 3), (512, 3)])
+@pytest.mark.parametrize("M,kind", [(16, 0), (20, 0), (4, 1), (16, 1), (32, 1), (8, 4), (16, 4), (6, 5), (12, 5), (20, 5), (128, 2), (256, 2), (512, 2), (128, 3), (256, 3), (512, 3)])
 def test_channelizer_kernels_match_oracle(orc, emu, M, kind):
-    """k_pfb (any M), k_pfb_tile (register DFT, M <= 32), k_pfb_tile2 (two frames per thread, M = 8, 16: kind 4) and k_pfb_ring (M = 128..1024) against firpfbchChannelizer"""
+    """k_pfb (any M), k_pfb_tile (register DFT, M <= 32), k_pfb_tile2 (two frames per thread, M = 8, 16: kind 4), k_pfb_tile_any (even M, not a power of two: kind 5) and k_pfb_ring (M = 128..1024) against firpfbchChannelizer"""
     nf = 71 if M >= 128 else 300
     x = make_signal(M * nf, 21)
     ref = orc.Firpfbch(M).execute(x)
