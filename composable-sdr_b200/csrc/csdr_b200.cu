@@ -57,6 +57,20 @@ void launch(void (*k)(Args...), dim3 grid, dim3 block, size_t smem, cudaStream_t
     CK(cudaGetLastError());
 }
 
+// launch as thread-block clusters of `cluster_x` CTAs (distributed shared memory between the CTAs of a cluster)
+template <class... Args, class... Act>
+void launch_cluster(void (*k)(Args...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, unsigned cluster_x, Act &&...a)
+{
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = cluster_x; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    CK(cudaLaunchKernelEx(&cfg, k, Args(std::forward<Act>(a))...));
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+}
+
 // cooperative launch (all CTAs co-resident: the kernel synchronises the grid itself): as many CTAs as fit, at most `want`
 template <class... Args, class... Act>
 void launch_coop(void (*k)(Args...), int want, dim3 block, cudaStream_t st, int sms, Act &&...a)
@@ -699,7 +713,8 @@ struct Channelizer {
     size_t smem = 0;
     void (*tile_kernel)(PfbTileParams) = nullptr; PfbTileParams tp{}; size_t tile_smem = 0; bool tile_two = false;   // M = 2..32, m = 7
     bool ring_ok = false; int ring_ctas = 1; void (*ring_kernel)(PfbRingParams) = nullptr;                                                 // M = 128..1024, m = 7
-    bool stream_ok = false; int stream_ctas = 1; DevBuf perm; void (*stream_kernel)(PfbStreamParams) = nullptr;                                                                              // M = 128..1024, m = 7 (default)
+    bool stream_ok = false; int stream_ctas = 1; DevBuf perm; void (*stream_kernel)(PfbStreamParams) = nullptr;
+    void (*stream_pair)(PfbStreamParams) = nullptr;     // firpfbch2: even / odd passes as clusters of two CTAs (CSDR_OPT_PFB_VARIANT = 3: two launches)                                                                              // M = 128..1024, m = 7 (default)
     bool over2 = false; unsigned long long frames_done = 0;     // firpfbch2 analyzer: hop M/2, generic kernel
 
     void init(const Ctx &c, unsigned M_, unsigned m_, float As_, bool over2_ = false)
@@ -775,6 +790,11 @@ struct Channelizer {
             CK(cudaMemcpyAsync(perm.p, pm.data(), M * sizeof(unsigned short), cudaMemcpyHostToDevice, c.stream));
             stream_kernel = log2M == 7 ? k_pfb_stream<7> : log2M == 8 ? k_pfb_stream<8> : log2M == 9 ? k_pfb_stream<9> : k_pfb_stream<10>;
             raise_dyn_smem(stream_kernel, pfb_stream_smem((int)M));
+            stream_pair = nullptr;
+            if (over2 && g_options[CSDR_OPT_PFB_VARIANT] != 3) {
+                stream_pair = log2M == 7 ? k_pfb_stream<7, true> : log2M == 8 ? k_pfb_stream<8, true> : log2M == 9 ? k_pfb_stream<9, true> : k_pfb_stream<10, true>;
+                raise_dyn_smem(stream_pair, pfb_stream_smem((int)M));
+            }
             CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&stream_ctas, stream_kernel, (int)M, pfb_stream_smem((int)M)));
             if (stream_ctas < 1) stream_ok = false;
             c.sync();
@@ -813,6 +833,21 @@ struct Channelizer {
         // filterbank on xr + M/2 (window of frame t starts at t M/2); two passes, output columns interleaved, and the sign
         // (-1)^(c t) of the per-channel factor is constant within a pass
         const int npass = (over2 && (stream_ok || tile_kernel)) ? 2 : 1;
+        if (npass == 2 && stream_ok && stream_pair) {
+            // both passes in one launch: clusters of two CTAs (even / odd frames of a stretch) that exchange their output tiles
+            // through distributed shared memory and write whole 128-byte lines
+            PfbStreamParams sp{};
+            const int nfe = (nf + 1) / 2, nfo = nf / 2;
+            sp.xr = p.xr; sp.y = y; sp.y_stride = y_stride; sp.pw = pw; sp.pw_stride = pw_stride; sp.nf = nfe; sp.nf_odd = nfo; sp.M = (int)M; sp.log2M = log2M;
+            sp.h = hd.as<float>(); sp.tw = tw.as<float2>(); sp.perm = perm.as<unsigned short>();
+            sp.ocs = 2; sp.oco = 0; sp.over2 = 1; sp.sc_even = p.scale;
+            sp.sc_odd = (p.parity0 & 1) ? -p.scale : p.scale; sp.sc_odd1 = ((p.parity0 + 1) & 1) ? -p.scale : p.scale;
+            const int slots = std::max(1, c.sms * stream_ctas / 2);
+            int T = (nfe + slots - 1) / slots;
+            T = std::max(2 * kPfbStTF, (T + kPfbStTF - 1) / kPfbStTF * kPfbStTF);
+            sp.T = T;
+            launch_cluster(stream_pair, dim3(2 * ((nfe + T - 1) / T)), dim3(M), pfb_stream_smem((int)M), c.stream, 2u, sp);
+        } else
         for (int e = 0; e < npass; e++) {
             const int nfp = npass == 2 ? (nf - e + 1) / 2 : nf;
             if (nfp <= 0) continue;

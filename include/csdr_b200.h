@@ -53,7 +53,8 @@ enum {
     CSDR_OPT_DEBUG = 8,           /* 1: print AGC speculation diagnostics to stderr (synchronises) */
     CSDR_OPT_PFB_VARIANT = 10,    /* channelizer kernel for M = 128..1024: 0 (default) one thread per polyphase branch, window in
                                      registers; 1 the ring-buffer kernel (cross-check); 2: M = 8, 16 on the one-frame-per-thread
-                                     tile kernel instead of the two-frame one (cross-check) */
+                                     tile kernel instead of the two-frame one (cross-check); 3: firpfbch2 for M = 128..1024 as two launches
+                                     (even / odd frames) instead of clusters of two CTAs (cross-check) */
     CSDR_OPT_AM_PLL_SEQUENTIAL = 11, /* 1: ampmodem's carrier loop runs as one sequential loop per lane (cross-check); 0 (default):
                                      time segments with a pull-in window, accepted within the loop's own quantisation noise */
     CSDR_OPT_FRONTEND_VARIANT = 9 /* front-end kernel for the standard half-band plan: 1 (default) raw tile by TMA tensor copy,
