@@ -111,9 +111,11 @@ def test_dc_blocker(cs, orc):
     assert_parity(y, ref, what="dcBlocker")
 
 
-@pytest.mark.parametrize("C", [16, 20, 64, 1024])
+@pytest.mark.parametrize("C", [2, 4, 8, 12, 16, 20, 24, 32, 64, 128, 512, 1024])
 def test_firpfbch(cs, orc, C):
-    nf = 600 if C < 1024 else 96
+    """every channelizer kernel: k_pfb_tile (2, 4, 32), k_pfb_tile2 (8, 16), k_pfb_tile_any (12, 20, 24), generic k_pfb (64),
+    k_pfb_stream (128, 512, 1024)"""
+    nf = 600 if C < 128 else 96
     x = make_signal(C * nf, 15)
     ref = orc.Firpfbch(C).execute(x)
     sizes = [C * 100, C * 7, C * 300]
@@ -257,11 +259,11 @@ def test_unfused_wbfm_demodulator(cs, orc):
     assert_parity(y, ref, rel=2e-4, what="wbFMDemodulator")
 
 
-@pytest.mark.parametrize("M", [2, 16, 20, 1024])
+@pytest.mark.parametrize("M", [2, 4, 8, 12, 16, 20, 32, 64, 128, 1024])
 def test_firpfbch2_oversampled_analyzer(cs, orc, M):
     """firpfbch2_crcf (2x oversampled): coarse block call in chunks of odd and even frame counts, and
     liquid's per-frame execute, against the oracle's sequential object"""
-    nf = 45 if M >= 1024 else 400
+    nf = 45 if M >= 128 else 400
     x = make_signal(M // 2 * nf, 29)
     ref = orc.Firpfbch2(M).execute(x)
     M2 = M // 2
@@ -276,3 +278,21 @@ def test_firpfbch2_oversampled_analyzer(cs, orc, M):
     L.csdr_firpfbch2_crcf_destroy(h)
     assert_parity(fr.T, ref[:, :5], what=f"firpfbch2 M={M}, frame by frame")
     assert not L.csdr_firpfbch2_crcf_create_kaiser(0, 7, 7, 80.0) and b"even" in L.csdr_last_error()
+
+
+def test_firpfbch2_cluster_pair_matches_two_launches(cs, orc):
+    """M = 1024: the even / odd passes as clusters of two CTAs (default) and as two launches (CSDR_OPT_PFB_VARIANT = 3) give the
+    same bits, for an odd and an even number of frames per call"""
+    M, M2 = 1024, 512
+    x = make_signal(M2 * 131, 31)
+    outs = {}
+    for variant in (0, 3):
+        cs.set_option(10, variant)
+        try:
+            o = run_pipe(cs, cs.firpfbch2Channelizer(M), x, [M2 * 33, M2 * 64, M2 * 1])
+        finally:
+            cs.set_option(10, 0)
+        outs[variant] = np.stack([np.concatenate([q[c] for q in o]) for c in range(M)])
+    assert outs[0].shape == outs[3].shape
+    assert np.array_equal(outs[0], outs[3])
+    assert_parity(outs[0], orc.Firpfbch2(M).execute(x), what="firpfbch2 M=1024, cluster pair")
