@@ -438,6 +438,15 @@ __device__ __forceinline__ void fsm_step(int &mode, unsigned &timer, bool ex, un
     }
 }
 
+__device__ __forceinline__ float be_rcp(float x)
+{
+#ifdef CSDR_EMU
+    return 1.0f / x;
+#else
+    float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r;
+#endif
+}
+
 // arg(x + jy) with a degree-8 minimax polynomial for atan on [0, 1] (max error 1.1e-7 rad, float32-limited; the
 // library atan2f is ~3x the instructions).  Exact zeros keep the library's signed-zero semantics.
 // Branch-free: |a| = min / max is 0 for two zeros (the quotient is replaced, not computed), the quadrant comes from the SIGN
@@ -448,7 +457,12 @@ __device__ __forceinline__ float be_atan2(float y, float x)
 {
     const float ax = fabsf(x), ay = fabsf(y);
     const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
-    const float a = (mx == 0.f) ? 0.f : __fdividef(mn, mx);
+    // min / max by one reciprocal.  Subnormal operands are real here (the gain loop overshoots after a stretch of digital
+    // silence and the products of two tiny outputs underflow), so both are lifted by 2^24 when the larger one is subnormal;
+    // the clamp then keeps two exact zeros at 0 * rcp(FLT_MIN) = 0, the quotient the signed-zero cases need, without a
+    // select of its own (7 instructions; the library division with its zero guard: 9).
+    const float lift = (mx < 1.17549435e-38f) ? 16777216.f : 1.f;
+    const float a = (mn * lift) * be_rcp(fmaxf(mx * lift, 1.17549435e-38f));
     const float s = a * a;
     float r = 0.0028340641874819994f;
     r = fmaf(r, s, -0.016005029901862144f);
@@ -625,6 +639,15 @@ constexpr size_t kAgcSmem = sizeof(float) * kAgcT * kAgcRow + sizeof(float2) * k
 
 // per-thread state of the emission: previous ungated output and the bit words of the current block
 struct AgcEmitState { float2 yp; unsigned ex, sr, si; };
+// (w << 1) | sign bit of v
+__device__ __forceinline__ unsigned be_shift_in_sign(unsigned w, float v)
+{
+#ifdef CSDR_EMU
+    return (w << 1) | ((unsigned)__float_as_int(v) >> 31);
+#else
+    return __funnelshift_l((unsigned)__float_as_int(v), w, 1);
+#endif
+}
 
 // samples [K0, K0 + NK) of the current block of this thread's row: gain loop and demodulation in one register-resident
 // loop (the demodulation's independent instructions fill the latency of the gain recurrence)
@@ -642,8 +665,10 @@ __device__ __forceinline__ void agc_emit_run(const AgcCoef &co, float g_thr, flo
             const float re = __fadd_rn(__fmul_rn(e.yp.x, y.x), __fmul_rn(e.yp.y, y.y));
             const float im = __fsub_rn(__fmul_rn(e.yp.x, y.y), __fmul_rn(e.yp.y, y.x));
             myrow[1 + k] = (EXACT ? atan2f(im, re) : be_atan2(im, re)) * fm_ref;
-            e.sr |= ((unsigned)__float_as_int(y.x) >> 31) << k;
-            e.si |= ((unsigned)__float_as_int(y.y) >> 31) << k;
+            // (one funnel shift per plane: the sign enters at bit 0, sample k of the block ends up at bit 31 - k; the word is
+            // reversed once when it is stored)
+            e.sr = be_shift_in_sign(e.sr, y.x);
+            e.si = be_shift_in_sign(e.si, y.y);
         } else {
             myx[k] = y;
         }
@@ -705,10 +730,11 @@ __global__ void __launch_bounds__(kAgcT, 4) k_agc_emit(const BackendParams p)
     const bool interior = (seg0 * L - p.W >= 0) && ((seg0 + kAgcT) * L <= n);
     const bool full_rows = (seg0 + kAgcT) * L <= n;            // every row of every emitted block is complete
     auto fetch = [&](int s) {
-        const float *q = pw + ubase + s * kAgcB;
         if (interior) {
+            // (32-bit element offsets from one base pointer: one wide multiply-add per load)
+            int off = ubase + s * kAgcB;
 #pragma unroll
-            for (int i = 0; i < 32; i++) nxt[i] = __ldg(q + i * L);
+            for (int i = 0; i < 32; i++, off += L) nxt[i] = __ldg(pw + off);
         } else {
 #pragma unroll
             for (int i = 0; i < 32; i++) {
@@ -808,7 +834,8 @@ __global__ void __launch_bounds__(kAgcT, 4) k_agc_emit(const BackendParams p)
             if (cnt > 0) {
                 const int wd = (b0 + (s - wsteps) * kAgcB) >> 5;
                 exb[wd] = es.ex;
-                if (FM) { sgr[wd] = es.sr; sgi[wd] = es.si; }
+                // full blocks collected the sign bits most recent sample first (agc_emit_run), ragged ones in place
+                if (FM) { sgr[wd] = cnt == kAgcB ? __brev(es.sr) : es.sr; sgi[wd] = cnt == kAgcB ? __brev(es.si) : es.si; }
                 if (u0 + cnt >= min(b0 + L, n)) p.seg_ylast[(long long)lane * p.nseg + seg] = es.yp;     // the segment's last sample
             }
             myrow[0] = __uint_as_float(cnt > 0 ? es.ex : 0u);

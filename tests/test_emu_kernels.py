@@ -96,7 +96,10 @@ def test_backend_matches_oracle(orc, emu, kw):
 
 def test_backend_speculation_misses_are_repaired(orc, emu):
     """a stream that sits in exact digital silence freezes the AGC gain, which no warm-up can guess: the
-    verify/fix-up pass must re-run those segments and still match the sequential loop."""
+    verify/fix-up pass must re-run those segments and still match the sequential loop.  When the weak signal resumes the
+    gain sits at its 1e6 clamp and overshoots: for a few dozen samples the products conj(y[n-1]) y[n] are SUBNORMAL, and
+    the discriminator's quotient has to stay exact there (be_atan2 lifts both operands before the fast reciprocal).  Only
+    this harness reaches that case: every chain of the product has a dc blocker in front, which leaves no exact zeros."""
     n = 12000
     x = np.zeros(n, np.complex64)
     x[:3000] = 0.2 * np.exp(2j * np.pi * 0.07 * np.arange(3000))
