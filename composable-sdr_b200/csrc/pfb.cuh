@@ -636,27 +636,38 @@ inline void pfb_stream_perm(int M, unsigned short *perm)
     }
 }
 
-// one radix-4 DIF pass over blocks of N (compile time) and every shorter one behind it, down to N = 16
-template <int N, int M>
-__device__ __forceinline__ void pfb_stream_passes(float2 *wf, const float2 *tp, int bq)
+// The radix-4 DIF passes over blocks of N (compile time) = M, M/4, ..., 16 with the thread's element and twiddle offsets computed
+// ONCE (they depend on the thread, not on the frame; in the 16-point pass 16 consecutive butterflies take the same j of 16
+// consecutive blocks: on the padded layout their elements are 17 apart -- 16 different banks -- and they share their twiddles): po[I] = padded offset of the butterfly's first element in pass I, to[I] = offset of its first twiddle.  The other
+// three elements are at compile-time distances -- k Q + k Q / 16 on the padded layout (Q a multiple of 16; for Q = 4 the four
+// elements share one group of 16) -- so the loads and stores of a pass are one register plus immediates.
+template <int N, int M, int I = 0>
+__device__ __forceinline__ void pfb_stream_pre(int bq, int tw0, int (&po)[5], int (&to)[5])
 {
     if constexpr (N > 4) {
         constexpr int Q = N >> 2;
         int j = bq & (Q - 1), base = (bq / Q) * N + j;
-        if constexpr (N == 16 && M >= 256) {
-            // 16 consecutive butterflies take the same j of 16 consecutive blocks: on the padded layout their elements are 17
-            // apart (16 different banks) and they share their twiddles; j-fastest order would put four of them on one bank
-            j = (bq >> 4) & 3;
-            base = (((bq & 15) | ((bq >> 6) << 4)) << 4) + j;
-        }
+        if constexpr (N == 16 && M >= 256) { j = (bq >> 4) & 3; base = (((bq & 15) | ((bq >> 6) << 4)) << 4) + j; }
+        po[I] = base + (base >> 4);
+        to[I] = tw0 + j;
+        pfb_stream_pre<(N >> 2), M, I + 1>(bq, tw0 + 3 * Q, po, to);
+    }
+}
+template <int N, int M, int I = 0>
+__device__ __forceinline__ void pfb_stream_passes_pre(float2 *wf, const float2 *stw, const int (&po)[5], const int (&to)[5])
+{
+    if constexpr (N > 4) {
+        constexpr int Q = N >> 2, D = Q >= 16 ? Q + Q / 16 : Q;      // padded distance of the butterfly's elements
+        float2 *e = wf + po[I];
+        const float2 *tp = stw + to[I];
         float2 x[4];
 #pragma unroll
-        for (int k = 0; k < 4; k++) { const int i = base + k * Q; x[k] = wf[i + (i >> 4)]; }
-        pfb_dif4(x, tp[j], tp[Q + j], tp[2 * Q + j]);
+        for (int k = 0; k < 4; k++) x[k] = e[k * D];
+        pfb_dif4(x, tp[0], tp[Q], tp[2 * Q]);
 #pragma unroll
-        for (int k = 0; k < 4; k++) { const int i = base + k * Q; wf[i + (i >> 4)] = x[k]; }
+        for (int k = 0; k < 4; k++) e[k * D] = x[k];
         __syncthreads();
-        pfb_stream_passes<(N >> 2), M>(wf, tp + 3 * Q, bq);
+        pfb_stream_passes_pre<(N >> 2), M, I + 1>(wf, stw, po, to);
     }
 }
 
@@ -716,6 +727,8 @@ __global__ void __launch_bounds__(1 << LM, 1) k_pfb_stream(const PfbStreamParams
     constexpr int QB = M >> 2;                                      // butterflies per frame and radix-4 pass
     const int fi = n / QB, bq = n - fi * QB;                        // this thread's frame and butterfly in the radix-4 passes
     float2 *wf = work + fi * WP;
+    int po[5], to[5];                                               // per-pass element / twiddle offsets of this thread
+    if constexpr (lm & 1) pfb_stream_pre<(M >> 1), M>(bq, M >> 1, po, to); else pfb_stream_pre<M, M>(bq, 0, po, to);
     __syncthreads();
     for (int t = t0; t < t1c; t += FI) {
         // ---- polyphase filter: four frames from registers
@@ -748,9 +761,9 @@ __global__ void __launch_bounds__(1 << LM, 1) k_pfb_stream(const PfbStreamParams
                 wr[i1 + (i1 >> 4)] = pfb_cmul(cf(a.x - c.x, a.y - c.y), stw[b]);
             }
             __syncthreads();
-            pfb_stream_passes<(M >> 1), M>(wf, stw + (M >> 1), bq);
+            pfb_stream_passes_pre<(M >> 1), M>(wf, stw, po, to);
         } else {
-            pfb_stream_passes<M, M>(wf, stw, bq);
+            pfb_stream_passes_pre<M, M>(wf, stw, po, to);
         }
         {
             // last pass (N = 4, no twiddles): results go into the transposed output tile
