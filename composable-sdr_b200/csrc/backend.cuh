@@ -275,12 +275,14 @@ __global__ void __launch_bounds__(32 * kDcWarps, kDcMinB) k_dc_scan(const DcPara
         tk_next = next_ticket();
         scan_block(tk, v, er, ei, sr[0], si[0]);
     }
-    while (tk < total) {
+    float2 vn[GW][S];
+    float ern[GW], ein[GW];
+    // one iteration of the pipeline: (v, er, ei) = current block, (vn, ern, ein) = where the next block goes.  Called with
+    // the two register sets alternating, so the next block becomes the current one without a copy.
+    auto iteration = [&](float2 (&v)[GW][S], float (&er)[GW], float (&ei)[GW], float2 (&vn)[GW][S], float (&ern)[GW], float (&ein)[GW]) {
         const int lane = tk / p.nblk, b = tk - lane * p.nblk;
         const bool bulk = block_bulk(tk);
         // ---- steps 0-1 of the next block
-        float2 vn[GW][S];
-        float ern[GW], ein[GW];
         int tk_next2 = total;
         if (tk_next < total) {
             load_block(tk_next, vn);
@@ -378,14 +380,12 @@ __global__ void __launch_bounds__(32 * kDcWarps, kDcMinB) k_dc_scan(const DcPara
             }
         }
         __syncthreads();      // s_red / s_cr and this block's half of sr / si are reused
-        // the next block becomes the current one
-#pragma unroll
-        for (int k = 0; k < GW; k++) {
-            er[k] = ern[k]; ei[k] = ein[k];
-#pragma unroll
-            for (int q = 0; q < S; q++) v[k][q] = vn[k][q];
-        }
         tk = tk_next; tk_next = tk_next2; cb ^= 1;
+    };
+    while (tk < total) {
+        iteration(v, er, ei, vn, ern, ein);
+        if (tk >= total) break;
+        iteration(vn, ern, ein, v, er, ei);
     }
     // tickets for the next launch: reset by the last CTA to leave
     if (t == 0) {
