@@ -60,3 +60,37 @@ def test_add_pipe_and_distribute():
     folds = [cs.addPipe(counting_pipe(log, f"d{i}", lambda a: a), cs.listSink()) for i in range(2)]
     res = cs.distribute_(folds).run(iter([[np.ones(2), np.zeros(3)], [np.ones(1), np.zeros(1)]]))
     assert [len(r) for r in res] == [3, 4]
+
+
+def test_reference_side_patch_script(tmp_path):
+    """integration/apply_gpu_blocks.py on a miniature stand-in for a checkout: the cabal link line and the two
+    wrapper bodies are replaced, everything around them is kept, a missing anchor is refused"""
+    import os
+    import subprocess
+    import sys
+    root = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+    script = os.path.join(root, "integration", "apply_gpu_blocks.py")
+    co = tmp_path / "co"
+    (co / "src" / "ComposableSDR").mkdir(parents=True)
+    (co / "composable-sdr.cabal").write_text("library\n  extra-lib-dirs:      /usr/local/lib\n  extra-libraries:     SoapySDR, liquid\n  other: kept\n")
+    chs = ('before\nforeign import ccall unsafe "agc_crcf_destroy" c_agc_crcf_destroy\n  :: Agc -> IO ()\n\n'
+           'agcExecuteBlock ::\n     sig\nagcExecuteBlock agc px n py = do\n  OLD AGC BODY\n\nagcCreate :: Float -> IO Agc\nmiddle\n'
+           'firpfbchCreate :: Int -> IO x\ncreate body\n\nfirpfbchChan ::\n  sig\nfirpfbchChan (fb, nco, nch) a = do\n  OLD PFB BODY\n\n'
+           'firpfbchChannelizer ::\n  after\n')
+    (co / "src" / "ComposableSDR" / "Liquid.chs").write_text(chs)
+    out = subprocess.run([sys.executable, script, str(co), "--lib-dir", "/opt/x"], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    cab = (co / "composable-sdr.cabal").read_text()
+    assert "SoapySDR, csdr_liquid_compat, csdr_b200, liquid" in cab and "/usr/local/lib, /opt/x" in cab and "other: kept" in cab
+    new = (co / "src" / "ComposableSDR" / "Liquid.chs").read_text()
+    assert "OLD AGC BODY" not in new and "OLD PFB BODY" not in new
+    assert "c_csdr_agc_squelch_execute_block agc px n py" in new and "c_csdr_firpfbch_execute_block fb nco x" in new
+    for kept in ("before", "middle", "create body", "  after", "agcCreate :: Float -> IO Agc", "firpfbchChannelizer ::"):
+        assert kept in new
+    assert out.stdout.startswith("--- a/composable-sdr.cabal")
+    # a tree without the anchors is refused and left alone
+    (co / "src" / "ComposableSDR" / "Liquid.chs").write_text("nothing to see\n")
+    (co / "composable-sdr.cabal").write_text("library\n  extra-lib-dirs:      /usr/local/lib\n  extra-libraries:     SoapySDR, liquid\n")
+    bad = subprocess.run([sys.executable, script, str(co)], capture_output=True, text=True)
+    assert bad.returncode != 0 and "anchor not found" in bad.stderr
+    assert (co / "src" / "ComposableSDR" / "Liquid.chs").read_text() == "nothing to see\n"
