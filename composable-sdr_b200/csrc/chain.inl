@@ -506,7 +506,6 @@ int csdr_chain_seek(csdr_chain q, uint64_t n_prior)
 {
     REQUIRE(q, TAG_CHAIN, -1);
     API_BEGIN
-    if (q->has_wb) throw CudaError{"chain: seek with DeWBFM is not implemented"};
     q->ctx.use();
     // samples behind the resampler that precede the new position (closed form: fe_seek)
     unsigned long long o_prior = n_prior;
@@ -533,6 +532,16 @@ int csdr_chain_seek(csdr_chain q, uint64_t n_prior)
         for (auto &b : q->ch.xr) if (b.p) CK(cudaMemsetAsync(b.p, 0, q->ch.hist_samples() * sizeof(float2), q->ctx.stream));
         q->ctx.sync();
     }
+    if (q->has_wb) {
+        // wide-band FM tail: the output decimator consumes whole blocks of `decim` demodulated samples on the stream's own grid,
+        // so the samples of the block the new position falls into count as pending (zeros; they belong to the warm-up, like
+        // the de-emphasis filter's and the decimator's empty histories: 2 decim m + 1 taps, m = 10)
+        const unsigned long long idx = q->C > 1 ? o_prior / q->hop : o_prior;       // demodulated samples per lane in front
+        q->wb.dec.fill = (size_t)(idx % q->wb.dec.M);
+        CK(cudaMemsetAsync(q->wb.dec.hist.p, 0, q->wb.dec.hist.cap, q->ctx.stream));
+        CK(cudaMemsetAsync(q->wb.deemph.state.p, 0, q->wb.deemph.state.cap, q->ctx.stream));
+        q->ctx.sync();
+    }
     return 0;
     API_END(-1)
 }
@@ -545,6 +554,7 @@ size_t csdr_chain_warmup_len(csdr_chain q)
     double r = q->has_resamp ? (double)q->fe.ms.rate : 1.0;
     double post = 45000.0;
     if (q->C > 1) post += (double)q->hop * (28.0 + 512.0 + (double)q->be.agc_timeout + 8.0);
+    if (q->has_wb) post += (double)q->hop * (2.0 * 10.0 * (double)q->wb.dec.M + 64.0);   // decimator taps + de-emphasis settling, per lane
     size_t w = (size_t)(q->has_resamp ? q->fe.geo.hcap : 0) + (size_t)std::ceil(post / r);
     return w;
 }

@@ -251,7 +251,8 @@ int      csdr_chain_run_file(csdr_chain q, const char *in_path, const char *out_
  * and the frame grid are closed-form in the sample index).  The caller feeds csdr_chain_warmup_len() samples of real
  * history first and discards the outputs they produce.  With a channelizer the shard should start on a frame boundary
  * of the stream (resampler output index = 0 mod C; 0 mod C/2 for the firpfbch2 channelizer, whose frame parity follows the
- * absolute frame index), so that every frame is produced by exactly one shard.  Not implemented for DeWBFM. */
+ * absolute frame index), so that every frame is produced by exactly one shard.  DeWBFM: the output decimator's block grid
+ * follows the absolute index of the demodulated samples as well. */
 int      csdr_chain_seek(csdr_chain q, uint64_t n_prior);
 size_t   csdr_chain_warmup_len(csdr_chain q);
 /* the CUDA stream (cudaStream_t) the chain launches on, for event timing by the caller */

@@ -343,6 +343,26 @@ def test_channelizer_time_segment_sharding(cs, orc):
     assert snr_db(y[512:], refm[512:]) >= 60.0
 
 
+def test_wbfm_time_segment_sharding(cs, orc):
+    """DeWBFM shards by time segments too: the output decimator's block grid follows the absolute index of the demodulated
+    samples, so a shard that starts anywhere continues the single-stream output (decim 4 and 5: 5 does not divide the
+    resampler's output count at the shard start)"""
+    from composable_sdr_b200 import shard
+    x = cs.synth.config2(3 << 20, keyed=None)
+    for decim in (4, 5):
+        mk = lambda: cs.Chain(2.56e6, 1e5, 200e3, cs.DeWBFM(decim), agc=-40.0)
+        ref = mk().process(x)[0]
+        start = (2 << 20) + 12345
+        pre = mk()
+        n_before = len(pre.process(x[:start])[0])
+        sh = mk()
+        warm = shard.seek_shard(sh, start, lambda i, j: x[i:j])
+        assert 0 < warm < start
+        y = sh.process(x[start:])[0]
+        assert len(y) == len(ref) - n_before
+        assert_parity(y, ref[n_before:], rel=REL_TOL_AFTER_DCBLOCK, what=f"DeWBFM {decim} time-segment shard")
+
+
 def test_firpfbch2_time_segment_sharding(cs, orc):
     """the channelizer the task names (firpfbch2_crcf, frames of C/2 samples) shards by time segments as well: the frame
     grid and the sign (-1)^(c t) of its per-channel factor follow the absolute position, for a shard that starts on an
