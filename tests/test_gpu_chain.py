@@ -103,6 +103,27 @@ def test_config3_raw_channels_and_mix(cs, orc):
     assert_parity(m, refm, rel=REL_TOL_FM_NOISE, what="config 3 --mix")
 
 
+def test_mix_variants_sum_the_right_buffers(cs, orc):
+    """--mix (Trans.hs:119-122) behind every kind of summand: gated cf32 (AGC, DeNo: the gate-aware sum over sample pairs),
+    ungated cf32 (no AGC: the plain sum), and -- once -- the plain sum forced for the gated discriminator case must equal
+    the gate-aware one bit for bit except for the sign of a zero"""
+    x = cs.synth.config3(1 << 18)
+    refc = orc.Chain(2.56e6, 0.0, 0.0, orc.DEMOD_NO, 0.0, -40.0, 16, True).process(x)[0]
+    yc = run_chain(cs.Chain(2.56e6, agc=-40.0, channels=16, mix_channels=True), x, [100000, 33])[0]
+    assert len(yc) == len(refc)
+    assert_parity(yc[64:], refc[64:], what="--mix of gated cf32 channels")
+    refn = orc.Chain(2.56e6, 0.0, 0.0, orc.DEMOD_NO, 0.0, 0.0, 16, True).process(x)[0]
+    yn = run_chain(cs.Chain(2.56e6, channels=16, mix_channels=True), x, [100000, 33])[0]
+    assert_parity(yn, refn, what="--mix of raw channels")
+    # the sum of the individually produced channels (no --mix) equals the chain's own --mix output
+    chans = run_chain(cs.Chain(2.56e6, demod=cs.DeNBFM(0.3), agc=-40.0, channels=16), x, [100000, 33])
+    fold = chans[0].copy()
+    for c in range(1, 16):
+        fold = (fold + chans[c]).astype(np.float32)
+    ym = run_chain(cs.Chain(2.56e6, demod=cs.DeNBFM(0.3), agc=-40.0, channels=16, mix_channels=True), x, [100000, 33])[0]
+    assert np.array_equal(fold, ym)
+
+
 def _gate_report(y, ref):
     """(number of samples whose squelch gate differs, mask of samples whose gate agrees)"""
     gy, gr = (np.asarray(y) != 0), (np.asarray(ref) != 0)
