@@ -429,12 +429,12 @@ struct Backend {
     DevBuf ydc, pwbuf, g_first, y_first, y_end, seg_ylast, barrier;
     int pw_ready_n = -1;       // the producer of the input has already written its power for a call of this many samples
     int FW = 3; unsigned long long last_refined = 0; int last_L = 0, last_W = 0, last_nwords = 0;
-    // self-tuning warm-up: the counters of every call are copied to pinned memory asynchronously; the next call looks
-    // at them (no synchronisation) and lengthens / shortens the warm-up
-    // self-tuning warm-up, deterministic: the counters of every call are copied to one of two pinned slots; call k waits for
-    // the copy of call k-2 (one call always stays in flight) and lengthens / shortens the warm-up from it
-    unsigned long long *h_counters = nullptr; cudaEvent_t ev_counters[2] = {nullptr, nullptr}; unsigned long long calls = 0;
-    unsigned long long seen[3] = {0, 0, 0}; int W_cur = 0, calm_calls = 0; long long nseg_of[2] = {1, 1};
+    // self-tuning warm-up, deterministic: the counters of every call are copied to one of kLag pinned slots; call k waits for
+    // the copy of call k - kLag (up to kLag - 1 calls stay in flight, so the wait is normally over before it starts) and
+    // lengthens / shortens the warm-up from it
+    static constexpr int kLag = 4;        // the warm-up plan of call k follows the counters of call k - kLag
+    unsigned long long *h_counters = nullptr; cudaEvent_t ev_counters[kLag] = {}; unsigned long long calls = 0;
+    unsigned long long seen[3] = {0, 0, 0}; int W_cur = 0, calm_calls = 0; long long nseg_of[kLag] = {1, 1, 1, 1};
     int sms = 148, dc_cur = 0, dc_depth = 1; unsigned dc_epoch = 0;
     ~Backend() { if (h_counters) cudaFreeHost(h_counters); for (auto e : ev_counters) if (e) cudaEventDestroy(e); }
 
@@ -598,15 +598,16 @@ struct Backend {
         int L = this->L;
         if (has_agc && !fixed_L) L = pick_segment(n, this->W_cur > 0 ? this->W_cur : this->W);
         int W = this->W;
-        const int slot = (int)(calls & 1);
+        const int slot = (int)(calls % kLag);
         if (has_agc && !fixed_L) {
             if (!h_counters) {
-                CK(cudaHostAlloc((void **)&h_counters, 2 * 3 * sizeof(unsigned long long), cudaHostAllocDefault));
-                for (auto &e : ev_counters) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming | cudaEventBlockingSync));
+                CK(cudaHostAlloc((void **)&h_counters, kLag * 3 * sizeof(unsigned long long), cudaHostAllocDefault));
+                // (spinning wait: a blocking one costs an interrupt wake-up per call, ~1 ms on a box with eight busy ranks)
+                for (auto &e : ev_counters) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
                 W_cur = this->W;
             }
-            if (calls >= 2) {
-                CK(cudaEventSynchronize(ev_counters[slot]));           // counters as they stood after call k-2
+            if (calls >= (unsigned long long)kLag) {
+                CK(cudaEventSynchronize(ev_counters[slot]));           // counters as they stood after call k - kLag
                 const unsigned long long *hc = h_counters + 3 * slot;
                 const unsigned long long seq = hc[0] - seen[0], refined = hc[2] - seen[2];
                 seen[0] = hc[0]; seen[1] = hc[1]; seen[2] = hc[2];
